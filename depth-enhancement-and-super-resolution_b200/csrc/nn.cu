@@ -1,0 +1,438 @@
+// Layout, padding, activation, normalisation and optimizer kernels (HBM-bound, NHWC fp32).
+// Reference call sites: models/networks.py:30 (InstanceNorm2d affine=False), :378-415 (ReflectionPad2d,
+// ReLU, Tanh), :546-557 (LeakyReLU 0.2 / ReLU), :629 (skip concat); models/translation_network.py:46
+// (GroupNorm(8, C, affine=True)), :472-478 (replicate padding); models/main_model.py:176 (Adam).
+#include "common.cuh"
+#include "../../include/dsr_b200.h"
+
+#define TPB 256
+#define ST(s) ((cudaStream_t)(s))
+
+// ------------------------------------------------------------------------------------------
+// NCHW <-> NHWC  (x: [N][C][P]  <->  y: [N][P][C]); 32x32 smem tile transpose
+// ------------------------------------------------------------------------------------------
+__global__ void transpose_cp_kernel(const float* __restrict__ x, float* __restrict__ y, int C, long P, int to_nhwc) {
+    __shared__ float tile[32][33];
+    int n = blockIdx.z;
+    long p0 = (long)blockIdx.x * 32;
+    int c0 = blockIdx.y * 32;
+    const float* xs = x + (long)n * C * P;
+    float* ys = y + (long)n * C * P;
+    if (to_nhwc) {  // read [c][p] coalesced along p, write [p][c] coalesced along c
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int c = c0 + r; long p = p0 + threadIdx.x;
+            tile[r][threadIdx.x] = (c < C && p < P) ? xs[(long)c * P + p] : 0.f;
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            long p = p0 + r; int c = c0 + threadIdx.x;
+            if (p < P && c < C) ys[p * C + c] = tile[threadIdx.x][r];
+        }
+    } else {        // read [p][c] coalesced along c, write [c][p] coalesced along p
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            long p = p0 + r; int c = c0 + threadIdx.x;
+            tile[r][threadIdx.x] = (p < P && c < C) ? xs[p * C + c] : 0.f;
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int c = c0 + r; long p = p0 + threadIdx.x;
+            if (c < C && p < P) ys[(long)c * P + p] = tile[threadIdx.x][r];
+        }
+    }
+}
+
+// strided channel-block copy: dst[p][doff + c] (=|+=) src[p][soff + c], c < nC   (concat / slice)
+__global__ void copy_channels_kernel(const float* __restrict__ src, int srcC, int soff, float* __restrict__ dst,
+                                     int dstC, int doff, int nC, long npix, int accumulate) {
+    long total = npix * nC;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long p = idx / nC; int c = (int)(idx - p * nC);
+        float v = src[p * srcC + soff + c];
+        float* d = dst + p * dstC + doff + c;
+        if (accumulate) *d += v; else *d = v;
+    }
+}
+__global__ void copy_channels_vec4_kernel(const float4* __restrict__ src, int srcC4, int soff4, float4* __restrict__ dst,
+                                          int dstC4, int doff4, int nC4, long npix) {
+    long total = npix * nC4;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long p = idx / nC4; int c = (int)(idx - p * nC4);
+        dst[p * dstC4 + doff4 + c] = src[p * srcC4 + soff4 + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// padding (zero / reflect / replicate), NHWC
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pad_src(int q, int p, int n, int mode) {  // padded index -> source index or -1
+    int i = q - p;
+    if (i >= 0 && i < n) return i;
+    if (mode == DSR_PAD_ZERO) return -1;
+    if (mode == DSR_PAD_REFLECT) return i < 0 ? -i : 2 * (n - 1) - i;
+    return i < 0 ? 0 : n - 1;  // replicate
+}
+__global__ void pad2d_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C,
+                                 int p, int mode) {
+    int Hp = H + 2 * p, Wp = W + 2 * p;
+    long total = (long)N * Hp * Wp * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C); long t = idx / C;
+        int qw = (int)(t % Wp); t /= Wp;
+        int qh = (int)(t % Hp); int n = (int)(t / Hp);
+        int i = pad_src(qh, p, H, mode), j = pad_src(qw, p, W, mode);
+        y[idx] = (i < 0 || j < 0) ? 0.f : x[(((long)n * H + i) * W + j) * C + c];
+    }
+}
+// list of padded indices that read source index i
+__device__ __forceinline__ int pad_readers(int i, int p, int n, int mode, int* qs) {
+    int k = 0;
+    qs[k++] = i + p;
+    if (mode == DSR_PAD_REFLECT) {
+        if (i >= 1 && i <= p) qs[k++] = p - i;
+        if (i <= n - 2 && i >= n - 1 - p) qs[k++] = 2 * (n - 1) - i + p;
+    } else if (mode == DSR_PAD_REPLICATE) {
+        if (i == 0) for (int q = 0; q < p; ++q) qs[k++] = q;
+        if (i == n - 1) for (int q = n + p; q < n + 2 * p; ++q) qs[k++] = q;
+    }
+    return k;
+}
+__global__ void pad2d_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int N, int H, int W, int C,
+                                 int p, int mode) {
+    int Hp = H + 2 * p, Wp = W + 2 * p;
+    long total = (long)N * H * W * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C); long t = idx / C;
+        int j = (int)(t % W); t /= W;
+        int i = (int)(t % H); int n = (int)(t / H);
+        int qh[16], qw[16];
+        int nh = pad_readers(i, p, H, mode, qh), nw = pad_readers(j, p, W, mode, qw);
+        float acc = 0.f;
+        for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b) acc += gy[(((long)n * Hp + qh[a]) * Wp + qw[b]) * C + c];
+        gx[idx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// activations
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float x, int kind, float slope) {
+    if (kind == DSR_ACT_RELU) return x > 0.f ? x : 0.f;
+    if (kind == DSR_ACT_LRELU) return x > 0.f ? x : slope * x;
+    if (kind == DSR_ACT_TANH) return tanhf(x);
+    return x;
+}
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n, int kind, float slope) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = act_apply(x[i], kind, slope);
+}
+// ref = x for relu / lrelu, = y for tanh
+__global__ void act_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ gy, float* __restrict__ gx,
+                               long n, int kind, float slope) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float r = ref[i], g = gy[i];
+        float d = 1.f;
+        if (kind == DSR_ACT_RELU) d = r > 0.f ? 1.f : 0.f;
+        else if (kind == DSR_ACT_LRELU) d = r > 0.f ? 1.f : slope;
+        else if (kind == DSR_ACT_TANH) d = 1.f - r * r;
+        gx[i] = g * d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-(n, c) sums over the pixels of an NHWC tensor:
+//   mode 0: sums[n][c] = (sum x, sum x^2)                         (norm statistics, bias gradient)
+//   mode 1: sums[n][c] = (sum dy', sum dy' * xhat), dy' = dy * 1[xhat > 0 if relu]   (IN backward)
+// blockDim = 256; lanes run along channels (coalesced), the rest of the block along pixels.
+// ------------------------------------------------------------------------------------------
+__global__ void channel_sums_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                    const float* __restrict__ prm, int N, long P, int C, long chunk, int mode,
+                                    int act, double* __restrict__ sums) {
+    __shared__ double sh[2][TPB];
+    int n = blockIdx.y;
+    int Cw = 1;
+    while (Cw < C && Cw < TPB) Cw <<= 1;
+    int rows = TPB / Cw;
+    int tx = threadIdx.x % Cw, ty = threadIdx.x / Cw;
+    long p_begin = (long)blockIdx.x * chunk, p_end = p_begin + chunk;
+    if (p_end > P) p_end = P;
+    const float* xs = x + (long)n * P * C;
+    const float* ds = dy ? dy + (long)n * P * C : nullptr;
+    long NC = (long)N * C;
+    for (int c0 = 0; c0 < C; c0 += Cw) {
+        int c = c0 + tx;
+        double a = 0.0, b = 0.0;
+        if (c < C) {
+            float mean = 0.f, scale = 1.f;
+            if (mode == 1) { mean = prm[(long)n * C + c]; scale = prm[NC + (long)n * C + c]; }
+            for (long p = p_begin + ty; p < p_end; p += rows) {
+                float v = xs[p * C + c];
+                if (mode == 0) { a += (double)v; b += (double)v * (double)v; }
+                else {
+                    float xh = (v - mean) * scale;
+                    float g = ds[p * C + c];
+                    if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
+                    a += (double)g; b += (double)(g * xh);
+                }
+            }
+        }
+        sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+        __syncthreads();
+        if (ty == 0 && c < C) {
+            for (int r = 1; r < rows; ++r) { a += sh[0][r * Cw + tx]; b += sh[1][r * Cw + tx]; }
+            atomicAdd(&sums[((long)n * C + c) * 2], a);
+            atomicAdd(&sums[((long)n * C + c) * 2 + 1], b);
+        }
+        __syncthreads();
+    }
+}
+
+// sums -> per-(n,c) (mean, scale, shift):  y = (x - mean) * scale + shift
+//   groups == 0: instance norm (biased variance over P), scale = rstd, shift = 0
+//   groups  > 0: group norm over (P x C/groups), scale = rstd_g * gamma_c, shift = beta_c
+__global__ void norm_finalize_kernel(const double* __restrict__ sums, int N, int C, long P, int groups,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     float* __restrict__ prm) {
+    long NC = (long)N * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < NC; idx += (long)gridDim.x * blockDim.x) {
+        int n = (int)(idx / C), c = (int)(idx % C);
+        double s = 0, q = 0, cnt;
+        if (groups == 0) { s = sums[idx * 2]; q = sums[idx * 2 + 1]; cnt = (double)P; }
+        else {
+            int cg = C / groups, g0 = (c / cg) * cg;
+            for (int k = 0; k < cg; ++k) { s += sums[((long)n * C + g0 + k) * 2]; q += sums[((long)n * C + g0 + k) * 2 + 1]; }
+            cnt = (double)P * cg;
+        }
+        double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0) var = 0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        prm[idx] = (float)mean;
+        prm[NC + idx] = groups == 0 ? rstd : rstd * (gamma ? gamma[c] : 1.f);
+        prm[2 * NC + idx] = groups == 0 ? 0.f : (beta ? beta[c] : 0.f);
+    }
+}
+
+// y = act((x - mean) * scale + shift) (+ residual)
+__global__ void norm_apply_fwd_kernel(const float* __restrict__ x, const float* __restrict__ prm,
+                                      const float* __restrict__ res, float* __restrict__ y, int N, long P, int C,
+                                      int act) {
+    long NC = (long)N * C, total = (long)N * P * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C);
+        int n = (int)(idx / (P * C));
+        long k = (long)n * C + c;
+        float v = (x[idx] - prm[k]) * prm[NC + k] + prm[2 * NC + k];
+        if (act == DSR_ACT_RELU) v = v > 0.f ? v : 0.f;
+        if (res) v += res[idx];
+        y[idx] = v;
+    }
+}
+// instance-norm backward: dx = rstd * (dy' - mean(dy') - xhat * mean(dy' * xhat))
+__global__ void in_apply_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                    const float* __restrict__ prm, const double* __restrict__ sums2,
+                                    float* __restrict__ dx, int N, long P, int C, int act) {
+    long NC = (long)N * C, total = (long)N * P * C;
+    float invP = 1.f / (float)P;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C);
+        int n = (int)(idx / (P * C));
+        long k = (long)n * C + c;
+        float rstd = prm[NC + k];
+        float xh = (x[idx] - prm[k]) * rstd;
+        float g = dy[idx];
+        if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
+        float m1 = (float)sums2[k * 2] * invP, m2 = (float)sums2[k * 2 + 1] * invP;
+        dx[idx] = rstd * (g - m1 - xh * m2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weights: 4-D parameter [D0][D1][R][S] <-> packed GEMM operand [(r*S+s)*Ck + ck][Co]
+//   kdim == 1: ck indexes D1, co indexes D0 (Conv2d forward, ConvTranspose2d dgrad)
+//   kdim == 0: ck indexes D0, co indexes D1 (Conv2d dgrad, ConvTranspose2d forward)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S, int kdim,
+                                   float* __restrict__ out) {
+    long total = (long)D0 * D1 * R * S;
+    int Ck = kdim ? D1 : D0, Co = kdim ? D0 : D1;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int co = (int)(idx % Co); long t = idx / Co;
+        int ck = (int)(t % Ck); int tap = (int)(t / Ck);
+        int d0 = kdim ? co : ck, d1 = kdim ? ck : co;
+        out[idx] = w[((long)d0 * D1 + d1) * R * S + tap];
+    }
+}
+__global__ void unpack_weight_kernel(const float* __restrict__ packed, int D0, int D1, int R, int S, int kdim,
+                                     float* __restrict__ w, int accumulate) {
+    long total = (long)D0 * D1 * R * S;
+    int Ck = kdim ? D1 : D0, Co = kdim ? D0 : D1;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int tap = (int)(idx % (R * S)); long t = idx / (R * S);
+        int d1 = (int)(t % D1); int d0 = (int)(t / D1);
+        int ck = kdim ? d1 : d0, co = kdim ? d0 : d1;
+        float v = packed[((long)tap * Ck + ck) * Co + co];
+        if (accumulate) w[idx] += v; else w[idx] = v;
+    }
+}
+
+// double -> float with scale (bias gradient, loss means)
+__global__ void cvt_f64_f32_kernel(const double* __restrict__ in, long stride_in, float* __restrict__ out, long n,
+                                   float scale, int accumulate) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float v = (float)(in[i * stride_in] * (double)scale);
+        if (accumulate) out[i] += v; else out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam over one flat fp32 arena (torch.optim.Adam semantics, no weight decay, no amsgrad)
+// ------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float grad_scale) {
+    long n4 = n >> 2;
+    float step = lr / bc1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 P = ld4(p + 4 * i), G = ld4(g + 4 * i), M = ld4(m + 4 * i), V = ld4(v + 4 * i);
+        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gr = gg[k] * grad_scale;
+            mm[k] = mm[k] + (gr - mm[k]) * (1.f - b1);
+            vv[k] = vv[k] * b2 + gr * gr * (1.f - b2);
+            float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+            pp[k] -= step * (mm[k] / denom);
+        }
+        st4(p + 4 * i, P); st4(m + 4 * i, M); st4(v + 4 * i, V);
+    }
+    if (blockIdx.x == 0) {
+        for (long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            float gr = g[i] * grad_scale;
+            float mk = m[i] + (gr - m[i]) * (1.f - b1);
+            float vk = v[i] * b2 + gr * gr * (1.f - b2);
+            m[i] = mk; v[i] = vk;
+            p[i] -= step * (mk / (sqrtf(vk) / bc2_sqrt + eps));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream) {
+    DSR_REQUIRE(x && y && N > 0 && C > 0 && P > 0, "bad arguments");
+    dim3 grid(dsr_cdiv(P, 32), dsr_cdiv(C, 32), N), block(32, 8);
+    transpose_cp_kernel<<<grid, block, 0, ST(stream)>>>(x, y, C, P, 1);
+    return dsr_check_launch("nchw_to_nhwc");
+}
+extern "C" int dsr_nhwc_to_nchw(const float* x, float* y, int N, int C, long P, void* stream) {
+    DSR_REQUIRE(x && y && N > 0 && C > 0 && P > 0, "bad arguments");
+    dim3 grid(dsr_cdiv(P, 32), dsr_cdiv(C, 32), N), block(32, 8);
+    transpose_cp_kernel<<<grid, block, 0, ST(stream)>>>(x, y, C, P, 0);
+    return dsr_check_launch("nhwc_to_nchw");
+}
+extern "C" int dsr_copy_channels(const float* src, int srcC, int soff, float* dst, int dstC, int doff, int nC,
+                                 long npix, int accumulate, void* stream) {
+    DSR_REQUIRE(src && dst && nC > 0 && soff + nC <= srcC && doff + nC <= dstC, "bad channel ranges");
+    bool vec = !accumulate && !(srcC & 3) && !(dstC & 3) && !(soff & 3) && !(doff & 3) && !(nC & 3) &&
+               !((uintptr_t)src & 15) && !((uintptr_t)dst & 15);
+    if (vec)
+        copy_channels_vec4_kernel<<<dsr_grid(npix * (nC / 4), TPB), TPB, 0, ST(stream)>>>(
+            (const float4*)src, srcC / 4, soff / 4, (float4*)dst, dstC / 4, doff / 4, nC / 4, npix);
+    else
+        copy_channels_kernel<<<dsr_grid(npix * nC, TPB), TPB, 0, ST(stream)>>>(src, srcC, soff, dst, dstC, doff, nC,
+                                                                                npix, accumulate);
+    return dsr_check_launch("copy_channels");
+}
+extern "C" int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, int mode, void* stream) {
+    DSR_REQUIRE(x && y && pad >= 0 && pad <= 7, "bad arguments");
+    DSR_REQUIRE(mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
+    pad2d_fwd_kernel<<<dsr_grid((long)N * (H + 2 * pad) * (W + 2 * pad) * C, TPB), TPB, 0, ST(stream)>>>(x, y, N, H, W, C,
+                                                                                                     pad, mode);
+    return dsr_check_launch("pad2d_fwd");
+}
+extern "C" int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream) {
+    DSR_REQUIRE(gy && gx && pad >= 0 && pad <= 7, "bad arguments");
+    pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode);
+    return dsr_check_launch("pad2d_bwd");
+}
+extern "C" int dsr_act_fwd(const float* x, float* y, long n, int kind, float slope, void* stream) {
+    DSR_REQUIRE(x && y, "null pointer");
+    act_fwd_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(x, y, n, kind, slope);
+    return dsr_check_launch("act_fwd");
+}
+extern "C" int dsr_act_bwd(const float* ref, const float* gy, float* gx, long n, int kind, float slope, void* stream) {
+    DSR_REQUIRE(ref && gy && gx, "null pointer");
+    act_bwd_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(ref, gy, gx, n, kind, slope);
+    return dsr_check_launch("act_bwd");
+}
+static void sums_launch_cfg(int N, long P, long* chunk, dim3* grid) {
+    long want = (long)dsr_num_sms() * 4 / (N > 0 ? N : 1);
+    if (want < 1) want = 1;
+    long c = (P + want - 1) / want;
+    if (c < 64) c = 64;
+    *chunk = c;
+    *grid = dim3((unsigned)((P + c - 1) / c), (unsigned)N);
+}
+extern "C" int dsr_channel_sums(const float* x, int N, long P, int C, double* sums, void* stream) {
+    DSR_REQUIRE(x && sums && N > 0 && P > 0 && C > 0, "bad arguments");
+    long chunk; dim3 grid;
+    sums_launch_cfg(N, P, &chunk, &grid);
+    channel_sums_kernel<<<grid, TPB, 0, ST(stream)>>>(x, nullptr, nullptr, N, P, C, chunk, 0, 0, sums);
+    return dsr_check_launch("channel_sums");
+}
+extern "C" int dsr_norm_finalize(const double* sums, int N, int C, long P, int groups, const float* gamma,
+                                 const float* beta, float eps, float* prm, void* stream) {
+    DSR_REQUIRE(sums && prm && (groups == 0 || C % groups == 0), "bad arguments");
+    norm_finalize_kernel<<<dsr_grid((long)N * C, TPB), TPB, 0, ST(stream)>>>(sums, N, C, P, groups, gamma, beta, eps, prm);
+    return dsr_check_launch("norm_finalize");
+}
+extern "C" int dsr_norm_apply_fwd(const float* x, const float* prm, const float* res, float* y, int N, long P, int C,
+                                  int act, void* stream) {
+    DSR_REQUIRE(x && prm && y, "null pointer");
+    norm_apply_fwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, prm, res, y, N, P, C, act);
+    return dsr_check_launch("norm_apply_fwd");
+}
+extern "C" int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm, int N, long P, int C, int act,
+                               double* sums2, void* stream) {
+    DSR_REQUIRE(x && dy && prm && sums2, "null pointer");
+    long chunk; dim3 grid;
+    sums_launch_cfg(N, P, &chunk, &grid);
+    channel_sums_kernel<<<grid, TPB, 0, ST(stream)>>>(x, dy, prm, N, P, C, chunk, 1, act, sums2);
+    return dsr_check_launch("in_bwd_sums");
+}
+extern "C" int dsr_in_bwd_apply(const float* x, const float* dy, const float* prm, const double* sums2, float* dx,
+                                int N, long P, int C, int act, void* stream) {
+    DSR_REQUIRE(x && dy && prm && sums2 && dx, "null pointer");
+    in_apply_bwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, sums2, dx, N, P, C, act);
+    return dsr_check_launch("in_bwd_apply");
+}
+extern "C" int dsr_pack_weight(const float* w, int D0, int D1, int R, int S, int kdim, float* out, void* stream) {
+    DSR_REQUIRE(w && out, "null pointer");
+    pack_weight_kernel<<<dsr_grid((long)D0 * D1 * R * S, TPB), TPB, 0, ST(stream)>>>(w, D0, D1, R, S, kdim, out);
+    return dsr_check_launch("pack_weight");
+}
+extern "C" int dsr_unpack_weight(const float* packed, int D0, int D1, int R, int S, int kdim, float* w, int accumulate,
+                                 void* stream) {
+    DSR_REQUIRE(packed && w, "null pointer");
+    unpack_weight_kernel<<<dsr_grid((long)D0 * D1 * R * S, TPB), TPB, 0, ST(stream)>>>(packed, D0, D1, R, S, kdim, w,
+                                                                                         accumulate);
+    return dsr_check_launch("unpack_weight");
+}
+extern "C" int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, long n, float scale, int accumulate,
+                               void* stream) {
+    DSR_REQUIRE(in && out, "null pointer");
+    cvt_f64_f32_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(in, stride_in, out, n, scale, accumulate);
+    return dsr_check_launch("cvt_f64_f32");
+}
+extern "C" int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2,
+                             float eps, int step, float grad_scale, void* stream) {
+    DSR_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad arguments");
+    DSR_REQUIRE(!((uintptr_t)p & 15) && !((uintptr_t)g & 15) && !((uintptr_t)m & 15) && !((uintptr_t)v & 15),
+                "arena pointers must be 16-byte aligned");
+    double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    adam_kernel<<<dsr_grid(n / 4 + 1, TPB), TPB, 0, ST(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1,
+                                                                  (float)sqrt(bc2), grad_scale);
+    return dsr_check_launch("adam_step");
+}

@@ -1,0 +1,588 @@
+"""torch.autograd.Function wrappers over the C-ABI library (one Function per op of the hot path).
+
+PyTorch is used for device memory, streams and the autograd graph only; every kernel that runs is
+ours (csrc/*.cu through include/dsr_b200.h).  Activations are logical NCHW tensors whose memory is
+NHWC (torch channels_last); loss-stack tensors (depth, normals, masks) are plain NCHW planes exactly
+as in the reference.  There is no CPU path: a non-CUDA tensor raises.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+PAD_MODES = {"zeros": PAD_ZERO, "zero": PAD_ZERO, "reflect": PAD_REFLECT, "replicate": PAD_REPLICATE}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t, dtype=torch.float32):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dsr_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("internal error: non-contiguous tensor handed to the C-ABI")
+    return t.data_ptr()
+
+
+def _call(name, *args):
+    _lib.call(name, *args, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers (raw, no autograd)
+# ------------------------------------------------------------------------------------------------
+def nhwc(x):
+    """logical NCHW fp32 tensor -> contiguous (N,H,W,C) tensor sharing memory when possible."""
+    if x.dim() != 4:
+        raise ValueError("expected a 4-D NCHW tensor")
+    if not x.is_cuda:
+        raise RuntimeError("dsr_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % x.device)
+    if x.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {x.dtype}")
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous():
+        return xp
+    N, C, H, W = x.shape
+    xc = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty((N, H, W, C), device=x.device, dtype=torch.float32)
+    _call("dsr_nchw_to_nhwc", _p(xc), _p(y), N, C, H * W)
+    return y
+
+
+def nchw(y):
+    """contiguous (N,H,W,C) tensor -> logical NCHW view (channels_last strides)."""
+    return y.permute(0, 3, 1, 2)
+
+
+def planes(x):
+    """logical NCHW tensor -> NCHW-contiguous tensor (the reference's layout for the loss stack)."""
+    if x.is_contiguous():
+        return x
+    N, C, H, W = x.shape
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous() and x.is_cuda and x.dtype == torch.float32:
+        y = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
+        _call("dsr_nhwc_to_nchw", _p(xp), _p(y), N, C, H * W)
+        return y
+    return x.contiguous()
+
+
+def _zeros_f64(n, device):
+    return torch.zeros(n, device=device, dtype=torch.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions
+# ------------------------------------------------------------------------------------------------
+def _pack(weight, kdim):
+    D0, D1, R, S = weight.shape
+    w = weight.detach()
+    w = w if w.is_contiguous() else w.contiguous()
+    out = torch.empty(D0 * D1 * R * S, device=w.device, dtype=torch.float32)
+    _call("dsr_pack_weight", _p(w), D0, D1, R, S, kdim, _p(out))
+    return out
+
+
+# Parameters registered here (data_ptr -> fp32 gradient view inside the gradient arena) get their
+# gradients ACCUMULATED in place by the backward kernels instead of being returned to autograd
+# (no AccumulateGrad add kernels, one flat buffer for Adam and for the NCCL buckets).  The arena
+# owner zeroes it once per step.  GRAD_READY, if set, is called with the parameter's data_ptr as
+# soon as its gradient kernel is enqueued - the hook the bucketed all-reduce overlaps on.
+DIRECT_GRADS = {}
+GRAD_READY = None
+
+
+def _grad_ready(param):
+    if GRAD_READY is not None:
+        GRAD_READY(param.data_ptr())
+
+
+def _bias_grad(dy_nhwc, Co, bias):
+    sums = _zeros_f64(Co * 2, dy_nhwc.device)
+    _call("dsr_channel_sums", _p(dy_nhwc), 1, dy_nhwc.numel() // Co, Co, _p(sums, torch.float64))
+    tgt = DIRECT_GRADS.get(bias.data_ptr())
+    if tgt is not None:
+        _call("dsr_cvt_f64_f32", _p(sums, torch.float64), 2, _p(tgt), Co, 1.0, 1)
+        _grad_ready(bias)
+        return None
+    gb = torch.empty(Co, device=dy_nhwc.device, dtype=torch.float32)
+    _call("dsr_cvt_f64_f32", _p(sums, torch.float64), 2, _p(gb), Co, 1.0, 0)
+    return gb
+
+
+def _weight_grad(dwk, weight, kdim):
+    D0, D1, R, S = weight.shape
+    tgt = DIRECT_GRADS.get(weight.data_ptr())
+    if tgt is not None:
+        _call("dsr_unpack_weight", _p(dwk), D0, D1, R, S, kdim, _p(tgt), 1)
+        _grad_ready(weight)
+        return None
+    gw = torch.empty(weight.shape, device=dwk.device, dtype=torch.float32)
+    _call("dsr_unpack_weight", _p(dwk), D0, D1, R, S, kdim, _p(gw), 0)
+    return gw
+
+
+class _Conv2d(Function):
+    """nn.Conv2d (zero padding; explicit pads are a separate op).  networks.py:379,385,414,453,544."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act_out):
+        xh = nhwc(x)
+        N, H, W, Ci = xh.shape
+        Co, Ci2, R, S = weight.shape
+        if Ci2 != Ci:
+            raise ValueError(f"conv2d: input has {Ci} channels, weight expects {Ci2}")
+        Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+        wk = _pack(weight, 1)
+        b = bias.detach() if bias is not None else None
+        _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 0, act_out)
+        ctx.cfg = (stride, pad, act_out, bias is not None)
+        ctx.bias_ref = bias
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, weight, y = ctx.saved_tensors
+        stride, pad, act_out, has_bias = ctx.cfg
+        N, H, W, Ci = xh.shape
+        Co, _, R, S = weight.shape
+        g = nhwc(gy)
+        _, Ho, Wo, _ = g.shape
+        if act_out == ACT_TANH:
+            g2 = torch.empty_like(g)
+            _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
+            g = g2
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wk = _pack(weight, 0)                       # [(r,s,co)][ci]
+            gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
+            _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 1, ACT_NONE)
+            gx = nchw(gxh)
+        if ctx.needs_input_grad[1]:
+            dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
+            _call("dsr_wgrad_simt", _p(xh), _p(g), _p(dwk), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad)
+            gw = _weight_grad(dwk, weight, 1)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = _bias_grad(g, Co, ctx.bias_ref)
+        return gx, gw, gb, None, None, None
+
+
+class _ConvTranspose2d(Function):
+    """nn.ConvTranspose2d.  networks.py:406,553,605,612; translation_network.py:508."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, opad, act_out):
+        xh = nhwc(x)
+        N, H, W, Ci = xh.shape
+        Ci2, Co, R, S = weight.shape
+        if Ci2 != Ci:
+            raise ValueError(f"conv_transpose2d: input has {Ci} channels, weight expects {Ci2}")
+        Ho, Wo = (H - 1) * stride - 2 * pad + R + opad, (W - 1) * stride - 2 * pad + S + opad
+        y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+        wk = _pack(weight, 0)                           # [(r,s,ci)][co]
+        b = bias.detach() if bias is not None else None
+        _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, act_out)
+        ctx.cfg = (stride, pad, act_out, bias is not None)
+        ctx.bias_ref = bias
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, weight, y = ctx.saved_tensors
+        stride, pad, act_out, has_bias = ctx.cfg
+        N, H, W, Ci = xh.shape
+        _, Co, R, S = weight.shape
+        g = nhwc(gy)
+        _, Ho, Wo, _ = g.shape
+        if act_out == ACT_TANH:
+            g2 = torch.empty_like(g)
+            _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
+            g = g2
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wk = _pack(weight, 1)                       # [(r,s,co)][ci]
+            gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
+            _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
+            gx = nchw(gxh)
+        if ctx.needs_input_grad[1]:
+            dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
+            _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
+            gw = _weight_grad(dwk, weight, 1)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = _bias_grad(g, Co, ctx.bias_ref)
+        return gx, gw, gb, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE):
+    return _Conv2d.apply(x, weight, bias, stride, padding, act_out)
+
+
+def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE):
+    return _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out)
+
+
+class _Pad2d(Function):
+    @staticmethod
+    def forward(ctx, x, pad, mode):
+        xh = nhwc(x)
+        N, H, W, C = xh.shape
+        y = torch.empty((N, H + 2 * pad, W + 2 * pad, C), device=x.device, dtype=torch.float32)
+        _call("dsr_pad2d_fwd", _p(xh), _p(y), N, H, W, C, pad, mode)
+        ctx.cfg = (N, H, W, C, pad, mode)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        N, H, W, C, pad, mode = ctx.cfg
+        g = nhwc(gy)
+        gx = torch.empty((N, H, W, C), device=g.device, dtype=torch.float32)
+        _call("dsr_pad2d_bwd", _p(g), _p(gx), N, H, W, C, pad, mode)
+        return nchw(gx), None, None
+
+
+def pad2d(x, pad, mode):
+    return _Pad2d.apply(x, pad, PAD_MODES[mode] if isinstance(mode, str) else mode)
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / activation / concat
+# ------------------------------------------------------------------------------------------------
+def _norm_params(xh, groups, gamma, beta, eps):
+    N, H, W, C = xh.shape
+    sums = _zeros_f64(N * C * 2, xh.device)
+    _call("dsr_channel_sums", _p(xh), N, H * W, C, _p(sums, torch.float64))
+    prm = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)
+    _call("dsr_norm_finalize", _p(sums, torch.float64), N, C, H * W, groups, _p(gamma), _p(beta), eps, _p(prm))
+    return prm
+
+
+class _InstanceNorm(Function):
+    """InstanceNorm2d(affine=False) [+ ReLU] [+ residual add].  networks.py:30, :380-381, :480."""
+
+    @staticmethod
+    def forward(ctx, x, eps, act, residual):
+        xh = nhwc(x)
+        N, H, W, C = xh.shape
+        prm = _norm_params(xh, 0, None, None, eps)
+        rh = nhwc(residual) if residual is not None else None
+        y = torch.empty_like(xh)
+        _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
+        ctx.act = act
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(xh, prm)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, prm = ctx.saved_tensors
+        N, H, W, C = xh.shape
+        g = nhwc(gy)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            sums2 = _zeros_f64(N * C * 2, g.device)
+            _call("dsr_in_bwd_sums", _p(xh), _p(g), _p(prm), N, H * W, C, ctx.act, _p(sums2, torch.float64))
+            gxh = torch.empty_like(xh)
+            _call("dsr_in_bwd_apply", _p(xh), _p(g), _p(prm), _p(sums2, torch.float64), _p(gxh), N, H * W, C, ctx.act)
+            gx = nchw(gxh)
+        gres = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return gx, None, None, gres
+
+
+def instance_norm(x, eps=1e-5, act=ACT_NONE, residual=None):
+    return _InstanceNorm.apply(x, eps, act, residual)
+
+
+def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None):
+    """GroupNorm(groups, C, affine=True) [+ReLU] [+residual], forward only (G_A_d is frozen on the hot
+    path, main_model.py:426).  translation_network.py:46."""
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
+                                    (residual is not None and residual.requires_grad)):
+        raise NotImplementedError("dsr_b200: GroupNorm backward is not on the main_network_best hot path "
+                                  "(G_A_d is frozen); run the translation generator under torch.no_grad()")
+    xh = nhwc(x)
+    N, H, W, C = xh.shape
+    prm = _norm_params(xh, groups, weight.detach().contiguous(), bias.detach().contiguous(), eps)
+    rh = nhwc(residual) if residual is not None else None
+    y = torch.empty_like(xh)
+    _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
+    return nchw(y)
+
+
+class _Act(Function):
+    @staticmethod
+    def forward(ctx, x, kind, slope):
+        xh = nhwc(x)
+        y = torch.empty_like(xh)
+        _call("dsr_act_fwd", _p(xh), _p(y), xh.numel(), kind, slope)
+        ctx.cfg = (kind, slope)
+        ctx.save_for_backward(y if kind == ACT_TANH else xh)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (ref,) = ctx.saved_tensors
+        kind, slope = ctx.cfg
+        g = nhwc(gy)
+        gx = torch.empty_like(g)
+        _call("dsr_act_bwd", _p(ref), _p(g), _p(gx), g.numel(), kind, slope)
+        return nchw(gx), None, None
+
+
+def relu(x):
+    return _Act.apply(x, ACT_RELU, 0.0)
+
+
+def leaky_relu(x, slope=0.2):
+    return _Act.apply(x, ACT_LRELU, slope)
+
+
+def tanh(x):
+    return _Act.apply(x, ACT_TANH, 0.0)
+
+
+class _Cat(Function):
+    """torch.cat(dim=1) of NHWC-backed tensors.  networks.py:629, main_model.py:302-306."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        hs = [nhwc(x) for x in xs]
+        N, H, W, _ = hs[0].shape
+        Cs = [h.shape[3] for h in hs]
+        y = torch.empty((N, H, W, sum(Cs)), device=hs[0].device, dtype=torch.float32)
+        off = 0
+        for h, c in zip(hs, Cs):
+            _call("dsr_copy_channels", _p(h), c, 0, _p(y), sum(Cs), off, c, N * H * W, 0)
+            off += c
+        ctx.Cs = Cs
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        g = nhwc(gy)
+        N, H, W, Ct = g.shape
+        outs, off = [], 0
+        for i, c in enumerate(ctx.Cs):
+            if ctx.needs_input_grad[i]:
+                gx = torch.empty((N, H, W, c), device=g.device, dtype=torch.float32)
+                _call("dsr_copy_channels", _p(g), Ct, off, _p(gx), c, 0, c, N * H * W, 0)
+                outs.append(nchw(gx))
+            else:
+                outs.append(None)
+            off += c
+        return tuple(outs)
+
+
+def cat(xs):
+    return _Cat.apply(*xs)
+
+
+# ------------------------------------------------------------------------------------------------
+# loss stack (NCHW planes)
+# ------------------------------------------------------------------------------------------------
+def hole_valid_masks(depth, border=-0.97):
+    """-> (hole, valid) float32 {0,1}.  main_model.py:208-230."""
+    d = planes(depth.detach())
+    B, C, H, W = d.shape
+    hole, valid = torch.empty_like(d), torch.empty_like(d)
+    _call("dsr_hole_valid_masks", _p(d), B * C, H, W, border, _p(hole), _p(valid))
+    return hole, valid
+
+
+def rect_holes(valid, depth, rects_dev, counts_dev, max_rects, extra_border=float("-inf")):
+    """-> (gt_mask uint8, masked depth, extra-hole mask).  main_model.py:257-298, :354-357, :396."""
+    v, d = planes(valid), planes(depth.detach())
+    B, _, H, W = d.shape
+    gt = torch.empty((B, 1, H, W), device=d.device, dtype=torch.uint8)
+    masked, extra = torch.empty_like(d), torch.empty_like(d)
+    _call("dsr_rect_holes", _p(v), _p(d), _p(rects_dev, torch.int32), _p(counts_dev, torch.int32), max_rects,
+          B, H, W, extra_border, _p(gt, torch.uint8), _p(masked), _p(extra))
+    return gt, masked, extra
+
+
+class _NormalsOld(Function):
+    @staticmethod
+    def forward(ctx, depth, scale):
+        d = planes(depth)
+        B, _, H, W = d.shape
+        out = torch.empty((B, 3, H, W), device=d.device, dtype=torch.float32)
+        _call("dsr_normals_old_fwd", _p(d), B, H, W, scale, _p(out))
+        ctx.scale = scale
+        ctx.save_for_backward(d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        B, _, H, W = d.shape
+        gd = torch.empty_like(d)
+        _call("dsr_normals_old_bwd", _p(d), _p(planes(g)), B, H, W, ctx.scale, _p(gd))
+        return gd, None
+
+
+class _NormalsNew(Function):
+    @staticmethod
+    def forward(ctx, depth, cams):
+        d = planes(depth)
+        B, _, H, W = d.shape
+        out = torch.empty((B, 3, H, W), device=d.device, dtype=torch.float32)
+        _call("dsr_normals_new_fwd", _p(d), _p(cams, torch.float64), B, H, W, _p(out))
+        ctx.save_for_backward(d, cams)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d, cams = ctx.saved_tensors
+        B, _, H, W = d.shape
+        gd = torch.empty_like(d)
+        _call("dsr_normals_new_bwd", _p(d), _p(planes(g)), _p(cams, torch.float64), B, H, W, _p(gd))
+        return gd, None
+
+
+def normals_old(depth, scale=1.0):
+    if depth.dtype != torch.float32:
+        raise TypeError("Input shold be torch.float32")      # norms.py:205-208
+    return _NormalsOld.apply(depth, float(scale))
+
+
+def normals_new(depth, cams):
+    return _NormalsNew.apply(depth, cams)
+
+
+class _TV(Function):
+    @staticmethod
+    def forward(ctx, x):
+        xp = planes(x)
+        B, C, H, W = xp.shape
+        acc = _zeros_f64(1, xp.device)
+        _call("dsr_tv_fwd", _p(xp), B * C, H, W, _p(acc, torch.float64))
+        out = torch.empty((), device=xp.device, dtype=torch.float32)
+        _call("dsr_cvt_f64_f32", _p(acc, torch.float64), 1, _p(out), 1, 1.0, 0)
+        ctx.save_for_backward(xp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (xp,) = ctx.saved_tensors
+        B, C, H, W = xp.shape
+        gx = torch.empty_like(xp)
+        _call("dsr_tv_bwd", _p(xp), B * C, H, W, _p(g.contiguous()), 1.0, _p(gx))
+        return gx
+
+
+def tv_loss(x):
+    return _TV.apply(x)
+
+
+class _MaskedDiff(Function):
+    """(mean |a*m - b*m|, mean (a*m - b*m)^2) over all elements; gradient flows to b only."""
+
+    @staticmethod
+    def forward(ctx, a, b, m1, m2):
+        a, b, m1 = planes(a.detach()), planes(b), planes(m1)
+        m2 = planes(m2) if m2 is not None else None
+        B, C, H, W = b.shape
+        acc = _zeros_f64(2, b.device)
+        _call("dsr_masked_diff_fwd", _p(a), _p(b), _p(m1), _p(m2), B, C, H * W, _p(acc, torch.float64))
+        out = torch.empty(2, device=b.device, dtype=torch.float32)
+        _call("dsr_cvt_f64_f32", _p(acc, torch.float64), 1, _p(out), 2, 1.0 / b.numel(), 0)
+        ctx.save_for_backward(a, b, m1, m2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, m1, m2 = ctx.saved_tensors
+        B, C, H, W = b.shape
+        gb = torch.empty_like(b)
+        inv = 1.0 / b.numel()
+        g = g.contiguous()
+        _call("dsr_masked_diff_bwd", _p(a), _p(b), _p(m1), _p(m2), B, C, H * W, _p(g), _p(g) + 4, inv, inv, _p(gb))
+        return None, gb, None, None
+
+
+def masked_l1_l2(a, b, m1, m2=None):
+    """-> float32[2] = (L1 mean, MSE mean) of (a*m1*m2, b*m1*m2)."""
+    return _MaskedDiff.apply(a, b, m1, m2)
+
+
+def masked_sums(d, p, m):
+    """-> float64[3] = (sum d*m, sum p*m, sum |d*m - p*m|).  main_model.py:308-318."""
+    d, p, m = planes(d.detach()), planes(p.detach()), planes(m)
+    out = _zeros_f64(3, d.device)
+    _call("dsr_masked_sums", _p(d), _p(p), _p(m), d.numel(), _p(out, torch.float64))
+    return out
+
+
+class _Smooth(Function):
+    """get_smooth_weight(depth, image, 3).  main_model.py:22-73."""
+
+    @staticmethod
+    def forward(ctx, depth, image, num_scales):
+        d, im = planes(depth), planes(image.detach())
+        B, _, H, W = d.shape
+        C = im.shape[1]
+        levels = []                       # coarsest first, like scale_pyramid(...).reverse()
+        for e in range(num_scales - 1, -1, -1):
+            if e == 0:
+                levels.append((d, im, H, W))
+            else:
+                nh, nw = H // 2 ** e, W // 2 ** e
+                dl = torch.empty((B, 1, nh, nw), device=d.device, dtype=torch.float32)
+                il = torch.empty((B, C, nh, nw), device=d.device, dtype=torch.float32)
+                _call("dsr_bilinear_ac_fwd", _p(d), B, H, W, nh, nw, _p(dl))
+                _call("dsr_bilinear_ac_fwd", _p(im), B * C, H, W, nh, nw, _p(il))
+                levels.append((dl, il, nh, nw))
+        acc = _zeros_f64(2 * num_scales, d.device)
+        out = torch.zeros((), device=d.device, dtype=torch.float32)
+        coefs = []
+        for i, (dl, il, h, w) in enumerate(levels):
+            _call("dsr_smooth_level_fwd", _p(dl), _p(il), B, C, h, w, _p(acc[2 * i:], torch.float64))
+            cx = 1.0 / (B * (h - 1) * w) / 2 ** i
+            cy = 1.0 / (B * h * (w - 1)) / 2 ** i
+            coefs.append((cx, cy))
+            _call("dsr_cvt_f64_f32", _p(acc[2 * i:], torch.float64), 1, _p(out), 1, cx, 1)
+            _call("dsr_cvt_f64_f32", _p(acc[2 * i + 1:], torch.float64), 1, _p(out), 1, cy, 1)
+        ctx.levels, ctx.coefs, ctx.shape = levels, coefs, (B, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W = ctx.shape
+        g = g.contiguous()
+        d_full = ctx.levels[-1][0]
+        gd = torch.empty_like(d_full)
+        cx, cy = ctx.coefs[-1]
+        _call("dsr_smooth_level_bwd", _p(d_full), _p(ctx.levels[-1][1]), B, C, H, W, _p(g), cx, cy, _p(gd), 0)
+        for (dl, il, h, w), (cx, cy) in zip(ctx.levels[:-1], ctx.coefs[:-1]):
+            gl = torch.empty_like(dl)
+            _call("dsr_smooth_level_bwd", _p(dl), _p(il), B, C, h, w, _p(g), cx, cy, _p(gl), 0)
+            _call("dsr_bilinear_ac_bwd", _p(gl), B, H, W, h, w, _p(gd))
+        ctx.levels = None
+        return gd, None, None
+
+
+def smooth_loss(depth, image, num_scales=3):
+    return _Smooth.apply(depth, image, num_scales)
+
+
+def ssim(a, b):
+    """Mean SSIM (11x11 Gaussian, sigma 1.5).  pytorch_ssim/__init__.py:17-37.  Forward only."""
+    a, b = planes(a.detach()), planes(b.detach())
+    B, C, H, W = a.shape
+    acc = _zeros_f64(1, a.device)
+    _call("dsr_ssim_fwd", _p(a), _p(b), B * C, H, W, _p(acc, torch.float64), None)
+    return (acc / a.numel()).to(torch.float32)[0]
+
+
+def adam_step(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+    _call("dsr_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale)

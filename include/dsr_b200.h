@@ -1,0 +1,131 @@
+/* dsr_b200 - C-ABI of the B200-native hot path of the image-guided depth-enhancement training step.
+ *
+ * Drop-in boundary.  The reference (neeek2303/Depth-Enhancement-and-Super-Resolution) is pure
+ * Python/PyTorch and has no FFI of its own; every entry point below replaces the ATen call(s) the
+ * reference makes at the cited file:line (citations into /root/reference).  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is DEVICE memory
+ * owned by the caller and outliving the call unless the name says `host`; `stream` is a
+ * cudaStream_t passed as void*; calls only enqueue work, never synchronise and never allocate;
+ * return 0 on success, a negative DSR_ERR_* otherwise (message via dsr_last_error_string(),
+ * thread-local).  The caller selects the device (cudaSetDevice) before calling.
+ * Layouts: "NCHW planes" = the reference's layout for depth / normals / masks; "NHWC" = the
+ * library's internal activation layout (torch channels_last memory).
+ */
+#ifndef DSR_B200_H
+#define DSR_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSR_B200_VERSION 100
+
+#define DSR_PAD_ZERO 0
+#define DSR_PAD_REFLECT 1      /* nn.ReflectionPad2d            models/networks.py:378,413,453 */
+#define DSR_PAD_REPLICATE 2    /* Conv2d(padding_mode='replicate') models/translation_network.py:472 */
+
+#define DSR_ACT_NONE 0
+#define DSR_ACT_RELU 1         /* nn.ReLU(True)                 models/networks.py:381,548 */
+#define DSR_ACT_LRELU 2        /* nn.LeakyReLU(0.2, False)      models/networks.py:546 */
+#define DSR_ACT_TANH 3         /* nn.Tanh                       models/networks.py:415,557 */
+
+int dsr_version(void);
+const char* dsr_last_error_string(void);
+int dsr_device_sm_count(void);
+int dsr_device_arch(void);      /* 100 on B200 */
+
+/* ---- loss stack: depth-derived stencils and reductions (NCHW planes, fp32) ------------------ */
+
+/* hole = 1[d <= border], valid = 1 - dilate3x3(hole).  models/main_model.py:208-230.  hole may be NULL. */
+int dsr_hole_valid_masks(const float* depth, int B, int H, int W, float border, float* hole, float* valid,
+                         void* stream);
+/* random rectangle holes.  models/main_model.py:257-298 (+ :354-357, :396 for `extra`).
+ * rects int32 [B][max_rects][4] = (x, y, size_x, size_y), counts int32 [B] (both device).
+ * gt_mask u8 {0,1}; masked = gt ? depth : -1; extra = 1[(masked < extra_border) || !gt] (may be NULL). */
+int dsr_rect_holes(const float* valid, const float* depth, const int* rects, const int* counts, int max_rects,
+                   int B, int H, int W, float extra_border, unsigned char* gt_mask, float* masked, float* extra,
+                   void* stream);
+/* image-space normals x scale, fwd / bwd.  models/norms.py:185-190 (caller's x100: main_model.py:345-349). */
+int dsr_normals_old_fwd(const float* depth, int B, int H, int W, float scale, float* out /*B,3,H,W*/, void* stream);
+int dsr_normals_old_bwd(const float* depth, const float* gout, int B, int H, int W, float scale, float* gdepth,
+                        void* stream);
+/* camera-space normals (fp64 inside), fwd / bwd.  models/norms.py:103-108, :75-101, :29-73.
+ * cams: double [B][11] = K^-1 row-major (9), w0 + shift, h0 + shift. */
+int dsr_normals_new_fwd(const float* depth, const double* cams, int B, int H, int W, float* out, void* stream);
+int dsr_normals_new_bwd(const float* depth, const float* gout, const double* cams, int B, int H, int W,
+                        float* gdepth, void* stream);
+/* tv_loss: *out_sum += sum of squared forward differences.  models/main_model.py:15-19.
+ * bwd: gx = coef * (*gscale) * d tv / dx. */
+int dsr_tv_fwd(const float* x, long planes, int H, int W, double* out_sum, void* stream);
+int dsr_tv_bwd(const float* x, long planes, int H, int W, const float* gscale, float coef, float* gx, void* stream);
+/* masked L1 / L2: t = (a*m1)*m2 - (b*m1)*m2; out2[0] += sum|t|, out2[1] += sum t^2.  a,b (B,C,plane),
+ * masks (B,1,plane), m2 may be NULL.  L1Loss/MSELoss call sites models/main_model.py:352,371-372,383-398.
+ * bwd: gb = -(c1*(*g_l1)*sign(t) + c2*(*g_l2)*2t) * m. */
+int dsr_masked_diff_fwd(const float* a, const float* b, const float* m1, const float* m2, int B, int C, long plane,
+                        double* out2, void* stream);
+int dsr_masked_diff_bwd(const float* a, const float* b, const float* m1, const float* m2, int B, int C, long plane,
+                        const float* g_l1, const float* g_l2, float c1, float c2, float* gb, void* stream);
+/* monitoring sums: out3 += (sum d*m, sum p*m, sum |d*m - p*m|).  models/main_model.py:308-318. */
+int dsr_masked_sums(const float* d, const float* p, const float* m, long total, double* out3, void* stream);
+/* smoothness loss pieces.  models/main_model.py:22-73 (F.upsample bilinear align_corners=True :34). */
+int dsr_bilinear_ac_fwd(const float* x, long planes, int H, int W, int nh, int nw, float* out, void* stream);
+int dsr_bilinear_ac_bwd(const float* g, long planes, int H, int W, int nh, int nw, float* gx /* += */, void* stream);
+int dsr_smooth_level_fwd(const float* d, const float* img, int B, int C, int h, int w, double* out2, void* stream);
+int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
+                         float cx, float cy, float* gd, int accumulate, void* stream);
+/* SSIM, 11x11 Gaussian sigma 1.5, zero padding: *out_sum += sum of the SSIM map; map may be NULL.
+ * models/pytorch_ssim/__init__.py:17-37. */
+int dsr_ssim_fwd(const float* a, const float* b, long planes, int H, int W, double* out_sum, float* map,
+                 void* stream);
+
+/* ---- network plumbing (NHWC fp32) ------------------------------------------------------------ */
+int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream);
+int dsr_nhwc_to_nchw(const float* x, float* y, int N, int C, long P, void* stream);
+/* dst[p][doff + c] (=|+=) src[p][soff + c]: torch.cat(dim=1) and its backward.  models/networks.py:629,
+ * models/main_model.py:302-306, models/translation_network.py:549. */
+int dsr_copy_channels(const float* src, int srcC, int soff, float* dst, int dstC, int doff, int nC, long npix,
+                      int accumulate, void* stream);
+int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, int mode, void* stream);
+int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream);
+int dsr_act_fwd(const float* x, float* y, long n, int kind, float slope, void* stream);
+int dsr_act_bwd(const float* ref, const float* gy, float* gx, long n, int kind, float slope, void* stream);
+/* per-(n,c) (sum, sum of squares) over P pixels, accumulated into sums (double [N][C][2], pre-zeroed). */
+int dsr_channel_sums(const float* x, int N, long P, int C, double* sums, void* stream);
+/* sums -> prm float [3][N][C] = (mean, scale, shift).  groups 0: InstanceNorm2d(affine=False)
+ * models/networks.py:30;  groups 8: GroupNorm(8,C,affine) models/translation_network.py:46. */
+int dsr_norm_finalize(const double* sums, int N, int C, long P, int groups, const float* gamma, const float* beta,
+                      float eps, float* prm, void* stream);
+/* y = act((x - mean) * scale + shift) (+ res).  act in {NONE, RELU}.  Residual: models/networks.py:480. */
+int dsr_norm_apply_fwd(const float* x, const float* prm, const float* res, float* y, int N, long P, int C, int act,
+                       void* stream);
+int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm, int N, long P, int C, int act, double* sums2,
+                    void* stream);
+int dsr_in_bwd_apply(const float* x, const float* dy, const float* prm, const double* sums2, float* dx, int N,
+                     long P, int C, int act, void* stream);
+/* 4-D parameter [D0][D1][R][S] <-> GEMM operand [(r*S+s)*Ck + ck][Co]; kdim selects which of D0/D1 is ck. */
+int dsr_pack_weight(const float* w, int D0, int D1, int R, int S, int kdim, float* out, void* stream);
+int dsr_unpack_weight(const float* packed, int D0, int D1, int R, int S, int kdim, float* w, int accumulate,
+                      void* stream);
+int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, long n, float scale, int accumulate, void* stream);
+
+/* ---- convolutions ---------------------------------------------------------------------------- */
+/* generic fp32 implicit GEMM (CUDA cores): out[m][co] = bias[co] + sum_k G(m,k) Wk[k][co].
+ * nn.Conv2d / nn.ConvTranspose2d call sites: models/networks.py:379,385,406,414,453,544,553,605,612;
+ * models/translation_network.py:472,478,495,508,563,568. */
+int dsr_conv_simt(const float* G, const float* Wk, const float* bias, float* out, int N, int Hg, int Wg, int Cg,
+                  int Ho, int Wo, int Co, int R, int S, int stride, int pad, int transposed, int act_out,
+                  void* stream);
+int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, int Wg, int Cg, int Ho, int Wo, int Cd,
+                   int R, int S, int stride, int pad, void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------------- */
+/* torch.optim.Adam (defaults) over one flat arena.  models/main_model.py:176, :429. */
+int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                  int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,145 @@
+"""Generate the golden fixtures under tests/golden/ from the LIVE reference.
+
+Run in the build container only (needs /root/reference, read-only):
+    python tests/golden/make_golden.py
+The reference cannot travel to the GPU box, so its outputs are committed as small .npz files; this
+script is the provenance of every number in them.  Recipe = SURVEY.md Appendix D (imageio stub,
+TrainOptions with a synthetic argv, MainModel on --gpu_ids -1).
+"""
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+sys.modules["imageio"] = types.ModuleType("imageio")
+
+import numpy as np
+import torch
+
+from oracle.ref_step import synthetic_batch
+
+torch.set_num_threads(8)
+
+
+def ref_opt(B, H, W):
+    sys.argv = ["main.py", "--gpu_ids", "-1", "--image_and_depth", "--custom_pathes", "--use_image_for_trans",
+                "--w_syn_l1", "15", "--w_real_l1_d", "40", "--norm_loss", "--w_syn_norm", "2",
+                "--use_smooth_loss", "--w_smooth", "1", "--w_syn_holes", "800", "--w_real_holes", "1600",
+                "--use_masked", "--use_scannet", "--lr", "0.0001", "--model", "main_network_best",
+                "--batch_size", str(B), "--name", "golden", "--do_train", "--model_type", "main",
+                "--checkpoints_dir", "/tmp/golden/ckpt", "--crop_size_h", str(H), "--crop_size_w", str(W)]
+    from options.train_options import TrainOptions
+    return TrainOptions().parse()
+
+
+def proj_vec(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, generator=g, dtype=torch.float64)
+
+
+def golden_step(B=2, H=128, W=128, depth_kind="smooth", tag="step_b2_128"):
+    opt = ref_opt(B, H, W)
+    from models.main_model import MainModel
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = MainModel(opt)
+    model.setup(opt)
+    model._train()
+    out = {}
+    # checksums of the initial weights: pins "same seed + same constructor order => same weights"
+    for name in model.model_names:
+        sd = getattr(model, "net" + name).state_dict()
+        out[f"wsum/{name}"] = np.array([float(sum(v.double().sum() for v in sd.values())),
+                                        float(sum(v.double().abs().sum() for v in sd.values())),
+                                        float(sum(v.numel() for v in sd.values()))])
+        out[f"wkeys/{name}"] = np.array(list(sd.keys()))
+        out[f"wshapes/{name}"] = np.array([str(tuple(v.shape)) for v in sd.values()])
+    batch = synthetic_batch(B, H, W, seed=1, depth_kind=depth_kind)
+    for k in ("A_i", "B_i", "A_d", "B_d"):
+        out[f"in/{k}"] = batch[k].numpy()
+    out["in/K"] = batch["K_A"].numpy()
+    out["in/crop"] = batch["crop_A"].numpy()
+    np.random.seed(0)
+    for it in range(2):
+        model.set_input(batch)
+        model.optimize_parameters(it, 1)
+        p = f"s{it}/"
+        for k, v in model.get_current_losses().items():
+            out[p + "loss/" + k] = np.float64(v)
+        out[p + "loss/G"] = np.float64(float(model.loss_G))
+        out[p + "loss/mean_of_abs_diff_syn"] = np.float64(model.loss_mean_of_abs_diff_syn)
+        out[p + "loss/mean_of_abs_diff_real"] = np.float64(model.loss_mean_of_abs_diff_real)
+        for k in ("pred_syn_depth", "pred_real_depth", "syn2real_depth", "syn_depth_by_image",
+                  "real_depth_by_image", "depth_masked", "syn2real_depth_masked"):
+            out[p + k] = getattr(model, k).detach().numpy().astype(np.float32)
+        if it == 0:
+            for k in ("syn_mask", "real_mask", "real_hole_mask"):
+                out[p + k] = getattr(model, k).numpy().astype(np.uint8)
+            out[p + "gt_mask_syn"] = model.gt_mask_syn.numpy().astype(np.uint8)
+            out[p + "gt_mask_real"] = model.gt_mask_real.numpy().astype(np.uint8)
+            out[p + "norm_syn_pred"] = model.norm_syn_pred.detach().numpy().astype(np.float16)
+            out[p + "norm_real"] = model.norm_real.detach().numpy().astype(np.float16)
+            # gradients: per tensor (L2 norm, projection on a fixed random vector), a few in full
+            gi = 0
+            for net in ("Depth_f", "Task"):
+                for n, prm in getattr(model, "net" + net).named_parameters():
+                    g = prm.grad.detach().double().flatten()
+                    out[p + f"gstat/{net}/{n}"] = np.array([float(g.norm()), float(g @ proj_vec(g.numel(), 1000 + gi))])
+                    gi += 1
+                    if g.numel() <= 8192:
+                        out[p + f"gfull/{net}/{n}"] = prm.grad.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
+
+
+def golden_ops():
+    """Per-op vectors from the reference's own functions (adversarial: skewed K, crop offset,
+    non-square, all-hole rows, borders)."""
+    from models import norms as rn
+    from models import main_model as rm
+    from models import pytorch_ssim as rs
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    B, H, W = 2, 40, 56
+    d = torch.rand(B, 1, H, W, generator=g) * 1.8 - 0.9
+    d[:, :, 5:9, 10:30] = -1.0
+    d[0, 0, 0, :] = -1.0
+    d[1, 0, :, W - 1] = -0.97
+    d[1, 0, 20, 20] = -0.9700001
+    img = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    K = torch.tensor([[[577.87, 0.7, 319.5], [0, 571.3, 239.5], [0, 0, 1]],
+                      [[600.0, 0, 320.0], [0, 600.0, 240.0], [0, 0, 1]]], dtype=torch.float64)
+    crop = torch.tensor([[64, 64 + H, 100, 100 + W], [0, H, 5, 5 + W]])
+    out["d"], out["img"], out["K"], out["crop"] = d.numpy(), img.numpy(), K.numpy(), crop.numpy()
+    out["normals_old"] = rn.SurfaceNormals()(d).numpy()
+    out["normals_new"] = rn.SurfaceNormals_new()(d, K, crop).numpy()
+    out["tv"] = np.float64(rm.tv_loss(out_t := rn.SurfaceNormals()(d) * 100))
+    d2 = torch.rand(B, 1, 64, 96, generator=g) * 2 - 1
+    im2 = torch.rand(B, 3, 64, 96, generator=g) * 2 - 1
+    out["smooth_d"], out["smooth_img"] = d2.numpy(), im2.numpy()
+    out["smooth"] = np.float64(rm.get_smooth_weight(d2, im2, 3))
+    a = torch.rand(2, 3, 33, 47, generator=g)
+    b = (a + 0.1 * torch.randn(2, 3, 33, 47, generator=g)).clamp(0, 1)
+    out["ssim_a"], out["ssim_b"] = a.numpy(), b.numpy()
+    out["ssim"] = np.float64(rs.ssim(a, b))
+    # hole / valid masks exactly as main_model.py:208-230 computes them
+    one, zero = torch.tensor(1).float(), torch.tensor(0).float()
+    holl = torch.where(d <= -0.97, one, zero)
+    r = holl.clone()
+    r[:, :, :-1, :] += r[:, :, 1:, :].clone()
+    r[:, :, 1:, :] += r[:, :, :-1, :].clone()
+    r[:, :, :, :-1] += r[:, :, :, 1:].clone()
+    r[:, :, :, 1:] += r[:, :, :, :-1].clone()
+    out["hole"] = holl.numpy().astype(np.uint8)
+    out["valid"] = torch.where(r < 1, one, zero).numpy().astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ops.npz"), **out)
+    print("wrote ops")
+
+
+if __name__ == "__main__":
+    golden_ops()
+    golden_step()
