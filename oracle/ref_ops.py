@@ -145,7 +145,8 @@ def surface_normals_new(depth, K, crop, shift=0.5):
     ny = Zv * Xu - Zu * Xv
     nz = Xv * Yu - Xu * Yv
     n = torch.stack([nx, ny, nz], dim=1)
-    n = n / torch.sqrt((n * n).sum(dim=1, keepdim=True)).clamp_min(1e-12)
+    # F.normalize (norms.py:72): v / max(||v||_2, 1e-12); vector_norm has a zero sub-gradient at 0
+    n = n / torch.linalg.vector_norm(n, dim=1, keepdim=True).clamp_min(1e-12)
     return n.to(torch.float32)
 
 

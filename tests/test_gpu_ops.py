@@ -1,0 +1,334 @@
+"""GPU parity of every op of the C-ABI library against the oracle / a CPU fp32 torch reference,
+on seeded inputs.  Integer-valued work (masks) must be BIT-EXACT; floating point within the
+tolerance written at each assert.  Run on the B200 box: python -m pytest tests -m gpu."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_ops
+from util import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from dsr_b200 import ops as o
+    assert torch.cuda.is_available()
+    return o
+
+
+def G(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def cl(x):
+    """CPU NCHW tensor -> CUDA tensor with NHWC memory (what the nets pass around)."""
+    return x.cuda().contiguous(memory_format=torch.channels_last)
+
+
+# ---------------------------------------------------------------------------------------------
+# masks (bit-exact)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 1, 40, 56), (1, 1, 2, 2), (3, 1, 128, 128), (6, 1, 256, 256), (1, 1, 7, 301)])
+def test_hole_valid_masks_bit_exact(ops, shape):
+    d = torch.rand(shape, generator=G(1)) * 2 - 1
+    d[torch.rand(shape, generator=G(2)) < 0.07] = -1.0
+    d[0, 0, 0, 0] = -0.97
+    d[0, 0, -1, -1] = -0.9700001
+    hole_r, valid_r = ref_ops.hole_valid_masks(d)
+    hole, valid = ops.hole_valid_masks(d.cuda())
+    assert torch.equal(hole.cpu(), hole_r) and torch.equal(valid.cpu(), valid_r)
+
+
+def test_hole_valid_masks_golden_and_degenerate(ops):
+    g = load_golden("ops.npz")
+    hole, valid = ops.hole_valid_masks(torch.from_numpy(g["d"]).cuda())
+    assert np.array_equal(hole.cpu().numpy().astype(np.uint8), g["hole"])
+    assert np.array_equal(valid.cpu().numpy().astype(np.uint8), g["valid"])
+    for fill, v in ((-1.0, 0.0), (0.3, 1.0)):                  # all-hole / no-hole
+        d = torch.full((2, 1, 16, 24), fill)
+        hole, valid = ops.hole_valid_masks(d.cuda())
+        assert float(valid.min()) == v and float(valid.max()) == v and float(hole.max()) == 1.0 - v
+
+
+@pytest.mark.parametrize("stage,HW", [("train", (128, 128)), ("train", (256, 256)), ("test", (128, 160)), ("train", (512, 640))])
+def test_rect_holes_bit_exact(ops, stage, HW):
+    from dsr_b200 import main_model
+    H, W = HW
+    B = 3
+    d = torch.rand(B, 1, H, W, generator=G(3)) * 1.6 - 0.8
+    d[torch.rand(B, 1, H, W, generator=G(4)) < 0.05] = -1.0
+    _, valid = ref_ops.hole_valid_masks(d)
+    np.random.seed(11)
+    rects_o = ref_ops.draw_rects(B, H, W, stage)
+    np.random.seed(11)
+    rects, counts = main_model.draw_rects(B, H, W, stage)       # product host RNG == oracle RNG stream
+    for i in range(B):
+        assert counts[i] == len(rects_o[i]) and np.array_equal(rects[i, :counts[i]], rects_o[i])
+    gt_r = ref_ops.rect_gt_mask(valid, rects_o)
+    masked_r = ref_ops.apply_gt_mask(d, gt_r)
+    extra_r = ((masked_r < -0.97) | (gt_r < 0.1)).float()
+    gt, masked, extra = ops.rect_holes(valid.cuda(), d.cuda(), torch.from_numpy(rects).cuda(),
+                                       torch.from_numpy(counts).cuda(), main_model.MAX_RECTS, extra_border=-0.97)
+    assert torch.equal(gt.cpu().to(torch.int64), gt_r)
+    assert torch.equal(masked.cpu(), masked_r) and torch.equal(extra.cpu(), extra_r)
+    _, _, extra2 = ops.rect_holes(valid.cuda(), d.cuda(), torch.from_numpy(rects).cuda(),
+                                  torch.from_numpy(counts).cuda(), main_model.MAX_RECTS)
+    assert torch.equal(extra2.cpu(), torch.where(gt_r > 0.1, torch.tensor(0.0), torch.tensor(1.0)))
+
+
+# ---------------------------------------------------------------------------------------------
+# normals / tv / masked losses / smoothness / ssim
+# ---------------------------------------------------------------------------------------------
+def _smooth_depth(B, H, W, seed):
+    from oracle.ref_step import synthetic_batch
+    return synthetic_batch(B, H, W, seed=seed, depth_kind="smooth")["A_d"]
+
+
+@pytest.mark.parametrize("HW", [(40, 56), (128, 128), (2, 2)])
+def test_normals_old_fwd_bwd(ops, HW):
+    H, W = HW
+    d = (torch.rand(2, 1, H, W, generator=G(5)) * 1.8 - 0.9).requires_grad_(True)
+    go = torch.randn(2, 3, H, W, generator=G(6))
+    ref = ref_ops.surface_normals_old(d) * 100
+    (ref * go).sum().backward()
+    dc = d.detach().cuda().requires_grad_(True)
+    out = ops.normals_old(dc, 100.0)
+    (out * go.cuda()).sum().backward()
+    assert (out.cpu() - ref.detach()).abs().max() <= 1e-4            # values are O(100)
+    assert rel_l2(dc.grad.cpu(), d.grad) <= 1e-4
+
+
+def test_normals_new_fwd_bwd_golden(ops):
+    from dsr_b200.norms import SurfaceNormals_new, camera_table
+    g = load_golden("ops.npz")
+    d = torch.from_numpy(g["d"])
+    K, crop = torch.from_numpy(g["K"]), torch.from_numpy(g["crop"])
+    out = SurfaceNormals_new()(d.cuda(), K, crop)
+    assert (out.cpu().numpy() - g["normals_new"]).__abs__().max() <= 1e-6
+    # backward on a non-degenerate depth map
+    d2 = _smooth_depth(2, 48, 64, 9).clamp_min(-0.9).requires_grad_(True)
+    go = torch.randn(2, 3, 48, 64, generator=G(7))
+    crop2 = torch.tensor([[10, 58, 20, 84], [0, 48, 0, 64]])
+    (ref_ops.surface_normals_new(d2, K, crop2) * go).sum().backward()
+    dc = d2.detach().cuda().requires_grad_(True)
+    (ops.normals_new(dc, camera_table(K, crop2, 0.5, "cuda")) * go.cuda()).sum().backward()
+    assert np.allclose(dc.grad.cpu().numpy(), d2.grad.numpy(), rtol=2e-3, atol=1e-3 * float(d2.grad.abs().median()))
+
+
+def test_tv_fwd_bwd(ops):
+    x = torch.randn(2, 3, 37, 53, generator=G(8)).requires_grad_(True)
+    ref = ref_ops.tv_loss(x)
+    ref.backward()
+    xc = x.detach().cuda().requires_grad_(True)
+    out = ops.tv_loss(xc)
+    (out * 1.0).backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * float(ref)
+    assert rel_l2(xc.grad.cpu(), x.grad) <= 1e-6
+
+
+@pytest.mark.parametrize("C,two", [(1, False), (1, True), (3, True)])
+def test_masked_l1_l2_fwd_bwd(ops, C, two):
+    a = torch.randn(2, C, 33, 47, generator=G(9))
+    b = torch.randn(2, C, 33, 47, generator=G(10)).requires_grad_(True)
+    m1 = (torch.rand(2, 1, 33, 47, generator=G(11)) < 0.7).float()
+    m2 = (torch.rand(2, 1, 33, 47, generator=G(12)) < 0.5).float() if two else None
+    am, bm = (a * m1, b * m1) if m2 is None else (a * m1 * m2, b * m1 * m2)
+    l1, l2 = ref_ops.l1_mean(am, bm), ref_ops.mse_mean(am, bm)
+    (3 * l1 + 7 * l2).backward()
+    bc = b.detach().cuda().requires_grad_(True)
+    out = ops.masked_l1_l2(a.cuda(), bc, m1.cuda(), m2.cuda() if two else None)
+    (3 * out[0] + 7 * out[1]).backward()
+    assert abs(float(out[0]) - float(l1)) <= 1e-5 * float(l1) and abs(float(out[1]) - float(l2)) <= 1e-5 * float(l2)
+    assert rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("HW", [(64, 96), (128, 128), (256, 320)])
+def test_smooth_fwd_bwd(ops, HW):
+    H, W = HW
+    d = (torch.rand(2, 1, H, W, generator=G(13)) * 2 - 1).requires_grad_(True)
+    img = torch.rand(2, 3, H, W, generator=G(14)) * 2 - 1
+    ref = ref_ops.smooth_loss(d, img, 3)
+    ref.backward()
+    dc = d.detach().cuda().requires_grad_(True)
+    out = ops.smooth_loss(dc, img.cuda(), 3)
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 1e-3 * float(ref)         # north_star: each loss within 1e-3 relative
+    assert abs(float(out) - float(ref)) <= 2e-5 * float(ref)         # what fp32 actually achieves
+    assert rel_l2(dc.grad.cpu(), d.grad) <= 1e-3
+
+
+def test_smooth_golden(ops):
+    g = load_golden("ops.npz")
+    out = ops.smooth_loss(torch.from_numpy(g["smooth_d"]).cuda(), torch.from_numpy(g["smooth_img"]).cuda(), 3)
+    assert abs(float(out) - float(g["smooth"])) <= 2e-5 * float(g["smooth"])
+
+
+def test_ssim(ops):
+    g = load_golden("ops.npz")
+    out = ops.ssim(torch.from_numpy(g["ssim_a"]).cuda(), torch.from_numpy(g["ssim_b"]).cuda())
+    assert abs(float(out) - float(g["ssim"])) <= 1e-5
+    a = torch.rand(1, 1, 70, 100, generator=G(15))
+    assert abs(float(ops.ssim(a.cuda(), a.cuda())) - 1.0) <= 1e-5     # identity property
+    b = torch.rand(1, 1, 70, 100, generator=G(16))
+    assert abs(float(ops.ssim(a.cuda(), b.cuda())) - float(ref_ops.ssim(a, b))) <= 1e-5
+
+
+def test_masked_sums(ops):
+    d, p = torch.randn(2, 1, 31, 45, generator=G(17)), torch.randn(2, 1, 31, 45, generator=G(18))
+    m = (torch.rand(2, 1, 31, 45, generator=G(19)) < 0.6).float()
+    s = ops.masked_sums(d.cuda(), p.cuda(), m.cuda()).cpu()
+    ref = torch.stack([(d * m).double().sum(), (p * m).double().sum(), (d * m - p * m).abs().double().sum()])
+    assert torch.allclose(s, ref, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# network plumbing
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [1, 3, 32, 261])
+def test_layout_roundtrip(ops, C):
+    x = torch.randn(2, C, 19, 23, generator=G(20))
+    xh = ops.nhwc(x.cuda())                                           # NCHW-contiguous in -> transpose kernel
+    assert torch.equal(xh.cpu(), x.permute(0, 2, 3, 1).contiguous())
+    back = ops.planes(ops.nchw(xh))
+    assert torch.equal(back.cpu(), x)
+
+
+@pytest.mark.parametrize("mode,p", [("reflect", 3), ("reflect", 1), ("replicate", 3), ("replicate", 1), ("zeros", 2)])
+def test_pad_fwd_bwd(ops, mode, p):
+    x = torch.randn(2, 5, 9, 11, generator=G(21)).requires_grad_(True)
+    ref = F.pad(x, (p, p, p, p), mode={"zeros": "constant"}.get(mode, mode))
+    go = torch.randn(ref.shape, generator=G(22))
+    (ref * go).sum().backward()
+    xc = cl(x.detach()).requires_grad_(True)
+    out = ops.pad2d(xc, p, mode)
+    (out * go.cuda()).sum().backward()
+    assert torch.equal(out.cpu(), ref.detach())
+    assert torch.allclose(xc.grad.cpu(), x.grad, atol=1e-6)
+
+
+def test_activations_and_cat(ops):
+    x = torch.randn(2, 8, 7, 9, generator=G(23)).requires_grad_(True)
+    go = torch.randn(2, 8, 7, 9, generator=G(24))
+    for fn, ref_fn in ((ops.relu, F.relu), (lambda t: ops.leaky_relu(t, 0.2), lambda t: F.leaky_relu(t, 0.2)),
+                       (ops.tanh, torch.tanh)):
+        x.grad = None
+        r = ref_fn(x)
+        (r * go).sum().backward()
+        xc = cl(x.detach()).requires_grad_(True)
+        o = fn(xc)
+        (o * go.cuda()).sum().backward()
+        assert torch.allclose(o.cpu(), r.detach(), atol=1e-6) and torch.allclose(xc.grad.cpu(), x.grad, atol=1e-6)
+    a, b, c = (torch.randn(2, n, 5, 6, generator=G(25 + n)) for n in (128, 1, 3))
+    ac, bc, cc = cl(a).requires_grad_(True), cl(b), cl(c).requires_grad_(True)
+    o = ops.cat([ac, bc, cc])
+    assert torch.equal(o.cpu(), torch.cat([a, b, c], 1))
+    go = torch.randn(o.shape, generator=G(30))
+    (o * go.cuda()).sum().backward()
+    assert torch.equal(ac.grad.cpu(), go[:, :128]) and torch.equal(cc.grad.cpu(), go[:, 129:])
+
+
+@pytest.mark.parametrize("shape,act,res", [((2, 32, 16, 16), 1, False), ((3, 128, 8, 8), 0, True),
+                                           ((2, 512, 2, 2), 0, False), ((1, 64, 33, 17), 1, False)])
+def test_instance_norm_fwd_bwd(ops, shape, act, res):
+    x = (torch.randn(shape, generator=G(31)) * 2 + 0.5).requires_grad_(True)
+    r = torch.randn(shape, generator=G(32)).requires_grad_(True) if res else None
+    ref = F.instance_norm(x, eps=1e-5)
+    if act:
+        ref = F.relu(ref)
+    if res:
+        ref = ref + r
+    go = torch.randn(shape, generator=G(33))
+    (ref * go).sum().backward()
+    xc = cl(x.detach()).requires_grad_(True)
+    rc = cl(r.detach()).requires_grad_(True) if res else None
+    out = ops.instance_norm(xc, 1e-5, act, rc)
+    (out * go.cuda()).sum().backward()
+    assert torch.allclose(out.cpu(), ref.detach(), atol=2e-5)
+    assert rel_l2(xc.grad.cpu(), x.grad) <= 1e-4
+    if res:
+        assert torch.allclose(rc.grad.cpu(), r.grad, atol=1e-6)
+
+
+def test_group_norm_fwd(ops):
+    x = torch.randn(2, 64, 12, 10, generator=G(34)) * 3 + 1
+    w, b = torch.randn(64, generator=G(35)), torch.randn(64, generator=G(36))
+    ref = F.relu(F.group_norm(x, 8, w, b, eps=1e-5))
+    with torch.no_grad():
+        out = ops.group_norm(cl(x), 8, w.cuda(), b.cuda(), 1e-5, 1)
+    assert torch.allclose(out.cpu(), ref, atol=3e-5)
+    with pytest.raises(NotImplementedError):
+        ops.group_norm(cl(x).requires_grad_(True), 8, w.cuda(), b.cuda(), 1e-5, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# convolutions: every layer-shape class of the five nets, small spatial sizes
+# ---------------------------------------------------------------------------------------------
+CONV_CASES = [  # Cin, Cout, k, stride, pad, H, W
+    (3, 32, 7, 1, 0, 22, 22), (2, 32, 7, 1, 0, 22, 22), (32, 128, 7, 1, 0, 22, 22), (64, 1, 7, 1, 0, 22, 22),
+    (32, 64, 3, 2, 1, 16, 16), (128, 128, 3, 1, 0, 18, 18), (256, 256, 3, 1, 0, 10, 10),
+    (261, 64, 4, 2, 1, 16, 16), (128, 64, 4, 2, 1, 16, 16), (512, 512, 4, 2, 1, 4, 4), (512, 512, 4, 2, 1, 2, 2),
+    (1, 32, 7, 1, 0, 22, 22), (32, 64, 4, 2, 1, 18, 18),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fwd_bwd(ops, case):
+    Ci, Co, k, s, p, H, W = case
+    x = torch.randn(2, Ci, H, W, generator=G(40)).requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=G(41)) * 0.05).requires_grad_(True)
+    b = torch.randn(Co, generator=G(42)).requires_grad_(True)
+    ref = F.conv2d(x, w, b, stride=s, padding=p)
+    go = torch.randn(ref.shape, generator=G(43))
+    (ref * go).sum().backward()
+    xc, wc, bc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    out = ops.conv2d(xc, wc, bc, s, p)
+    (out * go.cuda()).sum().backward()
+    assert rel_l2(out.cpu(), ref.detach()) <= 1e-5
+    assert rel_l2(xc.grad.cpu(), x.grad) <= 1e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 1e-5
+    assert rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
+
+
+CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
+    (128, 64, 3, 2, 1, 1, 8, 8), (64, 32, 3, 2, 1, 1, 9, 7), (512, 512, 4, 2, 1, 0, 2, 2), (1024, 256, 4, 2, 1, 0, 4, 4),
+    (128, 1, 4, 2, 1, 0, 16, 16), (256, 128, 4, 2, 1, 0, 8, 8),
+]
+
+
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose2d_fwd_bwd(ops, case):
+    Ci, Co, k, s, p, op, H, W = case
+    x = torch.randn(2, Ci, H, W, generator=G(44)).requires_grad_(True)
+    w = (torch.randn(Ci, Co, k, k, generator=G(45)) * 0.05).requires_grad_(True)
+    b = torch.randn(Co, generator=G(46)).requires_grad_(True)
+    ref = torch.tanh(F.conv_transpose2d(x, w, b, stride=s, padding=p, output_padding=op))
+    go = torch.randn(ref.shape, generator=G(47))
+    (ref * go).sum().backward()
+    xc, wc, bc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    out = ops.conv_transpose2d(xc, wc, bc, s, p, op, act_out=ops.ACT_TANH)
+    (out * go.cuda()).sum().backward()
+    assert rel_l2(out.cpu(), ref.detach()) <= 1e-5
+    assert rel_l2(xc.grad.cpu(), x.grad) <= 2e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 2e-5
+    assert rel_l2(bc.grad.cpu(), b.grad) <= 2e-5
+
+
+def test_adam_matches_oracle(ops):
+    n = 1003
+    p, g = torch.randn(n, generator=G(50)), torch.randn(n, generator=G(51))
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, mc, vc = p.clone().cuda(), m.clone().cuda(), v.clone().cuda()
+    # arena slices are 16-byte aligned: allocate padded
+    for step in (1, 2, 3):
+        gs = g * step
+        ref_ops.adam_update(p, gs, m, v, step, 1e-4)
+        ops.adam_step(pc, gs.cuda(), mc, vc, 1e-4, step)
+    assert torch.allclose(pc.cpu(), p, atol=1e-7) and torch.allclose(vc.cpu(), v, rtol=1e-5, atol=1e-12)
+
+
+def test_cpu_tensor_raises(ops):
+    with pytest.raises(RuntimeError):
+        ops.hole_valid_masks(torch.zeros(1, 1, 4, 4))
+    with pytest.raises(RuntimeError):
+        ops.conv2d(torch.zeros(1, 3, 8, 8), torch.zeros(4, 3, 3, 3))

@@ -1,0 +1,148 @@
+"""GPU parity of the networks and of the whole optimize_parameters step, through the public API
+(define_G / define_Gen / MainModel.set_input / optimize_parameters), against (a) the golden vectors
+recorded from the live reference and (b) the oracle on the same seeded inputs and weights.
+Gates (BASELINE.json north_star): input-derived masks bit-exact; pred rel-L2 <= 1e-2; each loss within
+1e-3 relative; parameter gradients cosine >= 0.999."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_nets, ref_step
+from util import (build_host_model, cosine, grad_is_informative, load_golden, rehome, rel_l2, state_dicts)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model_and_oracle(built_lib):
+    host = build_host_model(2, 128, 128)
+    sds = state_dicts(host)
+    dev = rehome(host, host.opt, [0])
+    return dev, sds
+
+
+def test_networks_forward_match_oracle(built_lib):
+    from dsr_b200 import networks, translation_network
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(5)
+    torch.manual_seed(3)
+    res = networks.define_G(3, 128, 32, "resnet_6blocks", "instance", False, "normal", 0.02, [])
+    x = torch.rand(2, 3, 64, 48, generator=g) * 2 - 1
+    ref = ref_nets.resnet_generator(res.state_dict(), x)
+    with torch.no_grad():
+        out = res.cuda()(x.cuda())
+    assert rel_l2(out.cpu(), ref) <= 1e-4
+    unet = networks.define_G(128, 1, 64, "unet_128", "instance", False, "normal", 0.02, [])
+    f = torch.rand(1, 128, 128, 256, generator=g) * 2 - 1
+    ref = ref_nets.unet_generator(unet.state_dict(), f)
+    with torch.no_grad():
+        out = unet.cuda()(f.cuda())
+    assert rel_l2(out.cpu(), ref) <= 1e-4
+    o = SimpleNamespace(ngf_img=32, ngf_depth=32, ngf=64, norm="group", dropout=False, init_type="normal", gpu_ids=[],
+                        input_nc_img=3, n_downsampling=2, use_semantic=False, n_blocks=9, upsampling_type="transpose",
+                        output_nc_depth=1, input_nc_depth=1)
+    gen = translation_network.define_Gen(o, input_type="img_depth")
+    d = torch.rand(2, 1, 32, 48, generator=g) * 2 - 1
+    im = torch.rand(2, 3, 32, 48, generator=g) * 2 - 1
+    ref = ref_nets.translation_generator(gen.state_dict(), d, im)
+    with torch.no_grad():
+        out = gen.cuda()(d.cuda(), im.cuda())
+    assert rel_l2(out.cpu(), ref) <= 1e-4
+
+
+def _check_step(model, out_losses, ref_losses, tol):
+    for k, ref in ref_losses.items():
+        if k == "G":
+            v = float(model.loss_G)
+        elif k.startswith("mean_of_abs"):
+            v = float(getattr(model, "loss_" + k))
+        else:
+            v = out_losses[k]
+        assert abs(v - ref) <= tol * max(abs(ref), 1e-3), (k, v, ref)
+
+
+def test_step_matches_reference_golden_and_oracle(model_and_oracle):
+    model, sds = model_and_oracle
+    g = load_golden("step_b2_128.npz")
+    batch = ref_step.synthetic_batch(2, 128, 128, seed=1, depth_kind="smooth")
+    orc = ref_step.OracleStep(sds, lr=1e-4)
+    model._train()
+    np.random.seed(0)
+    rng_state = np.random.get_state()
+    for it in range(2):
+        np.random.set_state(rng_state)
+        ref = orc.step(batch)
+        np.random.set_state(rng_state)
+        model.set_input(batch)
+        model.optimize_parameters(it, 1)
+        rng_state = np.random.get_state()
+        p = f"s{it}/"
+        if it == 0:                                                   # integer / index work: bit-exact
+            for k in ("syn_mask", "real_mask", "real_hole_mask"):
+                assert np.array_equal(getattr(model, k).cpu().numpy().astype(np.uint8), g[p + k]), k
+            assert np.array_equal(model.gt_mask_real.cpu().numpy(), g[p + "gt_mask_real"])
+            assert np.array_equal(model.gt_mask_syn.cpu().numpy(), g[p + "gt_mask_syn"])
+        for k in ("syn2real_depth", "syn_depth_by_image", "real_depth_by_image", "pred_syn_depth", "pred_real_depth"):
+            assert rel_l2(getattr(model, k).detach().cpu(), g[p + k]) <= 1e-2, (k, it)          # the gate
+            assert rel_l2(getattr(model, k).detach().cpu(), ref["tensors"][k].detach()) <= 2e-3, (k, it)
+        losses = model.get_current_losses()
+        gold = {k[len(p) + 5:]: float(g[k]) for k in g.files if k.startswith(p + "loss/")}
+        _check_step(model, losses, gold, 1e-3 if it == 0 else 5e-3)
+        if it == 0:
+            _check_step(model, losses, ref["losses"], 1e-3)
+            # gradients (read from the arena views before Adam consumed them? Adam does not modify grads)
+            flat_a, flat_b, worst = [], [], 1.0
+            for net in ("Depth_f", "Task"):
+                params = dict(model._unwrap(getattr(model, "net" + net)).named_parameters())
+                for n, gr in ((n, ref["grads"][(net, n)]) for n in orc.sd[net]):
+                    mine = params[n].grad.detach().cpu()
+                    if grad_is_informative(net, n):
+                        c = cosine(mine, gr)
+                        worst = min(worst, c)
+                        assert c >= 0.999, (net, n, c)
+                        flat_a.append(mine.flatten()); flat_b.append(gr.flatten())
+                        if f"{p}gfull/{net}/{n}" in g.files:
+                            assert cosine(mine, g[f"{p}gfull/{net}/{n}"]) >= 0.999, (net, n)
+                    else:
+                        assert float(mine.norm()) <= 1e-2 * max(float(torch.cat(flat_b).norm()) if flat_b else 1.0, 1e-3)
+            assert cosine(torch.cat(flat_a), torch.cat(flat_b)) >= 0.999
+    # weights after two Adam steps
+    for net in ("Depth_f", "Task"):
+        params = dict(model._unwrap(getattr(model, "net" + net)).named_parameters())
+        a = torch.cat([params[n].detach().cpu().flatten() for n in orc.sd[net]])
+        b = torch.cat([orc.sd[net][n].detach().flatten() for n in orc.sd[net]])
+        assert rel_l2(a, b) <= 1e-3
+
+
+def test_calculate_eval_mode_and_visuals(model_and_oracle):
+    model, _ = model_and_oracle
+    batch = ref_step.synthetic_batch(2, 128, 128, seed=2, depth_kind="noise")
+    model.eval()
+    with torch.no_grad():
+        model.set_input(batch)
+        model.calculate("test")
+    vis = model.get_current_visuals()
+    for k in model.visual_names:
+        assert k in vis and torch.is_tensor(vis[k]) and vis[k].shape[0] == 2, k
+    # test stage: p = 0 -> no artificial holes: depth_masked == real_depth
+    assert torch.equal(model.depth_masked.cpu(), batch["B_d"])
+    assert all(np.isfinite(v) for v in model.get_current_losses().values())
+    model._train()
+
+
+def test_checkpoint_roundtrip(model_and_oracle, tmp_path):
+    model, sds = model_and_oracle
+    model.save_dir = str(tmp_path)
+    model.save_networks("latest")
+    for name in model.model_names:
+        sd = torch.load(str(tmp_path / f"latest_net_{name}.pth"), map_location="cpu")
+        assert list(sd.keys()) == list(sds[name].keys())
+        assert all(v.dtype == torch.float32 and v.device.type == "cpu" for v in sd.values())
+    before = {n: p.detach().clone() for n, p in model.netTask.named_parameters()}
+    with torch.no_grad():
+        for p in model.netTask.parameters():
+            p.add_(1.0)
+    model.load_networks("latest", strict=True)
+    for n, p in model.netTask.named_parameters():
+        assert torch.equal(p.detach(), before[n])
+    assert model.arena is not None and all(p.data_ptr() in model.arena.index for p in model.arena.params)
