@@ -1,0 +1,531 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Every convolution / transposed convolution of the five networks (models/networks.py:379-415,544-616;
+// models/translation_network.py:472-570) is brought to ONE GEMM form by the operand-preparation
+// kernel (which also fuses the preceding norm-apply + activation + padding, so the padded /
+// re-arranged bf16 operand is written exactly once):
+//
+//     out[n, h*os+ph, w*os+pw, co] = bias[co] + sum_{t < T} sum_{c < Ca}  A[n, h+ah+dr_t, w+aw+ds_t, c] * W[co][t*Ca + c]
+//
+//   A  : bf16 NHWC "arranged" activation [N][Ha][Wa][Ca], Ca % 64 == 0, already padded, optionally
+//        space-to-depth (stride-2 convs become 2x2 stride-1 taps over 4*C channels) or channel-paired
+//        (C = 32: two adjacent pixels side by side so one 128-byte swizzle row holds a full K block);
+//   W  : bf16 [Cout][T*Ca], K-major;  transposed convs run as 4 output phases (os = 2).
+//   Precision: `npass` = 1 (bf16), 2 (A = hi+lo), 3 (A and W = hi+lo, ~16-bit significands, what the
+//   parity gates need - SURVEY.md Appendix E); all passes accumulate into the same fp32 TMEM tile.
+//
+// Kernel structure (one 128 x BLOCK_N output tile per CTA, optional split-K over gridDim.z):
+//   warp 0   : TMA producer  - per K step: 4-D box loads of the A tile(s) (box = 64ch x TW x TH x TN
+//              pixels = 128 rows of 128 B, SWIZZLE_128B) and 2-D box loads of the W tile(s)
+//   warp 1   : TMEM allocator + MMA issuer - tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
+//              smem descriptors K-major SWIZZLE_128B; tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2-5: epilogue - tcgen05.ld 32x32b.x32 -> +bias -> (tanh) -> fp32 NHWC stores (or red.add for split-K)
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/dsr_b200.h"
+
+#define ST(s) ((cudaStream_t)(s))
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t gtimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap (-> launch error on the host), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    uint64_t t0 = gtimer();
+    while (!mbar_try(bar, parity)) {
+        if (gtimer() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 B = 64 bf16; 8-row atoms of
+// 1024 B): start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) = 1024>>4,
+// version 1 [46,48), layout SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM kernel
+// ------------------------------------------------------------------------------------------------
+#define TC_MAX_TAPS 64
+struct TcParams {
+    int N, Ht, Wt;            // tile-space output grid (per phase)
+    int TW, TH, TN;           // tile = TN x TH x TW pixels = 128 rows
+    int tiles_w, tiles_h;     // tile counts along w / h (tiles_n = gridDim.x / (tiles_w * tiles_h))
+    int Ca, T;                // arranged channels, taps
+    int ah, aw;               // A coordinate offsets
+    int Ho, Wo, Cout, os, ph, pw;   // output tensor geometry
+    int act, ksteps_per_split, ksteps;
+    signed char dr[TC_MAX_TAPS], ds[TC_MAX_TAPS];
+};
+
+template <int BLOCK_N, int NPASS>
+struct TcCfg {
+    static constexpr int A_TILE = 128 * 128;                 // 128 rows x 128 B
+    static constexpr int W_TILE = BLOCK_N * 128;
+    static constexpr int NA = NPASS >= 2 ? 2 : 1;
+    static constexpr int NW = NPASS >= 3 ? 2 : 1;
+    static constexpr int STAGE = NA * A_TILE + NW * W_TILE;
+    static constexpr int STAGES = (200 * 1024 / STAGE) > 8 ? 8 : (200 * 1024 / STAGE);
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+template <int BLOCK_N, int NPASS>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+               const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+               const __grid_constant__ TcParams p, const float* __restrict__ bias, float* __restrict__ out) {
+    using Cfg = TcCfg<BLOCK_N, NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE;    // full[S], empty[S], tmem_full, tmem_ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::STAGES + 1);
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE + 8 * (2 * Cfg::STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int tile = blockIdx.x;
+    const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+    const int n0 = tile * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+    const int co0 = blockIdx.y * BLOCK_N;
+    const int kb = blockIdx.z * p.ksteps_per_split;
+    int ke = kb + p.ksteps_per_split;
+    if (ke > p.ksteps) ke = p.ksteps;
+    const int nk = ke - kb;
+    const int cblocks = p.Ca >> 6;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA_hi); tma_prefetch_desc(&mapW_hi);
+        if (NPASS >= 2) tma_prefetch_desc(&mapA_lo);
+        if (NPASS >= 3) tma_prefetch_desc(&mapW_lo);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+                mbar_wait(empty_bar(s), (it & 1) ^ 1);
+                const int k = kb + i;
+                const int t = k / cblocks, cb = k - t * cblocks;
+                const int ca = cb << 6;
+                const int hc = h0 + p.ah + p.dr[t], wc = w0 + p.aw + p.ds[t];
+                const uint32_t st = smem_base + s * Cfg::STAGE;
+                mbar_expect_tx(full_bar(s), Cfg::STAGE);
+                tma_load_4d(st, &mapA_hi, full_bar(s), ca, wc, hc, n0);
+                if (NPASS >= 2) tma_load_4d(st + Cfg::A_TILE, &mapA_lo, full_bar(s), ca, wc, hc, n0);
+                const int kw = t * p.Ca + ca;
+                tma_load_2d(st + Cfg::NA * Cfg::A_TILE, &mapW_hi, full_bar(s), kw, co0);
+                if (NPASS >= 3) tma_load_2d(st + Cfg::NA * Cfg::A_TILE + Cfg::W_TILE, &mapW_lo, full_bar(s), kw, co0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N);
+            uint32_t accum = 0;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+                mbar_wait(full_bar(s), it & 1);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * Cfg::STAGE;
+                const uint32_t a_hi = st, a_lo = st + Cfg::A_TILE;
+                const uint32_t w_hi = st + Cfg::NA * Cfg::A_TILE, w_lo = w_hi + Cfg::W_TILE;
+#pragma unroll
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const uint32_t a = (pass == 1) ? a_lo : a_hi;
+                    const uint32_t w = (pass == 2) ? w_lo : w_hi;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        tc_mma_bf16(tmem_acc, make_sdesc(a + kk * 32), make_sdesc(w + kk * 32), idesc, accum);
+                        accum = 1;
+                    }
+                }
+                tc_commit(empty_bar(s));            // frees this smem stage when the MMAs above retire
+            }
+            tc_commit(tmem_full_bar);               // accumulator complete -> epilogue
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+        const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+        const bool valid = (n < p.N) && (h < p.Ht) && (w < p.Wt);
+        float* orow = out + ((((long)n * p.Ho + (long)h * p.os + p.ph) * p.Wo) + (long)w * p.os + p.pw) * p.Cout;
+        if (nk > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+        }
+        const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+        const bool split = gridDim.z > 1;
+        constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            if (nk > 0) {
+                if (CH == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+                tc_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = 0u;
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int co = co0 + c0 + j;
+                    if (co < p.Cout) {
+                        float f = __uint_as_float(v[j]);
+                        if (add_bias) f += __ldg(bias + co);
+                        if (split) atomicAdd(orow + co, f);
+                        else {
+                            if (p.act == DSR_ACT_TANH) f = tanhf(f);
+                            v[j] = __float_as_uint(f);
+                        }
+                    }
+                }
+                if (!split) {
+                    if ((p.Cout & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < CH; j += 4) {
+                            const int co = co0 + c0 + j;
+                            if (co < p.Cout)
+                                *reinterpret_cast<uint4*>(orow + co) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const int co = co0 + c0 + j;
+                            if (co < p.Cout) orow[co] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation: fp32 NHWC -> arranged bf16 hi (+lo), fusing norm-apply + activation + padding
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int prep_pad_src(int q, int p, int n, int mode) {
+    int i = q - p;
+    if (i >= 0 && i < n) return i;
+    if (mode == DSR_PAD_ZERO) return -1;
+    if (mode == DSR_PAD_REFLECT) { i = i < 0 ? -i : 2 * (n - 1) - i; return (i >= 0 && i < n) ? i : -1; }
+    return i < 0 ? 0 : n - 1;
+}
+// one thread = 8 consecutive arranged channels (one 16-byte store per output tensor)
+__global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm,
+                               int act, float slope, int pad, int mode, int layout, int Cp,
+                               __nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo, int Ha, int Wa, int Ca) {
+    const int cg_per_pix = Ca >> 3;
+    const long total = (long)N * Ha * Wa * cg_per_pix;
+    const long NC = (long)N * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % cg_per_pix);
+        long t = idx / cg_per_pix;
+        const int wa = (int)(t % Wa); t /= Wa;
+        const int ha = (int)(t % Ha);
+        const int n = (int)(t / Ha);
+        const int q = cg << 3;
+        int c, qi, qj;       // source channel start, padded-space row / col
+        if (layout == DSR_TC_LAYOUT_NORMAL) { c = q; qi = ha; qj = wa; }
+        else if (layout == DSR_TC_LAYOUT_PAIR) { c = q % Cp; qi = ha; qj = wa + q / Cp; }
+        else { const int ab = q / Cp; c = q - ab * Cp; qi = 2 * ha + (ab >> 1); qj = 2 * wa + (ab & 1); }
+        const int Hq = H + 2 * pad, Wq = W + 2 * pad;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (qi < Hq && qj < Wq && c < C) {
+            const int i = prep_pad_src(qi, pad, H, mode), j = prep_pad_src(qj, pad, W, mode);
+            if (i >= 0 && j >= 0) {
+                const float* src = x + (((long)n * H + i) * W + j) * C + c;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (c + e < C) {
+                        float f = src[e];
+                        if (prm) {
+                            const long k = (long)n * C + c + e;
+                            f = (f - prm[k]) * prm[NC + k] + prm[2 * NC + k];
+                        }
+                        if (act == DSR_ACT_RELU) f = f > 0.f ? f : 0.f;
+                        else if (act == DSR_ACT_LRELU) f = f > 0.f ? f : slope * f;
+                        v[e] = f;
+                    }
+                }
+            }
+        }
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            hi[e] = __float2bfloat16_rn(v[e]);
+            lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+        }
+        const long o = (((long)n * Ha + ha) * Wa + wa) * Ca + q;
+        *reinterpret_cast<uint4*>(Ahi + o) = *reinterpret_cast<const uint4*>(hi);
+        if (Alo) *reinterpret_cast<uint4*>(Alo + o) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: 4-D fp32 parameter -> bf16 hi (+lo) [Cout][T*Ca], K-major
+//   variant CONV     : Conv2d weight (Cout, Cin, R, S); tap t = r*S + s, channel c          (stride 1)
+//   variant CONV_PAIR: as CONV with Ca = 2*Cp: tap t = r*ceil(S/2) + s2, q = (s&1)*Cp + c
+//   variant CONV_S2D : stride-2 conv (k <= 4) as 2x2 taps over 4*Cp channels: r = 2r'+a, s = 2s'+b
+//   variant CONVT_PH : ConvTranspose2d weight (Cin, Cout, R, S), stride 2, phase (a,b): taps (dr,ds) in {0,1}^2,
+//                      kh = pad + 2 - a - 2*dr, kw = pad + 2 - b - 2*ds (zero tap when outside the kernel)
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S, int variant, int Cp,
+                                      int pa, int pb, int pad, int Cout, int T, int Ca,
+                                      __nv_bfloat16* __restrict__ Whi, __nv_bfloat16* __restrict__ Wlo) {
+    const long K = (long)T * Ca, total = (long)Cout * K;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int co = (int)(idx / K);
+        const long k = idx - (long)co * K;
+        const int t = (int)(k / Ca), q = (int)(k - (long)t * Ca);
+        int r = -1, s = -1, c = -1;
+        if (variant == DSR_TC_W_CONV) { r = t / S; s = t - r * S; c = q; }
+        else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; r = t / S2; s = 2 * (t - r * S2) + q / Cp; c = q % Cp; }
+        else if (variant == DSR_TC_W_CONV_S2D) { const int ab = q / Cp; c = q - ab * Cp; r = 2 * (t >> 1) + (ab >> 1); s = 2 * (t & 1) + (ab & 1); }
+        else { c = q; r = pad + 2 - pa - 2 * (t >> 1); s = pad + 2 - pb - 2 * (t & 1); }
+        float v = 0.f;
+        const bool convT = (variant == DSR_TC_W_CONVT_PH);
+        const int Cin = convT ? D0 : D1;
+        if (r >= 0 && r < R && s >= 0 && s < S && c >= 0 && c < Cin)
+            v = convT ? w[(((long)c * D1 + co) * R + r) * S + s] : w[(((long)co * D1 + c) * R + r) * S + s];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        Whi[idx] = h;
+        if (Wlo) Wlo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { dsr_set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DSR_ERR_CUDA; }
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dsr_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return DSR_ERR_CUDA; }
+    return DSR_OK;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+template <int BLOCK_N, int NPASS>
+static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                     const TcParams& p, const float* bias, float* out, dim3 grid, cudaStream_t st) {
+    using Cfg = TcCfg<BLOCK_N, NPASS>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
+            dsr_set_error("conv_tc: cannot raise dynamic shared memory to %d", Cfg::SMEM);
+            return DSR_ERR_CUDA;
+        }
+        attr = true;
+    }
+    conv_tc_kernel<BLOCK_N, NPASS><<<grid, 192, Cfg::SMEM, st>>>(ah, al, wh, wl, p, bias, out);
+    return dsr_check_launch("conv_tc");
+}
+
+template <int NPASS>
+static int dispatch_n(int bn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                      const TcParams& p, const float* bias, float* out, dim3 grid, cudaStream_t st) {
+    switch (bn) {
+        case 16: return launch_tc<16, NPASS>(ah, al, wh, wl, p, bias, out, grid, st);
+        case 32: return launch_tc<32, NPASS>(ah, al, wh, wl, p, bias, out, grid, st);
+        case 64: return launch_tc<64, NPASS>(ah, al, wh, wl, p, bias, out, grid, st);
+        case 128: return launch_tc<128, NPASS>(ah, al, wh, wl, p, bias, out, grid, st);
+        case 256: return launch_tc<256, NPASS>(ah, al, wh, wl, p, bias, out, grid, st);
+    }
+    dsr_set_error("conv_tc: unsupported BLOCK_N %d", bn);
+    return DSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
+                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, void* stream) {
+    DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
+    DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
+    DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
+    DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_PAIR && Ca == 2 * Cp) ||
+                    (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
+    DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15), "operand buffers must be 16-byte aligned");
+    long total = (long)N * Ha * Wa * (Ca / 8);
+    tc_prep_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
+                                                                (__nv_bfloat16*)A_hi, (__nv_bfloat16*)A_lo, Ha, Wa, Ca);
+    return dsr_check_launch("tc_prep");
+}
+
+extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,
+                                  int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, void* stream) {
+    DSR_REQUIRE(w && W_hi && T > 0 && (Ca & 63) == 0, "bad arguments");
+    long total = (long)Cout * T * Ca;
+    tc_pack_weight_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(w, D0, D1, R, S, variant, Cp, phase_a, phase_b, pad, Cout, T,
+                                                                       Ca, (__nv_bfloat16*)W_hi, (__nv_bfloat16*)W_lo);
+    return dsr_check_launch("tc_pack_weight");
+}
+
+extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
+                           int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
+                           const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                           int split_k, void* stream) {
+    DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
+    DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
+    DSR_REQUIRE(T >= 1 && T <= TC_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
+    DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)W_hi & 15) && !((uintptr_t)out & 15), "buffers must be 16-byte aligned");
+    TcParams p;
+    p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.ah = a_off_h; p.aw = a_off_w;
+    p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.os = os; p.ph = ph; p.pw = pw; p.act = act;
+    for (int t = 0; t < T; ++t) { p.dr[t] = (signed char)tap_dr[t]; p.ds[t] = (signed char)tap_ds[t]; }
+    // tile shape: TW x TH x TN = 128 rows
+    int TW = Wt >= 16 ? 16 : pow2_ceil(Wt);
+    int TH = 128 / TW;
+    if (TH > pow2_ceil(Ht)) TH = pow2_ceil(Ht);
+    int TN = 128 / (TW * TH);
+    p.TW = TW; p.TH = TH; p.TN = TN;
+    p.tiles_w = dsr_cdiv(Wt, TW); p.tiles_h = dsr_cdiv(Ht, TH);
+    int tiles_n = dsr_cdiv(N, TN);
+    int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : (Cout > 16 ? 32 : 16)));
+    if (npass == 3 && bn == 256) bn = 128;          // keep >= 2 pipeline stages in 200 KB of smem
+    int tiles_co = dsr_cdiv(Cout, bn);
+    p.ksteps = T * (Ca / 64);
+    long ctas = (long)p.tiles_w * p.tiles_h * tiles_n * tiles_co;
+    int splits = 1;
+    if (split_k < 0) {              // auto: only when the grid would leave most SMs idle
+        if (ctas * 2 <= dsr_num_sms() && p.ksteps >= 16) {
+            splits = (int)(dsr_num_sms() / ctas);
+            if (splits > p.ksteps / 4) splits = p.ksteps / 4;
+            if (splits < 1) splits = 1;
+        }
+    } else if (split_k > 1) splits = split_k;
+    if (splits > 1 && act != DSR_ACT_NONE) splits = 1;
+    p.ksteps_per_split = dsr_cdiv(p.ksteps, splits);
+    splits = dsr_cdiv(p.ksteps, p.ksteps_per_split);
+    if (splits > 1) {
+        if (cudaMemsetAsync(out, 0, (size_t)N * Ho * Wo * Cout * sizeof(float), ST(stream)) != cudaSuccess) {
+            dsr_set_error("conv_tc: memset failed"); return DSR_ERR_CUDA;
+        }
+        DSR_REQUIRE(os == 1, "split-K with output phases would zero the other phases");
+    }
+    CUtensorMap mah, mal, mwh, mwl;
+    cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
+    cuuint64_t astr[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)Wa * Ca * 2, (cuuint64_t)Ha * Wa * Ca * 2};
+    cuuint32_t abox[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    int rc = encode_map(&mah, A_hi, 4, adims, astr, abox);
+    if (rc) return rc;
+    mal = mah;
+    if (npass >= 2 && (rc = encode_map(&mal, A_lo, 4, adims, astr, abox))) return rc;
+    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout};
+    cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
+    if ((rc = encode_map(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;
+    mwl = mwh;
+    if (npass >= 3 && (rc = encode_map(&mwl, W_lo, 2, wdims, wstr, wbox))) return rc;
+    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)tiles_co, (unsigned)splits);
+    if (npass == 1) return dispatch_n<1>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
+    if (npass == 2) return dispatch_n<2>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
+    return dispatch_n<3>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
+}

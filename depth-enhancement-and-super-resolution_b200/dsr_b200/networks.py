@@ -29,14 +29,17 @@ class Identity(nn.Module):                        # networks.py:13-15
 class Conv2d(nn.Conv2d):
     """nn.Conv2d with zeros / reflect / replicate ``padding_mode`` (networks.py:379; translation_network.py:472)."""
 
-    def forward(self, x, act_out=ops.ACT_NONE):
+    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None):
+        """pre_pad = (pad, mode) of an nn.ReflectionPad2d / ReplicationPad2d module placed right before
+        this conv: it is folded into the conv's operand preparation instead of materialising a padded copy."""
         if self.dilation != (1, 1) or self.groups != 1:
             raise NotImplementedError("dsr_b200.Conv2d: dilation/groups are not on the hot path")
-        p = self.padding[0]
-        if self.padding_mode != "zeros" and p > 0:
-            x = ops.pad2d(x, p, self.padding_mode)
-            p = 0
-        return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out)
+        p, mode = self.padding[0], self.padding_mode
+        if pre_pad is not None:
+            if p != 0:
+                raise NotImplementedError("dsr_b200.Conv2d: explicit pad module followed by a padded conv")
+            p, mode = pre_pad
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):        # networks.py:406, :553
@@ -92,6 +95,15 @@ def run_fused(mods, x):
         if isinstance(m, (InstanceNorm2d, GroupNorm)) and isinstance(nxt, ReLU):
             x = m(x, act=ops.ACT_RELU)
             i += 2
+        elif isinstance(m, (ReflectionPad2d, ReplicationPad2d)) and isinstance(nxt, Conv2d) and nxt.padding[0] == 0:
+            mode = "reflect" if isinstance(m, ReflectionPad2d) else "replicate"
+            nn2 = mods[i + 2] if i + 2 < len(mods) else None
+            if isinstance(nn2, Tanh):
+                x = nxt(x, act_out=ops.ACT_TANH, pre_pad=(m.padding[0], mode))
+                i += 3
+            else:
+                x = nxt(x, pre_pad=(m.padding[0], mode))
+                i += 2
         elif isinstance(m, (Conv2d, ConvTranspose2d)) and isinstance(nxt, Tanh):
             x = m(x, act_out=ops.ACT_TANH)
             i += 2

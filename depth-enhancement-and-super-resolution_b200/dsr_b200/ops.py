@@ -130,22 +130,142 @@ def _weight_grad(dwk, weight, kdim):
     return gw
 
 
+# ------------------------------------------------------------------------------------------------
+# tcgen05 engine (csrc/conv_tc.cu): operand preparation + weight packing + implicit GEMM
+# ------------------------------------------------------------------------------------------------
+CONFIG = {
+    "engine": "tc",      # "tc": tcgen05 implicit GEMM wherever the layer shape allows; "simt": fp32 CUDA cores only
+    "passes": 3,         # 1 = bf16, 2 = activations hi+lo, 3 = activations and weights hi+lo (parity mode)
+    "split_k": -1,       # -1 = automatic split-K for tiny-M layers
+}
+WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
+_PACK_CACHE = {}
+_LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
+_W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH = 0, 1, 2, 3
+
+
+def _rup(v, m):
+    return (v + m - 1) // m * m
+
+
+def _int_array(vals):
+    import ctypes
+    return (ctypes.c_int * len(vals))(*vals)
+
+
+def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W):
+    """Which arranged-operand layout serves this layer on the tcgen05 path (None -> CUDA-core path)."""
+    if CONFIG["engine"] != "tc" or R != S:
+        return None
+    if kind == "conv" and stride == 1 and R * S <= 64 and Ci >= 32:
+        if Ci == 32:
+            return dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=32, Ca=64, T=R * ((S + 1) // 2))
+        return dict(layout=_LAYOUT_NORMAL, variant=_W_CONV, Cp=_rup(Ci, 8), Ca=_rup(Ci, 64), T=R * S)
+    if kind == "conv" and stride == 2 and R in (3, 4) and pad == 1 and H % 2 == 0 and W % 2 == 0 and Ci >= 16:
+        Cp = _rup(Ci, 16)
+        return dict(layout=_LAYOUT_S2D, variant=_W_CONV_S2D, Cp=Cp, Ca=4 * Cp, T=4)
+    if kind == "convT" and stride == 2 and pad == 1 and ((R == 4 and opad == 0) or (R == 3 and opad == 1)) and Ci >= 32:
+        return dict(layout=_LAYOUT_NORMAL, variant=_W_CONVT_PH, Cp=_rup(Ci, 8), Ca=_rup(Ci, 64), T=4)
+    return None
+
+
+def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0):
+    """bf16 hi/lo packed copy of a parameter, cached until the parameter changes."""
+    npass = CONFIG["passes"]
+    epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
+    key = (weight.data_ptr(), weight._version, epoch, plan["variant"], plan["Ca"], phase, npass >= 3)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    for k in [k for k in _PACK_CACHE if k[0] == key[0] and k[3:6] == key[3:6]]:
+        del _PACK_CACHE[k]
+    D0, D1, R, S = weight.shape
+    w = weight.detach()
+    w = w if w.is_contiguous() else w.contiguous()
+    K = plan["T"] * plan["Ca"]
+    whi = torch.empty((Co, K), device=w.device, dtype=torch.bfloat16)
+    wlo = torch.empty((Co, K), device=w.device, dtype=torch.bfloat16) if npass >= 3 else None
+    _call("dsr_tc_pack_weight", _p(w), D0, D1, R, S, plan["variant"], plan["Cp"], phase[0], phase[1], pad, Co,
+          plan["T"], plan["Ca"], _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16))
+    _PACK_CACHE[key] = (whi, wlo)
+    return whi, wlo
+
+
+def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0):
+    """fp32 NHWC -> arranged bf16 hi(+lo) operand."""
+    N, H, W, C = xh.shape
+    Hq, Wq = H + 2 * pad, W + 2 * pad
+    if plan["layout"] == _LAYOUT_S2D:
+        Ha, Wa = (Hq + 1) // 2, (Wq + 1) // 2
+    else:
+        Ha, Wa = Hq, Wq
+    Ca = plan["Ca"]
+    ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
+    alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if CONFIG["passes"] >= 2 else None
+    _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
+          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca)
+    return ahi, alo, Ha, Wa
+
+
+def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo):
+    N, H, W, Ci = xh.shape
+    Co, _, R, S = weight.shape
+    ahi, alo, Ha, Wa = _tc_prep(xh, plan, pad, pad_mode)
+    whi, wlo = _tc_weights(weight, plan, Co)
+    if plan["layout"] == _LAYOUT_PAIR:
+        S2 = (S + 1) // 2
+        dr = [t // S2 for t in range(plan["T"])]
+        ds = [2 * (t % S2) for t in range(plan["T"])]
+    elif plan["layout"] == _LAYOUT_S2D:
+        dr, ds = [0, 0, 1, 1], [0, 1, 0, 1]
+    else:
+        dr = [t // S for t in range(R * S)]
+        ds = [t % S for t in range(R * S)]
+    y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
+    _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
+          _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0,
+          Ho, Wo, _p(bias), _p(y), Ho, Wo, 1, 0, 0, act_out, CONFIG["passes"], CONFIG["split_k"])
+    return y
+
+
+def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo):
+    N, H, W, Ci = xh.shape
+    _, Co, R, S = weight.shape
+    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO)              # zero halo of 1 around the input
+    y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
+    dr, ds = _int_array([0, 0, 1, 1]), _int_array([0, 1, 0, 1])
+    for a in (0, 1):
+        for b in (0, 1):
+            whi, wlo = _tc_weights(weight, plan, Co, phase=(a, b), pad=pad)
+            _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
+                  _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, 4, dr, ds, a, b, H, W, _p(bias), _p(y),
+                  Ho, Wo, 2, a, b, act_out, CONFIG["passes"], 1)
+    return y
+
+
 class _Conv2d(Function):
-    """nn.Conv2d (zero padding; explicit pads are a separate op).  networks.py:379,385,414,453,544."""
+    """nn.Conv2d with zeros / reflect / replicate padding.  networks.py:378-379,385,413-414,453,544;
+    translation_network.py:472,478,495,563."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, act_out):
+    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out):
         xh = nhwc(x)
         N, H, W, Ci = xh.shape
         Co, Ci2, R, S = weight.shape
         if Ci2 != Ci:
             raise ValueError(f"conv2d: input has {Ci} channels, weight expects {Ci2}")
         Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
-        y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
-        wk = _pack(weight, 1)
         b = bias.detach() if bias is not None else None
-        _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 0, act_out)
-        ctx.cfg = (stride, pad, act_out, bias is not None)
+        plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
+        if plan is not None:
+            y = _tc_conv_fwd(xh, weight.detach(), b, plan, stride, pad, pad_mode, act_out, Ho, Wo)
+        else:
+            xp, p = _explicit_pad(xh, pad, pad_mode)
+            y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+            wk = _pack(weight, 1)
+            _call("dsr_conv_simt", _p(xp), _p(wk), _p(b), _p(y), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
+                  stride, p, 0, act_out)
+        ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None)
         ctx.bias_ref = bias
         ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
         return nchw(y)
@@ -153,7 +273,7 @@ class _Conv2d(Function):
     @staticmethod
     def backward(ctx, gy):
         xh, weight, y = ctx.saved_tensors
-        stride, pad, act_out, has_bias = ctx.cfg
+        stride, pad, pad_mode, act_out, has_bias = ctx.cfg
         N, H, W, Ci = xh.shape
         Co, _, R, S = weight.shape
         g = nhwc(gy)
@@ -162,19 +282,35 @@ class _Conv2d(Function):
             g2 = torch.empty_like(g)
             _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
             g = g2
+        xp, p = _explicit_pad(xh, pad, pad_mode)                    # recomputed, not stored
+        Hp, Wp = xp.shape[1], xp.shape[2]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wk = _pack(weight, 0)                       # [(r,s,co)][ci]
-            gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
-            _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 1, ACT_NONE)
-            gx = nchw(gxh)
+            wk = _pack(weight, 0)                                   # [(r,s,co)][ci]
+            gxp = torch.empty((N, Hp, Wp, Ci), device=g.device, dtype=torch.float32)
+            _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxp), N, Ho, Wo, Co, Hp, Wp, Ci, R, S, stride, p, 1, ACT_NONE)
+            if xp is not xh:
+                gxh = torch.empty_like(xh)
+                _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
+                gxp = gxh
+            gx = nchw(gxp)
         if ctx.needs_input_grad[1]:
             dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
-            _call("dsr_wgrad_simt", _p(xh), _p(g), _p(dwk), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad)
+            _call("dsr_wgrad_simt", _p(xp), _p(g), _p(dwk), N, Hp, Wp, Ci, Ho, Wo, Co, R, S, stride, p)
             gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
+
+
+def _explicit_pad(xh, pad, pad_mode):
+    """materialise a non-zero padding mode for the CUDA-core path; zero padding stays implicit."""
+    if pad == 0 or pad_mode == PAD_ZERO:
+        return xh, pad
+    N, H, W, C = xh.shape
+    xp = torch.empty((N, H + 2 * pad, W + 2 * pad, C), device=xh.device, dtype=torch.float32)
+    _call("dsr_pad2d_fwd", _p(xh), _p(xp), N, H, W, C, pad, pad_mode)
+    return xp, 0
 
 
 class _ConvTranspose2d(Function):
@@ -188,10 +324,14 @@ class _ConvTranspose2d(Function):
         if Ci2 != Ci:
             raise ValueError(f"conv_transpose2d: input has {Ci} channels, weight expects {Ci2}")
         Ho, Wo = (H - 1) * stride - 2 * pad + R + opad, (W - 1) * stride - 2 * pad + S + opad
-        y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
-        wk = _pack(weight, 0)                           # [(r,s,ci)][co]
         b = bias.detach() if bias is not None else None
-        _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, act_out)
+        plan = tc_conv_plan("convT", Ci, Co, R, S, stride, pad, opad, H, W)
+        if plan is not None:
+            y = _tc_convT_fwd(xh, weight.detach(), b, plan, pad, act_out, Ho, Wo)
+        else:
+            y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+            wk = _pack(weight, 0)                       # [(r,s,ci)][co]
+            _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, act_out)
         ctx.cfg = (stride, pad, act_out, bias is not None)
         ctx.bias_ref = bias
         ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
@@ -224,8 +364,9 @@ class _ConvTranspose2d(Function):
         return gx, gw, gb, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE):
-    return _Conv2d.apply(x, weight, bias, stride, padding, act_out)
+def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO):
+    pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
+    return _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out)
 
 
 def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE):

@@ -120,6 +120,32 @@ int dsr_conv_simt(const float* G, const float* Wk, const float* bias, float* out
 int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, int Wg, int Cg, int Ho, int Wo, int Cd,
                    int R, int S, int stride, int pad, void* stream);
 
+/* tcgen05 / TMEM / TMA implicit GEMM (csrc/conv_tc.cu).  Three calls per convolution:
+ *   dsr_tc_prep        fp32 NHWC activation -> arranged bf16 hi(+lo) operand [N][Ha][Wa][Ca]; fuses the preceding
+ *                      norm-apply (prm = (mean, scale, shift) or NULL), ReLU / LeakyReLU, and the padding
+ *                      (nn.ReflectionPad2d / padding_mode='replicate' / zeros).  layout: NORMAL (Ca >= Cp >= C),
+ *                      PAIR (C = 32: pixel w and w+1 side by side, Ca = 2*Cp), S2D (space-to-depth of the padded
+ *                      input for stride-2 convs, Ca = 4*Cp).
+ *   dsr_tc_pack_weight 4-D fp32 parameter -> bf16 hi(+lo) [Cout][T*Ca] K-major for the matching variant.
+ *   dsr_tc_gemm        out[n, h*os+ph, w*os+pw, co] = bias[co] + sum_t sum_c A[n, h+ah+dr[t], w+aw+ds[t], c] W[co][t*Ca+c]
+ *                      npass 1 = bf16, 2 = A hi+lo, 3 = A and W hi+lo (fp32-class products); tap tables are HOST arrays;
+ *                      split_k: 1 = off, -1 = auto (tiny-M layers), >1 = that many K splits (out must not alias). */
+#define DSR_TC_LAYOUT_NORMAL 0
+#define DSR_TC_LAYOUT_PAIR 1
+#define DSR_TC_LAYOUT_S2D 2
+#define DSR_TC_W_CONV 0
+#define DSR_TC_W_CONV_PAIR 1
+#define DSR_TC_W_CONV_S2D 2
+#define DSR_TC_W_CONVT_PH 3
+int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
+                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, void* stream);
+int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,
+                       int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, void* stream);
+int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
+                int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
+                const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                int split_k, void* stream);
+
 /* ---- optimizer ------------------------------------------------------------------------------- */
 /* torch.optim.Adam (defaults) over one flat arena.  models/main_model.py:176, :429. */
 int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,

@@ -274,9 +274,21 @@ CONV_CASES = [  # Cin, Cout, k, stride, pad, H, W
 ]
 
 
+ENGINES = [("simt", 3, 1e-5), ("tc", 3, 3e-5), ("tc", 2, 4e-3), ("tc", 1, 8e-3)]
+
+
+@pytest.fixture(params=ENGINES, ids=lambda e: f"{e[0]}{e[1]}")
+def engine(request, ops):
+    old = dict(ops.CONFIG)
+    ops.CONFIG.update(engine=request.param[0], passes=request.param[1])
+    yield request.param
+    ops.CONFIG.update(old)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv2d_fwd_bwd(ops, case):
+def test_conv2d_fwd_bwd(ops, case, engine):
     Ci, Co, k, s, p, H, W = case
+    ftol = engine[2]
     x = torch.randn(2, Ci, H, W, generator=G(40)).requires_grad_(True)
     w = (torch.randn(Co, Ci, k, k, generator=G(41)) * 0.05).requires_grad_(True)
     b = torch.randn(Co, generator=G(42)).requires_grad_(True)
@@ -286,9 +298,29 @@ def test_conv2d_fwd_bwd(ops, case):
     xc, wc, bc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
     out = ops.conv2d(xc, wc, bc, s, p)
     (out * go.cuda()).sum().backward()
-    assert rel_l2(out.cpu(), ref.detach()) <= 1e-5
+    assert rel_l2(out.cpu(), ref.detach()) <= ftol
     assert rel_l2(xc.grad.cpu(), x.grad) <= 1e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 1e-5
     assert rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("mode,k,Ci,Co,H,W", [("reflect", 7, 32, 128, 24, 40), ("reflect", 3, 128, 128, 16, 16),
+                                              ("replicate", 3, 256, 256, 16, 16), ("replicate", 7, 64, 1, 32, 32),
+                                              ("replicate", 4, 32, 64, 32, 32), ("reflect", 3, 128, 128, 20, 12)])
+def test_conv2d_fused_padding_modes(ops, engine, mode, k, Ci, Co, H, W):
+    """pad module folded into the conv (ReflectionPad2d + Conv2d, padding_mode='replicate')."""
+    stride = 2 if k == 4 else 1
+    p = 1 if k == 4 else k // 2
+    x = torch.randn(3, Ci, H, W, generator=G(60)).requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=G(61)) * 0.05).requires_grad_(True)
+    b = torch.randn(Co, generator=G(62))
+    ref = torch.tanh(F.conv2d(F.pad(x, (p, p, p, p), mode=mode), w, b, stride=stride))
+    go = torch.randn(ref.shape, generator=G(63))
+    (ref * go).sum().backward()
+    xc, wc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True)
+    out = ops.conv2d(xc, wc, b.cuda(), stride, p, act_out=ops.ACT_TANH, pad_mode=mode)
+    (out * go.cuda()).sum().backward()
+    assert rel_l2(out.cpu(), ref.detach()) <= engine[2]
+    assert rel_l2(xc.grad.cpu(), x.grad) <= 2e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 2e-5
 
 
 CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
@@ -298,7 +330,7 @@ CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
 
 
 @pytest.mark.parametrize("case", CONVT_CASES)
-def test_conv_transpose2d_fwd_bwd(ops, case):
+def test_conv_transpose2d_fwd_bwd(ops, case, engine):
     Ci, Co, k, s, p, op, H, W = case
     x = torch.randn(2, Ci, H, W, generator=G(44)).requires_grad_(True)
     w = (torch.randn(Ci, Co, k, k, generator=G(45)) * 0.05).requires_grad_(True)
@@ -309,9 +341,29 @@ def test_conv_transpose2d_fwd_bwd(ops, case):
     xc, wc, bc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
     out = ops.conv_transpose2d(xc, wc, bc, s, p, op, act_out=ops.ACT_TANH)
     (out * go.cuda()).sum().backward()
-    assert rel_l2(out.cpu(), ref.detach()) <= 1e-5
+    assert rel_l2(out.cpu(), ref.detach()) <= engine[2]
     assert rel_l2(xc.grad.cpu(), x.grad) <= 2e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 2e-5
     assert rel_l2(bc.grad.cpu(), b.grad) <= 2e-5
+
+
+def test_tc_large_tiles_and_split_k(ops):
+    """full 16x8 tiles over several images, ragged edges, and the split-K path of the tiny-M layers."""
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3)
+        for (Ci, Co, k, s, p, N, H, W, split) in [(128, 128, 3, 1, 1, 5, 64, 64, 1), (64, 128, 3, 1, 1, 2, 40, 24, 1),
+                                                  (512, 512, 4, 2, 1, 3, 8, 8, -1), (512, 512, 4, 2, 1, 12, 4, 4, 8),
+                                                  (256, 512, 4, 2, 1, 2, 20, 12, -1)]:
+            ops.CONFIG.update(split_k=split)
+            x = torch.randn(N, Ci, H, W, generator=G(70))
+            w = torch.randn(Co, Ci, k, k, generator=G(71)) * 0.03
+            b = torch.randn(Co, generator=G(72))
+            ref = F.conv2d(x, w, b, stride=s, padding=p)
+            with torch.no_grad():
+                out = ops.conv2d(cl(x), w.cuda(), b.cuda(), s, p)
+            assert rel_l2(out.cpu(), ref) <= 3e-5, (Ci, Co, k, s, N, H, W, split)
+    finally:
+        ops.CONFIG.update(old)
 
 
 def test_adam_matches_oracle(ops):
