@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py - pair-samples/s of the main_network_best training step (MainModel.optimize_parameters)
+on synthetic RGB-D crops.  Contract: one JSON line on stdout from rank 0 (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "depth-enhancement-and-super-resolution_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {   # BASELINE.json configs[1] / configs[2]
+    "c2": dict(B=6, H=256, W=256, name="main_network_best training step, batch 6 per GPU, 256x256 crops"),
+    "c3": dict(B=3, H=512, W=640, name="main_network_best full-size 640x480 (fed as 512x640), batch 3 per GPU"),
+    "tiny": dict(B=1, H=128, W=128, name="debug"),
+}
+FLOP_PER_PAIR_256 = 606.2e9      # 2*174.68 + 4*64.20 GMAC-pairs
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        import statistics
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.samples))
+
+
+def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None):
+    """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
+    import numpy as np
+    import torch
+    from oracle import ref_step
+    if sds is None:
+        from dsr_b200 import main_model, options
+        torch.manual_seed(0)
+        host = main_model.MainModel(options.main_flags(gpu_ids=[], batch_size=B, crop_size_h=H, crop_size_w=W,
+                                                       name="cpu", checkpoints_dir="/tmp/dsr_bench"))
+        sds = {n: getattr(host, "net" + n).state_dict() for n in host.model_names}
+    orc = ref_step.OracleStep(sds, lr=1e-4)
+    batch = ref_step.synthetic_batch(B, H, W, seed=1, depth_kind="smooth")
+    np.random.seed(0)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.step(batch)
+        ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(),
+                host_cpus=os.cpu_count())
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    Bs = min(wl["B"], 2)                      # bounded sample: B=2 of the workload's crops per step
+    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup)
+    line = dict(impl="reference", metric="RGB-D train pair-samples/sec (main net)", value=r["value"], unit="pair-samples/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * r["s_per_step"],
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl["name"], crop=[wl["H"], wl["W"]], per_step_batch=Bs),
+                cpu_baseline=dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
+                                  sample=f"{args.steps} steps of batch {Bs} at {wl['H']}x{wl['W']} (oracle/ref_step.py, torch CPU fp32)"),
+                e2e=dict(value=r["value"], unit="pair-samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dsr_b200 import _lib, main_model, ops, options, parallel
+    from oracle.ref_step import synthetic_batch          # synthetic input generator only (shared with the tests)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.load()
+    ops.CONFIG.update(engine=args.engine, passes=args.passes, dtype=args.dtype)
+    wl = WORKLOADS[args.workload]
+    B, H, W = wl["B"], wl["H"], wl["W"]
+    opt = options.main_flags(gpu_ids=[local], batch_size=B, crop_size_h=H, crop_size_w=W, name="bench",
+                             checkpoints_dir="/tmp/dsr_bench")
+    torch.manual_seed(0)
+    model = main_model.MainModel(opt)
+    model._train()
+    sync = None
+    if world > 1:
+        parallel.broadcast_weights(model)
+        sync = parallel.GradBuckets(model)
+    # a few distinct host batches in pinned memory (per-rank seeds: each rank draws its own shard)
+    host_batches = []
+    for i in range(2):
+        b = synthetic_batch(B, H, W, seed=1 + 17 * rank + i, depth_kind="smooth")
+        for k in ("A_i", "B_i", "A_d", "B_d"):
+            b[k] = b[k].pin_memory()
+        host_batches.append(b)
+    dev_batches = [{k: (v.cuda() if torch.is_tensor(v) and v.dtype == torch.float32 else v) for k, v in b.items()}
+                   for b in host_batches]
+    np.random.seed(1234 + rank)
+    h2d = sum(host_batches[0][k].numel() * 4 for k in ("A_i", "B_i", "A_d", "B_d")) + 2 * B * 11 * 8 + 2 * B * (64 * 4 + 1) * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, read_loss):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            model.set_input(batches[i % len(batches)])
+            model.optimize_parameters(i, 1)
+            if read_loss:
+                float(model.loss_G)                   # D2H read of the step's result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    timed(dev_batches, args.warmup, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.LAUNCHES
+    ms = timed(dev_batches, args.steps, False)                 # inputs resident in HBM
+    launches = (_lib.LAUNCHES - l0) // max(args.steps, 1)
+    ms_e2e = timed(host_batches, args.steps, True)             # pinned host inputs, H2D + loss D2H inside
+    sampler.stop_flag = True
+
+    # per-kernel pass: CUDA events around every library call of ONE more step (same stream)
+    prof = None
+    if rank == 0:
+        _lib.PROFILE = []
+        model.set_input(dev_batches[0])
+        model.optimize_parameters(0, 1)
+        torch.cuda.synchronize()
+        rec, _lib.PROFILE = _lib.PROFILE, None
+        by = {}
+        for name, a, b, meta in rec:
+            d = by.setdefault(name, dict(ms=0.0, n=0, macs=0))
+            d["ms"] += a.elapsed_time(b); d["n"] += 1
+            if meta:
+                d["macs"] += meta["macs"]
+        prof = by
+    line = None
+    if rank == 0:
+        pk, pk_src = peaks()
+        total_ms = sum(d["ms"] for d in prof.values())
+        tc = prof.get("dsr_tc_gemm")
+        top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
+        mult = {1: 1, 2: 2, 3: 3}[args.passes]
+        if tc and tc["n"]:
+            achieved = 2.0 * tc["macs"] / (tc["ms"] * 1e-3) / 1e12
+            roof = dict(bound="tensor", kernel="conv_tc_kernel (dsr_tc_gemm)", achieved=achieved, peak=pk["bf16_tflops_sustained"],
+                        unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk_src + " (sustained: timed inside a long step)",
+                        launches_per_step=tc["n"], avg_launch_us=1e3 * tc["ms"] / tc["n"], share_of_step=tc["ms"] / total_ms,
+                        mma_passes=mult, executed_tflops=achieved * mult,
+                        note="achieved = algorithmic conv FLOPs of the layers on the tcgen05 path / their summed launch time; "
+                             "each product is issued as `mma_passes` 16-bit MMAs (hi/lo split), so the tensor pipe executes `executed_tflops`")
+        else:
+            k, d = top[0]
+            roof = dict(bound="hbm", kernel=k, achieved=None, peak=pk["hbm_gbs"], unit="GB/s", frac=None, traffic=None,
+                        share_of_step=d["ms"] / total_ms)
+        flop_step = FLOP_PER_PAIR_256 * (H * W / 65536.0) * B
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = cpu_baseline(2, H, W, steps=2, warmup=1)
+            cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
+                       sample=f"2 steps of batch 2 at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
+        line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
+                    unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=f"{args.dtype} x{args.passes} operands, f32 accumulate" if args.engine == "tc" else "f32",
+                    data="synthetic",
+                    config=dict(workload=wl["name"], crop=[H, W], batch_per_gpu=B, parallelism=f"dp{world}", engine=args.engine,
+                                l2_policy="inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                                algorithmic_tflop_per_step=flop_step / 1e12),
+                    e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="pair-samples/s", h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu,
+                    step_tflops=flop_step / (ms / args.steps * 1e-3) / 1e12,
+                    kernel_times_ms={k: round(d["ms"], 3) for k, d in top})
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--engine", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3])
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@
 //              smem descriptors K-major SWIZZLE_128B; tcgen05.commit releases the smem stage / signals the epilogue
 //   warps 2-5: epilogue - tcgen05.ld 32x32b.x32 -> +bias -> (tanh) -> fp32 NHWC stores (or red.add for split-K)
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/dsr_b200.h"
 
@@ -99,8 +100,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// operand format: 1 = bf16, 0 = f16 (same .kind::f16 tensor pipe)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -115,6 +117,8 @@ struct TcParams {
     int ah, aw;               // A coordinate offsets
     int Ho, Wo, Cout, os, ph, pw;   // output tensor geometry
     int act, ksteps_per_split, ksteps;
+    int f16;                  // operands are IEEE half (11-bit significand) instead of bf16
+    float out_scale;          // accumulator scale (undoes the power-of-two weight scale of the f16 path)
     signed char dr[TC_MAX_TAPS], ds[TC_MAX_TAPS];
 };
 
@@ -199,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N);
+            const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
             uint32_t accum = 0;
             for (int i = 0; i < nk; ++i) {
                 const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
@@ -253,7 +257,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 for (int j = 0; j < CH; ++j) {
                     const int co = co0 + c0 + j;
                     if (co < p.Cout) {
-                        float f = __uint_as_float(v[j]);
+                        float f = __uint_as_float(v[j]) * p.out_scale;
                         if (add_bias) f += __ldg(bias + co);
                         if (split) atomicAdd(orow + co, f);
                         else {
@@ -299,10 +303,25 @@ __device__ __forceinline__ int prep_pad_src(int q, int p, int n, int mode) {
     if (mode == DSR_PAD_REFLECT) { i = i < 0 ? -i : 2 * (n - 1) - i; return (i >= 0 && i < n) ? i : -1; }
     return i < 0 ? 0 : n - 1;
 }
+// x = hi + lo with hi, lo in the 16-bit operand format (bf16: 8+8 significand bits; f16: 11+11, the low
+// part degrading gracefully into half subnormals, i.e. an absolute error floor of 2^-25)
+__device__ __forceinline__ void split16(float x, int f16, unsigned short& hi, unsigned short& lo) {
+    if (f16) {
+        x = fminf(fmaxf(x, -65504.f), 65504.f);
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
+        hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+        hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
+    }
+}
 // one thread = 8 consecutive arranged channels (one 16-byte store per output tensor)
 __global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm,
                                int act, float slope, int pad, int mode, int layout, int Cp,
-                               __nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo, int Ha, int Wa, int Ca) {
+                               unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, int Ha, int Wa, int Ca,
+                               int f16) {
     const int cg_per_pix = Ca >> 3;
     const long total = (long)N * Ha * Wa * cg_per_pix;
     const long NC = (long)N * C;
@@ -340,12 +359,9 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W,
                 }
             }
         }
-        __align__(16) __nv_bfloat16 hi[8], lo[8];
+        __align__(16) unsigned short hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            hi[e] = __float2bfloat16_rn(v[e]);
-            lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
-        }
+        for (int e = 0; e < 8; ++e) split16(v[e], f16, hi[e], lo[e]);
         const long o = (((long)n * Ha + ha) * Wa + wa) * Ca + q;
         *reinterpret_cast<uint4*>(Ahi + o) = *reinterpret_cast<const uint4*>(hi);
         if (Alo) *reinterpret_cast<uint4*>(Alo + o) = *reinterpret_cast<const uint4*>(lo);
@@ -362,7 +378,8 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W,
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S, int variant, int Cp,
                                       int pa, int pb, int pad, int Cout, int T, int Ca,
-                                      __nv_bfloat16* __restrict__ Whi, __nv_bfloat16* __restrict__ Wlo) {
+                                      unsigned short* __restrict__ Whi, unsigned short* __restrict__ Wlo, int f16,
+                                      float wscale) {
     const long K = (long)T * Ca, total = (long)Cout * K;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int co = (int)(idx / K);
@@ -378,9 +395,10 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D
         const int Cin = convT ? D0 : D1;
         if (r >= 0 && r < R && s >= 0 && s < S && c >= 0 && c < Cin)
             v = convT ? w[(((long)c * D1 + co) * R + r) * S + s] : w[(((long)co * D1 + c) * R + r) * S + s];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        unsigned short h, l;
+        split16(v * wscale, f16, h, l);
         Whi[idx] = h;
-        if (Wlo) Wlo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (Wlo) Wlo[idx] = l;
     }
 }
 
@@ -446,7 +464,8 @@ static int dispatch_n(int bn, const CUtensorMap& ah, const CUtensorMap& al, cons
 }
 
 extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
-                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, void* stream) {
+                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
+                           void* stream) {
     DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
     DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
     DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
@@ -455,23 +474,24 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
     DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15), "operand buffers must be 16-byte aligned");
     long total = (long)N * Ha * Wa * (Ca / 8);
     tc_prep_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
-                                                                (__nv_bfloat16*)A_hi, (__nv_bfloat16*)A_lo, Ha, Wa, Ca);
+                                                                (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16);
     return dsr_check_launch("tc_prep");
 }
 
 extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,
-                                  int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, void* stream) {
+                                  int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, int f16, float wscale,
+                                  void* stream) {
     DSR_REQUIRE(w && W_hi && T > 0 && (Ca & 63) == 0, "bad arguments");
     long total = (long)Cout * T * Ca;
     tc_pack_weight_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(w, D0, D1, R, S, variant, Cp, phase_a, phase_b, pad, Cout, T,
-                                                                       Ca, (__nv_bfloat16*)W_hi, (__nv_bfloat16*)W_lo);
+                                                                       Ca, (unsigned short*)W_hi, (unsigned short*)W_lo, f16, wscale);
     return dsr_check_launch("tc_pack_weight");
 }
 
 extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                            int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
                            const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
-                           int split_k, void* stream) {
+                           int split_k, int f16, float out_scale, void* stream) {
     DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
     DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
     DSR_REQUIRE(T >= 1 && T <= TC_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
@@ -479,6 +499,7 @@ extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, in
     TcParams p;
     p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.ah = a_off_h; p.aw = a_off_w;
     p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.os = os; p.ph = ph; p.pw = pw; p.act = act;
+    p.f16 = f16; p.out_scale = out_scale;
     for (int t = 0; t < T; ++t) { p.dr[t] = (signed char)tap_dr[t]; p.ds[t] = (signed char)tap_ds[t]; }
     // tile shape: TW x TH x TN = 128 rows
     int TW = Wt >= 16 ? 16 : pow2_ceil(Wt);

@@ -75,11 +75,23 @@ def last_error():
     return load().dsr_last_error_string().decode()
 
 
+PROFILE = None        # when a list: every call appends (name, start_event, end_event, meta) - bench.py's
+PROFILE_META = None   # per-kernel timing pass (CUDA events on the launching stream)
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise RuntimeError(dsr_last_error_string) on failure."""
     global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.append((name, e0, e1, PROFILE_META))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
     LAUNCHES += 1

@@ -136,6 +136,7 @@ class ArenaAdam(torch.optim.Optimizer):
         a = self.arena
         ops.adam_step(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, g["lr"], self.n_steps, g["betas"][0], g["betas"][1],
                       g["eps"], self.grad_scale)
+        ops.WEIGHT_EPOCH += 1            # packed 16-bit copies of the trainable weights are now stale
 
 
 class MainModel(BaseModel):

@@ -34,6 +34,7 @@ def _p(t, dtype=torch.float32):
 
 def _call(name, *args):
     _lib.call(name, *args, _stream())
+    _lib.PROFILE_META = None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -135,13 +136,21 @@ def _weight_grad(dwk, weight, kdim):
 # ------------------------------------------------------------------------------------------------
 CONFIG = {
     "engine": "tc",      # "tc": tcgen05 implicit GEMM wherever the layer shape allows; "simt": fp32 CUDA cores only
-    "passes": 3,         # 1 = bf16, 2 = activations hi+lo, 3 = activations and weights hi+lo (parity mode)
+    "passes": 3,         # 1 = single 16-bit pass, 2 = activations hi+lo, 3 = activations and weights hi+lo (parity mode)
+    "dtype": "f16",      # 16-bit operand format: "f16" (11-bit significand, hi+lo = 22 bits) or "bf16" (8 / 16 bits)
     "split_k": -1,       # -1 = automatic split-K for tiny-M layers
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
-_PACK_CACHE = {}
 _LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
 _W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH = 0, 1, 2, 3
+
+
+W_SCALE = 64.0          # power-of-two weight scale of the f16 path: keeps the low half of N(0, 0.02)-sized weights normal
+
+
+def _tc_fmt():
+    f16 = CONFIG["dtype"] == "f16"
+    return int(f16), (1.0 / W_SCALE if f16 else 1.0)
 
 
 def _rup(v, m):
@@ -170,15 +179,23 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W):
 
 
 def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0):
-    """bf16 hi/lo packed copy of a parameter, cached until the parameter changes."""
+    """bf16 hi/lo packed copy of a parameter, cached ON the parameter object until it changes
+    (in-place updates bump ``_version``; the arena optimizer bumps WEIGHT_EPOCH)."""
     npass = CONFIG["passes"]
     epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
-    key = (weight.data_ptr(), weight._version, epoch, plan["variant"], plan["Ca"], phase, npass >= 3)
-    hit = _PACK_CACHE.get(key)
+    stamp = (weight._version, epoch, weight.data_ptr())
+    f16 = CONFIG["dtype"] == "f16"
+    key = (plan["variant"], plan["Ca"], phase, pad, npass >= 3, f16)
+    cache = getattr(weight, "_dsr_pack", None)
+    if cache is None or cache.get("stamp") != stamp:
+        cache = {"stamp": stamp}
+        try:
+            weight._dsr_pack = cache
+        except AttributeError:
+            pass
+    hit = cache.get(key)
     if hit is not None:
         return hit
-    for k in [k for k in _PACK_CACHE if k[0] == key[0] and k[3:6] == key[3:6]]:
-        del _PACK_CACHE[k]
     D0, D1, R, S = weight.shape
     w = weight.detach()
     w = w if w.is_contiguous() else w.contiguous()
@@ -186,8 +203,8 @@ def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0):
     whi = torch.empty((Co, K), device=w.device, dtype=torch.bfloat16)
     wlo = torch.empty((Co, K), device=w.device, dtype=torch.bfloat16) if npass >= 3 else None
     _call("dsr_tc_pack_weight", _p(w), D0, D1, R, S, plan["variant"], plan["Cp"], phase[0], phase[1], pad, Co,
-          plan["T"], plan["Ca"], _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16))
-    _PACK_CACHE[key] = (whi, wlo)
+          plan["T"], plan["Ca"], _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), int(f16), W_SCALE if f16 else 1.0)
+    cache[key] = (whi, wlo)
     return whi, wlo
 
 
@@ -203,7 +220,7 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0):
     ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
     alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if CONFIG["passes"] >= 2 else None
     _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
-          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca)
+          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, int(CONFIG["dtype"] == "f16"))
     return ahi, alo, Ha, Wa
 
 
@@ -222,9 +239,10 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo)
         dr = [t // S for t in range(R * S)]
         ds = [t % S for t in range(R * S)]
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
+    _lib.PROFILE_META = dict(macs=N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
     _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
           _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0,
-          Ho, Wo, _p(bias), _p(y), Ho, Wo, 1, 0, 0, act_out, CONFIG["passes"], CONFIG["split_k"])
+          Ho, Wo, _p(bias), _p(y), Ho, Wo, 1, 0, 0, act_out, CONFIG["passes"], CONFIG["split_k"], *_tc_fmt())
     return y
 
 
@@ -237,9 +255,11 @@ def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo):
     for a in (0, 1):
         for b in (0, 1):
             whi, wlo = _tc_weights(weight, plan, Co, phase=(a, b), pad=pad)
+            _lib.PROFILE_META = dict(macs=N * H * W * Co * Ci * R * S // 4 if R == 4 else N * H * W * Co * Ci * 9 // 4,
+                                     shape=(N, H, W, Ci, Co, R, -2))
             _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
                   _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, 4, dr, ds, a, b, H, W, _p(bias), _p(y),
-                  Ho, Wo, 2, a, b, act_out, CONFIG["passes"], 1)
+                  Ho, Wo, 2, a, b, act_out, CONFIG["passes"], 1, *_tc_fmt())
     return y
 
 
@@ -258,7 +278,7 @@ class _Conv2d(Function):
         b = bias.detach() if bias is not None else None
         plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
         if plan is not None:
-            y = _tc_conv_fwd(xh, weight.detach(), b, plan, stride, pad, pad_mode, act_out, Ho, Wo)
+            y = _tc_conv_fwd(xh, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo)
         else:
             xp, p = _explicit_pad(xh, pad, pad_mode)
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
@@ -327,7 +347,7 @@ class _ConvTranspose2d(Function):
         b = bias.detach() if bias is not None else None
         plan = tc_conv_plan("convT", Ci, Co, R, S, stride, pad, opad, H, W)
         if plan is not None:
-            y = _tc_convT_fwd(xh, weight.detach(), b, plan, pad, act_out, Ho, Wo)
+            y = _tc_convT_fwd(xh, weight, b, plan, pad, act_out, Ho, Wo)
         else:
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
             wk = _pack(weight, 0)                       # [(r,s,ci)][co]

@@ -128,7 +128,10 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
  *                      input for stride-2 convs, Ca = 4*Cp).
  *   dsr_tc_pack_weight 4-D fp32 parameter -> bf16 hi(+lo) [Cout][T*Ca] K-major for the matching variant.
  *   dsr_tc_gemm        out[n, h*os+ph, w*os+pw, co] = bias[co] + sum_t sum_c A[n, h+ah+dr[t], w+aw+ds[t], c] W[co][t*Ca+c]
- *                      npass 1 = bf16, 2 = A hi+lo, 3 = A and W hi+lo (fp32-class products); tap tables are HOST arrays;
+ *                      npass 1 = single 16-bit pass, 2 = A hi+lo, 3 = A and W hi+lo; tap tables are HOST arrays;
+ *                      f16 = 0: bf16 operands (8-bit significands; hi+lo = 16 bits), f16 = 1: IEEE half operands
+ *                      (11-bit; hi+lo = 22 bits, fp32-class products) with weights pre-scaled by the power of two
+ *                      `wscale` at pack time and out_scale = 1/wscale applied to the accumulator;
  *                      split_k: 1 = off, -1 = auto (tiny-M layers), >1 = that many K splits (out must not alias). */
 #define DSR_TC_LAYOUT_NORMAL 0
 #define DSR_TC_LAYOUT_PAIR 1
@@ -138,13 +141,13 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
 #define DSR_TC_W_CONV_S2D 2
 #define DSR_TC_W_CONVT_PH 3
 int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
-                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, void* stream);
+                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16, void* stream);
 int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,
-                       int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, void* stream);
+                       int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, int f16, float wscale, void* stream);
 int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                 int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
-                int split_k, void* stream);
+                int split_k, int f16, float out_scale, void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------------- */
 /* torch.optim.Adam (defaults) over one flat arena.  models/main_model.py:176, :429. */

@@ -274,14 +274,16 @@ CONV_CASES = [  # Cin, Cout, k, stride, pad, H, W
 ]
 
 
-ENGINES = [("simt", 3, 1e-5), ("tc", 3, 3e-5), ("tc", 2, 4e-3), ("tc", 1, 8e-3)]
+# (engine, passes, operand dtype, forward rel-L2 tolerance): what each precision mode is good for
+ENGINES = [("simt", 3, "f16", 1e-5), ("tc", 3, "f16", 1e-5), ("tc", 1, "f16", 1e-3), ("tc", 3, "bf16", 5e-5),
+           ("tc", 2, "bf16", 4e-3), ("tc", 1, "bf16", 8e-3)]
 
 
-@pytest.fixture(params=ENGINES, ids=lambda e: f"{e[0]}{e[1]}")
+@pytest.fixture(params=ENGINES, ids=lambda e: f"{e[0]}{e[1]}{e[2]}")
 def engine(request, ops):
     old = dict(ops.CONFIG)
-    ops.CONFIG.update(engine=request.param[0], passes=request.param[1])
-    yield request.param
+    ops.CONFIG.update(engine=request.param[0], passes=request.param[1], dtype=request.param[2])
+    yield (request.param[0], request.param[1], request.param[3])
     ops.CONFIG.update(old)
 
 
@@ -320,7 +322,8 @@ def test_conv2d_fused_padding_modes(ops, engine, mode, k, Ci, Co, H, W):
     out = ops.conv2d(xc, wc, b.cuda(), stride, p, act_out=ops.ACT_TANH, pad_mode=mode)
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= engine[2]
-    assert rel_l2(xc.grad.cpu(), x.grad) <= 2e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 2e-5
+    btol = max(2e-5, 2 * engine[2])        # the tanh backward reads the forward output
+    assert rel_l2(xc.grad.cpu(), x.grad) <= btol and rel_l2(wc.grad.cpu(), w.grad) <= btol
 
 
 CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
@@ -342,7 +345,8 @@ def test_conv_transpose2d_fwd_bwd(ops, case, engine):
     out = ops.conv_transpose2d(xc, wc, bc, s, p, op, act_out=ops.ACT_TANH)
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= engine[2]
-    assert rel_l2(xc.grad.cpu(), x.grad) <= 2e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 2e-5
+    btol = max(2e-5, 2 * engine[2])        # the tanh backward reads the forward output
+    assert rel_l2(xc.grad.cpu(), x.grad) <= btol and rel_l2(wc.grad.cpu(), w.grad) <= btol
     assert rel_l2(bc.grad.cpu(), b.grad) <= 2e-5
 
 
@@ -350,7 +354,7 @@ def test_tc_large_tiles_and_split_k(ops):
     """full 16x8 tiles over several images, ragged edges, and the split-K path of the tiny-M layers."""
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16")
         for (Ci, Co, k, s, p, N, H, W, split) in [(128, 128, 3, 1, 1, 5, 64, 64, 1), (64, 128, 3, 1, 1, 2, 40, 24, 1),
                                                   (512, 512, 4, 2, 1, 3, 8, 8, -1), (512, 512, 4, 2, 1, 12, 4, 4, 8),
                                                   (256, 512, 4, 2, 1, 2, 20, 12, -1)]:
@@ -361,7 +365,7 @@ def test_tc_large_tiles_and_split_k(ops):
             ref = F.conv2d(x, w, b, stride=s, padding=p)
             with torch.no_grad():
                 out = ops.conv2d(cl(x), w.cuda(), b.cuda(), s, p)
-            assert rel_l2(out.cpu(), ref) <= 3e-5, (Ci, Co, k, s, N, H, W, split)
+            assert rel_l2(out.cpu(), ref) <= 1e-5, (Ci, Co, k, s, N, H, W, split)
     finally:
         ops.CONFIG.update(old)
 
