@@ -373,6 +373,8 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W,
 //   variant CONV     : Conv2d weight (Cout, Cin, R, S); tap t = r*S + s, channel c          (stride 1)
 //   variant CONV_PAIR: as CONV with Ca = 2*Cp: tap t = r*ceil(S/2) + s2, q = (s&1)*Cp + c
 //   variant CONV_S2D : stride-2 conv (k <= 4) as 2x2 taps over 4*Cp channels: r = 2r'+a, s = 2s'+b
+//   variant CONV_DGRAD: Conv2d weight (Cout, Cin, R, S) for the stride-1 data gradient: GEMM output channel = ci,
+//                      K channel = co, tap t = (r', s') reads W[co][ci][R-1-r'][S-1-s']
 //   variant CONVT_PH : ConvTranspose2d weight (Cin, Cout, R, S), stride 2, phase (a,b): taps (dr,ds) in {0,1}^2,
 //                      kh = pad + 2 - a - 2*dr, kw = pad + 2 - b - 2*ds (zero tap when outside the kernel)
 // ------------------------------------------------------------------------------------------------
@@ -389,9 +391,11 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D
         if (variant == DSR_TC_W_CONV) { r = t / S; s = t - r * S; c = q; }
         else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; r = t / S2; s = 2 * (t - r * S2) + q / Cp; c = q % Cp; }
         else if (variant == DSR_TC_W_CONV_S2D) { const int ab = q / Cp; c = q - ab * Cp; r = 2 * (t >> 1) + (ab >> 1); s = 2 * (t & 1) + (ab & 1); }
+        else if (variant == DSR_TC_W_CONV_DGRAD) { r = R - 1 - t / S; s = S - 1 - (t - (t / S) * S); c = q; }
         else { c = q; r = pad + 2 - pa - 2 * (t >> 1); s = pad + 2 - pb - 2 * (t & 1); }
         float v = 0.f;
-        const bool convT = (variant == DSR_TC_W_CONVT_PH);
+        // convT-style indexing: the GEMM's K channel is the parameter's dim 0, its output channel dim 1
+        const bool convT = (variant == DSR_TC_W_CONVT_PH) || (variant == DSR_TC_W_CONV_DGRAD);
         const int Cin = convT ? D0 : D1;
         if (r >= 0 && r < R && s >= 0 && s < S && c >= 0 && c < Cin)
             v = convT ? w[(((long)c * D1 + co) * R + r) * S + s] : w[(((long)co * D1 + c) * R + r) * S + s];

@@ -137,19 +137,21 @@ def _weight_grad(dwk, weight, kdim):
 CONFIG = {
     "engine": "tc",      # "tc": tcgen05 implicit GEMM wherever the layer shape allows; "simt": fp32 CUDA cores only
     "passes": 3,         # 1 = single 16-bit pass, 2 = activations hi+lo, 3 = activations and weights hi+lo (parity mode)
-    "dtype": "f16",      # 16-bit operand format: "f16" (11-bit significand, hi+lo = 22 bits) or "bf16" (8 / 16 bits)
+    "dtype": "f16",      # forward operand format: "f16" (11-bit significand, hi+lo = 22 bits) or "bf16" (8 / 16 bits)
+    "bwd_dtype": "bf16", # backward (gradient) operand format: gradients span too many octaves for unscaled f16
+    "tc_backward": True, # run dgrad / wgrad on the tcgen05 path as well
     "split_k": -1,       # -1 = automatic split-K for tiny-M layers
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
 _LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
-_W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH = 0, 1, 2, 3
+_W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH, _W_CONV_DGRAD = 0, 1, 2, 3, 4
 
 
 W_SCALE = 64.0          # power-of-two weight scale of the f16 path: keeps the low half of N(0, 0.02)-sized weights normal
 
 
-def _tc_fmt():
-    f16 = CONFIG["dtype"] == "f16"
+def _tc_fmt(dtype=None):
+    f16 = (dtype or CONFIG["dtype"]) == "f16"
     return int(f16), (1.0 / W_SCALE if f16 else 1.0)
 
 
@@ -178,13 +180,13 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W):
     return None
 
 
-def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0):
+def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None):
     """bf16 hi/lo packed copy of a parameter, cached ON the parameter object until it changes
     (in-place updates bump ``_version``; the arena optimizer bumps WEIGHT_EPOCH)."""
     npass = CONFIG["passes"]
     epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
     stamp = (weight._version, epoch, weight.data_ptr())
-    f16 = CONFIG["dtype"] == "f16"
+    f16 = (dtype or CONFIG["dtype"]) == "f16"
     key = (plan["variant"], plan["Ca"], phase, pad, npass >= 3, f16)
     cache = getattr(weight, "_dsr_pack", None)
     if cache is None or cache.get("stamp") != stamp:
@@ -208,7 +210,7 @@ def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0):
     return whi, wlo
 
 
-def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0):
+def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=None):
     """fp32 NHWC -> arranged bf16 hi(+lo) operand."""
     N, H, W, C = xh.shape
     Hq, Wq = H + 2 * pad, W + 2 * pad
@@ -220,15 +222,20 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0):
     ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
     alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if CONFIG["passes"] >= 2 else None
     _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
-          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, int(CONFIG["dtype"] == "f16"))
+          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, int((dtype or CONFIG["dtype"]) == "f16"))
     return ahi, alo, Ha, Wa
 
 
-def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo):
+def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo, dtype=None, Co=None, macs=None):
+    """stride-1 / stride-2 convolution of `xh` with a Conv2d-layout weight on the tcgen05 path.
+    Also serves as the dgrad of ConvTranspose2d (its weight read as a Conv2d weight) and, with
+    plan['variant'] == _W_CONV_DGRAD, as the dgrad of a stride-1 Conv2d (flipped / transposed taps)."""
     N, H, W, Ci = xh.shape
-    Co, _, R, S = weight.shape
-    ahi, alo, Ha, Wa = _tc_prep(xh, plan, pad, pad_mode)
-    whi, wlo = _tc_weights(weight, plan, Co)
+    R, S = weight.shape[2], weight.shape[3]
+    if Co is None:
+        Co = weight.shape[0]
+    ahi, alo, Ha, Wa = _tc_prep(xh, plan, pad, pad_mode, dtype=dtype)
+    whi, wlo = _tc_weights(weight, plan, Co, dtype=dtype)
     if plan["layout"] == _LAYOUT_PAIR:
         S2 = (S + 1) // 2
         dr = [t // S2 for t in range(plan["T"])]
@@ -239,28 +246,71 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo)
         dr = [t // S for t in range(R * S)]
         ds = [t % S for t in range(R * S)]
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
-    _lib.PROFILE_META = dict(macs=N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
+    _lib.PROFILE_META = dict(macs=macs if macs is not None else N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
     _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
           _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0,
-          Ho, Wo, _p(bias), _p(y), Ho, Wo, 1, 0, 0, act_out, CONFIG["passes"], CONFIG["split_k"], *_tc_fmt())
+          Ho, Wo, _p(bias), _p(y), Ho, Wo, 1, 0, 0, act_out, CONFIG["passes"], CONFIG["split_k"], *_tc_fmt(dtype))
     return y
 
 
-def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo):
+def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None):
+    """stride-2 transposed convolution (4 output phases) of `xh` with a ConvTranspose2d-layout weight;
+    also the dgrad of a stride-2 Conv2d (whose (Cout, Cin, R, S) weight IS a ConvTranspose2d weight
+    from Cout to Cin channels)."""
     N, H, W, Ci = xh.shape
     _, Co, R, S = weight.shape
-    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO)              # zero halo of 1 around the input
+    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO, dtype=dtype)     # zero halo of 1 around the input
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     dr, ds = _int_array([0, 0, 1, 1]), _int_array([0, 1, 0, 1])
+    Ht, Wt = (Ho + 1) // 2, (Wo + 1) // 2
     for a in (0, 1):
         for b in (0, 1):
-            whi, wlo = _tc_weights(weight, plan, Co, phase=(a, b), pad=pad)
-            _lib.PROFILE_META = dict(macs=N * H * W * Co * Ci * R * S // 4 if R == 4 else N * H * W * Co * Ci * 9 // 4,
-                                     shape=(N, H, W, Ci, Co, R, -2))
+            whi, wlo = _tc_weights(weight, plan, Co, phase=(a, b), pad=pad, dtype=dtype)
+            _lib.PROFILE_META = dict(macs=N * H * W * Co * Ci * R * S // 4, shape=(N, H, W, Ci, Co, R, -2))
             _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
-                  _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, 4, dr, ds, a, b, H, W, _p(bias), _p(y),
-                  Ho, Wo, 2, a, b, act_out, CONFIG["passes"], 1, *_tc_fmt())
+                  _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, 4, dr, ds, a, b, Ht, Wt, _p(bias), _p(y),
+                  Ho, Wo, 2, a, b, act_out, CONFIG["passes"], 1, *_tc_fmt(dtype))
     return y
+
+
+def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
+    """dL/dx of a Conv2d on the tcgen05 path (None when the shape is not covered).  g: (N,Ho,Wo,Co)."""
+    if not CONFIG["tc_backward"]:
+        return None
+    N, Ho, Wo, Co = g.shape
+    _, Ci, R, S = weight.shape
+    dt = CONFIG["bwd_dtype"]
+    if stride == 1:
+        plan = tc_conv_plan("conv", Co, Ci, R, S, 1, 0, 0, Ho, Wo)
+        if plan is None or plan["layout"] != _LAYOUT_NORMAL:
+            return None
+        plan = dict(plan, variant=_W_CONV_DGRAD)
+        macs = N * Ho * Wo * Co * Ci * R * S
+        if pad_mode == PAD_ZERO or pad == 0:          # gradient w.r.t. the un-padded input directly
+            return _tc_conv_fwd(g, weight, None, plan, 1, R - 1 - pad, PAD_ZERO, ACT_NONE, H, W, dtype=dt, Co=Ci, macs=macs)
+        gxp = _tc_conv_fwd(g, weight, None, plan, 1, R - 1, PAD_ZERO, ACT_NONE, H + 2 * pad, W + 2 * pad, dtype=dt, Co=Ci, macs=macs)
+        gx = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
+        _call("dsr_pad2d_bwd", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode)
+        return gx
+    if stride == 2 and pad_mode == PAD_ZERO:
+        opad = H - ((Ho - 1) * 2 - 2 * pad + R)
+        plan = tc_conv_plan("convT", Co, Ci, R, S, 2, pad, opad, Ho, Wo)
+        if plan is None or W - ((Wo - 1) * 2 - 2 * pad + S) != opad:
+            return None
+        return _tc_convT_fwd(g, weight, None, plan, pad, ACT_NONE, H, W, dtype=dt)
+    return None
+
+
+def _tc_convT_dgrad(g, weight, stride, pad, H, W):
+    """dL/dx of a ConvTranspose2d = stride-2 Conv2d of g with the same weight read as (Cout=Ci, Cin=Co, R, S)."""
+    if not CONFIG["tc_backward"]:
+        return None
+    N, Ho, Wo, Co = g.shape
+    Ci, _, R, S = weight.shape
+    plan = tc_conv_plan("conv", Co, Ci, R, S, stride, pad, 0, Ho, Wo)
+    if plan is None or (Ho + 2 * pad - R) // stride + 1 != H or (Wo + 2 * pad - S) // stride + 1 != W:
+        return None
+    return _tc_conv_fwd(g, weight, None, plan, stride, pad, PAD_ZERO, ACT_NONE, H, W, dtype=CONFIG["bwd_dtype"], Co=Ci)
 
 
 class _Conv2d(Function):
@@ -306,13 +356,15 @@ class _Conv2d(Function):
         Hp, Wp = xp.shape[1], xp.shape[2]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wk = _pack(weight, 0)                                   # [(r,s,co)][ci]
-            gxp = torch.empty((N, Hp, Wp, Ci), device=g.device, dtype=torch.float32)
-            _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxp), N, Ho, Wo, Co, Hp, Wp, Ci, R, S, stride, p, 1, ACT_NONE)
-            if xp is not xh:
-                gxh = torch.empty_like(xh)
-                _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
-                gxp = gxh
+            gxp = _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W)
+            if gxp is None:
+                wk = _pack(weight, 0)                               # [(r,s,co)][ci]
+                gxp = torch.empty((N, Hp, Wp, Ci), device=g.device, dtype=torch.float32)
+                _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxp), N, Ho, Wo, Co, Hp, Wp, Ci, R, S, stride, p, 1, ACT_NONE)
+                if xp is not xh:
+                    gxh = torch.empty_like(xh)
+                    _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
+                    gxp = gxh
             gx = nchw(gxp)
         if ctx.needs_input_grad[1]:
             dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
@@ -371,9 +423,11 @@ class _ConvTranspose2d(Function):
             g = g2
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wk = _pack(weight, 1)                       # [(r,s,co)][ci]
-            gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
-            _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
+            gxh = _tc_convT_dgrad(g, weight, stride, pad, H, W)
+            if gxh is None:
+                wk = _pack(weight, 1)                   # [(r,s,co)][ci]
+                gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
+                _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
             gx = nchw(gxh)
         if ctx.needs_input_grad[1]:
             dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)

@@ -140,6 +140,7 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
 #define DSR_TC_W_CONV_PAIR 1
 #define DSR_TC_W_CONV_S2D 2
 #define DSR_TC_W_CONVT_PH 3
+#define DSR_TC_W_CONV_DGRAD 4
 int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
                 int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16, void* stream);
 int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,

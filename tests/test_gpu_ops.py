@@ -283,7 +283,9 @@ ENGINES = [("simt", 3, "f16", 1e-5), ("tc", 3, "f16", 1e-5), ("tc", 1, "f16", 1e
 def engine(request, ops):
     old = dict(ops.CONFIG)
     ops.CONFIG.update(engine=request.param[0], passes=request.param[1], dtype=request.param[2])
-    yield (request.param[0], request.param[1], request.param[3])
+    # (engine, passes, forward tolerance, dgrad tolerance: the backward operands are bf16 hi/lo)
+    xtol = 1e-5 if request.param[0] == "simt" else {3: 5e-5, 2: 4e-3, 1: 8e-3}[request.param[1]]
+    yield (request.param[0], request.param[1], request.param[3], xtol)
     ops.CONFIG.update(old)
 
 
@@ -301,7 +303,7 @@ def test_conv2d_fwd_bwd(ops, case, engine):
     out = ops.conv2d(xc, wc, bc, s, p)
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= ftol
-    assert rel_l2(xc.grad.cpu(), x.grad) <= 1e-5 and rel_l2(wc.grad.cpu(), w.grad) <= 1e-5
+    assert rel_l2(xc.grad.cpu(), x.grad) <= engine[3] and rel_l2(wc.grad.cpu(), w.grad) <= 1e-5
     assert rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
 
 
@@ -323,7 +325,7 @@ def test_conv2d_fused_padding_modes(ops, engine, mode, k, Ci, Co, H, W):
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= engine[2]
     btol = max(2e-5, 2 * engine[2])        # the tanh backward reads the forward output
-    assert rel_l2(xc.grad.cpu(), x.grad) <= btol and rel_l2(wc.grad.cpu(), w.grad) <= btol
+    assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= btol
 
 
 CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
@@ -346,7 +348,7 @@ def test_conv_transpose2d_fwd_bwd(ops, case, engine):
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= max(engine[2], 3e-5 if Ci >= 1024 else 0.0)
     btol = max(3e-5, 2 * engine[2])        # the tanh backward reads the forward output
-    assert rel_l2(xc.grad.cpu(), x.grad) <= btol and rel_l2(wc.grad.cpu(), w.grad) <= btol
+    assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= btol
     assert rel_l2(bc.grad.cpu(), b.grad) <= btol
 
 
