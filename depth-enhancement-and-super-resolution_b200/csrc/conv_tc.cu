@@ -294,6 +294,186 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// weight-gradient GEMM:  dWp[cm][t*Ca + c] (+)= sum_{pixels p of the base grid} M[p + moff][cm] * A[p + aoff + tap_t][c]
+//   M  : 16-bit arranged tensor whose channels index the rows of the weight gradient (dY for Conv2d, x for
+//        ConvTranspose2d), A : the arranged tensor the forward conv multiplied with (x, or dY for ConvTranspose2d).
+//   Both operands are read with the PIXEL dimension as the MMA K dimension, i.e. MN-major smem tiles: one TMA box
+//   = 64 pixels x 64 channels (128-byte rows, SWIZZLE_128B); descriptor SBO = 1024 (next 8 pixels), LBO = 8192
+//   (next 64 channels).  One CTA = one (tap, 128 x BLOCK_N) tile of dWp over a range of pixel tiles (split-K).
+// ------------------------------------------------------------------------------------------------
+struct WgParams {
+    int N, Hb, Wb;            // base grid
+    int TW, TH, TN;           // 64-pixel K tile
+    int tiles_w, tiles_h, tiles_total;
+    int tiles_per_split;
+    int mh, mw;               // M-side coordinate offsets
+    int ah, aw;               // A-side coordinate offsets
+    int Cm_real, Ca, T, n_tiles_c;   // rows of dWp, arranged A channels, taps, number of BLOCK_N tiles over Ca
+    int f16;
+    float out_scale;
+    signed char dr[TC_MAX_TAPS], ds[TC_MAX_TAPS];
+};
+
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int BLOCK_N, int NPASS>
+struct WgCfg {
+    static constexpr int BOX = 64 * 128;                     // 64 pixels x 128 B
+    static constexpr int NB = BLOCK_N / 64;
+    static constexpr int NM = NPASS >= 2 ? 2 : 1;            // M hi (+lo)
+    static constexpr int NA = NPASS >= 3 ? 2 : 1;            // A hi (+lo)
+    static constexpr int M_BYTES = 2 * BOX;                  // 128 channels
+    static constexpr int A_BYTES = NB * BOX;
+    static constexpr int STAGE = NM * M_BYTES + NA * A_BYTES;
+    static constexpr int STAGES = (200 * 1024 / STAGE) > 8 ? 8 : (200 * 1024 / STAGE);
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+template <int BLOCK_N, int NPASS>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapM_hi, const __grid_constant__ CUtensorMap mapM_lo,
+                const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                const __grid_constant__ WgParams p, float* __restrict__ dWp) {
+    using Cfg = WgCfg<BLOCK_N, NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::STAGES + 1);
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE + 8 * (2 * Cfg::STAGES + 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int t = blockIdx.x;                                 // tap
+    const int cm0 = (blockIdx.y / p.n_tiles_c) * 128;         // rows of dWp
+    const int cn0 = (blockIdx.y % p.n_tiles_c) * BLOCK_N;     // arranged A channel
+    const int kb = blockIdx.z * p.tiles_per_split;
+    int ke = kb + p.tiles_per_split;
+    if (ke > p.tiles_total) ke = p.tiles_total;
+    const int nk = ke - kb;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapM_hi); tma_prefetch_desc(&mapA_hi);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+                mbar_wait(empty_bar(s), (it & 1) ^ 1);
+                int tile = kb + i;
+                const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+                const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+                const int n0 = tile * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+                const uint32_t st = smem_base + s * Cfg::STAGE;
+                mbar_expect_tx(full_bar(s), Cfg::STAGE);
+                uint32_t dst = st;
+#pragma unroll
+                for (int b = 0; b < 2; ++b, dst += Cfg::BOX)
+                    tma_load_4d(dst, &mapM_hi, full_bar(s), cm0 + 64 * b, w0 + p.mw, h0 + p.mh, n0);
+                if (NPASS >= 2) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b, dst += Cfg::BOX)
+                        tma_load_4d(dst, &mapM_lo, full_bar(s), cm0 + 64 * b, w0 + p.mw, h0 + p.mh, n0);
+                }
+                const int ha = h0 + p.ah + p.dr[t], wa = w0 + p.aw + p.ds[t];
+#pragma unroll
+                for (int b = 0; b < Cfg::NB; ++b, dst += Cfg::BOX)
+                    tma_load_4d(dst, &mapA_hi, full_bar(s), cn0 + 64 * b, wa, ha, n0);
+                if (NPASS >= 3) {
+#pragma unroll
+                    for (int b = 0; b < Cfg::NB; ++b, dst += Cfg::BOX)
+                        tma_load_4d(dst, &mapA_lo, full_bar(s), cn0 + 64 * b, wa, ha, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // both operands MN-major: bits 15 / 16 of the instruction descriptor
+            const uint32_t idesc = make_idesc(128, BLOCK_N, p.f16 ? 0u : 1u) | (1u << 15) | (1u << 16);
+            uint32_t accum = 0;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+                mbar_wait(full_bar(s), it & 1);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * Cfg::STAGE;
+                const uint32_t m_hi = st, m_lo = st + Cfg::M_BYTES;
+                const uint32_t a_hi = st + Cfg::NM * Cfg::M_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+#pragma unroll
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const uint32_t m = (pass == 1) ? m_lo : m_hi;
+                    const uint32_t a = (pass == 2) ? a_lo : a_hi;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        tc_mma_bf16(tmem_acc, make_sdesc_mn(m + kk * 2048), make_sdesc_mn(a + kk * 2048), idesc, accum);
+                        accum = 1;
+                    }
+                }
+                tc_commit(empty_bar(s));
+            }
+            tc_commit(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int cm = cm0 + row;
+        const bool valid = cm < p.Cm_real && nk > 0;
+        float* orow = dWp + (long)cm * ((long)p.T * p.Ca) + (long)t * p.Ca;
+        if (nk > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+        }
+        const bool split = gridDim.z > 1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t v[32];
+            if (nk > 0) {
+                tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tc_wait_ld();
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int c = cn0 + c0 + j;
+                    if (c < p.Ca) {
+                        float4 f = make_float4(__uint_as_float(v[j]) * p.out_scale, __uint_as_float(v[j + 1]) * p.out_scale,
+                                               __uint_as_float(v[j + 2]) * p.out_scale, __uint_as_float(v[j + 3]) * p.out_scale);
+                        if (split) {
+                            atomicAdd(orow + c, f.x); atomicAdd(orow + c + 1, f.y);
+                            atomicAdd(orow + c + 2, f.z); atomicAdd(orow + c + 3, f.w);
+                        } else {
+                            *reinterpret_cast<float4*>(orow + c) = f;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BLOCK_N) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // operand preparation: fp32 NHWC -> arranged bf16 hi (+lo), fusing norm-apply + activation + padding
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int prep_pad_src(int q, int p, int n, int mode) {
@@ -378,6 +558,14 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W,
 //   variant CONVT_PH : ConvTranspose2d weight (Cin, Cout, R, S), stride 2, phase (a,b): taps (dr,ds) in {0,1}^2,
 //                      kh = pad + 2 - a - 2*dr, kw = pad + 2 - b - 2*ds (zero tap when outside the kernel)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_map_k(int variant, int t, int q, int R, int S, int Cp, int pa, int pb, int pad,
+                                         int& r, int& s, int& c) {
+    if (variant == DSR_TC_W_CONV) { r = t / S; s = t - r * S; c = q; }
+    else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; r = t / S2; s = 2 * (t - r * S2) + q / Cp; c = q % Cp; }
+    else if (variant == DSR_TC_W_CONV_S2D) { const int ab = q / Cp; c = q - ab * Cp; r = 2 * (t >> 1) + (ab >> 1); s = 2 * (t & 1) + (ab & 1); }
+    else if (variant == DSR_TC_W_CONV_DGRAD) { r = R - 1 - t / S; s = S - 1 - (t - (t / S) * S); c = q; }
+    else { c = q; r = pad + 2 - pa - 2 * (t >> 1); s = pad + 2 - pb - 2 * (t & 1); }
+}
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S, int variant, int Cp,
                                       int pa, int pb, int pad, int Cout, int T, int Ca,
                                       unsigned short* __restrict__ Whi, unsigned short* __restrict__ Wlo, int f16,
@@ -387,12 +575,8 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D
         const int co = (int)(idx / K);
         const long k = idx - (long)co * K;
         const int t = (int)(k / Ca), q = (int)(k - (long)t * Ca);
-        int r = -1, s = -1, c = -1;
-        if (variant == DSR_TC_W_CONV) { r = t / S; s = t - r * S; c = q; }
-        else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; r = t / S2; s = 2 * (t - r * S2) + q / Cp; c = q % Cp; }
-        else if (variant == DSR_TC_W_CONV_S2D) { const int ab = q / Cp; c = q - ab * Cp; r = 2 * (t >> 1) + (ab >> 1); s = 2 * (t & 1) + (ab & 1); }
-        else if (variant == DSR_TC_W_CONV_DGRAD) { r = R - 1 - t / S; s = S - 1 - (t - (t / S) * S); c = q; }
-        else { c = q; r = pad + 2 - pa - 2 * (t >> 1); s = pad + 2 - pb - 2 * (t & 1); }
+        int r, s, c;
+        tc_map_k(variant, t, q, R, S, Cp, pa, pb, pad, r, s, c);
         float v = 0.f;
         // convT-style indexing: the GEMM's K channel is the parameter's dim 0, its output channel dim 1
         const bool convT = (variant == DSR_TC_W_CONVT_PH) || (variant == DSR_TC_W_CONV_DGRAD);
@@ -403,6 +587,23 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D
         split16(v * wscale, f16, h, l);
         Whi[idx] = h;
         if (Wlo) Wlo[idx] = l;
+    }
+}
+// packed weight gradient [D0][T*Ca] (row = parameter dim 0, K channel = parameter dim 1) -> parameter layout
+__global__ void tc_unpack_wgrad_kernel(const float* __restrict__ dWp, int D0, int D1, int R, int S, int variant, int Cp,
+                                       int T, int Ca, float* __restrict__ grad, int accumulate) {
+    const long total = (long)D0 * D1 * R * S;
+    // gather form (one thread per parameter element): invert tc_map_k
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int s = (int)(idx % S); long u = idx / S;
+        const int r = (int)(u % R); u /= R;
+        const int c = (int)(u % D1); const int d0 = (int)(u / D1);
+        int t, q;
+        if (variant == DSR_TC_W_CONV) { t = r * S + s; q = c; }
+        else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; t = r * S2 + (s >> 1); q = (s & 1) * Cp + c; }
+        else { t = (r >> 1) * 2 + (s >> 1); q = ((r & 1) * 2 + (s & 1)) * Cp + c; }          // S2D
+        const float v = dWp[(long)d0 * ((long)T * Ca) + (long)t * Ca + q];
+        if (accumulate) grad[idx] += v; else grad[idx] = v;
     }
 }
 
@@ -553,4 +754,93 @@ extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, in
     if (npass == 1) return dispatch_n<1>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
     if (npass == 2) return dispatch_n<2>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
     return dispatch_n<3>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
+}
+
+template <int BLOCK_N, int NPASS>
+static int launch_wg(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& ah, const CUtensorMap& al,
+                     const WgParams& p, float* dWp, dim3 grid, cudaStream_t st) {
+    using Cfg = WgCfg<BLOCK_N, NPASS>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
+            dsr_set_error("wgrad_tc: cannot raise dynamic shared memory to %d", Cfg::SMEM);
+            return DSR_ERR_CUDA;
+        }
+        attr = true;
+    }
+    wgrad_tc_kernel<BLOCK_N, NPASS><<<grid, 192, Cfg::SMEM, st>>>(mh, ml, ah, al, p, dWp);
+    return dsr_check_launch("wgrad_tc");
+}
+template <int NPASS>
+static int dispatch_wg(int bn, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& ah, const CUtensorMap& al,
+                       const WgParams& p, float* dWp, dim3 grid, cudaStream_t st) {
+    switch (bn) {
+        case 64: return launch_wg<64, NPASS>(mh, ml, ah, al, p, dWp, grid, st);
+        case 128: return launch_wg<128, NPASS>(mh, ml, ah, al, p, dWp, grid, st);
+        case 256: return launch_wg<256, NPASS>(mh, ml, ah, al, p, dWp, grid, st);
+    }
+    dsr_set_error("wgrad_tc: unsupported BLOCK_N %d", bn);
+    return DSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h,
+                            int m_off_w, const void* A_hi, const void* A_lo, int Ha, int Wa, int Ca, int T,
+                            const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb, float* dWp,
+                            int npass, int f16, float out_scale, int split_k, void* stream) {
+    DSR_REQUIRE(M_hi && A_hi && dWp && tap_dr && tap_ds, "null pointer");
+    DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || M_lo) && (npass < 3 || A_lo), "bad precision mode");
+    DSR_REQUIRE(T >= 1 && T <= TC_MAX_TAPS && (Ca & 63) == 0 && (Cm & 63) == 0 && Cm_real >= 1 && Cm_real <= Cm, "bad GEMM shape");
+    WgParams p;
+    p.N = N; p.Hb = Hb; p.Wb = Wb; p.mh = m_off_h; p.mw = m_off_w; p.ah = a_off_h; p.aw = a_off_w;
+    p.Cm_real = Cm_real; p.Ca = Ca; p.T = T; p.f16 = f16; p.out_scale = out_scale;
+    for (int t = 0; t < T; ++t) { p.dr[t] = (signed char)tap_dr[t]; p.ds[t] = (signed char)tap_ds[t]; }
+    int TW = Wb >= 16 ? 16 : pow2_ceil(Wb);
+    int TH = 64 / TW;
+    if (TH > pow2_ceil(Hb)) TH = pow2_ceil(Hb);
+    int TN = 64 / (TW * TH);
+    p.TW = TW; p.TH = TH; p.TN = TN;
+    p.tiles_w = dsr_cdiv(Wb, TW); p.tiles_h = dsr_cdiv(Hb, TH);
+    p.tiles_total = p.tiles_w * p.tiles_h * dsr_cdiv(N, TN);
+    int bn = Ca >= 256 ? 256 : (Ca >= 128 ? 128 : 64);
+    if (npass == 3 && bn == 256) bn = 128;
+    p.n_tiles_c = dsr_cdiv(Ca, bn);
+    int tiles_m = dsr_cdiv(Cm_real, 128);
+    long ctas = (long)T * tiles_m * p.n_tiles_c;
+    int splits = 1;
+    if (split_k < 0) {
+        splits = (int)((2L * dsr_num_sms() + ctas - 1) / ctas);
+        if (splits > p.tiles_total / 4) splits = p.tiles_total / 4;
+        if (splits < 1) splits = 1;
+    } else if (split_k > 1) splits = split_k;
+    p.tiles_per_split = dsr_cdiv(p.tiles_total, splits);
+    splits = dsr_cdiv(p.tiles_total, p.tiles_per_split);
+    if (splits > 1 && cudaMemsetAsync(dWp, 0, (size_t)Cm_real * T * Ca * sizeof(float), ST(stream)) != cudaSuccess) {
+        dsr_set_error("wgrad_tc: memset failed"); return DSR_ERR_CUDA;
+    }
+    CUtensorMap mmh, mml, mah, mal;
+    cuuint64_t mdims[4] = {(cuuint64_t)Cm, (cuuint64_t)Wm, (cuuint64_t)Hm, (cuuint64_t)N};
+    cuuint64_t mstr[3] = {(cuuint64_t)Cm * 2, (cuuint64_t)Wm * Cm * 2, (cuuint64_t)Hm * Wm * Cm * 2};
+    cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
+    cuuint64_t astr[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)Wa * Ca * 2, (cuuint64_t)Ha * Wa * Ca * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    int rc = encode_map(&mmh, M_hi, 4, mdims, mstr, box);
+    if (rc) return rc;
+    mml = mmh;
+    if (npass >= 2 && (rc = encode_map(&mml, M_lo, 4, mdims, mstr, box))) return rc;
+    if ((rc = encode_map(&mah, A_hi, 4, adims, astr, box))) return rc;
+    mal = mah;
+    if (npass >= 3 && (rc = encode_map(&mal, A_lo, 4, adims, astr, box))) return rc;
+    dim3 grid((unsigned)T, (unsigned)(tiles_m * p.n_tiles_c), (unsigned)splits);
+    if (npass == 1) return dispatch_wg<1>(bn, mmh, mml, mah, mal, p, dWp, grid, ST(stream));
+    if (npass == 2) return dispatch_wg<2>(bn, mmh, mml, mah, mal, p, dWp, grid, ST(stream));
+    return dispatch_wg<3>(bn, mmh, mml, mah, mal, p, dWp, grid, ST(stream));
+}
+
+extern "C" int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
+                                   float* grad, int accumulate, void* stream) {
+    DSR_REQUIRE(dWp && grad, "null pointer");
+    DSR_REQUIRE(variant == DSR_TC_W_CONV || variant == DSR_TC_W_CONV_PAIR || variant == DSR_TC_W_CONV_S2D, "unsupported variant");
+    tc_unpack_wgrad_kernel<<<dsr_grid((long)D0 * D1 * R * S, 256), 256, 0, ST(stream)>>>(dWp, D0, D1, R, S, variant, Cp, T, Ca, grad,
+                                                                                        accumulate);
+    return dsr_check_launch("tc_unpack_wgrad");
 }

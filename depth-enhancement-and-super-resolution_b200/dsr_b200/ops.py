@@ -140,6 +140,7 @@ CONFIG = {
     "dtype": "f16",      # forward operand format: "f16" (11-bit significand, hi+lo = 22 bits) or "bf16" (8 / 16 bits)
     "bwd_dtype": "bf16", # backward (gradient) operand format: gradients span too many octaves for unscaled f16
     "tc_backward": True, # run dgrad / wgrad on the tcgen05 path as well
+    "wgrad_passes": 3,   # weight-gradient GEMM: 1 = one 16-bit pass, 2 = dY hi+lo, 3 = dY and x hi+lo
     "split_k": -1,       # -1 = automatic split-K for tiny-M layers
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
@@ -164,7 +165,7 @@ def _int_array(vals):
     return (ctypes.c_int * len(vals))(*vals)
 
 
-def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W):
+def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W, min_ci=16):
     """Which arranged-operand layout serves this layer on the tcgen05 path (None -> CUDA-core path)."""
     if CONFIG["engine"] != "tc" or R != S:
         return None
@@ -172,7 +173,7 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W):
         if Ci == 32:
             return dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=32, Ca=64, T=R * ((S + 1) // 2))
         return dict(layout=_LAYOUT_NORMAL, variant=_W_CONV, Cp=_rup(Ci, 8), Ca=_rup(Ci, 64), T=R * S)
-    if kind == "conv" and stride == 2 and R in (3, 4) and pad == 1 and H % 2 == 0 and W % 2 == 0 and Ci >= 16:
+    if kind == "conv" and stride == 2 and R in (3, 4) and pad == 1 and H % 2 == 0 and W % 2 == 0 and Ci >= min_ci:
         Cp = _rup(Ci, 16)
         return dict(layout=_LAYOUT_S2D, variant=_W_CONV_S2D, Cp=Cp, Ca=4 * Cp, T=4)
     if kind == "convT" and stride == 2 and pad == 1 and ((R == 4 and opad == 0) or (R == 3 and opad == 1)) and Ci >= 32:
@@ -210,8 +211,33 @@ def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None):
     return whi, wlo
 
 
+class _Prepared:
+    """Arranged 16-bit copies of ONE fp32 NHWC tensor, made at most once per (layout, padding, format):
+    the backward pass feeds the same dY (or x) to the data-gradient and the weight-gradient GEMMs."""
+
+    def __init__(self, xh):
+        self.xh, self.made = xh, {}
+        self.shape, self.device = xh.shape, xh.device
+
+    def get(self, plan, pad, pad_mode, dtype=None):
+        key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dtype or CONFIG["dtype"])
+        hit = self.made.get(key)
+        if hit is None:
+            hit = self.made[key] = _tc_prep(self.xh, plan, pad, pad_mode, dtype=dtype)
+        return hit
+
+    def any_normal(self, Ca, dtype):
+        """an already-made NORMAL-layout zero-padded copy -> (ahi, alo, Ha, Wa, pad) or None"""
+        for (layout, _, ca, pad, mode, dt), v in self.made.items():
+            if layout == _LAYOUT_NORMAL and ca == Ca and dt == dtype and (mode == PAD_ZERO or pad == 0):
+                return v + (pad,)
+        return None
+
+
 def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=None):
     """fp32 NHWC -> arranged bf16 hi(+lo) operand."""
+    if isinstance(xh, _Prepared):
+        return xh.get(plan, pad, pad_mode, dtype)
     N, H, W, C = xh.shape
     Hq, Wq = H + 2 * pad, W + 2 * pad
     if plan["layout"] == _LAYOUT_S2D:
@@ -236,15 +262,7 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
         Co = weight.shape[0]
     ahi, alo, Ha, Wa = _tc_prep(xh, plan, pad, pad_mode, dtype=dtype)
     whi, wlo = _tc_weights(weight, plan, Co, dtype=dtype)
-    if plan["layout"] == _LAYOUT_PAIR:
-        S2 = (S + 1) // 2
-        dr = [t // S2 for t in range(plan["T"])]
-        ds = [2 * (t % S2) for t in range(plan["T"])]
-    elif plan["layout"] == _LAYOUT_S2D:
-        dr, ds = [0, 0, 1, 1], [0, 1, 0, 1]
-    else:
-        dr = [t // S for t in range(R * S)]
-        ds = [t % S for t in range(R * S)]
+    dr, ds = _tc_taps(plan, R, S)
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     _lib.PROFILE_META = dict(macs=macs if macs is not None else N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
     _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
@@ -313,6 +331,75 @@ def _tc_convT_dgrad(g, weight, stride, pad, H, W):
     return _tc_conv_fwd(g, weight, None, plan, stride, pad, PAD_ZERO, ACT_NONE, H, W, dtype=CONFIG["bwd_dtype"], Co=Ci)
 
 
+def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, variant):
+    """weight gradient GEMM over the base grid (Hb x Wb x N):  rows = channels of M (prepared NORMAL, zero pad),
+    columns = arranged channels of A x taps; result unpacked / accumulated into the parameter's gradient."""
+    dt, npass = CONFIG["bwd_dtype"], min(CONFIG["wgrad_passes"], CONFIG["passes"])
+    Cm = _rup(Cm_real, 64)
+    got = M.any_normal(Cm, dt)
+    if got is None:
+        m_plan = dict(layout=_LAYOUT_NORMAL, Cp=_rup(Cm_real, 8), Ca=Cm)
+        got = M.get(m_plan, 0, PAD_ZERO, dt) + (0,)
+    mhi, mlo, Hm, Wm, mpad = got
+    ahi, alo, Ha, Wa = A.get(a_plan, a_pad, a_pad_mode, dt)
+    N = M.shape[0]
+    T, Ca = a_plan["T"], a_plan["Ca"]
+    D0, D1, R, S = weight.shape
+    dwp = torch.empty((Cm_real, T * Ca), device=M.device, dtype=torch.float32)
+    f16, _ = _tc_fmt(dt)
+    _lib.PROFILE_META = dict(macs=N * Hb * Wb * D0 * D1 * R * S, shape=(N, Hb, Wb, Cm_real, Ca, T, 0))
+    _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
+          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
+          Hb, Wb, _p(dwp), npass, f16, 1.0, -1)
+    tgt = DIRECT_GRADS.get(weight.data_ptr())
+    if tgt is not None:
+        _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(tgt), 1)
+        _grad_ready(weight)
+        return None
+    gw = torch.empty(weight.shape, device=M.device, dtype=torch.float32)
+    _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(gw), 0)
+    return gw
+
+
+def _tc_taps(plan, R, S):
+    if plan["layout"] == _LAYOUT_PAIR:
+        S2 = (S + 1) // 2
+        return [t // S2 for t in range(plan["T"])], [2 * (t % S2) for t in range(plan["T"])]
+    if plan["layout"] == _LAYOUT_S2D:
+        return [0, 0, 1, 1], [0, 1, 0, 1]
+    return [t // S for t in range(R * S)], [t % S for t in range(R * S)]
+
+
+def _tc_conv_wgrad(xP, gP, weight, stride, pad, pad_mode):
+    """dL/dW of a Conv2d on the tcgen05 path -> (handled, grad or None).  xP / gP: _Prepared x (N,H,W,Ci), dY."""
+    if not CONFIG["tc_backward"]:
+        return False, None
+    N, H, W, Ci = xP.shape
+    _, Ho, Wo, Co = gP.shape
+    _, _, R, S = weight.shape
+    plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
+    if plan is None:
+        return False, None
+    dr, ds = _tc_taps(plan, R, S)
+    return True, _tc_wgrad(gP, Co, xP, plan, pad, pad_mode, dr, ds, Ho, Wo, weight, plan["variant"])
+
+
+def _tc_convT_wgrad(xP, gP, weight, stride, pad):
+    """dL/dW of a stride-2 ConvTranspose2d = the weight gradient of the adjoint Conv2d (dY -> x) whose
+    (Cout=Ci, Cin=Co, R, S) weight is this very parameter."""
+    if not CONFIG["tc_backward"]:
+        return False, None
+    N, H, W, Ci = xP.shape
+    _, Ho, Wo, Co = gP.shape
+    _, _, R, S = weight.shape
+    plan = tc_conv_plan("conv", Co, Ci, R, S, stride, pad, 0, Ho, Wo, min_ci=1)
+    if plan is None or plan["layout"] != _LAYOUT_S2D or (Ho + 2 * pad - R) // stride + 1 != H or \
+            (Wo + 2 * pad - S) // stride + 1 != W:
+        return False, None
+    dr, ds = _tc_taps(plan, R, S)
+    return True, _tc_wgrad(xP, Ci, gP, plan, pad, PAD_ZERO, dr, ds, H, W, weight, _W_CONV_S2D)
+
+
 class _Conv2d(Function):
     """nn.Conv2d with zeros / reflect / replicate padding.  networks.py:378-379,385,413-414,453,544;
     translation_network.py:472,478,495,563."""
@@ -352,12 +439,13 @@ class _Conv2d(Function):
             g2 = torch.empty_like(g)
             _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
             g = g2
-        xp, p = _explicit_pad(xh, pad, pad_mode)                    # recomputed, not stored
-        Hp, Wp = xp.shape[1], xp.shape[2]
+        gP = _Prepared(g)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gxp = _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W)
+            gxp = _tc_conv_dgrad(gP, weight, stride, pad, pad_mode, H, W)
             if gxp is None:
+                xp, p = _explicit_pad(xh, pad, pad_mode)            # recomputed, not stored
+                Hp, Wp = xp.shape[1], xp.shape[2]
                 wk = _pack(weight, 0)                               # [(r,s,co)][ci]
                 gxp = torch.empty((N, Hp, Wp, Ci), device=g.device, dtype=torch.float32)
                 _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxp), N, Ho, Wo, Co, Hp, Wp, Ci, R, S, stride, p, 1, ACT_NONE)
@@ -367,9 +455,13 @@ class _Conv2d(Function):
                     gxp = gxh
             gx = nchw(gxp)
         if ctx.needs_input_grad[1]:
-            dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
-            _call("dsr_wgrad_simt", _p(xp), _p(g), _p(dwk), N, Hp, Wp, Ci, Ho, Wo, Co, R, S, stride, p)
-            gw = _weight_grad(dwk, weight, 1)
+            done, gw = _tc_conv_wgrad(_Prepared(xh), gP, weight, stride, pad, pad_mode)
+            if not done:
+                xp, p = _explicit_pad(xh, pad, pad_mode)
+                dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
+                _call("dsr_wgrad_simt", _p(xp), _p(g), _p(dwk), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
+                      stride, p)
+                gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
         return gx, gw, gb, None, None, None, None
@@ -421,18 +513,21 @@ class _ConvTranspose2d(Function):
             g2 = torch.empty_like(g)
             _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
             g = g2
+        gP = _Prepared(g)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gxh = _tc_convT_dgrad(g, weight, stride, pad, H, W)
+            gxh = _tc_convT_dgrad(gP, weight, stride, pad, H, W)
             if gxh is None:
                 wk = _pack(weight, 1)                   # [(r,s,co)][ci]
                 gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
                 _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
             gx = nchw(gxh)
         if ctx.needs_input_grad[1]:
-            dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
-            _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
-            gw = _weight_grad(dwk, weight, 1)
+            done, gw = _tc_convT_wgrad(_Prepared(xh), gP, weight, stride, pad)
+            if not done:
+                dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
+                _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
+                gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
         return gx, gw, gb, None, None, None, None

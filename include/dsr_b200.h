@@ -150,6 +150,16 @@ int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int C
                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
                 int split_k, int f16, float out_scale, void* stream);
 
+/* weight gradient on the tcgen05 path: dWp[cm][t*Ca + c] = sum_p M[p + moff][cm] * A[p + aoff + tap_t][c] over the
+ * base grid (Hb x Wb x N); M = arranged dY (Conv2d) or x (ConvTranspose2d), A = the arranged operand of the forward
+ * GEMM.  dWp is fp32 [Cm_real][T*Ca]; dsr_tc_unpack_wgrad scatters it back into the (D0, D1, R, S) parameter layout. */
+int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h,
+                 int m_off_w, const void* A_hi, const void* A_lo, int Ha, int Wa, int Ca, int T, const int* tap_dr,
+                 const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb, float* dWp, int npass, int f16,
+                 float out_scale, int split_k, void* stream);
+int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
+                        float* grad, int accumulate, void* stream);
+
 /* ---- optimizer ------------------------------------------------------------------------------- */
 /* torch.optim.Adam (defaults) over one flat arena.  models/main_model.py:176, :429. */
 int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,

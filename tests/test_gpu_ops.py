@@ -303,7 +303,7 @@ def test_conv2d_fwd_bwd(ops, case, engine):
     out = ops.conv2d(xc, wc, bc, s, p)
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= ftol
-    assert rel_l2(xc.grad.cpu(), x.grad) <= engine[3] and rel_l2(wc.grad.cpu(), w.grad) <= 1e-5
+    assert rel_l2(xc.grad.cpu(), x.grad) <= engine[3] and rel_l2(wc.grad.cpu(), w.grad) <= max(1e-5, engine[3])
     assert rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
 
 
@@ -325,7 +325,7 @@ def test_conv2d_fused_padding_modes(ops, engine, mode, k, Ci, Co, H, W):
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= engine[2]
     btol = max(2e-5, 2 * engine[2])        # the tanh backward reads the forward output
-    assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= btol
+    assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= max(btol, engine[3])
 
 
 CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
@@ -348,7 +348,7 @@ def test_conv_transpose2d_fwd_bwd(ops, case, engine):
     (out * go.cuda()).sum().backward()
     assert rel_l2(out.cpu(), ref.detach()) <= max(engine[2], 3e-5 if Ci >= 1024 else 0.0)
     btol = max(3e-5, 2 * engine[2])        # the tanh backward reads the forward output
-    assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= btol
+    assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= max(btol, engine[3])
     assert rel_l2(bc.grad.cpu(), b.grad) <= btol
 
 
@@ -368,6 +368,35 @@ def test_tc_large_tiles_and_split_k(ops):
             with torch.no_grad():
                 out = ops.conv2d(cl(x), w.cuda(), b.cuda(), s, p)
             assert rel_l2(out.cpu(), ref) <= 1e-5, (Ci, Co, k, s, N, H, W, split)
+    finally:
+        ops.CONFIG.update(old)
+
+
+@pytest.mark.parametrize("wpass,tol", [(3, 5e-5), (2, 4e-3), (1, 8e-3)])
+def test_tc_wgrad_large(ops, wpass, tol):
+    """weight gradient on the tcgen05 path: several 64-pixel K tiles, split-K, ragged edges, every layout
+    (NORMAL / PAIR / S2D conv, S2D transposed conv incl. the 1-channel head)."""
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=wpass)
+        for (kind, Ci, Co, k, s, p, op, N, H, W) in [("conv", 128, 128, 3, 1, 1, 0, 3, 40, 24), ("conv", 32, 128, 7, 1, 3, 0, 2, 36, 20),
+                                                     ("conv", 261, 64, 4, 2, 1, 0, 2, 32, 48), ("conv", 64, 128, 3, 2, 1, 0, 2, 24, 24),
+                                                     ("conv", 512, 512, 4, 2, 1, 0, 3, 4, 4), ("convT", 1024, 256, 4, 2, 1, 0, 2, 8, 8),
+                                                     ("convT", 128, 1, 4, 2, 1, 0, 2, 32, 32), ("convT", 128, 64, 3, 2, 1, 1, 2, 20, 12)]:
+            x = torch.randn(N, Ci, H, W, generator=G(80)).requires_grad_(True)
+            if kind == "conv":
+                w = (torch.randn(Co, Ci, k, k, generator=G(81)) * 0.05).requires_grad_(True)
+                ref = F.conv2d(x, w, None, stride=s, padding=p)
+            else:
+                w = (torch.randn(Ci, Co, k, k, generator=G(81)) * 0.05).requires_grad_(True)
+                ref = F.conv_transpose2d(x, w, None, stride=s, padding=p, output_padding=op)
+            go = torch.randn(ref.shape, generator=G(82))
+            (ref * go).sum().backward()
+            xc, wc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True)
+            out = ops.conv2d(xc, wc, None, s, p) if kind == "conv" else ops.conv_transpose2d(xc, wc, None, s, p, op)
+            (out * go.cuda()).sum().backward()
+            assert rel_l2(wc.grad.cpu(), w.grad) <= tol, (kind, Ci, Co, k, s, N, H, W, rel_l2(wc.grad.cpu(), w.grad))
+            assert rel_l2(xc.grad.cpu(), x.grad) <= 5e-5
     finally:
         ops.CONFIG.update(old)
 
