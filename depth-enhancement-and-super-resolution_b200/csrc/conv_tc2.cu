@@ -1,0 +1,409 @@
+// Halo-resident, persistent tcgen05 implicit GEMM (second-generation convolution kernel, sm_100a).
+//
+// Same GEMM form as conv_tc.cu (out[n,h*os+ph,w*os+pw,co] = bias[co] + sum_t sum_c A[n,h+ah+dr_t,w+aw+ds_t,c] W[co][t*Ca+c]),
+// different data movement.  Profiling the first kernel (profiles/r1_*) showed the 128x128 tile is bound by the
+// L2->SM operand feed: every tap re-loads a full 128-pixel A tile.  Here
+//   * an output tile is 8 (w) x 16 (h) pixels; for each 64-channel block ONE TMA box brings the whole input patch
+//     (16 pixels wide x (16 + max_dr) rows, SWIZZLE_128B, 2 KB per patch row) into shared memory and every tap
+//     of the window is issued straight from it: the A descriptor of tap (dr, ds) starts at patch + (dr*16+ds)*128 B
+//     with a stride of 2048 B between 8-row groups (one group = the 8 pixels of an output row); an A byte now
+//     crosses L2->SM once per 64-channel block instead of once per tap;
+//   * CTAs are persistent (grid = min(tiles, SMs)); the accumulator is double-buffered in TMEM
+//     (2 x BLOCK_N columns) so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * the epilogue can emit the InstanceNorm / GroupNorm statistics of its tile (per-(n, c) sum and sum of squares,
+//     fp64 red.add) so the separate channel_sums pass over the activation disappears.
+// Warp roles (224 threads): 0 = patch TMA producer, 1 = weight TMA producer, 2 = TMEM allocator + MMA issuer,
+// 3..6 = epilogue (TMEM lane quadrant = warp % 4).
+#include "tc_common.cuh"
+
+#define TC2_MAX_TAPS 64
+#define TC2_TH 16
+#define TC2_TW 8
+
+struct Tc2Params {
+    int N, Ht, Wt;
+    int tiles_w, tiles_h, tiles_co, total_tiles;
+    int Ca, T, cblocks;
+    int ah, aw, Hp, PW;       // patch = Hp rows x PW pixels x 128 B (PW = 8 + widest tap offset)
+    int Ho, Wo, Cout, os, ph, pw;
+    int act, f16, base_off_mode;
+    float out_scale;
+    int n_pb, n_ws;
+    unsigned patch_plane_bytes;    // Hp * PW * 128 rounded up to the 1024-byte swizzle repeat (smem placement)
+    unsigned patch_tx_bytes;       // Hp * PW * 128 (what one TMA box delivers)
+    signed char dr[TC2_MAX_TAPS], ds[TC2_MAX_TAPS];
+};
+
+// K-major SWIZZLE_128B descriptor with an explicit 8-row-group stride and base offset (start address not aligned to
+// the 1024-byte swizzle repeat: base_offset = (start >> 7) & 7)
+__device__ __forceinline__ uint64_t make_sdesc_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)(base_off & 7) << 49) | ((uint64_t)2 << 61);
+}
+
+// optional per-CTA wait-time counters (clock64 ticks): [0] MMA waits patch, [1] MMA waits weights, [2] MMA waits a free
+// accumulator, [3] MMA role total, [4] epilogue waits accumulator, [5] epilogue role total, [6] patch producer waits a
+// free buffer, [7] weight producer waits a free stage.  Enabled by dsr_tc2_set_debug (profiling aid).
+__device__ long long* g_tc2_dbg = nullptr;
+#define TC2_TIMED_WAIT(slot, bar, parity)                 \
+    do {                                                  \
+        if (dbg) {                                        \
+            const long long t0_ = clock64();              \
+            mbar_wait(bar, parity);                       \
+            dbg_acc[slot] += clock64() - t0_;             \
+        } else {                                          \
+            mbar_wait(bar, parity);                       \
+        }                                                 \
+    } while (0)
+
+template <int BLOCK_N, int NPASS>
+__global__ void __launch_bounds__(224, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                const __grid_constant__ Tc2Params p, const float* __restrict__ bias, float* __restrict__ out,
+                double* __restrict__ stats) {
+    constexpr int NA = NPASS >= 2 ? 2 : 1;
+    constexpr int NW = NPASS >= 3 ? 2 : 1;
+    constexpr uint32_t W_TILE = BLOCK_N * 128;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t patch_set = NA * p.patch_plane_bytes;
+    const uint32_t w_base = smem_base + p.n_pb * patch_set;
+    const uint32_t w_stage = NW * W_TILE;
+    const uint32_t bar_base = w_base + p.n_ws * w_stage;
+    // barriers: pf[n_pb] pe[n_pb] wf[n_ws] we[n_ws] af[2] ae[2], then the TMEM pointer
+    auto pf = [&](int i) { return bar_base + 8u * i; };
+    auto pe = [&](int i) { return bar_base + 8u * (p.n_pb + i); };
+    auto wf = [&](int i) { return bar_base + 8u * (2 * p.n_pb + i); };
+    auto we = [&](int i) { return bar_base + 8u * (2 * p.n_pb + p.n_ws + i); };
+    auto af = [&](int i) { return bar_base + 8u * (2 * p.n_pb + 2 * p.n_ws + i); };
+    auto ae = [&](int i) { return bar_base + 8u * (2 * p.n_pb + 2 * p.n_ws + 2 + i); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.n_pb + 2 * p.n_ws + 4);
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* dbg = g_tc2_dbg;
+    long long dbg_acc[3] = {0, 0, 0};
+    const long long t_start = dbg ? clock64() : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA_hi); tma_prefetch_desc(&mapW_hi);
+        if (NPASS >= 2) tma_prefetch_desc(&mapA_lo);
+        if (NPASS >= 3) tma_prefetch_desc(&mapW_lo);
+        for (int i = 0; i < p.n_pb; ++i) { mbar_init(pf(i), 1); mbar_init(pe(i), 1); }
+        for (int i = 0; i < p.n_ws; ++i) { mbar_init(wf(i), 1); mbar_init(we(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(af(i), 1); mbar_init(ae(i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===== patch producer: one box per (tile, 64-channel block) =====
+        if (lane == 0) {
+            int pi = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int r = tile / p.tiles_co;
+                const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+                const int th_i = r % p.tiles_h;
+                const int n = r / p.tiles_h;
+                const int hc = th_i * TC2_TH + p.ah, wc = tw_i * TC2_TW + p.aw;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
+                    const int b = pi % p.n_pb, it = pi / p.n_pb;
+                    TC2_TIMED_WAIT(0, pe(b), (it & 1) ^ 1);
+                    const uint32_t dst = smem_base + b * patch_set;
+                    mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
+                    tma_load_4d(dst, &mapA_hi, pf(b), cb << 6, wc, hc, n);
+                    if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb << 6, wc, hc, n);
+                }
+            }
+            if (dbg) dbg[blockIdx.x * 8 + 6] = dbg_acc[0];
+        }
+    } else if (warp == 1) {
+        // ===== weight producer: one [BLOCK_N x 64] tile (hi, lo) per (tile, block, tap) =====
+        if (lane == 0) {
+            int wi = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int co0 = (tile % p.tiles_co) * BLOCK_N;
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    for (int t = 0; t < p.T; ++t, ++wi) {
+                        const int s = wi % p.n_ws, it = wi / p.n_ws;
+                        TC2_TIMED_WAIT(0, we(s), (it & 1) ^ 1);
+                        const uint32_t dst = w_base + s * w_stage;
+                        const int kw = t * p.Ca + (cb << 6);
+                        mbar_expect_tx(wf(s), w_stage);
+                        tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
+                        if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
+                    }
+                }
+            }
+            if (dbg) dbg[blockIdx.x * 8 + 7] = dbg_acc[0];
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
+            const uint32_t sbo = (uint32_t)p.PW * 128u;       // stride between the 8-pixel row groups of the patch
+            int pi = 0, wi = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+                const int ab = ti & 1;
+                TC2_TIMED_WAIT(2, ae(ab), ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
+                uint32_t accum = 0;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
+                    const int b = pi % p.n_pb;
+                    TC2_TIMED_WAIT(0, pf(b), (pi / p.n_pb) & 1);
+                    tc_fence_after();
+                    const uint32_t patch_hi = smem_base + b * patch_set, patch_lo = patch_hi + p.patch_plane_bytes;
+                    for (int t = 0; t < p.T; ++t, ++wi) {
+                        const int s = wi % p.n_ws;
+                        TC2_TIMED_WAIT(1, wf(s), (wi / p.n_ws) & 1);
+                        tc_fence_after();
+                        const uint32_t w_hi = w_base + s * w_stage, w_lo = w_hi + W_TILE;
+                        const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 128u;
+                        const uint32_t boff = p.base_off_mode ? (uint32_t)(p.ds[t] & 7) : 0u;
+#pragma unroll
+                        for (int pass = 0; pass < NPASS; ++pass) {
+                            const uint32_t a = ((pass == 1) ? patch_lo : patch_hi) + shift;
+                            const uint32_t w = (pass == 2) ? w_lo : w_hi;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                tc_mma_bf16(d_tmem, make_sdesc_ex(a + kk * 32, sbo, boff), make_sdesc(w + kk * 32), idesc, accum);
+                                accum = 1;
+                            }
+                        }
+                        tc_commit(we(s));
+                    }
+                    tc_commit(pe(b));
+                }
+                tc_commit(af(ab));
+            }
+            if (dbg) {
+                dbg[blockIdx.x * 8 + 0] = dbg_acc[0]; dbg[blockIdx.x * 8 + 1] = dbg_acc[1];
+                dbg[blockIdx.x * 8 + 2] = dbg_acc[2]; dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
+            }
+        }
+    } else {
+        // ===== epilogue warps 3..6 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int th = row >> 3, tw = row & 7;
+        constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const int ab = ti & 1;
+            int r = tile / p.tiles_co;
+            const int co0 = (tile - r * p.tiles_co) * BLOCK_N;
+            const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+            const int th_i = r % p.tiles_h;
+            const int n = r / p.tiles_h;
+            const int h = th_i * TC2_TH + th, w = tw_i * TC2_TW + tw;
+            const bool valid = (h < p.Ht) && (w < p.Wt);
+            float* orow = out + ((((long)n * p.Ho + (long)h * p.os + p.ph) * p.Wo) + (long)w * p.os + p.pw) * p.Cout;
+            TC2_TIMED_WAIT(0, af(ab), (ti >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BLOCK_N + c0);
+                if (CH == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int co = co0 + c0 + j;
+                    float x = 0.f;
+                    if (valid && co < p.Cout) {
+                        x = __uint_as_float(v[j]) * p.out_scale;
+                        if (bias != nullptr) x += __ldg(bias + co);
+                    }
+                    f[j] = x;
+                }
+                if (valid) {
+                    if (p.act == DSR_ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(tanhf(f[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(f[j]);
+                    }
+                    if ((p.Cout & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < CH; j += 4) {
+                            const int co = co0 + c0 + j;
+                            if (co < p.Cout)
+                                *reinterpret_cast<uint4*>(orow + co) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const int co = co0 + c0 + j;
+                            if (co < p.Cout) orow[co] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+                if (stats != nullptr && CH == 32) {
+                    // column sums over the warp's 32 pixels by a reduce-scatter butterfly: after the five exchange steps
+                    // lane l holds the total of channel c0 + l (31 shuffles per quantity instead of 160)
+                    float g[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) g[j] = f[j] * f[j];
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const bool up = (lane & step) != 0;
+#pragma unroll
+                        for (int j = 0; j < step; ++j) {
+                            const float sf = up ? f[j] : f[j + step];
+                            const float sg = up ? g[j] : g[j + step];
+                            const float rf = __shfl_xor_sync(0xffffffffu, sf, step);
+                            const float rg = __shfl_xor_sync(0xffffffffu, sg, step);
+                            f[j] = (up ? f[j + step] : f[j]) + rf;
+                            g[j] = (up ? g[j + step] : g[j]) + rg;
+                        }
+                    }
+                    const int co = co0 + c0 + lane;
+                    if (co < p.Cout) {
+                        double* sp = stats + ((long)n * p.Cout + co) * 2;
+                        atomicAdd(sp, (double)f[0]);
+                        atomicAdd(sp + 1, (double)g[0]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ae(ab));
+        }
+        if (dbg && warp == 3 && lane == 0) { dbg[blockIdx.x * 8 + 4] = dbg_acc[0]; dbg[blockIdx.x * 8 + 5] = clock64() - t_start; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+#define ST(s) ((cudaStream_t)(s))
+static const int TC2_SMEM_MAX = 227 * 1024;
+
+template <int BLOCK_N, int NPASS>
+static int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                      const Tc2Params& p, const float* bias, float* out, double* stats, int grid, int smem, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_MAX) != cudaSuccess) {
+            dsr_set_error("conv_tc2: cannot raise dynamic shared memory to %d", TC2_SMEM_MAX);
+            return DSR_ERR_CUDA;
+        }
+        attr = true;
+    }
+    conv_tc2_kernel<BLOCK_N, NPASS><<<grid, 224, smem, st>>>(ah, al, wh, wl, p, bias, out, stats);
+    return dsr_check_launch("conv_tc2");
+}
+
+template <int NPASS>
+static int dispatch_tc2(int bn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                        const Tc2Params& p, const float* bias, float* out, double* stats, int grid, int smem, cudaStream_t st) {
+    switch (bn) {
+        case 16: return launch_tc2<16, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+        case 32: return launch_tc2<32, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+        case 64: return launch_tc2<64, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+        case 128: return launch_tc2<128, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+        case 256: return launch_tc2<256, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+    }
+    dsr_set_error("conv_tc2: unsupported BLOCK_N %d", bn);
+    return DSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int dsr_tc2_set_debug(long long* counters) {
+    if (cudaMemcpyToSymbol(g_tc2_dbg, &counters, sizeof(counters)) != cudaSuccess) {
+        dsr_set_error("dsr_tc2_set_debug: cudaMemcpyToSymbol failed");
+        return DSR_ERR_CUDA;
+    }
+    return DSR_OK;
+}
+
+static int tc2_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
+                            int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
+                            const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                            int f16, float out_scale, double* stats, void* stream) {
+    DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
+    DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
+    DSR_REQUIRE(T >= 1 && T <= TC2_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
+    DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)W_hi & 15) && !((uintptr_t)out & 15), "buffers must be 16-byte aligned");
+    DSR_REQUIRE(!stats || act == DSR_ACT_NONE, "statistics are taken before any activation");
+    Tc2Params p;
+    int max_dr = 0, max_ds = 0;
+    for (int t = 0; t < T; ++t) {
+        if (tap_dr[t] < 0 || tap_ds[t] < 0) { dsr_set_error("conv_tc2: negative tap offset"); return DSR_ERR_UNSUPPORTED; }
+        p.dr[t] = (signed char)tap_dr[t]; p.ds[t] = (signed char)tap_ds[t];
+        if (tap_dr[t] > max_dr) max_dr = tap_dr[t];
+        if (tap_ds[t] > max_ds) max_ds = tap_ds[t];
+    }
+    if (max_ds > 8 || (long)Ht * Wt < 128 || Wt < TC2_TW) {
+        dsr_set_error("conv_tc2: shape not covered (tap window %d wide, output %dx%d)", max_ds + 1, Ht, Wt);
+        return DSR_ERR_UNSUPPORTED;
+    }
+    int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : (Cout > 16 ? 32 : 16)));
+    if (stats && bn < 32) bn = 32;
+    bn = tc2_env("DSR_TC2_BN", bn);
+    p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.cblocks = Ca / 64;
+    p.ah = a_off_h; p.aw = a_off_w; p.Hp = TC2_TH + max_dr;
+    p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.os = os; p.ph = ph; p.pw = pw; p.act = act;
+    p.f16 = f16; p.out_scale = out_scale;
+    p.base_off_mode = tc2_env("DSR_TC2_BASEOFF", 0);   // measured on B200: the swizzle XOR uses absolute smem address bits,
+                                                        // so shifted descriptor starts need NO base offset
+    p.tiles_w = dsr_cdiv(Wt, TC2_TW); p.tiles_h = dsr_cdiv(Ht, TC2_TH); p.tiles_co = dsr_cdiv(Cout, bn);
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_co * N;
+    p.PW = tc2_env("DSR_TC2_PW", TC2_TW + max_ds);
+    p.patch_tx_bytes = (unsigned)p.Hp * p.PW * 128u;
+    p.patch_plane_bytes = (p.patch_tx_bytes + 1023u) & ~1023u;
+    const int na = npass >= 2 ? 2 : 1, nw = npass >= 3 ? 2 : 1;
+    const long patch_set = (long)na * p.patch_plane_bytes, w_stage = (long)nw * bn * 128;
+    const long budget = TC2_SMEM_MAX - 1024 - 512;
+    // shared-memory plan: double-buffer the patch when at least 4 weight stages (>= 96 KB in flight hides the L2
+    // latency at full MMA rate) still fit beside it
+    const int want_ws = tc2_env("DSR_TC2_MINWS", 4);
+    p.n_pb = (2 * patch_set + want_ws * w_stage <= budget && (p.cblocks > 1 || p.total_tiles > dsr_num_sms())) ? 2 : 1;
+    p.n_pb = tc2_env("DSR_TC2_NPB", p.n_pb);
+    long ws = (budget - p.n_pb * patch_set) / w_stage;
+    if (ws > 8) ws = 8;
+    if (ws < 2) { dsr_set_error("conv_tc2: tile does not fit shared memory"); return DSR_ERR_UNSUPPORTED; }
+    p.n_ws = (int)ws;
+    const int smem = (int)(p.n_pb * patch_set + p.n_ws * w_stage + 1024 + 512);
+
+    CUtensorMap mah, mal, mwh, mwl;
+    cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
+    cuuint64_t astr[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)Wa * Ca * 2, (cuuint64_t)Ha * Wa * Ca * 2};
+    cuuint32_t abox[4] = {64, (cuuint32_t)p.PW, (cuuint32_t)p.Hp, 1};
+    int rc = encode_map(&mah, A_hi, 4, adims, astr, abox);
+    if (rc) return rc;
+    mal = mah;
+    if (npass >= 2 && (rc = encode_map(&mal, A_lo, 4, adims, astr, abox))) return rc;
+    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout};
+    cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
+    if ((rc = encode_map(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;
+    mwl = mwh;
+    if (npass >= 3 && (rc = encode_map(&mwl, W_lo, 2, wdims, wstr, wbox))) return rc;
+    int grid = p.total_tiles < dsr_num_sms() ? p.total_tiles : dsr_num_sms();
+    if (npass == 1) return dispatch_tc2<1>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    if (npass == 2) return dispatch_tc2<2>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    return dispatch_tc2<3>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+}

@@ -29,9 +29,10 @@ class Identity(nn.Module):                        # networks.py:13-15
 class Conv2d(nn.Conv2d):
     """nn.Conv2d with zeros / reflect / replicate ``padding_mode`` (networks.py:379; translation_network.py:472)."""
 
-    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None):
+    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None, want_stats=False):
         """pre_pad = (pad, mode) of an nn.ReflectionPad2d / ReplicationPad2d module placed right before
-        this conv: it is folded into the conv's operand preparation instead of materialising a padded copy."""
+        this conv: it is folded into the conv's operand preparation instead of materialising a padded copy.
+        want_stats: also return the per-(n, c) statistics of the output for the norm layer that follows."""
         if self.dilation != (1, 1) or self.groups != 1:
             raise NotImplementedError("dsr_b200.Conv2d: dilation/groups are not on the hot path")
         p, mode = self.padding[0], self.padding_mode
@@ -39,13 +40,13 @@ class Conv2d(nn.Conv2d):
             if p != 0:
                 raise NotImplementedError("dsr_b200.Conv2d: explicit pad module followed by a padded conv")
             p, mode = pre_pad
-        return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode)
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode, want_stats=want_stats)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):        # networks.py:406, :553
-    def forward(self, x, act_out=ops.ACT_NONE):
+    def forward(self, x, act_out=ops.ACT_NONE, want_stats=False):
         return ops.conv_transpose2d(x, self.weight, self.bias, self.stride[0], self.padding[0],
-                                    self.output_padding[0], act_out)
+                                    self.output_padding[0], act_out, want_stats=want_stats)
 
 
 class ReflectionPad2d(nn.ReflectionPad2d):        # networks.py:378
@@ -59,15 +60,15 @@ class ReplicationPad2d(nn.ReplicationPad2d):
 
 
 class InstanceNorm2d(nn.InstanceNorm2d):          # networks.py:30 (affine=False, no running stats)
-    def forward(self, x, act=ops.ACT_NONE, residual=None):
+    def forward(self, x, act=ops.ACT_NONE, residual=None, stats=None):
         if self.affine or self.track_running_stats:
             raise NotImplementedError("dsr_b200.InstanceNorm2d: only affine=False, track_running_stats=False")
-        return ops.instance_norm(x, self.eps, act, residual)
+        return ops.instance_norm(x, self.eps, act, residual, stats)
 
 
 class GroupNorm(nn.GroupNorm):                    # translation_network.py:46
-    def forward(self, x, act=ops.ACT_NONE, residual=None):
-        return ops.group_norm(x, self.num_groups, self.weight, self.bias, self.eps, act, residual)
+    def forward(self, x, act=ops.ACT_NONE, residual=None, stats=None):
+        return ops.group_norm(x, self.num_groups, self.weight, self.bias, self.eps, act, residual, stats)
 
 
 class ReLU(nn.ReLU):
@@ -85,32 +86,56 @@ class Tanh(nn.Tanh):
         return ops.tanh(x)
 
 
-def run_fused(mods, x):
-    """Run a module list, fusing the adjacent pairs our kernels handle in one pass:
-    norm + ReLU, conv + Tanh."""
-    i = 0
+def _conv_like(m):
+    """the Conv2d / ConvTranspose2d a module list entry runs (translation_network.ConvTranspose wraps one)"""
+    if isinstance(m, (Conv2d, ConvTranspose2d)):
+        return m
+    inner = getattr(m, "transposeconv", None)
+    return inner if isinstance(inner, ConvTranspose2d) else None
+
+
+def run_fused(mods, x, tail_stats=False):
+    """Run a module list, fusing what our kernels handle in one pass: pad module + conv, conv + Tanh, norm + ReLU,
+    and conv -> norm statistics (taken by the GEMM epilogue, handed to the norm layer).  tail_stats: the list ends
+    with a conv whose norm layer is applied by the caller (residual blocks) -> returns (x, stats)."""
+    norms = (InstanceNorm2d, GroupNorm)
+    i, stats = 0, None
     while i < len(mods):
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < len(mods) else None
-        if isinstance(m, (InstanceNorm2d, GroupNorm)) and isinstance(nxt, ReLU):
-            x = m(x, act=ops.ACT_RELU)
-            i += 2
-        elif isinstance(m, (ReflectionPad2d, ReplicationPad2d)) and isinstance(nxt, Conv2d) and nxt.padding[0] == 0:
-            mode = "reflect" if isinstance(m, ReflectionPad2d) else "replicate"
-            nn2 = mods[i + 2] if i + 2 < len(mods) else None
-            if isinstance(nn2, Tanh):
-                x = nxt(x, act_out=ops.ACT_TANH, pre_pad=(m.padding[0], mode))
-                i += 3
-            else:
-                x = nxt(x, pre_pad=(m.padding[0], mode))
+        if isinstance(m, norms):
+            if isinstance(nxt, ReLU):
+                x = m(x, act=ops.ACT_RELU, stats=stats)
                 i += 2
-        elif isinstance(m, (Conv2d, ConvTranspose2d)) and isinstance(nxt, Tanh):
-            x = m(x, act_out=ops.ACT_TANH)
-            i += 2
-        else:
-            x = m(x)
-            i += 1
-    return x
+            else:
+                x = m(x, stats=stats)
+                i += 1
+            stats = None
+            continue
+        stats = None
+        pre_pad, j = None, i
+        if isinstance(m, (ReflectionPad2d, ReplicationPad2d)) and isinstance(nxt, Conv2d) and nxt.padding[0] == 0:
+            pre_pad = (m.padding[0], "reflect" if isinstance(m, ReflectionPad2d) else "replicate")
+            j = i + 1
+        conv = _conv_like(mods[j])
+        if conv is not None:
+            after = mods[j + 1] if j + 1 < len(mods) else None
+            kw = {}
+            if pre_pad is not None:
+                kw["pre_pad"] = pre_pad
+            if isinstance(after, Tanh):
+                x = conv(x, act_out=ops.ACT_TANH, **kw)
+                i = j + 2
+            elif isinstance(after, norms) or (after is None and tail_stats):
+                x, stats = conv(x, want_stats=True, **kw)
+                i = j + 1
+            else:
+                x = conv(x, **kw)
+                i = j + 1
+            continue
+        x = m(x)
+        i += 1
+    return (x, stats) if tail_stats else x
 
 
 class FusedSequential(nn.Sequential):
@@ -285,7 +310,8 @@ class ResnetBlock(nn.Module):                     # networks.py:424-481
     def forward(self, x):
         mods = list(self.conv_block)
         if isinstance(mods[-1], (InstanceNorm2d, GroupNorm)):      # skip add fused into the norm pass
-            return mods[-1](run_fused(mods[:-1], x), residual=x)   # networks.py:480
+            y, stats = run_fused(mods[:-1], x, tail_stats=True)
+            return mods[-1](y, residual=x, stats=stats)            # networks.py:480
         return x + self.conv_block(x)
 
 

@@ -142,6 +142,9 @@ CONFIG = {
     "tc_backward": True, # run dgrad / wgrad on the tcgen05 path as well
     "wgrad_passes": 3,   # weight-gradient GEMM: 1 = one 16-bit pass, 2 = dY hi+lo, 3 = dY and x hi+lo
     "split_k": -1,       # -1 = automatic split-K for tiny-M layers
+    "tc_halo": True,     # second-generation GEMM (halo-resident A patches, persistent CTAs) wherever it applies
+    "tc_cm": True,       # third-generation channel-major GEMM for Cout >= 128 layers
+    "halo_min_tiles": 120,
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
 _LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
@@ -252,7 +255,36 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=N
     return ahi, alo, Ha, Wa
 
 
-def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo, dtype=None, Co=None, macs=None):
+def _tc_kernel_for(N, Ht, Wt, Co, ds):
+    """which GEMM kernel serves this output grid: 3 = channel-major (csrc/conv_tc3.cu, Cout >= 128), 2 = halo
+    pixel-major (csrc/conv_tc2.cu), 1 = first generation with split-K (few tiles, long K; forced split-K)."""
+    if not CONFIG["tc_halo"] or CONFIG["split_k"] > 1 or Ht * Wt < 128 or Wt < 8 or max(ds) > 8:
+        return 1
+    if Co >= 128 and Ht >= 16 and CONFIG["tc_cm"]:
+        tiles = N * ((Ht + 31) // 32) * ((Wt + 7) // 8) * ((Co + 127) // 128)
+        return 3 if tiles >= CONFIG["halo_min_tiles"] else 1
+    bn = 256 if Co >= 256 else 128
+    tiles = N * ((Ht + 15) // 16) * ((Wt + 7) // 8) * ((Co + bn - 1) // bn)
+    return 2 if tiles >= CONFIG["halo_min_tiles"] else 1
+
+
+def _tc_gemm(ahi, alo, N, Ha, Wa, Ca, whi, wlo, Co, T, dr, ds, aoh, aow, Ht, Wt, bias, y, Ho, Wo, os_, ph, pw, act_out,
+             dtype, split_k, stats=None):
+    """one GEMM launch on the best kernel for the shape; returns True when `stats` was filled by the epilogue"""
+    which = CONFIG.get("force_kernel") or _tc_kernel_for(N, Ht, Wt, Co, list(ds))
+    if which == 1:
+        _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
+              _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
+              Ho, Wo, os_, ph, pw, act_out, CONFIG["passes"], split_k, *_tc_fmt(dtype))
+        return False
+    _call("dsr_tc_gemm3" if which == 3 else "dsr_tc_gemm2", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
+          _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
+          Ho, Wo, os_, ph, pw, act_out, CONFIG["passes"], *_tc_fmt(dtype), _p(stats, torch.float64))
+    return stats is not None
+
+
+def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo, dtype=None, Co=None, macs=None,
+                 stats=None):
     """stride-1 / stride-2 convolution of `xh` with a Conv2d-layout weight on the tcgen05 path.
     Also serves as the dgrad of ConvTranspose2d (its weight read as a Conv2d weight) and, with
     plan['variant'] == _W_CONV_DGRAD, as the dgrad of a stride-1 Conv2d (flipped / transposed taps)."""
@@ -265,13 +297,14 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
     dr, ds = _tc_taps(plan, R, S)
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     _lib.PROFILE_META = dict(macs=macs if macs is not None else N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
-    _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
-          _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0,
-          Ho, Wo, _p(bias), _p(y), Ho, Wo, 1, 0, 0, act_out, CONFIG["passes"], CONFIG["split_k"], *_tc_fmt(dtype))
+    filled = _tc_gemm(ahi, alo, N, Ha, Wa, plan["Ca"], whi, wlo, Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0, Ho, Wo,
+                      bias, y, Ho, Wo, 1, 0, 0, act_out, dtype, CONFIG["split_k"], stats)
+    if stats is not None:
+        stats.filled = filled
     return y
 
 
-def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None):
+def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stats=None):
     """stride-2 transposed convolution (4 output phases) of `xh` with a ConvTranspose2d-layout weight;
     also the dgrad of a stride-2 Conv2d (whose (Cout, Cin, R, S) weight IS a ConvTranspose2d weight
     from Cout to Cin channels)."""
@@ -285,9 +318,10 @@ def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None):
         for b in (0, 1):
             whi, wlo = _tc_weights(weight, plan, Co, phase=(a, b), pad=pad, dtype=dtype)
             _lib.PROFILE_META = dict(macs=N * H * W * Co * Ci * R * S // 4, shape=(N, H, W, Ci, Co, R, -2))
-            _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, plan["Ca"],
-                  _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, 4, dr, ds, a, b, Ht, Wt, _p(bias), _p(y),
-                  Ho, Wo, 2, a, b, act_out, CONFIG["passes"], 1, *_tc_fmt(dtype))
+            filled = _tc_gemm(ahi, alo, N, Ha, Wa, plan["Ca"], whi, wlo, Co, 4, dr, ds, a, b, Ht, Wt, bias, y, Ho, Wo, 2, a, b,
+                              act_out, dtype, 1, stats)
+    if stats is not None:
+        stats.filled = filled
     return y
 
 
@@ -405,7 +439,7 @@ class _Conv2d(Function):
     translation_network.py:472,478,495,563."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out):
+    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out, want_stats):
         xh = nhwc(x)
         N, H, W, Ci = xh.shape
         Co, Ci2, R, S = weight.shape
@@ -413,9 +447,10 @@ class _Conv2d(Function):
             raise ValueError(f"conv2d: input has {Ci} channels, weight expects {Ci2}")
         Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
         b = bias.detach() if bias is not None else None
+        stats = _new_stats(N, Co, x.device) if want_stats else None
         plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
         if plan is not None:
-            y = _tc_conv_fwd(xh, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo)
+            y = _tc_conv_fwd(xh, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, stats=stats)
         else:
             xp, p = _explicit_pad(xh, pad, pad_mode)
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
@@ -425,10 +460,10 @@ class _Conv2d(Function):
         ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None)
         ctx.bias_ref = bias
         ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
-        return nchw(y)
+        return _with_stats(ctx, y, stats)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gstats=None):
         xh, weight, y = ctx.saved_tensors
         stride, pad, pad_mode, act_out, has_bias = ctx.cfg
         N, H, W, Ci = xh.shape
@@ -464,7 +499,26 @@ class _Conv2d(Function):
                 gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
+
+
+def _new_stats(N, C, device):
+    """per-(n, c) (sum, sum of squares) accumulator the GEMM epilogue adds into (InstanceNorm / GroupNorm statistics)"""
+    st = torch.zeros(N * C * 2, device=device, dtype=torch.float64)
+    st.filled = False
+    return st
+
+
+def _with_stats(ctx, y, stats):
+    """Function outputs: the activation and (non-differentiable) its channel statistics, taken by the GEMM epilogue
+    when the kernel supports it and by one channel_sums pass otherwise."""
+    if stats is None:
+        return nchw(y), None
+    if not stats.filled:
+        N, H, W, C = y.shape
+        _call("dsr_channel_sums", _p(y), N, H * W, C, _p(stats, torch.float64))
+    ctx.mark_non_differentiable(stats)
+    return nchw(y), stats
 
 
 def _explicit_pad(xh, pad, pad_mode):
@@ -481,7 +535,7 @@ class _ConvTranspose2d(Function):
     """nn.ConvTranspose2d.  networks.py:406,553,605,612; translation_network.py:508."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, opad, act_out):
+    def forward(ctx, x, weight, bias, stride, pad, opad, act_out, want_stats):
         xh = nhwc(x)
         N, H, W, Ci = xh.shape
         Ci2, Co, R, S = weight.shape
@@ -489,9 +543,10 @@ class _ConvTranspose2d(Function):
             raise ValueError(f"conv_transpose2d: input has {Ci} channels, weight expects {Ci2}")
         Ho, Wo = (H - 1) * stride - 2 * pad + R + opad, (W - 1) * stride - 2 * pad + S + opad
         b = bias.detach() if bias is not None else None
+        stats = _new_stats(N, Co, x.device) if want_stats else None
         plan = tc_conv_plan("convT", Ci, Co, R, S, stride, pad, opad, H, W)
         if plan is not None:
-            y = _tc_convT_fwd(xh, weight, b, plan, pad, act_out, Ho, Wo)
+            y = _tc_convT_fwd(xh, weight, b, plan, pad, act_out, Ho, Wo, stats=stats)
         else:
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
             wk = _pack(weight, 0)                       # [(r,s,ci)][co]
@@ -499,10 +554,10 @@ class _ConvTranspose2d(Function):
         ctx.cfg = (stride, pad, act_out, bias is not None)
         ctx.bias_ref = bias
         ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
-        return nchw(y)
+        return _with_stats(ctx, y, stats)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gstats=None):
         xh, weight, y = ctx.saved_tensors
         stride, pad, act_out, has_bias = ctx.cfg
         N, H, W, Ci = xh.shape
@@ -530,16 +585,20 @@ class _ConvTranspose2d(Function):
                 gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO):
+def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO, want_stats=False):
+    """-> y, or (y, stats) with want_stats: stats = float64 [N*Cout*2] per-(n, c) (sum, sum of squares) of y for the
+    normalisation layer that follows (instance_norm / group_norm take it through their `stats` argument)."""
     pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
-    return _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out)
+    y, st = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats)
+    return (y, st) if want_stats else y
 
 
-def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE):
-    return _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out)
+def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE, want_stats=False):
+    y, st = _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out, want_stats)
+    return (y, st) if want_stats else y
 
 
 class _Pad2d(Function):
@@ -568,10 +627,13 @@ def pad2d(x, pad, mode):
 # ------------------------------------------------------------------------------------------------
 # normalisation / activation / concat
 # ------------------------------------------------------------------------------------------------
-def _norm_params(xh, groups, gamma, beta, eps):
+def _norm_params(xh, groups, gamma, beta, eps, sums=None):
     N, H, W, C = xh.shape
-    sums = _zeros_f64(N * C * 2, xh.device)
-    _call("dsr_channel_sums", _p(xh), N, H * W, C, _p(sums, torch.float64))
+    if sums is None:
+        sums = _zeros_f64(N * C * 2, xh.device)
+        _call("dsr_channel_sums", _p(xh), N, H * W, C, _p(sums, torch.float64))
+    elif sums.numel() != N * C * 2:
+        raise ValueError("norm statistics do not match the activation shape")
     prm = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)
     _call("dsr_norm_finalize", _p(sums, torch.float64), N, C, H * W, groups, _p(gamma), _p(beta), eps, _p(prm))
     return prm
@@ -581,10 +643,10 @@ class _InstanceNorm(Function):
     """InstanceNorm2d(affine=False) [+ ReLU] [+ residual add].  networks.py:30, :380-381, :480."""
 
     @staticmethod
-    def forward(ctx, x, eps, act, residual):
+    def forward(ctx, x, eps, act, residual, stats):
         xh = nhwc(x)
         N, H, W, C = xh.shape
-        prm = _norm_params(xh, 0, None, None, eps)
+        prm = _norm_params(xh, 0, None, None, eps, stats)
         rh = nhwc(residual) if residual is not None else None
         y = torch.empty_like(xh)
         _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
@@ -606,14 +668,14 @@ class _InstanceNorm(Function):
             _call("dsr_in_bwd_apply", _p(xh), _p(g), _p(prm), _p(sums2, torch.float64), _p(gxh), N, H * W, C, ctx.act)
             gx = nchw(gxh)
         gres = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        return gx, None, None, gres
+        return gx, None, None, gres, None
 
 
-def instance_norm(x, eps=1e-5, act=ACT_NONE, residual=None):
-    return _InstanceNorm.apply(x, eps, act, residual)
+def instance_norm(x, eps=1e-5, act=ACT_NONE, residual=None, stats=None):
+    return _InstanceNorm.apply(x, eps, act, residual, stats)
 
 
-def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None):
+def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None, stats=None):
     """GroupNorm(groups, C, affine=True) [+ReLU] [+residual], forward only (G_A_d is frozen on the hot
     path, main_model.py:426).  translation_network.py:46."""
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
@@ -622,7 +684,7 @@ def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None):
                                   "(G_A_d is frozen); run the translation generator under torch.no_grad()")
     xh = nhwc(x)
     N, H, W, C = xh.shape
-    prm = _norm_params(xh, groups, weight.detach().contiguous(), bias.detach().contiguous(), eps)
+    prm = _norm_params(xh, groups, weight.detach().contiguous(), bias.detach().contiguous(), eps, stats)
     rh = nhwc(residual) if residual is not None else None
     y = torch.empty_like(xh)
     _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)

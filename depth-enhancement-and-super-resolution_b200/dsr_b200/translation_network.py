@@ -128,7 +128,8 @@ class ResnetBlock(nn.Module):                     # translation_network.py:554-5
 
     def forward(self, x):
         mods = list(self.conv_block)
-        return mods[-1](run_fused(mods[:-1], x), residual=x)       # translation_network.py:574
+        y, stats = run_fused(mods[:-1], x, tail_stats=True)
+        return mods[-1](y, residual=x, stats=stats)                # translation_network.py:574
 
 
 class ResnetBottlenec(nn.Module):                 # translation_network.py:533-552

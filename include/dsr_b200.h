@@ -150,6 +150,31 @@ int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int C
                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
                 int split_k, int f16, float out_scale, void* stream);
 
+/* second-generation GEMM (csrc/conv_tc2.cu): same contract as dsr_tc_gemm without split-K; the A operand of an 8x16-pixel
+ * output tile is ONE shared-memory patch per 64-channel block that every tap reads at a shifted descriptor address;
+ * persistent CTAs, double-buffered TMEM accumulators.  stats (may be NULL): double [N][Cout][2], pre-zeroed by the
+ * caller; the epilogue adds the per-(n, c) sum and sum of squares of the outputs (InstanceNorm2d / GroupNorm statistics,
+ * models/networks.py:30, models/translation_network.py:46).  Returns DSR_ERR_UNSUPPORTED (-3) for shapes it does not
+ * cover (tap window wider than 9, outputs smaller than 128 pixels or narrower than 8). */
+int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
+                 int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
+                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                 int f16, float out_scale, double* stats, void* stream);
+
+/* third-generation GEMM for Cout >= 128 (csrc/conv_tc3.cu): channel-major accumulator (M = 128 output channels,
+ * N = 8 x TH <= 256 pixels per MMA, the shape that runs at the tensor floor with both operands in shared memory),
+ * 32-channel K blocks (SWIZZLE_64B), tile height picked per layer to fill whole waves of SMs, coalesced NHWC stores and
+ * thread-local norm statistics.  Same contract as dsr_tc_gemm2; needs Ht >= 16 and Wt >= 8. */
+int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
+                 int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
+                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                 int f16, float out_scale, double* stats, void* stream);
+int dsr_tc3_set_debug(long long* counters);
+
+/* profiling aid: counters = device long long [grid][8] (or NULL to switch off): per-CTA clock64 ticks the roles of the
+ * dsr_tc_gemm2 kernel spent waiting (see csrc/conv_tc2.cu).  Synchronous (cudaMemcpyToSymbol). */
+int dsr_tc2_set_debug(long long* counters);
+
 /* weight gradient on the tcgen05 path: dWp[cm][t*Ca + c] = sum_p M[p + moff][cm] * A[p + aoff + tap_t][c] over the
  * base grid (Hb x Wb x N); M = arranged dY (Conv2d) or x (ConvTranspose2d), A = the arranged operand of the forward
  * GEMM.  dWp is fp32 [Cm_real][T*Ca]; dsr_tc_unpack_wgrad scatters it back into the (D0, D1, R, S) parameter layout. */

@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Per-layer micro-benchmark of the tcgen05 convolution kernels on the layer shapes of the five nets
+ at the C2 workload (12 images per call).  Checks each result against a torch
+fp32 convolution on the GPU (test infrastructure only) and prints time / executed TFLOP/s.
+
+  python scripts/bench_layers.py [--set fwd|all] [--halo 0|1|both] [--baseoff 0|1|both] [--iters 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "depth-enhancement-and-super-resolution_b200"))
+
+import torch
+import torch.nn.functional as F
+
+LAYERS = [  # name, kind, N, Ci, Co, k, stride, pad, pad_mode, H, W
+    ("res128 3x3 reflect (I2D/Depth_f block)", "conv", 12, 128, 128, 3, 1, 1, "reflect", 64, 64),
+    ("gad256 3x3 replicate (G_A_d block)", "conv", 6, 256, 256, 3, 1, 1, "replicate", 64, 64),
+    ("head 7x7 32->128 reflect", "conv", 12, 32, 128, 7, 1, 3, "reflect", 256, 256),
+    ("down 3x3 s2 32->64", "conv", 12, 32, 64, 3, 2, 1, "zeros", 256, 256),
+    ("down 3x3 s2 64->128", "conv", 12, 64, 128, 3, 2, 1, "zeros", 128, 128),
+    ("unet down 4x4 s2 261->64", "conv", 12, 261, 64, 4, 2, 1, "zeros", 256, 256),
+    ("unet down 4x4 s2 64->128", "conv", 12, 64, 128, 4, 2, 1, "zeros", 128, 128),
+    ("unet down 4x4 s2 128->256", "conv", 12, 128, 256, 4, 2, 1, "zeros", 64, 64),
+    ("unet down 4x4 s2 256->512", "conv", 12, 256, 512, 4, 2, 1, "zeros", 32, 32),
+    ("unet up convT 4x4 1024->256", "convT", 12, 1024, 256, 4, 2, 1, 0, 16, 16),
+    ("unet up convT 4x4 512->128", "convT", 12, 512, 128, 4, 2, 1, 0, 32, 32),
+    ("unet up convT 4x4 256->64", "convT", 12, 256, 64, 4, 2, 1, 0, 64, 64),
+    ("resnet up convT 3x3 128->64", "convT", 12, 128, 64, 3, 2, 1, 1, 64, 64),
+    ("gad up convT 4x4 256->128", "convT", 6, 256, 128, 4, 2, 1, 0, 64, 64),
+]
+
+
+def run(layer, ops, iters, check=True):
+    name, kind, N, Ci, Co, k, s, p, extra, H, W = layer
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    if kind == "conv":
+        w = (torch.randn(Co, Ci, k, k, generator=g) * 0.05).cuda()
+        fn = lambda: ops.conv2d(x, w, None, s, p, pad_mode=extra)
+        macs = N * (H // s) * (W // s) * Co * Ci * k * k
+    else:
+        w = (torch.randn(Ci, Co, k, k, generator=g) * 0.05).cuda()
+        fn = lambda: ops.conv_transpose2d(x, w, None, s, p, extra)
+        macs = N * H * W * Co * Ci * k * k
+    with torch.no_grad():
+        y = fn()
+        torch.cuda.synchronize()
+        err = None
+        if check:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            if kind == "conv":
+                mode = {"zeros": "constant"}.get(extra, extra)
+                ref = F.conv2d(F.pad(x, (p, p, p, p), mode=mode), w, None, stride=s)
+            else:
+                ref = F.conv_transpose2d(x, w, None, stride=s, padding=p, output_padding=extra)
+            err = float((y.double() - ref.double()).norm() / ref.double().norm())
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_all = e0.elapsed_time(e1) / iters
+        # GEMM-only time: record the library calls of one forward, then replay ONLY the GEMM calls back to back
+        # (queued launches hide the host-side tensor-map encoding) between two events
+        from dsr_b200 import _lib
+        calls, orig = [], _lib.call
+        _lib.call = lambda nm, *a: (calls.append((nm, a)), orig(nm, *a))[1]
+        fn()
+        _lib.call = orig
+        torch.cuda.synchronize()
+        gemms = [(nm, a) for nm, a in calls if nm in ("dsr_tc_gemm", "dsr_tc_gemm2", "dsr_tc_gemm3")]
+        which = sorted({nm for nm, _ in gemms})
+        for _ in range(2):
+            for nm, a in gemms:
+                orig(nm, *a)
+        e0.record()
+        for _ in range(iters):
+            for nm, a in gemms:
+                orig(nm, *a)
+        e1.record()
+        torch.cuda.synchronize()
+        gemm_ms = e0.elapsed_time(e1) / iters
+        waits = None
+        if which in (["dsr_tc_gemm2"], ["dsr_tc_gemm3"]) and os.environ.get("DSR_BENCH_WAITS"):
+            lib = _lib.load()
+            buf = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+            setdbg = lib.dsr_tc2_set_debug if which == ["dsr_tc_gemm2"] else lib.dsr_tc3_set_debug
+            setdbg(buf.data_ptr())
+            orig(*gemms[0][:1], *gemms[0][1])
+            torch.cuda.synchronize()
+            setdbg(None)
+            b = buf.view(148, 8).double()
+            names = ["mma_wait_patch", "mma_wait_w", "mma_wait_acc", "mma_total", "epi_wait_acc", "epi_total", "pprod_wait", "wprod_wait"]
+            waits = {n: [float(b[:, i].mean()), float(b[:, i].max())] for i, n in enumerate(names)}
+    return dict(name=name, err=err, ms_layer=ms_all, ms_gemm=gemm_ms, kernels=which, waits=waits,
+                alg_tflops=2 * macs / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--halo", default="both", help="kernel generations to run: 0/1 = first, 1 = best available, 'k1,k2,k3' = forced list")
+    ap.add_argument("--baseoff", default="1")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--passes", type=int, default=3)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--env", default="", help="comma-separated NAME=VALUE sets, ';' between alternatives to sweep")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    from dsr_b200 import _lib, ops
+    _lib.load()
+    ops.CONFIG.update(engine="tc", passes=args.passes, dtype="f16")
+    results = []
+    if args.halo.startswith("k"):
+        halos = [int(x[1:]) + 10 for x in args.halo.split(",")]          # 11/12/13 = forced kernel 1/2/3
+    else:
+        halos = [0, 1] if args.halo == "both" else [int(args.halo)]
+    baseoffs = [0, 1] if args.baseoff == "both" else [int(args.baseoff)]
+    ops.CONFIG.update(halo_min_tiles=0)
+    envsets = [e for e in args.env.split(";")] if args.env else [""]
+    for layer in LAYERS:
+        if args.only and not any(o in layer[0] for o in args.only.split(",")):
+            continue
+        for halo in halos:
+            for bo in (baseoffs if halo == 1 else [0]):
+                for es in (envsets if halo else [""]):
+                    ops.CONFIG.update(tc_halo=bool(halo), force_kernel=(halo - 10 if halo > 10 else None))
+                    os.environ["DSR_TC2_BASEOFF"] = str(bo)
+                    for k in [k for k in os.environ if k.startswith("DSR_TC2_") and k != "DSR_TC2_BASEOFF"]:
+                        del os.environ[k]
+                    for kv in filter(None, es.split(",")):
+                        k, v = kv.split("=")
+                        os.environ[k] = v
+                    try:
+                        r = run(layer, ops, args.iters)
+                    except Exception as e:          # keep going: one bad shape must not hide the others
+                        r = dict(name=layer[0], error=str(e)[:200])
+                    r.update(halo=halo, baseoff=bo, env=es)
+                    results.append(r)
+                    print(json.dumps(r), flush=True)
+    if args.json:
+        json.dump(results, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
