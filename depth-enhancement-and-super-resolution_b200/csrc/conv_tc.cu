@@ -99,11 +99,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     const uint32_t tmem_acc = *tmem_ptr_gen;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-                mbar_wait(empty_bar(s), (it & 1) ^ 1);
+        // ===== TMA producer (whole warp loops and waits, one elected lane issues) =====
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+            mbar_wait(empty_bar(s), (it & 1) ^ 1);
+            if (elect_one()) {
                 const int k = kb + i;
                 const int t = k / cblocks, cb = k - t * cblocks;
                 const int ca = cb << 6;
@@ -116,32 +116,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 tma_load_2d(st + Cfg::NA * Cfg::A_TILE, &mapW_hi, full_bar(s), kw, co0);
                 if (NPASS >= 3) tma_load_2d(st + Cfg::NA * Cfg::A_TILE + Cfg::W_TILE, &mapW_lo, full_bar(s), kw, co0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
-            uint32_t accum = 0;
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-                mbar_wait(full_bar(s), it & 1);
-                tc_fence_after();
+        // ===== MMA issuer (whole warp loops and waits, one elected lane issues: see elect_one) =====
+        const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
+        const uint64_t desc0 = make_sdesc(0);
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+            mbar_wait(full_bar(s), it & 1);
+            if (elect_one()) {
                 const uint32_t st = smem_base + s * Cfg::STAGE;
-                const uint32_t a_hi = st, a_lo = st + Cfg::A_TILE;
-                const uint32_t w_hi = st + Cfg::NA * Cfg::A_TILE, w_lo = w_hi + Cfg::W_TILE;
+                const uint64_t a_hi = desc0 + (uint64_t)((st & 0x3FFFF) >> 4), a_lo = a_hi + (uint64_t)(Cfg::A_TILE >> 4);
+                const uint64_t w_hi = a_hi + (uint64_t)((Cfg::NA * Cfg::A_TILE) >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_TILE >> 4);
 #pragma unroll
-                for (int pass = 0; pass < NPASS; ++pass) {
-                    const uint32_t a = (pass == 1) ? a_lo : a_hi;
-                    const uint32_t w = (pass == 2) ? w_lo : w_hi;
+                for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(tmem_acc, a_hi + 2 * kk, w_hi + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                if (NPASS >= 2) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        tc_mma_bf16(tmem_acc, make_sdesc(a + kk * 32), make_sdesc(w + kk * 32), idesc, accum);
-                        accum = 1;
-                    }
+                    for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(tmem_acc, a_lo + 2 * kk, w_hi + 2 * kk, idesc, 1u);
+                }
+                if (NPASS >= 3) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(tmem_acc, a_hi + 2 * kk, w_lo + 2 * kk, idesc, 1u);
                 }
                 tc_commit(empty_bar(s));            // frees this smem stage when the MMAs above retire
+                if (i == nk - 1) tc_commit(tmem_full_bar);       // accumulator complete -> epilogue
             }
-            tc_commit(tmem_full_bar);               // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
@@ -290,10 +291,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapM_hi, const __grid_consta
     const uint32_t tmem_acc = *tmem_ptr_gen;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-                mbar_wait(empty_bar(s), (it & 1) ^ 1);
+        // TMA producer (whole warp loops and waits, one elected lane issues)
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+            mbar_wait(empty_bar(s), (it & 1) ^ 1);
+            if (elect_one()) {
                 int tile = kb + i;
                 const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
                 const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
@@ -319,32 +321,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapM_hi, const __grid_consta
                         tma_load_4d(dst, &mapA_lo, full_bar(s), cn0 + 64 * b, wa, ha, n0);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // both operands MN-major: bits 15 / 16 of the instruction descriptor
-            const uint32_t idesc = make_idesc(128, BLOCK_N, p.f16 ? 0u : 1u) | (1u << 15) | (1u << 16);
-            uint32_t accum = 0;
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-                mbar_wait(full_bar(s), it & 1);
-                tc_fence_after();
+        // MMA issuer; both operands MN-major: bits 15 / 16 of the instruction descriptor
+        const uint32_t idesc = make_idesc(128, BLOCK_N, p.f16 ? 0u : 1u) | (1u << 15) | (1u << 16);
+        const uint64_t desc0 = make_sdesc_mn(0);
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
+            mbar_wait(full_bar(s), it & 1);
+            if (elect_one()) {
                 const uint32_t st = smem_base + s * Cfg::STAGE;
-                const uint32_t m_hi = st, m_lo = st + Cfg::M_BYTES;
-                const uint32_t a_hi = st + Cfg::NM * Cfg::M_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+                const uint64_t m_hi = desc0 + (uint64_t)((st & 0x3FFFF) >> 4), m_lo = m_hi + (uint64_t)(Cfg::M_BYTES >> 4);
+                const uint64_t a_hi = m_hi + (uint64_t)((Cfg::NM * Cfg::M_BYTES) >> 4), a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
-                for (int pass = 0; pass < NPASS; ++pass) {
-                    const uint32_t m = (pass == 1) ? m_lo : m_hi;
-                    const uint32_t a = (pass == 2) ? a_lo : a_hi;
+                for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(tmem_acc, m_hi + 128 * kk, a_hi + 128 * kk, idesc, (i | kk) ? 1u : 0u);
+                if (NPASS >= 2) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        tc_mma_bf16(tmem_acc, make_sdesc_mn(m + kk * 2048), make_sdesc_mn(a + kk * 2048), idesc, accum);
-                        accum = 1;
-                    }
+                    for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(tmem_acc, m_lo + 128 * kk, a_hi + 128 * kk, idesc, 1u);
+                }
+                if (NPASS >= 3) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(tmem_acc, m_hi + 128 * kk, a_lo + 128 * kk, idesc, 1u);
                 }
                 tc_commit(empty_bar(s));
+                if (i == nk - 1) tc_commit(tmem_full_bar);
             }
-            tc_commit(tmem_full_bar);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;

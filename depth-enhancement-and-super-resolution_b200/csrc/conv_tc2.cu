@@ -107,7 +107,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 
     if (warp == 0) {
         // ===== patch producer: one box per (tile, 64-channel block) =====
-        if (lane == 0) {
+        {
             int pi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int r = tile / p.tiles_co;
@@ -118,17 +118,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
                     const int b = pi % p.n_pb, it = pi / p.n_pb;
                     TC2_TIMED_WAIT(0, pe(b), (it & 1) ^ 1);
-                    const uint32_t dst = smem_base + b * patch_set;
-                    mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
-                    tma_load_4d(dst, &mapA_hi, pf(b), cb << 6, wc, hc, n);
-                    if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb << 6, wc, hc, n);
+                    if (elect_one()) {
+                        const uint32_t dst = smem_base + b * patch_set;
+                        mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
+                        tma_load_4d(dst, &mapA_hi, pf(b), cb << 6, wc, hc, n);
+                        if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb << 6, wc, hc, n);
+                    }
+                    __syncwarp();
                 }
             }
-            if (dbg) dbg[blockIdx.x * 8 + 6] = dbg_acc[0];
+            if (dbg && lane == 0) dbg[blockIdx.x * 16 + 6] = dbg_acc[0];
         }
     } else if (warp == 1) {
         // ===== weight producer: one [BLOCK_N x 64] tile (hi, lo) per (tile, block, tap) =====
-        if (lane == 0) {
+        {
             int wi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int co0 = (tile % p.tiles_co) * BLOCK_N;
@@ -136,59 +139,71 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     for (int t = 0; t < p.T; ++t, ++wi) {
                         const int s = wi % p.n_ws, it = wi / p.n_ws;
                         TC2_TIMED_WAIT(0, we(s), (it & 1) ^ 1);
-                        const uint32_t dst = w_base + s * w_stage;
-                        const int kw = t * p.Ca + (cb << 6);
-                        mbar_expect_tx(wf(s), w_stage);
-                        tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
-                        if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
+                        if (elect_one()) {
+                            const uint32_t dst = w_base + s * w_stage;
+                            const int kw = t * p.Ca + (cb << 6);
+                            mbar_expect_tx(wf(s), w_stage);
+                            tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
+                            if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
+                        }
+                        __syncwarp();
                     }
                 }
             }
-            if (dbg) dbg[blockIdx.x * 8 + 7] = dbg_acc[0];
+            if (dbg && lane == 0) dbg[blockIdx.x * 16 + 7] = dbg_acc[0];
         }
     } else if (warp == 2) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop and the waits; one elected lane issues =====
+        {
             const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
-            const uint32_t sbo = (uint32_t)p.PW * 128u;       // stride between the 8-pixel row groups of the patch
+            const uint64_t pdesc0 = make_sdesc_ex(0, (uint32_t)p.PW * 128u, 0);   // stride between the 8-pixel row groups
+            const uint64_t wdesc0 = make_sdesc(0);
             int pi = 0, wi = 0, ti = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
                 const int ab = ti & 1;
                 TC2_TIMED_WAIT(2, ae(ab), ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
-                uint32_t accum = 0;
                 for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
                     const int b = pi % p.n_pb;
                     TC2_TIMED_WAIT(0, pf(b), (pi / p.n_pb) & 1);
-                    tc_fence_after();
                     const uint32_t patch_hi = smem_base + b * patch_set, patch_lo = patch_hi + p.patch_plane_bytes;
                     for (int t = 0; t < p.T; ++t, ++wi) {
                         const int s = wi % p.n_ws;
                         TC2_TIMED_WAIT(1, wf(s), (wi / p.n_ws) & 1);
-                        tc_fence_after();
-                        const uint32_t w_hi = w_base + s * w_stage, w_lo = w_hi + W_TILE;
-                        const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 128u;
-                        const uint32_t boff = p.base_off_mode ? (uint32_t)(p.ds[t] & 7) : 0u;
+                        if (elect_one()) {
+                            const uint32_t w_hi = w_base + s * w_stage;
+                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 128u;
+                            const uint64_t boff = p.base_off_mode ? ((uint64_t)(p.ds[t] & 7) << 49) : 0ull;
+                            const uint64_t pd_hi = (pdesc0 | boff) + (uint64_t)(((patch_hi + shift) & 0x3FFFF) >> 4);
+                            const uint64_t pd_lo = (pdesc0 | boff) + (uint64_t)(((patch_lo + shift) & 0x3FFFF) >> 4);
+                            const uint64_t wd_hi = wdesc0 + (uint64_t)((w_hi & 0x3FFFF) >> 4);
+                            const uint64_t wd_lo = wd_hi + (uint64_t)(W_TILE >> 4);
+                            const uint32_t first = (cb | t) ? 1u : 0u;          // 0 only for the first MMA of the tile
 #pragma unroll
-                        for (int pass = 0; pass < NPASS; ++pass) {
-                            const uint32_t a = ((pass == 1) ? patch_lo : patch_hi) + shift;
-                            const uint32_t w = (pass == 2) ? w_lo : w_hi;
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_hi + 2 * kk, idesc, kk ? 1u : first);
+                            if (NPASS >= 2) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                tc_mma_bf16(d_tmem, make_sdesc_ex(a + kk * 32, sbo, boff), make_sdesc(w + kk * 32), idesc, accum);
-                                accum = 1;
+                                for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d_tmem, pd_lo + 2 * kk, wd_hi + 2 * kk, idesc, 1u);
+                            }
+                            if (NPASS >= 3) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_lo + 2 * kk, idesc, 1u);
+                            }
+                            tc_commit(we(s));
+                            if (t == p.T - 1) {
+                                tc_commit(pe(b));
+                                if (cb == p.cblocks - 1) tc_commit(af(ab));
                             }
                         }
-                        tc_commit(we(s));
+                        __syncwarp();
                     }
-                    tc_commit(pe(b));
                 }
-                tc_commit(af(ab));
             }
-            if (dbg) {
-                dbg[blockIdx.x * 8 + 0] = dbg_acc[0]; dbg[blockIdx.x * 8 + 1] = dbg_acc[1];
-                dbg[blockIdx.x * 8 + 2] = dbg_acc[2]; dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
+            if (dbg && lane == 0) {
+                dbg[blockIdx.x * 16 + 0] = dbg_acc[0]; dbg[blockIdx.x * 16 + 1] = dbg_acc[1];
+                dbg[blockIdx.x * 16 + 2] = dbg_acc[2]; dbg[blockIdx.x * 16 + 3] = clock64() - t_start;
             }
         }
     } else {
@@ -281,7 +296,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(ae(ab));
         }
-        if (dbg && warp == 3 && lane == 0) { dbg[blockIdx.x * 8 + 4] = dbg_acc[0]; dbg[blockIdx.x * 8 + 5] = clock64() - t_start; }
+        if (dbg && warp == 3 && lane == 0) { dbg[blockIdx.x * 16 + 4] = dbg_acc[0]; dbg[blockIdx.x * 16 + 5] = clock64() - t_start; }
     }
     tc_fence_before();
     __syncthreads();

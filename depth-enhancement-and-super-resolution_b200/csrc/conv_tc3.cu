@@ -100,10 +100,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + 9] = clock64() - t_start;     // set-up time
 
     if (warp == 0) {
         // ===== patch producer: one box per (tile, 32-channel block) =====
-        if (lane == 0) {
+        {
             int pi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int r = tile / p.tiles_co;
@@ -114,17 +115,20 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
                     const int b = pi % p.n_pb, it = pi / p.n_pb;
                     TC3_TIMED_WAIT(0, pe(b), (it & 1) ^ 1);
-                    const uint32_t dst = smem_base + b * patch_set;
-                    mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
-                    tma_load_4d(dst, &mapA_hi, pf(b), cb << 5, wc, hc, n);
-                    if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb << 5, wc, hc, n);
+                    if (elect_one()) {
+                        const uint32_t dst = smem_base + b * patch_set;
+                        mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
+                        tma_load_4d(dst, &mapA_hi, pf(b), cb << 5, wc, hc, n);
+                        if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb << 5, wc, hc, n);
+                    }
+                    __syncwarp();
                 }
             }
-            if (dbg) dbg[blockIdx.x * 8 + 6] = dbg_acc[0];
+            if (dbg && lane == 0) dbg[blockIdx.x * 16 + 6] = dbg_acc[0];
         }
     } else if (warp == 1) {
         // ===== weight producer: one [128 co x 32 k] tile (hi, lo) per (tile, block, tap) =====
-        if (lane == 0) {
+        {
             int wi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int co0 = (tile % p.tiles_co) * 128;
@@ -132,58 +136,70 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     for (int t = 0; t < p.T; ++t, ++wi) {
                         const int s = wi % p.n_ws, it = wi / p.n_ws;
                         TC3_TIMED_WAIT(0, we(s), (it & 1) ^ 1);
-                        const uint32_t dst = w_base + s * w_stage;
-                        const int kw = t * p.Ca + (cb << 5);
-                        mbar_expect_tx(wf(s), w_stage);
-                        tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
-                        if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
+                        if (elect_one()) {
+                            const uint32_t dst = w_base + s * w_stage;
+                            const int kw = t * p.Ca + (cb << 5);
+                            mbar_expect_tx(wf(s), w_stage);
+                            tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
+                            if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
+                        }
+                        __syncwarp();
                     }
                 }
             }
-            if (dbg) dbg[blockIdx.x * 8 + 7] = dbg_acc[0];
+            if (dbg && lane == 0) dbg[blockIdx.x * 16 + 7] = dbg_acc[0];
         }
     } else if (warp == 2) {
-        // ===== MMA issuer: A operand = weights (M = 128 channels), B operand = shifted patch (N = 8*TH pixels) =====
-        if (lane == 0) {
+        // ===== MMA issuer: A operand = weights (M = 128 channels), B operand = shifted patch (N = 8*TH pixels).
+        // The whole warp runs the (warp-uniform) loop and the waits; one elected lane issues. =====
+        {
             const uint32_t idesc = make_idesc(128, 8 * p.TH, p.f16 ? 0u : 1u);
-            const uint32_t sbo_patch = (uint32_t)p.PW * 64u;
+            const uint64_t wdesc0 = make_sdesc64(0, 512);                       // address field added per MMA
+            const uint64_t pdesc0 = make_sdesc64(0, (uint32_t)p.PW * 64u);
             int pi = 0, wi = 0, ti = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
                 const int ab = ti & 1;
                 TC3_TIMED_WAIT(2, ae(ab), ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)ab * ACC_COLS;
-                uint32_t accum = 0;
                 for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
                     const int b = pi % p.n_pb;
                     TC3_TIMED_WAIT(0, pf(b), (pi / p.n_pb) & 1);
-                    tc_fence_after();
                     const uint32_t patch_hi = smem_base + b * patch_set, patch_lo = patch_hi + p.patch_plane_bytes;
                     for (int t = 0; t < p.T; ++t, ++wi) {
                         const int s = wi % p.n_ws;
                         TC3_TIMED_WAIT(1, wf(s), (wi / p.n_ws) & 1);
-                        tc_fence_after();
-                        const uint32_t w_hi = w_base + s * w_stage, w_lo = w_hi + W_TILE;
-                        const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 64u;
-#pragma unroll
-                        for (int pass = 0; pass < NPASS; ++pass) {
-                            const uint32_t a = ((pass == 1) ? patch_lo : patch_hi) + shift;
-                            const uint32_t w = (pass == 2) ? w_lo : w_hi;
-#pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {
-                                tc_mma_bf16(d_tmem, make_sdesc64(w + kk * 32, 512), make_sdesc64(a + kk * 32, sbo_patch), idesc, accum);
-                                accum = 1;
+                        if (elect_one()) {
+                            const uint32_t w_hi = w_base + s * w_stage;
+                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 64u;
+                            const uint64_t wd_hi = wdesc0 + (uint64_t)((w_hi & 0x3FFFF) >> 4);
+                            const uint64_t wd_lo = wd_hi + (uint64_t)(W_TILE >> 4);
+                            const uint64_t pd_hi = pdesc0 + (uint64_t)(((patch_hi + shift) & 0x3FFFF) >> 4);
+                            const uint64_t pd_lo = pdesc0 + (uint64_t)(((patch_lo + shift) & 0x3FFFF) >> 4);
+                            const uint32_t first = (cb | t) ? 1u : 0u;          // 0 only for the first MMA of the tile
+                            tc_mma_bf16(d_tmem, wd_hi, pd_hi, idesc, first);
+                            tc_mma_bf16(d_tmem, wd_hi + 2, pd_hi + 2, idesc, 1u);
+                            if (NPASS >= 2) {
+                                tc_mma_bf16(d_tmem, wd_hi, pd_lo, idesc, 1u);
+                                tc_mma_bf16(d_tmem, wd_hi + 2, pd_lo + 2, idesc, 1u);
+                            }
+                            if (NPASS >= 3) {
+                                tc_mma_bf16(d_tmem, wd_lo, pd_hi, idesc, 1u);
+                                tc_mma_bf16(d_tmem, wd_lo + 2, pd_hi + 2, idesc, 1u);
+                            }
+                            tc_commit(we(s));
+                            if (t == p.T - 1) {
+                                tc_commit(pe(b));
+                                if (cb == p.cblocks - 1) tc_commit(af(ab));
                             }
                         }
-                        tc_commit(we(s));
+                        __syncwarp();
                     }
-                    tc_commit(pe(b));
                 }
-                tc_commit(af(ab));
             }
-            if (dbg) {
-                dbg[blockIdx.x * 8 + 0] = dbg_acc[0]; dbg[blockIdx.x * 8 + 1] = dbg_acc[1];
-                dbg[blockIdx.x * 8 + 2] = dbg_acc[2]; dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
+            if (dbg && lane == 0) {
+                dbg[blockIdx.x * 16 + 0] = dbg_acc[0]; dbg[blockIdx.x * 16 + 1] = dbg_acc[1];
+                dbg[blockIdx.x * 16 + 2] = dbg_acc[2]; dbg[blockIdx.x * 16 + 3] = clock64() - t_start;
             }
         }
     } else {
@@ -207,8 +223,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 #pragma unroll 1
             for (int c0 = 0; c0 < ncols; c0 += 16) {
                 uint32_t v[16];
+                const long long tl0 = dbg ? clock64() : 0;
                 tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * ACC_COLS + c0), v);
                 tc_wait_ld();
+                if (dbg) dbg_acc[1] += clock64() - tl0;
                 // 16 columns = 2 tile rows of 8 pixels
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -236,7 +254,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 atomicAdd(sp + 1, (double)ssq);
             }
         }
-        if (dbg && warp == 3 && lane == 0) { dbg[blockIdx.x * 8 + 4] = dbg_acc[0]; dbg[blockIdx.x * 8 + 5] = clock64() - t_start; }
+        if (dbg && warp == 3 && lane == 0) {
+            dbg[blockIdx.x * 16 + 4] = dbg_acc[0]; dbg[blockIdx.x * 16 + 5] = clock64() - t_start;
+            dbg[blockIdx.x * 16 + 8] = dbg_acc[1];
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -427,14 +427,15 @@ extern "C" int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, lon
     cvt_f64_f32_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(in, stride_in, out, n, scale, accumulate);
     return dsr_check_launch("cvt_f64_f32");
 }
-extern "C" int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2,
-                             float eps, int step, float grad_scale, void* stream) {
+extern "C" int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2,
+                             double eps, int step, float grad_scale, void* stream) {
     DSR_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad arguments");
     DSR_REQUIRE(!((uintptr_t)p & 15) && !((uintptr_t)g & 15) && !((uintptr_t)m & 15) && !((uintptr_t)v & 15),
                 "arena pointers must be 16-byte aligned");
-    double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    // hyper-parameters arrive as doubles (python floats) so 1 - beta is formed exactly like torch.optim.Adam forms it
+    double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
     adam_kernel<<<dsr_grid(n / 4 + 1, TPB), TPB, 0, ST(stream)>>>(
-        p, g, m, v, n, (float)((double)lr / bc1), b2, (float)(1.0 - (double)b1), (float)(1.0 - (double)b2), eps,
+        p, g, m, v, n, (float)(lr / bc1), (float)b2, (float)(1.0 - b1), (float)(1.0 - b2), (float)eps,
         (float)sqrt(bc2), grad_scale);
     return dsr_check_launch("adam_step");
 }

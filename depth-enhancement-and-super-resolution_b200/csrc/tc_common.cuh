@@ -86,6 +86,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// exactly one lane of a converged warp returns true.  Issuing tcgen05.mma / TMA / tcgen05.commit under
+// `if (elect_one())` in an otherwise warp-uniform loop lets the compiler keep descriptors in uniform registers and emit
+// the instruction once; under `if (lane == 0)` it wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (measured: ~146
+// issue cycles per MMA, more than the 64..128-cycle tensor floor).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

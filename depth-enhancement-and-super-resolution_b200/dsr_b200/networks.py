@@ -29,7 +29,7 @@ class Identity(nn.Module):                        # networks.py:13-15
 class Conv2d(nn.Conv2d):
     """nn.Conv2d with zeros / reflect / replicate ``padding_mode`` (networks.py:379; translation_network.py:472)."""
 
-    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None, want_stats=False):
+    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None, want_stats=False, pro=None):
         """pre_pad = (pad, mode) of an nn.ReflectionPad2d / ReplicationPad2d module placed right before
         this conv: it is folded into the conv's operand preparation instead of materialising a padded copy.
         want_stats: also return the per-(n, c) statistics of the output for the norm layer that follows."""
@@ -40,13 +40,21 @@ class Conv2d(nn.Conv2d):
             if p != 0:
                 raise NotImplementedError("dsr_b200.Conv2d: explicit pad module followed by a padded conv")
             p, mode = pre_pad
-        return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode, want_stats=want_stats)
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode, want_stats=want_stats,
+                          pro=pro)
+
+    def fusable(self, x, pre_pad=None):
+        p = pre_pad[0] if pre_pad is not None else self.padding[0]
+        return ops.conv_fusable("conv", x, self.weight, self.stride[0], p)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):        # networks.py:406, :553
-    def forward(self, x, act_out=ops.ACT_NONE, want_stats=False):
+    def forward(self, x, act_out=ops.ACT_NONE, want_stats=False, pro=None):
         return ops.conv_transpose2d(x, self.weight, self.bias, self.stride[0], self.padding[0],
-                                    self.output_padding[0], act_out, want_stats=want_stats)
+                                    self.output_padding[0], act_out, want_stats=want_stats, pro=pro)
+
+    def fusable(self, x, pre_pad=None):
+        return ops.conv_fusable("convT", x, self.weight, self.stride[0], self.padding[0], self.output_padding[0])
 
 
 class ReflectionPad2d(nn.ReflectionPad2d):        # networks.py:378
@@ -95,34 +103,46 @@ def _conv_like(m):
 
 
 def run_fused(mods, x, tail_stats=False):
-    """Run a module list, fusing what our kernels handle in one pass: pad module + conv, conv + Tanh, norm + ReLU,
-    and conv -> norm statistics (taken by the GEMM epilogue, handed to the norm layer).  tail_stats: the list ends
-    with a conv whose norm layer is applied by the caller (residual blocks) -> returns (x, stats)."""
-    norms = (InstanceNorm2d, GroupNorm)
-    i, stats = 0, None
-    while i < len(mods):
-        m = mods[i]
-        nxt = mods[i + 1] if i + 1 < len(mods) else None
-        if isinstance(m, norms):
-            if isinstance(nxt, ReLU):
-                x = m(x, act=ops.ACT_RELU, stats=stats)
-                i += 2
-            else:
-                x = m(x, stats=stats)
-                i += 1
-            stats = None
-            continue
-        stats = None
-        pre_pad, j = None, i
-        if isinstance(m, (ReflectionPad2d, ReplicationPad2d)) and isinstance(nxt, Conv2d) and nxt.padding[0] == 0:
-            pre_pad = (m.padding[0], "reflect" if isinstance(m, ReflectionPad2d) else "replicate")
-            j = i + 1
-        conv = _conv_like(mods[j])
-        if conv is not None:
-            after = mods[j + 1] if j + 1 < len(mods) else None
+    """Run a module list as fused units  [norm] [ReLU | LeakyReLU] [pad module] conv [Tanh]:
+      * the norm-apply, the activation and the padding are folded into the conv's operand preparation
+        (ops.Prologue) whenever the conv runs on the tcgen05 path - the normalised tensor is never written;
+      * Tanh goes into the GEMM epilogue;
+      * when a norm layer follows, the GEMM epilogue also takes its statistics and hands them over.
+    Anything else runs module by module (norm + ReLU still share one pass).  tail_stats: the list ends with a conv
+    whose norm layer is applied by the caller (residual blocks) -> returns (x, stats)."""
+    norms, pads = (InstanceNorm2d, GroupNorm), (ReflectionPad2d, ReplicationPad2d)
+    n, i, stats = len(mods), 0, None          # stats = statistics of x, meaningful only while mods[i] is a norm layer
+    while i < n:
+        j, norm, act, pad = i, None, None, None
+        if isinstance(mods[j], norms):
+            norm, j = mods[j], j + 1
+        if j < n and isinstance(mods[j], (ReLU, LeakyReLU)):
+            act, j = mods[j], j + 1
+        if j + 1 < n and isinstance(mods[j], pads) and isinstance(mods[j + 1], Conv2d) and mods[j + 1].padding[0] == 0:
+            pad, j = mods[j], j + 1
+        conv = _conv_like(mods[j]) if j < n else None
+        pre_pad = (pad.padding[0], "reflect" if isinstance(pad, ReflectionPad2d) else "replicate") if pad is not None else None
+        plain = norm is None and act is None
+        if conv is not None and (plain or conv.fusable(x, pre_pad)):
             kw = {}
             if pre_pad is not None:
                 kw["pre_pad"] = pre_pad
+            if not plain:
+                a, slope = ops.ACT_NONE, 0.0
+                if isinstance(act, LeakyReLU):
+                    a, slope = ops.ACT_LRELU, act.negative_slope
+                elif act is not None:
+                    a = ops.ACT_RELU
+                if isinstance(norm, GroupNorm):
+                    kw["pro"] = ops.Prologue(stats, True, norm.eps, norm.num_groups, norm.weight, norm.bias, a, slope)
+                elif norm is not None:
+                    if norm.affine or norm.track_running_stats:
+                        raise NotImplementedError("dsr_b200.InstanceNorm2d: only affine=False, track_running_stats=False")
+                    kw["pro"] = ops.Prologue(stats, True, norm.eps, 0, None, None, a, slope)
+                else:
+                    kw["pro"] = ops.Prologue(act=a, slope=slope)
+            after = mods[j + 1] if j + 1 < n else None
+            stats = None
             if isinstance(after, Tanh):
                 x = conv(x, act_out=ops.ACT_TANH, **kw)
                 i = j + 2
@@ -133,8 +153,18 @@ def run_fused(mods, x, tail_stats=False):
                 x = conv(x, **kw)
                 i = j + 1
             continue
-        x = m(x)
-        i += 1
+        m = mods[i]
+        if isinstance(m, norms):
+            if i + 1 < n and isinstance(mods[i + 1], ReLU):
+                x = m(x, act=ops.ACT_RELU, stats=stats)
+                i += 2
+            else:
+                x = m(x, stats=stats)
+                i += 1
+        else:
+            x = m(x)
+            i += 1
+        stats = None
     return (x, stats) if tail_stats else x
 
 

@@ -218,15 +218,16 @@ class _Prepared:
     """Arranged 16-bit copies of ONE fp32 NHWC tensor, made at most once per (layout, padding, format):
     the backward pass feeds the same dY (or x) to the data-gradient and the weight-gradient GEMMs."""
 
-    def __init__(self, xh):
+    def __init__(self, xh, prm=None, act=ACT_NONE, slope=0.0):
         self.xh, self.made = xh, {}
         self.shape, self.device = xh.shape, xh.device
+        self.prm, self.act, self.slope = prm, act, slope      # fused prologue: norm-apply + activation on the way in
 
     def get(self, plan, pad, pad_mode, dtype=None):
         key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dtype or CONFIG["dtype"])
         hit = self.made.get(key)
         if hit is None:
-            hit = self.made[key] = _tc_prep(self.xh, plan, pad, pad_mode, dtype=dtype)
+            hit = self.made[key] = _tc_prep(self.xh, plan, pad, pad_mode, self.prm, self.act, self.slope, dtype=dtype)
         return hit
 
     def any_normal(self, Ca, dtype):
@@ -434,12 +435,50 @@ def _tc_convT_wgrad(xP, gP, weight, stride, pad):
     return True, _tc_wgrad(xP, Ci, gP, plan, pad, PAD_ZERO, dr, ds, H, W, weight, _W_CONV_S2D)
 
 
+class Prologue:
+    """What sits between the producer of a conv's input and the conv itself, folded into the conv's operand
+    preparation instead of running as separate passes: a normalisation layer (InstanceNorm2d(affine=False) when
+    groups == 0, GroupNorm(groups, C, affine) otherwise; `stats` = per-(n, c) sums of the RAW input, usually taken by
+    the producing GEMM's epilogue) and / or an activation (ReLU / LeakyReLU)."""
+
+    def __init__(self, stats=None, norm=False, eps=1e-5, groups=0, gamma=None, beta=None, act=ACT_NONE, slope=0.0):
+        self.stats, self.norm, self.eps, self.groups = stats, norm, eps, groups
+        self.gamma, self.beta, self.act, self.slope = gamma, beta, act, slope
+
+    def params(self, xh):
+        if not self.norm:
+            return None
+        g = self.gamma.detach().contiguous() if self.gamma is not None else None
+        b = self.beta.detach().contiguous() if self.beta is not None else None
+        return _norm_params(xh, self.groups, g, b, self.eps, self.stats)
+
+
+def _prologue_bwd(pro, prm, xh, gz):
+    """gradient w.r.t. the RAW conv input given the gradient w.r.t. the normalised / activated operand"""
+    if pro is None:
+        return gz
+    N, H, W, C = xh.shape
+    if pro.norm:
+        if pro.groups != 0:
+            raise NotImplementedError("dsr_b200: GroupNorm backward is not on the main_network_best hot path")
+        sums2 = _zeros_f64(N * C * 2, gz.device)
+        _call("dsr_in_bwd_sums", _p(xh), _p(gz), _p(prm), N, H * W, C, pro.act, _p(sums2, torch.float64))
+        gx = torch.empty_like(xh)
+        _call("dsr_in_bwd_apply", _p(xh), _p(gz), _p(prm), _p(sums2, torch.float64), _p(gx), N, H * W, C, pro.act)
+        return gx
+    if pro.act != ACT_NONE:
+        gx = torch.empty_like(xh)
+        _call("dsr_act_bwd", _p(xh), _p(gz), _p(gx), gz.numel(), pro.act, pro.slope)
+        return gx
+    return gz
+
+
 class _Conv2d(Function):
     """nn.Conv2d with zeros / reflect / replicate padding.  networks.py:378-379,385,413-414,453,544;
     translation_network.py:472,478,495,563."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out, want_stats):
+    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out, want_stats, pro):
         xh = nhwc(x)
         N, H, W, Ci = xh.shape
         Co, Ci2, R, S = weight.shape
@@ -449,8 +488,14 @@ class _Conv2d(Function):
         b = bias.detach() if bias is not None else None
         stats = _new_stats(N, Co, x.device) if want_stats else None
         plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
+        prm = None
+        if pro is not None:
+            if plan is None:
+                raise RuntimeError("internal error: a fused prologue needs the tcgen05 path (see conv_fusable)")
+            prm = pro.params(xh)
         if plan is not None:
-            y = _tc_conv_fwd(xh, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, stats=stats)
+            xin = xh if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
+            y = _tc_conv_fwd(xin, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, stats=stats)
         else:
             xp, p = _explicit_pad(xh, pad, pad_mode)
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
@@ -458,13 +503,14 @@ class _Conv2d(Function):
             _call("dsr_conv_simt", _p(xp), _p(wk), _p(b), _p(y), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
                   stride, p, 0, act_out)
         ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None)
-        ctx.bias_ref = bias
-        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
+        ctx.bias_ref, ctx.pro = bias, pro
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, prm)
         return _with_stats(ctx, y, stats)
 
     @staticmethod
     def backward(ctx, gy, _gstats=None):
-        xh, weight, y = ctx.saved_tensors
+        xh, weight, y, prm = ctx.saved_tensors
+        pro = ctx.pro
         stride, pad, pad_mode, act_out, has_bias = ctx.cfg
         N, H, W, Ci = xh.shape
         Co, _, R, S = weight.shape
@@ -488,9 +534,10 @@ class _Conv2d(Function):
                     gxh = torch.empty_like(xh)
                     _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
                     gxp = gxh
-            gx = nchw(gxp)
+            gx = nchw(_prologue_bwd(pro, prm, xh, gxp))
         if ctx.needs_input_grad[1]:
-            done, gw = _tc_conv_wgrad(_Prepared(xh), gP, weight, stride, pad, pad_mode)
+            xP = _Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
+            done, gw = _tc_conv_wgrad(xP, gP, weight, stride, pad, pad_mode)
             if not done:
                 xp, p = _explicit_pad(xh, pad, pad_mode)
                 dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
@@ -499,7 +546,7 @@ class _Conv2d(Function):
                 gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None
 
 
 def _new_stats(N, C, device):
@@ -535,7 +582,7 @@ class _ConvTranspose2d(Function):
     """nn.ConvTranspose2d.  networks.py:406,553,605,612; translation_network.py:508."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, opad, act_out, want_stats):
+    def forward(ctx, x, weight, bias, stride, pad, opad, act_out, want_stats, pro):
         xh = nhwc(x)
         N, H, W, Ci = xh.shape
         Ci2, Co, R, S = weight.shape
@@ -545,20 +592,27 @@ class _ConvTranspose2d(Function):
         b = bias.detach() if bias is not None else None
         stats = _new_stats(N, Co, x.device) if want_stats else None
         plan = tc_conv_plan("convT", Ci, Co, R, S, stride, pad, opad, H, W)
+        prm = None
+        if pro is not None:
+            if plan is None:
+                raise RuntimeError("internal error: a fused prologue needs the tcgen05 path (see conv_fusable)")
+            prm = pro.params(xh)
         if plan is not None:
-            y = _tc_convT_fwd(xh, weight, b, plan, pad, act_out, Ho, Wo, stats=stats)
+            xin = xh if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
+            y = _tc_convT_fwd(xin, weight, b, plan, pad, act_out, Ho, Wo, stats=stats)
         else:
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
             wk = _pack(weight, 0)                       # [(r,s,ci)][co]
             _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, act_out)
         ctx.cfg = (stride, pad, act_out, bias is not None)
-        ctx.bias_ref = bias
-        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
+        ctx.bias_ref, ctx.pro = bias, pro
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, prm)
         return _with_stats(ctx, y, stats)
 
     @staticmethod
     def backward(ctx, gy, _gstats=None):
-        xh, weight, y = ctx.saved_tensors
+        xh, weight, y, prm = ctx.saved_tensors
+        pro = ctx.pro
         stride, pad, act_out, has_bias = ctx.cfg
         N, H, W, Ci = xh.shape
         _, Co, R, S = weight.shape
@@ -576,28 +630,40 @@ class _ConvTranspose2d(Function):
                 wk = _pack(weight, 1)                   # [(r,s,co)][ci]
                 gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
                 _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
-            gx = nchw(gxh)
+            gx = nchw(_prologue_bwd(pro, prm, xh, gxh))
         if ctx.needs_input_grad[1]:
-            done, gw = _tc_convT_wgrad(_Prepared(xh), gP, weight, stride, pad)
+            xP = _Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
+            done, gw = _tc_convT_wgrad(xP, gP, weight, stride, pad)
             if not done:
                 dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
                 _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
                 gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO, want_stats=False):
+def conv_fusable(kind, x, weight, stride, padding, output_padding=0):
+    """True when this layer runs on the tcgen05 path, i.e. can take a fused Prologue"""
+    N, C, H, W = x.shape
+    if kind == "conv":
+        Co, Ci, R, S = weight.shape
+        return tc_conv_plan("conv", Ci, Co, R, S, stride, padding, 0, H, W) is not None
+    Ci, Co, R, S = weight.shape
+    return tc_conv_plan("convT", Ci, Co, R, S, stride, padding, output_padding, H, W) is not None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO, want_stats=False, pro=None):
     """-> y, or (y, stats) with want_stats: stats = float64 [N*Cout*2] per-(n, c) (sum, sum of squares) of y for the
     normalisation layer that follows (instance_norm / group_norm take it through their `stats` argument)."""
     pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
-    y, st = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats)
+    y, st = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats, pro)
     return (y, st) if want_stats else y
 
 
-def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE, want_stats=False):
-    y, st = _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out, want_stats)
+def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE, want_stats=False,
+                     pro=None):
+    y, st = _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out, want_stats, pro)
     return (y, st) if want_stats else y
 
 

@@ -171,7 +171,7 @@ int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int 
                  int f16, float out_scale, double* stats, void* stream);
 int dsr_tc3_set_debug(long long* counters);
 
-/* profiling aid: counters = device long long [grid][8] (or NULL to switch off): per-CTA clock64 ticks the roles of the
+/* profiling aid: counters = device long long [grid][16] (or NULL to switch off): per-CTA clock64 ticks the roles of the
  * dsr_tc_gemm2 kernel spent waiting (see csrc/conv_tc2.cu).  Synchronous (cudaMemcpyToSymbol). */
 int dsr_tc2_set_debug(long long* counters);
 
@@ -187,7 +187,7 @@ int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int vari
 
 /* ---- optimizer ------------------------------------------------------------------------------- */
 /* torch.optim.Adam (defaults) over one flat arena.  models/main_model.py:176, :429. */
-int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2, double eps,
                   int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus

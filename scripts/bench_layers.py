@@ -92,14 +92,14 @@ def run(layer, ops, iters, check=True):
         waits = None
         if which in (["dsr_tc_gemm2"], ["dsr_tc_gemm3"]) and os.environ.get("DSR_BENCH_WAITS"):
             lib = _lib.load()
-            buf = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+            buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
             setdbg = lib.dsr_tc2_set_debug if which == ["dsr_tc_gemm2"] else lib.dsr_tc3_set_debug
             setdbg(buf.data_ptr())
             orig(*gemms[0][:1], *gemms[0][1])
             torch.cuda.synchronize()
             setdbg(None)
-            b = buf.view(148, 8).double()
-            names = ["mma_wait_patch", "mma_wait_w", "mma_wait_acc", "mma_total", "epi_wait_acc", "epi_total", "pprod_wait", "wprod_wait"]
+            b = buf.view(148, 16).double()
+            names = ["mma_wait_patch", "mma_wait_w", "mma_wait_acc", "mma_total", "epi_wait_acc", "epi_total", "pprod_wait", "wprod_wait", "epi_ld", "setup"]
             waits = {n: [float(b[:, i].mean()), float(b[:, i].max())] for i, n in enumerate(names)}
     return dict(name=name, err=err, ms_layer=ms_all, ms_gemm=gemm_ms, kernels=which, waits=waits,
                 alg_tflops=2 * macs / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None)
