@@ -471,17 +471,17 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W,
 // ------------------------------------------------------------------------------------------------
 // weight packing: 4-D fp32 parameter -> bf16 hi (+lo) [Cout][T*Ca], K-major
 //   variant CONV     : Conv2d weight (Cout, Cin, R, S); tap t = r*S + s, channel c          (stride 1)
-//   variant CONV_PAIR: as CONV with Ca = 2*Cp: tap t = r*ceil(S/2) + s2, q = (s&1)*Cp + c
+//   variant CONV_PAIR: as CONV with Ca = g*Cp (g pixels side by side): tap t = r*ceil(S/g) + s/g, q = (s%g)*Cp + c
 //   variant CONV_S2D : stride-2 conv (k <= 4) as 2x2 taps over 4*Cp channels: r = 2r'+a, s = 2s'+b
 //   variant CONV_DGRAD: Conv2d weight (Cout, Cin, R, S) for the stride-1 data gradient: GEMM output channel = ci,
 //                      K channel = co, tap t = (r', s') reads W[co][ci][R-1-r'][S-1-s']
 //   variant CONVT_PH : ConvTranspose2d weight (Cin, Cout, R, S), stride 2, phase (a,b): taps (dr,ds) in {0,1}^2,
 //                      kh = pad + 2 - a - 2*dr, kw = pad + 2 - b - 2*ds (zero tap when outside the kernel)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_map_k(int variant, int t, int q, int R, int S, int Cp, int pa, int pb, int pad,
+__device__ __forceinline__ void tc_map_k(int variant, int t, int q, int R, int S, int Cp, int g, int pa, int pb, int pad,
                                          int& r, int& s, int& c) {
     if (variant == DSR_TC_W_CONV) { r = t / S; s = t - r * S; c = q; }
-    else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; r = t / S2; s = 2 * (t - r * S2) + q / Cp; c = q % Cp; }
+    else if (variant == DSR_TC_W_CONV_PAIR) { const int Sg = (S + g - 1) / g; r = t / Sg; s = g * (t - r * Sg) + q / Cp; c = q % Cp; }
     else if (variant == DSR_TC_W_CONV_S2D) { const int ab = q / Cp; c = q - ab * Cp; r = 2 * (t >> 1) + (ab >> 1); s = 2 * (t & 1) + (ab & 1); }
     else if (variant == DSR_TC_W_CONV_DGRAD) { r = R - 1 - t / S; s = S - 1 - (t - (t / S) * S); c = q; }
     else { c = q; r = pad + 2 - pa - 2 * (t >> 1); s = pad + 2 - pb - 2 * (t & 1); }
@@ -496,7 +496,7 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D
         const long k = idx - (long)co * K;
         const int t = (int)(k / Ca), q = (int)(k - (long)t * Ca);
         int r, s, c;
-        tc_map_k(variant, t, q, R, S, Cp, pa, pb, pad, r, s, c);
+        tc_map_k(variant, t, q, R, S, Cp, Ca / Cp, pa, pb, pad, r, s, c);
         float v = 0.f;
         // convT-style indexing: the GEMM's K channel is the parameter's dim 0, its output channel dim 1
         const bool convT = (variant == DSR_TC_W_CONVT_PH) || (variant == DSR_TC_W_CONV_DGRAD);
@@ -520,7 +520,7 @@ __global__ void tc_unpack_wgrad_kernel(const float* __restrict__ dWp, int D0, in
         const int c = (int)(u % D1); const int d0 = (int)(u / D1);
         int t, q;
         if (variant == DSR_TC_W_CONV) { t = r * S + s; q = c; }
-        else if (variant == DSR_TC_W_CONV_PAIR) { const int S2 = (S + 1) / 2; t = r * S2 + (s >> 1); q = (s & 1) * Cp + c; }
+        else if (variant == DSR_TC_W_CONV_PAIR) { const int g = Ca / Cp, Sg = (S + g - 1) / g; t = r * Sg + s / g; q = (s % g) * Cp + c; }
         else { t = (r >> 1) * 2 + (s >> 1); q = ((r & 1) * 2 + (s & 1)) * Cp + c; }          // S2D
         const float v = dWp[(long)d0 * ((long)T * Ca) + (long)t * Ca + q];
         if (accumulate) grad[idx] += v; else grad[idx] = v;
@@ -566,7 +566,7 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
     DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
     DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
     DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
-    DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_PAIR && Ca == 2 * Cp) ||
+    DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_PAIR && Ca % Cp == 0 && Ca >= 2 * Cp) ||
                     (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
     DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15), "operand buffers must be 16-byte aligned");
     long total = (long)N * Ha * Wa * (Ca / 8);

@@ -206,6 +206,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         // ===== epilogue warps 3..6: lane = output channel, columns = pixels =====
         const int q = warp & 3;
         const int ncols = 8 * p.TH;
+        const long pstride = (long)p.os * p.Cout;                 // between horizontally adjacent output pixels
+        const long rstride = (long)p.os * p.Wo * p.Cout;          // between tile rows
+        const bool tanh_out = p.act == DSR_ACT_TANH;
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
             const int ab = ti & 1;
@@ -217,6 +220,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             const int h0 = th_i * p.TH, w0 = tw_i * TC3_TW;
             const bool cvalid = co < p.Cout;
             const float bv = (bias != nullptr && cvalid) ? __ldg(bias + co) : 0.f;
+            const int wvalid = p.Wt - w0 < 8 ? p.Wt - w0 : 8;     // pixels of a tile row inside the image
+            int hvalid = p.Ht - h0;                                // rows of the tile inside the image
+            if (hvalid > p.TH) hvalid = p.TH;
+            if (!cvalid) hvalid = 0;
+            float* obase = out + (((long)n * p.Ho + (long)h0 * p.os + p.ph) * p.Wo + (long)w0 * p.os + p.pw) * p.Cout + co;
             float ssum = 0.f, ssq = 0.f;
             TC3_TIMED_WAIT(0, af(ab), (ti >> 1) & 1);
             tc_fence_after();
@@ -230,16 +238,28 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 // 16 columns = 2 tile rows of 8 pixels
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    const int h = h0 + (c0 >> 3) + hh;
-                    if (h < p.Ht && cvalid) {
-                        float* orow = out + (((long)n * p.Ho + (long)h * p.os + p.ph) * p.Wo + (long)w0 * p.os + p.pw) * p.Cout + co;
+                    const int hr = (c0 >> 3) + hh;
+                    if (hr < hvalid) {
+                        float* orow = obase + (long)hr * rstride;
+                        float x[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (w0 + j < p.Wt) {
-                                float x = __uint_as_float(v[hh * 8 + j]) * p.out_scale + bv;
-                                ssum += x; ssq += x * x;
-                                if (p.act == DSR_ACT_TANH) x = tanhf(x);
-                                orow[(long)j * p.os * p.Cout] = x;
+                        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[hh * 8 + j]) * p.out_scale + bv;
+                        if (wvalid == 8) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { ssum += x[j]; ssq += x[j] * x[j]; }
+                            if (tanh_out) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = tanhf(x[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) orow[j * pstride] = x[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (j < wvalid) {
+                                    ssum += x[j]; ssq += x[j] * x[j];
+                                    orow[j * pstride] = tanh_out ? tanhf(x[j]) : x[j];
+                                }
                             }
                         }
                     }

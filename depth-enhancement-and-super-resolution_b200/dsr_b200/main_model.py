@@ -271,7 +271,7 @@ class MainModel(BaseModel):
 
         d_in = ops.cat([torch.cat([self.syn2real_depth_masked, self.depth_masked], 0), depth_by_image])
         feat_depth = self.netDepth_f(d_in)
-        pred = self.netTask(ops.cat([image_features, feat_depth, d_in, images]))
+        pred = self.netTask(ops.LazyCat([image_features, feat_depth, d_in, images]))
         self.pred_syn_depth, self.pred_real_depth = pred[:B], pred[B:]
 
         n = float(self.syn_depth.numel())

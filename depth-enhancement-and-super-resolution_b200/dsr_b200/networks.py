@@ -40,6 +40,12 @@ class Conv2d(nn.Conv2d):
             if p != 0:
                 raise NotImplementedError("dsr_b200.Conv2d: explicit pad module followed by a padded conv")
             p, mode = pre_pad
+        if isinstance(x, ops.LazyCat):
+            if want_stats or pro is not None:
+                raise NotImplementedError("dsr_b200.Conv2d: a LazyCat input takes no fused prologue / statistics")
+            if ops.conv_fusable("conv", x, self.weight, self.stride[0], p):
+                return ops.cat_conv2d(x.parts, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode)
+            x = ops.cat(x.parts)
         return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode, want_stats=want_stats,
                           pro=pro)
 

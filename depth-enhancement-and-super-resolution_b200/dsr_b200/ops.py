@@ -144,6 +144,7 @@ CONFIG = {
     "split_k": -1,       # -1 = automatic split-K for tiny-M layers
     "tc_halo": True,     # second-generation GEMM (halo-resident A patches, persistent CTAs) wherever it applies
     "tc_cm": True,       # third-generation channel-major GEMM for Cout >= 128 layers
+    "tc_first_layers": True,   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
     "halo_min_tiles": 120,
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
@@ -172,6 +173,9 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W, min_ci=16):
     """Which arranged-operand layout serves this layer on the tcgen05 path (None -> CUDA-core path)."""
     if CONFIG["engine"] != "tc" or R != S:
         return None
+    if kind == "conv" and stride == 1 and Ci <= 8 and R >= 5 and CONFIG["tc_first_layers"]:
+        # 1..8-channel first layers: 8 horizontally adjacent pixels x 8 channels form one 64-wide K block per kernel row
+        return dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=8, Ca=64, T=R * ((S + 7) // 8))
     if kind == "conv" and stride == 1 and R * S <= 64 and Ci >= 32:
         if Ci == 32:
             return dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=32, Ca=64, T=R * ((S + 1) // 2))
@@ -398,8 +402,9 @@ def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, 
 
 def _tc_taps(plan, R, S):
     if plan["layout"] == _LAYOUT_PAIR:
-        S2 = (S + 1) // 2
-        return [t // S2 for t in range(plan["T"])], [2 * (t % S2) for t in range(plan["T"])]
+        g = plan["Ca"] // plan["Cp"]
+        Sg = (S + g - 1) // g
+        return [t // Sg for t in range(plan["T"])], [g * (t % Sg) for t in range(plan["T"])]
     if plan["layout"] == _LAYOUT_S2D:
         return [0, 0, 1, 1], [0, 1, 0, 1]
     return [t // S for t in range(R * S)], [t % S for t in range(R * S)]
@@ -641,6 +646,89 @@ class _ConvTranspose2d(Function):
         if has_bias and ctx.needs_input_grad[2]:
             gb = _bias_grad(g, Co, ctx.bias_ref)
         return gx, gw, gb, None, None, None, None, None, None
+
+
+class LazyCat:
+    """torch.cat(parts, dim=1) that has not been materialised yet: a Conv2d that receives one runs `cat_conv2d`,
+    which concatenates inside the op and - in the backward pass - computes the data gradient only for the channel
+    range of the parts that need one (main_model.py:305-306: of the 261 Task input channels only the 128 of
+    Depth_f's features do)."""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+        self.shape = (parts[0].shape[0], sum(p.shape[1] for p in parts)) + tuple(parts[0].shape[2:])
+
+
+class _CatConv2d(Function):
+    """nn.Conv2d applied to torch.cat(xs, 1).  networks.py:544 on main_model.py:305-306."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, stride, pad, pad_mode, act_out, *xs):
+        hs = [nhwc(x) for x in xs]
+        N, H, W, _ = hs[0].shape
+        Cs = [h.shape[3] for h in hs]
+        Ci = sum(Cs)
+        xh = torch.empty((N, H, W, Ci), device=hs[0].device, dtype=torch.float32)
+        off = 0
+        for h, c in zip(hs, Cs):
+            _call("dsr_copy_channels", _p(h), c, 0, _p(xh), Ci, off, c, N * H * W, 0)
+            off += c
+        Co, Ci2, R, S = weight.shape
+        if Ci2 != Ci:
+            raise ValueError(f"conv2d: input has {Ci} channels, weight expects {Ci2}")
+        plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
+        if plan is None:
+            raise RuntimeError("internal error: cat_conv2d needs the tcgen05 path")
+        Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        b = bias.detach() if bias is not None else None
+        y = _tc_conv_fwd(xh, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo)
+        ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None, Cs)
+        ctx.bias_ref = bias
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, weight, y = ctx.saved_tensors
+        stride, pad, pad_mode, act_out, has_bias, Cs = ctx.cfg
+        N, H, W, Ci = xh.shape
+        Co, _, R, S = weight.shape
+        g = nhwc(gy)
+        if act_out == ACT_TANH:
+            g2 = torch.empty_like(g)
+            _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
+            g = g2
+        gP = _Prepared(g)
+        needs = ctx.needs_input_grad[6:]
+        offs = [sum(Cs[:i]) for i in range(len(Cs))]
+        gxs = [None] * len(Cs)
+        idx = [i for i, nd in enumerate(needs) if nd]
+        if idx:
+            c0, c1 = offs[idx[0]], offs[idx[-1]] + Cs[idx[-1]]
+            w_slice = weight.detach()[:, c0:c1].contiguous()
+            gxr = _tc_conv_dgrad(gP, w_slice, stride, pad, pad_mode, H, W)
+            if gxr is None:
+                raise RuntimeError("internal error: cat_conv2d data gradient is not covered by the tcgen05 path")
+            for i in idx:
+                if offs[i] == c0 and Cs[i] == c1 - c0:
+                    gxs[i] = nchw(gxr)
+                else:
+                    gi = torch.empty((N, H, W, Cs[i]), device=g.device, dtype=torch.float32)
+                    _call("dsr_copy_channels", _p(gxr), c1 - c0, offs[i] - c0, _p(gi), Cs[i], 0, Cs[i], N * H * W, 0)
+                    gxs[i] = nchw(gi)
+        gw = gb = None
+        if ctx.needs_input_grad[0]:
+            done, gw = _tc_conv_wgrad(_Prepared(xh), gP, weight, stride, pad, pad_mode)
+            if not done:
+                raise RuntimeError("internal error: cat_conv2d weight gradient is not covered by the tcgen05 path")
+        if has_bias and ctx.needs_input_grad[1]:
+            gb = _bias_grad(g, Co, ctx.bias_ref)
+        return (gw, gb, None, None, None, None) + tuple(gxs)
+
+
+def cat_conv2d(parts, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO):
+    pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
+    return _CatConv2d.apply(weight, bias, stride, padding, pad_mode, act_out, *parts)
 
 
 def conv_fusable(kind, x, weight, stride, padding, output_padding=0):

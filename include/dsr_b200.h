@@ -124,7 +124,8 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
  *   dsr_tc_prep        fp32 NHWC activation -> arranged bf16 hi(+lo) operand [N][Ha][Wa][Ca]; fuses the preceding
  *                      norm-apply (prm = (mean, scale, shift) or NULL), ReLU / LeakyReLU, and the padding
  *                      (nn.ReflectionPad2d / padding_mode='replicate' / zeros).  layout: NORMAL (Ca >= Cp >= C),
- *                      PAIR (C = 32: pixel w and w+1 side by side, Ca = 2*Cp), S2D (space-to-depth of the padded
+ *                      PAIR (g = Ca/Cp horizontally adjacent pixels side by side: g = 2 for C = 32 layers, g = 8 for the
+ *                      1..8-channel first layers, so one 128-byte swizzle row holds a full K block), S2D (space-to-depth of the padded
  *                      input for stride-2 convs, Ca = 4*Cp).
  *   dsr_tc_pack_weight 4-D fp32 parameter -> bf16 hi(+lo) [Cout][T*Ca] K-major for the matching variant.
  *   dsr_tc_gemm        out[n, h*os+ph, w*os+pw, co] = bias[co] + sum_t sum_c A[n, h+ah+dr[t], w+aw+ds[t], c] W[co][t*Ca+c]

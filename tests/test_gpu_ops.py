@@ -401,6 +401,67 @@ def test_tc_wgrad_large(ops, wpass, tol):
         ops.CONFIG.update(old)
 
 
+def test_cat_conv2d_restricted_dgrad(ops):
+    """conv over a lazily concatenated input: forward == conv(cat), gradients only for the parts that need one"""
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16")
+        Cs, H, W = (128, 128, 2, 3), 32, 48
+        xs = [torch.randn(2, c, H, W, generator=G(90 + i)) for i, c in enumerate(Cs)]
+        xs[1].requires_grad_(True)
+        w = (torch.randn(64, sum(Cs), 4, 4, generator=G(95)) * 0.05).requires_grad_(True)
+        b = torch.randn(64, generator=G(96)).requires_grad_(True)
+        ref = F.conv2d(torch.cat(xs, 1), w, b, stride=2, padding=1)
+        go = torch.randn(ref.shape, generator=G(97))
+        (ref * go).sum().backward()
+        xc = [cl(x.detach()) for x in xs]
+        xc[1].requires_grad_(True)
+        wc, bc = w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+        out = ops.cat_conv2d(xc, wc, bc, 2, 1)
+        (out * go.cuda()).sum().backward()
+        assert rel_l2(out.cpu(), ref.detach()) <= 1e-5
+        assert rel_l2(xc[1].grad.cpu(), xs[1].grad) <= 5e-5 and xc[0].grad is None
+        assert rel_l2(wc.grad.cpu(), w.grad) <= 5e-5 and rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
+    finally:
+        ops.CONFIG.update(old)
+
+
+def test_fused_prologue_matches_unfused(ops):
+    """[InstanceNorm, ReLU, ReflectionPad, Conv] as ONE fused unit == the same modules run one by one (fwd + bwd)"""
+    from dsr_b200 import networks as nw
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16")
+        torch.manual_seed(5)
+        mods = [nw.Conv2d(64, 128, 3, stride=2, padding=1), nw.InstanceNorm2d(128), nw.ReLU(True), nw.ReflectionPad2d(1),
+                nw.Conv2d(128, 128, 3, padding=0), nw.InstanceNorm2d(128), nw.ReLU(True),
+                nw.ConvTranspose2d(128, 64, 3, stride=2, padding=1, output_padding=1), nw.Tanh()]
+        for m in mods:
+            m.cuda()
+        x = torch.randn(2, 64, 32, 32, generator=G(98))
+        go = torch.randn(2, 64, 32, 32, generator=G(99)).cuda()
+        res = []
+        for fused in (True, False):
+            xc = cl(x).requires_grad_(True)
+            for m in mods:
+                for p_ in m.parameters():
+                    p_.grad = None
+            if fused:
+                y = nw.run_fused(mods, xc)
+            else:
+                y = xc
+                for m in mods:
+                    y = m(y)
+            (y * go).sum().backward()
+            res.append((y.detach().cpu(), xc.grad.cpu(), [p_.grad.cpu().clone() for m in mods for p_ in m.parameters()]))
+        assert rel_l2(res[0][0], res[1][0]) <= 2e-5 and rel_l2(res[0][1], res[1][1]) <= 2e-4
+        for ga, gb in zip(res[0][2], res[1][2]):
+            if gb.dim() == 4:                                   # weights (biases in front of an IN are ~0 noise)
+                assert rel_l2(ga, gb) <= 2e-4
+    finally:
+        ops.CONFIG.update(old)
+
+
 def test_adam_matches_oracle(ops):
     n = 1003
     p, g = torch.randn(n, generator=G(50)), torch.randn(n, generator=G(51))
