@@ -325,7 +325,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapM_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // MMA issuer; both operands MN-major: bits 15 / 16 of the instruction descriptor
-        const uint32_t idesc = make_idesc(128, BLOCK_N, p.f16 ? 0u : 1u) | (1u << 15) | (1u << 16);
+        // operand formats are independent fields of the instruction descriptor (bits 7..9: A = M tensor, 10..12: B = A
+        // tensor): dY is bf16 (gradients span too many octaves for half) while x may be the forward pass's f16 operand
+        const uint32_t idesc = (1u << 4) | (((p.f16 & 1) ? 0u : 1u) << 7) | (((p.f16 & 2) ? 0u : 1u) << 10) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24) | (1u << 15) | (1u << 16);
         const uint64_t desc0 = make_sdesc_mn(0);
         for (int i = 0; i < nk; ++i) {
             const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
@@ -417,54 +420,87 @@ __device__ __forceinline__ void split16(float x, int f16, unsigned short& hi, un
         hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
     }
 }
-// one thread = 8 consecutive arranged channels (one 16-byte store per output tensor)
-__global__ void tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm,
-                               int act, float slope, int pad, int mode, int layout, int Cp,
-                               unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, int Ha, int Wa, int Ca,
-                               int f16) {
-    const int cg_per_pix = Ca >> 3;
-    const long total = (long)N * Ha * Wa * cg_per_pix;
+// One block walks arranged rows (n, ha); one thread-item = 8 consecutive arranged channels of one arranged pixel (two
+// 16-byte loads, one 16-byte store per output plane).  The (mean, scale, shift) table of the fused norm-apply is staged
+// in shared memory per image; csum (optional) receives the per-source-channel sum of everything written (the bias
+// gradient when the tensor is dY), accumulated in shared memory per block and flushed with fp64 atomics.
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm,
+               int act, float slope, int pad, int mode, int layout, int Cp,
+               unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, int Ha, int Wa, int Ca,
+               int f16, double* __restrict__ csum) {
+    extern __shared__ float prep_sm[];
+    float* s_prm = prep_sm;
+    float* s_sum = prep_sm + (prm ? 3 * C : 0);
+    const int tid = threadIdx.x;
+    const int cg = Ca >> 3, items = Wa * cg;
+    const int Hq = H + 2 * pad, Wq = W + 2 * pad;
+    const bool vec = (C & 3) == 0;
     const long NC = (long)N * C;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(idx % cg_per_pix);
-        long t = idx / cg_per_pix;
-        const int wa = (int)(t % Wa); t /= Wa;
-        const int ha = (int)(t % Ha);
-        const int n = (int)(t / Ha);
-        const int q = cg << 3;
-        int c, qi, qj;       // source channel start, padded-space row / col
-        if (layout == DSR_TC_LAYOUT_NORMAL) { c = q; qi = ha; qj = wa; }
-        else if (layout == DSR_TC_LAYOUT_PAIR) { c = q % Cp; qi = ha; qj = wa + q / Cp; }
-        else { const int ab = q / Cp; c = q - ab * Cp; qi = 2 * ha + (ab >> 1); qj = 2 * wa + (ab & 1); }
-        const int Hq = H + 2 * pad, Wq = W + 2 * pad;
-        float v[8];
+    if (csum) {
+        for (int i = tid; i < C; i += 256) s_sum[i] = 0.f;
+        __syncthreads();
+    }
+    int cached_n = -1;
+    for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
+        const int n = row / Ha, ha = row - n * Ha;
+        if (prm && n != cached_n) {
+            __syncthreads();
+            for (int i = tid; i < C; i += 256) {
+                s_prm[i] = prm[(long)n * C + i]; s_prm[C + i] = prm[NC + (long)n * C + i]; s_prm[2 * C + i] = prm[2 * NC + (long)n * C + i];
+            }
+            cached_n = n;
+            __syncthreads();
+        }
+        for (int it = tid; it < items; it += 256) {
+            const int wa = it / cg, q = (it - wa * cg) << 3;
+            int c, qi, qj;       // source channel start, padded-space row / col
+            if (layout == DSR_TC_LAYOUT_NORMAL) { c = q; qi = ha; qj = wa; }
+            else if (layout == DSR_TC_LAYOUT_PAIR) { const int g = q / Cp; c = q - g * Cp; qi = ha; qj = wa + g; }
+            else { const int ab = q / Cp; c = q - ab * Cp; qi = 2 * ha + (ab >> 1); qj = 2 * wa + (ab & 1); }
+            float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (qi < Hq && qj < Wq && c < C) {
-            const int i = prep_pad_src(qi, pad, H, mode), j = prep_pad_src(qj, pad, W, mode);
-            if (i >= 0 && j >= 0) {
-                const float* src = x + (((long)n * H + i) * W + j) * C + c;
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (qi < Hq && qj < Wq && c < C) {
+                const int i = prep_pad_src(qi, pad, H, mode), j = prep_pad_src(qj, pad, W, mode);
+                if (i >= 0 && j >= 0) {
+                    const float* src = x + (long)((n * H + i) * W + j) * C + c;
+                    if (vec && c + 8 <= C) {
+                        const float4 a = ld4(src), b4 = ld4(src + 4);
+                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+                    } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if (c + e < C) {
-                        float f = src[e];
-                        if (prm) {
-                            const long k = (long)n * C + c + e;
-                            f = (f - prm[k]) * prm[NC + k] + prm[2 * NC + k];
-                        }
-                        if (act == DSR_ACT_RELU) f = f > 0.f ? f : 0.f;
-                        else if (act == DSR_ACT_LRELU) f = f > 0.f ? f : slope * f;
-                        v[e] = f;
+                        for (int e = 0; e < 8; ++e) if (c + e < C) v[e] = src[e];
+                    }
+                    if (prm) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (c + e < C) v[e] = (v[e] - s_prm[c + e]) * s_prm[C + c + e] + s_prm[2 * C + c + e];
+                    }
+                    if (act == DSR_ACT_RELU) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : 0.f;
+                    } else if (act == DSR_ACT_LRELU) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : slope * v[e];
+                    }
+                    if (csum) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (c + e < C) atomicAdd(&s_sum[c + e], v[e]);
                     }
                 }
             }
-        }
-        __align__(16) unsigned short hi[8], lo[8];
+            __align__(16) unsigned short hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split16(v[e], f16, hi[e], lo[e]);
-        const long o = (((long)n * Ha + ha) * Wa + wa) * Ca + q;
-        *reinterpret_cast<uint4*>(Ahi + o) = *reinterpret_cast<const uint4*>(hi);
-        if (Alo) *reinterpret_cast<uint4*>(Alo + o) = *reinterpret_cast<const uint4*>(lo);
+            for (int e = 0; e < 8; ++e) split16(v[e], f16, hi[e], lo[e]);
+            const long o = ((long)row * Wa + wa) * Ca + q;
+            *reinterpret_cast<uint4*>(Ahi + o) = *reinterpret_cast<const uint4*>(hi);
+            if (Alo) *reinterpret_cast<uint4*>(Alo + o) = *reinterpret_cast<const uint4*>(lo);
+        }
+    }
+    if (csum) {
+        __syncthreads();
+        for (int i = tid; i < C; i += 256) atomicAdd(&csum[i], (double)s_sum[i]);
     }
 }
 
@@ -562,16 +598,22 @@ static int dispatch_n(int bn, const CUtensorMap& ah, const CUtensorMap& al, cons
 
 extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
                            int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
-                           void* stream) {
+                           double* csum, void* stream) {
     DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
     DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
     DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
     DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_PAIR && Ca % Cp == 0 && Ca >= 2 * Cp) ||
                     (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
     DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15), "operand buffers must be 16-byte aligned");
-    long total = (long)N * Ha * Wa * (Ca / 8);
-    tc_prep_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
-                                                                (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16);
+    DSR_REQUIRE(!csum || (layout != DSR_TC_LAYOUT_PAIR && (pad == 0 || pad_mode == DSR_PAD_ZERO)),
+                "channel sums need every source element to be written exactly once (no pixel groups, zero padding)");
+    DSR_REQUIRE((long)N * (H + 2 * pad) * (W + 2 * pad) < (1L << 31) && C <= 8192, "tensor too large for 32-bit pixel indices");
+    const long rows = (long)N * Ha;
+    const long cap = (long)dsr_num_sms() * 8;
+    const int grid = (int)(rows < cap ? rows : cap);
+    const size_t smem = ((prm ? 3 * (size_t)C : 0) + (csum ? (size_t)C : 0)) * sizeof(float);
+    tc_prep_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
+                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16, csum);
     return dsr_check_launch("tc_prep");
 }
 

@@ -247,6 +247,130 @@ __global__ void in_apply_bwd_kernel(const float* __restrict__ x, const float* __
     }
 }
 
+// float4 versions (C % 4 == 0, 16-byte aligned): blockIdx.y = image, one thread-item = 4 channels of one pixel.
+// These passes are pure HBM streams (12 .. 20 B per element); the scalar versions above spent their time in 64-bit
+// div / mod per element.
+__global__ void __launch_bounds__(256)
+norm_apply_fwd_vec4_kernel(const float4* __restrict__ x, const float* __restrict__ prm, const float4* __restrict__ res,
+                           float4* __restrict__ y, int N, int P, int C4, int act) {
+    const int n = blockIdx.y;
+    const long NC = (long)N * C4 * 4;
+    const float* pm = prm + (long)n * C4 * 4;
+    const long base = (long)n * P * C4;
+    const int total = P * C4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = (i % C4) * 4;
+        const float4 m = ld4(pm + c), sc = ld4(pm + NC + c), sh = ld4(pm + 2 * NC + c);
+        float4 v = x[base + i];
+        v.x = (v.x - m.x) * sc.x + sh.x; v.y = (v.y - m.y) * sc.y + sh.y;
+        v.z = (v.z - m.z) * sc.z + sh.z; v.w = (v.w - m.w) * sc.w + sh.w;
+        if (act == DSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (res) { const float4 r = res[base + i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        y[base + i] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+in_apply_bwd_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float* __restrict__ prm,
+                         const double* __restrict__ sums2, float4* __restrict__ dx, int N, int P, int C4, int act) {
+    const int n = blockIdx.y;
+    const long NC = (long)N * C4 * 4;
+    const float* pm = prm + (long)n * C4 * 4;
+    const double* s2 = sums2 + (long)n * C4 * 8;
+    const long base = (long)n * P * C4;
+    const int total = P * C4;
+    const float invP = 1.f / (float)P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = (i % C4) * 4;
+        const float4 m = ld4(pm + c), rs = ld4(pm + NC + c);
+        const float4 xv = x[base + i], g4 = dy[base + i];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float ms[4] = {m.x, m.y, m.z, m.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xh = (xs[k] - ms[k]) * rr[k];
+            float g = gs[k];
+            if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
+            const float m1 = (float)s2[(c + k) * 2] * invP, m2 = (float)s2[(c + k) * 2 + 1] * invP;
+            o[k] = rr[k] * (g - m1 - xh * m2);
+        }
+        dx[base + i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void __launch_bounds__(256)
+act_bwd_vec4_kernel(const float4* __restrict__ ref, const float4* __restrict__ gy, float4* __restrict__ gx, long n4, int kind,
+                    float slope) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 r = ref[i], g = gy[i];
+        const float rs[4] = {r.x, r.y, r.z, r.w}, gs[4] = {g.x, g.y, g.z, g.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float d = 1.f;
+            if (kind == DSR_ACT_RELU) d = rs[k] > 0.f ? 1.f : 0.f;
+            else if (kind == DSR_ACT_LRELU) d = rs[k] > 0.f ? 1.f : slope;
+            else if (kind == DSR_ACT_TANH) d = 1.f - rs[k] * rs[k];
+            o[k] = gs[k] * d;
+        }
+        gx[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+// IN-backward sums, float4: lanes run along channel quads, warps along pixels; per-(n, c) (sum dy', sum dy' * xhat)
+__global__ void __launch_bounds__(256)
+in_bwd_sums_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float* __restrict__ prm, int N, int P,
+                        int C4, int chunk, int act, double* __restrict__ sums) {
+    extern __shared__ float sh_s[];              // [rows][C4*4][2]
+    const int n = blockIdx.y;
+    const int Cw = C4 < 256 ? C4 : 256;          // threads along channel quads (C4 <= 256 here)
+    const int rows = 256 / Cw;
+    const int tx = threadIdx.x % Cw, ty = threadIdx.x / Cw;
+    const long NC = (long)N * C4 * 4;
+    const float* pm = prm + (long)n * C4 * 4;
+    const long base = (long)n * P * C4;
+    int p_begin = blockIdx.x * chunk, p_end = p_begin + chunk;
+    if (p_end > P) p_end = P;
+    for (int c0 = 0; c0 < C4; c0 += Cw) {
+        const int cq = c0 + tx;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (cq < C4 && ty < rows) {
+            const float4 m = ld4(pm + cq * 4), rs = ld4(pm + NC + cq * 4);
+            const float ms[4] = {m.x, m.y, m.z, m.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+            for (int p = p_begin + ty; p < p_end; p += rows) {
+                const float4 xv = x[base + (long)p * C4 + cq], gv = dy[base + (long)p * C4 + cq];
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float xh = (xs[k] - ms[k]) * rr[k];
+                    float g = gs[k];
+                    if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
+                    a[k] += g; b[k] += g * xh;
+                }
+            }
+        }
+        // reduce over the `rows` pixel lanes of the block, then one fp64 atomic per (n, c, quantity)
+        float* mine = sh_s + ((ty * Cw + tx) * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { mine[k] = a[k]; mine[4 + k] = b[k]; }
+        __syncthreads();
+        if (ty == 0 && cq < C4) {
+            double da[4], db[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { da[k] = 0.0; db[k] = 0.0; }
+            for (int r = 0; r < rows; ++r) {
+                const float* o = sh_s + ((r * Cw + tx) * 8);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { da[k] += (double)o[k]; db[k] += (double)o[4 + k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                atomicAdd(&sums[((long)n * C4 * 4 + cq * 4 + k) * 2], da[k]);
+                atomicAdd(&sums[((long)n * C4 * 4 + cq * 4 + k) * 2 + 1], db[k]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // weights: 4-D parameter [D0][D1][R][S] <-> packed GEMM operand [(r*S+s)*Ck + ck][Co]
 //   kdim == 1: ck indexes D1, co indexes D0 (Conv2d forward, ConvTranspose2d dgrad)
@@ -365,7 +489,11 @@ extern "C" int dsr_act_fwd(const float* x, float* y, long n, int kind, float slo
 }
 extern "C" int dsr_act_bwd(const float* ref, const float* gy, float* gx, long n, int kind, float slope, void* stream) {
     DSR_REQUIRE(ref && gy && gx, "null pointer");
-    act_bwd_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(ref, gy, gx, n, kind, slope);
+    if (!(n & 3) && !((uintptr_t)ref & 15) && !((uintptr_t)gy & 15) && !((uintptr_t)gx & 15))
+        act_bwd_vec4_kernel<<<dsr_grid(n / 4, 256), 256, 0, ST(stream)>>>((const float4*)ref, (const float4*)gy, (float4*)gx, n / 4, kind,
+                                                                         slope);
+    else
+        act_bwd_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(ref, gy, gx, n, kind, slope);
     return dsr_check_launch("act_bwd");
 }
 static void sums_launch_cfg(int N, long P, long* chunk, dim3* grid) {
@@ -392,7 +520,17 @@ extern "C" int dsr_norm_finalize(const double* sums, int N, int C, long P, int g
 extern "C" int dsr_norm_apply_fwd(const float* x, const float* prm, const float* res, float* y, int N, long P, int C,
                                   int act, void* stream) {
     DSR_REQUIRE(x && prm && y, "null pointer");
-    norm_apply_fwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, prm, res, y, N, P, C, act);
+    const bool vec = !(C & 3) && !((uintptr_t)x & 15) && !((uintptr_t)y & 15) && !((uintptr_t)res & 15) && !((uintptr_t)prm & 15) &&
+                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31);
+    if (vec) {
+        const long items = P * (C / 4);
+        long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
+        if (gx > cap) gx = cap;
+        norm_apply_fwd_vec4_kernel<<<dim3((unsigned)gx, (unsigned)N), 256, 0, ST(stream)>>>((const float4*)x, prm, (const float4*)res,
+                                                                                           (float4*)y, N, (int)P, C / 4, act);
+    } else {
+        norm_apply_fwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, prm, res, y, N, P, C, act);
+    }
     return dsr_check_launch("norm_apply_fwd");
 }
 extern "C" int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm, int N, long P, int C, int act,
@@ -400,13 +538,29 @@ extern "C" int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm
     DSR_REQUIRE(x && dy && prm && sums2, "null pointer");
     long chunk; dim3 grid;
     sums_launch_cfg(N, P, &chunk, &grid);
-    channel_sums_kernel<<<grid, TPB, 0, ST(stream)>>>(x, dy, prm, N, P, C, chunk, 1, act, sums2);
+    const bool vec = !(C & 3) && C / 4 <= 256 && (256 % (C / 4 < 256 ? C / 4 : 256)) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)dy & 15) &&
+                     !((uintptr_t)prm & 15) && !((N * (long)C) & 3) && P * (C / 4) < (1L << 31);
+    if (vec)
+        in_bwd_sums_vec4_kernel<<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, N, (int)P,
+                                                                                   C / 4, (int)chunk, act, sums2);
+    else
+        channel_sums_kernel<<<grid, TPB, 0, ST(stream)>>>(x, dy, prm, N, P, C, chunk, 1, act, sums2);
     return dsr_check_launch("in_bwd_sums");
 }
 extern "C" int dsr_in_bwd_apply(const float* x, const float* dy, const float* prm, const double* sums2, float* dx,
                                 int N, long P, int C, int act, void* stream) {
     DSR_REQUIRE(x && dy && prm && sums2 && dx, "null pointer");
-    in_apply_bwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, sums2, dx, N, P, C, act);
+    const bool vec = !(C & 3) && !((uintptr_t)x & 15) && !((uintptr_t)dy & 15) && !((uintptr_t)dx & 15) && !((uintptr_t)prm & 15) &&
+                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31);
+    if (vec) {
+        const long items = P * (C / 4);
+        long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
+        if (gx > cap) gx = cap;
+        in_apply_bwd_vec4_kernel<<<dim3((unsigned)gx, (unsigned)N), 256, 0, ST(stream)>>>((const float4*)x, (const float4*)dy, prm, sums2,
+                                                                                         (float4*)dx, N, (int)P, C / 4, act);
+    } else {
+        in_apply_bwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, sums2, dx, N, P, C, act);
+    }
     return dsr_check_launch("in_bwd_apply");
 }
 extern "C" int dsr_pack_weight(const float* w, int D0, int D1, int R, int S, int kdim, float* out, void* stream) {

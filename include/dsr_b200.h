@@ -143,7 +143,8 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
 #define DSR_TC_W_CONVT_PH 3
 #define DSR_TC_W_CONV_DGRAD 4
 int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
-                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16, void* stream);
+                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
+                double* csum /* optional: += per-channel sums of x (bias gradient of a dY), pre-zeroed */, void* stream);
 int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,
                        int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, int f16, float wscale, void* stream);
 int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
@@ -178,7 +179,9 @@ int dsr_tc2_set_debug(long long* counters);
 
 /* weight gradient on the tcgen05 path: dWp[cm][t*Ca + c] = sum_p M[p + moff][cm] * A[p + aoff + tap_t][c] over the
  * base grid (Hb x Wb x N); M = arranged dY (Conv2d) or x (ConvTranspose2d), A = the arranged operand of the forward
- * GEMM.  dWp is fp32 [Cm_real][T*Ca]; dsr_tc_unpack_wgrad scatters it back into the (D0, D1, R, S) parameter layout. */
+ * GEMM.  dWp is fp32 [Cm_real][T*Ca]; dsr_tc_unpack_wgrad scatters it back into the (D0, D1, R, S) parameter layout.
+ * f16: bit 0 = M is IEEE half (else bf16), bit 1 = A is IEEE half (else bf16); the hardware requires both operands of
+ * one kind::f16 MMA to have the same format (mixed formats raise an illegal-instruction fault), so pass 0 or 3. */
 int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h,
                  int m_off_w, const void* A_hi, const void* A_lo, int Ha, int Wa, int Ca, int T, const int* tap_dr,
                  const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb, float* dWp, int npass, int f16,

@@ -19,7 +19,7 @@ if [ "${NCU:-1}" = "1" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
   $CMD > $out/plain_$tag.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-4000} -c ${NCU_COUNT:-1400} --csv --log-file $out/launches_$tag.csv $CMD > $out/ncu_l_$tag.log 2>&1
-  for k in ${NCU_KERNELS:-conv_tc_kernel wgrad_tc_kernel}; do
+  for k in ${NCU_KERNELS-conv_tc3_kernel conv_tc2_kernel}; do
     ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_KSKIP:-60} -c 3 -f -o $out/prof_${k}_$tag $CMD > $out/ncu_${k}_$tag.log 2>&1
     tail -2 $out/ncu_${k}_$tag.log
   done
