@@ -34,6 +34,8 @@ struct TcParams {
     int ah, aw;               // A coordinate offsets
     int Ho, Wo, Cout, os, ph, pw;   // output tensor geometry
     int act, ksteps_per_split, ksteps;
+    int nphase, tiles_per_phase;   // nphase = 4: the four output phases of a stride-2 transposed conv in ONE launch
+                                   // (phase (a, b): A offsets + (a, b), output offsets (a, b), weight rows + phase*Cout)
     int f16;                  // operands are IEEE half (11-bit significand) instead of bf16
     float out_scale;          // accumulator scale (undoes the power-of-two weight scale of the f16 path)
     signed char dr[TC_MAX_TAPS], ds[TC_MAX_TAPS];
@@ -71,6 +73,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 
     // tile coordinates
     int tile = blockIdx.x;
+    const int phase = tile / p.tiles_per_phase;
+    tile -= phase * p.tiles_per_phase;
+    const int pa = phase >> 1, pb = phase & 1;
     const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
     const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
     const int n0 = tile * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
@@ -107,14 +112,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 const int k = kb + i;
                 const int t = k / cblocks, cb = k - t * cblocks;
                 const int ca = cb << 6;
-                const int hc = h0 + p.ah + p.dr[t], wc = w0 + p.aw + p.ds[t];
+                const int hc = h0 + p.ah + pa + p.dr[t], wc = w0 + p.aw + pb + p.ds[t];
                 const uint32_t st = smem_base + s * Cfg::STAGE;
                 mbar_expect_tx(full_bar(s), Cfg::STAGE);
                 tma_load_4d(st, &mapA_hi, full_bar(s), ca, wc, hc, n0);
                 if (NPASS >= 2) tma_load_4d(st + Cfg::A_TILE, &mapA_lo, full_bar(s), ca, wc, hc, n0);
-                const int kw = t * p.Ca + ca;
-                tma_load_2d(st + Cfg::NA * Cfg::A_TILE, &mapW_hi, full_bar(s), kw, co0);
-                if (NPASS >= 3) tma_load_2d(st + Cfg::NA * Cfg::A_TILE + Cfg::W_TILE, &mapW_lo, full_bar(s), kw, co0);
+                const int kw = t * p.Ca + ca, wrow = phase * p.Cout + co0;
+                tma_load_2d(st + Cfg::NA * Cfg::A_TILE, &mapW_hi, full_bar(s), kw, wrow);
+                if (NPASS >= 3) tma_load_2d(st + Cfg::NA * Cfg::A_TILE + Cfg::W_TILE, &mapW_lo, full_bar(s), kw, wrow);
             }
             __syncwarp();
         }
@@ -151,7 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
         const int n = n0 + tn, h = h0 + th, w = w0 + tw;
         const bool valid = (n < p.N) && (h < p.Ht) && (w < p.Wt);
-        float* orow = out + ((((long)n * p.Ho + (long)h * p.os + p.ph) * p.Wo) + (long)w * p.os + p.pw) * p.Cout;
+        float* orow = out + ((((long)n * p.Ho + (long)h * p.os + p.ph + pa) * p.Wo) + (long)w * p.os + p.pw + pb) * p.Cout;
         if (nk > 0) {
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
@@ -629,9 +634,10 @@ extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, 
 
 extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                            int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
-                           const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                           const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
                            int split_k, int f16, float out_scale, void* stream) {
     DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
+    DSR_REQUIRE(nphase == 1 || (nphase == 4 && os == 2 && ph == 0 && pw == 0), "phases: 1, or 4 with output stride 2");
     DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
     DSR_REQUIRE(T >= 1 && T <= TC_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
     DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)W_hi & 15) && !((uintptr_t)out & 15), "buffers must be 16-byte aligned");
@@ -652,7 +658,7 @@ extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, in
     if (npass == 3 && bn == 256) bn = 128;          // keep >= 2 pipeline stages in 200 KB of smem
     int tiles_co = dsr_cdiv(Cout, bn);
     p.ksteps = T * (Ca / 64);
-    long ctas = (long)p.tiles_w * p.tiles_h * tiles_n * tiles_co;
+    long ctas = (long)p.tiles_w * p.tiles_h * tiles_n * tiles_co * nphase;
     int splits = 1;
     if (split_k < 0) {              // auto: only when the grid would leave most SMs idle
         if (ctas * 2 <= dsr_num_sms() && p.ksteps >= 16) {
@@ -662,13 +668,14 @@ extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, in
         }
     } else if (split_k > 1) splits = split_k;
     if (splits > 1 && act != DSR_ACT_NONE) splits = 1;
+
     p.ksteps_per_split = dsr_cdiv(p.ksteps, splits);
     splits = dsr_cdiv(p.ksteps, p.ksteps_per_split);
     if (splits > 1) {
         if (cudaMemsetAsync(out, 0, (size_t)N * Ho * Wo * Cout * sizeof(float), ST(stream)) != cudaSuccess) {
             dsr_set_error("conv_tc: memset failed"); return DSR_ERR_CUDA;
         }
-        DSR_REQUIRE(os == 1, "split-K with output phases would zero the other phases");
+        DSR_REQUIRE(os == 1 || nphase == 4, "split-K of a single output phase would zero the other phases");
     }
     CUtensorMap mah, mal, mwh, mwl;
     cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
@@ -678,13 +685,14 @@ extern "C" int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, in
     if (rc) return rc;
     mal = mah;
     if (npass >= 2 && (rc = encode_map(&mal, A_lo, 4, adims, astr, abox))) return rc;
-    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout};
+    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout * nphase};     // phase weight matrices stacked along rows
     cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
     cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
     if ((rc = encode_map(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;
     mwl = mwh;
     if (npass >= 3 && (rc = encode_map(&mwl, W_lo, 2, wdims, wstr, wbox))) return rc;
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)tiles_co, (unsigned)splits);
+    p.nphase = nphase; p.tiles_per_phase = p.tiles_w * p.tiles_h * tiles_n;
+    dim3 grid((unsigned)(p.tiles_per_phase * nphase), (unsigned)tiles_co, (unsigned)splits);
     if (npass == 1) return dispatch_n<1>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
     if (npass == 2) return dispatch_n<2>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));
     return dispatch_n<3>(bn, mah, mal, mwh, mwl, p, bias, out, grid, ST(stream));

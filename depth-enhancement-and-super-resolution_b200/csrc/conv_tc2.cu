@@ -26,6 +26,7 @@ struct Tc2Params {
     int Ca, T, cblocks;
     int ah, aw, Hp, PW;       // patch = Hp rows x PW pixels x 128 B (PW = 8 + widest tap offset)
     int Ho, Wo, Cout, os, ph, pw;
+    int nphase, tiles_per_phase;  // 4 output phases of a stride-2 transposed conv in one launch (see conv_tc.cu)
     int act, f16, base_off_mode;
     float out_scale;
     int n_pb, n_ws;
@@ -80,6 +81,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     auto af = [&](int i) { return bar_base + 8u * (2 * p.n_pb + 2 * p.n_ws + i); };
     auto ae = [&](int i) { return bar_base + 8u * (2 * p.n_pb + 2 * p.n_ws + 2 + i); };
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.n_pb + 2 * p.n_ws + 4);
+    const uint32_t epi_base = bar_base + 512u;          // 4 KB of per-warp bias copies + 16 KB of store staging tiles
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,11 +112,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         {
             int pi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                int r = tile / p.tiles_co;
+                const int phase = tile / p.tiles_per_phase;
+                int r = (tile - phase * p.tiles_per_phase) / p.tiles_co;
                 const int tw_i = r % p.tiles_w; r /= p.tiles_w;
                 const int th_i = r % p.tiles_h;
                 const int n = r / p.tiles_h;
-                const int hc = th_i * TC2_TH + p.ah, wc = tw_i * TC2_TW + p.aw;
+                const int hc = th_i * TC2_TH + p.ah + (phase >> 1), wc = tw_i * TC2_TW + p.aw + (phase & 1);
                 for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
                     const int b = pi % p.n_pb, it = pi / p.n_pb;
                     TC2_TIMED_WAIT(0, pe(b), (it & 1) ^ 1);
@@ -134,7 +137,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         {
             int wi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int co0 = (tile % p.tiles_co) * BLOCK_N;
+                const int phase = tile / p.tiles_per_phase;
+                const int co0 = ((tile - phase * p.tiles_per_phase) % p.tiles_co) * BLOCK_N + phase * p.Cout;
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     for (int t = 0; t < p.T; ++t, ++wi) {
                         const int s = wi % p.n_ws, it = wi / p.n_ws;
@@ -208,21 +212,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         }
     } else {
         // ===== epilogue warps 3..6 =====
+        // TMEM lane = pixel, registers = channels.  A thread's 32 channels of one pixel are staged through a per-warp 4 KB
+        // shared-memory tile (16-byte granules XOR-swizzled by the row, conflict-free both ways) and leave as 512-byte
+        // coalesced stores: lane l of store i writes granule (l & 7) of pixel i*4 + (l >> 3).  Bias comes from a per-warp
+        // shared copy (one load per tile instead of one __ldg per element).
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int th = row >> 3, tw = row & 7;
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+        float* s_bias = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + q * 256;
+        float4* stg = reinterpret_cast<float4*>(smem_raw + (epi_base + 4096 - smem_u32(smem_raw))) + q * 256;
+        const bool vec_out = (p.Cout & 3) == 0 && CH == 32;
+        const bool tanh_out = p.act == DSR_ACT_TANH;
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
             const int ab = ti & 1;
-            int r = tile / p.tiles_co;
-            const int co0 = (tile - r * p.tiles_co) * BLOCK_N;
+            const int phase = tile / p.tiles_per_phase;
+            const int tp = tile - phase * p.tiles_per_phase;
+            int r = tp / p.tiles_co;
+            const int co0 = (tp - r * p.tiles_co) * BLOCK_N;
             const int tw_i = r % p.tiles_w; r /= p.tiles_w;
             const int th_i = r % p.tiles_h;
             const int n = r / p.tiles_h;
             const int h = th_i * TC2_TH + th, w = tw_i * TC2_TW + tw;
             const bool valid = (h < p.Ht) && (w < p.Wt);
-            float* orow = out + ((((long)n * p.Ho + (long)h * p.os + p.ph) * p.Wo) + (long)w * p.os + p.pw) * p.Cout;
+            // pixel (0, 0) of the tile in the output tensor; rows of the tile are os*Wo*Cout apart, pixels os*Cout
+            float* obase = out + ((((long)n * p.Ho + (long)(th_i * TC2_TH) * p.os + p.ph + (phase >> 1)) * p.Wo) +
+                                  (long)(tw_i * TC2_TW) * p.os + p.pw + (phase & 1)) * p.Cout;
+            const long pstride = (long)p.os * p.Cout, rstride = (long)p.os * p.Wo * p.Cout;
+            float* orow = obase + (long)th * rstride + (long)tw * pstride;
+#pragma unroll
+            for (int k = 0; k < (BLOCK_N + 31) / 32; ++k) {
+                const int co = co0 + k * 32 + lane;
+                s_bias[k * 32 + lane] = (bias != nullptr && co < p.Cout) ? __ldg(bias + co) : 0.f;
+            }
+            __syncwarp();
             TC2_TIMED_WAIT(0, af(ab), (ti >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -232,63 +256,60 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 if (CH == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
                 tc_wait_ld();
                 float f[32];
+                const int nch = p.Cout - co0 - c0;              // channels of this chunk inside the tensor (may exceed CH)
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int co = co0 + c0 + j;
-                    float x = 0.f;
-                    if (valid && co < p.Cout) {
-                        x = __uint_as_float(v[j]) * p.out_scale;
-                        if (bias != nullptr) x += __ldg(bias + co);
+                for (int j = 0; j < CH; ++j)
+                    f[j] = (valid && j < nch) ? __uint_as_float(v[j]) * p.out_scale + s_bias[c0 + j] : 0.f;
+                if (vec_out) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        if (tanh_out) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+                        stg[lane * 8 + (j ^ (lane & 7))] = o;
                     }
-                    f[j] = x;
-                }
-                if (valid) {
-                    if (p.act == DSR_ACT_TANH) {
+                    __syncwarp();
+                    const int g = lane & 7;
+                    if (g * 4 < nch) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(tanhf(f[j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(f[j]);
-                    }
-                    if ((p.Cout & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < CH; j += 4) {
-                            const int co = co0 + c0 + j;
-                            if (co < p.Cout)
-                                *reinterpret_cast<uint4*>(orow + co) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            const int co = co0 + c0 + j;
-                            if (co < p.Cout) orow[co] = __uint_as_float(v[j]);
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + (lane >> 3);            // pixel of this warp: tile row q*4 + i/2, column (i&1)*4 + lane/8
+                            const int hh = q * 4 + (i >> 1), ww = (i & 1) * 4 + (lane >> 3);
+                            if (th_i * TC2_TH + hh < p.Ht && tw_i * TC2_TW + ww < p.Wt) {
+                                const float4 o = stg[rr * 8 + (g ^ (rr & 7))];
+                                *reinterpret_cast<float4*>(obase + (long)hh * rstride + (long)ww * pstride + co0 + c0 + g * 4) = o;
+                            }
                         }
                     }
+                    __syncwarp();
+                } else if (valid) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (j < nch) orow[co0 + c0 + j] = tanh_out ? tanhf(f[j]) : f[j];
                 }
                 if (stats != nullptr && CH == 32) {
                     // column sums over the warp's 32 pixels by a reduce-scatter butterfly: after the five exchange steps
                     // lane l holds the total of channel c0 + l (31 shuffles per quantity instead of 160)
-                    float g[32];
+                    float g2[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) g[j] = f[j] * f[j];
+                    for (int j = 0; j < 32; ++j) g2[j] = f[j] * f[j];
 #pragma unroll
                     for (int step = 16; step >= 1; step >>= 1) {
                         const bool up = (lane & step) != 0;
 #pragma unroll
                         for (int j = 0; j < step; ++j) {
                             const float sf = up ? f[j] : f[j + step];
-                            const float sg = up ? g[j] : g[j + step];
+                            const float sg = up ? g2[j] : g2[j + step];
                             const float rf = __shfl_xor_sync(0xffffffffu, sf, step);
                             const float rg = __shfl_xor_sync(0xffffffffu, sg, step);
                             f[j] = (up ? f[j + step] : f[j]) + rf;
-                            g[j] = (up ? g[j + step] : g[j]) + rg;
+                            g2[j] = (up ? g2[j + step] : g2[j]) + rg;
                         }
                     }
                     const int co = co0 + c0 + lane;
                     if (co < p.Cout) {
                         double* sp = stats + ((long)n * p.Cout + co) * 2;
                         atomicAdd(sp, (double)f[0]);
-                        atomicAdd(sp + 1, (double)g[0]);
+                        atomicAdd(sp + 1, (double)g2[0]);
                     }
                 }
             }
@@ -311,6 +332,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 #define ST(s) ((cudaStream_t)(s))
 static const int TC2_SMEM_MAX = 227 * 1024;
+static const int TC2_EPI_SMEM = 4096 + 16384;
 
 template <int BLOCK_N, int NPASS>
 static int launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
@@ -356,8 +378,9 @@ static int tc2_env(const char* name, int dflt) {
 
 extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                             int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
-                            const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                            const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
                             int f16, float out_scale, double* stats, void* stream) {
+    DSR_REQUIRE(nphase == 1 || (nphase == 4 && os == 2 && ph == 0 && pw == 0), "phases: 1, or 4 with output stride 2");
     DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
     DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
     DSR_REQUIRE(T >= 1 && T <= TC2_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
@@ -385,13 +408,14 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     p.base_off_mode = tc2_env("DSR_TC2_BASEOFF", 0);   // measured on B200: the swizzle XOR uses absolute smem address bits,
                                                         // so shifted descriptor starts need NO base offset
     p.tiles_w = dsr_cdiv(Wt, TC2_TW); p.tiles_h = dsr_cdiv(Ht, TC2_TH); p.tiles_co = dsr_cdiv(Cout, bn);
-    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_co * N;
+    p.nphase = nphase; p.tiles_per_phase = p.tiles_w * p.tiles_h * p.tiles_co * N;
+    p.total_tiles = p.tiles_per_phase * nphase;
     p.PW = tc2_env("DSR_TC2_PW", TC2_TW + max_ds);
     p.patch_tx_bytes = (unsigned)p.Hp * p.PW * 128u;
     p.patch_plane_bytes = (p.patch_tx_bytes + 1023u) & ~1023u;
     const int na = npass >= 2 ? 2 : 1, nw = npass >= 3 ? 2 : 1;
     const long patch_set = (long)na * p.patch_plane_bytes, w_stage = (long)nw * bn * 128;
-    const long budget = TC2_SMEM_MAX - 1024 - 512;
+    const long budget = TC2_SMEM_MAX - 1024 - 512 - TC2_EPI_SMEM;
     // shared-memory plan: double-buffer the patch when at least 4 weight stages (>= 96 KB in flight hides the L2
     // latency at full MMA rate) still fit beside it
     const int want_ws = tc2_env("DSR_TC2_MINWS", 4);
@@ -401,7 +425,7 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     if (ws > 8) ws = 8;
     if (ws < 2) { dsr_set_error("conv_tc2: tile does not fit shared memory"); return DSR_ERR_UNSUPPORTED; }
     p.n_ws = (int)ws;
-    const int smem = (int)(p.n_pb * patch_set + p.n_ws * w_stage + 1024 + 512);
+    const int smem = (int)(p.n_pb * patch_set + p.n_ws * w_stage + 1024 + 512 + TC2_EPI_SMEM);
 
     CUtensorMap mah, mal, mwh, mwl;
     cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
@@ -411,7 +435,7 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     if (rc) return rc;
     mal = mah;
     if (npass >= 2 && (rc = encode_map(&mal, A_lo, 4, adims, astr, abox))) return rc;
-    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout};
+    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout * nphase};
     cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
     cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
     if ((rc = encode_map(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;

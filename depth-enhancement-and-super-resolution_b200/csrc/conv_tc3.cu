@@ -28,6 +28,7 @@ struct Tc3Params {
     int Ca, T, cblocks;       // cblocks = Ca / 32
     int ah, aw, Hp, PW;       // patch = Hp rows x PW pixels x 64 B
     int Ho, Wo, Cout, os, ph, pw;
+    int nphase, tiles_per_phase;  // 4 output phases of a stride-2 transposed conv in one launch (see conv_tc.cu)
     int act, f16;
     float out_scale;
     int n_pb, n_ws;
@@ -107,11 +108,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         {
             int pi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                int r = tile / p.tiles_co;
+                const int phase = tile / p.tiles_per_phase;
+                int r = (tile - phase * p.tiles_per_phase) / p.tiles_co;
                 const int tw_i = r % p.tiles_w; r /= p.tiles_w;
                 const int th_i = r % p.tiles_h;
                 const int n = r / p.tiles_h;
-                const int hc = th_i * p.TH + p.ah, wc = tw_i * TC3_TW + p.aw;
+                const int hc = th_i * p.TH + p.ah + (phase >> 1), wc = tw_i * TC3_TW + p.aw + (phase & 1);
                 for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
                     const int b = pi % p.n_pb, it = pi / p.n_pb;
                     TC3_TIMED_WAIT(0, pe(b), (it & 1) ^ 1);
@@ -131,7 +133,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         {
             int wi = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int co0 = (tile % p.tiles_co) * 128;
+                const int phase = tile / p.tiles_per_phase;
+                const int co0 = ((tile - phase * p.tiles_per_phase) % p.tiles_co) * 128 + phase * p.Cout;
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     for (int t = 0; t < p.T; ++t, ++wi) {
                         const int s = wi % p.n_ws, it = wi / p.n_ws;
@@ -212,8 +215,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
             const int ab = ti & 1;
-            int r = tile / p.tiles_co;
-            const int co = (tile - r * p.tiles_co) * 128 + q * 32 + lane;
+            const int phase = tile / p.tiles_per_phase;
+            const int tp = tile - phase * p.tiles_per_phase;
+            int r = tp / p.tiles_co;
+            const int co = (tp - r * p.tiles_co) * 128 + q * 32 + lane;
             const int tw_i = r % p.tiles_w; r /= p.tiles_w;
             const int th_i = r % p.tiles_h;
             const int n = r / p.tiles_h;
@@ -224,7 +229,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             int hvalid = p.Ht - h0;                                // rows of the tile inside the image
             if (hvalid > p.TH) hvalid = p.TH;
             if (!cvalid) hvalid = 0;
-            float* obase = out + (((long)n * p.Ho + (long)h0 * p.os + p.ph) * p.Wo + (long)w0 * p.os + p.pw) * p.Cout + co;
+            float* obase = out + (((long)n * p.Ho + (long)h0 * p.os + p.ph + (phase >> 1)) * p.Wo + (long)w0 * p.os + p.pw + (phase & 1)) * p.Cout + co;
             float ssum = 0.f, ssq = 0.f;
             TC3_TIMED_WAIT(0, af(ab), (ti >> 1) & 1);
             tc_fence_after();
@@ -350,8 +355,9 @@ static int tc3_pick_th(int N, int Ht, int Wt, int tiles_co, int sms) {
 
 extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                             int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
-                            const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                            const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
                             int f16, float out_scale, double* stats, void* stream) {
+    DSR_REQUIRE(nphase == 1 || (nphase == 4 && os == 2 && ph == 0 && pw == 0), "phases: 1, or 4 with output stride 2");
     DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
     DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
     DSR_REQUIRE(T >= 1 && T <= TC3_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
@@ -371,13 +377,14 @@ extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, i
     }
     p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.cblocks = Ca / 32;
     p.tiles_co = dsr_cdiv(Cout, 128);
-    p.TH = tc3_env("DSR_TC3_TH", tc3_pick_th(N, Ht, Wt, p.tiles_co, dsr_num_sms()));
+    p.TH = tc3_env("DSR_TC3_TH", tc3_pick_th(N, Ht, Wt, p.tiles_co * nphase, dsr_num_sms()));
     if (p.TH < 2 || p.TH > 32 || (p.TH & 1)) { dsr_set_error("conv_tc3: bad tile height %d", p.TH); return DSR_ERR_ARG; }
     p.ah = a_off_h; p.aw = a_off_w; p.Hp = p.TH + max_dr; p.PW = TC3_TW + max_ds;
     p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.os = os; p.ph = ph; p.pw = pw; p.act = act;
     p.f16 = f16; p.out_scale = out_scale;
     p.tiles_w = dsr_cdiv(Wt, TC3_TW); p.tiles_h = dsr_cdiv(Ht, p.TH);
-    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_co * N;
+    p.nphase = nphase; p.tiles_per_phase = p.tiles_w * p.tiles_h * p.tiles_co * N;
+    p.total_tiles = p.tiles_per_phase * nphase;
     p.patch_tx_bytes = (unsigned)p.Hp * p.PW * 64u;
     p.patch_plane_bytes = (p.patch_tx_bytes + 1023u) & ~1023u;
     const int na = npass >= 2 ? 2 : 1, nw = npass >= 3 ? 2 : 1;
@@ -399,7 +406,7 @@ extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, i
     if (rc) return rc;
     mal = mah;
     if (npass >= 2 && (rc = encode_map64(&mal, A_lo, 4, adims, astr, abox))) return rc;
-    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout};
+    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout * nphase};
     cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
     cuuint32_t wbox[2] = {32, 128};
     if ((rc = encode_map64(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;

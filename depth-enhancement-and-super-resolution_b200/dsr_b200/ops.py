@@ -255,6 +255,41 @@ class _Prepared:
         return None
 
 
+def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
+    """the four output-phase weight matrices of a stride-2 transposed conv, stacked along rows ([4*Co][T*Ca]) so one GEMM
+    launch serves all phases; cached on the parameter like _tc_weights"""
+    npass = CONFIG["passes"]
+    epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
+    stamp = (weight._version, epoch, weight.data_ptr())
+    f16 = (dtype or CONFIG["dtype"]) == "f16"
+    key = ("phases", plan["Ca"], pad, npass >= 3, f16)
+    cache = getattr(weight, "_dsr_pack", None)
+    if cache is None or cache.get("stamp") != stamp:
+        cache = {"stamp": stamp}
+        try:
+            weight._dsr_pack = cache
+        except AttributeError:
+            pass
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    D0, D1, R, S = weight.shape
+    w = weight.detach()
+    w = w if w.is_contiguous() else w.contiguous()
+    K = plan["T"] * plan["Ca"]
+    whi = torch.empty((4 * Co, K), device=w.device, dtype=torch.bfloat16)
+    wlo = torch.empty((4 * Co, K), device=w.device, dtype=torch.bfloat16) if npass >= 3 else None
+    for a in (0, 1):
+        for b in (0, 1):
+            ph = 2 * a + b
+            _call("dsr_tc_pack_weight", _p(w), D0, D1, R, S, plan["variant"], plan["Cp"], a, b, pad, Co, plan["T"], plan["Ca"],
+                  _p(whi[ph * Co:(ph + 1) * Co], torch.bfloat16),
+                  _p(wlo[ph * Co:(ph + 1) * Co], torch.bfloat16) if wlo is not None else None,
+                  int(f16), W_SCALE if f16 else 1.0)
+    cache[key] = (whi, wlo)
+    return whi, wlo
+
+
 def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=None, csum=None):
     """fp32 NHWC -> arranged bf16 hi(+lo) operand."""
     if isinstance(xh, _Prepared):
@@ -274,31 +309,31 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=N
     return ahi, alo, Ha, Wa
 
 
-def _tc_kernel_for(N, Ht, Wt, Co, ds):
+def _tc_kernel_for(N, Ht, Wt, Co, ds, nphase=1):
     """which GEMM kernel serves this output grid: 3 = channel-major (csrc/conv_tc3.cu, Cout >= 128), 2 = halo
     pixel-major (csrc/conv_tc2.cu), 1 = first generation with split-K (few tiles, long K; forced split-K)."""
     if not CONFIG["tc_halo"] or CONFIG["split_k"] > 1 or Ht * Wt < 128 or Wt < 8 or max(ds) > 8:
         return 1
     if Co >= 128 and Ht >= 16 and CONFIG["tc_cm"]:
-        tiles = N * ((Ht + 31) // 32) * ((Wt + 7) // 8) * ((Co + 127) // 128)
+        tiles = nphase * N * ((Ht + 31) // 32) * ((Wt + 7) // 8) * ((Co + 127) // 128)
         return 3 if tiles >= CONFIG["halo_min_tiles"] else 1
     bn = 256 if Co >= 256 else 128
-    tiles = N * ((Ht + 15) // 16) * ((Wt + 7) // 8) * ((Co + bn - 1) // bn)
+    tiles = nphase * N * ((Ht + 15) // 16) * ((Wt + 7) // 8) * ((Co + bn - 1) // bn)
     return 2 if tiles >= CONFIG["halo_min_tiles"] else 1
 
 
 def _tc_gemm(ahi, alo, N, Ha, Wa, Ca, whi, wlo, Co, T, dr, ds, aoh, aow, Ht, Wt, bias, y, Ho, Wo, os_, ph, pw, act_out,
-             dtype, split_k, stats=None):
+             dtype, split_k, stats=None, nphase=1):
     """one GEMM launch on the best kernel for the shape; returns True when `stats` was filled by the epilogue"""
-    which = CONFIG.get("force_kernel") or _tc_kernel_for(N, Ht, Wt, Co, list(ds))
+    which = CONFIG.get("force_kernel") or _tc_kernel_for(N, Ht, Wt, Co, list(ds), nphase)
     if which == 1:
         _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
               _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
-              Ho, Wo, os_, ph, pw, act_out, CONFIG["passes"], split_k, *_tc_fmt(dtype))
+              Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], split_k, *_tc_fmt(dtype))
         return False
     _call("dsr_tc_gemm3" if which == 3 else "dsr_tc_gemm2", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
           _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
-          Ho, Wo, os_, ph, pw, act_out, CONFIG["passes"], *_tc_fmt(dtype), _p(stats, torch.float64))
+          Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], *_tc_fmt(dtype), _p(stats, torch.float64))
     return stats is not None
 
 
@@ -333,12 +368,12 @@ def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stat
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     dr, ds = _int_array([0, 0, 1, 1]), _int_array([0, 1, 0, 1])
     Ht, Wt = (Ho + 1) // 2, (Wo + 1) // 2
-    for a in (0, 1):
-        for b in (0, 1):
-            whi, wlo = _tc_weights(weight, plan, Co, phase=(a, b), pad=pad, dtype=dtype)
-            _lib.PROFILE_META = dict(macs=N * H * W * Co * Ci * R * S // 4, shape=(N, H, W, Ci, Co, R, -2))
-            filled = _tc_gemm(ahi, alo, N, Ha, Wa, plan["Ca"], whi, wlo, Co, 4, dr, ds, a, b, Ht, Wt, bias, y, Ho, Wo, 2, a, b,
-                              act_out, dtype, 1, stats)
+    if Ho % 2 or Wo % 2:
+        raise ValueError("transposed convolution phases need an even output size")
+    whi, wlo = _tc_weights_phases(weight, plan, Co, pad, dtype)
+    _lib.PROFILE_META = dict(macs=N * H * W * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, -2))
+    filled = _tc_gemm(ahi, alo, N, Ha, Wa, plan["Ca"], whi, wlo, Co, 4, dr, ds, 0, 0, Ht, Wt, bias, y, Ho, Wo, 2, 0, 0,
+                      act_out, dtype, CONFIG["split_k"] if act_out == ACT_NONE else 1, stats, nphase=4)
     if stats is not None:
         stats.filled = filled
     return y

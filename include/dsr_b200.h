@@ -133,7 +133,10 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
  *                      f16 = 0: bf16 operands (8-bit significands; hi+lo = 16 bits), f16 = 1: IEEE half operands
  *                      (11-bit; hi+lo = 22 bits, fp32-class products) with weights pre-scaled by the power of two
  *                      `wscale` at pack time and out_scale = 1/wscale applied to the accumulator;
- *                      split_k: 1 = off, -1 = auto (tiny-M layers), >1 = that many K splits (out must not alias). */
+ *                      split_k: 1 = off, -1 = auto (tiny-M layers), >1 = that many K splits (out must not alias);
+ *                      nphase: 1, or 4 = all four output phases of a stride-2 transposed conv in one launch (os = 2,
+ *                      ph = pw = 0; phase (a, b) adds (a, b) to the A offsets and to the output offsets and reads the
+ *                      weight rows [phase*Cout, (phase+1)*Cout) of W = four stacked [Cout][T*Ca] matrices). */
 #define DSR_TC_LAYOUT_NORMAL 0
 #define DSR_TC_LAYOUT_PAIR 1
 #define DSR_TC_LAYOUT_S2D 2
@@ -149,7 +152,7 @@ int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant
                        int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, int f16, float wscale, void* stream);
 int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                 int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
-                const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
                 int split_k, int f16, float out_scale, void* stream);
 
 /* second-generation GEMM (csrc/conv_tc2.cu): same contract as dsr_tc_gemm without split-K; the A operand of an 8x16-pixel
@@ -160,7 +163,7 @@ int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int C
  * cover (tap window wider than 9, outputs smaller than 128 pixels or narrower than 8). */
 int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                  int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
-                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
                  int f16, float out_scale, double* stats, void* stream);
 
 /* third-generation GEMM for Cout >= 128 (csrc/conv_tc3.cu): channel-major accumulator (M = 128 output channels,
@@ -169,7 +172,7 @@ int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int 
  * thread-local norm statistics.  Same contract as dsr_tc_gemm2; needs Ht >= 16 and Wt >= 8. */
 int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                  int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
-                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int act, int npass,
+                 const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
                  int f16, float out_scale, double* stats, void* stream);
 int dsr_tc3_set_debug(long long* counters);
 
