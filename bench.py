@@ -125,7 +125,7 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     B, H, W = wl["B"], wl["H"], wl["W"]
     opt = options.main_flags(gpu_ids=[local], batch_size=B, crop_size_h=H, crop_size_w=W, name="bench",
-                             checkpoints_dir="/tmp/dsr_bench")
+                             checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(args.graph) and world == 1)
     torch.manual_seed(0)
     model = main_model.MainModel(opt)
     model._train()
@@ -169,7 +169,7 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    timed(dev_batches, args.warmup, False)
+    timed(dev_batches, args.warmup + (model.graph_warmup + 1 if model.use_graph else 0), False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -184,7 +184,7 @@ def run_ours(args):
     if rank == 0:
         _lib.PROFILE = []
         model.set_input(dev_batches[0])
-        model.optimize_parameters(0, 1)
+        model._step_body()                    # eager launches, so every library call can be bracketed by events
         torch.cuda.synchronize()
         rec, _lib.PROFILE = _lib.PROFILE, None
         by = {}
@@ -225,6 +225,7 @@ def run_ours(args):
                     dtype=f"{args.dtype} x{args.passes} operands, f32 accumulate" if args.engine == "tc" else "f32",
                     data="synthetic",
                     config=dict(workload=wl["name"], crop=[H, W], batch_per_gpu=B, parallelism=f"dp{world}", engine=args.engine,
+                                cuda_graph=bool(model.use_graph),
                                 l2_policy="inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                                 algorithmic_tflop_per_step=flop_step / 1e12),
                     e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="pair-samples/s", h2d_bytes_per_step=h2d,
@@ -248,6 +249,7 @@ def main():
     ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="1 = replay the training step as a CUDA graph (default), 0 = eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

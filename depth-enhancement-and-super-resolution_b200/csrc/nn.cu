@@ -581,6 +581,56 @@ extern "C" int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, lon
     cvt_f64_f32_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(in, stride_in, out, n, scale, accumulate);
     return dsr_check_launch("cvt_f64_f32");
 }
+// Adam whose step count and hyper-parameters live on the device, so that the launch parameters never change and the
+// whole training step can be replayed as a CUDA graph: `tick` advances the counter, every block of the update kernel
+// derives the bias corrections from it (double precision, like torch.optim.Adam on the host).
+__global__ void adam_tick_kernel(int* step) { if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1; }
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long n, const double* __restrict__ hyper, const int* __restrict__ step,
+                                float grad_scale) {
+    __shared__ float sc[6];
+    if (threadIdx.x == 0) {
+        const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+        const int t = *step;
+        sc[0] = (float)(lr / (1.0 - pow(b1, (double)t)));
+        sc[1] = (float)b2; sc[2] = (float)(1.0 - b1); sc[3] = (float)(1.0 - b2); sc[4] = (float)eps;
+        sc[5] = (float)sqrt(1.0 - pow(b2, (double)t));
+    }
+    __syncthreads();
+    const float stepsz = sc[0], b2 = sc[1], omb1 = sc[2], omb2 = sc[3], eps = sc[4], bc2_sqrt = sc[5];
+    long n4 = n >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 P = ld4(p + 4 * i), G = ld4(g + 4 * i), M = ld4(m + 4 * i), V = ld4(v + 4 * i);
+        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gr = gg[k] * grad_scale;
+            mm[k] = mm[k] + (gr - mm[k]) * omb1;
+            vv[k] = vv[k] * b2 + gr * gr * omb2;
+            float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+            pp[k] -= stepsz * (mm[k] / denom);
+        }
+        st4(p + 4 * i, P); st4(m + 4 * i, M); st4(v + 4 * i, V);
+    }
+    if (blockIdx.x == 0) {
+        for (long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            float gr = g[i] * grad_scale;
+            float mk = m[i] + (gr - m[i]) * omb1;
+            float vk = v[i] * b2 + gr * gr * omb2;
+            m[i] = mk; v[i] = vk;
+            p[i] -= stepsz * (mk / (sqrtf(vk) / bc2_sqrt + eps));
+        }
+    }
+}
+extern "C" int dsr_adam_step_dev(float* p, const float* g, float* m, float* v, long n, const double* hyper, int* step,
+                                 float grad_scale, void* stream) {
+    DSR_REQUIRE(p && g && m && v && hyper && step && n > 0, "bad arguments");
+    DSR_REQUIRE(!((uintptr_t)p & 15) && !((uintptr_t)g & 15) && !((uintptr_t)m & 15) && !((uintptr_t)v & 15),
+                "arena pointers must be 16-byte aligned");
+    adam_tick_kernel<<<1, 32, 0, ST(stream)>>>(step);
+    adam_dev_kernel<<<dsr_grid(n / 4 + 1, TPB), TPB, 0, ST(stream)>>>(p, g, m, v, n, hyper, step, grad_scale);
+    return dsr_check_launch("adam_step_dev");
+}
 extern "C" int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2,
                              double eps, int step, float grad_scale, void* stream) {
     DSR_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad arguments");

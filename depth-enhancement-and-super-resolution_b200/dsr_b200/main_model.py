@@ -123,19 +123,38 @@ class ArenaAdam(torch.optim.Optimizer):
     def __init__(self, arena, lr):
         self.arena = arena
         super().__init__(arena.params, dict(lr=lr, betas=(0.9, 0.999), eps=1e-8))
-        self.n_steps = 0
         self.grad_scale = 1.0
+        dev = arena.flat.device
+        # the step counter and (lr, beta1, beta2, eps) live on the device: the kernel launch never changes, so the
+        # step can be replayed as a CUDA graph; the host mirrors are only for bookkeeping / LR schedulers
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.hyper_dev = torch.zeros(4, device=dev, dtype=torch.float64)
+        self._hyper_host = torch.zeros(4, dtype=torch.float64).pin_memory() if dev.type == "cuda" else torch.zeros(4, dtype=torch.float64)
+        self._hyper_key = None
+        self.sync_hyper()
+
+    @property
+    def n_steps(self):
+        return int(self.step_dev.item())
+
+    def sync_hyper(self):
+        """upload (lr, betas, eps) when a scheduler or the user changed them (host-side, outside any graph)"""
+        g = self.param_groups[0]
+        key = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]))
+        if key != self._hyper_key:
+            self._hyper_host.copy_(torch.tensor(key, dtype=torch.float64))
+            self.hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_key = key
 
     def zero_grad(self, set_to_none=False):
         self.arena.zero_grad()
 
     @torch.no_grad()
     def step(self, closure=None):
-        g = self.param_groups[0]
-        self.n_steps += 1
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyper()
         a = self.arena
-        ops.adam_step(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, g["lr"], self.n_steps, g["betas"][0], g["betas"][1],
-                      g["eps"], self.grad_scale)
+        ops.adam_step_dev(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, self.hyper_dev, self.step_dev, self.grad_scale)
         ops.WEIGHT_EPOCH += 1            # packed 16-bit copies of the trainable weights are now stale
 
 
@@ -203,6 +222,15 @@ class MainModel(BaseModel):
         self.loss_L1_real = 0
         self.arena = None
         self.grad_sync = None            # set by parallel.GradBuckets for multi-GPU runs
+        # CUDA-graph replay of the whole training step (static input / rectangle buffers, device-side Adam state)
+        self.use_graph = bool(getattr(opt, "cuda_graph", False))
+        self.graph_warmup = 2            # eager steps before the capture (fills caches, raises smem limits)
+        self._graph = None
+        self._gstream = None
+        self._eager_steps = 0
+        self._in = None                  # persistent device inputs
+        self._rect = None                # persistent pinned + device rectangle tables
+        self._rects_staged = False
         if self.isTrain:
             if self.gpu_ids:
                 self._build_arena()
@@ -216,35 +244,65 @@ class MainModel(BaseModel):
         self.optimizer_G = ArenaAdam(self.arena, self.opt.lr)
 
     # ------------------------------------------------------------------------------------------
-    def _h2d(self, t):
+    def _pinned(self, t):
         t = t if t.dtype == torch.float32 else t.float()
-        if t.device.type == "cpu" and self.device.type == "cuda":
-            if not t.is_pinned():
-                t = t.pin_memory()
-            return t.to(self.device, non_blocking=True)
-        return t.to(self.device)
+        if t.device.type == "cpu" and self.device.type == "cuda" and not t.is_pinned():
+            t = t.pin_memory()
+        return t
 
     def set_input(self, input):                                     # main_model.py:179-201
         AtoB = self.opt.direction == "AtoB"
-        self.syn_image = self._h2d(input["A_i" if AtoB else "B_i"])
-        self.real_image = self._h2d(input["B_i" if AtoB else "A_i"])
-        self.syn_depth = self._h2d(input["A_d" if AtoB else "B_d"])
-        self.real_depth = self._h2d(input["B_d" if AtoB else "A_d"])
+        src = dict(syn_image=input["A_i" if AtoB else "B_i"], real_image=input["B_i" if AtoB else "A_i"],
+                   syn_depth=input["A_d" if AtoB else "B_d"], real_depth=input["B_d" if AtoB else "A_d"])
         self.image_paths = input["A_paths" if AtoB else "B_paths"]
         self.A_paths = input["A_paths"]
         self.B_paths = input["B_paths"]
         self.K_A, self.K_B = input["K_A"], input["K_B"]
         self.crop_A, self.crop_B = input["crop_A"], input["crop_B"]
         # the fp64 K^-1 / crop table the normal kernels read (norms.py:75-89), uploaded once per batch
-        self.cam_A = camera_table(self.K_A, self.crop_A, 0.5, self.device)
-        self.cam_B = camera_table(self.K_B, self.crop_B, 0.5, self.device)
+        cams = dict(cam_A=camera_table(self.K_A, self.crop_A, 0.5), cam_B=camera_table(self.K_B, self.crop_B, 0.5))
+        shapes = {k: tuple(v.shape) for k, v in src.items()}
+        if self._in is None or self._in["shapes"] != shapes:
+            if self._graph is not None:
+                raise RuntimeError("dsr_b200: the captured CUDA graph is bound to the first batch shape; "
+                                   "call reset_graph() before changing it")
+            self._in = dict(shapes=shapes)
+            for k, v in src.items():
+                self._in[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
+            for k, v in cams.items():
+                self._in[k] = torch.empty(v.shape, device=self.device, dtype=torch.float64)
+        # persistent device tensors (same addresses every step: no allocation, graph-replay safe)
+        for k, v in src.items():
+            self._in[k].copy_(self._pinned(v), non_blocking=True)
+            setattr(self, k, self._in[k])
+        for k, v in cams.items():
+            self._in[k].copy_(v.pin_memory() if self.device.type == "cuda" else v, non_blocking=True)
+            setattr(self, k, self._in[k])
 
-    def _upload_rects(self, rects, counts):
-        r = torch.from_numpy(rects)
-        c = torch.from_numpy(counts)
-        if self.device.type == "cuda":
-            r, c = r.pin_memory(), c.pin_memory()
-        return r.to(self.device, non_blocking=True), c.to(self.device, non_blocking=True)
+    def _stage_rects(self, B, H, W, stage):
+        """host RNG in the reference's order - real loop first, then syn (main_model.py:257-298) - into persistent
+        pinned tables, then one async H2D copy each"""
+        rr, rc = draw_rects(B, H, W, stage)
+        sr, sc = draw_rects(B, H, W, stage)
+        cuda = self.device.type == "cuda"
+        if self._rect is None or self._rect["B"] != B:
+            mk = lambda shape: torch.zeros(shape, dtype=torch.int32).pin_memory() if cuda else torch.zeros(shape, dtype=torch.int32)
+            # a small ring of pinned staging tables: the host may run several steps ahead of the device (graph replay),
+            # so a slot is rewritten only after the copy that read it has completed
+            ring = [dict(host=[mk((B, MAX_RECTS, 4)), mk((B,)), mk((B, MAX_RECTS, 4)), mk((B,))],
+                         done=torch.cuda.Event() if cuda else None) for _ in range(4)]
+            self._rect = dict(B=B, ring=ring, turn=0)
+            self._rect["dev"] = [torch.zeros_like(t, device=self.device) for t in ring[0]["host"]]
+        slot = self._rect["ring"][self._rect["turn"] % 4]
+        self._rect["turn"] += 1
+        if cuda:
+            slot["done"].synchronize()
+        for h, d, a in zip(slot["host"], self._rect["dev"], (rr, rc, sr, sc)):
+            h.copy_(torch.from_numpy(a))
+            d.copy_(h, non_blocking=True)
+        if cuda:
+            slot["done"].record()
+        self._rects_staged = True
 
     def forward(self, stage="train"):                               # main_model.py:204-336
         B, _, H, W = self.real_depth.shape
@@ -260,11 +318,10 @@ class MainModel(BaseModel):
 
         if not self.opt.use_masked:
             raise NotImplementedError("dsr_b200: --use_masked is required (backward_G of the reference needs gt_mask_syn)")
-        # host RNG in the reference's order: real loop first, then syn (main_model.py:257-298)
-        rr, rc = draw_rects(B, H, W, stage)
-        sr, sc = draw_rects(B, H, W, stage)
-        rr, rc = self._upload_rects(rr, rc)
-        sr, sc = self._upload_rects(sr, sc)
+        if not self._rects_staged:          # (the graph driver stages them before replaying)
+            self._stage_rects(B, H, W, stage)
+        self._rects_staged = False
+        rr, rc, sr, sc = self._rect["dev"]
         self.gt_mask_real, self.depth_masked, self._a_r = ops.rect_holes(self.real_mask, self.real_depth, rr, rc, MAX_RECTS)
         self.gt_mask_syn, self.syn2real_depth_masked, self._a_s = ops.rect_holes(
             self.syn_mask, self.syn2real_depth, sr, sc, MAX_RECTS, extra_border=self.border)
@@ -343,7 +400,7 @@ class MainModel(BaseModel):
     def mask_real_add_holes(self):
         return (self.pred_real_depth * self._a_r).detach()
 
-    def optimize_parameters(self, iters=0, fr=1):                   # main_model.py:422-429
+    def _step_body(self):                                           # main_model.py:425-429
         self.forward()
         self.set_requires_grad([self.netG_A_d, self.netI2D_features, self.netImage2Depth], False)
         self.optimizer_G.zero_grad()
@@ -351,6 +408,56 @@ class MainModel(BaseModel):
         if self.grad_sync is not None:
             self.grad_sync.finish()
         self.optimizer_G.step()
+
+    def reset_graph(self):
+        self._graph, self._eager_steps = None, 0
+
+    def optimize_parameters(self, iters=0, fr=1):                   # main_model.py:422-429
+        """One training step.  With ``use_graph`` the first ``graph_warmup`` calls run eagerly, the next one captures
+        the whole step (forward, loss stack, backward, gradient all-reduce, Adam) into a CUDA graph, and every later
+        call only draws the rectangle tables on the host (reference RNG order) and replays it: ~800 kernel launches
+        become one."""
+        if not (self.use_graph and self.device.type == "cuda" and self.isTrain):
+            return self._step_body()
+        cur = torch.cuda.current_stream()
+        if self._graph is None:
+            # Warm-up steps and the capture run on ONE dedicated stream: the autograd engine remembers the stream every
+            # node (incl. the parameters' AccumulateGrad nodes) was built on and orders the backward pass across them
+            # with events - an event of an un-captured stream inside the capture is an error.
+            if self._gstream is None:
+                self._gstream = torch.cuda.Stream()
+            gs = self._gstream
+            gs.wait_stream(cur)
+            with torch.cuda.stream(gs):
+                if self._eager_steps < self.graph_warmup:
+                    self._eager_steps += 1
+                    self._step_body()
+                    cur.wait_stream(gs)
+                    return
+                B, _, H, W = self.real_depth.shape
+                for k, v in list(vars(self).items()):       # drop the previous step's autograd graph
+                    if torch.is_tensor(v) and v.grad_fn is not None:
+                        setattr(self, k, v.detach())
+                if self._rect is None:
+                    self._stage_rects(B, H, W, "train")
+                self._rects_staged = True                   # capture records kernels only: the host RNG must not advance
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                from . import _lib
+                l0 = _lib.LAUNCHES
+                with torch.cuda.graph(graph, stream=gs):
+                    self._step_body()
+                self._graph = graph
+                self.graph_launches = _lib.LAUNCHES - l0     # library calls recorded into the graph (= per replay)
+            cur.wait_stream(gs)
+        B, _, H, W = self.real_depth.shape
+        self.optimizer_G.sync_hyper()
+        self._stage_rects(B, H, W, "train")
+        self._rects_staged = False
+        self._graph.replay()
+        from . import _lib
+        _lib.LAUNCHES += self.graph_launches
+        ops.WEIGHT_EPOCH += 1                    # eager consumers must re-pack the trainable weights
 
     def calculate(self, stage="test"):                              # main_model.py:433-436
         self.forward(stage)

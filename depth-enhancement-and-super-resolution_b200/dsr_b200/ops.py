@@ -1173,3 +1173,9 @@ def ssim(a, b):
 
 def adam_step(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
     _call("dsr_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale)
+
+
+def adam_step_dev(p, g, m, v, hyper, step, grad_scale=1.0):
+    """Adam with device-resident step counter (int32[1], incremented here) and hyper-parameters (float64[4])."""
+    _call("dsr_adam_step_dev", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper, torch.float64), _p(step, torch.int32),
+          grad_scale)

@@ -197,6 +197,11 @@ int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int vari
 int dsr_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2, double eps,
                   int step, float grad_scale, void* stream);
 
+/* same update with the step counter (int, incremented by the call) and (lr, beta1, beta2, eps) as doubles in DEVICE memory:
+ * launch parameters never change, so the whole training step can be captured once and replayed as a CUDA graph. */
+int dsr_adam_step_dev(float* p, const float* g, float* m, float* v, long n, const double* hyper, int* step,
+                      float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

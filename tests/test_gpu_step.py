@@ -119,6 +119,42 @@ def test_step_matches_reference_golden_and_oracle(model_and_oracle):
         assert rel_l2(a, b) <= 5e-3
 
 
+def test_cuda_graph_replay_matches_eager(built_lib):
+    """One replay of the captured step (static buffers, device-side Adam state, host RNG outside the graph) against one
+    eager step FROM THE SAME STATE.  (Whole trajectories cannot be compared: fp32 atomics make two eager runs differ by
+    ~1e-5 after one Adam step, and the first Adam steps move every weight by +-lr whatever the gradient size, so that
+    noise grows several-fold per step.)"""
+    from dsr_b200 import ops
+    host = build_host_model(2, 128, 128)
+    batches = [ref_step.synthetic_batch(2, 128, 128, seed=s, depth_kind="smooth") for s in (1, 2)]
+    m = rehome(host, host.opt, [0])
+    m.use_graph = True
+    m._train()
+    np.random.seed(7)
+    for it in range(4):                                 # 2 eager warm-up steps, capture + replay, one more replay
+        m.set_input(batches[it % 2])
+        m.optimize_parameters(it, 1)
+    assert m._graph is not None and m.optimizer_G.n_steps == 4
+    state = (m.arena.flat, m.arena.exp_avg, m.arena.exp_avg_sq, m.optimizer_G.step_dev)
+    snap = [t.clone() for t in state]
+    out = []
+    for use_graph in (True, False):
+        for t, s0 in zip(state, snap):
+            t.copy_(s0)
+        ops.WEIGHT_EPOCH += 1
+        m.use_graph = use_graph
+        np.random.seed(11)
+        m.set_input(batches[0])
+        m.optimize_parameters(9, 1)
+        out.append((float(m.loss_G), m.pred_real_depth.detach().clone(), m.arena.grad.clone(), m.arena.flat.clone()))
+    (la, pa, ga, wa), (lb, pb, gb, wb) = out
+    assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
+    assert rel_l2(pa.cpu(), pb.cpu()) <= 1e-5
+    assert cosine(ga.cpu(), gb.cpu()) >= 0.99999
+    assert float((wa - wb).abs().max()) <= 2.1e-4          # at most a sign flip of a noise-level gradient: 2 * lr
+    assert m.optimizer_G.n_steps == 5
+
+
 def test_calculate_eval_mode_and_visuals(model_and_oracle):
     model, _ = model_and_oracle
     batch = ref_step.synthetic_batch(2, 128, 128, seed=2, depth_kind="noise")
