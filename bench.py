@@ -119,13 +119,14 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     _lib.load()
     ops.CONFIG.update(engine=args.engine, passes=args.passes, dtype=args.dtype)
     wl = WORKLOADS[args.workload]
     B, H, W = wl["B"], wl["H"], wl["W"]
     opt = options.main_flags(gpu_ids=[local], batch_size=B, crop_size_h=H, crop_size_w=W, name="bench",
-                             checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(args.graph) and world == 1)
+                             checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(args.graph))
     torch.manual_seed(0)
     model = main_model.MainModel(opt)
     model._train()
@@ -181,12 +182,18 @@ def run_ours(args):
 
     # per-kernel pass: CUDA events around every library call of ONE more step (same stream)
     prof = None
+    # every rank runs this extra eager step (its gradient all-reduce is a collective); rank 0 brackets each call
     if rank == 0:
         _lib.PROFILE = []
-        model.set_input(dev_batches[0])
-        model._step_body()                    # eager launches, so every library call can be bracketed by events
-        torch.cuda.synchronize()
+    model.set_input(dev_batches[0])
+    model._step_body()                        # eager launches, so every library call can be bracketed by events
+    torch.cuda.synchronize()
+    if rank == 0:
         rec, _lib.PROFILE = _lib.PROFILE, None
+        if args.layer_table:
+            rows = [dict(call=name, ms=round(a.elapsed_time(b), 4), **({"shape": list(meta["shape"]), "gmacs": round(meta["macs"] / 1e9, 3)} if meta else {}))
+                    for name, a, b, meta in rec]
+            json.dump(rows, open(args.layer_table, "w"))
         by = {}
         for name, a, b, meta in rec:
             d = by.setdefault(name, dict(ms=0.0, n=0, macs=0))
@@ -198,17 +205,29 @@ def run_ours(args):
     if rank == 0:
         pk, pk_src = peaks()
         total_ms = sum(d["ms"] for d in prof.values())
-        tc = prof.get("dsr_tc_gemm")
         top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
         mult = {1: 1, 2: 2, 3: 3}[args.passes]
-        if tc and tc["n"]:
+        gemm_calls = {k: d for k, d in prof.items() if k in ("dsr_tc_gemm", "dsr_tc_gemm2", "dsr_tc_gemm3", "dsr_tc_wgrad") and d["n"]}
+        kernel_of = dict(dsr_tc_gemm="conv_tc_kernel", dsr_tc_gemm2="conv_tc2_kernel", dsr_tc_gemm3="conv_tc3_kernel",
+                         dsr_tc_wgrad="wgrad_tc_kernel")
+        if gemm_calls:
+            dom = max(gemm_calls, key=lambda k: gemm_calls[k]["ms"])           # the dominant kernel of the step
+            tc = gemm_calls[dom]
             achieved = 2.0 * tc["macs"] / (tc["ms"] * 1e-3) / 1e12
-            roof = dict(bound="tensor", kernel="conv_tc_kernel (dsr_tc_gemm)", achieved=achieved, peak=pk["bf16_tflops_sustained"],
-                        unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk_src + " (sustained: timed inside a long step)",
+            fam_ms = sum(d["ms"] for d in gemm_calls.values())
+            fam_macs = sum(d["macs"] for d in gemm_calls.values())
+            roof = dict(bound="tensor", kernel=f"{kernel_of[dom]} ({dom})", achieved=achieved, peak=pk["bf16_tflops_sustained"],
+                        unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"], traffic=None,
+                        peak_source=pk_src + " (sustained: timed inside a long step)",
                         launches_per_step=tc["n"], avg_launch_us=1e3 * tc["ms"] / tc["n"], share_of_step=tc["ms"] / total_ms,
-                        mma_passes=mult, executed_tflops=achieved * mult,
-                        note="achieved = algorithmic conv FLOPs of the layers on the tcgen05 path / their summed launch time; "
-                             "each product is issued as `mma_passes` 16-bit MMAs (hi/lo split), so the tensor pipe executes `executed_tflops`")
+                        mma_passes=mult, executed_tflops=achieved * mult, executed_frac=achieved * mult / pk["bf16_tflops_sustained"],
+                        all_tcgen05_gemms=dict(share_of_step=fam_ms / total_ms, achieved=2.0 * fam_macs / (fam_ms * 1e-3) / 1e12,
+                                               executed_tflops=2.0 * fam_macs * mult / (fam_ms * 1e-3) / 1e12,
+                                               ms={kernel_of[k]: round(d["ms"], 3) for k, d in gemm_calls.items()}),
+                        note="achieved = algorithmic conv FLOPs of the layers this kernel served / their summed launch time (CUDA "
+                             "events on the launching stream around every library call of one eager step); each product is issued as "
+                             "`mma_passes` 16-bit MMAs (hi/lo operand split needed by the parity gates), so the tensor pipe executes "
+                             "`executed_tflops`; DRAM traffic per launch: see the ncu --set full summaries under profiles/")
         else:
             k, d = top[0]
             roof = dict(bound="hbm", kernel=k, achieved=None, peak=pk["hbm_gbs"], unit="GB/s", frac=None, traffic=None,
@@ -249,6 +268,7 @@ def main():
     ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default="", help="write every library call of one step (name, ms, shape, GMACs) to this JSON file")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the training step as a CUDA graph (default), 0 = eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -32,6 +32,12 @@ LAYERS = [  # name, kind, N, Ci, Co, k, stride, pad, pad_mode, H, W
     ("unet up convT 4x4 256->64", "convT", 12, 256, 64, 4, 2, 1, 0, 64, 64),
     ("resnet up convT 3x3 128->64", "convT", 12, 128, 64, 3, 2, 1, 1, 64, 64),
     ("gad up convT 4x4 256->128", "convT", 6, 256, 128, 4, 2, 1, 0, 64, 64),
+    ("first 7x7 3->32 reflect", "conv", 12, 3, 32, 7, 1, 3, "reflect", 256, 256),
+    ("resnet up2 convT 3x3 64->32", "convT", 12, 64, 32, 3, 2, 1, 1, 128, 128),
+    ("dgrad-like 7x7 128->32 zeros", "conv", 12, 128, 32, 7, 1, 3, "zeros", 256, 256),
+    ("gad head 7x7 64->1 replicate", "conv", 6, 64, 1, 7, 1, 3, "replicate", 256, 256),
+    ("unet head convT 4x4 128->1", "convT", 12, 128, 1, 4, 2, 1, 0, 128, 128),
+    ("down 3x3 s2 32->64 b", "conv", 12, 32, 64, 3, 2, 1, "zeros", 256, 256),
 ]
 
 
