@@ -254,7 +254,13 @@ def run_ours(args):
                     kernel_times_ms={k: round(d["ms"], 3) for k, d in top})
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroying a communicator whose collectives were captured into a live CUDA
+        # graph blocked for minutes on the B200 box; a barrier + hard exit is deterministic and torchrun sees exit code 0
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
