@@ -181,6 +181,24 @@ def run_ours(args):
     sampler.stop_flag = True
 
     # per-kernel pass: CUDA events around every library call of ONE more step (same stream)
+    if args.kernel_table and rank == 0 and world == 1:
+        # in-situ kernel durations (CUPTI through torch.profiler): warm caches and real overlap, unlike the serialised
+        # cold-cache ncu pass; used for the time breakdown only, never for the headline numbers
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            for i in range(3):
+                model.set_input(dev_batches[i % len(dev_batches)])
+                model.optimize_parameters(i, 1)
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in tp.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                d = agg.setdefault(ev.name[:90], [0, 0.0])
+                d[0] += 1; d[1] += ev.device_time
+        evs = sorted((ev for ev in tp.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        third = evs[2 * len(evs) // 3:]                                 # the launches of (about) the last step, in order
+        json.dump(dict(per_kernel=sorted(([k, v[0] / 3.0, v[1] / 3.0] for k, v in agg.items()), key=lambda r: -r[2]),
+                       last_step=[[ev.name[:60], ev.device_time] for ev in third]), open(args.kernel_table, "w"))
     prof = None
     # every rank runs this extra eager step (its gradient all-reduce is a collective); rank 0 brackets each call
     if rank == 0:
@@ -275,6 +293,7 @@ def main():
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default="", help="write every library call of one step (name, ms, shape, GMACs) to this JSON file")
+    ap.add_argument("--kernel-table", default="", help="write the in-situ per-kernel device times of 3 steps (torch.profiler / CUPTI, warm caches) to this JSON file")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the training step as a CUDA graph (default), 0 = eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -1,0 +1,183 @@
+// Single-output-channel convolutions (the depth heads): Conv2d k x k stride 1 -> 1 channel (translation_network.py:495,
+// G_A_d's 7x7 64 -> 1 + tanh) and ConvTranspose2d 4x4 stride 2 pad 1 -> 1 channel (networks.py:553, the U-Net heads
+// 128 -> 1 + tanh).  As GEMMs these have N = 1 (0.2 .. 0.4 GMAC per call, 500 / 200 us on the tensor path with a 16-wide
+// MMA of which one column is real); they are bandwidth-bound reductions over the input, so they run on CUDA cores:
+// fp32 NHWC input read once into shared memory (with the fused norm-apply + activation prologue and the padding mode
+// applied on the way in), channel-quad-major tiles so a warp's float4 reads are conflict-free, weights broadcast from
+// shared memory, bias + tanh in the epilogue.
+#include "common.cuh"
+#include "../../include/dsr_b200.h"
+
+#define ST(s) ((cudaStream_t)(s))
+#define O1_TILE 16
+#define O1_CC 16                 // channels per shared-memory chunk
+
+__device__ __forceinline__ int o1_pad_src(int i, int n, int mode) {       // index in [-(pad), n + pad) -> source or -1
+    if (i >= 0 && i < n) return i;
+    if (mode == DSR_PAD_ZERO) return -1;
+    if (mode == DSR_PAD_REFLECT) { i = i < 0 ? -i : 2 * (n - 1) - i; return (i >= 0 && i < n) ? i : -1; }
+    return i < 0 ? 0 : n - 1;
+}
+
+__device__ __forceinline__ float o1_prologue(float v, const float* __restrict__ prm, long NC, long k, int act, float slope) {
+    if (prm) v = (v - prm[k]) * prm[NC + k] + prm[2 * NC + k];
+    if (act == DSR_ACT_RELU) v = v > 0.f ? v : 0.f;
+    else if (act == DSR_ACT_LRELU) v = v > 0.f ? v : slope * v;
+    return v;
+}
+
+// stride-1 R x S convolution to one channel.  Block = 16 x 16 output pixels; per 16-channel chunk the (16+R-1)^2 input
+// patch sits in shared memory as [channel quad][y][x] float4.
+__global__ void __launch_bounds__(256)
+conv_out1_s1_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act_in,
+                    float slope, const float* __restrict__ w /* [C][R][S] */, const float* __restrict__ bias, int R, int S,
+                    int pad, int pad_mode, int act_out, float* __restrict__ out, int Ho, int Wo) {
+    extern __shared__ float4 o1_sm[];
+    const int PH = O1_TILE + R - 1, PW = O1_TILE + S - 1;
+    float4* tile = o1_sm;                                   // [4][PH][PW]
+    float4* wsm = o1_sm + 4 * PH * PW;                      // [R*S][4]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tiles_w = (Wo + O1_TILE - 1) / O1_TILE, tiles_h = (Ho + O1_TILE - 1) / O1_TILE;
+    const long NC = (long)N * C;
+    for (int t = blockIdx.x; t < N * tiles_h * tiles_w; t += gridDim.x) {
+        const int n = t / (tiles_h * tiles_w), r0 = t - n * tiles_h * tiles_w;
+        const int h0 = (r0 / tiles_w) * O1_TILE, w0 = (r0 % tiles_w) * O1_TILE;
+        float acc = 0.f;
+        for (int c0 = 0; c0 < C; c0 += O1_CC) {
+            __syncthreads();
+            for (int i = tid; i < 4 * PH * PW; i += 256) {
+                const int cq = i / (PH * PW), pq = i - cq * PH * PW;
+                const int py = pq / PW, px = pq - py * PW;
+                const int sy = o1_pad_src(h0 + py - pad, H, pad_mode), sx = o1_pad_src(w0 + px - pad, W, pad_mode);
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (sy >= 0 && sx >= 0) {
+                    const int c = c0 + cq * 4;
+                    const float* src = x + ((long)(n * H + sy) * W + sx) * C + c;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c + e < C) v[e] = o1_prologue(src[e], prm, NC, (long)n * C + c + e, act_in, slope);
+                }
+                tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            for (int i = tid; i < R * S * 4; i += 256) {
+                const int tap = i >> 2, cq = i & 3, c = c0 + cq * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? w[(long)(c + e) * R * S + tap] : 0.f;
+                wsm[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncthreads();
+            for (int r = 0; r < R; ++r)
+                for (int s = 0; s < S; ++s) {
+                    const int tap = r * S + s;
+#pragma unroll
+                    for (int cq = 0; cq < 4; ++cq) {
+                        const float4 a = tile[(cq * PH + ty + r) * PW + tx + s], b = wsm[tap * 4 + cq];
+                        acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+                    }
+                }
+        }
+        const int h = h0 + ty, ww = w0 + tx;
+        if (h < Ho && ww < Wo) {
+            float o = acc + (bias ? bias[0] : 0.f);
+            if (act_out == DSR_ACT_TANH) o = tanhf(o);
+            out[((long)n * Ho + h) * Wo + ww] = o;
+        }
+    }
+}
+
+// ConvTranspose2d 4x4 stride 2 pad 1 to one channel: each thread owns one input pixel position (h, w) and produces its four
+// output phases out[2h+a][2w+b] = sum_{dr,ds in {0,1}} sum_c x[h-1+a+dr][w-1+b+ds][c] * W[c][3-a-2dr][3-b-2ds].
+__global__ void __launch_bounds__(256)
+convT4_out1_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act_in,
+                   float slope, const float* __restrict__ w /* [C][4][4] */, const float* __restrict__ bias, int act_out,
+                   float* __restrict__ out /* N x 2H x 2W */) {
+    extern __shared__ float4 o1_sm[];
+    const int PH = O1_TILE + 2, PW = O1_TILE + 2;
+    float4* tile = o1_sm;                                   // [4][PH][PW]
+    float4* wsm = o1_sm + 4 * PH * PW;                      // [16][4]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tiles_w = (W + O1_TILE - 1) / O1_TILE, tiles_h = (H + O1_TILE - 1) / O1_TILE;
+    const long NC = (long)N * C;
+    for (int t = blockIdx.x; t < N * tiles_h * tiles_w; t += gridDim.x) {
+        const int n = t / (tiles_h * tiles_w), r0 = t - n * tiles_h * tiles_w;
+        const int h0 = (r0 / tiles_w) * O1_TILE, w0 = (r0 % tiles_w) * O1_TILE;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = 0; c0 < C; c0 += O1_CC) {
+            __syncthreads();
+            for (int i = tid; i < 4 * PH * PW; i += 256) {
+                const int cq = i / (PH * PW), pq = i - cq * PH * PW;
+                const int py = pq / PW, px = pq - py * PW;
+                const int sy = h0 + py - 1, sx = w0 + px - 1;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+                    const int c = c0 + cq * 4;
+                    const float* src = x + ((long)(n * H + sy) * W + sx) * C + c;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c + e < C) v[e] = o1_prologue(src[e], prm, NC, (long)n * C + c + e, act_in, slope);
+                }
+                tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            for (int i = tid; i < 64; i += 256) {
+                const int tap = i >> 2, cq = i & 3, c = c0 + cq * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? w[(long)(c + e) * 16 + tap] : 0.f;
+                wsm[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+                        for (int ds = 0; ds < 2; ++ds) {
+                            const int tap = (3 - a - 2 * dr) * 4 + (3 - b - 2 * ds);
+#pragma unroll
+                            for (int cq = 0; cq < 4; ++cq) {
+                                const float4 xv = tile[(cq * PH + ty + a + dr) * PW + tx + b + ds], wv = wsm[tap * 4 + cq];
+                                acc[a * 2 + b] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+                            }
+                        }
+        }
+        const int h = h0 + ty, ww = w0 + tx;
+        if (h < H && ww < W) {
+            const float bv = bias ? bias[0] : 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float o = acc[a * 2 + b] + bv;
+                    if (act_out == DSR_ACT_TANH) o = tanhf(o);
+                    out[((long)n * 2 * H + 2 * h + a) * 2 * W + 2 * ww + b] = o;
+                }
+        }
+    }
+}
+
+extern "C" int dsr_conv_out1(const float* x, int N, int H, int W, int C, const float* prm, int act_in, float slope,
+                             const float* w, const float* bias, int R, int S, int pad, int pad_mode, int transposed,
+                             int act_out, float* out, void* stream) {
+    DSR_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
+    DSR_REQUIRE((long)N * H * W < (1L << 31) / 4, "tensor too large for 32-bit pixel indices");
+    if (transposed) {
+        DSR_REQUIRE(R == 4 && S == 4 && pad == 1, "transposed variant: 4x4, stride 2, padding 1");
+        const int tiles = N * dsr_cdiv(H, O1_TILE) * dsr_cdiv(W, O1_TILE);
+        const size_t smem = (4 * (O1_TILE + 2) * (O1_TILE + 2) + 64) * sizeof(float4);
+        const int cap = dsr_num_sms() * 4;
+        convT4_out1_kernel<<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias, act_out, out);
+        return dsr_check_launch("conv_out1 (transposed)");
+    }
+    DSR_REQUIRE(R >= 1 && S >= 1 && R <= 9 && S <= 9 && pad >= 0, "kernel size 1..9");
+    DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
+    const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+    const int tiles = N * dsr_cdiv(Ho, O1_TILE) * dsr_cdiv(Wo, O1_TILE);
+    const size_t smem = (4 * (O1_TILE + R - 1) * (O1_TILE + S - 1) + R * S * 4) * sizeof(float4);
+    const int cap = dsr_num_sms() * 4;
+    conv_out1_s1_kernel<<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias, R, S, pad,
+                                                                           pad_mode, act_out, out, Ho, Wo);
+    return dsr_check_launch("conv_out1");
+}

@@ -527,27 +527,35 @@ __device__ __forceinline__ void tc_map_k(int variant, int t, int q, int R, int S
     else if (variant == DSR_TC_W_CONV_DGRAD) { r = R - 1 - t / S; s = S - 1 - (t - (t / S) * S); c = q; }
     else { c = q; r = pad + 2 - pa - 2 * (t >> 1); s = pad + 2 - pb - 2 * (t & 1); }
 }
-__global__ void tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S, int variant, int Cp,
-                                      int pa, int pb, int pad, int Cout, int T, int Ca,
-                                      unsigned short* __restrict__ Whi, unsigned short* __restrict__ Wlo, int f16,
-                                      float wscale) {
-    const long K = (long)T * Ca, total = (long)Cout * K;
+// one thread = 8 consecutive K positions of one output row (same tap, 8 consecutive arranged channels): eight gathered
+// 4-byte loads (the parameter is small and L2-resident) and one 16-byte store per plane
+__global__ void __launch_bounds__(256)
+tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S, int variant, int Cp,
+                      int pa, int pb, int pad, int Cout, int T, int Ca,
+                      unsigned short* __restrict__ Whi, unsigned short* __restrict__ Wlo, int f16, float wscale) {
+    const int Ca8 = Ca >> 3;
+    const long total = (long)Cout * T * Ca8;
+    const bool convT = (variant == DSR_TC_W_CONVT_PH) || (variant == DSR_TC_W_CONV_DGRAD);
+    const int Cin = convT ? D0 : D1;
+    const int g = Ca / Cp;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int co = (int)(idx / K);
-        const long k = idx - (long)co * K;
-        const int t = (int)(k / Ca), q = (int)(k - (long)t * Ca);
-        int r, s, c;
-        tc_map_k(variant, t, q, R, S, Cp, Ca / Cp, pa, pb, pad, r, s, c);
-        float v = 0.f;
-        // convT-style indexing: the GEMM's K channel is the parameter's dim 0, its output channel dim 1
-        const bool convT = (variant == DSR_TC_W_CONVT_PH) || (variant == DSR_TC_W_CONV_DGRAD);
-        const int Cin = convT ? D0 : D1;
-        if (r >= 0 && r < R && s >= 0 && s < S && c >= 0 && c < Cin)
-            v = convT ? w[(((long)c * D1 + co) * R + r) * S + s] : w[(((long)co * D1 + c) * R + r) * S + s];
-        unsigned short h, l;
-        split16(v * wscale, f16, h, l);
-        Whi[idx] = h;
-        if (Wlo) Wlo[idx] = l;
+        const int q8 = (int)(idx % Ca8);
+        const long u = idx / Ca8;
+        const int t = (int)(u % T), co = (int)(u / T);
+        __align__(16) unsigned short hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int r, sx, c;
+            tc_map_k(variant, t, q8 * 8 + e, R, S, Cp, g, pa, pb, pad, r, sx, c);
+            float v = 0.f;
+            // convT-style indexing: the GEMM's K channel is the parameter's dim 0, its output channel dim 1
+            if (r >= 0 && r < R && sx >= 0 && sx < S && c >= 0 && c < Cin)
+                v = convT ? w[(((long)c * D1 + co) * R + r) * S + sx] : w[(((long)co * D1 + c) * R + r) * S + sx];
+            split16(v * wscale, f16, hi[e], lo[e]);
+        }
+        const long o = ((long)co * T + t) * Ca + q8 * 8;
+        *reinterpret_cast<uint4*>(Whi + o) = *reinterpret_cast<const uint4*>(hi);
+        if (Wlo) *reinterpret_cast<uint4*>(Wlo + o) = *reinterpret_cast<const uint4*>(lo);
     }
 }
 // packed weight gradient [D0][T*Ca] (row = parameter dim 0, K channel = parameter dim 1) -> parameter layout
@@ -605,7 +613,8 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
                            int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
                            double* csum, void* stream) {
     DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
-    DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
+    DSR_REQUIRE(((Ca & 63) == 0 || (Ca == 8 && layout == DSR_TC_LAYOUT_NORMAL)) && (Cp & 7) == 0 && Cp >= C,
+                "Ca must be a multiple of 64 (or 8 for the compact first-layer operand) and Cp a multiple of 8 >= C");
     DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
     DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_PAIR && Ca % Cp == 0 && Ca >= 2 * Cp) ||
                     (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
@@ -626,7 +635,8 @@ extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, 
                                   int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, int f16, float wscale,
                                   void* stream) {
     DSR_REQUIRE(w && W_hi && T > 0 && (Ca & 63) == 0, "bad arguments");
-    long total = (long)Cout * T * Ca;
+    DSR_REQUIRE(!((uintptr_t)W_hi & 15) && !((uintptr_t)W_lo & 15), "packed weight buffers must be 16-byte aligned");
+    long total = (long)Cout * T * (Ca / 8);
     tc_pack_weight_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(w, D0, D1, R, S, variant, Cp, phase_a, phase_b, pad, Cout, T,
                                                                        Ca, (unsigned short*)W_hi, (unsigned short*)W_lo, f16, wscale);
     return dsr_check_launch("tc_pack_weight");

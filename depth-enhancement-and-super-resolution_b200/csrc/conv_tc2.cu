@@ -26,6 +26,10 @@ struct Tc2Params {
     int Ca, T, cblocks;
     int ah, aw, Hp, PW;       // patch = Hp rows x PW pixels x 128 B (PW = 8 + widest tap offset)
     int Ho, Wo, Cout, os, ph, pw;
+    int a_mode;               // 1: compact first-layer operand - A is [pixels][8 channels] (16-byte pixel rows, NO swizzle); the
+                              // K block of a kernel row = 8 horizontally adjacent pixels x 8 channels = 128 contiguous bytes
+                              // starting at the tap's pixel, i.e. MMA row i starts 16 B after row i-1 (overlapping rows:
+                              // no-swizzle K-major descriptor with LBO = 16 B, SBO = patch row pitch)
     int nphase, tiles_per_phase;  // 4 output phases of a stride-2 transposed conv in one launch (see conv_tc.cu)
     int act, f16, base_off_mode;
     float out_scale;
@@ -160,7 +164,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         // ===== MMA issuer: the whole warp runs the (warp-uniform) loop and the waits; one elected lane issues =====
         {
             const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
-            const uint64_t pdesc0 = make_sdesc_ex(0, (uint32_t)p.PW * 128u, 0);   // stride between the 8-pixel row groups
+            // A descriptor template: SWIZZLE_128B rows of 128 B (stride between the 8-pixel row groups = patch pitch), or
+            // for the compact first-layer operand no swizzle, 16-byte rows, LBO = 16 B, SBO = patch pitch
+            const uint32_t pix_bytes = p.a_mode ? 16u : 128u;
+            const uint64_t pdesc0 = p.a_mode
+                ? ((uint64_t)1 << 16) | ((uint64_t)(((uint32_t)p.PW * 16u) >> 4) << 32) | ((uint64_t)1 << 46)
+                : make_sdesc_ex(0, (uint32_t)p.PW * 128u, 0);
             const uint64_t wdesc0 = make_sdesc(0);
             int pi = 0, wi = 0, ti = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
@@ -177,7 +186,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                         TC2_TIMED_WAIT(1, wf(s), (wi / p.n_ws) & 1);
                         if (elect_one()) {
                             const uint32_t w_hi = w_base + s * w_stage;
-                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 128u;
+                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * pix_bytes;
                             const uint64_t boff = p.base_off_mode ? ((uint64_t)(p.ds[t] & 7) << 49) : 0ull;
                             const uint64_t pd_hi = (pdesc0 | boff) + (uint64_t)(((patch_hi + shift) & 0x3FFFF) >> 4);
                             const uint64_t pd_lo = (pdesc0 | boff) + (uint64_t)(((patch_lo + shift) & 0x3FFFF) >> 4);
@@ -379,11 +388,12 @@ static int tc2_env(const char* name, int dflt) {
 extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                             int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
                             const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
-                            int f16, float out_scale, double* stats, void* stream) {
+                            int f16, float out_scale, double* stats, int a_mode, void* stream) {
     DSR_REQUIRE(nphase == 1 || (nphase == 4 && os == 2 && ph == 0 && pw == 0), "phases: 1, or 4 with output stride 2");
     DSR_REQUIRE(A_hi && W_hi && out && tap_dr && tap_ds, "null pointer");
+    DSR_REQUIRE(a_mode == 0 || (a_mode == 1 && Ca == 8), "compact operand mode needs an 8-channel arranged tensor");
     DSR_REQUIRE(npass >= 1 && npass <= 3 && (npass < 2 || A_lo) && (npass < 3 || W_lo), "bad precision mode");
-    DSR_REQUIRE(T >= 1 && T <= TC2_MAX_TAPS && (Ca & 63) == 0 && Cout >= 1, "bad GEMM shape");
+    DSR_REQUIRE(T >= 1 && T <= TC2_MAX_TAPS && ((Ca & 63) == 0 || a_mode == 1) && Cout >= 1, "bad GEMM shape");
     DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)W_hi & 15) && !((uintptr_t)out & 15), "buffers must be 16-byte aligned");
     DSR_REQUIRE(!stats || act == DSR_ACT_NONE, "statistics are taken before any activation");
     Tc2Params p;
@@ -401,7 +411,8 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : (Cout > 16 ? 32 : 16)));
     if (stats && bn < 32) bn = 32;
     bn = tc2_env("DSR_TC2_BN", bn);
-    p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.cblocks = Ca / 64;
+    const int Kt = a_mode ? 64 : Ca;          // K elements per tap in the weight matrix
+    p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Kt; p.T = T; p.cblocks = a_mode ? 1 : Ca / 64; p.a_mode = a_mode;
     p.ah = a_off_h; p.aw = a_off_w; p.Hp = TC2_TH + max_dr;
     p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.os = os; p.ph = ph; p.pw = pw; p.act = act;
     p.f16 = f16; p.out_scale = out_scale;
@@ -410,8 +421,8 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     p.tiles_w = dsr_cdiv(Wt, TC2_TW); p.tiles_h = dsr_cdiv(Ht, TC2_TH); p.tiles_co = dsr_cdiv(Cout, bn);
     p.nphase = nphase; p.tiles_per_phase = p.tiles_w * p.tiles_h * p.tiles_co * N;
     p.total_tiles = p.tiles_per_phase * nphase;
-    p.PW = tc2_env("DSR_TC2_PW", TC2_TW + max_ds);
-    p.patch_tx_bytes = (unsigned)p.Hp * p.PW * 128u;
+    p.PW = tc2_env("DSR_TC2_PW", TC2_TW + max_ds + (a_mode ? 7 : 0));    // compact rows reach 7 pixels further right
+    p.patch_tx_bytes = (unsigned)p.Hp * p.PW * (a_mode ? 16u : 128u);
     p.patch_plane_bytes = (p.patch_tx_bytes + 1023u) & ~1023u;
     const int na = npass >= 2 ? 2 : 1, nw = npass >= 3 ? 2 : 1;
     const long patch_set = (long)na * p.patch_plane_bytes, w_stage = (long)nw * bn * 128;
@@ -430,13 +441,14 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     CUtensorMap mah, mal, mwh, mwl;
     cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
     cuuint64_t astr[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)Wa * Ca * 2, (cuuint64_t)Ha * Wa * Ca * 2};
-    cuuint32_t abox[4] = {64, (cuuint32_t)p.PW, (cuuint32_t)p.Hp, 1};
-    int rc = encode_map(&mah, A_hi, 4, adims, astr, abox);
+    cuuint32_t abox[4] = {(cuuint32_t)(a_mode ? 8 : 64), (cuuint32_t)p.PW, (cuuint32_t)p.Hp, 1};
+    const CUtensorMapSwizzle aswz = a_mode ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
+    int rc = encode_map(&mah, A_hi, 4, adims, astr, abox, aswz);
     if (rc) return rc;
     mal = mah;
-    if (npass >= 2 && (rc = encode_map(&mal, A_lo, 4, adims, astr, abox))) return rc;
-    cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout * nphase};
-    cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
+    if (npass >= 2 && (rc = encode_map(&mal, A_lo, 4, adims, astr, abox, aswz))) return rc;
+    cuuint64_t wdims[2] = {(cuuint64_t)T * Kt, (cuuint64_t)Cout * nphase};
+    cuuint64_t wstr[1] = {(cuuint64_t)T * Kt * 2};
     cuuint32_t wbox[2] = {64, (cuuint32_t)bn};
     if ((rc = encode_map(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;
     mwl = mwh;

@@ -113,6 +113,32 @@ __global__ void pad2d_bwd_kernel(const float* __restrict__ gy, float* __restrict
     }
 }
 
+// float4 version: one thread = 4 channels of one source pixel; interior pixels have exactly one reader
+__global__ void __launch_bounds__(256)
+pad2d_bwd_vec4_kernel(const float4* __restrict__ gy, float4* __restrict__ gx, int N, int H, int W, int C4, int p, int mode) {
+    const int Hp = H + 2 * p, Wp = W + 2 * p;
+    const int total = N * H * W * C4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = idx % C4; int t = idx / C4;
+        const int j = t % W; t /= W;
+        const int i = t % H; const int n = t / H;
+        float4 acc;
+        if (i > p && i < H - 1 - p && j > p && j < W - 1 - p) {
+            acc = gy[((long)(n * Hp + i + p) * Wp + j + p) * C4 + c];
+        } else {
+            int qh[16], qw[16];
+            const int nh = pad_readers(i, p, H, mode, qh), nw = pad_readers(j, p, W, mode, qw);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int a = 0; a < nh; ++a)
+                for (int b = 0; b < nw; ++b) {
+                    const float4 v = gy[((long)(n * Hp + qh[a]) * Wp + qw[b]) * C4 + c];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+        }
+        gx[idx] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // activations
 // ------------------------------------------------------------------------------------------
@@ -479,7 +505,11 @@ extern "C" int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int 
 }
 extern "C" int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream) {
     DSR_REQUIRE(gy && gx && pad >= 0 && pad <= 7, "bad arguments");
-    pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode);
+    if (!(C & 3) && !((uintptr_t)gy & 15) && !((uintptr_t)gx & 15) && (long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 4) < (1L << 31))
+        pad2d_bwd_vec4_kernel<<<dsr_grid((long)N * H * W * (C / 4), 256), 256, 0, ST(stream)>>>((const float4*)gy, (float4*)gx, N, H, W,
+                                                                                               C / 4, pad, mode);
+    else
+        pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode);
     return dsr_check_launch("pad2d_bwd");
 }
 extern "C" int dsr_act_fwd(const float* x, float* y, long n, int kind, float slope, void* stream) {

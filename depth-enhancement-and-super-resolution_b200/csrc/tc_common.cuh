@@ -116,12 +116,12 @@ static inline PFN_encodeTiled get_encode() {
     return fn;
 }
 static inline int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { dsr_set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DSR_ERR_CUDA; }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dsr_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return DSR_ERR_CUDA; }
     return DSR_OK;

@@ -401,6 +401,8 @@ class MainModel(BaseModel):
         return (self.pred_real_depth * self._a_r).detach()
 
     def _step_body(self):                                           # main_model.py:425-429
+        if self.device.type == "cuda":
+            ops.zero_pool_reset(self.device)       # one memset for every accumulator of the step
         self.forward()
         self.set_requires_grad([self.netG_A_d, self.netI2D_features, self.netImage2Depth], False)
         self.optimizer_G.zero_grad()

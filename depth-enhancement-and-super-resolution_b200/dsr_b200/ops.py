@@ -76,8 +76,48 @@ def planes(x):
     return x.contiguous()
 
 
+class _ZeroPool:
+    """Pre-zeroed fp64 scratch for the step's accumulators (norm statistics, IN-backward sums, bias-gradient sums,
+    loss reductions): ~200 tiny buffers per step come out of one arena that is cleared by ONE memset per step
+    (``zero_pool_reset``, called by the model at the top of the step) instead of ~200 fill kernels."""
+    CAP = 1 << 22            # doubles (32 MB)
+
+    def __init__(self):
+        self.buf, self.used, self.high = {}, {}, {}
+
+    def take(self, n, device):
+        key = (device.type, device.index)
+        if key not in self.buf:
+            return torch.zeros(n, device=device, dtype=torch.float64)       # pool not armed on this device
+        n8 = (n + 7) // 8 * 8
+        u = self.used[key]
+        if u + n8 > self.CAP:
+            return torch.zeros(n, device=device, dtype=torch.float64)
+        self.used[key] = u + n8
+        return self.buf[key][u:u + n]
+
+    def reset(self, device):
+        key = (device.type, device.index)
+        if key not in self.buf:
+            self.buf[key] = torch.zeros(self.CAP, device=device, dtype=torch.float64)
+            self.used[key] = 0
+            return
+        u = self.used[key]
+        if u:
+            self.buf[key][:u].zero_()
+        self.used[key] = 0
+
+
+_ZERO_POOL = _ZeroPool()
+
+
+def zero_pool_reset(device):
+    """call once at the top of a step: re-zeroes what the previous step handed out"""
+    _ZERO_POOL.reset(torch.device(device))
+
+
 def _zeros_f64(n, device):
-    return torch.zeros(n, device=device, dtype=torch.float64)
+    return _ZERO_POOL.take(n, torch.device(device))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -151,7 +191,9 @@ CONFIG = {
     "tc_halo": True,     # second-generation GEMM (halo-resident A patches, persistent CTAs) wherever it applies
     "tc_cm": True,       # third-generation channel-major GEMM for Cout >= 128 layers
     "reuse_fwd_operand": True,  # wgrad reads the forward pass's arranged operand (when formats match) instead of re-preparing x
-    "tc_first_layers": True,   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
+    "out1": True,        # one-output-channel heads on CUDA cores (bandwidth-bound reductions) instead of N = 16 MMAs
+    "tc_first_layers": True,
+    "tc_compact_first": True,   # ... reading the 8-pixel K blocks from a compact 8-channel operand (no 8x expansion)   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
     "halo_min_tiles": 120,
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
@@ -181,8 +223,13 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W, min_ci=16):
     if CONFIG["engine"] != "tc" or R != S:
         return None
     if kind == "conv" and stride == 1 and Ci <= 8 and R >= 5 and CONFIG["tc_first_layers"]:
-        # 1..8-channel first layers: 8 horizontally adjacent pixels x 8 channels form one 64-wide K block per kernel row
-        return dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=8, Ca=64, T=R * ((S + 7) // 8))
+        # 1..8-channel first layers: 8 horizontally adjacent pixels x 8 channels form one 64-wide K block per kernel row.
+        # "compact": the forward GEMM reads that block straight out of an 8-channel arranged tensor (16-byte pixel rows,
+        # overlapping MMA rows) instead of an 8x expanded copy; the expanded PAIR form still serves the weight gradient.
+        plan = dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=8, Ca=64, T=R * ((S + 7) // 8))
+        if S <= 8 and CONFIG["tc_compact_first"]:
+            plan["compact"] = True
+        return plan
     if kind == "conv" and stride == 1 and R * S <= 64 and Ci >= 32:
         if Ci == 32:
             return dict(layout=_LAYOUT_PAIR, variant=_W_CONV_PAIR, Cp=32, Ca=64, T=R * ((S + 1) // 2))
@@ -323,17 +370,18 @@ def _tc_kernel_for(N, Ht, Wt, Co, ds, nphase=1):
 
 
 def _tc_gemm(ahi, alo, N, Ha, Wa, Ca, whi, wlo, Co, T, dr, ds, aoh, aow, Ht, Wt, bias, y, Ho, Wo, os_, ph, pw, act_out,
-             dtype, split_k, stats=None, nphase=1):
+             dtype, split_k, stats=None, nphase=1, a_mode=0):
     """one GEMM launch on the best kernel for the shape; returns True when `stats` was filled by the epilogue"""
-    which = CONFIG.get("force_kernel") or _tc_kernel_for(N, Ht, Wt, Co, list(ds), nphase)
+    which = 2 if a_mode else (CONFIG.get("force_kernel") or _tc_kernel_for(N, Ht, Wt, Co, list(ds), nphase))
     if which == 1:
         _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
               _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
               Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], split_k, *_tc_fmt(dtype))
         return False
+    extra = (a_mode,) if which == 2 else ()
     _call("dsr_tc_gemm3" if which == 3 else "dsr_tc_gemm2", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
           _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
-          Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], *_tc_fmt(dtype), _p(stats, torch.float64))
+          Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], *_tc_fmt(dtype), _p(stats, torch.float64), *extra)
     return stats is not None
 
 
@@ -346,13 +394,16 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
     R, S = weight.shape[2], weight.shape[3]
     if Co is None:
         Co = weight.shape[0]
-    ahi, alo, Ha, Wa = _tc_prep(xh, plan, pad, pad_mode, dtype=dtype)
     whi, wlo = _tc_weights(weight, plan, Co, dtype=dtype)
     dr, ds = _tc_taps(plan, R, S)
+    a_mode, a_plan = 0, plan
+    if plan.get("compact") and Ho * Wo >= 128 and Wo >= 8:
+        a_mode, a_plan = 1, dict(layout=_LAYOUT_NORMAL, Cp=8, Ca=8)       # 8-channel operand, same weights / taps
+    ahi, alo, Ha, Wa = _tc_prep(xh, a_plan, pad, pad_mode, dtype=dtype)
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     _lib.PROFILE_META = dict(macs=macs if macs is not None else N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
-    filled = _tc_gemm(ahi, alo, N, Ha, Wa, plan["Ca"], whi, wlo, Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0, Ho, Wo,
-                      bias, y, Ho, Wo, 1, 0, 0, act_out, dtype, CONFIG["split_k"], stats)
+    filled = _tc_gemm(ahi, alo, N, Ha, Wa, a_plan["Ca"], whi, wlo, Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0, Ho, Wo,
+                      bias, y, Ho, Wo, 1, 0, 0, act_out, dtype, CONFIG["split_k"], stats, a_mode=a_mode)
     if stats is not None:
         stats.filled = filled
     return y
@@ -554,7 +605,13 @@ class _Conv2d(Function):
                 raise RuntimeError("internal error: a fused prologue needs the tcgen05 path (see conv_fusable)")
             prm = pro.params(xh)
         ctx.xP = None
-        if plan is not None:
+        if Co == 1 and stride == 1 and R <= 9 and S <= 9 and CONFIG["out1"] and (pro is None or plan is not None):
+            # depth head: a bandwidth-bound reduction, on CUDA cores straight from the fp32 activation (csrc/conv_out1.cu)
+            y = torch.empty((N, Ho, Wo, 1), device=x.device, dtype=torch.float32)
+            w = weight.detach()
+            _call("dsr_conv_out1", _p(xh), N, H, W, Ci, _p(prm), pro.act if pro else ACT_NONE, pro.slope if pro else 0.0,
+                  _p(w if w.is_contiguous() else w.contiguous()), _p(b), R, S, pad, pad_mode, 0, act_out, _p(y))
+        elif plan is not None:
             xin = _Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
             y = _tc_conv_fwd(xin, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, stats=stats)
             if CONFIG["reuse_fwd_operand"] and ctx.needs_input_grad[1]:
@@ -661,7 +718,13 @@ class _ConvTranspose2d(Function):
                 raise RuntimeError("internal error: a fused prologue needs the tcgen05 path (see conv_fusable)")
             prm = pro.params(xh)
         ctx.xP = None
-        if plan is not None:
+        if Co == 1 and R == 4 and S == 4 and stride == 2 and pad == 1 and opad == 0 and CONFIG["out1"] and \
+                (pro is None or plan is not None):
+            y = torch.empty((N, Ho, Wo, 1), device=x.device, dtype=torch.float32)
+            w = weight.detach()
+            _call("dsr_conv_out1", _p(xh), N, H, W, Ci, _p(prm), pro.act if pro else ACT_NONE, pro.slope if pro else 0.0,
+                  _p(w if w.is_contiguous() else w.contiguous()), _p(b), 4, 4, 1, PAD_ZERO, 1, act_out, _p(y))
+        elif plan is not None:
             xin = _Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
             y = _tc_convT_fwd(xin, weight, b, plan, pad, act_out, Ho, Wo, stats=stats)
             if CONFIG["reuse_fwd_operand"] and ctx.needs_input_grad[1]:
@@ -1105,7 +1168,7 @@ def masked_l1_l2(a, b, m1, m2=None):
 def masked_sums(d, p, m):
     """-> float64[3] = (sum d*m, sum p*m, sum |d*m - p*m|).  main_model.py:308-318."""
     d, p, m = planes(d.detach()), planes(p.detach()), planes(m)
-    out = _zeros_f64(3, d.device)
+    out = torch.zeros(3, device=d.device, dtype=torch.float64)      # read lazily by the caller: not from the per-step pool
     _call("dsr_masked_sums", _p(d), _p(p), _p(m), d.numel(), _p(out, torch.float64))
     return out
 

@@ -120,6 +120,14 @@ int dsr_conv_simt(const float* G, const float* Wk, const float* bias, float* out
 int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, int Wg, int Cg, int Ho, int Wo, int Cd,
                    int R, int S, int stride, int pad, void* stream);
 
+/* one-output-channel heads on CUDA cores (csrc/conv_out1.cu): Conv2d R x S stride 1 (w = [1][C][R][S]) or, with
+ * transposed = 1, ConvTranspose2d 4x4 stride 2 padding 1 (w = [C][1][4][4]); fp32 NHWC input read once through shared
+ * memory with the fused (mean, scale, shift) + ReLU / LeakyReLU prologue and the padding mode; bias + optional tanh.
+ * models/translation_network.py:495 (64 -> 1, 7x7), models/networks.py:553 (128 -> 1).  out = N x Ho x Wo (x 1). */
+int dsr_conv_out1(const float* x, int N, int H, int W, int C, const float* prm, int act_in, float slope,
+                  const float* w, const float* bias, int R, int S, int pad, int pad_mode, int transposed,
+                  int act_out, float* out, void* stream);
+
 /* tcgen05 / TMEM / TMA implicit GEMM (csrc/conv_tc.cu).  Three calls per convolution:
  *   dsr_tc_prep        fp32 NHWC activation -> arranged bf16 hi(+lo) operand [N][Ha][Wa][Ca]; fuses the preceding
  *                      norm-apply (prm = (mean, scale, shift) or NULL), ReLU / LeakyReLU, and the padding
@@ -164,7 +172,10 @@ int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int C
 int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
                  int Cout, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Ht, int Wt,
                  const float* bias, float* out, int Ho, int Wo, int os, int ph, int pw, int nphase, int act, int npass,
-                 int f16, float out_scale, double* stats, void* stream);
+                 int f16, float out_scale, double* stats, int a_mode, void* stream);
+/* a_mode 1 = compact first-layer operand: A is an 8-channel arranged tensor (Ca = 8, zero-padded channels, made by
+ * dsr_tc_prep with layout NORMAL); one tap per kernel row, its K block = 8 adjacent pixels x 8 channels read straight
+ * from the 16-byte pixel rows (no 8x expansion in memory); W rows hold 64 K values per tap (variant CONV_PAIR, Cp = 8). */
 
 /* third-generation GEMM for Cout >= 128 (csrc/conv_tc3.cu): channel-major accumulator (M = 128 output channels,
  * N = 8 x TH <= 256 pixels per MMA, the shape that runs at the tensor floor with both operands in shared memory),

@@ -14,7 +14,7 @@ rc1=$?; tail -3 $out/gpu_ops_$tag.log
 timeout 900 python -m pytest tests/test_gpu_step.py -m gpu -q -x --timeout 600 > $out/gpu_step_$tag.log 2>&1
 rc2=$?; tail -3 $out/gpu_step_$tag.log
 if [ $rc1 -ne 0 ] || [ $rc2 -ne 0 ]; then echo "tests failed ($rc1,$rc2): skipping bench/ncu"; exit 1; fi
-timeout 900 python bench.py --steps 10 --warmup 3 --layer-table $out/layers_step_$tag.json > $out/bench_$tag.json 2> $out/bench_$tag.err || { tail -5 $out/bench_$tag.err; exit 2; }
+timeout 900 python bench.py --steps 10 --warmup 3 --layer-table $out/layers_step_$tag.json --kernel-table $out/kernels_step_$tag.json > $out/bench_$tag.json 2> $out/bench_$tag.err || { tail -5 $out/bench_$tag.err; exit 2; }
 tail -1 $out/bench_$tag.json | cut -c1-400
 if [ "${NCU:-1}" = "1" ]; then
   # eager launches under ncu (a graph replay would hide the library-call boundaries): 3 warm-up + 2 timed + 2 e2e + 1 profile steps
