@@ -64,6 +64,21 @@ class ClockSampler(threading.Thread):
                     samples=len(self.samples))
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the newest committed `ncu --set full` summary under profiles/
+    (scripts/ncu_summary.py traffic ...); None when no capture is committed."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*traffic*.json")), reverse=True):
+        try:
+            d = json.load(open(path)).get(kernel)
+        except Exception:
+            d = None
+        if d:
+            return dict(bytes_per_launch=d["dram_bytes_per_launch"], captured_launches=d["captured_launches"],
+                        source=os.path.relpath(path, ROOT))
+    return None
+
+
 def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None):
     """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
     import numpy as np
@@ -234,8 +249,10 @@ def run_ours(args):
             achieved = 2.0 * tc["macs"] / (tc["ms"] * 1e-3) / 1e12
             fam_ms = sum(d["ms"] for d in gemm_calls.values())
             fam_macs = sum(d["macs"] for d in gemm_calls.values())
+            tr = ncu_traffic(kernel_of[dom])
             roof = dict(bound="tensor", kernel=f"{kernel_of[dom]} ({dom})", achieved=achieved, peak=pk["bf16_tflops_sustained"],
-                        unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"], traffic=None,
+                        unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"],
+                        traffic=tr["bytes_per_launch"] if tr else None, traffic_source=tr,
                         peak_source=pk_src + " (sustained: timed inside a long step)",
                         launches_per_step=tc["n"], avg_launch_us=1e3 * tc["ms"] / tc["n"], share_of_step=tc["ms"] / total_ms,
                         mma_passes=mult, executed_tflops=achieved * mult, executed_frac=achieved * mult / pk["bf16_tflops_sustained"],
@@ -245,7 +262,8 @@ def run_ours(args):
                         note="achieved = algorithmic conv FLOPs of the layers this kernel served / their summed launch time (CUDA "
                              "events on the launching stream around every library call of one eager step); each product is issued as "
                              "`mma_passes` 16-bit MMAs (hi/lo operand split needed by the parity gates), so the tensor pipe executes "
-                             "`executed_tflops`; DRAM traffic per launch: see the ncu --set full summaries under profiles/")
+                             "`executed_tflops`; traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the launches "
+                             "captured by ncu --set full (profiles/, a previous run of the same command on the same workload)")
         else:
             k, d = top[0]
             roof = dict(bound="hbm", kernel=k, achieved=None, peak=pk["hbm_gbs"], unit="GB/s", frac=None, traffic=None,

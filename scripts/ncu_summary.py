@@ -56,5 +56,33 @@ def full(path, out):
             f.write("\n")
 
 
+def traffic(out, *paths):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel in the given --set full
+    captures -> JSON that bench.py reads for `roofline.traffic`"""
+    import json
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tmult = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    res = {}
+    for path in paths:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        idx = {h: i for i, h in enumerate(hdr)}
+        for r in data:
+            name = re.sub(r"<.*", "", short(r[idx["Kernel Name"]]))
+            rd = float(r[idx["dram__bytes_read.sum"]]) * mult[units[idx["dram__bytes_read.sum"]]]
+            wr = float(r[idx["dram__bytes_write.sum"]]) * mult[units[idx["dram__bytes_write.sum"]]]
+            us = float(r[idx["gpu__time_duration.sum"]]) * tmult[units[idx["gpu__time_duration.sum"]]]
+            tp = float(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])
+            res.setdefault(name, []).append(dict(kernel=short(r[idx["Kernel Name"]]), grid=r[idx["Grid Size"]], dram_read_bytes=rd,
+                                                 dram_write_bytes=wr, time_us=us, tensor_pipe_active_pct=tp))
+    summary = {k: dict(captured_launches=len(v), dram_bytes_per_launch=sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in v) / len(v),
+                       launches=v, source=[p for p in paths]) for k, v in res.items()}
+    json.dump(summary, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], *sys.argv[3:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
