@@ -40,20 +40,21 @@ def get_smooth_weight(depth, Image, num_scales):
     return ops.smooth_loss(depth, Image, num_scales)
 
 
-def draw_rects(batch, H, W, stage="train", rng=np.random):
+def draw_rects(batch, H, W, stage="train", rng=np.random, p_train=0.90, div=8):
     """The np.random call sequence of ONE of the two rectangle loops (main_model.py:261-267 /
-    :282-288): randint(10,n) -> choice(W) -> choice(H) -> randint(W//150, W//8)*binomial(1,p) ->
-    randint(H//150, H//8)*binomial(1,p).  Returns (rects int32 [batch, MAX_RECTS, 4], counts int32 [batch])."""
+    :282-288): randint(10,n) -> choice(W) -> choice(H) -> randint(W//150, W//div)*binomial(1,p) ->
+    randint(H//150, H//div)*binomial(1,p).  Returns (rects int32 [batch, MAX_RECTS, 4], counts int32 [batch]).
+    (main_sr_model.py:298-305, :319-326 use div = 10 and p = 0.95 for the real loop.)"""
     n = 60 if stage == "train" else 11
-    p = 0.90 if stage == "train" else 0
+    p = p_train if stage == "train" else 0
     rects = np.zeros((batch, MAX_RECTS, 4), dtype=np.int32)
     counts = np.zeros((batch,), dtype=np.int32)
     for i in range(batch):
         number = rng.randint(10, n)
         xs = rng.choice(W, number, replace=False)
         ys = rng.choice(H, number, replace=False)
-        sizes_x = rng.randint(W // 150, W // 8, number) * rng.binomial(1, p)
-        sizes_y = rng.randint(H // 150, H // 8, number) * rng.binomial(1, p)
+        sizes_x = rng.randint(W // 150, W // div, number) * rng.binomial(1, p)
+        sizes_y = rng.randint(H // 150, H // div, number) * rng.binomial(1, p)
         counts[i] = number
         rects[i, :number, 0], rects[i, :number, 1] = xs, ys
         rects[i, :number, 2], rects[i, :number, 3] = sizes_x, sizes_y
@@ -159,6 +160,9 @@ class ArenaAdam(torch.optim.Optimizer):
 
 
 class MainModel(BaseModel):
+    RECT_REAL = dict(p_train=0.90, div=8)          # main_model.py:260,265-266
+    RECT_SYN = dict(p_train=0.90, div=8)           # main_model.py:281,286-287
+
     @staticmethod
     def modify_commandline_options(parser, is_train=True):         # main_model.py:79-87
         parser.set_defaults(no_dropout=True)
@@ -282,8 +286,8 @@ class MainModel(BaseModel):
     def _stage_rects(self, B, H, W, stage):
         """host RNG in the reference's order - real loop first, then syn (main_model.py:257-298) - into persistent
         pinned tables, then one async H2D copy each"""
-        rr, rc = draw_rects(B, H, W, stage)
-        sr, sc = draw_rects(B, H, W, stage)
+        rr, rc = draw_rects(B, H, W, stage, **self.RECT_REAL)
+        sr, sc = draw_rects(B, H, W, stage, **self.RECT_SYN)
         cuda = self.device.type == "cuda"
         if self._rect is None or self._rect["B"] != B:
             mk = lambda shape: torch.zeros(shape, dtype=torch.int32).pin_memory() if cuda else torch.zeros(shape, dtype=torch.int32)

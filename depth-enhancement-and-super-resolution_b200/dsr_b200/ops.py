@@ -1225,6 +1225,53 @@ def smooth_loss(depth, image, num_scales=3):
     return _Smooth.apply(depth, image, num_scales)
 
 
+class _Bicubic(Function):
+    """F.interpolate(x, size=(Ho, Wo), mode='bicubic') (align_corners=False).  main_sr_model.py:279-293, :361, :396-398.
+    Keeps the input's memory layout (NHWC-backed activations stay NHWC, NCHW planes stay planes)."""
+
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        B, C, H, W = x.shape
+        xp = x.permute(0, 2, 3, 1)
+        if C > 1 and xp.is_contiguous():                       # channels-last activation
+            y = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+            _call("dsr_bicubic_fwd", _p(xp), B, H, W, C, Ho, Wo, _p(y))
+            ctx.cfg = (B, H, W, C, Ho, Wo, True)
+            return nchw(y)
+        xc = planes(x)
+        y = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+        _call("dsr_bicubic_fwd", _p(xc), B * C, H, W, 1, Ho, Wo, _p(y))
+        ctx.cfg = (B, H, W, C, Ho, Wo, False)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, H, W, C, Ho, Wo, cl = ctx.cfg
+        if cl:
+            g = nhwc(gy)
+            gx = torch.zeros((B, H, W, C), device=gy.device, dtype=torch.float32)
+            _call("dsr_bicubic_bwd", _p(g), B, H, W, C, Ho, Wo, _p(gx))
+            return nchw(gx), None, None
+        g = planes(gy)
+        gx = torch.zeros((B, C, H, W), device=gy.device, dtype=torch.float32)
+        _call("dsr_bicubic_bwd", _p(g), B * C, H, W, 1, Ho, Wo, _p(gx))
+        return gx, None, None
+
+
+def bicubic(x, size):
+    return _Bicubic.apply(x, int(size[0]), int(size[1]))
+
+
+def nearest(x, size):
+    """F.interpolate(x, size, mode='nearest') of NCHW planes (masks / depth; no gradient).
+    main_sr_model.py:394-395, :452, :459."""
+    xc = planes(x.detach())
+    B, C, H, W = xc.shape
+    y = torch.empty((B, C, int(size[0]), int(size[1])), device=xc.device, dtype=torch.float32)
+    _call("dsr_nearest_fwd", _p(xc), B * C, H, W, 1, int(size[0]), int(size[1]), _p(y))
+    return y
+
+
 def ssim(a, b):
     """Mean SSIM (11x11 Gaussian, sigma 1.5).  pytorch_ssim/__init__.py:17-37.  Forward only."""
     a, b = planes(a.detach()), planes(b.detach())

@@ -79,6 +79,13 @@ int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, 
  * models/pytorch_ssim/__init__.py:17-37. */
 int dsr_ssim_fwd(const float* a, const float* b, long planes, int H, int W, double* out_sum, float* map,
                  void* stream);
+/* resampling of the super-resolution step, tensors [N][H][W][C] (C = 1: NCHW planes with N = B*C).
+ * F.interpolate(mode='bicubic') (align_corners=False, A=-0.75): models/main_sr_model.py:279-293, :361, :368-372,
+ * :396-398; its adjoint (gx += W^T gy, gx zeroed by the caller) for :361; F.interpolate(mode='nearest'): :394-395,
+ * :452, :459. */
+int dsr_bicubic_fwd(const float* x, int N, int H, int W, int C, int Ho, int Wo, float* y, void* stream);
+int dsr_bicubic_bwd(const float* gy, int N, int H, int W, int C, int Ho, int Wo, float* gx /* += */, void* stream);
+int dsr_nearest_fwd(const float* x, int N, int H, int W, int C, int Ho, int Wo, float* y, void* stream);
 
 /* ---- network plumbing (NHWC fp32) ------------------------------------------------------------ */
 int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream);

@@ -40,24 +40,26 @@ def hole_valid_masks(depth, border=BORDER):
     return hole.to(torch.float32), valid
 
 
-def draw_rects(batch, H, W, stage="train", rng=np.random):
+def draw_rects(batch, H, W, stage="train", rng=np.random, p_train=0.90, div=8):
     """Host RNG stream of the random rectangle holes for ONE of the two loops.
 
     models/main_model.py:257-273 (real) and :278-294 (syn): per sample, in this order:
     randint(10, n) -> choice(W, number, replace=False) -> choice(H, number, replace=False) ->
     randint(W//150, W//8, number) * binomial(1, p) -> randint(H//150, H//8, number) *
     binomial(1, p); n, p = (60, 0.9) for 'train', (11, 0) otherwise.
+    models/main_sr_model.py:298-305, :319-326: same stream with ``// 10`` instead of ``// 8`` and
+    p = 0.95 for the real loop (``p_train`` / ``div``).
     Returns a list (len batch) of int arrays (number, 4) = [x, y, size_x, size_y].
     """
     n = 60 if stage == "train" else 11
-    p = 0.90 if stage == "train" else 0
+    p = p_train if stage == "train" else 0
     out = []
     for _ in range(batch):
         number = rng.randint(10, n)
         xs = rng.choice(W, number, replace=False)
         ys = rng.choice(H, number, replace=False)
-        sx = rng.randint(W // 150, W // 8, number) * rng.binomial(1, p)
-        sy = rng.randint(H // 150, H // 8, number) * rng.binomial(1, p)
+        sx = rng.randint(W // 150, W // div, number) * rng.binomial(1, p)
+        sy = rng.randint(H // 150, H // div, number) * rng.binomial(1, p)
         out.append(np.stack([xs, ys, sx, sy], axis=1).astype(np.int64))
     return out
 
@@ -288,6 +290,123 @@ def loss_stack(t, w=None):
     G = G + L["smooth"] * w["w_smooth"]                                 # :408
     G = G * w["scale_G"]                                                # :417
     return G, L, V
+
+
+# --------------------------------------------------------------------------------------------
+# super-resolution step  (models/main_sr_model.py)
+# --------------------------------------------------------------------------------------------
+def bicubic(x, size):
+    """The reference's own call: F.interpolate(x, size, mode='bicubic').  models/main_sr_model.py:279-293, :361,
+    :368-372, :396-398.  Used by the SR step oracle so that it follows the reference bit for bit: the HR nets amplify
+    a 1e-6 resampling difference to 6e-3 on the bottleneck weight gradients (measured with bicubic_restated)."""
+    return F.interpolate(x, size=tuple(size), mode="bicubic")
+
+
+def bicubic_restated(x, size):
+    """What that call computes (align_corners=False; cubic convolution A = -0.75 over border-clamped taps, source
+    coordinate (o + 0.5) * in/out - 0.5), restated tap by tap with no call into torch's interpolate; pinned against
+    tests/golden/resize.npz and used to check the CUDA kernel."""
+    A = -0.75
+
+    def taps(n_in, n_out):
+        o = torch.arange(n_out, dtype=torch.float32)
+        r = (float(n_in) / float(n_out)) * (o + 0.5) - 0.5
+        f = torch.floor(r)
+        t = r - f
+        c1 = lambda v: ((A + 2) * v - (A + 3)) * v * v + 1
+        c2 = lambda v: ((A * v - 5 * A) * v + 8 * A) * v - 4 * A
+        wts = torch.stack([c2(t + 1), c1(t), c1(1 - t), c2(2 - t)], 1)                 # (n_out, 4)
+        idx = (f.long()[:, None] + torch.arange(-1, 3)[None, :]).clamp(0, n_in - 1)      # (n_out, 4)
+        return idx, wts
+
+    B, C, H, W = x.shape
+    iy, wy = taps(H, size[0])
+    ix, wx = taps(W, size[1])
+    rows = (x[:, :, :, ix] * wx.to(x.dtype)).sum(-1)                     # (B, C, H, Wo)
+    return (rows[:, :, iy, :] * wy.to(x.dtype)[None, None, :, :, None]).sum(3)        # (B, C, Ho, Wo)
+
+
+def nearest(x, size):
+    """F.interpolate(x, size, mode='nearest'): src = min(floor(dst * in/out), in - 1).
+    models/main_sr_model.py:394-395, :452, :459."""
+    H, W = x.shape[2], x.shape[3]
+    iy = torch.floor(torch.arange(size[0], dtype=torch.float32) * (float(H) / size[0])).long().clamp(max=H - 1)
+    ix = torch.floor(torch.arange(size[1], dtype=torch.float32) * (float(W) / size[1])).long().clamp(max=W - 1)
+    return x[:, :, iy][:, :, :, ix]
+
+
+SR_DEFAULT_WEIGHTS = dict(w_syn_l1=15.0, w_real_l1_d=90.0, w_real_l1_i=0.1, w_syn_norm=3.0,
+                          w_smooth=1.0, w_syn_holes=1600.0, w_real_holes=1600.0, scale_G=1.0)   # README.md:86
+
+
+def loss_stack_sr(t, lr_size, w=None):
+    """Loss stack of the SR step, models/main_sr_model.py:391-482.  ``t`` as for loss_stack plus
+    pred_real_depth_hr (HR) and pred_real_depth (= bicubic x0.5 of it); real_* tensors at HR on entry.
+    Returns (loss_G, terms, visuals)."""
+    w = dict(SR_DEFAULT_WEIGHTS, **(w or {}))
+    L, V = {}, {}
+    h, wd = lr_size
+    mr = nearest(t["real_mask"], (h, wd))                                # :394
+    hr = nearest(t["real_hole_mask"], (h, wd))                           # :395
+    rd = bicubic(t["real_depth"], (h, wd))                               # :396
+    ri = bicubic(t["real_image"], (h, wd))                               # :397
+    V["real_depth_by_image"] = bicubic(t["real_depth_by_image"], (h, wd))   # :398
+    V.update(real_mask=mr, real_hole_mask=hr, real_depth=rd, real_image=ri)
+    ms = t["syn_mask"]
+    ps, pr, pr_hr = t["pred_syn_depth"], t["pred_real_depth"], t["pred_real_depth_hr"]
+    sd, s2r = t["syn_depth"], t["syn2real_depth_masked"]
+    n_s = surface_normals_old(sd) * 100                                  # :402-410
+    n_sp = surface_normals_old(ps) * 100
+    n_rp_hr = surface_normals_old(pr_hr) * 100
+    L["tv_syn_norm_old"] = tv_loss(n_sp) * (10 ** -7)
+    L["tv_real_norm_old"] = tv_loss(n_rp_hr) * (10 ** -7)
+    L["syn_norms_old"] = l1_mean(n_s, n_sp)
+    a_s = ((s2r < BORDER) | (t["gt_mask_syn"] < 0.1)).to(torch.float32)  # :412-415
+    a_r = nearest(torch.where(t["gt_mask_real"] > 0.1, torch.tensor(0.0), torch.tensor(1.0)), (h, wd))   # :458-459
+    V["a_s"], V["a_r"] = a_s, a_r
+    N_s = surface_normals_new(sd, t["K_A"], t["crop_A"])                 # :425-431
+    N_s2r = surface_normals_new(s2r, t["K_A"], t["crop_A"])
+    N_sp = surface_normals_new(ps, t["K_A"], t["crop_A"])
+    N_r = surface_normals_new(rd, t["K_B"], t["crop_B"])
+    N_rp = surface_normals_new(pr, t["K_B"], t["crop_B"])
+    N_rp_hr = surface_normals_new(pr_hr, t["K_A"], t["crop_A"])
+    V.update(norm_syn=N_s, norm_syn2real=N_s2r, norm_syn_pred=N_sp, norm_real=N_r, norm_real_pred=N_rp,
+             norm_real_pred_hr=N_rp_hr)
+    L["tv_syn_norm"] = tv_loss(N_sp) * (10 ** -7)
+    L["tv_real_norm"] = tv_loss(N_rp) * (10 ** -7)
+    L["syn_norms"] = mse_mean(N_s * ms, N_rp_hr * ms)                    # :434
+    L["syn_norms_holes"] = l1_mean(N_s * ms * a_s, N_sp * ms * a_s)      # :435
+    L["holes_syn"] = l1_mean(sd * ms * a_s, ps * ms * a_s)               # :445-452
+    L["holes_syn_l2"] = mse_mean(sd * ms * a_s, ps * ms * a_s) * 5
+    L["task_syn"] = l1_mean(sd * ms, ps * ms)
+    L["task_real_by_depth"] = l1_mean(rd * mr, pr * mr)
+    L["task_real_by_image"] = l1_mean(nearest(sd, (h, wd)) * hr, pr * hr)
+    G = (L["task_syn"] * w["w_syn_l1"] + L["holes_syn"] * w["w_syn_holes"]
+         + w["w_syn_holes"] * L["holes_syn_l2"] + L["task_real_by_depth"] * w["w_real_l1_d"]
+         + L["task_real_by_image"] * w["w_real_l1_i"] + L["tv_syn_norm"] * 1
+         + L["syn_norms_holes"] * w["w_syn_norm"] * 5 + L["tv_real_norm"] * 2
+         + L["syn_norms_old"] * w["w_syn_norm"] * 5 + L["tv_real_norm_old"] * 2
+         + L["tv_syn_norm_old"] * 1)                                     # :455
+    L["holes_real"] = l1_mean(rd * a_r, pr * a_r)                       # :460
+    L["holes_real_l2"] = mse_mean(rd * a_r, pr * a_r) * 5               # :461
+    G = G + L["holes_real"] * w["w_real_holes"] + L["holes_real_l2"] * w["w_real_holes"]   # :462
+    G = G + L["syn_norms"] * w["w_syn_norm"]                            # :469
+    L["smooth"] = smooth_loss(pr, ri, 3)                                # :472
+    G = G + L["smooth"] * w["w_smooth"]
+    G = G * w["scale_G"]                                                # :482
+    return G, L, V
+
+
+def monitor_scalars_sr(t, lr_size):
+    """models/main_sr_model.py:362-372 (real side: bicubic-resized depth AND mask)."""
+    out = {}
+    d, m, p = t["syn_depth"], t["syn_mask"], t["pred_syn_depth"].detach()
+    out["syn_mean_diff"] = float((d * m).mean() - (p * m).mean())
+    out["mean_of_abs_diff_syn"] = float((d * m - p * m).abs().mean())
+    d, m, p = bicubic(t["real_depth"], lr_size), bicubic(t["real_mask"], lr_size), t["pred_real_depth"].detach()
+    out["real_mean_diff"] = float((d * m).mean() - (p * m).mean())
+    out["mean_of_abs_diff_real"] = float((d * m - p * m).abs().mean())
+    return out
 
 
 def monitor_scalars(t):

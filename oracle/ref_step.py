@@ -83,6 +83,78 @@ class OracleStep:
         return dict(tensors=t, losses=losses, visuals=visuals, grads=grads)
 
 
+class OracleSRStep(OracleStep):
+    """One ``MainSRModel.optimize_parameters`` step (models/main_sr_model.py:228-497).  ``lr_size`` =
+    (opt.crop_size_h, opt.crop_size_w); the batch holds HR (2h x 2w) tensors."""
+
+    def __init__(self, state_dicts, lr_size, lr=2e-5, weights=None):
+        super().__init__(state_dicts, lr=lr, weights=weights)
+        self.lr_size = tuple(lr_size)
+
+    def forward(self, batch, stage="train"):
+        h, w = self.lr_size
+        t = {}
+        t["syn_image"], t["real_image"] = batch["A_i"].float(), batch["B_i"].float()
+        t["syn_depth"], t["real_depth"] = batch["A_d"].float(), batch["B_d"].float()
+        t["K_A"], t["K_B"], t["crop_A"], t["crop_B"] = batch["K_A"], batch["K_B"], batch["crop_A"], batch["crop_B"]
+        t["real_hole_mask"], t["real_mask"] = ref_ops.hole_valid_masks(t["real_depth"])
+        _, t["syn_mask"] = ref_ops.hole_valid_masks(t["syn_depth"])
+        B, _, H, W = t["real_depth"].shape
+        with torch.no_grad():
+            t["syn2real_depth"] = ref_nets.translation_generator(self.sd["G_A_d"], t["syn_depth"], t["syn_image"])
+            f_real = ref_nets.resnet_generator(self.sd["I2D_features"], ref_ops.bicubic(t["real_image"], (h, w)))   # :279
+            t["real_depth_by_image"] = ref_ops.bicubic(ref_nets.unet_generator(self.sd["Image2Depth"], f_real), (H, W))
+            f_real = ref_ops.bicubic(f_real, (H, W))
+            f_syn = ref_nets.resnet_generator(self.sd["I2D_features"], ref_ops.bicubic(t["syn_image"], (h, w)))     # :285
+            t["syn_depth_by_image"] = ref_ops.bicubic(ref_nets.unet_generator(self.sd["Image2Depth"], f_syn), (H, W))
+            f_syn = ref_ops.bicubic(f_syn, (H, W))
+        t["rects_real"] = ref_ops.draw_rects(B, H, W, stage, p_train=0.95, div=10)           # :298-305
+        t["gt_mask_real"] = ref_ops.rect_gt_mask(t["real_mask"], t["rects_real"])
+        t["depth_masked"] = ref_ops.apply_gt_mask(t["real_depth"], t["gt_mask_real"])
+        t["rects_syn"] = ref_ops.draw_rects(B, H, W, stage, p_train=0.90, div=10)            # :319-326
+        t["gt_mask_syn"] = ref_ops.rect_gt_mask(t["syn_mask"], t["rects_syn"])
+        t["syn2real_depth_masked"] = ref_ops.apply_gt_mask(t["syn2real_depth"], t["gt_mask_syn"])
+        in_r = torch.cat([t["depth_masked"], t["real_depth_by_image"]], 1)
+        fd_r = ref_nets.resnet_generator(self.sd["Depth_f"], in_r)
+        t["pred_real_depth_hr"] = ref_nets.unet_generator(self.sd["Task"], torch.cat([f_real, fd_r, in_r, t["real_image"]], 1))
+        in_s = torch.cat([t["syn2real_depth_masked"], t["syn_depth_by_image"]], 1)
+        fd_s = ref_nets.resnet_generator(self.sd["Depth_f"], in_s)
+        t["pred_syn_depth"] = ref_nets.unet_generator(self.sd["Task"], torch.cat([f_syn, fd_s, in_s, t["syn_image"]], 1))
+        t["pred_real_depth"] = ref_ops.bicubic(t["pred_real_depth_hr"], (h, w))                # :361
+        t["monitor"] = ref_ops.monitor_scalars_sr(t, (h, w))
+        return t
+
+    def step(self, batch, stage="train", update=True):
+        for net in TRAINABLE:
+            for p in self.sd[net].values():
+                p.grad = None
+        t = self.forward(batch, stage)
+        loss_G, terms, visuals = ref_ops.loss_stack_sr(t, self.lr_size, self.weights)
+        loss_G.backward()
+        grads = {(net, n): p.grad.detach().clone() for net in TRAINABLE for n, p in self.sd[net].items()}
+        if update:
+            self.n_step += 1
+            with torch.no_grad():
+                for net in TRAINABLE:
+                    for n, p in self.sd[net].items():
+                        m, v = self.adam[(net, n)]
+                        ref_ops.adam_update(p, p.grad, m, v, self.n_step, self.lr)
+        losses = {k: float(v) for k, v in terms.items()}
+        losses.update(t["monitor"])
+        losses["G"] = float(loss_G)
+        return dict(tensors=t, losses=losses, visuals=visuals, grads=grads)
+
+
+def synthetic_sr_batch(B, h, w, seed=1, depth_kind="smooth"):
+    """HR (2h x 2w) synthetic batch with the K / crop conventions of data/my_naive_sr_dataset.py:190-207:
+    K_A scaled by [[2,1,2],[1,2,2],[1,1,1]], crop_A = HR extent, crop_B = LR extent."""
+    b = synthetic_batch(B, 2 * h, 2 * w, seed=seed, depth_kind=depth_kind)
+    scale = torch.tensor([[2.0, 1, 2], [1, 2, 2], [1, 1, 1]], dtype=torch.float64)
+    b["K_A"] = b["K_A"] * scale
+    b["crop_B"] = torch.tensor([[0, h, 0, w]] * B)
+    return b
+
+
 def synthetic_batch(B, H, W, seed=1, depth_kind="noise"):
     """Synthetic RGB-D batch of SURVEY.md section 8(d) / Appendix D (CPU tensors, dataset dict keys of
     data/my_main_dataset.py:195)."""

@@ -96,6 +96,82 @@ def golden_step(B=2, H=128, W=128, depth_kind="smooth", tag="step_b2_128"):
     print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
 
 
+def golden_sr_step(B=1, h=128, w=128, tag="sr_step_b1_128"):
+    """One + one MainSRModel steps (models/main_sr_model.py) on a B=1, LR 128x128 -> HR 256x256 synthetic batch,
+    flags of README.md:86.  The reference hard-codes gpu_ids=[0,1,2,3] for G_A_d (main_sr_model.py:166), so
+    translation_network.init_net is wrapped to force gpu_ids=[]."""
+    from oracle.ref_step import synthetic_sr_batch
+    sys.argv = ["main.py", "--gpu_ids", "-1", "--image_and_depth", "--custom_pathes", "--use_image_for_trans",
+                "--w_syn_l1", "15", "--w_real_l1_d", "90", "--norm_loss", "--w_syn_norm", "3",
+                "--use_smooth_loss", "--w_smooth", "1", "--w_syn_holes", "1600", "--w_real_holes", "1600",
+                "--use_masked", "--use_scannet", "--lr", "0.00002", "--model", "main_network_best",
+                "--batch_size", str(B), "--name", "golden_sr", "--do_train", "--model_type", "main", "--SR",
+                "--checkpoints_dir", "/tmp/golden/ckpt", "--crop_size_h", str(h), "--crop_size_w", str(w)]
+    from options.train_options import TrainOptions
+    opt = TrainOptions().parse()
+    from models import translation_network as tn
+    orig = tn.init_net
+    tn.init_net = lambda net, init_type="normal", init_gain="relu", gpu_ids=[], param=None: orig(net, init_type, init_gain, [], param)
+    from models.main_sr_model import MainSRModel
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = MainSRModel(opt)
+    model.setup(opt)
+    model._train()
+    out = {}
+    for name in model.model_names:
+        sd = getattr(model, "net" + name).state_dict()
+        out[f"wsum/{name}"] = np.array([float(sum(v.double().sum() for v in sd.values())),
+                                        float(sum(v.double().abs().sum() for v in sd.values())),
+                                        float(sum(v.numel() for v in sd.values()))])
+    batch = synthetic_sr_batch(B, h, w, seed=1, depth_kind="smooth")
+    np.random.seed(0)
+    for it in range(2):
+        model.set_input(batch)
+        model.optimize_parameters(it, 1)
+        p = f"s{it}/"
+        for k, v in model.get_current_losses().items():
+            out[p + "loss/" + k] = np.float64(v)
+        out[p + "loss/G"] = np.float64(float(model.loss_G))
+        out[p + "loss/mean_of_abs_diff_syn"] = np.float64(model.loss_mean_of_abs_diff_syn)
+        out[p + "loss/mean_of_abs_diff_real"] = np.float64(model.loss_mean_of_abs_diff_real)
+        for k in ("pred_syn_depth", "pred_real_depth", "pred_real_depth_hr"):
+            out[p + k] = getattr(model, k).detach().numpy().astype(np.float32)
+        if it == 0:
+            for k in ("syn2real_depth", "syn_depth_by_image", "real_depth_by_image", "real_depth"):
+                out[p + k] = getattr(model, k).detach().numpy().astype(np.float16)
+            for k in ("syn_mask", "real_mask", "real_hole_mask"):
+                out[p + k] = getattr(model, k).numpy().astype(np.uint8)
+            out[p + "gt_mask_syn"] = model.gt_mask_syn.numpy().astype(np.uint8)
+            out[p + "gt_mask_real"] = model.gt_mask_real.numpy().astype(np.uint8)
+            gi = 0
+            for net in ("Depth_f", "Task"):
+                for n, prm in getattr(model, "net" + net).named_parameters():
+                    g = prm.grad.detach().double().flatten()
+                    out[p + f"gstat/{net}/{n}"] = np.array([float(g.norm()), float(g @ proj_vec(g.numel(), 1000 + gi))])
+                    gi += 1
+    tn.init_net = orig
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
+
+
+def golden_resize():
+    """F.interpolate bicubic / nearest vectors (the torch calls of main_sr_model.py:279-293, :361, :394-398)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(2, 3, 24, 36, generator=g) * 2 - 1
+    out = {"x": x.numpy()}
+    for name, size in (("down", (12, 18)), ("up", (48, 72)), ("odd", (10, 50))):
+        out["bicubic_" + name] = F.interpolate(x, size=size, mode="bicubic").numpy()
+        out["nearest_" + name] = F.interpolate(x, size=size, mode="nearest").numpy()
+    xg = x.clone().requires_grad_(True)
+    gy = torch.rand(2, 3, 12, 18, generator=g)
+    (F.interpolate(xg, size=(12, 18), mode="bicubic") * gy).sum().backward()
+    out["gy_down"], out["gx_down"] = gy.numpy(), xg.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "resize.npz"), **out)
+    print("wrote resize")
+
+
 def golden_ops():
     """Per-op vectors from the reference's own functions (adversarial: skewed K, crop offset,
     non-square, all-hole rows, borders)."""
@@ -141,5 +217,13 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    golden_ops()
-    golden_step()
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr"]
+    sys.argv = sys.argv[:1]
+    if "ops" in which:
+        golden_ops()
+    if "step" in which:
+        golden_step()
+    if "resize" in which:
+        golden_resize()
+    if "sr" in which:
+        golden_sr_step()

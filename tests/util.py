@@ -11,10 +11,23 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-def build_host_model(B, H, W, gpu_ids=(), seed=0, **kw):
+def _model_cls(sr):
+    if sr:
+        from dsr_b200 import main_sr_model
+        return main_sr_model.MainSRModel
+    from dsr_b200 import main_model
+    return main_model.MainModel
+
+
+SR_FLAGS = dict(w_real_l1_d=90.0, w_syn_norm=3.0, w_syn_holes=1600.0, w_real_holes=1600.0, lr=0.00002, SR=True)   # README.md:86
+
+
+def build_host_model(B, H, W, gpu_ids=(), seed=0, sr=False, **kw):
     """MainModel with the seeded reference initialisation (torch.manual_seed(seed) before the
     constructors == the weights the golden run had; checked by test_host_logic)."""
-    from dsr_b200 import main_model, options
+    from dsr_b200 import options
+    if sr:
+        kw = dict(SR_FLAGS, **kw)
     opt = options.main_flags(gpu_ids=list(gpu_ids), batch_size=B, crop_size_h=H, crop_size_w=W, name="t",
                              checkpoints_dir="/tmp/dsr_ck", **kw)
     torch.manual_seed(seed)
@@ -24,7 +37,7 @@ def build_host_model(B, H, W, gpu_ids=(), seed=0, **kw):
         # the reference initialises on the device when gpu_ids is set (CUDA RNG); for parity we want
         # the CPU-seeded weights, so build on the host and move afterwards
         opt.gpu_ids = []
-    m = main_model.MainModel(opt)
+    m = _model_cls(sr)(opt)
     if gpu_ids:
         m = rehome(m, opt, list(gpu_ids))
     return m
@@ -35,7 +48,7 @@ def rehome(host_model, opt, gpu_ids):
     from dsr_b200 import main_model
     sds = state_dicts(host_model)
     opt.gpu_ids = gpu_ids
-    m = main_model.MainModel(opt)
+    m = type(host_model)(opt)
     for name, sd in sds.items():
         main_model.MainModel._unwrap(getattr(m, "net" + name)).load_state_dict(sd)
     return m
