@@ -22,9 +22,39 @@ for p in (ROOT, PKG):
 WORKLOADS = {   # BASELINE.json configs[1] / configs[2]
     "c2": dict(B=6, H=256, W=256, name="main_network_best training step, batch 6 per GPU, 256x256 crops"),
     "c3": dict(B=3, H=512, W=640, name="main_network_best full-size 640x480 (fed as 512x640), batch 3 per GPU"),
+    # BASELINE.json configs[3] at the reference's native x2 (main_sr_model.py; README.md:86 uses batch 1): H, W = LR crop
+    # (the U-Net-128 of Image2Depth needs LR sides that are multiples of 128, so 256x320 -> 512x640 cannot run in the reference)
+    "c4": dict(B=1, H=512, W=640, sr=True, name="main_sr_model x2 depth super-resolution step (LR 512x640 -> HR 1024x1280, README.md:86), batch 1 per GPU"),
     "tiny": dict(B=1, H=128, W=128, name="debug"),
 }
 FLOP_PER_PAIR_256 = 606.2e9      # 2*174.68 + 4*64.20 GMAC-pairs
+# SR step: G_A_d, Depth_f (fwd + bwd), Task (fwd + bwd) run on HR pixels, I2D_features and Image2Depth on LR pixels
+FLOP_SR_HR_256 = 2e9 * (50.55 + 3 * (43.63 + 20.57))
+FLOP_SR_LR_256 = 2e9 * (43.84 + 16.11)
+
+
+def step_flops(wl):
+    px = wl["H"] * wl["W"] / 65536.0
+    if wl.get("sr"):
+        return wl["B"] * (FLOP_SR_HR_256 * 4 * px + FLOP_SR_LR_256 * px)
+    return wl["B"] * FLOP_PER_PAIR_256 * px
+
+
+def make_model(wl, gpu_ids, graph, name="bench"):
+    from dsr_b200 import main_model, main_sr_model, options
+    kw = dict(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"], crop_size_w=wl["W"], name=name,
+              checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(graph))
+    if wl.get("sr"):       # README.md:86
+        kw.update(w_real_l1_d=90.0, w_syn_norm=3.0, w_syn_holes=1600.0, w_real_holes=1600.0, lr=0.00002, SR=True)
+        return main_sr_model.MainSRModel(options.main_flags(**kw))
+    return main_model.MainModel(options.main_flags(**kw))
+
+
+def make_batch(wl, seed):
+    from oracle.ref_step import synthetic_batch, synthetic_sr_batch      # synthetic input generator only (shared with the tests)
+    if wl.get("sr"):
+        return synthetic_sr_batch(wl["B"], wl["H"], wl["W"], seed=seed, depth_kind="smooth")
+    return synthetic_batch(wl["B"], wl["H"], wl["W"], seed=seed, depth_kind="smooth")
 
 
 def peaks():
@@ -79,19 +109,18 @@ def ncu_traffic(kernel):
     return None
 
 
-def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None):
+def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False):
     """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
     import numpy as np
     import torch
     from oracle import ref_step
+    wl = dict(B=B, H=H, W=W, sr=sr)
     if sds is None:
-        from dsr_b200 import main_model, options
         torch.manual_seed(0)
-        host = main_model.MainModel(options.main_flags(gpu_ids=[], batch_size=B, crop_size_h=H, crop_size_w=W,
-                                                       name="cpu", checkpoints_dir="/tmp/dsr_bench"))
+        host = make_model(wl, [], False, name="cpu")
         sds = {n: getattr(host, "net" + n).state_dict() for n in host.model_names}
-    orc = ref_step.OracleStep(sds, lr=1e-4)
-    batch = ref_step.synthetic_batch(B, H, W, seed=1, depth_kind="smooth")
+    orc = ref_step.OracleSRStep(sds, (H, W), lr=2e-5) if sr else ref_step.OracleStep(sds, lr=1e-4)
+    batch = make_batch(wl, 1)
     np.random.seed(0)
     ts = []
     for i in range(warmup + steps):
@@ -110,7 +139,7 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     Bs = min(wl["B"], 2)                      # bounded sample: B=2 of the workload's crops per step
-    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup)
+    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")))
     line = dict(impl="reference", metric="RGB-D train pair-samples/sec (main net)", value=r["value"], unit="pair-samples/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * r["s_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -122,12 +151,40 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def inference_ms_per_frame(local, iters=20):
+    """BASELINE.json's second number: ms per 640x480 frame (fed as 512x640, batch 1) of the enhancement forward
+    (`calculate('test')` minus PNG writing, main_model.py:433-436 -> forward only here), device-timed, host inputs."""
+    import numpy as np
+    import torch
+    wl = dict(B=1, H=512, W=640)
+    torch.manual_seed(0)
+    m = make_model(wl, [local], False, name="infer")
+    m.eval()
+    b = make_batch(wl, 5)
+    for k in ("A_i", "B_i", "A_d", "B_d"):
+        b[k] = b[k].pin_memory()
+    np.random.seed(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(3 + iters):
+            if i == 3:
+                torch.cuda.synchronize()
+                e0.record()
+            m.set_input(b)
+            m.forward("test")
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return dict(ms_per_frame=ms, frames_per_s=1e3 / ms, shape=[512, 640], batch=1,
+                note="set_input (H2D from pinned host) + forward('test'): G_A_d + I2D_features + Image2Depth + Depth_f + Task on "
+                     "the [syn; real] pair, eager launches")
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from dsr_b200 import _lib, main_model, ops, options, parallel
-    from oracle.ref_step import synthetic_batch          # synthetic input generator only (shared with the tests)
+    from dsr_b200 import _lib, ops, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -140,10 +197,8 @@ def run_ours(args):
     ops.CONFIG.update(engine=args.engine, passes=args.passes, dtype=args.dtype)
     wl = WORKLOADS[args.workload]
     B, H, W = wl["B"], wl["H"], wl["W"]
-    opt = options.main_flags(gpu_ids=[local], batch_size=B, crop_size_h=H, crop_size_w=W, name="bench",
-                             checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(args.graph))
     torch.manual_seed(0)
-    model = main_model.MainModel(opt)
+    model = make_model(wl, [local], args.graph)
     model._train()
     sync = None
     if world > 1:
@@ -152,7 +207,7 @@ def run_ours(args):
     # a few distinct host batches in pinned memory (per-rank seeds: each rank draws its own shard)
     host_batches = []
     for i in range(2):
-        b = synthetic_batch(B, H, W, seed=1 + 17 * rank + i, depth_kind="smooth")
+        b = make_batch(wl, 1 + 17 * rank + i)
         for k in ("A_i", "B_i", "A_d", "B_d"):
             b[k] = b[k].pin_memory()
         host_batches.append(b)
@@ -268,12 +323,16 @@ def run_ours(args):
             k, d = top[0]
             roof = dict(bound="hbm", kernel=k, achieved=None, peak=pk["hbm_gbs"], unit="GB/s", frac=None, traffic=None,
                         share_of_step=d["ms"] / total_ms)
-        flop_step = FLOP_PER_PAIR_256 * (H * W / 65536.0) * B
+        flop_step = step_flops(wl)
         cpu = None
-        if not args.no_cpu_baseline:
-            r = cpu_baseline(2, H, W, steps=2, warmup=1)
+        if not args.no_cpu_baseline and world == 1:
+            Bc = min(B, 2)
+            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")))
             cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
-                       sample=f"2 steps of batch 2 at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
+                       sample=f"2 steps of batch {Bc} at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
+        extras = None
+        if args.inference and not wl.get("sr") and world == 1:
+            extras = inference_ms_per_frame(local)
         line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
                     unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -286,7 +345,7 @@ def run_ours(args):
                     e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="pair-samples/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu,
-                    step_tflops=flop_step / (ms / args.steps * 1e-3) / 1e12,
+                    step_tflops=flop_step / (ms / args.steps * 1e-3) / 1e12, inference_640x480=extras,
                     kernel_times_ms={k: round(d["ms"], 3) for k, d in top})
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -312,6 +371,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default="", help="write every library call of one step (name, ms, shape, GMACs) to this JSON file")
     ap.add_argument("--kernel-table", default="", help="write the in-situ per-kernel device times of 3 steps (torch.profiler / CUPTI, warm caches) to this JSON file")
+    ap.add_argument("--inference", type=int, default=1, help="1 = also time the 640x480 inference forward (ms/frame)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the training step as a CUDA graph (default), 0 = eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

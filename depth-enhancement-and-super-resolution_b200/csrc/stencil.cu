@@ -1,5 +1,5 @@
-// Depth-derived stencil / reduction kernels of the loss stack (HBM-bound; NCHW fp32 planes exactly
-// as the reference holds them).  Reference call sites: models/main_model.py:208-230 (masks),
+// Remaining untiled kernels of the loss stack (monitoring sums, bilinear pyramid resize, SSIM); the depth-derived
+// stencils proper live in stencil_tiled.cu.  (HBM-bound; NCHW fp32 planes exactly as the reference holds them.)  Reference call sites: models/main_model.py:208-230 (masks),
 // :257-298 (rectangle holes), :340-417 (loss stack), models/norms.py (normals),
 // models/pytorch_ssim/__init__.py (SSIM).  C-ABI entry points at the bottom (include/dsr_b200.h).
 #include "common.cuh"
@@ -7,196 +7,6 @@
 #include "../../include/dsr_b200.h"
 
 #define TPB 256
-
-// ------------------------------------------------------------------------------------------
-// hole / valid masks  (main_model.py:208-230): hole = d <= border; valid = !dilate3x3(hole)
-// ------------------------------------------------------------------------------------------
-__global__ void hole_valid_kernel(const float* __restrict__ d, int B, int H, int W, float border,
-                                  float* __restrict__ hole, float* __restrict__ valid) {
-    long total = (long)B * H * W;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int j = (int)(idx % W);
-        int i = (int)((idx / W) % H);
-        const float* p = d + (idx - (long)i * W - j);
-        bool any = false;
-#pragma unroll
-        for (int di = -1; di <= 1; ++di) {
-            int ii = i + di;
-            if (ii < 0 || ii >= H) continue;
-#pragma unroll
-            for (int dj = -1; dj <= 1; ++dj) {
-                int jj = j + dj;
-                if (jj < 0 || jj >= W) continue;
-                any |= (__ldg(p + (long)ii * W + jj) <= border);
-            }
-        }
-        if (hole) hole[idx] = (d[idx] <= border) ? 1.f : 0.f;
-        valid[idx] = any ? 0.f : 1.f;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// rectangle holes (main_model.py:257-298 + :354-357 / :396)
-//   gt = !(valid > 0.05 && covered);  masked = gt ? depth : -1;
-//   extra = (masked < extra_border) || !gt      (extra_border = -inf for the real domain)
-// rects: int32 [B][max_rects][4] = x, y, size_x, size_y ; counts int32 [B]
-// ------------------------------------------------------------------------------------------
-__global__ void rect_holes_kernel(const float* __restrict__ valid, const float* __restrict__ depth,
-                                  const int* __restrict__ rects, const int* __restrict__ counts, int max_rects,
-                                  int H, int W, float extra_border, unsigned char* __restrict__ gt,
-                                  float* __restrict__ masked, float* __restrict__ extra) {
-    extern __shared__ int srect[];
-    int b = blockIdx.y;
-    int n = counts[b];
-    for (int t = threadIdx.x; t < n * 4; t += blockDim.x) srect[t] = rects[(long)b * max_rects * 4 + t];
-    __syncthreads();
-    long plane = (long)H * W;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += (long)gridDim.x * blockDim.x) {
-        int x = (int)(p % W), y = (int)(p / W);
-        bool cov = false;
-        for (int r = 0; r < n; ++r) {
-            int rx = srect[4 * r], ry = srect[4 * r + 1], sx = srect[4 * r + 2], sy = srect[4 * r + 3];
-            cov |= (x >= rx) & (x < rx + sx) & (y >= ry) & (y < ry + sy);
-        }
-        long o = (long)b * plane + p;
-        bool g = !((valid[o] > 0.05f) && cov);
-        float m = g ? depth[o] : -1.f;
-        gt[o] = g ? 1 : 0;
-        masked[o] = m;
-        if (extra) extra[o] = ((m < extra_border) || !g) ? 1.f : 0.f;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// normals
-// ------------------------------------------------------------------------------------------
-__global__ void normals_old_fwd_kernel(const float* __restrict__ d, int B, int H, int W, float scale,
-                                       float* __restrict__ out) {
-    long plane = (long)H * W, total = (long)B * plane;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int b = (int)(idx / plane);
-        long p = idx - (long)b * plane;
-        int i = (int)(p / W), j = (int)(p % W);
-        float n[3];
-        old_normal_fwd(d + (long)b * plane, H, W, i, j, scale, n);
-        float* o = out + (long)b * 3 * plane + p;
-        o[0] = n[0]; o[plane] = n[1]; o[2 * plane] = n[2];
-    }
-}
-__global__ void normals_old_bwd_kernel(const float* __restrict__ d, const float* __restrict__ g, int B, int H,
-                                       int W, float scale, float* __restrict__ gd) {
-    long plane = (long)H * W, total = (long)B * plane;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int b = (int)(idx / plane);
-        long p = idx - (long)b * plane;
-        int i = (int)(p / W), j = (int)(p % W);
-        gd[idx] = old_normal_bwd(d + (long)b * plane, g + (long)b * 3 * plane, plane, H, W, i, j, scale);
-    }
-}
-__global__ void normals_new_fwd_kernel(const float* __restrict__ d, const double* __restrict__ cams, int B,
-                                       int H, int W, float* __restrict__ out) {
-    long plane = (long)H * W, total = (long)B * plane;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int b = (int)(idx / plane);
-        long p = idx - (long)b * plane;
-        int i = (int)(p / W), j = (int)(p % W);
-        float n[3];
-        new_normal_fwd(d + (long)b * plane, cams + b * DSR_CAM_DOUBLES, H, W, i, j, n);
-        float* o = out + (long)b * 3 * plane + p;
-        o[0] = n[0]; o[plane] = n[1]; o[2 * plane] = n[2];
-    }
-}
-__global__ void normals_new_bwd_kernel(const float* __restrict__ d, const float* __restrict__ g,
-                                       const double* __restrict__ cams, int B, int H, int W,
-                                       float* __restrict__ gd) {
-    long plane = (long)H * W, total = (long)B * plane;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int b = (int)(idx / plane);
-        long p = idx - (long)b * plane;
-        int i = (int)(p / W), j = (int)(p % W);
-        gd[idx] = new_normal_bwd(d + (long)b * plane, g + (long)b * 3 * plane, plane,
-                                 cams + b * DSR_CAM_DOUBLES, H, W, i, j);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// total variation (main_model.py:15-19): sum of squared forward differences, x is (BC, H, W)
-// ------------------------------------------------------------------------------------------
-__global__ void tv_fwd_kernel(const float* __restrict__ x, long planes, int H, int W, double* __restrict__ out) {
-    __shared__ double red[32];
-    long plane = (long)H * W, total = planes * plane;
-    double acc = 0.0;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long p = idx % plane;
-        int i = (int)(p / W), j = (int)(p % W);
-        float v = x[idx];
-        float a = 0.f;
-        if (j < W - 1) { float t = v - x[idx + 1]; a += t * t; }
-        if (i < H - 1) { float t = v - x[idx + W]; a += t * t; }
-        acc += (double)a;
-    }
-    acc = block_sum<double>(acc, red);
-    if (threadIdx.x == 0) atomicAdd(out, acc);
-}
-__global__ void tv_bwd_kernel(const float* __restrict__ x, long planes, int H, int W, const float* __restrict__ gscale,
-                              float coef, float* __restrict__ gx) {
-    long plane = (long)H * W, total = planes * plane;
-    float gs = coef * (gscale ? *gscale : 1.f) * 2.f;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long p = idx % plane;
-        int i = (int)(p / W), j = (int)(p % W);
-        float v = x[idx];
-        float a = 0.f;
-        if (j < W - 1) a += v - x[idx + 1];
-        if (j > 0) a -= x[idx - 1] - v;
-        if (i < H - 1) a += v - x[idx + W];
-        if (i > 0) a -= x[idx - W] - v;
-        gx[idx] = gs * a;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// masked L1 / L2 sums:  t = (a*m1)*m2 - (b*m1)*m2 ; out[0] += sum|t| ; out[1] += sum t^2
-// a, b are (B, C, H, W); masks are (B, 1, H, W) (m2 may be null).  main_model.py:352,371-372,383-398
-// ------------------------------------------------------------------------------------------
-__global__ void masked_diff_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                       const float* __restrict__ m1, const float* __restrict__ m2, int B, int C,
-                                       long plane, double* __restrict__ out) {
-    __shared__ double red[32];
-    long total = (long)B * C * plane;
-    double s1 = 0.0, s2 = 0.0;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long bc = idx / plane;
-        long mo = (bc / C) * plane + (idx - bc * plane);
-        float m = m1[mo];
-        float ta = a[idx] * m, tb = b[idx] * m;
-        if (m2) { float mm = m2[mo]; ta *= mm; tb *= mm; }
-        float t = ta - tb;
-        s1 += (double)fabsf(t);
-        s2 += (double)(t * t);
-    }
-    s1 = block_sum<double>(s1, red);
-    s2 = block_sum<double>(s2, red);
-    if (threadIdx.x == 0) { atomicAdd(out, s1); atomicAdd(out + 1, s2); }
-}
-// grad wrt b:  gb = -(c1*g1*sign(t) + c2*g2*2t) * m
-__global__ void masked_diff_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                       const float* __restrict__ m1, const float* __restrict__ m2, int B, int C,
-                                       long plane, const float* __restrict__ g1, const float* __restrict__ g2,
-                                       float c1, float c2, float* __restrict__ gb) {
-    long total = (long)B * C * plane;
-    float w1 = c1 * (g1 ? *g1 : 0.f), w2 = c2 * (g2 ? *g2 : 0.f);
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long bc = idx / plane;
-        long mo = (bc / C) * plane + (idx - bc * plane);
-        float m = m1[mo];
-        float ta = a[idx] * m, tb = b[idx] * m;
-        if (m2) { float mm = m2[mo]; ta *= mm; tb *= mm; m *= mm; }
-        float t = ta - tb;
-        float sg = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f);
-        gb[idx] = -(w1 * sg + w2 * 2.f * t) * m;
-    }
-}
 
 // sums for the monitoring scalars (main_model.py:308-318): out = [sum d*m, sum p*m, sum |d*m - p*m|]
 __global__ void masked_sums_kernel(const float* __restrict__ d, const float* __restrict__ p,
@@ -249,54 +59,6 @@ __global__ void bilinear_ac_bwd_kernel(const float* __restrict__ g, long planes,
         atomicAdd(s + (long)y1 * W + x1, v * ly1 * lx1);
     }
 }
-// one pyramid level: d (B,1,h,w), img (B,C,h,w).  'x' = difference along H, 'y' = along W.
-// out[0] += sum |dx * wx| ; out[1] += sum |dy * wy|
-__device__ __forceinline__ float smooth_weight(const float* img, int C, long plane, long o, long step) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s += fabsf(img[c * plane + o] - img[c * plane + o + step]);
-    return __expf(-s / (float)C);
-}
-__global__ void smooth_level_fwd_kernel(const float* __restrict__ d, const float* __restrict__ img, int B, int C,
-                                        int h, int w, double* __restrict__ out) {
-    __shared__ double red[32];
-    long plane = (long)h * w, total = (long)B * plane;
-    double sx = 0, sy = 0;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int b = (int)(idx / plane);
-        long p = idx - (long)b * plane;
-        int i = (int)(p / w), j = (int)(p % w);
-        const float* im = img + (long)b * C * plane;
-        float v = d[idx];
-        if (i < h - 1) sx += (double)fabsf((v - d[idx + w]) * smooth_weight(im, C, plane, p, w));
-        if (j < w - 1) sy += (double)fabsf((v - d[idx + 1]) * smooth_weight(im, C, plane, p, 1));
-    }
-    sx = block_sum<double>(sx, red); sy = block_sum<double>(sy, red);
-    if (threadIdx.x == 0) { atomicAdd(out, sx); atomicAdd(out + 1, sy); }
-}
-// gd[idx] (+)= g * (cx * d/dd sum|dx wx| + cy * d/dd sum|dy wy|)
-__global__ void smooth_level_bwd_kernel(const float* __restrict__ d, const float* __restrict__ img, int B, int C,
-                                        int h, int w, const float* __restrict__ gscale, float cx, float cy,
-                                        float* __restrict__ gd, int accumulate) {
-    long plane = (long)h * w, total = (long)B * plane;
-    float g = gscale ? *gscale : 1.f;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        int b = (int)(idx / plane);
-        long p = idx - (long)b * plane;
-        int i = (int)(p / w), j = (int)(p % w);
-        const float* im = img + (long)b * C * plane;
-        float v = d[idx], acc = 0.f;
-        if (i < h - 1) { float t = (v - d[idx + w]); float wt = smooth_weight(im, C, plane, p, w);
-                         float s = t * wt; acc += cx * wt * ((s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f)); }
-        if (i > 0)     { float t = (d[idx - w] - v); float wt = smooth_weight(im, C, plane, p - w, w);
-                         float s = t * wt; acc -= cx * wt * ((s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f)); }
-        if (j < w - 1) { float t = (v - d[idx + 1]); float wt = smooth_weight(im, C, plane, p, 1);
-                         float s = t * wt; acc += cy * wt * ((s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f)); }
-        if (j > 0)     { float t = (d[idx - 1] - v); float wt = smooth_weight(im, C, plane, p - 1, 1);
-                         float s = t * wt; acc -= cy * wt * ((s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f)); }
-        if (accumulate) gd[idx] += g * acc; else gd[idx] = g * acc;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // SSIM (pytorch_ssim/__init__.py:17-37): 11x11 Gaussian (sigma 1.5), zero 'same' padding,
 // separable passes staged in shared memory; one 32x32 output tile of one (b,c) plane per CTA.
@@ -362,79 +124,6 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, 
 // ------------------------------------------------------------------------------------------
 #define ST(s) ((cudaStream_t)(s))
 
-extern "C" int dsr_hole_valid_masks(const float* depth, int B, int H, int W, float border, float* hole,
-                                    float* valid, void* stream) {
-    DSR_REQUIRE(depth && valid && B > 0 && H > 0 && W > 0, "bad arguments");
-    long n = (long)B * H * W;
-    hole_valid_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(depth, B, H, W, border, hole, valid);
-    return dsr_check_launch("hole_valid_masks");
-}
-
-extern "C" int dsr_rect_holes(const float* valid, const float* depth, const int* rects, const int* counts,
-                              int max_rects, int B, int H, int W, float extra_border, unsigned char* gt_mask,
-                              float* masked, float* extra, void* stream) {
-    DSR_REQUIRE(valid && depth && rects && counts && gt_mask && masked, "null pointer");
-    DSR_REQUIRE(max_rects > 0 && max_rects <= 1024, "max_rects out of range");
-    int gx = dsr_cdiv((long)H * W, TPB);
-    int cap = dsr_num_sms() * 8 / (B > 0 ? B : 1);
-    if (cap < 1) cap = 1;
-    if (gx > cap) gx = cap;
-    dim3 grid(gx, B);
-    rect_holes_kernel<<<grid, TPB, max_rects * 4 * sizeof(int), ST(stream)>>>(valid, depth, rects, counts, max_rects,
-                                                                              H, W, extra_border, gt_mask, masked, extra);
-    return dsr_check_launch("rect_holes");
-}
-
-extern "C" int dsr_normals_old_fwd(const float* depth, int B, int H, int W, float scale, float* out, void* stream) {
-    DSR_REQUIRE(depth && out && H >= 2 && W >= 2, "bad arguments");
-    normals_old_fwd_kernel<<<dsr_grid((long)B * H * W, TPB), TPB, 0, ST(stream)>>>(depth, B, H, W, scale, out);
-    return dsr_check_launch("normals_old_fwd");
-}
-extern "C" int dsr_normals_old_bwd(const float* depth, const float* gout, int B, int H, int W, float scale,
-                                   float* gdepth, void* stream) {
-    DSR_REQUIRE(depth && gout && gdepth && H >= 2 && W >= 2, "bad arguments");
-    normals_old_bwd_kernel<<<dsr_grid((long)B * H * W, TPB), TPB, 0, ST(stream)>>>(depth, gout, B, H, W, scale, gdepth);
-    return dsr_check_launch("normals_old_bwd");
-}
-extern "C" int dsr_normals_new_fwd(const float* depth, const double* cams, int B, int H, int W, float* out,
-                                   void* stream) {
-    DSR_REQUIRE(depth && cams && out && H >= 2 && W >= 2, "bad arguments");
-    normals_new_fwd_kernel<<<dsr_grid((long)B * H * W, TPB), TPB, 0, ST(stream)>>>(depth, cams, B, H, W, out);
-    return dsr_check_launch("normals_new_fwd");
-}
-extern "C" int dsr_normals_new_bwd(const float* depth, const float* gout, const double* cams, int B, int H, int W,
-                                   float* gdepth, void* stream) {
-    DSR_REQUIRE(depth && gout && cams && gdepth && H >= 2 && W >= 2, "bad arguments");
-    normals_new_bwd_kernel<<<dsr_grid((long)B * H * W, TPB), TPB, 0, ST(stream)>>>(depth, gout, cams, B, H, W, gdepth);
-    return dsr_check_launch("normals_new_bwd");
-}
-
-extern "C" int dsr_tv_fwd(const float* x, long planes, int H, int W, double* out_sum, void* stream) {
-    DSR_REQUIRE(x && out_sum, "null pointer");
-    tv_fwd_kernel<<<dsr_grid(planes * H * W, TPB), TPB, 0, ST(stream)>>>(x, planes, H, W, out_sum);
-    return dsr_check_launch("tv_fwd");
-}
-extern "C" int dsr_tv_bwd(const float* x, long planes, int H, int W, const float* gscale, float coef, float* gx,
-                          void* stream) {
-    DSR_REQUIRE(x && gx, "null pointer");
-    tv_bwd_kernel<<<dsr_grid(planes * H * W, TPB), TPB, 0, ST(stream)>>>(x, planes, H, W, gscale, coef, gx);
-    return dsr_check_launch("tv_bwd");
-}
-
-extern "C" int dsr_masked_diff_fwd(const float* a, const float* b, const float* m1, const float* m2, int B, int C,
-                                   long plane, double* out2, void* stream) {
-    DSR_REQUIRE(a && b && m1 && out2, "null pointer");
-    masked_diff_fwd_kernel<<<dsr_grid((long)B * C * plane, TPB), TPB, 0, ST(stream)>>>(a, b, m1, m2, B, C, plane, out2);
-    return dsr_check_launch("masked_diff_fwd");
-}
-extern "C" int dsr_masked_diff_bwd(const float* a, const float* b, const float* m1, const float* m2, int B, int C,
-                                   long plane, const float* g_l1, const float* g_l2, float c1, float c2, float* gb,
-                                   void* stream) {
-    DSR_REQUIRE(a && b && m1 && gb, "null pointer");
-    masked_diff_bwd_kernel<<<dsr_grid((long)B * C * plane, TPB), TPB, 0, ST(stream)>>>(a, b, m1, m2, B, C, plane, g_l1,
-                                                                                        g_l2, c1, c2, gb);
-    return dsr_check_launch("masked_diff_bwd");
-}
 extern "C" int dsr_masked_sums(const float* d, const float* p, const float* m, long total, double* out3, void* stream) {
     DSR_REQUIRE(d && p && m && out3, "null pointer");
     masked_sums_kernel<<<dsr_grid(total, TPB), TPB, 0, ST(stream)>>>(d, p, m, total, out3);
@@ -451,20 +140,6 @@ extern "C" int dsr_bilinear_ac_bwd(const float* g, long planes, int H, int W, in
     bilinear_ac_bwd_kernel<<<dsr_grid(planes * nh * nw, TPB), TPB, 0, ST(stream)>>>(g, planes, H, W, nh, nw, gx);
     return dsr_check_launch("bilinear_ac_bwd");
 }
-extern "C" int dsr_smooth_level_fwd(const float* d, const float* img, int B, int C, int h, int w, double* out2,
-                                    void* stream) {
-    DSR_REQUIRE(d && img && out2, "null pointer");
-    smooth_level_fwd_kernel<<<dsr_grid((long)B * h * w, TPB), TPB, 0, ST(stream)>>>(d, img, B, C, h, w, out2);
-    return dsr_check_launch("smooth_level_fwd");
-}
-extern "C" int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
-                                    float cx, float cy, float* gd, int accumulate, void* stream) {
-    DSR_REQUIRE(d && img && gd, "null pointer");
-    smooth_level_bwd_kernel<<<dsr_grid((long)B * h * w, TPB), TPB, 0, ST(stream)>>>(d, img, B, C, h, w, gscale, cx, cy,
-                                                                                     gd, accumulate);
-    return dsr_check_launch("smooth_level_bwd");
-}
-
 extern "C" int dsr_ssim_fwd(const float* a, const float* b, long planes, int H, int W, double* out_sum, float* map,
                             void* stream) {
     DSR_REQUIRE(a && b && out_sum, "null pointer");
