@@ -380,7 +380,7 @@ __device__ __forceinline__ void point_diffs(const double* __restrict__ o, int LN
         dv[k][0] = d01.x - u01.x; dv[k][1] = d01.y - u01.y; dv[k][2] = d23.x - u23.x; dv[k][3] = d23.y - u23.y;
     }
 }
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 normals_new_fwd_quad(const float* __restrict__ d, const double* __restrict__ cams, int H, int W, float* __restrict__ out) {
     __shared__ __align__(16) double sP[3 * (TH + 2) * PW];
     constexpr int LN = (TH + 2) * PW;
@@ -414,7 +414,7 @@ normals_new_fwd_quad(const float* __restrict__ d, const double* __restrict__ cam
 // backward: stage P with a 2-pixel halo, phase 1 = per-pixel adjoints (dL/dPu, dL/dPv) of the tile + 1-pixel halo in
 // fp32 (column quads [j0 - 4, j0 + TW + 4), rows [i0 - 1, i0 + TH]), phase 2 = gather through np.gradient's taps and
 // project on the ray of the output pixel: dL/dz = sum c * (dPu . ray) + sum c * (dPv . ray), dL/dd = dL/dz / 2.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 normals_new_bwd_quad(const float* __restrict__ d, const float* __restrict__ g, const double* __restrict__ cams, int H, int W,
                      float* __restrict__ gd) {
     extern __shared__ __align__(16) double sP[];                 // [3][(TH+4)*PW] doubles, then [6][(TH+2)*PW] floats
@@ -652,7 +652,7 @@ masked_diff_bwd_v(const float* __restrict__ a, const float* __restrict__ b, cons
 // ------------------------------------------------------------------------------------------
 #define SM_MAXC 4
 __device__ __forceinline__ float sgnf(float s) { return (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f); }
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 smooth_fwd_quad(const float* __restrict__ d, const float* __restrict__ img, int C, int h, int w, double* __restrict__ out) {
     __shared__ double red[32];
     const int j = blockIdx.x * TW + ((threadIdx.x & 15) << 2);
@@ -665,6 +665,7 @@ smooth_fwd_quad(const float* __restrict__ d, const float* __restrict__ img, int 
     const float invC = 1.f / (float)C;
     float fx = 0.f, fy = 0.f;
     if (j < w) {
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int i = ibase + k;
             if (i >= h) break;
@@ -692,7 +693,7 @@ smooth_fwd_quad(const float* __restrict__ d, const float* __restrict__ img, int 
     if (threadIdx.x == 0) { atomicAdd(out, ax); atomicAdd(out + 1, ay); }
 }
 // gd (=|+=) g * (cx * d/dd sum|dx wx| + cy * d/dd sum|dy wy|)
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 smooth_bwd_quad(const float* __restrict__ d, const float* __restrict__ img, int C, int h, int w,
                 const float* __restrict__ gscale, float cx, float cy, float* __restrict__ gd, int accumulate) {
     const Quad q(h, w);
