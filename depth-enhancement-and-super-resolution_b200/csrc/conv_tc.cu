@@ -425,18 +425,37 @@ __device__ __forceinline__ void split16(float x, int f16, unsigned short& hi, un
         hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
     }
 }
+// two values -> packed 16-bit (hi, lo) pairs with the paired conversion instructions (cvt.rn.f16x2.f32 / bf16x2)
+__device__ __forceinline__ void split16x2(float x0, float x1, int f16, unsigned& hi, unsigned& lo) {
+    if (f16) {
+        x0 = fminf(fmaxf(x0, -65504.f), 65504.f); x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 b = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - b.x, x1 - b.y);
+        hi = *reinterpret_cast<const unsigned*>(&h); lo = *reinterpret_cast<const unsigned*>(&l);
+    } else {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+        const float2 b = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - b.x, x1 - b.y);
+        hi = *reinterpret_cast<const unsigned*>(&h); lo = *reinterpret_cast<const unsigned*>(&l);
+    }
+}
 // One block walks arranged rows (n, ha); one thread-item = 8 consecutive arranged channels of one arranged pixel (two
-// 16-byte loads, one 16-byte store per output plane).  The (mean, scale, shift) table of the fused norm-apply is staged
-// in shared memory per image; csum (optional) receives the per-source-channel sum of everything written (the bias
-// gradient when the tensor is dY), accumulated in shared memory per block and flushed with fp64 atomics.
+// 16-byte loads, one 16-byte store per output plane).  The kernel is instruction-bound, not memory-bound, so the item
+// decomposition uses multiply-high "magic" divisions (exact for the item counts involved: it * d < 2^32), the
+// (mean, scale, shift) table of the fused norm-apply is staged in shared memory per image and read with 16-byte loads,
+// and the hi/lo split uses the paired conversion instructions.  csum (optional) receives the per-source-channel sum of
+// everything written (the bias gradient when the tensor is dY), accumulated in shared memory per block and flushed with
+// fp64 atomics.
 __global__ void __launch_bounds__(256)
 tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm,
                int act, float slope, int pad, int mode, int layout, int Cp,
                unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, int Ha, int Wa, int Ca,
-               int f16, double* __restrict__ csum) {
-    extern __shared__ float prep_sm[];
+               int f16, double* __restrict__ csum, unsigned magic_cg, unsigned magic_cp, unsigned magic_ha) {
+    extern __shared__ __align__(16) float prep_sm[];
+    const int Cs = (C + 3) & ~3;                  // 16-byte aligned parameter rows
     float* s_prm = prep_sm;
-    float* s_sum = prep_sm + (prm ? 3 * C : 0);
+    float* s_sum = prep_sm + (prm ? 3 * Cs : 0);
     const int tid = threadIdx.x;
     const int cg = Ca >> 3, items = Wa * cg;
     const int Hq = H + 2 * pad, Wq = W + 2 * pad;
@@ -448,21 +467,25 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
     }
     int cached_n = -1;
     for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
-        const int n = row / Ha, ha = row - n * Ha;
+        const int n = magic_ha ? (int)__umulhi((unsigned)row, magic_ha) : row, ha = row - n * Ha;
         if (prm && n != cached_n) {
             __syncthreads();
             for (int i = tid; i < C; i += 256) {
-                s_prm[i] = prm[(long)n * C + i]; s_prm[C + i] = prm[NC + (long)n * C + i]; s_prm[2 * C + i] = prm[2 * NC + (long)n * C + i];
+                s_prm[i] = prm[(long)n * C + i]; s_prm[Cs + i] = prm[NC + (long)n * C + i]; s_prm[2 * Cs + i] = prm[2 * NC + (long)n * C + i];
             }
             cached_n = n;
             __syncthreads();
         }
         for (int it = tid; it < items; it += 256) {
-            const int wa = it / cg, q = (it - wa * cg) << 3;
+            const int wa = magic_cg ? (int)__umulhi((unsigned)it, magic_cg) : it, q = (it - wa * cg) << 3;
             int c, qi, qj;       // source channel start, padded-space row / col
             if (layout == DSR_TC_LAYOUT_NORMAL) { c = q; qi = ha; qj = wa; }
-            else if (layout == DSR_TC_LAYOUT_PAIR) { const int g = q / Cp; c = q - g * Cp; qi = ha; qj = wa + g; }
-            else { const int ab = q / Cp; c = q - ab * Cp; qi = 2 * ha + (ab >> 1); qj = 2 * wa + (ab & 1); }
+            else {
+                const int g = magic_cp ? (int)__umulhi((unsigned)q, magic_cp) : q;
+                c = q - g * Cp;
+                if (layout == DSR_TC_LAYOUT_PAIR) { qi = ha; qj = wa + g; }
+                else { qi = 2 * ha + (g >> 1); qj = 2 * wa + (g & 1); }
+            }
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -470,7 +493,8 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
                 const int i = prep_pad_src(qi, pad, H, mode), j = prep_pad_src(qj, pad, W, mode);
                 if (i >= 0 && j >= 0) {
                     const float* src = x + (long)((n * H + i) * W + j) * C + c;
-                    if (vec && c + 8 <= C) {
+                    const bool full = vec && c + 8 <= C;
+                    if (full) {
                         const float4 a = ld4(src), b4 = ld4(src + 4);
                         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
                     } else {
@@ -478,13 +502,25 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
                         for (int e = 0; e < 8; ++e) if (c + e < C) v[e] = src[e];
                     }
                     if (prm) {
+                        if (full) {
+                            float m[8], sc[8], sh[8];
+                            *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(s_prm + c);
+                            *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(s_prm + c + 4);
+                            *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(s_prm + Cs + c);
+                            *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(s_prm + Cs + c + 4);
+                            *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(s_prm + 2 * Cs + c);
+                            *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(s_prm + 2 * Cs + c + 4);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (c + e < C) v[e] = (v[e] - s_prm[c + e]) * s_prm[C + c + e] + s_prm[2 * C + c + e];
+                            for (int e = 0; e < 8; ++e) v[e] = (v[e] - m[e]) * sc[e] + sh[e];
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (c + e < C) v[e] = (v[e] - s_prm[c + e]) * s_prm[Cs + c + e] + s_prm[2 * Cs + c + e];
+                        }
                     }
                     if (act == DSR_ACT_RELU) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : 0.f;
+                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
                     } else if (act == DSR_ACT_LRELU) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : slope * v[e];
@@ -495,12 +531,12 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
                     }
                 }
             }
-            __align__(16) unsigned short hi[8], lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split16(v[e], f16, hi[e], lo[e]);
+            uint4 hi, lo;
+            split16x2(v[0], v[1], f16, hi.x, lo.x); split16x2(v[2], v[3], f16, hi.y, lo.y);
+            split16x2(v[4], v[5], f16, hi.z, lo.z); split16x2(v[6], v[7], f16, hi.w, lo.w);
             const long o = ((long)row * Wa + wa) * Ca + q;
-            *reinterpret_cast<uint4*>(Ahi + o) = *reinterpret_cast<const uint4*>(hi);
-            if (Alo) *reinterpret_cast<uint4*>(Alo + o) = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(Ahi + o) = hi;
+            if (Alo) *reinterpret_cast<uint4*>(Alo + o) = lo;
         }
     }
     if (csum) {
@@ -516,6 +552,9 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
 //   variant CONV_S2D : stride-2 conv (k <= 4) as 2x2 taps over 4*Cp channels: r = 2r'+a, s = 2s'+b
 //   variant CONV_DGRAD: Conv2d weight (Cout, Cin, R, S) for the stride-1 data gradient: GEMM output channel = ci,
 //                      K channel = co, tap t = (r', s') reads W[co][ci][R-1-r'][S-1-s']
+//   variant CONV_DGRAD_PAIR: the same data gradient for narrow layers (Cin = 32): GEMM row co' = dx*Cin + ci is output
+//                      channel ci of the pixel at column 2k + dx, the A operand is read as pixel PAIRS (Ca = 2*Cp):
+//                      tap t = (r', a), K channel q = b*Cp + co reads W[co][ci][R-1-r'][S-1-(2a+b-dx)] (zero outside)
 //   variant CONVT_PH : ConvTranspose2d weight (Cin, Cout, R, S), stride 2, phase (a,b): taps (dr,ds) in {0,1}^2,
 //                      kh = pad + 2 - a - 2*dr, kw = pad + 2 - b - 2*ds (zero tap when outside the kernel)
 // ------------------------------------------------------------------------------------------------
@@ -546,8 +585,17 @@ tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S,
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             int r, sx, c;
-            tc_map_k(variant, t, q8 * 8 + e, R, S, Cp, g, pa, pb, pad, r, sx, c);
             float v = 0.f;
+            if (variant == DSR_TC_W_CONV_DGRAD_PAIR) {
+                const int q = q8 * 8 + e, Sg = S / 2 + 1;
+                const int dx = co / D1, ci = co - dx * D1, rr = t / Sg, a = t - rr * Sg, b = q / Cp, cc = q - b * Cp;
+                const int sidx = 2 * a + b - dx;
+                if (sidx >= 0 && sidx < S && rr < R && cc < D0 && dx < 2)
+                    v = w[(((long)cc * D1 + ci) * R + (R - 1 - rr)) * S + (S - 1 - sidx)];
+                split16(v * wscale, f16, hi[e], lo[e]);
+                continue;
+            }
+            tc_map_k(variant, t, q8 * 8 + e, R, S, Cp, g, pa, pb, pad, r, sx, c);
             // convT-style indexing: the GEMM's K channel is the parameter's dim 0, its output channel dim 1
             if (r >= 0 && r < R && sx >= 0 && sx < S && c >= 0 && c < Cin)
                 v = convT ? w[(((long)c * D1 + co) * R + r) * S + sx] : w[(((long)co * D1 + c) * R + r) * S + sx];
@@ -625,9 +673,15 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
     const long rows = (long)N * Ha;
     const long cap = (long)dsr_num_sms() * 8;
     const int grid = (int)(rows < cap ? rows : cap);
-    const size_t smem = ((prm ? 3 * (size_t)C : 0) + (csum ? (size_t)C : 0)) * sizeof(float);
+    const size_t Cs = ((size_t)C + 3) & ~(size_t)3;
+    const size_t smem = ((prm ? 3 * Cs : 0) + (csum ? (size_t)C : 0)) * sizeof(float);
+    // floor(n / d) == umulhi(n, 2^32 / d + 1) whenever n * d < 2^32
+    auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / d + 1); };   // 0: divisor 1
+    DSR_REQUIRE((unsigned long long)Wa * (Ca >> 3) * (Ca >> 3) < (1ull << 32) && (unsigned long long)Ca * Cp < (1ull << 32) &&
+                    (unsigned long long)rows * Ha < (1ull << 32), "tensor too large for the magic-number index divisions");
     tc_prep_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
-                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16, csum);
+                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16, csum,
+                                                    magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha));
     return dsr_check_launch("tc_prep");
 }
 

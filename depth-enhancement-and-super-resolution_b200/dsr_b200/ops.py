@@ -195,10 +195,11 @@ CONFIG = {
     "tc_first_layers": True,
     "tc_compact_first": True,   # ... reading the 8-pixel K blocks from a compact 8-channel operand (no 8x expansion)   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
     "halo_min_tiles": 120,
+    "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
 _LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
-_W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH, _W_CONV_DGRAD = 0, 1, 2, 3, 4
+_W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH, _W_CONV_DGRAD, _W_CONV_DGRAD_PAIR = 0, 1, 2, 3, 4, 5
 
 
 W_SCALE = 64.0          # power-of-two weight scale of the f16 path: keeps the low half of N(0, 0.02)-sized weights normal
@@ -430,6 +431,27 @@ def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stat
     return y
 
 
+def _tc_dgrad_pair(gP, weight, padq, Hout, Wout, dt):
+    """Stride-1 data gradient of a Conv2d with few input channels (the 7x7 32 -> 128 head of the ResNets), written as a
+    GEMM whose rows are PAIRS of horizontally adjacent output pixels: N = 2 * Cin = 64 runs the tensor pipe at full rate
+    where N = 32 runs at half, for (S/2 + 1) * 2 / S = 8/7 of the MACs.  The zero-padded dY (N, Ha, Wa, Co) is read
+    through the view (N, Ha, Wa/2, 2*Co) - no copy - and the (N, Hout, Wout, Cin) output through (N, Hout, Wout/2, 2*Cin)."""
+    N, Ho, Wo, Co = gP.shape
+    _, Ci, R, S = weight.shape
+    a_plan = dict(layout=_LAYOUT_NORMAL, Cp=Co, Ca=Co)
+    ahi, alo, Ha, Wa = _tc_prep(gP, a_plan, padq, PAD_ZERO, dtype=dt)
+    Sg = S // 2 + 1
+    T = R * Sg
+    w_plan = dict(variant=_W_CONV_DGRAD_PAIR, Cp=Co, Ca=2 * Co, T=T)
+    whi, wlo = _tc_weights(weight, w_plan, 2 * Ci, dtype=dt)
+    dr, ds = [t // Sg for t in range(T)], [t % Sg for t in range(T)]
+    y = torch.empty((N, Hout, Wout, Ci), device=gP.device, dtype=torch.float32)
+    _lib.PROFILE_META = dict(macs=N * Hout * Wout * Co * Ci * R * S, shape=(N, Hout, Wout, Co, Ci, R, 1))
+    _tc_gemm(ahi, alo, N, Ha, Wa // 2, 2 * Co, whi, wlo, 2 * Ci, T, _int_array(dr), _int_array(ds), 0, 0, Hout, Wout // 2,
+             None, y, Hout, Wout // 2, 1, 0, 0, ACT_NONE, dt, CONFIG["split_k"])
+    return y
+
+
 def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
     """dL/dx of a Conv2d on the tcgen05 path (None when the shape is not covered).  g: (N,Ho,Wo,Co)."""
     if not CONFIG["tc_backward"]:
@@ -443,9 +465,16 @@ def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
             return None
         plan = dict(plan, variant=_W_CONV_DGRAD)
         macs = N * Ho * Wo * Co * Ci * R * S
+        pair = (CONFIG["dgrad_pair"] and Ci <= 32 and Ci % 8 == 0 and Co % 64 == 0 and W % 2 == 0 and Wo % 2 == 0
+                and isinstance(g, _Prepared) and S >= 3 and R * (S // 2 + 1) <= 64 and (W + 2 * pad) // 2 >= 8)
         if pad_mode == PAD_ZERO or pad == 0:          # gradient w.r.t. the un-padded input directly
+            if pair:
+                return _tc_dgrad_pair(g, weight, R - 1 - pad, H, W, dt)
             return _tc_conv_fwd(g, weight, None, plan, 1, R - 1 - pad, PAD_ZERO, ACT_NONE, H, W, dtype=dt, Co=Ci, macs=macs)
-        gxp = _tc_conv_fwd(g, weight, None, plan, 1, R - 1, PAD_ZERO, ACT_NONE, H + 2 * pad, W + 2 * pad, dtype=dt, Co=Ci, macs=macs)
+        if pair:
+            gxp = _tc_dgrad_pair(g, weight, R - 1, H + 2 * pad, W + 2 * pad, dt)
+        else:
+            gxp = _tc_conv_fwd(g, weight, None, plan, 1, R - 1, PAD_ZERO, ACT_NONE, H + 2 * pad, W + 2 * pad, dtype=dt, Co=Ci, macs=macs)
         gx = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
         _call("dsr_pad2d_bwd", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode)
         return gx

@@ -160,6 +160,7 @@ int dsr_conv_out1(const float* x, int N, int H, int W, int C, const float* prm, 
 #define DSR_TC_W_CONV_S2D 2
 #define DSR_TC_W_CONVT_PH 3
 #define DSR_TC_W_CONV_DGRAD 4
+#define DSR_TC_W_CONV_DGRAD_PAIR 5   /* stride-1 data gradient producing 2 adjacent pixels x Cin outputs per GEMM row (N = 2*Cin) */
 int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
                 int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
                 double* csum /* optional: += per-channel sums of x (bias gradient of a dY), pre-zeroed */, void* stream);
