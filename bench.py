@@ -25,6 +25,8 @@ WORKLOADS = {   # BASELINE.json configs[1] / configs[2]
     # BASELINE.json configs[3] at the reference's native x2 (main_sr_model.py; README.md:86 uses batch 1): H, W = LR crop
     # (the U-Net-128 of Image2Depth needs LR sides that are multiples of 128, so 256x320 -> 512x640 cannot run in the reference)
     "c4": dict(B=1, H=512, W=640, sr=True, name="main_sr_model x2 depth super-resolution step (LR 512x640 -> HR 1024x1280, README.md:86), batch 1 per GPU"),
+    # BASELINE.json configs[0] (the reference's own CPU-runnable case), on the GPU: I2D_model.py, README.md:28 flags
+    "c1": dict(B=2, H=256, W=256, i2d=True, name="I2D Image Guidance Network training step, batch 2, 256x256"),
     "tiny": dict(B=1, H=128, W=128, name="debug"),
 }
 FLOP_PER_PAIR_256 = 606.2e9      # 2*174.68 + 4*64.20 GMAC-pairs
@@ -35,13 +37,18 @@ FLOP_SR_LR_256 = 2e9 * (43.84 + 16.11)
 
 def step_flops(wl):
     px = wl["H"] * wl["W"] / 65536.0
+    if wl.get("i2d"):        # Image_f forward (21.92 GMAC) + Task U-Net 128->1 forward + dgrad + wgrad (8.05 GMAC each) per image, 2 images per pair
+        return wl["B"] * 2 * 2e9 * (21.92 + 3 * 8.05) * px
     if wl.get("sr"):
         return wl["B"] * (FLOP_SR_HR_256 * 4 * px + FLOP_SR_LR_256 * px)
     return wl["B"] * FLOP_PER_PAIR_256 * px
 
 
 def make_model(wl, gpu_ids, graph, name="bench"):
-    from dsr_b200 import main_model, main_sr_model, options
+    from dsr_b200 import I2D_model, main_model, main_sr_model, options
+    if wl.get("i2d"):
+        return I2D_model.I2DModel(options.i2d_flags(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"], crop_size_w=wl["W"],
+                                                    name=name, checkpoints_dir="/tmp/dsr_bench"))
     kw = dict(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"], crop_size_w=wl["W"], name=name,
               checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(graph))
     if wl.get("sr"):       # README.md:86
@@ -109,17 +116,20 @@ def ncu_traffic(kernel):
     return None
 
 
-def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False):
+def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False):
     """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
     import numpy as np
     import torch
     from oracle import ref_step
-    wl = dict(B=B, H=H, W=W, sr=sr)
+    wl = dict(B=B, H=H, W=W, sr=sr, i2d=i2d)
     if sds is None:
         torch.manual_seed(0)
         host = make_model(wl, [], False, name="cpu")
         sds = {n: getattr(host, "net" + n).state_dict() for n in host.model_names}
-    orc = ref_step.OracleSRStep(sds, (H, W), lr=2e-5) if sr else ref_step.OracleStep(sds, lr=1e-4)
+    if i2d:
+        orc = ref_step.OracleI2DStep(sds, lr=2e-4)
+    else:
+        orc = ref_step.OracleSRStep(sds, (H, W), lr=2e-5) if sr else ref_step.OracleStep(sds, lr=1e-4)
     batch = make_batch(wl, 1)
     np.random.seed(0)
     ts = []
@@ -139,7 +149,7 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     Bs = min(wl["B"], 2)                      # bounded sample: B=2 of the workload's crops per step
-    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")))
+    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")))
     line = dict(impl="reference", metric="RGB-D train pair-samples/sec (main net)", value=r["value"], unit="pair-samples/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * r["s_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -214,7 +224,9 @@ def run_ours(args):
     dev_batches = [{k: (v.cuda() if torch.is_tensor(v) and v.dtype == torch.float32 else v) for k, v in b.items()}
                    for b in host_batches]
     np.random.seed(1234 + rank)
-    h2d = sum(host_batches[0][k].numel() * 4 for k in ("A_i", "B_i", "A_d", "B_d")) + 2 * B * 11 * 8 + 2 * B * (64 * 4 + 1) * 4
+    h2d = sum(host_batches[0][k].numel() * 4 for k in ("A_i", "B_i", "A_d", "B_d"))
+    if not wl.get("i2d"):
+        h2d += 2 * B * 11 * 8 + 2 * B * (64 * 4 + 1) * 4          # camera tables + rectangle tables
 
     def barrier():
         torch.cuda.synchronize()
@@ -327,11 +339,11 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             Bc = min(B, 2)
-            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")))
+            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")))
             cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
                        sample=f"2 steps of batch {Bc} at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
         extras = None
-        if args.inference and not wl.get("sr") and world == 1:
+        if args.inference and not wl.get("sr") and not wl.get("i2d") and world == 1:
             extras = inference_ms_per_frame(local)
         line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
                     unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,

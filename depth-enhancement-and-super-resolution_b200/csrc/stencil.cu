@@ -119,11 +119,22 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, 
     if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
+// valid-depth mask of the Image Guidance step (models/I2D_model.py:223,226): out = (d < thr) ? 0 : 1
+__global__ void below_mask_kernel(const float* __restrict__ d, long n, float thr, float* __restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = (d[i] < thr) ? 0.f : 1.f;
+}
+
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
 #define ST(s) ((cudaStream_t)(s))
 
+extern "C" int dsr_below_mask(const float* depth, long n, float thr, float* out, void* stream) {
+    DSR_REQUIRE(depth && out && n > 0, "bad arguments");
+    below_mask_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(depth, n, thr, out);
+    return dsr_check_launch("below_mask");
+}
 extern "C" int dsr_masked_sums(const float* d, const float* p, const float* m, long total, double* out3, void* stream) {
     DSR_REQUIRE(d && p && m && out3, "null pointer");
     masked_sums_kernel<<<dsr_grid(total, TPB), TPB, 0, ST(stream)>>>(d, p, m, total, out3);

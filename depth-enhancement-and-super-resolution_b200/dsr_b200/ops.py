@@ -1078,6 +1078,14 @@ def hole_valid_masks(depth, border=-0.97):
     return hole, valid
 
 
+def below_mask(depth, thr):
+    """-> float32 {0,1}: 0 where depth < thr.  I2D_model.py:223,226."""
+    d = planes(depth.detach())
+    out = torch.empty_like(d)
+    _call("dsr_below_mask", _p(d), d.numel(), float(thr), _p(out))
+    return out
+
+
 def rect_holes(valid, depth, rects_dev, counts_dev, max_rects, extra_border=float("-inf")):
     """-> (gt_mask uint8, masked depth, extra-hole mask).  main_model.py:257-298, :354-357, :396."""
     v, d = planes(valid), planes(depth.detach())

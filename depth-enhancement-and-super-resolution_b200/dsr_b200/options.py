@@ -22,6 +22,7 @@ _DEFAULTS = dict(
     w_real_l1_d=1.0, w_real_l1_i=0.1, w_smooth=0.1, ImageDepthf_outf=128, ImageDepthf_basef=32,
     ImageDepthf_type="resnet_6blocks", I2D_base=64, I2D_type="unet_128", scale_G=1.0, use_edge=False,
     use_masked=False, crop_size_h=384, crop_size_w=512, lambda_identity=0.5, isTrain=True,
+    Imagef_ndown=2, Imagef_basef=32, Imagef_outf=16, Imagef_type="resnet_6blocks", w_real_l1=0.1, use_D=False, pool_size=50,
 )
 
 
@@ -29,6 +30,14 @@ def default_opt(**overrides):
     d = dict(_DEFAULTS)
     d.update(overrides)
     return SimpleNamespace(**d)
+
+
+def i2d_flags(**overrides):
+    """README.md:28 - the published Image Guidance Network (``--model I2D``) training command."""
+    d = dict(model="I2D", model_type="I2D", w_real_l1=1.0, w_syn_l1=1.0, lr=0.0002, Imagef_outf=128, Imagef_basef=32,
+             norm_loss=True, batch_size=12, crop_size_h=256, crop_size_w=256)
+    d.update(overrides)
+    return default_opt(**d)
 
 
 def main_flags(**overrides):

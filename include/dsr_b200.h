@@ -41,6 +41,8 @@ int dsr_device_arch(void);      /* 100 on B200 */
 /* hole = 1[d <= border], valid = 1 - dilate3x3(hole).  models/main_model.py:208-230.  hole may be NULL. */
 int dsr_hole_valid_masks(const float* depth, int B, int H, int W, float border, float* hole, float* valid,
                          void* stream);
+/* out = (depth < thr) ? 0 : 1: the valid-depth mask of the Image Guidance step, models/I2D_model.py:223,226. */
+int dsr_below_mask(const float* depth, long n, float thr, float* out, void* stream);
 /* random rectangle holes.  models/main_model.py:257-298 (+ :354-357, :396 for `extra`).
  * rects int32 [B][max_rects][4] = (x, y, size_x, size_y), counts int32 [B] (both device).
  * gt_mask u8 {0,1}; masked = gt ? depth : -1; extra = 1[(masked < extra_border) || !gt] (may be NULL). */

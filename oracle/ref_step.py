@@ -145,6 +145,53 @@ class OracleSRStep(OracleStep):
         return dict(tensors=t, losses=losses, visuals=visuals, grads=grads)
 
 
+class OracleI2DStep:
+    """One ``I2DModel.optimize_parameters`` step (models/I2D_model.py:163-250): Image_f + Task on the syn and the real
+    image, masked L1 (mask = depth >= -0.97, :223-227), Adam over netTask only (:143).  Image_f's own gradients are never
+    used by the reference (no optimizer owns them), so they are not computed here."""
+
+    def __init__(self, state_dicts, lr=2e-4, w_syn_l1=1.0, w_real_l1=1.0, scale_G=1.0):
+        self.sd = {k: collections.OrderedDict((n, t.detach().clone().float()) for n, t in v.items())
+                   for k, v in state_dicts.items()}
+        self.lr, self.w = lr, (w_syn_l1, w_real_l1, scale_G)
+        self.n_step = 0
+        self.adam = {}
+        for n, p in self.sd["Task"].items():
+            p.requires_grad_(True)
+            self.adam[n] = (torch.zeros_like(p), torch.zeros_like(p))
+
+    def step(self, batch, update=True):
+        for p in self.sd["Task"].values():
+            p.grad = None
+        t = {}
+        t["syn_image"], t["real_image"] = batch["A_i"].float(), batch["B_i"].float()
+        t["syn_depth"], t["real_depth"] = batch["A_d"].float(), batch["B_d"].float()
+        with torch.no_grad():
+            f_syn = ref_nets.resnet_generator(self.sd["Image_f"], t["syn_image"])
+            f_real = ref_nets.resnet_generator(self.sd["Image_f"], t["real_image"])
+        t["pred_syn_depth"] = ref_nets.unet_generator(self.sd["Task"], f_syn)
+        t["pred_real_depth"] = ref_nets.unet_generator(self.sd["Task"], f_real)
+        L = {}
+        L["syn_norms"] = ref_ops.l1_mean(ref_ops.surface_normals_old(t["syn_depth"]),
+                                         ref_ops.surface_normals_old(t["pred_syn_depth"].detach()))        # :217 (not in loss_G)
+        m_s = torch.where(t["syn_depth"] < -0.97, torch.tensor(0.0), torch.tensor(1.0))                  # :223
+        L["task_syn"] = ref_ops.l1_mean(t["syn_depth"] * m_s, t["pred_syn_depth"] * m_s)
+        m_r = torch.where(t["real_depth"] < -0.97, torch.tensor(0.0), torch.tensor(1.0))                 # :226
+        L["task_real"] = ref_ops.l1_mean(t["real_depth"] * m_r, t["pred_real_depth"] * m_r)
+        G = (L["task_syn"] * self.w[0] + L["task_real"] * self.w[1]) * self.w[2]                         # :230-234
+        G.backward()
+        grads = {n: p.grad.detach().clone() for n, p in self.sd["Task"].items()}
+        if update:
+            self.n_step += 1
+            with torch.no_grad():
+                for n, p in self.sd["Task"].items():
+                    m, v = self.adam[n]
+                    ref_ops.adam_update(p, p.grad, m, v, self.n_step, self.lr)
+        losses = {k: float(v) for k, v in L.items()}
+        losses["G"] = float(G)
+        return dict(tensors=t, losses=losses, grads=grads)
+
+
 def synthetic_sr_batch(B, h, w, seed=1, depth_kind="smooth"):
     """HR (2h x 2w) synthetic batch with the K / crop conventions of data/my_naive_sr_dataset.py:190-207:
     K_A scaled by [[2,1,2],[1,2,2],[1,1,1]], crop_A = HR extent, crop_B = LR extent."""

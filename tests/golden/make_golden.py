@@ -155,6 +155,47 @@ def golden_sr_step(B=1, h=128, w=128, tag="sr_step_b1_128"):
     print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
 
 
+def golden_i2d_step(B=2, H=128, W=128, tag="i2d_step_b2_128"):
+    """Two I2DModel steps (models/I2D_model.py), flags of README.md:28, B = 2 at 128x128."""
+    sys.argv = ["main.py", "--gpu_ids", "-1", "--image_and_depth", "--custom_pathes", "--w_real_l1", "1", "--w_syn_l1", "1",
+                "--lr", "0.0002", "--Imagef_outf", "128", "--Imagef_basef", "32", "--use_scannet", "--model", "I2D",
+                "--norm_loss", "--do_train", "--batch_size", str(B), "--name", "golden_i2d",
+                "--checkpoints_dir", "/tmp/golden/ckpt", "--crop_size_h", str(H), "--crop_size_w", str(W)]
+    from options.train_options import TrainOptions
+    opt = TrainOptions().parse()
+    from models.I2D_model import I2DModel
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = I2DModel(opt)
+    model.setup(opt)
+    model._train()
+    out = {}
+    for name in model.model_names:
+        sd = getattr(model, "net" + name).state_dict()
+        out[f"wsum/{name}"] = np.array([float(sum(v.double().sum() for v in sd.values())),
+                                        float(sum(v.double().abs().sum() for v in sd.values())),
+                                        float(sum(v.numel() for v in sd.values()))])
+        out[f"wkeys/{name}"] = np.array(list(sd.keys()))
+    batch = synthetic_batch(B, H, W, seed=1, depth_kind="smooth")
+    for it in range(2):
+        model.set_input(batch)
+        model.optimize_parameters(it)
+        p = f"s{it}/"
+        for k, v in model.get_current_losses().items():
+            out[p + "loss/" + k] = np.float64(v)
+        out[p + "loss/G"] = np.float64(float(model.loss_G))
+        for k in ("pred_syn_depth", "pred_real_depth"):
+            out[p + k] = getattr(model, k).detach().numpy().astype(np.float32)
+        if it == 0:
+            gi = 0
+            for n, prm in model.netTask.named_parameters():
+                g = prm.grad.detach().double().flatten()
+                out[p + f"gstat/Task/{n}"] = np.array([float(g.norm()), float(g @ proj_vec(g.numel(), 1000 + gi))])
+                gi += 1
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
+
+
 def golden_resize():
     """F.interpolate bicubic / nearest vectors (the torch calls of main_sr_model.py:279-293, :361, :394-398)."""
     import torch.nn.functional as F
@@ -217,7 +258,7 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -227,3 +268,5 @@ if __name__ == "__main__":
         golden_resize()
     if "sr" in which:
         golden_sr_step()
+    if "i2d" in which:
+        golden_i2d_step()
