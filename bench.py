@@ -48,7 +48,7 @@ def make_model(wl, gpu_ids, graph, name="bench"):
     from dsr_b200 import I2D_model, main_model, main_sr_model, options
     if wl.get("i2d"):
         return I2D_model.I2DModel(options.i2d_flags(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"], crop_size_w=wl["W"],
-                                                    name=name, checkpoints_dir="/tmp/dsr_bench"))
+                                                    name=name, checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(graph)))
     kw = dict(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"], crop_size_w=wl["W"], name=name,
               checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(graph))
     if wl.get("sr"):       # README.md:86

@@ -42,22 +42,35 @@ __global__ void transpose_cp_kernel(const float* __restrict__ x, float* __restri
 }
 
 // strided channel-block copy: dst[p][doff + c] (=|+=) src[p][soff + c], c < nC   (concat / slice)
+// (division-free: one warp walks the channels of one pixel; for a handful of channels one lane owns one pixel)
 __global__ void copy_channels_kernel(const float* __restrict__ src, int srcC, int soff, float* __restrict__ dst,
                                      int dstC, int doff, int nC, long npix, int accumulate) {
-    long total = npix * nC;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long p = idx / nC; int c = (int)(idx - p * nC);
-        float v = src[p * srcC + soff + c];
-        float* d = dst + p * dstC + doff + c;
-        if (accumulate) *d += v; else *d = v;
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+    if (nC <= 8) {
+        for (long p = tid; p < npix; p += nthr) {
+            const float* s = src + p * srcC + soff;
+            float* d = dst + p * dstC + doff;
+            for (int c = 0; c < nC; ++c) { if (accumulate) d[c] += s[c]; else d[c] = s[c]; }
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    for (long p = tid >> 5; p < npix; p += nthr >> 5) {
+        const float* s = src + p * srcC + soff;
+        float* d = dst + p * dstC + doff;
+        for (int c = lane; c < nC; c += 32) { if (accumulate) d[c] += s[c]; else d[c] = s[c]; }
     }
 }
 __global__ void copy_channels_vec4_kernel(const float4* __restrict__ src, int srcC4, int soff4, float4* __restrict__ dst,
                                           int dstC4, int doff4, int nC4, long npix) {
-    long total = npix * nC4;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        long p = idx / nC4; int c = (int)(idx - p * nC4);
-        dst[p * dstC4 + doff4 + c] = src[p * srcC4 + soff4 + c];
+    // G lanes walk the float4 groups of one pixel (G = 8, 16 or 32 by channel count): no per-item divisions
+    const int G = nC4 >= 32 ? 32 : (nC4 >= 16 ? 16 : 8), sh = nC4 >= 32 ? 5 : (nC4 >= 16 ? 4 : 3);
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+    const int lane = (int)(tid & (G - 1));
+    for (long p = tid >> sh; p < npix; p += nthr >> sh) {
+        const float4* s = src + p * srcC4 + soff4;
+        float4* d = dst + p * dstC4 + doff4;
+        for (int c = lane; c < nC4; c += G) d[c] = s[c];
     }
 }
 
@@ -295,30 +308,41 @@ norm_apply_fwd_vec4_kernel(const float4* __restrict__ x, const float* __restrict
         y[base + i] = v;
     }
 }
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)).  The per-(n, c) constants (mean, rstd, and the two fp64 sums turned
+// into fp32 means) are staged once per block in shared memory; the old form re-read 8 doubles and converted them per
+// 16-byte item and ran at 39 % of HBM peak.
 __global__ void __launch_bounds__(256)
 in_apply_bwd_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float* __restrict__ prm,
                          const double* __restrict__ sums2, float4* __restrict__ dx, int N, int P, int C4, int act) {
-    const int n = blockIdx.y;
-    const long NC = (long)N * C4 * 4;
-    const float* pm = prm + (long)n * C4 * 4;
-    const double* s2 = sums2 + (long)n * C4 * 8;
+    extern __shared__ __align__(16) float s_c[];          // [4][C]: mean, rstd, m1, m2
+    const int n = blockIdx.y, C = C4 * 4;
+    const long NC = (long)N * C;
+    const float invP = 1.f / (float)P;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        s_c[c] = prm[(long)n * C + c];
+        s_c[C + c] = prm[NC + (long)n * C + c];
+        s_c[2 * C + c] = (float)sums2[((long)n * C + c) * 2] * invP;
+        s_c[3 * C + c] = (float)sums2[((long)n * C + c) * 2 + 1] * invP;
+    }
+    __syncthreads();
     const long base = (long)n * P * C4;
     const int total = P * C4;
-    const float invP = 1.f / (float)P;
+    const bool pow2 = (C4 & (C4 - 1)) == 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int c = (i % C4) * 4;
-        const float4 m = ld4(pm + c), rs = ld4(pm + NC + c);
+        const int c = (pow2 ? (i & (C4 - 1)) : (i % C4)) * 4;
+        const float4 m = *reinterpret_cast<const float4*>(s_c + c), rs = *reinterpret_cast<const float4*>(s_c + C + c);
+        const float4 a1 = *reinterpret_cast<const float4*>(s_c + 2 * C + c), a2 = *reinterpret_cast<const float4*>(s_c + 3 * C + c);
         const float4 xv = x[base + i], g4 = dy[base + i];
         const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
         const float ms[4] = {m.x, m.y, m.z, m.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+        const float m1[4] = {a1.x, a1.y, a1.z, a1.w}, m2[4] = {a2.x, a2.y, a2.z, a2.w};
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float xh = (xs[k] - ms[k]) * rr[k];
             float g = gs[k];
             if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
-            const float m1 = (float)s2[(c + k) * 2] * invP, m2 = (float)s2[(c + k) * 2 + 1] * invP;
-            o[k] = rr[k] * (g - m1 - xh * m2);
+            o[k] = rr[k] * (g - m1[k] - xh * m2[k]);
         }
         dx[base + i] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -489,11 +513,11 @@ extern "C" int dsr_copy_channels(const float* src, int srcC, int soff, float* ds
     bool vec = !accumulate && !(srcC & 3) && !(dstC & 3) && !(soff & 3) && !(doff & 3) && !(nC & 3) &&
                !((uintptr_t)src & 15) && !((uintptr_t)dst & 15);
     if (vec)
-        copy_channels_vec4_kernel<<<dsr_grid(npix * (nC / 4), TPB), TPB, 0, ST(stream)>>>(
+        copy_channels_vec4_kernel<<<dsr_grid(npix * (nC / 4 >= 32 ? 32 : (nC / 4 >= 16 ? 16 : 8)), TPB), TPB, 0, ST(stream)>>>(
             (const float4*)src, srcC / 4, soff / 4, (float4*)dst, dstC / 4, doff / 4, nC / 4, npix);
     else
-        copy_channels_kernel<<<dsr_grid(npix * nC, TPB), TPB, 0, ST(stream)>>>(src, srcC, soff, dst, dstC, doff, nC,
-                                                                                npix, accumulate);
+        copy_channels_kernel<<<dsr_grid(nC <= 8 ? npix : npix * 32, TPB), TPB, 0, ST(stream)>>>(src, srcC, soff, dst, dstC, doff, nC,
+                                                                                                 npix, accumulate);
     return dsr_check_launch("copy_channels");
 }
 extern "C" int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, int mode, void* stream) {
@@ -551,7 +575,7 @@ extern "C" int dsr_norm_apply_fwd(const float* x, const float* prm, const float*
                                   int act, void* stream) {
     DSR_REQUIRE(x && prm && y, "null pointer");
     const bool vec = !(C & 3) && !((uintptr_t)x & 15) && !((uintptr_t)y & 15) && !((uintptr_t)res & 15) && !((uintptr_t)prm & 15) &&
-                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31);
+                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31) && C <= 2048;       // 4 C floats of shared memory
     if (vec) {
         const long items = P * (C / 4);
         long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
@@ -581,12 +605,12 @@ extern "C" int dsr_in_bwd_apply(const float* x, const float* dy, const float* pr
                                 int N, long P, int C, int act, void* stream) {
     DSR_REQUIRE(x && dy && prm && sums2 && dx, "null pointer");
     const bool vec = !(C & 3) && !((uintptr_t)x & 15) && !((uintptr_t)dy & 15) && !((uintptr_t)dx & 15) && !((uintptr_t)prm & 15) &&
-                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31);
+                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31) && C <= 2048;       // 4 C floats of shared memory
     if (vec) {
         const long items = P * (C / 4);
         long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
         if (gx > cap) gx = cap;
-        in_apply_bwd_vec4_kernel<<<dim3((unsigned)gx, (unsigned)N), 256, 0, ST(stream)>>>((const float4*)x, (const float4*)dy, prm, sums2,
+        in_apply_bwd_vec4_kernel<<<dim3((unsigned)gx, (unsigned)N), 256, 4 * (size_t)C * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, sums2,
                                                                                          (float4*)dx, N, (int)P, C / 4, act);
     } else {
         in_apply_bwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, sums2, dx, N, P, C, act);

@@ -56,7 +56,10 @@ class I2DModel(BaseModel):
         self.arena = None
         self.grad_sync = None
         self._in = None
-        self.use_graph, self.graph_warmup = False, 0     # eager launches (the step is ~250 library calls)
+        # CUDA-graph replay of the whole step, as in MainModel (persistent inputs, device-side Adam state)
+        self.use_graph = bool(getattr(opt, "cuda_graph", False))
+        self.graph_warmup = 2
+        self._graph, self._gstream, self._eager_steps, self.graph_launches = None, None, 0, 0
         if self.isTrain:
             if self.gpu_ids:
                 self.arena = ParamArena([self._unwrap(self.netTask)], self.device)
@@ -72,6 +75,8 @@ class I2DModel(BaseModel):
         self.image_paths = input["A_paths" if AtoB else "B_paths"]
         shapes = {k: tuple(v.shape) for k, v in src.items()}
         if self._in is None or self._in["shapes"] != shapes:
+            if getattr(self, "_graph", None) is not None:
+                raise RuntimeError("dsr_b200: the captured CUDA graph is bound to the first batch shape; call reset_graph()")
             self._in = dict(shapes=shapes)
             for k, v in src.items():
                 self._in[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
@@ -113,7 +118,38 @@ class I2DModel(BaseModel):
             self.loss_G.backward()
 
     def optimize_parameters(self, iters=0, fr=700):                 # I2D_model.py:237-250
-        self._step_body()
+        if not (self.use_graph and self.device.type == "cuda" and self.isTrain):
+            return self._step_body()
+        from . import _lib
+        cur = torch.cuda.current_stream()
+        if self._graph is None:
+            if self._gstream is None:
+                self._gstream = torch.cuda.Stream()
+            gs = self._gstream
+            gs.wait_stream(cur)
+            with torch.cuda.stream(gs):     # warm-up and capture on ONE stream (autograd remembers each node's stream)
+                if self._eager_steps < self.graph_warmup:
+                    self._eager_steps += 1
+                    self._step_body()
+                    cur.wait_stream(gs)
+                    return
+                for k, v in list(vars(self).items()):
+                    if torch.is_tensor(v) and v.grad_fn is not None:
+                        setattr(self, k, v.detach())
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0 = _lib.LAUNCHES
+                with torch.cuda.graph(graph, stream=gs):
+                    self._step_body()
+                self._graph, self.graph_launches = graph, _lib.LAUNCHES - l0
+            cur.wait_stream(gs)
+        self.optimizer_G.sync_hyper()
+        self._graph.replay()
+        _lib.LAUNCHES += self.graph_launches
+        ops.WEIGHT_EPOCH += 1
+
+    def reset_graph(self):
+        self._graph, self._eager_steps = None, 0
 
     def _step_body(self):
         if self.device.type == "cuda":

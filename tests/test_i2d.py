@@ -91,3 +91,30 @@ def test_i2d_step_matches_reference_golden_and_oracle(built_lib):
             assert cosine(torch.cat(fa), torch.cat(fb)) >= 0.999
     vis = model.get_current_visuals()
     assert all(k in vis for k in model.visual_names)
+
+
+@pytest.mark.gpu
+def test_i2d_graph_replay_matches_eager(built_lib):
+    """same weights, same batch: the replayed step's loss equals the eager step's"""
+    from dsr_b200 import ops
+    batch = ref_step.synthetic_batch(2, 128, 128, seed=3, depth_kind="smooth")
+    model, _ = _host_model(gpu_ids=[0])
+    model._train()
+    model.use_graph = True
+    for it in range(4):                                  # 2 eager warm-up steps, capture + replay, one more replay
+        model.set_input(batch)
+        model.optimize_parameters(it)
+    assert model._graph is not None and model.optimizer_G.n_steps == 4
+    state = (model.arena.flat, model.arena.exp_avg, model.arena.exp_avg_sq, model.optimizer_G.step_dev)
+    snap = [t.clone() for t in state]
+    out = []
+    for use_graph in (True, False):
+        for t, s0 in zip(state, snap):
+            t.copy_(s0)
+        ops.WEIGHT_EPOCH += 1
+        model.use_graph = use_graph
+        model.set_input(batch)
+        model.optimize_parameters(9)
+        out.append((float(model.loss_G), model.pred_real_depth.detach().clone()))
+    assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[1][0])
+    assert rel_l2(out[0][1].cpu(), out[1][1].cpu()) <= 1e-5
