@@ -307,6 +307,8 @@ def run_ours(args):
         total_ms = sum(d["ms"] for d in prof.values())
         top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
         mult = {1: 1, 2: 2, 3: 3}[args.passes]
+        wmult = min(mult, int(ops.CONFIG["wgrad_passes"]))          # the weight-gradient GEMM issues fewer passes
+        passes_of = dict(dsr_tc_gemm=mult, dsr_tc_gemm2=mult, dsr_tc_gemm3=mult, dsr_tc_wgrad=wmult)
         gemm_calls = {k: d for k, d in prof.items() if k in ("dsr_tc_gemm", "dsr_tc_gemm2", "dsr_tc_gemm3", "dsr_tc_wgrad") and d["n"]}
         kernel_of = dict(dsr_tc_gemm="conv_tc_kernel", dsr_tc_gemm2="conv_tc2_kernel", dsr_tc_gemm3="conv_tc3_kernel",
                          dsr_tc_wgrad="wgrad_tc_kernel")
@@ -322,9 +324,11 @@ def run_ours(args):
                         traffic=tr["bytes_per_launch"] if tr else None, traffic_source=tr,
                         peak_source=pk_src + " (sustained: timed inside a long step)",
                         launches_per_step=tc["n"], avg_launch_us=1e3 * tc["ms"] / tc["n"], share_of_step=tc["ms"] / total_ms,
-                        mma_passes=mult, executed_tflops=achieved * mult, executed_frac=achieved * mult / pk["bf16_tflops_sustained"],
+                        mma_passes=passes_of[dom], executed_tflops=achieved * passes_of[dom],
+                        executed_frac=achieved * passes_of[dom] / pk["bf16_tflops_sustained"],
                         all_tcgen05_gemms=dict(share_of_step=fam_ms / total_ms, achieved=2.0 * fam_macs / (fam_ms * 1e-3) / 1e12,
-                                               executed_tflops=2.0 * fam_macs * mult / (fam_ms * 1e-3) / 1e12,
+                                               executed_tflops=2.0 * sum(d["macs"] * passes_of[k] for k, d in gemm_calls.items()) / (fam_ms * 1e-3) / 1e12,
+                                               mma_passes={kernel_of[k]: passes_of[k] for k in gemm_calls},
                                                ms={kernel_of[k]: round(d["ms"], 3) for k, d in gemm_calls.items()}),
                         note="achieved = algorithmic conv FLOPs of the layers this kernel served / their summed launch time (CUDA "
                              "events on the launching stream around every library call of one eager step); each product is issued as "
@@ -348,7 +352,8 @@ def run_ours(args):
         line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
                     unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype=f"{args.dtype} x{args.passes} operands, f32 accumulate" if args.engine == "tc" else "f32",
+                    dtype=(f"{args.dtype} x{args.passes} operands (weight gradients: {ops.CONFIG['bwd_dtype']} x{wmult}), f32 accumulate"
+                           if args.engine == "tc" else "f32"),
                     data="synthetic",
                     config=dict(workload=wl["name"], crop=[H, W], batch_per_gpu=B, parallelism=f"dp{world}", engine=args.engine,
                                 cuda_graph=bool(model.use_graph),

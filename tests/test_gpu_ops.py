@@ -282,7 +282,9 @@ ENGINES = [("simt", 3, "f16", 1e-5), ("tc", 3, "f16", 1e-5), ("tc", 1, "f16", 1e
 @pytest.fixture(params=ENGINES, ids=lambda e: f"{e[0]}{e[1]}{e[2]}")
 def engine(request, ops):
     old = dict(ops.CONFIG)
-    ops.CONFIG.update(engine=request.param[0], passes=request.param[1], dtype=request.param[2])
+    # wgrad_passes follows `passes` here: these op-level tolerances are those of the full-precision weight gradient;
+    # the default single-pass weight gradient is covered by test_tc_wgrad_large[1-...] and by the step-level gates
+    ops.CONFIG.update(engine=request.param[0], passes=request.param[1], dtype=request.param[2], wgrad_passes=request.param[1])
     # (engine, passes, forward tolerance, dgrad tolerance: the backward operands are bf16 hi/lo)
     xtol = 1e-5 if request.param[0] == "simt" else {3: 5e-5, 2: 4e-3, 1: 8e-3}[request.param[1]]
     yield (request.param[0], request.param[1], request.param[3], xtol)
@@ -356,7 +358,7 @@ def test_tc_large_tiles_and_split_k(ops):
     """full 16x8 tiles over several images, ragged edges, and the split-K path of the tiny-M layers."""
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16")
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3)
         for (Ci, Co, k, s, p, N, H, W, split) in [(128, 128, 3, 1, 1, 5, 64, 64, 1), (64, 128, 3, 1, 1, 2, 40, 24, 1),
                                                   (512, 512, 4, 2, 1, 3, 8, 8, -1), (512, 512, 4, 2, 1, 12, 4, 4, 8),
                                                   (256, 512, 4, 2, 1, 2, 20, 12, -1)]:
@@ -405,7 +407,7 @@ def test_cat_conv2d_restricted_dgrad(ops):
     """conv over a lazily concatenated input: forward == conv(cat), gradients only for the parts that need one"""
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16")
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3)
         Cs, H, W = (128, 128, 2, 3), 32, 48
         xs = [torch.randn(2, c, H, W, generator=G(90 + i)) for i, c in enumerate(Cs)]
         xs[1].requires_grad_(True)
@@ -431,7 +433,7 @@ def test_fused_prologue_matches_unfused(ops):
     from dsr_b200 import networks as nw
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16")
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3)
         torch.manual_seed(5)
         mods = [nw.Conv2d(64, 128, 3, stride=2, padding=1), nw.InstanceNorm2d(128), nw.ReLU(True), nw.ReflectionPad2d(1),
                 nw.Conv2d(128, 128, 3, padding=0), nw.InstanceNorm2d(128), nw.ReLU(True),
