@@ -574,6 +574,11 @@ tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S,
                       unsigned short* __restrict__ Whi, unsigned short* __restrict__ Wlo, int f16, float wscale) {
     const int Ca8 = Ca >> 3;
     const long total = (long)Cout * T * Ca8;
+    if (pa < 0) {                 // all four output phases of a stride-2 transposed conv in one launch (grid.y = phase)
+        pa = blockIdx.y >> 1; pb = blockIdx.y & 1;
+        Whi += (long)blockIdx.y * Cout * T * Ca;
+        if (Wlo) Wlo += (long)blockIdx.y * Cout * T * Ca;
+    }
     const bool convT = (variant == DSR_TC_W_CONVT_PH) || (variant == DSR_TC_W_CONV_DGRAD);
     const int Cin = convT ? D0 : D1;
     const int g = Ca / Cp;
@@ -691,7 +696,8 @@ extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, 
     DSR_REQUIRE(w && W_hi && T > 0 && (Ca & 63) == 0, "bad arguments");
     DSR_REQUIRE(!((uintptr_t)W_hi & 15) && !((uintptr_t)W_lo & 15), "packed weight buffers must be 16-byte aligned");
     long total = (long)Cout * T * (Ca / 8);
-    tc_pack_weight_kernel<<<dsr_grid(total, 256), 256, 0, ST(stream)>>>(w, D0, D1, R, S, variant, Cp, phase_a, phase_b, pad, Cout, T,
+    DSR_REQUIRE(phase_a >= 0 || variant == DSR_TC_W_CONVT_PH, "phase -1 (all four phases, stacked rows) is for the transposed-conv variant");
+    tc_pack_weight_kernel<<<dim3(dsr_grid(total, 256, phase_a < 0 ? 2 : 8), phase_a < 0 ? 4 : 1), 256, 0, ST(stream)>>>(w, D0, D1, R, S, variant, Cp, phase_a, phase_b, pad, Cout, T,
                                                                        Ca, (unsigned short*)W_hi, (unsigned short*)W_lo, f16, wscale);
     return dsr_check_launch("tc_pack_weight");
 }

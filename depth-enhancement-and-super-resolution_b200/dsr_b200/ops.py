@@ -198,11 +198,25 @@ CONFIG = {
     "tc_first_layers": True,
     "tc_compact_first": True,   # ... reading the 8-pixel K blocks from a compact 8-channel operand (no 8x expansion)   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
     "halo_min_tiles": 120,
+    "fwd_passes": 0,     # forward GEMMs of the trainable nets: 0 = `passes`, 2 = activations hi+lo x weights hi only
+    "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
 _LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
 _W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH, _W_CONV_DGRAD, _W_CONV_DGRAD_PAIR = 0, 1, 2, 3, 4, 5
+
+
+_FWD = {"trainable": False}     # set by conv2d / conv_transpose2d / cat_conv2d: is the running layer on the autograd tape?
+
+
+def _passes(dtype):
+    """MMA passes of a forward GEMM (dtype None = the forward operand format) or of a data-gradient GEMM"""
+    if dtype is None and not _FWD["trainable"] and CONFIG["frozen_passes"]:
+        return min(CONFIG["frozen_passes"], CONFIG["passes"])       # frozen nets run under no_grad (main_model.py:426)
+    if dtype is None and _FWD["trainable"] and CONFIG["fwd_passes"]:
+        return min(CONFIG["fwd_passes"], CONFIG["passes"])
+    return CONFIG["passes"]
 
 
 W_SCALE = 64.0          # power-of-two weight scale of the f16 path: keeps the low half of N(0, 0.02)-sized weights normal
@@ -249,7 +263,7 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W, min_ci=16):
 def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None):
     """bf16 hi/lo packed copy of a parameter, cached ON the parameter object until it changes
     (in-place updates bump ``_version``; the arena optimizer bumps WEIGHT_EPOCH)."""
-    npass = CONFIG["passes"]
+    npass = _passes(dtype)
     epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
     stamp = (weight._version, epoch, weight.data_ptr())
     f16 = (dtype or CONFIG["dtype"]) == "f16"
@@ -312,7 +326,7 @@ class _Prepared:
 def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
     """the four output-phase weight matrices of a stride-2 transposed conv, stacked along rows ([4*Co][T*Ca]) so one GEMM
     launch serves all phases; cached on the parameter like _tc_weights"""
-    npass = CONFIG["passes"]
+    npass = _passes(dtype)
     epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
     stamp = (weight._version, epoch, weight.data_ptr())
     f16 = (dtype or CONFIG["dtype"]) == "f16"
@@ -333,13 +347,9 @@ def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
     K = plan["T"] * plan["Ca"]
     whi = torch.empty((4 * Co, K), device=w.device, dtype=torch.bfloat16)
     wlo = torch.empty((4 * Co, K), device=w.device, dtype=torch.bfloat16) if npass >= 3 else None
-    for a in (0, 1):
-        for b in (0, 1):
-            ph = 2 * a + b
-            _call("dsr_tc_pack_weight", _p(w), D0, D1, R, S, plan["variant"], plan["Cp"], a, b, pad, Co, plan["T"], plan["Ca"],
-                  _p(whi[ph * Co:(ph + 1) * Co], torch.bfloat16),
-                  _p(wlo[ph * Co:(ph + 1) * Co], torch.bfloat16) if wlo is not None else None,
-                  int(f16), W_SCALE if f16 else 1.0)
+    # phase -1: one launch packs the four phase matrices into the stacked rows (grid.y = phase)
+    _call("dsr_tc_pack_weight", _p(w), D0, D1, R, S, plan["variant"], plan["Cp"], -1, -1, pad, Co, plan["T"], plan["Ca"],
+          _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16) if wlo is not None else None, int(f16), W_SCALE if f16 else 1.0)
     cache[key] = (whi, wlo)
     return whi, wlo
 
@@ -357,6 +367,8 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=N
     Ca = plan["Ca"]
     ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
     alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if (CONFIG["passes"] >= 2 and need_lo) else None
+    if _lib.PROFILE is not None:
+        _lib.PROFILE_META = dict(macs=0, shape=(N, H, W, C, Ca, plan["layout"], pad, int(prm is not None), int(alo is not None)))
     _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
           _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, int((dtype or CONFIG["dtype"]) == "f16"),
           _p(csum, torch.float64))
@@ -383,12 +395,12 @@ def _tc_gemm(ahi, alo, N, Ha, Wa, Ca, whi, wlo, Co, T, dr, ds, aoh, aow, Ht, Wt,
     if which == 1:
         _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
               _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
-              Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], split_k, *_tc_fmt(dtype))
+              Ho, Wo, os_, ph, pw, nphase, act_out, _passes(dtype), split_k, *_tc_fmt(dtype))
         return False
     extra = (a_mode,) if which == 2 else ()
     _call("dsr_tc_gemm3" if which == 3 else "dsr_tc_gemm2", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
           _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
-          Ho, Wo, os_, ph, pw, nphase, act_out, CONFIG["passes"], *_tc_fmt(dtype), _p(stats, torch.float64), *extra)
+          Ho, Wo, os_, ph, pw, nphase, act_out, _passes(dtype), *_tc_fmt(dtype), _p(stats, torch.float64), *extra)
     return stats is not None
 
 
@@ -887,6 +899,7 @@ class _CatConv2d(Function):
 
 def cat_conv2d(parts, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO):
     pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
+    _FWD["trainable"] = torch.is_grad_enabled() and (weight.requires_grad or any(p.requires_grad for p in parts))
     return _CatConv2d.apply(weight, bias, stride, padding, pad_mode, act_out, *parts)
 
 
@@ -904,12 +917,14 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode
     """-> y, or (y, stats) with want_stats: stats = float64 [N*Cout*2] per-(n, c) (sum, sum of squares) of y for the
     normalisation layer that follows (instance_norm / group_norm take it through their `stats` argument)."""
     pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
+    _FWD["trainable"] = torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad)
     y, st = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats, pro)
     return (y, st) if want_stats else y
 
 
 def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act_out=ACT_NONE, want_stats=False,
                      pro=None):
+    _FWD["trainable"] = torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad)
     y, st = _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out, want_stats, pro)
     return (y, st) if want_stats else y
 

@@ -42,6 +42,7 @@ def main():
         model.set_input(batch)
         model.optimize_parameters(0, 1)
         pred = max(rel_l2(getattr(model, k).detach().cpu(), g["s0/" + k]) for k in ("pred_syn_depth", "pred_real_depth"))
+        froz = {k: rel_l2(getattr(model, k).detach().cpu(), g["s0/" + k]) for k in ("syn2real_depth", "real_depth_by_image")}
         losses = model.get_current_losses()
         lerr = max(abs(losses[k] - float(g["s0/loss/" + k])) / max(abs(float(g["s0/loss/" + k])), 1e-3) for k in losses)
         worst, wname, fa, fb = 1.0, "", [], []
@@ -54,7 +55,7 @@ def main():
                     if c < worst:
                         worst, wname = c, f"{net}.{n}"
                     fa.append(mine.flatten()); fb.append(gr.flatten())
-        print(f"{spec:40s} pred {pred:.2e}  loss {lerr:.2e}  worst cos {worst:.6f} ({wname})  flat cos {cosine(torch.cat(fa), torch.cat(fb)):.7f}", flush=True)
+        print(f"{spec:40s} pred {pred:.2e}  loss {lerr:.2e}  worst cos {worst:.6f} ({wname})  flat cos {cosine(torch.cat(fa), torch.cat(fb)):.7f}  frozen outs {froz['syn2real_depth']:.2e} {froz['real_depth_by_image']:.2e}", flush=True)
         model.arena.release()
 
 

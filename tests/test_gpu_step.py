@@ -150,7 +150,9 @@ def test_cuda_graph_replay_matches_eager(built_lib):
     (la, pa, ga, wa), (lb, pb, gb, wb) = out
     assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
     assert rel_l2(pa.cpu(), pb.cpu()) <= 1e-5
-    assert cosine(ga.cpu(), gb.cpu()) >= 0.99999
+    # two EAGER runs from the same state already differ by 1 - cos = 2e-6 .. 5e-6 (scripts/noise_probe.py: atomics sum in
+    # another order every run and the nets amplify that ~1e4-fold), with occasional 5e-5 outliers: gate at 1e-4
+    assert cosine(ga.cpu(), gb.cpu()) >= 0.9999
     assert float((wa - wb).abs().max()) <= 2.1e-4          # at most a sign flip of a noise-level gradient: 2 * lr
     assert m.optimizer_G.n_steps == 5
 
