@@ -465,6 +465,10 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
         for (int i = tid; i < C; i += 256) s_sum[i] = 0.f;
         __syncthreads();
     }
+    // bias-gradient sums: when every item of a thread covers the same 8 channels (256 % cg == 0, NORMAL layout) they are
+    // kept in registers and folded once at the end - the per-item shared-memory atomics were 16-way conflicted
+    const bool reg_sum = csum && layout == DSR_TC_LAYOUT_NORMAL && (256 % cg) == 0;
+    float racc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int cached_n = -1;
     for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
         const int n = magic_ha ? (int)__umulhi((unsigned)row, magic_ha) : row, ha = row - n * Ha;
@@ -525,7 +529,10 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : slope * v[e];
                     }
-                    if (csum) {
+                    if (reg_sum) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) racc[e] += v[e];
+                    } else if (csum) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) if (c + e < C) atomicAdd(&s_sum[c + e], v[e]);
                     }
@@ -540,6 +547,11 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
         }
     }
     if (csum) {
+        if (reg_sum) {
+            const int c = (tid % cg) << 3;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (c + e < C) atomicAdd(&s_sum[c + e], racc[e]);
+        }
         __syncthreads();
         for (int i = tid; i < C; i += 256) atomicAdd(&csum[i], (double)s_sum[i]);
     }

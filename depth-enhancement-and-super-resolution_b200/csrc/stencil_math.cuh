@@ -31,46 +31,9 @@ DSR_HD float dsr_gcoef(int j, int i, int n) {
     return i == j + 1 ? 0.5f : (i == j - 1 ? -0.5f : 0.f);
 }
 
-// A plane - or a shared-memory tile of it - addressed by ABSOLUTE pixel coordinates: v(i, j) = p[i * ld + j]
-// (for a tile whose first element is pixel (i0, j0): p = tile - (i0 * ld + j0), ld = tile row pitch).
-struct PlaneView {
-    const float* p;
-    long ld;
-    DSR_HD float operator()(int i, int j) const { return p[(long)i * ld + j]; }
-};
-// np.gradient-style derivative along H / W at (i, j) read through a view
-DSR_HD float view_grad_h(const PlaneView& d, int i, int j, int H) {
-    if (i == 0) return d(1, j) - d(0, j);
-    if (i == H - 1) return d(H - 1, j) - d(H - 2, j);
-    return (d(i + 1, j) - d(i - 1, j)) / 2.f;
-}
-DSR_HD float view_grad_w(const PlaneView& d, int i, int j, int W) {
-    if (j == 0) return d(i, 1) - d(i, 0);
-    if (j == W - 1) return d(i, W - 1) - d(i, W - 2);
-    return (d(i, j + 1) - d(i, j - 1)) / 2.f;
-}
-
 // ---------------------------------------------------------------------------------------------
 // old (image-space) normals: n = (-dH, -dW, 1) / (|.| + 1e-6), times `scale`
 // ---------------------------------------------------------------------------------------------
-DSR_HD void old_normal_from_grads(float gh, float gw, float scale, float out[3]) {
-    float v0 = -gh, v1 = -gw, v2 = 1.f;
-    float r = sqrtf(v0 * v0 + v1 * v1 + v2 * v2);
-    float den = r + 1e-6f;
-    out[0] = (v0 / den) * scale;
-    out[1] = (v1 / den) * scale;
-    out[2] = (v2 / den) * scale;
-}
-DSR_HD void old_normal_adj_from_grads(float gh, float gw, float scale, float g0, float g1, float g2, float& dgh, float& dgw) {
-    float v0 = -gh, v1 = -gw, v2 = 1.f;
-    float r = sqrtf(v0 * v0 + v1 * v1 + v2 * v2);
-    float den = r + 1e-6f;
-    float dn0 = g0 * scale, dn1 = g1 * scale, dn2 = g2 * scale;
-    float dot = dn0 * v0 + dn1 * v1 + dn2 * v2;
-    float k = dot / (r * den * den);
-    dgh = -(dn0 / den - k * v0);
-    dgw = -(dn1 / den - k * v1);
-}
 DSR_HD void old_normal_fwd(const float* d, int H, int W, int i, int j, float scale, float out[3]) {
     float gh = dsr_grad<float>(d + j, i, H, W);
     float gw = dsr_grad<float>(d + (long)i * W, j, W, 1);
@@ -224,31 +187,8 @@ DSR_HD float new_normal_bwd(const float* d, const float* g /*3 planes*/, long pl
     return (float)(acc * 0.5);  // z = (d + 1) / 2
 }
 
-// --- tiled form of the camera-space normals: the point map P is staged once per pixel (fp64, one reciprocal for the
-// ray), its np.gradient differences are taken in fp64 (that is where the cancellation is: |dP| ~ 1e-3 |P|) and
-// rounded to fp32; cross product, normalisation and the adjoint run in fp32 (error ~1e-7 on a unit normal).
-DSR_HD void cam_ray1(const double* cam, int i, int j, double& rx, double& ry) {
-    double u = cam[9] + (double)j, v = cam[10] + (double)i;
-    double a = cam[0] * u + cam[1] * v + cam[2];
-    double b = cam[3] * u + cam[4] * v + cam[5];
-    double c = cam[6] * u + cam[7] * v + cam[8];
-    rx = a / c;
-    ry = b / c;
-}
-// which neighbours np.gradient uses at index i of a line of n: (ia, ib, 1/step)
-DSR_HD void grad_taps(int i, int n, int& ia, int& ib, double& inv) {
-    if (i == 0) { ia = 0; ib = 1; inv = 1.0; }
-    else if (i == n - 1) { ia = n - 2; ib = n - 1; inv = 1.0; }
-    else { ia = i - 1; ib = i + 1; inv = 0.5; }
-}
-DSR_HD void new_normal_from_grads(const float Pu[3], const float Pv[3], float out[3]) {
-    float m0 = Pv[1] * Pu[2] - Pu[1] * Pv[2];
-    float m1 = Pv[2] * Pu[0] - Pu[2] * Pv[0];
-    float m2 = Pv[0] * Pu[1] - Pu[0] * Pv[1];
-    float r = sqrtf(m0 * m0 + m1 * m1 + m2 * m2);
-    float den = r > 1e-12f ? r : 1e-12f;
-    out[0] = m0 / den; out[1] = m1 / den; out[2] = m2 / den;
-}
+// --- adjoint of the camera-space normal in fp32, from fp32 copies of the fp64 point differences (the tiled kernels of
+// stencil_tiled.cu: differences and the forward cross product stay fp64 - both cancel - the rest is fp32)
 DSR_HD void new_normal_adj_from_grads(const float Pu[3], const float Pv[3], float g0, float g1, float g2,
                                       float dPu[3], float dPv[3]) {
     float m[3] = {Pv[1] * Pu[2] - Pu[1] * Pv[2], Pv[2] * Pu[0] - Pu[2] * Pv[0], Pv[0] * Pu[1] - Pu[0] * Pv[1]};

@@ -34,24 +34,6 @@ static int tile_grid(int planes, int H, int W) {
     return (int)(it.ntiles < cap ? it.ntiles : cap);
 }
 
-// stage rows [i0-HALO, i0+TH+HALO) x cols [j0-HALO, j0+TW+HALO) of `plane` (coordinates clamped into the image)
-template <int HALO>
-__device__ __forceinline__ void load_tile(const float* __restrict__ plane, int H, int W, int i0, int j0, float* tile) {
-    constexpr int LH = TH + 2 * HALO, LW = TW + 2 * HALO;
-    for (int t = threadIdx.x; t < LH * LW; t += NT) {
-        const int r = t / LW, c = t - r * LW;
-        const int i = min(max(i0 - HALO + r, 0), H - 1), j = min(max(j0 - HALO + c, 0), W - 1);
-        tile[t] = __ldg(plane + (long)i * W + j);
-    }
-}
-template <int HALO>
-__device__ __forceinline__ PlaneView tile_view(const float* tile, int i0, int j0) {
-    constexpr int LW = TW + 2 * HALO;
-    PlaneView v;
-    v.ld = LW;
-    v.p = tile - ((long)(i0 - HALO) * LW + (j0 - HALO));
-    return v;
-}
 // 4 adjacent outputs of row i starting at column j (j % 4 == 0): one 16-byte store when the row allows it
 __device__ __forceinline__ void store4(float* __restrict__ plane, int W, int i, int j, const float v[4], bool vec) {
     float* o = plane + (long)i * W + j;
@@ -333,74 +315,56 @@ struct Cam {
         if (!affine) { const double c = k[6] * u + k[7] * v + k[8]; rx = rx / c; ry = ry / c; }
     }
 };
-// stage rows [i0 - RH, i0 + TH + RH) x column quads [j0 - 4, j0 + TW + 4) of the point map
-template <int RH>
-__device__ __forceinline__ void stage_points_quads(const float* __restrict__ p, const Cam& cam, int H, int W, int i0, int j0,
-                                                   bool vin, double* __restrict__ sP) {
-    constexpr int ROWS = TH + 2 * RH, QN = PW / 4, LN = ROWS * PW;
-    for (int t = threadIdx.x; t < ROWS * QN; t += NT) {
-        const int r = t / QN, qx = t - r * QN;
-        const int i = min(max(i0 - RH + r, 0), H - 1), j = j0 - 4 + 4 * qx;
-        float dv[4];
-        if (vin && j >= 0 && j + 3 < W) {
-            const float4 c = ld4(p + (long)i * W + j);
-            dv[0] = c.x; dv[1] = c.y; dv[2] = c.z; dv[3] = c.w;
-        } else {
+// raw fp64 differences of the point map for the 4 pixels (i, j .. j+3), from the depths of the quad's row (zc: columns
+// j-1 .. j+4), of the row above (zu) and below (zl), all border-clamped like their coordinates iu / il / jc
+__device__ __forceinline__ void quad_point_diffs(const Cam& cam, int i, int iu, int il, const int jc[6], const float zc[6],
+                                                 const float zu[4], const float zl[4], double du[3][4], double dv[3][4]) {
+    double Pc[3][6];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dv[e] = __ldg(p + (long)i * W + min(max(j + e, 0), W - 1));
-        }
-        double P0[4], P1[4], P2[4];
+    for (int e = 0; e < 6; ++e) {
+        double rx, ry;
+        cam.ray(i, jc[e], rx, ry);
+        const double z = ((double)zc[e] + 1.0) / 2.0;
+        Pc[0][e] = rx * z; Pc[1][e] = ry * z; Pc[2][e] = z;
+    }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            double rx, ry;
-            cam.ray(i, min(max(j + e, 0), W - 1), rx, ry);
-            const double z = ((double)dv[e] + 1.0) / 2.0;
-            P0[e] = rx * z; P1[e] = ry * z; P2[e] = z;
-        }
-        double* o = sP + r * PW + 4 * qx;
-        *reinterpret_cast<double2*>(o) = make_double2(P0[0], P0[1]);
-        *reinterpret_cast<double2*>(o + 2) = make_double2(P0[2], P0[3]);
-        *reinterpret_cast<double2*>(o + LN) = make_double2(P1[0], P1[1]);
-        *reinterpret_cast<double2*>(o + LN + 2) = make_double2(P1[2], P1[3]);
-        *reinterpret_cast<double2*>(o + 2 * LN) = make_double2(P2[0], P2[1]);
-        *reinterpret_cast<double2*>(o + 2 * LN + 2) = make_double2(P2[2], P2[3]);
+    for (int e = 0; e < 4; ++e) {
+        double rxu, ryu, rxl, ryl;
+        cam.ray(iu, jc[e + 1], rxu, ryu);
+        cam.ray(il, jc[e + 1], rxl, ryl);
+        const double zU = ((double)zu[e] + 1.0) / 2.0, zL = ((double)zl[e] + 1.0) / 2.0;
+        dv[0][e] = rxl * zL - rxu * zU; dv[1][e] = ryl * zL - ryu * zU; dv[2][e] = zL - zU;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) du[k][e] = Pc[k][e + 2] - Pc[k][e];
     }
 }
-// raw (unscaled) fp64 differences of the staged point map for the 4 pixels at shared position `o` (component stride LN):
-// du[k][e] = P_k[e+1] - P_k[e-1] along W, dv[k][e] = P_k[row+1] - P_k[row-1] along H
-__device__ __forceinline__ void point_diffs(const double* __restrict__ o, int LN, double du[3][4], double dv[3][4]) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double* c = o + k * LN;
-        const double2 c01 = *reinterpret_cast<const double2*>(c), c23 = *reinterpret_cast<const double2*>(c + 2);
-        const double2 u01 = *reinterpret_cast<const double2*>(c - PW), u23 = *reinterpret_cast<const double2*>(c - PW + 2);
-        const double2 d01 = *reinterpret_cast<const double2*>(c + PW), d23 = *reinterpret_cast<const double2*>(c + PW + 2);
-        const double cl = c[-1], cr = c[4];
-        du[k][0] = c01.y - cl; du[k][1] = c23.x - c01.x; du[k][2] = c23.y - c01.y; du[k][3] = cr - c23.x;
-        dv[k][0] = d01.x - u01.x; dv[k][1] = d01.y - u01.y; dv[k][2] = d23.x - u23.x; dv[k][3] = d23.y - u23.y;
-    }
-}
-__global__ void __launch_bounds__(NT, 4)
+// forward: no shared memory - the point map of the 14 pixels a quad touches (6 in its row, 4 above, 4 below) is rebuilt in
+// registers from three clamped 16-byte depth loads; the ray is affine in (i, j), so neighbours cost one DFMA each.
+__global__ void __launch_bounds__(NT, 3)
 normals_new_fwd_quad(const float* __restrict__ d, const double* __restrict__ cams, int H, int W, float* __restrict__ out) {
-    __shared__ __align__(16) double sP[3 * (TH + 2) * PW];
-    constexpr int LN = (TH + 2) * PW;
-    const int i0 = blockIdx.y * TH, j0 = blockIdx.x * TW;
-    const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) << 2;
+    const Quad q(H, W);
+    if (!q.ok) return;
     const long plane = (long)H * W;
-    const Cam cam(cams + blockIdx.z * DSR_CAM_DOUBLES);
+    const float* p = d + q.pl * plane;
+    const Cam cam(cams + q.pl * DSR_CAM_DOUBLES);
     const bool vin = vec_ok(d, W), vout = vec_ok(out, W);
-    stage_points_quads<1>(d + blockIdx.z * plane, cam, H, W, i0, j0, vin, sP);
-    __syncthreads();
-    const int i = i0 + ty, j = j0 + tx;
-    if (i >= H || j >= W) return;
+    const int iu = max(q.i - 1, 0), il = min(q.i + 1, H - 1);
+    float zu[4], zl[4], zc[6];
+    load4(p + (long)iu * W, q.j, W, vin, zu);
+    load4(p + (long)il * W, q.j, W, vin, zl);
+    load6(p + (long)q.i * W, q.j, W, vin, zc);
+    // column coordinates clamped like the loads (the !vin path clamps every column; the vec path only the two outer ones)
+    int jc[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) jc[e] = min(max(q.j - 1 + e, 0), W - 1);
     double du[3][4], dv[3][4];
-    point_diffs(sP + (ty + 1) * PW + 4 + tx, LN, du, dv);
-    const float fh = edge_f(i, H);
+    quad_point_diffs(cam, q.i, iu, il, jc, zc, zu, zl, du, dv);
+    const float fh = edge_f(q.i, H);
     float n0[4], n1[4], n2[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         // m = Pv x Pu with Pu = du * su, Pv = dv * sv: the power-of-two factors commute with every rounding
-        const float sc = fh * edge_f(j + e, W);
+        const float sc = fh * edge_f(q.j + e, W);
         const float m0 = (float)(dv[1][e] * du[2][e] - du[1][e] * dv[2][e]) * sc;
         const float m1 = (float)(dv[2][e] * du[0][e] - du[2][e] * dv[0][e]) * sc;
         const float m2 = (float)(dv[0][e] * du[1][e] - du[0][e] * dv[1][e]) * sc;
@@ -408,24 +372,37 @@ normals_new_fwd_quad(const float* __restrict__ d, const double* __restrict__ cam
         const float k = 1.f / (r > 1e-12f ? r : 1e-12f);
         n0[e] = m0 * k; n1[e] = m1 * k; n2[e] = m2 * k;
     }
-    float* o = out + (long)blockIdx.z * 3 * plane;
-    store4(o, W, i, j, n0, vout); store4(o + plane, W, i, j, n1, vout); store4(o + 2 * plane, W, i, j, n2, vout);
+    float* o = out + (long)q.pl * 3 * plane;
+    store4(o, W, q.i, q.j, n0, vout); store4(o + plane, W, q.i, q.j, n1, vout); store4(o + 2 * plane, W, q.i, q.j, n2, vout);
 }
-// backward: stage P with a 2-pixel halo, phase 1 = per-pixel adjoints (dL/dPu, dL/dPv) of the tile + 1-pixel halo in
-// fp32 (column quads [j0 - 4, j0 + TW + 4), rows [i0 - 1, i0 + TH]), phase 2 = gather through np.gradient's taps and
-// project on the ray of the output pixel: dL/dz = sum c * (dPu . ray) + sum c * (dPv . ray), dL/dd = dL/dz / 2.
+// backward: the DEPTH tile (+ 2-pixel halo, fp32) is staged in shared memory; phase 1 = per-pixel adjoints (dL/dPu, dL/dPv)
+// of the tile + 1-pixel halo in fp32 (column quads [j0 - 4, j0 + TW + 4), rows [i0 - 1, i0 + TH]), each task rebuilding
+// the point differences of its quad in fp64 registers; phase 2 = gather through np.gradient's taps and project on the
+// ray of the output pixel: dL/dz = sum c * (dPu . ray) + sum c * (dPv . ray), dL/dd = dL/dz / 2.
 __global__ void __launch_bounds__(NT, 3)
 normals_new_bwd_quad(const float* __restrict__ d, const float* __restrict__ g, const double* __restrict__ cams, int H, int W,
                      float* __restrict__ gd) {
-    extern __shared__ __align__(16) double sP[];                 // [3][(TH+4)*PW] doubles, then [6][(TH+2)*PW] floats
-    constexpr int LN2 = (TH + 4) * PW, LN1 = (TH + 2) * PW, QN = PW / 4;
-    float* adj = reinterpret_cast<float*>(sP + 3 * LN2);
+    extern __shared__ __align__(16) float sD[];                  // [(TH+4)][PW] depths, then [6][(TH+2)*PW] adjoints
+    constexpr int LN1 = (TH + 2) * PW, QN = PW / 4;
+    float* adj = sD + (TH + 4) * PW;
     const int i0 = blockIdx.y * TH, j0 = blockIdx.x * TW;
     const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) << 2;
     const long plane = (long)H * W;
+    const float* p = d + blockIdx.z * plane;
     const Cam cam(cams + blockIdx.z * DSR_CAM_DOUBLES);
     const bool vin = vec_ok(d, W) && vec_ok(g, W), vout = vec_ok(gd, W);
-    stage_points_quads<2>(d + blockIdx.z * plane, cam, H, W, i0, j0, vin, sP);
+    for (int t = threadIdx.x; t < (TH + 4) * QN; t += NT) {      // depths, rows / columns clamped into the image
+        const int r = t / QN, qx = t - r * QN;
+        const int i = min(max(i0 - 2 + r, 0), H - 1), j = j0 - 4 + 4 * qx;
+        float4 v;
+        if (vin && j >= 0 && j + 3 < W) v = ld4(p + (long)i * W + j);
+        else {
+            const float* row = p + (long)i * W;
+            v = make_float4(__ldg(row + min(max(j, 0), W - 1)), __ldg(row + min(max(j + 1, 0), W - 1)),
+                            __ldg(row + min(max(j + 2, 0), W - 1)), __ldg(row + min(max(j + 3, 0), W - 1)));
+        }
+        *reinterpret_cast<float4*>(sD + r * PW + 4 * qx) = v;
+    }
     __syncthreads();
     const float* gp = g + (long)blockIdx.z * 3 * plane;
     for (int t = threadIdx.x; t < (TH + 2) * QN; t += NT) {
@@ -437,8 +414,17 @@ normals_new_bwd_quad(const float* __restrict__ d, const float* __restrict__ g, c
 #pragma unroll
             for (int e = 0; e < 4; ++e) A[k][e] = 0.f;
         if (i >= 0 && i < H && j + 3 >= 0 && j < W) {
+            const float* c = sD + (r + 1) * PW + 4 * qx;            // depth row of pixel row i
+            const float4 c4 = *reinterpret_cast<const float4*>(c), u4 = *reinterpret_cast<const float4*>(c - PW),
+                         l4 = *reinterpret_cast<const float4*>(c + PW);
+            // (the first / last quad of the staged row has no left / right neighbour column; its outer pixel is unused)
+            const float zc[6] = {qx > 0 ? c[-1] : c4.x, c4.x, c4.y, c4.z, c4.w, qx < QN - 1 ? c[4] : c4.w};
+            const float zu[4] = {u4.x, u4.y, u4.z, u4.w}, zl[4] = {l4.x, l4.y, l4.z, l4.w};
+            int jc[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) jc[e] = min(max(j - 1 + e, 0), W - 1);
             double du[3][4], dv[3][4];
-            point_diffs(sP + (r + 1) * PW + 4 * qx, LN2, du, dv);
+            quad_point_diffs(cam, i, max(i - 1, 0), min(i + 1, H - 1), jc, zc, zu, zl, du, dv);
             float g0[4], g1[4], g2[4];
             if (vin && j >= 0 && j + 3 < W) {
                 load4(gp + (long)i * W, j, W, true, g0); load4(gp + plane + (long)i * W, j, W, true, g1);
@@ -785,7 +771,7 @@ extern "C" int dsr_normals_new_fwd(const float* depth, const double* cams, int B
 extern "C" int dsr_normals_new_bwd(const float* depth, const float* gout, const double* cams, int B, int H, int W,
                                    float* gdepth, void* stream) {
     DSR_REQUIRE(depth && gout && cams && gdepth && B > 0 && H >= 2 && W >= 2 && PLANES_OK(B, H, W), "bad arguments");
-    const size_t smem = 3 * (TH + 4) * PW * sizeof(double) + 6 * (TH + 2) * PW * sizeof(float);
+    const size_t smem = ((TH + 4) * PW + 6 * (TH + 2) * PW) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(normals_new_bwd_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
