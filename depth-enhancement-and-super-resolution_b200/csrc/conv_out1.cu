@@ -26,14 +26,43 @@ __device__ __forceinline__ float o1_prologue(float v, const float* __restrict__ 
     return v;
 }
 
+// 4 consecutive channels of one source pixel with the fused norm-apply + activation prologue: 16-byte loads when the
+// channel count allows it (the per-element form cost 4 + 12 scalar loads)
+__device__ __forceinline__ float4 o1_load4(const float* __restrict__ src, int c, int C, const float* __restrict__ prm, long NC,
+                                           long k, int act, float slope, bool vec) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+        const float4 a = ld4(src);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        if (prm) {
+            const float4 m = ld4(prm + k), sc = ld4(prm + NC + k), sh = ld4(prm + 2 * NC + k);
+            v[0] = (v[0] - m.x) * sc.x + sh.x; v[1] = (v[1] - m.y) * sc.y + sh.y;
+            v[2] = (v[2] - m.z) * sc.z + sh.z; v[3] = (v[3] - m.w) * sc.w + sh.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (act == DSR_ACT_RELU) v[e] = v[e] > 0.f ? v[e] : 0.f;
+            else if (act == DSR_ACT_LRELU) v[e] = v[e] > 0.f ? v[e] : slope * v[e];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (c + e < C) v[e] = o1_prologue(src[e], prm, NC, k + e, act, slope);
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // stride-1 R x S convolution to one channel.  Block = 16 x 16 output pixels; per 16-channel chunk the (16+R-1)^2 input
 // patch sits in shared memory as [channel quad][y][x] float4.
+template <int K>        // K = R = S when known at compile time (7: constant divisors in the staging loop), 0 = generic
 __global__ void __launch_bounds__(256)
 conv_out1_s1_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act_in,
-                    float slope, const float* __restrict__ w /* [C][R][S] */, const float* __restrict__ bias, int R, int S,
+                    float slope, const float* __restrict__ w /* [C][R][S] */, const float* __restrict__ bias, int R_, int S_,
                     int pad, int pad_mode, int act_out, float* __restrict__ out, int Ho, int Wo) {
     extern __shared__ float4 o1_sm[];
+    const int R = K ? K : R_, S = K ? K : S_;
     const int PH = O1_TILE + R - 1, PW = O1_TILE + S - 1;
+    const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && (!prm || !((uintptr_t)prm & 15));
     float4* tile = o1_sm;                                   // [4][PH][PW]
     float4* wsm = o1_sm + 4 * PH * PW;                      // [R*S][4]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -49,15 +78,12 @@ conv_out1_s1_kernel(const float* __restrict__ x, int N, int H, int W, int C, con
                 const int cq = i / (PH * PW), pq = i - cq * PH * PW;
                 const int py = pq / PW, px = pq - py * PW;
                 const int sy = o1_pad_src(h0 + py - pad, H, pad_mode), sx = o1_pad_src(w0 + px - pad, W, pad_mode);
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (sy >= 0 && sx >= 0) {
                     const int c = c0 + cq * 4;
-                    const float* src = x + ((long)(n * H + sy) * W + sx) * C + c;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (c + e < C) v[e] = o1_prologue(src[e], prm, NC, (long)n * C + c + e, act_in, slope);
+                    if (c < C) v = o1_load4(x + ((long)(n * H + sy) * W + sx) * C + c, c, C, prm, NC, (long)n * C + c, act_in, slope, vec);
                 }
-                tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+                tile[i] = v;
             }
             for (int i = tid; i < R * S * 4; i += 256) {
                 const int tap = i >> 2, cq = i & 3, c = c0 + cq * 4;
@@ -93,9 +119,10 @@ convT4_out1_kernel(const float* __restrict__ x, int N, int H, int W, int C, cons
                    float slope, const float* __restrict__ w /* [C][4][4] */, const float* __restrict__ bias, int act_out,
                    float* __restrict__ out /* N x 2H x 2W */) {
     extern __shared__ float4 o1_sm[];
-    const int PH = O1_TILE + 2, PW = O1_TILE + 2;
+    constexpr int PH = O1_TILE + 2, PW = O1_TILE + 2;
     float4* tile = o1_sm;                                   // [4][PH][PW]
     float4* wsm = o1_sm + 4 * PH * PW;                      // [16][4]
+    const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && (!prm || !((uintptr_t)prm & 15));
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int tiles_w = (W + O1_TILE - 1) / O1_TILE, tiles_h = (H + O1_TILE - 1) / O1_TILE;
     const long NC = (long)N * C;
@@ -109,15 +136,12 @@ convT4_out1_kernel(const float* __restrict__ x, int N, int H, int W, int C, cons
                 const int cq = i / (PH * PW), pq = i - cq * PH * PW;
                 const int py = pq / PW, px = pq - py * PW;
                 const int sy = h0 + py - 1, sx = w0 + px - 1;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
                     const int c = c0 + cq * 4;
-                    const float* src = x + ((long)(n * H + sy) * W + sx) * C + c;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (c + e < C) v[e] = o1_prologue(src[e], prm, NC, (long)n * C + c + e, act_in, slope);
+                    if (c < C) v = o1_load4(x + ((long)(n * H + sy) * W + sx) * C + c, c, C, prm, NC, (long)n * C + c, act_in, slope, vec);
                 }
-                tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+                tile[i] = v;
             }
             for (int i = tid; i < 64; i += 256) {
                 const int tap = i >> 2, cq = i & 3, c = c0 + cq * 4;
@@ -177,7 +201,11 @@ extern "C" int dsr_conv_out1(const float* x, int N, int H, int W, int C, const f
     const int tiles = N * dsr_cdiv(Ho, O1_TILE) * dsr_cdiv(Wo, O1_TILE);
     const size_t smem = (4 * (O1_TILE + R - 1) * (O1_TILE + S - 1) + R * S * 4) * sizeof(float4);
     const int cap = dsr_num_sms() * 4;
-    conv_out1_s1_kernel<<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias, R, S, pad,
-                                                                           pad_mode, act_out, out, Ho, Wo);
+    if (R == 7 && S == 7)
+        conv_out1_s1_kernel<7><<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias, R, S, pad,
+                                                                                  pad_mode, act_out, out, Ho, Wo);
+    else
+        conv_out1_s1_kernel<0><<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias, R, S, pad,
+                                                                                  pad_mode, act_out, out, Ho, Wo);
     return dsr_check_launch("conv_out1");
 }

@@ -595,9 +595,11 @@ tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S,
     const int Cin = convT ? D0 : D1;
     const int g = Ca / Cp;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int q8 = (int)(idx % Ca8);
-        const long u = idx / Ca8;
-        const int t = (int)(u % T), co = (int)(u / T);
+        // taps fastest: the R x S taps of one (co, c) pair are contiguous in the parameter, so a warp's gathered 4-byte
+        // loads fall into a few sectors (channel-fastest order touched 32 sectors per load: the kernel was L2-gather bound)
+        const int t = (int)(idx % T);
+        const long u = idx / T;
+        const int q8 = (int)(u % Ca8), co = (int)(u / Ca8);
         __align__(16) unsigned short hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
