@@ -18,7 +18,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 --layer-table $out/layers_step
 tail -1 $out/bench_$tag.json | cut -c1-400
 if [ "${NCU:-1}" = "1" ]; then
   # eager launches under ncu (a graph replay would hide the library-call boundaries): 3 warm-up + 2 timed + 2 e2e + 1 profile steps
-  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --graph 0"
+  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --graph 0 --inference 0"
   $CMD > $out/plain_$tag.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-4600} -c ${NCU_COUNT:-1200} --csv --log-file $out/launches_$tag.csv $CMD > $out/ncu_l_$tag.log 2>&1
   for k in ${NCU_KERNELS-conv_tc3_kernel conv_tc2_kernel}; do
