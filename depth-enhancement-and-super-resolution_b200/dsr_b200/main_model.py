@@ -468,3 +468,44 @@ class MainModel(BaseModel):
     def calculate(self, stage="test"):                              # main_model.py:433-436
         self.forward(stage)
         self.backward_G(back=False)
+
+    @torch.no_grad()
+    def forward_test_graph(self):
+        """``forward('test')`` (the inference pass of main.py:109-132) replayed as a CUDA graph: the first two calls run
+        eagerly, the third captures, later calls draw the (size-zero) test-stage rectangles on the host in the reference's
+        RNG order and replay ~400 launches as one.  Inputs come from ``set_input`` (persistent device buffers); the
+        result tensors (``pred_real_depth`` ...) keep their addresses and are overwritten by every replay."""
+        if self.device.type != "cuda":
+            return self.forward("test")
+        B, _, H, W = self.real_depth.shape
+        key = (B, H, W)
+        st = getattr(self, "_tgraph", None)
+        if st is None or st["key"] != key:
+            st = self._tgraph = dict(key=key, graph=None, eager=0, stream=torch.cuda.Stream())
+        cur = torch.cuda.current_stream()
+        if st["graph"] is None:
+            gs = st["stream"]
+            gs.wait_stream(cur)
+            with torch.cuda.stream(gs):
+                if st["eager"] < 2:
+                    st["eager"] += 1
+                    ops.zero_pool_reset(self.device)
+                    self.forward("test")
+                    cur.wait_stream(gs)
+                    return
+                self._stage_rects(B, H, W, "test")
+                self._rects_staged = True
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=gs):
+                    ops.zero_pool_reset(self.device)     # the accumulators of the pass are re-zeroed by every replay
+                    self.forward("test")
+                st["graph"] = graph
+                st["outs"] = {k: v for k, v in vars(self).items() if torch.is_tensor(v)}
+            cur.wait_stream(gs)
+            return
+        self._stage_rects(B, H, W, "test")
+        self._rects_staged = False
+        st["graph"].replay()
+        for k, v in st["outs"].items():
+            setattr(self, k, v)

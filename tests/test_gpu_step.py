@@ -173,6 +173,27 @@ def test_calculate_eval_mode_and_visuals(model_and_oracle):
     model._train()
 
 
+def test_inference_graph_replay_matches_eager(model_and_oracle):
+    """forward('test') replayed as a CUDA graph (forward_test_graph) == the eager pass, for two different inputs"""
+    model, _ = model_and_oracle
+    model.eval()
+    batches = [ref_step.synthetic_batch(2, 128, 128, seed=s, depth_kind="noise") for s in (4, 5)]
+    with torch.no_grad():
+        for i in range(5):                              # 2 eager, capture, 2 replays
+            model.set_input(batches[i % 2])
+            model.forward_test_graph()
+        assert model._tgraph["graph"] is not None
+        for b in batches:
+            model.set_input(b)
+            model.forward_test_graph()
+            got = {k: getattr(model, k).detach().clone() for k in ("pred_real_depth", "pred_syn_depth", "syn2real_depth", "depth_masked")}
+            model.set_input(b)
+            model.forward("test")
+            for k, v in got.items():
+                assert rel_l2(v.cpu(), getattr(model, k).detach().cpu()) <= 1e-5, k
+    model._train()
+
+
 def test_checkpoint_roundtrip(model_and_oracle, tmp_path):
     model, sds = model_and_oracle
     model.save_dir = str(tmp_path)
