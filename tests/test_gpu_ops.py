@@ -482,3 +482,102 @@ def test_cpu_tensor_raises(ops):
         ops.hole_valid_masks(torch.zeros(1, 1, 4, 4))
     with pytest.raises(RuntimeError):
         ops.conv2d(torch.zeros(1, 3, 8, 8), torch.zeros(4, 3, 3, 3))
+
+
+# ---------------------------------------------------------------------------------------------
+# ragged sizes for the tiled / register-quad stencil kernels (csrc/stencil_tiled.cu): planes smaller than one 16 x 64
+# tile, widths that are not a multiple of 4 (scalar load / store paths), sizes that end one pixel past a tile border
+# ---------------------------------------------------------------------------------------------
+RAGGED = [(2, 2), (3, 5), (16, 64), (17, 65), (5, 130), (33, 66), (31, 127), (48, 192)]
+
+
+@pytest.mark.parametrize("HW", RAGGED)
+def test_stencils_ragged_sizes(ops, HW):
+    from dsr_b200.norms import camera_table
+    H, W = HW
+    B = 3
+    d = torch.rand(B, 1, H, W, generator=G(90)) * 1.8 - 0.9
+    d[torch.rand(B, 1, H, W, generator=G(91)) < 0.1] = -1.0
+    # masks: bit-exact
+    hole_ref, valid_ref = ref_ops.hole_valid_masks(d)
+    hole, valid = ops.hole_valid_masks(d.cuda())
+    assert torch.equal(hole.cpu(), hole_ref) and torch.equal(valid.cpu(), valid_ref)
+    # image-space normals, forward + backward
+    x = d.clone().requires_grad_(True)
+    go = torch.randn(B, 3, H, W, generator=G(92))
+    ref = ref_ops.surface_normals_old(x) * 100
+    (ref * go).sum().backward()
+    xc = d.cuda().requires_grad_(True)
+    out = ops.normals_old(xc, 100.0)
+    (out * go.cuda()).sum().backward()
+    assert (out.cpu() - ref.detach()).abs().max() <= 1e-4 and rel_l2(xc.grad.cpu(), x.grad) <= 1e-4
+    # camera-space normals (smooth depth: the backward is ill-conditioned on noise), forward + backward
+    ds = _smooth_depth(B, max(H, 10), max(W, 10), 93)[:, :, :H, :W].clamp_min(-0.9).contiguous().requires_grad_(True)
+    K = torch.tensor([[577.87, 0.7, 319.5], [0, 571.3, 239.5], [0, 0, 1]], dtype=torch.float64).repeat(B, 1, 1)
+    crop = torch.tensor([[7, 7 + H, 3, 3 + W]] * B)
+    refn = ref_ops.surface_normals_new(ds, K, crop)
+    (refn * go).sum().backward()
+    dc = ds.detach().cuda().requires_grad_(True)
+    outn = ops.normals_new(dc, camera_table(K, crop, 0.5, "cuda"))
+    (outn * go.cuda()).sum().backward()
+    assert (outn.cpu() - refn.detach()).abs().max() <= 2e-6
+    assert np.allclose(dc.grad.cpu().numpy(), ds.grad.numpy(), rtol=2e-3, atol=1e-3 * float(ds.grad.abs().median()) + 1e-12)
+    # TV, forward + backward
+    n3 = torch.randn(B, 3, H, W, generator=G(94)).requires_grad_(True)
+    reft = ref_ops.tv_loss(n3)
+    reft.backward()
+    nc = n3.detach().cuda().requires_grad_(True)
+    outt = ops.tv_loss(nc)
+    outt.backward()
+    assert abs(float(outt) - float(reft)) <= 1e-5 * max(float(reft), 1e-6) and rel_l2(nc.grad.cpu(), n3.grad) <= 1e-6
+    # masked L1 / MSE, forward + backward
+    a = torch.randn(B, 3, H, W, generator=G(95))
+    b = torch.randn(B, 3, H, W, generator=G(96)).requires_grad_(True)
+    m1 = (torch.rand(B, 1, H, W, generator=G(97)) < 0.7).float()
+    m2 = (torch.rand(B, 1, H, W, generator=G(98)) < 0.5).float()
+    l1, l2 = ref_ops.l1_mean(a * m1 * m2, b * m1 * m2), ref_ops.mse_mean(a * m1 * m2, b * m1 * m2)
+    (l1 + 3 * l2).backward()
+    bc = b.detach().cuda().requires_grad_(True)
+    o = ops.masked_l1_l2(a.cuda(), bc, m1.cuda(), m2.cuda())
+    (o[0] + 3 * o[1]).backward()
+    assert abs(float(o[0]) - float(l1)) <= 1e-5 * float(l1) and abs(float(o[1]) - float(l2)) <= 1e-5 * float(l2)
+    assert rel_l2(bc.grad.cpu(), b.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("HW", [(8, 12), (17, 65), (36, 132)])
+def test_smooth_ragged_sizes(ops, HW):
+    H, W = HW
+    d = (torch.rand(2, 1, H, W, generator=G(13)) * 2 - 1).requires_grad_(True)
+    img = torch.rand(2, 3, H, W, generator=G(14)) * 2 - 1
+    ref = ref_ops.smooth_loss(d, img, 3)
+    ref.backward()
+    dc = d.detach().cuda().requires_grad_(True)
+    out = ops.smooth_loss(dc, img.cuda(), 3)
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 2e-5 * float(ref) and rel_l2(dc.grad.cpu(), d.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("HW", [(5, 7), (17, 65), (40, 130)])
+def test_rect_holes_ragged_sizes(ops, HW):
+    """rectangle tables drawn by the host in the reference's RNG order, planes that straddle tile borders"""
+    H, W = HW
+    B = 2
+    d = torch.rand(B, 1, H, W, generator=G(80)) * 1.8 - 0.9
+    d[torch.rand(B, 1, H, W, generator=G(81)) < 0.1] = -1.0
+    _, valid = ref_ops.hole_valid_masks(d)
+    rng = np.random.RandomState(5)
+    rects = []
+    for _ in range(B):
+        n = rng.randint(3, 12)
+        rects.append(np.stack([rng.randint(0, W, n), rng.randint(0, H, n), rng.randint(0, max(2, W // 2), n),
+                               rng.randint(0, max(2, H // 2), n)], 1).astype(np.int64))
+    gt_ref = ref_ops.rect_gt_mask(valid, rects)
+    masked_ref = ref_ops.apply_gt_mask(d, gt_ref)
+    tab = np.zeros((B, 64, 4), dtype=np.int32)
+    cnt = np.zeros((B,), dtype=np.int32)
+    for i, r in enumerate(rects):
+        tab[i, :len(r)] = r
+        cnt[i] = len(r)
+    gt, masked, extra = ops.rect_holes(valid.cuda(), d.cuda(), torch.from_numpy(tab).cuda(), torch.from_numpy(cnt).cuda(), 64)
+    assert np.array_equal(gt.cpu().numpy(), gt_ref.numpy().astype(np.uint8))
+    assert torch.equal(masked.cpu(), masked_ref)
