@@ -465,9 +465,9 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
         for (int i = tid; i < C; i += 256) s_sum[i] = 0.f;
         __syncthreads();
     }
-    // bias-gradient sums: when every item of a thread covers the same 8 channels (256 % cg == 0, NORMAL layout) they are
+    // bias-gradient sums: when every item of a thread covers the same 8 channels (256 % cg == 0, NORMAL / S2D layout) they are
     // kept in registers and folded once at the end - the per-item shared-memory atomics were 16-way conflicted
-    const bool reg_sum = csum && layout == DSR_TC_LAYOUT_NORMAL && (256 % cg) == 0;
+    const bool reg_sum = csum && layout != DSR_TC_LAYOUT_PAIR && (256 % cg) == 0;
     float racc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int cached_n = -1;
     for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
@@ -548,7 +548,8 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
     }
     if (csum) {
         if (reg_sum) {
-            const int c = (tid % cg) << 3;
+            const int q0 = (tid % cg) << 3;
+            const int c = layout == DSR_TC_LAYOUT_NORMAL ? q0 : q0 - (q0 / Cp) * Cp;
 #pragma unroll
             for (int e = 0; e < 8; ++e) if (c + e < C) atomicAdd(&s_sum[c + e], racc[e]);
         }
@@ -690,7 +691,8 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
                 "channel sums need every source element to be written exactly once (no pixel groups, zero padding)");
     DSR_REQUIRE((long)N * (H + 2 * pad) * (W + 2 * pad) < (1L << 31) && C <= 8192, "tensor too large for 32-bit pixel indices");
     const long rows = (long)N * Ha;
-    const long cap = (long)dsr_num_sms() * 8;
+    // with bias-gradient sums every block ends with C fp64 atomics on the same C addresses: fewer, longer blocks
+    const long cap = (long)dsr_num_sms() * (csum ? 3 : 8);
     const int grid = (int)(rows < cap ? rows : cap);
     const size_t Cs = ((size_t)C + 3) & ~(size_t)3;
     const size_t smem = ((prm ? 3 * Cs : 0) + (csum ? (size_t)C : 0)) * sizeof(float);
