@@ -140,3 +140,54 @@ extern "C" int dsr_nearest_fwd(const float* x, int N, int H, int W, int C, int H
     nearest_fwd_kernel<<<dsr_grid((long)N * Ho * Wo * C, TPB), TPB, 0, ST(stream)>>>(x, N, H, W, C, Ho, Wo, sh, sw, y);
     return dsr_check_launch("nearest_fwd");
 }
+
+// ------------------------------------------------------------------------------------------
+// On-disk formats either side of the path
+//   input : uint16 PNG depth in millimetres, clipped at `max_mm` (5100), -> d / max_mm * 2 - 1 (float64 arithmetic as numpy
+//           does for int / int, then float32), data/my_main_dataset.py:35-52; uint8 RGB -> (x - 127.5) / 127.5 (float32)
+//   output: clip((pred + 1) / 2, 0, 1) * 5100 -> uint16 (truncation), rows [crop, H - crop), models/main_model.py:321-333
+// ------------------------------------------------------------------------------------------
+__global__ void u16_to_depth_kernel(const unsigned short* __restrict__ in, long n, int max_mm, float* __restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int v = in[i];
+        const double d = (double)(v > max_mm ? max_mm : v) / (double)max_mm;
+        out[i] = (float)(d * 2.0 - 1.0);
+    }
+}
+// HWC uint8 (as decoded from the file) -> CHW float32 planes
+__global__ void u8_to_image_kernel(const unsigned char* __restrict__ in, int N, int H, int W, int C, float* __restrict__ out) {
+    const long plane = (long)H * W, total = (long)N * plane * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long p = i / C, n = p / plane, q = p - n * plane;
+        out[(n * C + c) * plane + q] = ((float)in[i] - 127.5f) / 127.5f;
+    }
+}
+__global__ void depth_to_u16_kernel(const float* __restrict__ pred, int N, int H, int W, int crop, float scale,
+                                    unsigned short* __restrict__ out) {
+    const int Ho = H - 2 * crop;
+    const long total = (long)N * Ho * W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        const long r = i / W;
+        const int h = (int)(r % Ho), n = (int)(r / Ho);
+        float v = (pred[((long)n * H + h + crop) * W + w] + 1.f) / 2.f;
+        v = fminf(fmaxf(v, 0.f), 1.f) * scale;
+        out[i] = (unsigned short)v;                 // numpy astype(np.uint16): truncation
+    }
+}
+extern "C" int dsr_u16_to_depth(const unsigned short* in, long n, int max_mm, float* out, void* stream) {
+    DSR_REQUIRE(in && out && n > 0 && max_mm > 0, "bad arguments");
+    u16_to_depth_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(in, n, max_mm, out);
+    return dsr_check_launch("u16_to_depth");
+}
+extern "C" int dsr_u8_to_image(const unsigned char* in, int N, int H, int W, int C, float* out, void* stream) {
+    DSR_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
+    u8_to_image_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(in, N, H, W, C, out);
+    return dsr_check_launch("u8_to_image");
+}
+extern "C" int dsr_depth_to_u16(const float* pred, int N, int H, int W, int crop, float scale, unsigned short* out, void* stream) {
+    DSR_REQUIRE(pred && out && N > 0 && W > 0 && crop >= 0 && H > 2 * crop, "bad arguments");
+    depth_to_u16_kernel<<<dsr_grid((long)N * (H - 2 * crop) * W, TPB), TPB, 0, ST(stream)>>>(pred, N, H, W, crop, scale, out);
+    return dsr_check_launch("depth_to_u16");
+}

@@ -342,8 +342,11 @@ class MainModel(BaseModel):
         self.loss_mean_of_abs_diff_syn = LazyScalar(lambda: s_syn[2] / n)
         self.loss_real_mean_diff = LazyScalar(lambda: (s_real[0] - s_real[1]) / n)
         self.loss_mean_of_abs_diff_real = LazyScalar(lambda: s_real[2] / n)
-        if getattr(self.opt, "save_all", False) and stage == "test":
-            raise NotImplementedError("dsr_b200: PNG export (--save_all) is a 'next' row (SURVEY.md section 8f.4)")
+        if getattr(self.opt, "save_all", False) and stage == "test":               # main_model.py:321-333
+            from . import io
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("dsr_b200: --save_all writes files: use forward('test'), not forward_test_graph()")
+            self.saved_files = io.save_predictions(self.pred_real_depth, self.B_paths, self.opt.save_image_folder, 16)
 
     def backward_G(self, back=True):                                # main_model.py:340-419
         opt = self.opt

@@ -85,6 +85,9 @@ class MainSRModel(MainModel):
         pred = self.netTask(ops.LazyCat([image_features, feat_depth, d_in, images]))
         if not train:
             self.pred_real_depth_hr = pred
+            if getattr(opt, "save_all", False):                      # main_sr_model.py:376-386: HR prediction, rows [32, H - 32)
+                from . import io
+                self.saved_files = io.save_predictions(pred, self.B_paths, opt.save_image_folder, 32)
             return
         self.pred_syn_depth, self.pred_real_depth_hr = pred[:B], pred[B:]
         self.pred_real_depth = ops.bicubic(self.pred_real_depth_hr, (h, w))                   # :361, on the gradient path
@@ -99,8 +102,6 @@ class MainSRModel(MainModel):
         self.loss_mean_of_abs_diff_syn = LazyScalar(lambda: s_syn[2] / n_hr)
         self.loss_real_mean_diff = LazyScalar(lambda: (s_real[0] - s_real[1]) / n_lr)
         self.loss_mean_of_abs_diff_real = LazyScalar(lambda: s_real[2] / n_lr)
-        if getattr(opt, "save_all", False) and stage == "test":
-            raise NotImplementedError("dsr_b200: PNG export (--save_all) is a 'next' row (SURVEY.md section 8f.4)")
 
     def backward_G(self, back=True):                                # main_sr_model.py:391-484
         opt = self.opt

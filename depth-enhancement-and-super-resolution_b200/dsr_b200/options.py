@@ -16,7 +16,7 @@ _DEFAULTS = dict(
     # train_options.py
     continue_train=False, epoch_count=1, phase="train", n_epochs=100, n_epochs_decay=100, beta1=0.5, lr=0.0002,
     gan_mode="lsgan", lr_policy="linear", lr_decay_iters=50, replace_transpose=False, print_mean=False,
-    save_all=False, SR=False, Depthf_ndown=2, Task_ndown=2, Depthf_basef=32, Task_basef=64, Depthf_outf=128,
+    save_all=False, save_image_folder="./results/", SR=False, Depthf_ndown=2, Task_ndown=2, Depthf_basef=32, Task_basef=64, Depthf_outf=128,
     Depthf_type="resnet_6blocks", Task_type="unet_128", use_rec_as_real_input=False, use_image_for_trans=False,
     norm_loss=False, use_smooth_loss=False, w_syn_norm=0.0, w_syn_l1=1.0, w_syn_holes=2.0, w_real_holes=5.0,
     w_real_l1_d=1.0, w_real_l1_i=0.1, w_smooth=0.1, ImageDepthf_outf=128, ImageDepthf_basef=32,

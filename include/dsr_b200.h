@@ -89,6 +89,13 @@ int dsr_bicubic_fwd(const float* x, int N, int H, int W, int C, int Ho, int Wo, 
 int dsr_bicubic_bwd(const float* gy, int N, int H, int W, int C, int Ho, int Wo, float* gx /* += */, void* stream);
 int dsr_nearest_fwd(const float* x, int N, int H, int W, int C, int Ho, int Wo, float* y, void* stream);
 
+/* on-disk formats either side of the path.  Input (data/my_main_dataset.py:35-52): uint16 depth in mm -> min(d, max_mm) /
+ * max_mm * 2 - 1; HWC uint8 RGB -> CHW (x - 127.5) / 127.5.  Output (models/main_model.py:321-333, --save_all):
+ * uint16(clip((pred + 1) / 2, 0, 1) * scale) of rows [crop, H - crop). */
+int dsr_u16_to_depth(const unsigned short* in, long n, int max_mm, float* out, void* stream);
+int dsr_u8_to_image(const unsigned char* in, int N, int H, int W, int C, float* out, void* stream);
+int dsr_depth_to_u16(const float* pred, int N, int H, int W, int crop, float scale, unsigned short* out, void* stream);
+
 /* ---- network plumbing (NHWC fp32) ------------------------------------------------------------ */
 int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream);
 int dsr_nhwc_to_nchw(const float* x, float* y, int N, int C, long P, void* stream);
