@@ -96,6 +96,13 @@ int dsr_u16_to_depth(const unsigned short* in, long n, int max_mm, float* out, v
 int dsr_u8_to_image(const unsigned char* in, int N, int H, int W, int C, float* out, void* stream);
 int dsr_depth_to_u16(const float* pred, int N, int H, int W, int crop, float scale, unsigned short* out, void* stream);
 
+/* batch evaluator of new_metrics.py (:115-191): per-image fp64 sums, out double [B][16] =
+ * {n, sum|d|, sum d^2} over ~target_hole | the same over ~target_hole & hole | over ~(hole | target_hole) |
+ * {3 n, sum |dn|^2} of the first-order normals outside the dilated target holes (kinv: double [B][9] = K^-1, may be NULL) |
+ * {n, sum} of the 'valid' 11x11 SSIM map (with_ssim).  hole = input < thr, target_hole = target < thr (:224-225). */
+int dsr_eval_metric_sums(const float* pred, const float* target, const float* input, const double* kinv, int B, int H, int W,
+                         float hole_threshold, double max_depth, int with_ssim, double* out, void* stream);
+
 /* ---- network plumbing (NHWC fp32) ------------------------------------------------------------ */
 int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream);
 int dsr_nhwc_to_nchw(const float* x, float* y, int N, int C, long P, void* stream);

@@ -196,6 +196,46 @@ def golden_i2d_step(B=2, H=128, W=128, tag="i2d_step_b2_128"):
     print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
 
 
+def metric_cases():
+    """synthetic uint16-valued depth triples (input with holes, prediction, target with holes) + ScanNet intrinsics"""
+    rs = np.random.RandomState(21)
+    cases = []
+    for (H, W) in ((48, 64), (33, 47)):
+        yy, xx = np.mgrid[0:H, 0:W]
+        target = np.round(1500 + 20 * xx + 12 * yy + 300 * np.sin(xx / 9.0) + rs.rand(H, W) * 15).astype(np.float64)
+        target[5:9, 10:22] = 0
+        target[rs.rand(H, W) < 0.02] = 0
+        target[0, :3] = 6000                                  # clipped to max_depth
+        pred = np.round(target + rs.randn(H, W) * 25 + 10).clip(0, 65535)
+        pred[target == 0] = np.round(1400 + rs.rand(int((target == 0).sum())) * 100)
+        inp = target.copy()
+        inp[20:30, 30:44] = 0                                 # holes of the input that the target does not have
+        inp[rs.rand(H, W) < 0.05] = 0
+        cases.append((pred, target, inp))
+    K = np.array([[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1.0]])
+    return cases, K
+
+
+def golden_metrics():
+    """new_metrics.calc_metrics of the live reference on synthetic triples (albumentations / skimage / imageio / tqdm are
+    stubbed: calc_metrics itself only needs numpy, scipy and torch)."""
+    for name in ("albumentations", "tqdm", "skimage", "skimage.transform"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skimage.transform"].resize = lambda a, shape: a
+    import new_metrics as nm
+    cases, K = metric_cases()
+    names = ["rmse", "mae", "rmse_h", "rmse_d", "psnr", "ssim", "mae_h", "mae_d", "mse_v"]
+    out = {"names": np.array(names)}
+    for i, (pred, target, inp) in enumerate(cases):
+        p, t = pred.clip(0, 5100), target.clip(0, 5100)
+        r = nm.calc_metrics(p, t, inp < nm.holes_threshold, t < nm.holes_threshold, K, 5100, names)
+        out[f"c{i}/pred"], out[f"c{i}/target"], out[f"c{i}/input"] = pred, target, inp
+        out[f"c{i}/values"] = np.array([float(r[n]) for n in names])
+    out["K"] = K
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+    print("wrote metrics", {n: float(v) for n, v in zip(names, out["c0/values"])})
+
+
 def golden_resize():
     """F.interpolate bicubic / nearest vectors (the torch calls of main_sr_model.py:279-293, :361, :394-398)."""
     import torch.nn.functional as F
@@ -258,7 +298,7 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -270,3 +310,5 @@ if __name__ == "__main__":
         golden_sr_step()
     if "i2d" in which:
         golden_i2d_step()
+    if "metrics" in which:
+        golden_metrics()
