@@ -587,6 +587,96 @@ extern "C" int dsr_norm_apply_fwd(const float* x, const float* prm, const float*
     }
     return dsr_check_launch("norm_apply_fwd");
 }
+// ------------------------------------------------------------------------------------------
+// GroupNorm(groups, C, affine) [+ReLU] backward (translation_network.py:46; the generators of the translation block).
+//   xhat = (x - mean_g) * rstd_g,  y = act(xhat * gamma + beta),  g = dy * act'(.)
+//   dbeta_c = sum g, dgamma_c = sum g * xhat,
+//   dx = rstd_g * (gamma_c * g - mean_g(gamma * g) - xhat * mean_g(gamma * g * xhat))      (means over the group's P * C/G elements)
+// prm = (mean, rstd, 0) per (n, c) as written by norm_finalize with gamma = beta = NULL.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_bwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ prm,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, int N, long P, int C, int act,
+                   long chunk, double* __restrict__ sums2) {
+    extern __shared__ float gsm[];                 // [2][C]
+    const int n = blockIdx.y;
+    const long NC = (long)N * C, p0 = (long)blockIdx.x * chunk, p1 = p0 + chunk < P ? p0 + chunk : P;
+    for (int c = threadIdx.x; c < 2 * C; c += 256) gsm[c] = 0.f;
+    __syncthreads();
+    const long base = (long)n * P * C;
+    for (long i = p0 * C + threadIdx.x; i < p1 * C; i += 256) {
+        const int c = (int)(i % C);
+        const long k = (long)n * C + c;
+        const float xh = (x[base + i] - prm[k]) * prm[NC + k];
+        float g = dy[base + i];
+        if (act == DSR_ACT_RELU && !(xh * gamma[c] + beta[c] > 0.f)) g = 0.f;
+        atomicAdd(&gsm[c], g);
+        atomicAdd(&gsm[C + c], g * xh);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        atomicAdd(&sums2[((long)n * C + c) * 2], (double)gsm[c]);
+        atomicAdd(&sums2[((long)n * C + c) * 2 + 1], (double)gsm[C + c]);
+    }
+}
+// per (n, c): the two group means the apply pass needs; per c: dgamma / dbeta (=|+=)
+__global__ void gn_bwd_finalize_kernel(const double* __restrict__ sums2, const float* __restrict__ gamma, int N, int C, int groups,
+                                       long P, float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       int accumulate) {
+    const int cg = C / groups;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)N * C; idx += (long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx / C), c = (int)(idx % C), g0 = (c / cg) * cg;
+        double a = 0, b = 0;
+        for (int k = 0; k < cg; ++k) {
+            a += (double)gamma[g0 + k] * sums2[((long)n * C + g0 + k) * 2];
+            b += (double)gamma[g0 + k] * sums2[((long)n * C + g0 + k) * 2 + 1];
+        }
+        const double M = (double)P * cg;
+        coef[idx * 2] = (float)(a / M);
+        coef[idx * 2 + 1] = (float)(b / M);
+        if (n == 0) {
+            double s1 = 0, s2 = 0;
+            for (int m = 0; m < N; ++m) { s1 += sums2[((long)m * C + c) * 2]; s2 += sums2[((long)m * C + c) * 2 + 1]; }
+            if (accumulate) { dbeta[c] += (float)s1; dgamma[c] += (float)s2; } else { dbeta[c] = (float)s1; dgamma[c] = (float)s2; }
+        }
+    }
+}
+__global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ prm,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
+                                    float* __restrict__ dx, int N, long P, int C, int act) {
+    const long NC = (long)N * C, total = (long)N * P * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const int n = (int)(idx / (P * C));
+        const long k = (long)n * C + c;
+        const float rstd = prm[NC + k], xh = (x[idx] - prm[k]) * rstd;
+        float g = dy[idx];
+        if (act == DSR_ACT_RELU && !(xh * gamma[c] + beta[c] > 0.f)) g = 0.f;
+        dx[idx] = rstd * (gamma[c] * g - coef[k * 2] - xh * coef[k * 2 + 1]);
+    }
+}
+extern "C" int dsr_gn_bwd_sums(const float* x, const float* dy, const float* prm, const float* gamma, const float* beta, int N,
+                               long P, int C, int act, double* sums2, void* stream) {
+    DSR_REQUIRE(x && dy && prm && gamma && beta && sums2 && N > 0 && N <= 65535 && P > 0 && C > 0 && C <= 4096, "bad arguments");
+    long blocks = (long)dsr_num_sms() * 4 / N + 1;
+    if (blocks > P) blocks = P;
+    const long chunk = (P + blocks - 1) / blocks;
+    gn_bwd_sums_kernel<<<dim3((unsigned)((P + chunk - 1) / chunk), (unsigned)N), 256, 2 * (size_t)C * sizeof(float), ST(stream)>>>(
+        x, dy, prm, gamma, beta, N, P, C, act, chunk, sums2);
+    return dsr_check_launch("gn_bwd_sums");
+}
+extern "C" int dsr_gn_bwd_finalize(const double* sums2, const float* gamma, int N, int C, int groups, long P, float* coef,
+                                   float* dgamma, float* dbeta, int accumulate, void* stream) {
+    DSR_REQUIRE(sums2 && gamma && coef && dgamma && dbeta && groups > 0 && C % groups == 0, "bad arguments");
+    gn_bwd_finalize_kernel<<<dsr_grid((long)N * C, TPB), TPB, 0, ST(stream)>>>(sums2, gamma, N, C, groups, P, coef, dgamma, dbeta, accumulate);
+    return dsr_check_launch("gn_bwd_finalize");
+}
+extern "C" int dsr_gn_bwd_apply(const float* x, const float* dy, const float* prm, const float* gamma, const float* beta,
+                                const float* coef, float* dx, int N, long P, int C, int act, void* stream) {
+    DSR_REQUIRE(x && dy && prm && gamma && beta && coef && dx, "null pointer");
+    gn_bwd_apply_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, gamma, beta, coef, dx, N, P, C, act);
+    return dsr_check_launch("gn_bwd_apply");
+}
 extern "C" int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm, int N, long P, int C, int act,
                                double* sums2, void* stream) {
     DSR_REQUIRE(x && dy && prm && sums2, "null pointer");

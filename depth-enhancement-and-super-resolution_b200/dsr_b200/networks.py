@@ -129,7 +129,9 @@ def run_fused(mods, x, tail_stats=False):
         conv = _conv_like(mods[j]) if j < n else None
         pre_pad = (pad.padding[0], "reflect" if isinstance(pad, ReflectionPad2d) else "replicate") if pad is not None else None
         plain = norm is None and act is None
-        if conv is not None and (plain or conv.fusable(x, pre_pad)):
+        # a GroupNorm that trains (its gamma / beta need gradients) runs as its own op: the fused prologue is forward-only
+        gn_trains = isinstance(norm, GroupNorm) and torch.is_grad_enabled() and (norm.weight.requires_grad or x.requires_grad)
+        if conv is not None and not gn_trains and (plain or conv.fusable(x, pre_pad)):
             kw = {}
             if pre_pad is not None:
                 kw["pre_pad"] = pre_pad

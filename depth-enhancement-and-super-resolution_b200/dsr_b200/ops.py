@@ -1003,20 +1003,66 @@ def instance_norm(x, eps=1e-5, act=ACT_NONE, residual=None, stats=None):
     return _InstanceNorm.apply(x, eps, act, residual, stats)
 
 
+def _param_grad(vals, param):
+    """gradient of a 1-D parameter: accumulated into the gradient arena when the parameter lives there, returned otherwise"""
+    tgt = DIRECT_GRADS.get(param.data_ptr())
+    if tgt is not None:
+        tgt.add_(vals)
+        _grad_ready(param)
+        return None
+    return vals
+
+
+class _GroupNorm(Function):
+    """GroupNorm(groups, C, affine=True) [+ReLU] [+residual] with its backward (csrc/nn.cu gn_bwd_*): the generators of the
+    translation block train through it.  translation_network.py:46, :472-483, :563-574."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps, act, residual, stats):
+        xh = nhwc(x)
+        N, H, W, C = xh.shape
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        if stats is None:
+            stats = _zeros_f64(N * C * 2, xh.device)
+            _call("dsr_channel_sums", _p(xh), N, H * W, C, _p(stats, torch.float64))
+        prm = _norm_params(xh, groups, w, b, eps, stats)
+        rh = nhwc(residual) if residual is not None else None
+        y = torch.empty_like(xh)
+        _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
+        if any(ctx.needs_input_grad):
+            hat = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)         # (mean, rstd, 0): gamma = beta = NULL
+            _call("dsr_norm_finalize", _p(stats, torch.float64), N, C, H * W, groups, None, None, eps, _p(hat))
+            ctx.save_for_backward(xh, hat, weight, bias)
+        ctx.cfg = (groups, act, residual is not None)
+        return nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, hat, weight, bias = ctx.saved_tensors
+        groups, act, has_res = ctx.cfg
+        N, H, W, C = xh.shape
+        g = nhwc(gy)
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        sums2 = _zeros_f64(N * C * 2, g.device)
+        _call("dsr_gn_bwd_sums", _p(xh), _p(g), _p(hat), _p(w), _p(b), N, H * W, C, act, _p(sums2, torch.float64))
+        coef = torch.empty(N * C * 2, device=g.device, dtype=torch.float32)
+        dgamma = torch.empty(C, device=g.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=g.device, dtype=torch.float32)
+        _call("dsr_gn_bwd_finalize", _p(sums2, torch.float64), _p(w), N, C, groups, H * W, _p(coef), _p(dgamma), _p(dbeta), 0)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gxh = torch.empty_like(xh)
+            _call("dsr_gn_bwd_apply", _p(xh), _p(g), _p(hat), _p(w), _p(b), _p(coef), _p(gxh), N, H * W, C, act)
+            gx = nchw(gxh)
+        gw = _param_grad(dgamma, weight) if ctx.needs_input_grad[1] else None
+        gb = _param_grad(dbeta, bias) if ctx.needs_input_grad[2] else None
+        gres = gy if (has_res and ctx.needs_input_grad[6]) else None
+        return gx, gw, gb, None, None, None, gres, None
+
+
 def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None, stats=None):
-    """GroupNorm(groups, C, affine=True) [+ReLU] [+residual], forward only (G_A_d is frozen on the hot
-    path, main_model.py:426).  translation_network.py:46."""
-    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
-                                    (residual is not None and residual.requires_grad)):
-        raise NotImplementedError("dsr_b200: GroupNorm backward is not on the main_network_best hot path "
-                                  "(G_A_d is frozen); run the translation generator under torch.no_grad()")
-    xh = nhwc(x)
-    N, H, W, C = xh.shape
-    prm = _norm_params(xh, groups, weight.detach().contiguous(), bias.detach().contiguous(), eps, stats)
-    rh = nhwc(residual) if residual is not None else None
-    y = torch.empty_like(xh)
-    _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
-    return nchw(y)
+    """GroupNorm(groups, C, affine=True) [+ReLU] [+residual].  translation_network.py:46."""
+    return _GroupNorm.apply(x, weight, bias, groups, eps, act, residual, stats)
 
 
 class _Act(Function):

@@ -1,10 +1,13 @@
-"""Translation generator G_A_d (frozen on the hot path) - drop-in for the ``define_Gen`` /
-``Generator`` part of the reference's ``models/translation_network.py``.
+"""Translation generator (``define_Gen`` / ``Generator``: G_A_d, frozen on the hot path) and the PatchGAN
+discriminator (``define_D`` / ``NLayerDiscriminator``) - drop-in for those parts of the reference's
+``models/translation_network.py``.
 
-Same module tree => same ``state_dict`` keys (``enc_img.model.*``, ``enc_depth.model.*``,
-``bottlenec.model.*.conv_block.*``, ``dec_depth.model.*``).  Forward only:
-the main training step never back-propagates into G_A_d (main_model.py:426); the backward of this
-family belongs to the translation_block row.
+Same module trees => same ``state_dict`` keys (``enc_img.model.*``, ``enc_depth.model.*``,
+``bottlenec.model.*.conv_block.*``, ``dec_depth.model.*``, discriminator ``model.N.*``).
+The main training step never back-propagates into G_A_d (main_model.py:426) and runs it under ``no_grad`` with the
+norm layers folded into the conv prologues; with gradients enabled the GroupNorm layers run as their own op
+(``ops.group_norm``, which has a backward), so both families train - the building blocks of the translation_block
+row (the ``TranslationModel`` step itself is not built yet).
 Reference: /root/reference/models/translation_network.py (file:line cited per symbol).
 """
 import functools
@@ -15,7 +18,7 @@ from torch.nn import init
 
 from . import ops
 from .networks import (Conv2d, ConvTranspose2d as _ConvT2d, DeviceModule, FusedSequential, GroupNorm, Identity,
-                       InstanceNorm2d, ReLU, Tanh, run_fused)
+                       InstanceNorm2d, LeakyReLU, ReLU, Tanh, run_fused)
 
 
 def get_norm_layer(norm_type="instance"):         # translation_network.py:34-52
@@ -182,3 +185,47 @@ class Generator(nn.Module):                       # translation_network.py:612-6
             return self.dec_depth(self.bottlenec(depth, img))
         depth = self.enc_depth(depth)
         return self.dec_depth(self.bottlenec(depth))
+
+
+class NLayerDiscriminator(nn.Module):             # translation_network.py:735-776
+    """PatchGAN discriminator: conv k4 s2 + LeakyReLU(0.2), (n_layers - 1) x [conv k4 s2, norm, LeakyReLU], conv k4 s1,
+    norm, LeakyReLU, conv k4 s1 -> 1 channel prediction map."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_bias=False):
+        super().__init__()
+        norm_layer = norm_layer or (lambda c: Identity())
+        kw, padw = 4, 1
+        sequence = [Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw, bias=True), LeakyReLU(0.2, True)]
+        nf_mult = 1
+        for n in range(1, n_layers):
+            nf_mult_prev, nf_mult = nf_mult, min(2 ** n, 8)
+            sequence += [Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw, bias=use_bias),
+                         norm_layer(ndf * nf_mult), LeakyReLU(0.2, True)]
+        nf_mult_prev, nf_mult = nf_mult, min(2 ** n_layers, 8)
+        sequence += [Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=1, padding=padw, bias=use_bias),
+                     norm_layer(ndf * nf_mult), LeakyReLU(0.2, True)]
+        sequence += [Conv2d(ndf * nf_mult, 1, kernel_size=kw, stride=1, padding=padw, bias=True)]
+        self.model = nn.Sequential(*sequence)      # plain Sequential: an Identity norm sits between conv and activation
+
+    def forward(self, input):
+        return self.model(input)
+
+
+def define_D(opt, input_type="depth"):            # translation_network.py:666-724
+    try:
+        input_nc = {"depth": 1, "normal": 3, "depth_normal": 4}[input_type]
+    except KeyError:
+        raise NotImplementedError("Input for discriminator [%s] is not recognized" % input_type)
+    norm_layer = get_norm_layer(norm_type=opt.norm_d)
+    use_bias = opt.norm_d == "instance"
+    if opt.netD == "basic":
+        net = NLayerDiscriminator(input_nc, opt.ndf, n_layers=3, norm_layer=norm_layer, use_bias=use_bias)
+    elif opt.netD == "n_layers":
+        net = NLayerDiscriminator(input_nc, opt.ndf, opt.n_layers_D, norm_layer=norm_layer, use_bias=use_bias)
+    elif opt.netD in ("pixel", "Gu"):
+        raise NotImplementedError("dsr_b200: discriminator [%s] is not built (README.md:51 trains with n_layers)" % opt.netD)
+    else:
+        raise NotImplementedError("Discriminator model name [%s] is not recognized" % opt.netD)
+    if getattr(opt, "use_spnorm", False):
+        raise NotImplementedError("dsr_b200: spectral normalisation of the discriminator is not built")
+    return init_net(net=net, init_type=opt.init_type, init_gain="leaky_relu", gpu_ids=opt.gpu_ids, param=0.2)

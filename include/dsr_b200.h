@@ -127,6 +127,16 @@ int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm, int N, lo
                     void* stream);
 int dsr_in_bwd_apply(const float* x, const float* dy, const float* prm, const double* sums2, float* dx, int N,
                      long P, int C, int act, void* stream);
+/* GroupNorm(groups, C, affine) [+ReLU] backward, translation_network.py:46 (the translation generators).  prm = (mean, rstd, 0)
+ * per (n, c) from dsr_norm_finalize with gamma = beta = NULL.  sums2 double [N][C][2] (pre-zeroed) = (sum g, sum g * xhat);
+ * finalize: coef float [N][C][2] = the two group means of the apply pass, dgamma / dbeta float [C] (=|+=);
+ * apply: dx = rstd * (gamma * g - coef0 - xhat * coef1). */
+int dsr_gn_bwd_sums(const float* x, const float* dy, const float* prm, const float* gamma, const float* beta, int N, long P,
+                    int C, int act, double* sums2, void* stream);
+int dsr_gn_bwd_finalize(const double* sums2, const float* gamma, int N, int C, int groups, long P, float* coef, float* dgamma,
+                        float* dbeta, int accumulate, void* stream);
+int dsr_gn_bwd_apply(const float* x, const float* dy, const float* prm, const float* gamma, const float* beta, const float* coef,
+                     float* dx, int N, long P, int C, int act, void* stream);
 /* 4-D parameter [D0][D1][R][S] <-> GEMM operand [(r*S+s)*Ck + ck][Co]; kdim selects which of D0/D1 is ck. */
 int dsr_pack_weight(const float* w, int D0, int D1, int R, int S, int kdim, float* out, void* stream);
 int dsr_unpack_weight(const float* packed, int D0, int D1, int R, int S, int kdim, float* w, int accumulate,

@@ -117,3 +117,34 @@ def translation_generator(sd, depth, img, n_blocks=9, n_down=2):
         j += 3
     x = _rconv(x, sd[f"dec_depth.model.{j}.weight"], sd[f"dec_depth.model.{j}.bias"], 7, 1)
     return torch.tanh(x)
+
+
+def nlayer_discriminator(sd, x, n_layers=3):
+    """translation_network.NLayerDiscriminator with norm_d='none' (models/translation_network.py:735-776): conv k4 s2 + bias,
+    LeakyReLU(0.2); (n_layers - 1) x [conv k4 s2, LeakyReLU]; conv k4 s1, LeakyReLU; conv k4 s1 + bias -> 1 channel.
+    Sequential indices: 0 | 2, 5, ... (conv, Identity, LeakyReLU) | last."""
+    x = F.leaky_relu(F.conv2d(x, sd["model.0.weight"], sd["model.0.bias"], stride=2, padding=1), 0.2)
+    j = 2
+    for _ in range(1, n_layers):
+        x = F.leaky_relu(F.conv2d(x, sd[f"model.{j}.weight"], sd.get(f"model.{j}.bias"), stride=2, padding=1), 0.2)
+        j += 3
+    x = F.leaky_relu(F.conv2d(x, sd[f"model.{j}.weight"], sd.get(f"model.{j}.bias"), stride=1, padding=1), 0.2)
+    j += 3
+    return F.conv2d(x, sd[f"model.{j}.weight"], sd[f"model.{j}.bias"], stride=1, padding=1)
+
+
+def gan_block_step(sd_g, sd_d, depth, img, real):
+    """The compute of BASELINE configs[4] (generator + PatchGAN discriminator, forward + backward) with the LSGAN terms of
+    models/translation_model.py: loss_G = 0.5 * MSE(D(G(depth, img)), 1) (:214), back-propagated through D into G;
+    loss_D = 0.5 * (MSE(D(real), 1) + MSE(D(fake.detach()), 0)) (:199-205), back-propagated into D.
+    sd_g / sd_d: state dicts whose tensors require grad.  -> dict(fake, pred_fake, loss_G, loss_D, grads_g, grads_d)."""
+    fake = translation_generator(sd_g, depth, img)
+    pred_fake = nlayer_discriminator(sd_d, fake)
+    loss_G = 0.5 * F.mse_loss(pred_fake, torch.ones_like(pred_fake))
+    gg = torch.autograd.grad(loss_G, [v for v in sd_g.values()], allow_unused=True)
+    pred_real = nlayer_discriminator(sd_d, real)
+    pred_fake_d = nlayer_discriminator(sd_d, fake.detach())
+    loss_D = 0.5 * (F.mse_loss(pred_real, torch.ones_like(pred_real)) + F.mse_loss(pred_fake_d, torch.zeros_like(pred_fake_d)))
+    gd = torch.autograd.grad(loss_D, [v for v in sd_d.values()])
+    return dict(fake=fake.detach(), pred_fake=pred_fake.detach(), loss_G=float(loss_G), loss_D=float(loss_D),
+                grads_g=dict(zip(sd_g.keys(), gg)), grads_d=dict(zip(sd_d.keys(), gd)))

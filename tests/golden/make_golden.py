@@ -236,6 +236,48 @@ def golden_metrics():
     print("wrote metrics", {n: float(v) for n, v in zip(names, out["c0/values"])})
 
 
+def golden_gan_blocks(B=2, H=64, W=64, tag="gan_blocks_b2_64"):
+    """Generator (img_depth, GroupNorm) + NLayerDiscriminator (norm_d none) of the live reference, forward + backward with the
+    LSGAN terms of translation_model.py:199-214 - the compute of BASELINE configs[4]."""
+    from types import SimpleNamespace
+    import torch.nn as nn
+    from models import translation_network as tn
+    torch.manual_seed(0)
+    og = SimpleNamespace(ngf_img=32, ngf_depth=32, ngf=64, norm="group", dropout=False, init_type="normal", gpu_ids=[],
+                         input_nc_img=3, n_downsampling=2, use_semantic=False, n_blocks=9, upsampling_type="transpose",
+                         output_nc_depth=1, input_nc_depth=1)
+    G = tn.define_Gen(og, input_type="img_depth")
+    od = SimpleNamespace(ndf=64, n_layers_D=3, norm_d="none", netD="n_layers", init_type="normal", gpu_ids=[], use_spnorm=False)
+    D = tn.define_D(od, input_type="depth")
+    g = torch.Generator().manual_seed(3)
+    depth = torch.rand(B, 1, H, W, generator=g) * 1.8 - 0.9
+    img = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    real = torch.rand(B, 1, H, W, generator=g) * 1.8 - 0.9
+    crit = tn.GANLoss("lsgan")
+    fake = G(depth, img)
+    pred_fake = D(fake)
+    loss_G = 0.5 * crit(pred_fake, True)                                   # translation_model.py:214
+    loss_G.backward()
+    out = {"in/depth": depth.numpy(), "in/img": img.numpy(), "in/real": real.numpy(),
+           "fake": fake.detach().numpy(), "pred_fake": pred_fake.detach().numpy(), "loss_G": np.float64(float(loss_G))}
+    for name, net in (("G", G), ("D", D)):
+        sd = net.state_dict()
+        out[f"wkeys/{name}"] = np.array(list(sd.keys()))
+        out[f"wsum/{name}"] = np.array([float(sum(v.double().abs().sum() for v in sd.values()))])
+    for gi, (n, prm) in enumerate(G.named_parameters()):
+        gr = prm.grad.detach().double().flatten()
+        out[f"gG/{n}"] = np.array([float(gr.norm()), float(gr @ proj_vec(gr.numel(), 2000 + gi))])
+    D.zero_grad()
+    loss_D = 0.5 * (crit(D(real), True) + crit(D(fake.detach()), False))   # translation_model.py:199-205
+    loss_D.backward()
+    out["loss_D"] = np.float64(float(loss_D))
+    for gi, (n, prm) in enumerate(D.named_parameters()):
+        gr = prm.grad.detach().double().flatten()
+        out[f"gD/{n}"] = np.array([float(gr.norm()), float(gr @ proj_vec(gr.numel(), 3000 + gi))])
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print("wrote", tag, float(loss_G), float(loss_D))
+
+
 def golden_resize():
     """F.interpolate bicubic / nearest vectors (the torch calls of main_sr_model.py:279-293, :361, :394-398)."""
     import torch.nn.functional as F
@@ -298,7 +340,7 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -312,3 +354,5 @@ if __name__ == "__main__":
         golden_i2d_step()
     if "metrics" in which:
         golden_metrics()
+    if "gan" in which:
+        golden_gan_blocks()

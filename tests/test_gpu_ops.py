@@ -258,9 +258,7 @@ def test_group_norm_fwd(ops):
     ref = F.relu(F.group_norm(x, 8, w, b, eps=1e-5))
     with torch.no_grad():
         out = ops.group_norm(cl(x), 8, w.cuda(), b.cuda(), 1e-5, 1)
-    assert torch.allclose(out.cpu(), ref, atol=3e-5)
-    with pytest.raises(NotImplementedError):
-        ops.group_norm(cl(x).requires_grad_(True), 8, w.cuda(), b.cuda(), 1e-5, 1)
+    assert torch.allclose(out.cpu(), ref, atol=3e-5)          # (the backward: tests/test_translation_blocks.py)
 
 
 # ---------------------------------------------------------------------------------------------
