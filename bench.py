@@ -27,6 +27,9 @@ WORKLOADS = {   # BASELINE.json configs[1] / configs[2]
     "c4": dict(B=1, H=512, W=640, sr=True, name="main_sr_model x2 depth super-resolution step (LR 512x640 -> HR 1024x1280, README.md:86), batch 1 per GPU"),
     # BASELINE.json configs[0] (the reference's own CPU-runnable case), on the GPU: I2D_model.py, README.md:28 flags
     "c1": dict(B=2, H=256, W=256, i2d=True, name="I2D Image Guidance Network training step, batch 2, 256x256"),
+    # BASELINE.json configs[4]: the two network families of translation_block (NOT the full TranslationModel, see
+    # dsr_b200/translation_blocks.py): generator + PatchGAN discriminator, LSGAN generator and discriminator steps
+    "c5": dict(B=6, H=256, W=256, gan=True, name="translation_block generator + n_layers PatchGAN discriminator, LSGAN G step + D step, batch 6, 256x256"),
     "tiny": dict(B=1, H=128, W=128, name="debug"),
 }
 FLOP_PER_PAIR_256 = 606.2e9      # 2*174.68 + 4*64.20 GMAC-pairs
@@ -37,6 +40,8 @@ FLOP_SR_LR_256 = 2e9 * (43.84 + 16.11)
 
 def step_flops(wl):
     px = wl["H"] * wl["W"] / 65536.0
+    if wl.get("gan"):        # generator fwd + dgrad + wgrad (50.55 GMAC each), discriminator: 3 forwards, 3 data-gradient and 2 weight-
+        return wl["B"] * 2e9 * (3 * 50.55 + 8 * 3.10) * px          # gradient passes of 3.10 GMAC (k4 convs 1-64-128-256-512-1)
     if wl.get("i2d"):        # Image_f forward (21.92 GMAC) + Task U-Net 128->1 forward + dgrad + wgrad (8.05 GMAC each) per image, 2 images per pair
         return wl["B"] * 2 * 2e9 * (21.92 + 3 * 8.05) * px
     if wl.get("sr"):
@@ -46,6 +51,12 @@ def step_flops(wl):
 
 def make_model(wl, gpu_ids, graph, name="bench"):
     from dsr_b200 import I2D_model, main_model, main_sr_model, options
+    if wl.get("gan"):
+        from dsr_b200 import translation_blocks
+        return translation_blocks.GanBlockStep(options.default_opt(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"],
+                                                                   crop_size_w=wl["W"], name=name, checkpoints_dir="/tmp/dsr_bench",
+                                                                   lr=0.0002, netD="n_layers", n_layers_D=3, norm_d="none", ndf=64,
+                                                                   cuda_graph=bool(graph)))
     if wl.get("i2d"):
         return I2D_model.I2DModel(options.i2d_flags(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"], crop_size_w=wl["W"],
                                                     name=name, checkpoints_dir="/tmp/dsr_bench", cuda_graph=bool(graph)))
@@ -116,16 +127,34 @@ def ncu_traffic(kernel):
     return None
 
 
-def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False):
+def cpu_gan_baseline(sds, batch, steps, warmup):
+    """oracle/ref_nets.gan_block_step (generator + discriminator forward / backward, torch CPU fp32) on the host cores"""
+    import torch
+    from oracle import ref_nets
+    sd_g = {k: v.detach().clone().float().requires_grad_(True) for k, v in sds["G_A"].items()}
+    sd_d = {k: v.detach().clone().float().requires_grad_(True) for k, v in sds["D_A_depth"].items()}
+    ts = []
+    for _ in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref_nets.gan_block_step(sd_g, sd_d, batch["A_d"], batch["A_i"], batch["B_d"])
+        ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    B = batch["A_d"].shape[0]
+    return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count())
+
+
+def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=False):
     """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
     import numpy as np
     import torch
     from oracle import ref_step
-    wl = dict(B=B, H=H, W=W, sr=sr, i2d=i2d)
+    wl = dict(B=B, H=H, W=W, sr=sr, i2d=i2d, gan=gan)
     if sds is None:
         torch.manual_seed(0)
         host = make_model(wl, [], False, name="cpu")
         sds = {n: getattr(host, "net" + n).state_dict() for n in host.model_names}
+    if gan:
+        return cpu_gan_baseline(sds, make_batch(wl, 1), steps, warmup)
     if i2d:
         orc = ref_step.OracleI2DStep(sds, lr=2e-4)
     else:
@@ -149,7 +178,7 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     Bs = min(wl["B"], 2)                      # bounded sample: B=2 of the workload's crops per step
-    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")))
+    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")))
     line = dict(impl="reference", metric="RGB-D train pair-samples/sec (main net)", value=r["value"], unit="pair-samples/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * r["s_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -234,8 +263,8 @@ def run_ours(args):
     dev_batches = [{k: (v.cuda() if torch.is_tensor(v) and v.dtype == torch.float32 else v) for k, v in b.items()}
                    for b in host_batches]
     np.random.seed(1234 + rank)
-    h2d = sum(host_batches[0][k].numel() * 4 for k in ("A_i", "B_i", "A_d", "B_d"))
-    if not wl.get("i2d"):
+    h2d = sum(host_batches[0][k].numel() * 4 for k in (("A_i", "A_d", "B_d") if wl.get("gan") else ("A_i", "B_i", "A_d", "B_d")))
+    if not wl.get("i2d") and not wl.get("gan"):
         h2d += 2 * B * 11 * 8 + 2 * B * (64 * 4 + 1) * 4          # camera tables + rectangle tables
 
     def barrier():
@@ -359,11 +388,11 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             Bc = min(B, 2)
-            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")))
+            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")))
             cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
                        sample=f"2 steps of batch {Bc} at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
         extras = None
-        if args.inference and not wl.get("sr") and not wl.get("i2d") and world == 1:
+        if args.inference and not wl.get("sr") and not wl.get("i2d") and not wl.get("gan") and world == 1:
             extras = inference_ms_per_frame(local)
         line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
                     unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,

@@ -16,11 +16,11 @@ import itertools
 import torch
 
 from . import networks, ops
-from .base_model import BaseModel
+from .base_model import BaseModel, GraphStepMixin
 from .main_model import ArenaAdam, ParamArena
 
 
-class I2DModel(BaseModel):
+class I2DModel(GraphStepMixin, BaseModel):
     @staticmethod
     def modify_commandline_options(parser, is_train=True):         # I2D_model.py:68-76
         parser.set_defaults(no_dropout=True)
@@ -56,10 +56,7 @@ class I2DModel(BaseModel):
         self.arena = None
         self.grad_sync = None
         self._in = None
-        # CUDA-graph replay of the whole step, as in MainModel (persistent inputs, device-side Adam state)
-        self.use_graph = bool(getattr(opt, "cuda_graph", False))
-        self.graph_warmup = 2
-        self._graph, self._gstream, self._eager_steps, self.graph_launches = None, None, 0, 0
+        self._graph_init(opt)        # CUDA-graph replay of the whole step (persistent inputs, device-side Adam state)
         if self.isTrain:
             if self.gpu_ids:
                 self.arena = ParamArena([self._unwrap(self.netTask)], self.device)
@@ -118,38 +115,7 @@ class I2DModel(BaseModel):
             self.loss_G.backward()
 
     def optimize_parameters(self, iters=0, fr=700):                 # I2D_model.py:237-250
-        if not (self.use_graph and self.device.type == "cuda" and self.isTrain):
-            return self._step_body()
-        from . import _lib
-        cur = torch.cuda.current_stream()
-        if self._graph is None:
-            if self._gstream is None:
-                self._gstream = torch.cuda.Stream()
-            gs = self._gstream
-            gs.wait_stream(cur)
-            with torch.cuda.stream(gs):     # warm-up and capture on ONE stream (autograd remembers each node's stream)
-                if self._eager_steps < self.graph_warmup:
-                    self._eager_steps += 1
-                    self._step_body()
-                    cur.wait_stream(gs)
-                    return
-                for k, v in list(vars(self).items()):
-                    if torch.is_tensor(v) and v.grad_fn is not None:
-                        setattr(self, k, v.detach())
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                l0 = _lib.LAUNCHES
-                with torch.cuda.graph(graph, stream=gs):
-                    self._step_body()
-                self._graph, self.graph_launches = graph, _lib.LAUNCHES - l0
-            cur.wait_stream(gs)
-        self.optimizer_G.sync_hyper()
-        self._graph.replay()
-        _lib.LAUNCHES += self.graph_launches
-        ops.WEIGHT_EPOCH += 1
-
-    def reset_graph(self):
-        self._graph, self._eager_steps = None, 0
+        self._graph_optimize()
 
     def _step_body(self):
         if self.device.type == "cuda":

@@ -158,3 +158,52 @@ class BaseModel(ABC):
             if net is not None:
                 for param in net.parameters():
                     param.requires_grad = requires_grad
+
+
+class GraphStepMixin:
+    """CUDA-graph replay of a whole training step for models whose step has no host-side randomness: the first
+    ``graph_warmup`` calls run ``_step_body`` eagerly, the next one captures it, later calls replay it.  Needs persistent
+    input buffers (``set_input`` copies into fixed device tensors) and device-side optimizer state (``ArenaAdam``).
+    (``MainModel`` has its own variant that also stages the rectangle tables drawn on the host.)"""
+    use_graph = False
+    graph_warmup = 2
+
+    def _graph_init(self, opt):
+        self.use_graph = bool(getattr(opt, "cuda_graph", False))
+        self._graph, self._gstream, self._eager_steps, self.graph_launches = None, None, 0, 0
+
+    def reset_graph(self):
+        self._graph, self._eager_steps = None, 0
+
+    def _graph_optimize(self):
+        from . import _lib, ops
+        if not (self.use_graph and self.device.type == "cuda" and self.isTrain):
+            return self._step_body()
+        cur = torch.cuda.current_stream()
+        if self._graph is None:
+            if self._gstream is None:
+                self._gstream = torch.cuda.Stream()
+            gs = self._gstream
+            gs.wait_stream(cur)
+            with torch.cuda.stream(gs):     # warm-up and capture on ONE stream (autograd remembers each node's stream)
+                if self._eager_steps < self.graph_warmup:
+                    self._eager_steps += 1
+                    self._step_body()
+                    cur.wait_stream(gs)
+                    return
+                for k, v in list(vars(self).items()):
+                    if torch.is_tensor(v) and v.grad_fn is not None:
+                        setattr(self, k, v.detach())
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0 = _lib.LAUNCHES
+                with torch.cuda.graph(graph, stream=gs):
+                    self._step_body()
+                self._graph, self.graph_launches = graph, _lib.LAUNCHES - l0
+            cur.wait_stream(gs)
+        for o in self.optimizers:
+            if hasattr(o, "sync_hyper"):
+                o.sync_hyper()
+        self._graph.replay()
+        _lib.LAUNCHES += self.graph_launches
+        ops.WEIGHT_EPOCH += 1
