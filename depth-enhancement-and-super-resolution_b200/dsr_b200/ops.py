@@ -1376,6 +1376,58 @@ def nearest(x, size):
     return y
 
 
+class _FovNormals(Function):
+    """translation_network.SurfaceNormals (models/translation_network.py:329-360): field-of-view normals."""
+
+    @staticmethod
+    def forward(ctx, depth):
+        d = planes(depth)
+        B, _, H, W = d.shape
+        out = torch.empty((B, 3, H, W), device=d.device, dtype=torch.float32)
+        _call("dsr_fov_normals_fwd", _p(d), B, H, W, _p(out))
+        ctx.save_for_backward(d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        B, _, H, W = d.shape
+        gd = torch.zeros_like(d)
+        _call("dsr_fov_normals_bwd", _p(d), _p(planes(g)), B, H, W, _p(gd))
+        return gd
+
+
+def fov_normals(depth):
+    return _FovNormals.apply(depth)
+
+
+class _CosSim(Function):
+    """CosSimLoss (models/translation_network.py:310-316): mean over pixels of 1 - cos(x, y) along dim 1; gradient to x."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        xp, yp = planes(x), planes(y.detach())
+        B, C, H, W = xp.shape
+        acc = _zeros_f64(1, xp.device)
+        _call("dsr_cos_sim_fwd", _p(xp), _p(yp), B, C, H * W, _p(acc, torch.float64))
+        out = torch.empty((), device=xp.device, dtype=torch.float32)
+        _call("dsr_cvt_f64_f32", _p(acc, torch.float64), 1, _p(out), 1, 1.0 / (B * H * W), 0)
+        ctx.save_for_backward(xp, yp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xp, yp = ctx.saved_tensors
+        B, C, H, W = xp.shape
+        gx = torch.empty_like(xp)
+        _call("dsr_cos_sim_bwd", _p(xp), _p(yp), B, C, H * W, _p(g.contiguous()), 1.0 / (B * H * W), _p(gx))
+        return gx, None
+
+
+def cos_sim_loss(x, y):
+    return _CosSim.apply(x, y)
+
+
 def ssim(a, b):
     """Mean SSIM (11x11 Gaussian, sigma 1.5).  pytorch_ssim/__init__.py:17-37.  Forward only."""
     a, b = planes(a.detach()), planes(b.detach())

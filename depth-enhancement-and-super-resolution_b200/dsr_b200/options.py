@@ -40,6 +40,19 @@ def i2d_flags(**overrides):
     return default_opt(**d)
 
 
+def translation_flags(**overrides):
+    """README.md:51 - the published translation_block training command (normal init for the parity fixtures) with the
+    defaults of TranslationModel.modify_commandline_options (translation_model.py:14-43)."""
+    d = dict(model="translation_block", model_type="translation", netD="n_layers", n_layers_D=3, norm_d="none", ndf=64, lr=0.0002,
+             beta1=0.5, max_distance=5100, batch_size=6, crop_size_h=256, crop_size_w=256, use_spnorm=False,
+             l_cycle_A_begin=10.0, l_cycle_A_end=10.0, l_cycle_B_begin=5.0, l_cycle_B_end=5.0, l_identity=1.0, l_normal=1.0,
+             l_depth_A_begin=5.0, l_depth_A_end=0.0, l_depth_B_begin=5.0, l_depth_B_end=0.0, l_mean_A=0.0, l_mean_B=0.0, l_tv_A=0.0,
+             l_max_iter=5000, l_num_iter=5000, num_iter_gen=3, num_iter_dis=1, no_idt_A=True, use_cycle_A=False, use_cycle_B=True,
+             disc_for_normals=True, disc_for_depth=True, inp_B="img_depth", w_decay_G=0.0001)
+    d.update(overrides)
+    return default_opt(**d)
+
+
 def main_flags(**overrides):
     """README.md:70 - the published main_network_best training command."""
     d = dict(use_image_for_trans=True, w_syn_l1=15.0, w_real_l1_d=40.0, norm_loss=True, w_syn_norm=2.0,

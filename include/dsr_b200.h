@@ -103,6 +103,15 @@ int dsr_depth_to_u16(const float* pred, int N, int H, int W, int crop, float sca
 int dsr_eval_metric_sums(const float* pred, const float* target, const float* input, const double* kinv, int B, int H, int W,
                          float hole_threshold, double max_depth, int with_ssim, double* out, void* stream);
 
+/* translation block only.  Field-of-view normals translation_network.SurfaceNormals (models/translation_network.py:329-360),
+ * fwd / bwd (gdepth zeroed by the caller, +=); CosSimLoss (:310-316): *out_sum += sum over pixels of 1 - cos(x, y) along the
+ * channel dimension, bwd: gx = coef * (*gscale) * d sum / dx. */
+int dsr_fov_normals_fwd(const float* depth, int B, int H, int W, float* out /*B,3,H,W*/, void* stream);
+int dsr_fov_normals_bwd(const float* depth, const float* gout, int B, int H, int W, float* gdepth /* += */, void* stream);
+int dsr_cos_sim_fwd(const float* x, const float* y, int B, int C, long plane, double* out_sum, void* stream);
+int dsr_cos_sim_bwd(const float* x, const float* y, int B, int C, long plane, const float* gscale, float coef, float* gx,
+                    void* stream);
+
 /* ---- network plumbing (NHWC fp32) ------------------------------------------------------------ */
 int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream);
 int dsr_nhwc_to_nchw(const float* x, float* y, int N, int C, long P, void* stream);

@@ -278,6 +278,78 @@ def golden_gan_blocks(B=2, H=64, W=64, tag="gan_blocks_b2_64"):
     print("wrote", tag, float(loss_G), float(loss_D))
 
 
+def translation_batch(B, H, W, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    d = lambda: torch.rand(B, 1, H, W, generator=g) * 1.6 - 0.7
+    A_d, B_d = d(), d()
+    A_d[:, :, 5:9, 10:20] = -1.0                       # holes of the A domain (hole_mask_A = depth <= -0.98)
+    return dict(A_name=["a"] * B, B_name=["b"] * B, A_img=torch.rand(B, 3, H, W, generator=g) * 2 - 1, A_depth=A_d,
+                B_img=torch.rand(B, 3, H, W, generator=g) * 2 - 1, B_depth=B_d)
+
+
+def golden_translation_step(B=1, H=64, W=64, n_gen=2, tag="translation_step_b1_64"):
+    """One TranslationModel.optimize_parameters (models/translation_model.py:274-291) of the live reference, default loss flags,
+    --num_iter_gen 2, normal init; the loop is unrolled here to record the first generator iteration's gradients."""
+    sys.argv = ["main.py", "--gpu_ids", "-1", "--custom_pathes", "--use_scannet", "--lr", "0.0002", "--model", "translation_block",
+                "--batch_size", str(B), "--name", "golden_tr", "--netD", "n_layers", "--crop_size_h", str(H), "--crop_size_w", str(W),
+                "--do_train", "--max_distance", "5100", "--init_type", "normal", "--model_type", "translation",
+                "--num_iter_gen", str(n_gen), "--checkpoints_dir", "/tmp/golden/ckpt"]
+    from options.train_options import TrainOptions
+    opt = TrainOptions().parse()
+    from models.translation_model import TranslationModel
+    torch.manual_seed(0)
+    model = TranslationModel(opt)
+    model.setup(opt)
+    batch = translation_batch(B, H, W)
+    out = {}
+    nets = ["G_A", "G_B", "D_A_depth", "D_B_depth", "D_A_normal", "D_B_normal"]
+    for name in nets:
+        sd = getattr(model, "net" + name).state_dict()
+        out[f"wkeys/{name}"] = np.array(list(sd.keys()))
+        out[f"wsum/{name}"] = np.array([float(sum(v.double().abs().sum() for v in sd.values()))])
+    model.set_input(batch)
+    model.set_requires_grad(model.disc, False)
+    for it in range(opt.num_iter_gen):
+        model.forward()
+        model.zero_grad([model.netG_A, model.netG_B])
+        model.backward_G()
+        if it == 0:
+            for k in ("fake_depth_B", "fake_depth_A", "rec_depth_B", "idt_B", "fake_norm_B", "real_norm_A"):
+                out["s0/" + k] = getattr(model, k).detach().numpy()
+            for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+                out["s0/loss/" + k] = np.float64(float(getattr(model, "loss_" + k)))
+            out["s0/loss/G"] = np.float64(float(model.loss_G))
+            gi = 0
+            for name in ("G_A", "G_B"):
+                for n, prm in getattr(model, "net" + name).named_parameters():
+                    gr = prm.grad.detach().double().flatten()
+                    out[f"s0/g/{name}/{n}"] = np.array([float(gr.norm()), float(gr @ proj_vec(gr.numel(), 4000 + gi))])
+                    gi += 1
+        model.optimizer_G.step()
+    model.set_requires_grad(model.disc, True)
+    model.set_requires_grad([model.netG_A, model.netG_B], False)
+    model.zero_grad(model.disc)
+    model.backward_D_A()
+    model.backward_D_B()
+    gi = 0
+    for name in ("D_A_depth", "D_A_normal", "D_B_depth", "D_B_normal"):
+        out["end/loss/" + name] = np.float64(float(getattr(model, "loss_" + name)))
+        for n, prm in getattr(model, "net" + name).named_parameters():
+            gr = prm.grad.detach().double().flatten()
+            out[f"end/g/{name}/{n}"] = np.array([float(gr.norm()), float(gr @ proj_vec(gr.numel(), 5000 + gi))])
+            gi += 1
+    model.optimizer_D.step()
+    for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+        out["end/loss/" + k] = np.float64(float(getattr(model, "loss_" + k)))
+    out["end/fake_depth_B"] = model.fake_depth_B.detach().numpy()
+    for name in nets:                                   # weights after the step: pins both Adam variants
+        sd = getattr(model, "net" + name).state_dict()
+        v = torch.cat([t.double().flatten() for t in sd.values()])
+        out[f"end/w/{name}"] = np.array([float(v.norm()), float(v @ proj_vec(v.numel(), 6000))])
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print("wrote", tag, {k: float(v) for k, v in out.items() if k.startswith("s0/loss/")})
+
+
 def golden_resize():
     """F.interpolate bicubic / nearest vectors (the torch calls of main_sr_model.py:279-293, :361, :394-398)."""
     import torch.nn.functional as F
@@ -340,7 +412,7 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -356,3 +428,5 @@ if __name__ == "__main__":
         golden_metrics()
     if "gan" in which:
         golden_gan_blocks()
+    if "translation" in which:
+        golden_translation_step()

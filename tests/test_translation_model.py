@@ -1,0 +1,142 @@
+"""``TranslationModel`` (SURVEY.md section 8f rank 3 / BASELINE configs[4]): the oracle against golden vectors of one
+optimize_parameters call of the live reference (CPU), and the CUDA model against golden + oracle (GPU), main-step gates."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_translation
+from tests_proj import proj_vec
+from util import cosine, load_golden, rel_l2
+
+NETS = ["G_A", "G_B", "D_A_depth", "D_B_depth", "D_A_normal", "D_B_normal"]
+DISCS = ["D_A_depth", "D_A_normal", "D_B_depth", "D_B_normal"]
+
+
+def translation_batch(B, H, W, seed=4):          # == tests/golden/make_golden.py:translation_batch
+    g = torch.Generator().manual_seed(seed)
+    d = lambda: torch.rand(B, 1, H, W, generator=g) * 1.6 - 0.7
+    A_d, B_d = d(), d()
+    A_d[:, :, 5:9, 10:20] = -1.0
+    return dict(A_name=["a"] * B, B_name=["b"] * B, A_img=torch.rand(B, 3, H, W, generator=g) * 2 - 1, A_depth=A_d,
+                B_img=torch.rand(B, 3, H, W, generator=g) * 2 - 1, B_depth=B_d)
+
+
+def _model(gpu_ids=()):
+    from dsr_b200 import options, translation_model
+    opt = options.translation_flags(gpu_ids=[], batch_size=1, crop_size_h=64, crop_size_w=64, num_iter_gen=2, name="t",
+                                    checkpoints_dir="/tmp/dsr_ck")
+    torch.manual_seed(0)
+    host = translation_model.TranslationModel(opt)
+    sds = {n: {k: v.detach().clone() for k, v in getattr(host, "net" + n).state_dict().items()} for n in NETS}
+    if not gpu_ids:
+        return host, sds
+    opt.gpu_ids = list(gpu_ids)
+    dev = translation_model.TranslationModel(opt)
+    for n, sd in sds.items():
+        dev._unwrap(getattr(dev, "net" + n)).load_state_dict(sd)
+    return dev, sds
+
+
+def test_translation_oracle_matches_reference():
+    g = load_golden("translation_step_b1_64.npz")
+    host, sds = _model()
+    for n in NETS:                                   # same seed + constructor order => the golden run's weights
+        assert list(sds[n].keys()) == list(g["wkeys/" + n]), n
+        a = float(sum(v.double().abs().sum() for v in sds[n].values()))
+        assert abs(a - float(g["wsum/" + n][0])) <= 1e-9 * a, n
+    orc = ref_translation.OracleTranslationStep(sds, num_iter_gen=2)
+    out = orc.step(translation_batch(1, 64, 64))
+    f = out["first"]
+    for k in ("fake_depth_B", "fake_depth_A", "rec_depth_B", "idt_B", "fake_norm_B", "real_norm_A"):
+        assert rel_l2(f["tensors"][k], g["s0/" + k]) <= 2e-5, k
+    for k, v in f["losses"].items():
+        assert abs(v - float(g["s0/loss/" + k])) <= 2e-5 * abs(float(g["s0/loss/" + k])), (k, v)
+    gi = 0
+    for name in ("G_A", "G_B"):
+        for n in sds[name]:
+            ref_norm, ref_proj = g[f"s0/g/{name}/{n}"]
+            gr = f["grads"][(name, n)].double().flatten()
+            assert abs(float(gr.norm()) - ref_norm) <= 2e-3 * ref_norm, (name, n)
+            assert abs(float(gr @ proj_vec(gr.numel(), 4000 + gi)) - ref_proj) <= 2e-3 * ref_norm, (name, n)
+            gi += 1
+    for k in DISCS + ["G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"]:
+        assert abs(out["losses"][k] - float(g["end/loss/" + k])) <= 2e-3 * abs(float(g["end/loss/" + k])), k
+    for n in NETS:                                   # weights after the whole call: both Adam variants (weight decay on G)
+        v = torch.cat([t.detach().double().flatten() for t in orc.sd[n].values()])
+        ref_norm, ref_proj = g["end/w/" + n]
+        assert abs(float(v.norm()) - ref_norm) <= 1e-6 * ref_norm and abs(float(v @ proj_vec(v.numel(), 6000)) - ref_proj) <= 1e-4 * ref_norm, n
+
+
+@pytest.mark.gpu
+def test_fov_normals_and_cos_sim_ops(built_lib):
+    from dsr_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    for (H, W) in ((40, 56), (64, 64), (2, 3)):
+        d = (torch.rand(2, 1, H, W, generator=g) * 1.6 - 0.7).requires_grad_(True)
+        go = torch.randn(2, 3, H, W, generator=g)
+        ref = ref_translation.fov_normals(d)
+        (ref * go).sum().backward()
+        dc = d.detach().cuda().requires_grad_(True)
+        out = ops.fov_normals(dc)
+        (out * go.cuda()).sum().backward()
+        assert float((out.detach().cpu() - ref.detach()).abs().max()) <= 2e-5          # unit normals, fp32 cross products
+        assert rel_l2(dc.grad.cpu(), d.grad) <= 2e-3
+    x = torch.randn(2, 3, 17, 23, generator=g).requires_grad_(True)
+    y = torch.randn(2, 3, 17, 23, generator=g)
+    ref = ref_translation.cos_sim_loss(x, y)
+    ref.backward()
+    xc = x.detach().cuda().requires_grad_(True)
+    out = ops.cos_sim_loss(xc, y.cuda())
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 1e-6 and rel_l2(xc.grad.cpu(), x.grad) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_translation_step_matches_reference_golden_and_oracle(built_lib):
+    g = load_golden("translation_step_b1_64.npz")
+    model, sds = _model(gpu_ids=[0])
+    batch = translation_batch(1, 64, 64)
+    orc = ref_translation.OracleTranslationStep(sds, num_iter_gen=2)
+    ref = orc.step(batch)
+    # first generator iteration by hand (forward + backward_G) to compare gradients before Adam moves the weights
+    model.set_input(batch)
+    model.set_requires_grad(model.disc, False)
+    model.forward()
+    model.optimizer_G.zero_grad()
+    model.backward_G()
+    for k in ("fake_depth_B", "fake_depth_A", "rec_depth_B", "idt_B"):
+        assert rel_l2(getattr(model, k).detach().cpu(), g["s0/" + k]) <= 1e-2, k                     # the gate
+        assert rel_l2(getattr(model, k).detach().cpu(), ref["first"]["tensors"][k]) <= 2e-3, k
+    for k in ("fake_norm_B", "real_norm_A"):
+        assert rel_l2(getattr(model, k).detach().cpu(), g["s0/" + k]) <= 1e-2, k
+    for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+        v, want = float(getattr(model, "loss_" + k)), float(g["s0/loss/" + k])
+        assert abs(v - want) <= 1e-3 * abs(want), (k, v, want)
+    assert abs(float(model.loss_G) - float(g["s0/loss/G"])) <= 1e-3 * float(g["s0/loss/G"])
+    fa, fb = [], []
+    for name in ("G_A", "G_B"):
+        for n, prm in model._unwrap(getattr(model, "net" + name)).named_parameters():
+            gr = ref["first"]["grads"].get((name, n))
+            if gr is None or float(gr.norm()) == 0.0:
+                continue
+            c = cosine(prm.grad.detach().cpu(), gr)
+            assert c >= 0.999, (name, n, c)
+            fa.append(prm.grad.detach().cpu().flatten()); fb.append(gr.flatten())
+    assert cosine(torch.cat(fa), torch.cat(fb)) >= 0.999
+    model.set_requires_grad(model.disc, True)
+    # the whole call from the same initial weights on a fresh model: losses at the end and the weights after both updates
+    model2, _ = _model(gpu_ids=[0])
+    model2.set_input(batch)
+    model2.optimize_parameters(0)
+    for k in DISCS + ["G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"]:
+        v, want = float(getattr(model2, "loss_" + k)), float(g["end/loss/" + k])
+        assert abs(v - want) <= 1e-2 * abs(want), (k, v, want)        # behind one Adam step: gate-level tolerance (as in the main step)
+    for n in NETS:
+        net = model2._unwrap(getattr(model2, "net" + n))
+        v = torch.cat([t.detach().double().flatten().cpu() for t in net.state_dict().values()])
+        ref_norm, ref_proj = g["end/w/" + n]
+        assert abs(float(v.norm()) - ref_norm) <= 1e-5 * ref_norm, n
+    losses = model2.get_current_losses()
+    assert all(np.isfinite(v) for v in losses.values()) and set(model2.loss_names) == set(losses)
