@@ -27,9 +27,10 @@ WORKLOADS = {   # BASELINE.json configs[1] / configs[2]
     "c4": dict(B=1, H=512, W=640, sr=True, name="main_sr_model x2 depth super-resolution step (LR 512x640 -> HR 1024x1280, README.md:86), batch 1 per GPU"),
     # BASELINE.json configs[0] (the reference's own CPU-runnable case), on the GPU: I2D_model.py, README.md:28 flags
     "c1": dict(B=2, H=256, W=256, i2d=True, name="I2D Image Guidance Network training step, batch 2, 256x256"),
-    # BASELINE.json configs[4]: the two network families of translation_block (NOT the full TranslationModel, see
-    # dsr_b200/translation_blocks.py): generator + PatchGAN discriminator, LSGAN generator and discriminator steps
-    "c5": dict(B=6, H=256, W=256, gan=True, name="translation_block generator + n_layers PatchGAN discriminator, LSGAN G step + D step, batch 6, 256x256"),
+    # BASELINE.json configs[4]: TranslationModel.optimize_parameters (3 generator iterations + 1 discriminator update), README.md:51
+    "c5": dict(B=6, H=256, W=256, tr=True, name="translation_block TranslationModel.optimize_parameters (3 G iterations + 1 D update), batch 6, 256x256"),
+    # the two network families alone (dsr_b200/translation_blocks.py): generator + PatchGAN discriminator, LSGAN G step + D step
+    "c5b": dict(B=6, H=256, W=256, gan=True, name="generator + n_layers PatchGAN discriminator, LSGAN G step + D step, batch 6, 256x256"),
     "tiny": dict(B=1, H=128, W=128, name="debug"),
 }
 FLOP_PER_PAIR_256 = 606.2e9      # 2*174.68 + 4*64.20 GMAC-pairs
@@ -40,6 +41,9 @@ FLOP_SR_LR_256 = 2e9 * (43.84 + 16.11)
 
 def step_flops(wl):
     px = wl["H"] * wl["W"] / 65536.0
+    if wl.get("tr"):         # per generator iteration: 5 generator forwards + 4 backward (dgrad + wgrad) = 13 passes of 50.55 GMAC,
+        # 4 discriminator forwards + 4 data gradients (3.1 GMAC each); discriminator update: 8 forwards + 8 dgrad + 8 wgrad
+        return wl["B"] * 2e9 * (3 * (13 * 50.55 + 8 * 3.10) + 24 * 3.10) * px
     if wl.get("gan"):        # generator fwd + dgrad + wgrad (50.55 GMAC each), discriminator: 3 forwards, 3 data-gradient and 2 weight-
         return wl["B"] * 2e9 * (3 * 50.55 + 8 * 3.10) * px          # gradient passes of 3.10 GMAC (k4 convs 1-64-128-256-512-1)
     if wl.get("i2d"):        # Image_f forward (21.92 GMAC) + Task U-Net 128->1 forward + dgrad + wgrad (8.05 GMAC each) per image, 2 images per pair
@@ -51,6 +55,11 @@ def step_flops(wl):
 
 def make_model(wl, gpu_ids, graph, name="bench"):
     from dsr_b200 import I2D_model, main_model, main_sr_model, options
+    if wl.get("tr"):
+        from dsr_b200 import translation_model
+        return translation_model.TranslationModel(options.translation_flags(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"],
+                                                                            crop_size_w=wl["W"], name=name, checkpoints_dir="/tmp/dsr_bench",
+                                                                            cuda_graph=bool(graph)))
     if wl.get("gan"):
         from dsr_b200 import translation_blocks
         return translation_blocks.GanBlockStep(options.default_opt(gpu_ids=gpu_ids, batch_size=wl["B"], crop_size_h=wl["H"],
@@ -70,6 +79,9 @@ def make_model(wl, gpu_ids, graph, name="bench"):
 
 def make_batch(wl, seed):
     from oracle.ref_step import synthetic_batch, synthetic_sr_batch      # synthetic input generator only (shared with the tests)
+    if wl.get("tr"):
+        b = synthetic_batch(wl["B"], wl["H"], wl["W"], seed=seed, depth_kind="smooth")
+        return dict(A_name=b["A_paths"], B_name=b["B_paths"], A_img=b["A_i"], A_depth=b["A_d"], B_img=b["B_i"], B_depth=b["B_d"])
     if wl.get("sr"):
         return synthetic_sr_batch(wl["B"], wl["H"], wl["W"], seed=seed, depth_kind="smooth")
     return synthetic_batch(wl["B"], wl["H"], wl["W"], seed=seed, depth_kind="smooth")
@@ -143,16 +155,27 @@ def cpu_gan_baseline(sds, batch, steps, warmup):
     return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count())
 
 
-def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=False):
+def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=False, tr=False):
     """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
     import numpy as np
     import torch
     from oracle import ref_step
-    wl = dict(B=B, H=H, W=W, sr=sr, i2d=i2d, gan=gan)
+    wl = dict(B=B, H=H, W=W, sr=sr, i2d=i2d, gan=gan, tr=tr)
     if sds is None:
         torch.manual_seed(0)
         host = make_model(wl, [], False, name="cpu")
         sds = {n: getattr(host, "net" + n).state_dict() for n in host.model_names}
+    if tr:
+        from oracle import ref_translation
+        orc = ref_translation.OracleTranslationStep(sds)
+        batch = make_batch(wl, 1)
+        ts = []
+        for _ in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.step(batch)
+            ts.append(time.perf_counter() - t0)
+        ts = ts[warmup:]
+        return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count())
     if gan:
         return cpu_gan_baseline(sds, make_batch(wl, 1), steps, warmup)
     if i2d:
@@ -178,7 +201,7 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     Bs = min(wl["B"], 2)                      # bounded sample: B=2 of the workload's crops per step
-    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")))
+    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
     line = dict(impl="reference", metric="RGB-D train pair-samples/sec (main net)", value=r["value"], unit="pair-samples/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * r["s_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -257,14 +280,16 @@ def run_ours(args):
     host_batches = []
     for i in range(2):
         b = make_batch(wl, 1 + 17 * rank + i)
-        for k in ("A_i", "B_i", "A_d", "B_d"):
-            b[k] = b[k].pin_memory()
+        for k in b:
+            if torch.is_tensor(b[k]) and b[k].dtype == torch.float32:
+                b[k] = b[k].pin_memory()
         host_batches.append(b)
     dev_batches = [{k: (v.cuda() if torch.is_tensor(v) and v.dtype == torch.float32 else v) for k, v in b.items()}
                    for b in host_batches]
     np.random.seed(1234 + rank)
-    h2d = sum(host_batches[0][k].numel() * 4 for k in (("A_i", "A_d", "B_d") if wl.get("gan") else ("A_i", "B_i", "A_d", "B_d")))
-    if not wl.get("i2d") and not wl.get("gan"):
+    in_keys = ("A_img", "A_depth", "B_img", "B_depth") if wl.get("tr") else (("A_i", "A_d", "B_d") if wl.get("gan") else ("A_i", "B_i", "A_d", "B_d"))
+    h2d = sum(host_batches[0][k].numel() * 4 for k in in_keys)
+    if not any(wl.get(k) for k in ("i2d", "gan", "tr")):
         h2d += 2 * B * 11 * 8 + 2 * B * (64 * 4 + 1) * 4          # camera tables + rectangle tables
 
     def barrier():
@@ -388,11 +413,11 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             Bc = min(B, 2)
-            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")))
+            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
             cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
                        sample=f"2 steps of batch {Bc} at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
         extras = None
-        if args.inference and not wl.get("sr") and not wl.get("i2d") and not wl.get("gan") and world == 1:
+        if args.inference and not any(wl.get(k) for k in ("sr", "i2d", "gan", "tr")) and world == 1:
             extras = inference_ms_per_frame(local)
         line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
                     unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,

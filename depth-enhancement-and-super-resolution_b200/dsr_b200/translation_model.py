@@ -15,7 +15,7 @@ real_img_B)`` twice per forward and throws the first result away (:177-178); her
 import torch
 
 from . import ops, translation_network
-from .base_model import BaseModel
+from .base_model import BaseModel, GraphStepMixin
 from .main_model import ArenaAdam, ParamArena
 from .translation_blocks import GanBlockStep
 
@@ -27,7 +27,7 @@ def data_to_meters(x, max_distance):                                # util/util.
     return (x * scale + scale) / 1000.0
 
 
-class TranslationModel(BaseModel):
+class TranslationModel(GraphStepMixin, BaseModel):
     @staticmethod
     def modify_commandline_options(parser, is_train):               # translation_model.py:13-43
         for name, default in (("l_cycle_A_begin", 10.0), ("l_cycle_A_end", 10.0), ("l_cycle_B_begin", 5.0), ("l_cycle_B_end", 5.0),
@@ -97,12 +97,15 @@ class TranslationModel(BaseModel):
             self.opt_names = ["optimizer_G", "optimizer_D"]
         self._in = None
         self.loss_idt_A = 0
+        self._graph_init(opt)        # optional CUDA-graph replay of the whole optimize_parameters call (opt.cuda_graph)
 
     def set_input(self, input):                                     # translation_model.py:129-137
         self.name_A, self.name_B = input["A_name"], input["B_name"]
         src = dict(real_img_A=input["A_img"], real_depth_A=input["A_depth"], real_img_B=input["B_img"], real_depth_B=input["B_depth"])
         shapes = {k: tuple(v.shape) for k, v in src.items()}
         if self._in is None or self._in["shapes"] != shapes:
+            if getattr(self, "_graph", None) is not None:
+                raise RuntimeError("dsr_b200: the captured CUDA graph is bound to the first batch shape; call reset_graph()")
             self._in = dict(shapes=shapes)
             for k, v in src.items():
                 self._in[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
@@ -199,6 +202,9 @@ class TranslationModel(BaseModel):
         self.optimizer_G.step()
 
     def optimize_parameters(self, iters=0, fr=1):                   # translation_model.py:274-291
+        self._graph_optimize()
+
+    def _step_body(self):
         if self.device.type == "cuda":
             ops.zero_pool_reset(self.device)
         self.set_requires_grad(self.disc, False)
@@ -218,8 +224,6 @@ class TranslationModel(BaseModel):
             self.backward_D_B()
             self.optimizer_D.step()
         self.set_requires_grad([self.netG_A, self.netG_B], True)
-
-    _step_body = optimize_parameters
 
     def calc_l_step(self):                                          # :293-298
         o = self.opt
