@@ -209,3 +209,131 @@ extern "C" int dsr_conv_out1(const float* x, int N, int H, int W, int C, const f
                                                                                   pad_mode, act_out, out, Ho, Wo);
     return dsr_check_launch("conv_out1");
 }
+
+// Data gradient of a stride-1 convolution that has ONE output channel (the generator heads 64 -> 1 of the translation block,
+// the last discriminator layer 512 -> 1): gx[n][i][j][c] = sum_{r,s} g[n][i + off - r][j + off - s] * W[c][r][s]  (g = 0 outside).
+// An outer product per tap, bound by writing gx: one thread = one pixel, 16 channels at a time in registers, the gradient
+// tile and the [tap][channel] weights in shared memory.  (The CUDA-core fallback spent ~5 ms per 7x7 head at 6 x 256 x 256.)
+__global__ void __launch_bounds__(256)
+conv1_dgrad_kernel(const float* __restrict__ g, int N, int Ho, int Wo, const float* __restrict__ w /* [C][R][S] */, int C, int R,
+                   int S, int off, float* __restrict__ gx, int Hx, int Wx) {
+    extern __shared__ float d1_sm[];
+    const int PH = O1_TILE + R - 1, PW = O1_TILE + S - 1;
+    float* tile = d1_sm;                                    // [PH][PW] gradient patch
+    float* wsm = d1_sm + ((PH * PW + 3) & ~3);              // [R*S][C]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int i = tid; i < R * S * C; i += 256) {
+        const int tap = i / C, c = i - tap * C;
+        wsm[i] = w[(long)c * R * S + tap];
+    }
+    const int tiles_w = (Wx + O1_TILE - 1) / O1_TILE, tiles_h = (Hx + O1_TILE - 1) / O1_TILE;
+    for (int t = blockIdx.x; t < N * tiles_h * tiles_w; t += gridDim.x) {
+        const int n = t / (tiles_h * tiles_w), r0 = t - n * tiles_h * tiles_w;
+        const int i0 = (r0 / tiles_w) * O1_TILE, j0 = (r0 % tiles_w) * O1_TILE;
+        __syncthreads();
+        for (int q = tid; q < PH * PW; q += 256) {
+            const int py = q / PW, px = q - py * PW;
+            const int gy = i0 + off - (R - 1) + py, gxx = j0 + off - (S - 1) + px;
+            tile[q] = (gy >= 0 && gy < Ho && gxx >= 0 && gxx < Wo) ? g[((long)n * Ho + gy) * Wo + gxx] : 0.f;
+        }
+        __syncthreads();
+        const int i = i0 + ty, j = j0 + tx;
+        if (i >= Hx || j >= Wx) continue;
+        float* o = gx + (((long)n * Hx + i) * Wx + j) * C;
+        for (int c0 = 0; c0 < C; c0 += 16) {
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            for (int r = 0; r < R; ++r)
+                for (int s = 0; s < S; ++s) {
+                    const float gv = tile[(ty + (R - 1) - r) * PW + tx + (S - 1) - s];      // g[i + off - r][j + off - s]
+                    const float* wr = wsm + (r * S + s) * C + c0;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wr + e);
+                        acc[e] += gv * wv.x; acc[e + 1] += gv * wv.y; acc[e + 2] += gv * wv.z; acc[e + 3] += gv * wv.w;
+                    }
+                }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) st4(o + c0 + e, make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
+        }
+    }
+}
+extern "C" int dsr_conv1_dgrad(const float* g, int N, int Ho, int Wo, const float* w, int C, int R, int S, int off, float* gx,
+                               int Hx, int Wx, void* stream) {
+    DSR_REQUIRE(g && w && gx && N > 0 && Ho > 0 && Wo > 0 && Hx > 0 && Wx > 0, "bad arguments");
+    DSR_REQUIRE(C >= 16 && (C & 15) == 0 && R >= 1 && S >= 1 && R <= 9 && S <= 9 && !((uintptr_t)gx & 15), "C % 16 == 0, kernel size 1..9");
+    const size_t smem = ((((size_t)(O1_TILE + R - 1) * (O1_TILE + S - 1) + 3) & ~(size_t)3) + (size_t)R * S * C) * sizeof(float);
+    DSR_REQUIRE(smem <= 200 * 1024, "weights do not fit shared memory");
+    static size_t raised = 0;
+    if (smem > 48 * 1024 && smem > raised) {
+        if (cudaFuncSetAttribute(conv1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            dsr_set_error("conv1_dgrad: cannot raise dynamic shared memory to %d", (int)smem);
+            return DSR_ERR_CUDA;
+        }
+        raised = smem;
+    }
+    const int tiles = N * dsr_cdiv(Hx, O1_TILE) * dsr_cdiv(Wx, O1_TILE);
+    const int cap = dsr_num_sms() * 4;
+    conv1_dgrad_kernel<<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(g, N, Ho, Wo, w, C, R, S, off, gx, Hx, Wx);
+    return dsr_check_launch("conv1_dgrad");
+}
+
+// Border term of the data gradient of a stride-2, padding-1 Conv2d whose padding is replicate / reflect (the generator
+// encoders, translation_network.py:478).  With gxp = the gradient w.r.t. the explicitly padded input (H+2 x W+2),
+//   gx = gxp[1..H][1..W]  (the zero-padding data gradient: the tcgen05 transposed-phase GEMM)
+//      + the one-pixel FRAME of gxp folded onto the source pixels the padding mode read it from.
+// The frame is 2(W+2)+2H pixels per image with <= 2x2 taps each, so this kernel evaluates it directly: one warp per
+// affected source pixel, lanes over input channels, frame pixels summed in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+conv_s2_border_dgrad_kernel(const float* __restrict__ g, int N, int Ho, int Wo, int Co, const float* __restrict__ w /* [Co][Ci][R][S] */,
+                            int Ci, int R, int S, int mode, float* __restrict__ gx, int H, int W) {
+    const int lo_h = mode == DSR_PAD_REFLECT ? 1 : 0, hi_h = mode == DSR_PAD_REFLECT ? H - 2 : H - 1;
+    const int lo_w = mode == DSR_PAD_REFLECT ? 1 : 0, hi_w = mode == DSR_PAD_REFLECT ? W - 2 : W - 1;
+    const int nr = lo_h == hi_h ? 1 : 2, nc = lo_w == hi_w ? 1 : 2;
+    const int per_img = nr * W + (H - nr) * nc;
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long item = warp; item < (long)N * per_img; item += nwarps) {
+        const int n = (int)(item / per_img), q = (int)(item - (long)n * per_img);
+        int i, j;
+        if (q < nr * W) { i = q / W == 0 ? lo_h : hi_h; j = q - (q / W) * W; }
+        else {
+            const int q2 = q - nr * W, k = q2 / nc;
+            i = k; if (i >= lo_h) ++i; if (nr == 2 && i >= hi_h) ++i;
+            j = (q2 - k * nc) == 0 ? lo_w : hi_w;
+        }
+        // padded rows / columns (frame or centre) that read source row i / column j
+        int ph[3], pw[3], nph = 0, npw = 0;
+        ph[nph++] = i + 1; if (i == lo_h) ph[nph++] = 0; if (i == hi_h) ph[nph++] = H + 1;
+        pw[npw++] = j + 1; if (j == lo_w) pw[npw++] = 0; if (j == hi_w) pw[npw++] = W + 1;
+        for (int c = lane; c < Ci; c += 32) {
+            float acc = 0.f;
+            for (int a = 0; a < nph; ++a)
+                for (int b = 0; b < npw; ++b) {
+                    if (a == 0 && b == 0) continue;                       // the centre pixel: already in gx
+                    for (int r = ph[a] & 1; r < R; r += 2) {
+                        const int oh = (ph[a] - r) >> 1;
+                        if (ph[a] - r < 0 || oh >= Ho) continue;
+                        for (int s = pw[b] & 1; s < S; s += 2) {
+                            const int ow = (pw[b] - s) >> 1;
+                            if (pw[b] - s < 0 || ow >= Wo) continue;
+                            const float* gp = g + (((long)n * Ho + oh) * Wo + ow) * Co;
+                            const float* wp = w + ((long)c * R + r) * S + s;
+                            for (int co = 0; co < Co; ++co) acc = fmaf(gp[co], wp[(long)co * Ci * R * S], acc);
+                        }
+                    }
+                }
+            gx[(((long)n * H + i) * W + j) * Ci + c] += acc;
+        }
+    }
+}
+extern "C" int dsr_conv_s2_border_dgrad(const float* g, int N, int Ho, int Wo, int Co, const float* w, int Ci, int R, int S,
+                                        int pad_mode, float* gx, int H, int W, void* stream) {
+    DSR_REQUIRE(g && w && gx && N > 0 && Ho > 0 && Wo > 0 && Co > 0 && Ci > 0 && H > 0 && W > 0, "bad arguments");
+    DSR_REQUIRE(R >= 1 && S >= 1 && Ho == (H + 2 - R) / 2 + 1 && Wo == (W + 2 - S) / 2 + 1, "stride 2, padding 1 geometry");
+    DSR_REQUIRE(pad_mode == DSR_PAD_REPLICATE || (pad_mode == DSR_PAD_REFLECT && H >= 2 && W >= 2), "replicate or reflect padding");
+    const long warps = (long)N * (2L * W + 2L * H);
+    conv_s2_border_dgrad_kernel<<<dsr_grid(warps * 32, 256), 256, 0, ST(stream)>>>(g, N, Ho, Wo, Co, w, Ci, R, S, pad_mode, gx, H, W);
+    return dsr_check_launch("conv_s2_border_dgrad");
+}

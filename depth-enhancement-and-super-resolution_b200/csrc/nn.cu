@@ -311,9 +311,13 @@ norm_apply_fwd_vec4_kernel(const float4* __restrict__ x, const float* __restrict
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)).  The per-(n, c) constants (mean, rstd, and the two fp64 sums turned
 // into fp32 means) are staged once per block in shared memory; the old form re-read 8 doubles and converted them per
 // 16-byte item and ran at 39 % of HBM peak.
+template <bool GN>
 __global__ void __launch_bounds__(256)
 in_apply_bwd_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float* __restrict__ prm,
-                         const double* __restrict__ sums2, float4* __restrict__ dx, int N, int P, int C4, int act) {
+                         const double* __restrict__ sums2, float4* __restrict__ dx, int N, int P, int C4, int act,
+                         const float* __restrict__ gamma = nullptr, const float* __restrict__ beta = nullptr,
+                         const float* __restrict__ coef = nullptr) {
+    // GN: the GroupNorm form (affine gamma / beta, group means `coef` from gn_bwd_finalize): [6][C] adds gamma, beta
     extern __shared__ __align__(16) float s_c[];          // [4][C]: mean, rstd, m1, m2
     const int n = blockIdx.y, C = C4 * 4;
     const long NC = (long)N * C;
@@ -321,8 +325,15 @@ in_apply_bwd_vec4_kernel(const float4* __restrict__ x, const float4* __restrict_
     for (int c = threadIdx.x; c < C; c += 256) {
         s_c[c] = prm[(long)n * C + c];
         s_c[C + c] = prm[NC + (long)n * C + c];
-        s_c[2 * C + c] = (float)sums2[((long)n * C + c) * 2] * invP;
-        s_c[3 * C + c] = (float)sums2[((long)n * C + c) * 2 + 1] * invP;
+        if (GN) {
+            s_c[2 * C + c] = coef[((long)n * C + c) * 2];
+            s_c[3 * C + c] = coef[((long)n * C + c) * 2 + 1];
+            s_c[4 * C + c] = gamma[c];
+            s_c[5 * C + c] = beta[c];
+        } else {
+            s_c[2 * C + c] = (float)sums2[((long)n * C + c) * 2] * invP;
+            s_c[3 * C + c] = (float)sums2[((long)n * C + c) * 2 + 1] * invP;
+        }
     }
     __syncthreads();
     const long base = (long)n * P * C4;
@@ -337,12 +348,24 @@ in_apply_bwd_vec4_kernel(const float4* __restrict__ x, const float4* __restrict_
         const float ms[4] = {m.x, m.y, m.z, m.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
         const float m1[4] = {a1.x, a1.y, a1.z, a1.w}, m2[4] = {a2.x, a2.y, a2.z, a2.w};
         float o[4];
+        if (GN) {
+            const float4 g4a = *reinterpret_cast<const float4*>(s_c + 4 * C + c), b4a = *reinterpret_cast<const float4*>(s_c + 5 * C + c);
+            const float ga[4] = {g4a.x, g4a.y, g4a.z, g4a.w}, be[4] = {b4a.x, b4a.y, b4a.z, b4a.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float xh = (xs[k] - ms[k]) * rr[k];
-            float g = gs[k];
-            if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
-            o[k] = rr[k] * (g - m1[k] - xh * m2[k]);
+            for (int k = 0; k < 4; ++k) {
+                const float xh = (xs[k] - ms[k]) * rr[k];
+                float g = gs[k];
+                if (act == DSR_ACT_RELU && !(xh * ga[k] + be[k] > 0.f)) g = 0.f;
+                o[k] = rr[k] * (ga[k] * g - m1[k] - xh * m2[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xh = (xs[k] - ms[k]) * rr[k];
+                float g = gs[k];
+                if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
+                o[k] = rr[k] * (g - m1[k] - xh * m2[k]);
+            }
         }
         dx[base + i] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -366,9 +389,11 @@ act_bwd_vec4_kernel(const float4* __restrict__ ref, const float4* __restrict__ g
     }
 }
 // IN-backward sums, float4: lanes run along channel quads, warps along pixels; per-(n, c) (sum dy', sum dy' * xhat)
+template <bool GN>      // GN: ReLU gate on xhat * gamma + beta (GroupNorm with affine parameters)
 __global__ void __launch_bounds__(256)
 in_bwd_sums_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float* __restrict__ prm, int N, int P,
-                        int C4, int chunk, int act, double* __restrict__ sums) {
+                        int C4, int chunk, int act, double* __restrict__ sums, const float* __restrict__ gamma = nullptr,
+                        const float* __restrict__ beta = nullptr) {
     extern __shared__ float sh_s[];              // [rows][C4*4][2]
     const int n = blockIdx.y;
     const int Cw = C4 < 256 ? C4 : 256;          // threads along channel quads (C4 <= 256 here)
@@ -385,6 +410,11 @@ in_bwd_sums_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__
         if (cq < C4 && ty < rows) {
             const float4 m = ld4(pm + cq * 4), rs = ld4(pm + NC + cq * 4);
             const float ms[4] = {m.x, m.y, m.z, m.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+            float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+            if (GN) {
+                const float4 g4 = ld4(gamma + cq * 4), b4 = ld4(beta + cq * 4);
+                ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+            }
             for (int p = p_begin + ty; p < p_end; p += rows) {
                 const float4 xv = x[base + (long)p * C4 + cq], gv = dy[base + (long)p * C4 + cq];
                 const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -392,7 +422,7 @@ in_bwd_sums_vec4_kernel(const float4* __restrict__ x, const float4* __restrict__
                 for (int k = 0; k < 4; ++k) {
                     const float xh = (xs[k] - ms[k]) * rr[k];
                     float g = gs[k];
-                    if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
+                    if (act == DSR_ACT_RELU && !((GN ? xh * ga[k] + be[k] : xh) > 0.f)) g = 0.f;
                     a[k] += g; b[k] += g * xh;
                 }
             }
@@ -658,6 +688,16 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __
 extern "C" int dsr_gn_bwd_sums(const float* x, const float* dy, const float* prm, const float* gamma, const float* beta, int N,
                                long P, int C, int act, double* sums2, void* stream) {
     DSR_REQUIRE(x && dy && prm && gamma && beta && sums2 && N > 0 && N <= 65535 && P > 0 && C > 0 && C <= 4096, "bad arguments");
+    const bool vec = !(C & 3) && C / 4 <= 256 && (256 % (C / 4)) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)dy & 15) &&
+                     !((uintptr_t)prm & 15) && !((uintptr_t)gamma & 15) && !((uintptr_t)beta & 15) && !((N * (long)C) & 3) &&
+                     P * (C / 4) < (1L << 31);
+    if (vec) {              // float4 loads, register accumulation, one fp64 atomic per (block, channel, quantity)
+        long vchunk; dim3 grid;
+        sums_launch_cfg(N, P, &vchunk, &grid);
+        in_bwd_sums_vec4_kernel<true><<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, N, (int)P,
+                                                                                         C / 4, (int)vchunk, act, sums2, gamma, beta);
+        return dsr_check_launch("gn_bwd_sums");
+    }
     long blocks = (long)dsr_num_sms() * 4 / N + 1;
     if (blocks > P) blocks = P;
     const long chunk = (P + blocks - 1) / blocks;
@@ -674,6 +714,16 @@ extern "C" int dsr_gn_bwd_finalize(const double* sums2, const float* gamma, int 
 extern "C" int dsr_gn_bwd_apply(const float* x, const float* dy, const float* prm, const float* gamma, const float* beta,
                                 const float* coef, float* dx, int N, long P, int C, int act, void* stream) {
     DSR_REQUIRE(x && dy && prm && gamma && beta && coef && dx, "null pointer");
+    const bool vec = !(C & 3) && !((uintptr_t)x & 15) && !((uintptr_t)dy & 15) && !((uintptr_t)dx & 15) && !((uintptr_t)prm & 15) &&
+                     !((N * (long)C) & 3) && P * (C / 4) < (1L << 31) && C <= 1024;       // 6 C floats of shared memory
+    if (vec) {
+        const long items = P * (C / 4);
+        long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
+        if (gx > cap) gx = cap;
+        in_apply_bwd_vec4_kernel<true><<<dim3((unsigned)gx, (unsigned)N), 256, 6 * (size_t)C * sizeof(float), ST(stream)>>>(
+            (const float4*)x, (const float4*)dy, prm, nullptr, (float4*)dx, N, (int)P, C / 4, act, gamma, beta, coef);
+        return dsr_check_launch("gn_bwd_apply");
+    }
     gn_bwd_apply_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, gamma, beta, coef, dx, N, P, C, act);
     return dsr_check_launch("gn_bwd_apply");
 }
@@ -685,8 +735,8 @@ extern "C" int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm
     const bool vec = !(C & 3) && C / 4 <= 256 && (256 % (C / 4 < 256 ? C / 4 : 256)) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)dy & 15) &&
                      !((uintptr_t)prm & 15) && !((N * (long)C) & 3) && P * (C / 4) < (1L << 31);
     if (vec)
-        in_bwd_sums_vec4_kernel<<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, N, (int)P,
-                                                                                   C / 4, (int)chunk, act, sums2);
+        in_bwd_sums_vec4_kernel<false><<<grid, 256, 256 * 8 * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, N, (int)P,
+                                                                                          C / 4, (int)chunk, act, sums2);
     else
         channel_sums_kernel<<<grid, TPB, 0, ST(stream)>>>(x, dy, prm, N, P, C, chunk, 1, act, sums2);
     return dsr_check_launch("in_bwd_sums");
@@ -700,7 +750,7 @@ extern "C" int dsr_in_bwd_apply(const float* x, const float* dy, const float* pr
         const long items = P * (C / 4);
         long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
         if (gx > cap) gx = cap;
-        in_apply_bwd_vec4_kernel<<<dim3((unsigned)gx, (unsigned)N), 256, 4 * (size_t)C * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, sums2,
+        in_apply_bwd_vec4_kernel<false><<<dim3((unsigned)gx, (unsigned)N), 256, 4 * (size_t)C * sizeof(float), ST(stream)>>>((const float4*)x, (const float4*)dy, prm, sums2,
                                                                                          (float4*)dx, N, (int)P, C / 4, act);
     } else {
         in_apply_bwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, dy, prm, sums2, dx, N, P, C, act);

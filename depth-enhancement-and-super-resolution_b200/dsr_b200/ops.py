@@ -180,6 +180,7 @@ def _weight_grad(dwk, weight, kdim):
 # tcgen05 engine (csrc/conv_tc.cu): operand preparation + weight packing + implicit GEMM
 # ------------------------------------------------------------------------------------------------
 CONFIG = {
+    "s2_border": True,   # replicate / reflect stride-2 convs: tcgen05 data gradient + CUDA-core border term
     "engine": "tc",      # "tc": tcgen05 implicit GEMM wherever the layer shape allows; "simt": fp32 CUDA cores only
     "passes": 3,         # 1 = single 16-bit pass, 2 = activations hi+lo, 3 = activations and weights hi+lo (parity mode)
     "dtype": "f16",      # forward operand format: "f16" (11-bit significand, hi+lo = 22 bits) or "bf16" (8 / 16 bits: measured
@@ -496,12 +497,20 @@ def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
         gx = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
         _call("dsr_pad2d_bwd", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode)
         return gx
-    if stride == 2 and pad_mode == PAD_ZERO:
+    if stride == 2 and (pad_mode == PAD_ZERO or (pad == 1 and CONFIG["s2_border"])):
         opad = H - ((Ho - 1) * 2 - 2 * pad + R)
         plan = tc_conv_plan("convT", Co, Ci, R, S, 2, pad, opad, Ho, Wo)
         if plan is None or W - ((Wo - 1) * 2 - 2 * pad + S) != opad:
             return None
-        return _tc_convT_fwd(g, weight, None, plan, pad, ACT_NONE, H, W, dtype=dt)
+        gx = _tc_convT_fwd(g, weight, None, plan, pad, ACT_NONE, H, W, dtype=dt)
+        if pad_mode != PAD_ZERO:
+            # replicate / reflect padding: the interior of the padded-input gradient IS the zero-padding data gradient;
+            # its one-pixel frame is folded onto the border pixels by a small CUDA-core kernel (csrc/conv_out1.cu)
+            w = weight.detach()
+            gh = g.xh if isinstance(g, _Prepared) else g
+            _call("dsr_conv_s2_border_dgrad", _p(gh), N, Ho, Wo, Co, _p(w if w.is_contiguous() else w.contiguous()), Ci, R, S,
+                  pad_mode, _p(gx), H, W)
+        return gx
     return None
 
 
@@ -667,6 +676,7 @@ class _Conv2d(Function):
             xp, p = _explicit_pad(xh, pad, pad_mode)
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
             wk = _pack(weight, 1)
+            _lib.PROFILE_META = dict(macs=0, shape=("conv_simt", N, H, W, Ci, Co, R, stride))
             _call("dsr_conv_simt", _p(xp), _p(wk), _p(b), _p(y), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
                   stride, p, 0, act_out)
         ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None)
@@ -691,11 +701,31 @@ class _Conv2d(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gxp = _tc_conv_dgrad(gP, weight, stride, pad, pad_mode, H, W)
+            if gxp is None and stride == 1 and CONFIG["out1"] and R <= 9 and S <= 9 and (
+                    (Co == 1 and Ci % 16 == 0 and R * S * Ci * 4 <= 180 * 1024) or Ci == 1):
+                # one-channel layers (csrc/conv_out1.cu): a conv with ONE output channel has an outer-product data gradient;
+                # a conv with ONE input channel has a many-to-one convolution (flipped taps) as its data gradient
+                explicit = pad > 0 and pad_mode != PAD_ZERO
+                Hx, Wx = (H + 2 * pad, W + 2 * pad) if explicit else (H, W)
+                w = weight.detach()
+                gxp = torch.empty((N, Hx, Wx, Ci), device=g.device, dtype=torch.float32)
+                if Co == 1:
+                    _call("dsr_conv1_dgrad", _p(g), N, Ho, Wo, _p(w if w.is_contiguous() else w.contiguous()), Ci, R, S,
+                          0 if explicit else pad, _p(gxp), Hx, Wx)
+                else:
+                    wf = torch.flip(w[:, 0], dims=(1, 2)).contiguous()                  # [Co][R][S], taps flipped
+                    _call("dsr_conv_out1", _p(g), N, Ho, Wo, Co, None, ACT_NONE, 0.0, _p(wf), None, R, S,
+                          R - 1 - (0 if explicit else pad), PAD_ZERO, 0, ACT_NONE, _p(gxp))
+                if explicit:
+                    gxh = torch.empty_like(xh)
+                    _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
+                    gxp = gxh
             if gxp is None:
                 xp, p = _explicit_pad(xh, pad, pad_mode)            # recomputed, not stored
                 Hp, Wp = xp.shape[1], xp.shape[2]
                 wk = _pack(weight, 0)                               # [(r,s,co)][ci]
                 gxp = torch.empty((N, Hp, Wp, Ci), device=g.device, dtype=torch.float32)
+                _lib.PROFILE_META = dict(macs=0, shape=("conv_simt", N, H, W, Ci, Co, R, stride))
                 _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxp), N, Ho, Wo, Co, Hp, Wp, Ci, R, S, stride, p, 1, ACT_NONE)
                 if xp is not xh:
                     gxh = torch.empty_like(xh)
@@ -708,6 +738,7 @@ class _Conv2d(Function):
             if not done:
                 xp, p = _explicit_pad(xh, pad, pad_mode)
                 dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
+                _lib.PROFILE_META = dict(macs=0, shape=("wgrad_simt", N, H, W, Ci, Co, R, stride))
                 _call("dsr_wgrad_simt", _p(xp), _p(g), _p(dwk), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
                       stride, p)
                 gw = _weight_grad(dwk, weight, 1)
@@ -779,6 +810,7 @@ class _ConvTranspose2d(Function):
         else:
             y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
             wk = _pack(weight, 0)                       # [(r,s,ci)][co]
+            _lib.PROFILE_META = dict(macs=0, shape=("conv_simt", N, H, W, Ci, Co, R, stride))
             _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, act_out)
         ctx.cfg = (stride, pad, act_out, bias is not None)
         ctx.bias_ref, ctx.pro = bias, pro
@@ -805,6 +837,7 @@ class _ConvTranspose2d(Function):
             if gxh is None:
                 wk = _pack(weight, 1)                   # [(r,s,co)][ci]
                 gxh = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
+                _lib.PROFILE_META = dict(macs=0, shape=("conv_simt", N, H, W, Ci, Co, R, stride))
                 _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
             gx = nchw(_prologue_bwd(pro, prm, xh, gxh))
         if ctx.needs_input_grad[1]:
@@ -812,6 +845,7 @@ class _ConvTranspose2d(Function):
             done, gw = _tc_convT_wgrad(xP, gP, weight, stride, pad)
             if not done:
                 dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
+                _lib.PROFILE_META = dict(macs=0, shape=("wgrad_simt", N, H, W, Ci, Co, R, stride))
                 _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
                 gw = _weight_grad(dwk, weight, 1)
         if has_bias and ctx.needs_input_grad[2]:

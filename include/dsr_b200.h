@@ -169,6 +169,17 @@ int dsr_wgrad_simt(const float* G, const float* D, float* dWk, int N, int Hg, in
 int dsr_conv_out1(const float* x, int N, int H, int W, int C, const float* prm, int act_in, float slope,
                   const float* w, const float* bias, int R, int S, int pad, int pad_mode, int transposed,
                   int act_out, float* out, void* stream);
+/* data gradient of a stride-1 Conv2d with ONE output channel (weights [1][C][R][S]): gx[n][i][j][c] = sum_{r,s}
+ * g[n][i + off - r][j + off - s] * W[c][r][s], gx (N, Hx, Wx, C) NHWC; off = the conv's implicit zero padding (0 when gx is
+ * the gradient of an explicitly padded input).  models/translation_network.py:495 (generator head), :773 (discriminator head). */
+int dsr_conv1_dgrad(const float* g, int N, int Ho, int Wo, const float* w, int C, int R, int S, int off, float* gx, int Hx, int Wx,
+                    void* stream);
+/* border term of the data gradient of a stride-2, padding-1 Conv2d with replicate / reflect padding (weights [Co][Ci][R][S]):
+ * gx (N, H, W, Ci) already holds the zero-padding data gradient; this ADDS the one-pixel frame of the padded-input gradient
+ * onto the source pixels the padding mode read it from.  models/translation_network.py:478 (encoder 4x4 stride-2 convs,
+ * padding_mode='replicate'). */
+int dsr_conv_s2_border_dgrad(const float* g, int N, int Ho, int Wo, int Co, const float* w, int Ci, int R, int S, int pad_mode,
+                             float* gx, int H, int W, void* stream);
 
 /* tcgen05 / TMEM / TMA implicit GEMM (csrc/conv_tc.cu).  Three calls per convolution:
  *   dsr_tc_prep        fp32 NHWC activation -> arranged bf16 hi(+lo) operand [N][Ha][Wa][Ca]; fuses the preceding

@@ -309,7 +309,9 @@ def test_conv2d_fwd_bwd(ops, case, engine):
 
 @pytest.mark.parametrize("mode,k,Ci,Co,H,W", [("reflect", 7, 32, 128, 24, 40), ("reflect", 3, 128, 128, 16, 16),
                                               ("replicate", 3, 256, 256, 16, 16), ("replicate", 7, 64, 1, 32, 32),
-                                              ("replicate", 4, 32, 64, 32, 32), ("reflect", 3, 128, 128, 20, 12)])
+                                              ("replicate", 4, 32, 64, 32, 32), ("reflect", 3, 128, 128, 20, 12),
+                                              ("reflect", 4, 64, 128, 20, 12), ("replicate", 4, 3, 64, 16, 24),
+                                              ("replicate", 4, 64, 128, 2, 2), ("reflect", 4, 32, 32, 2, 4)])
 def test_conv2d_fused_padding_modes(ops, engine, mode, k, Ci, Co, H, W):
     """pad module folded into the conv (ReflectionPad2d + Conv2d, padding_mode='replicate')."""
     stride = 2 if k == 4 else 1

@@ -52,15 +52,16 @@ def test_constructors_and_oracle_match_reference():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("C", [64, 24, 256])        # 24: the scalar kernels (C/4 does not divide the block), others float4
 @pytest.mark.parametrize("act,res", [(0, False), (1, False), (0, True)])
-def test_group_norm_backward(built_lib, act, res):
+def test_group_norm_backward(built_lib, act, res, C):
     from dsr_b200 import ops
     g = torch.Generator().manual_seed(5)
-    x = (torch.randn(3, 64, 12, 10, generator=g) * 2 + 0.5).requires_grad_(True)
-    w = (torch.randn(64, generator=g) * 0.5 + 1).requires_grad_(True)
-    b = torch.randn(64, generator=g).requires_grad_(True)
-    r = torch.randn(3, 64, 12, 10, generator=g).requires_grad_(True) if res else None
-    go = torch.randn(3, 64, 12, 10, generator=g)
+    x = (torch.randn(3, C, 12, 10, generator=g) * 2 + 0.5).requires_grad_(True)
+    w = (torch.randn(C, generator=g) * 0.5 + 1).requires_grad_(True)
+    b = torch.randn(C, generator=g).requires_grad_(True)
+    r = torch.randn(3, C, 12, 10, generator=g).requires_grad_(True) if res else None
+    go = torch.randn(3, C, 12, 10, generator=g)
     ref = F.group_norm(x, 8, w, b, eps=1e-5)
     ref = F.relu(ref) if act else ref
     ref = ref + r if res else ref
