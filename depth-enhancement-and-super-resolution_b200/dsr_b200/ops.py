@@ -200,6 +200,13 @@ CONFIG = {
     "tc_compact_first": True,   # ... reading the 8-pixel K blocks from a compact 8-channel operand (no 8x expansion)   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
     "halo_min_tiles": 120,
     "fwd_passes": 0,     # forward GEMMs of the trainable nets: 0 = `passes`, 2 = activations hi+lo x weights hi only
+    "big_hw": 1024,      # layers with >= this many output pixels per sample may run fewer MMA passes (0 = off):
+    "big_fwd_passes": 0, #   forward GEMMs (0 = no override).  Measured on the golden step (scripts/precision_probe.py, r74):
+                         #   2-pass forwards at >= 32^2 / 64^2 / 128^2 give worst gradient cosine 0.972 / 0.953 / 0.973 - fail
+    "big_bwd_passes": 1, #   data-gradient GEMMs: ONE bf16 pass.  Measured: worst per-tensor cosine 0.999310 with 1 pass at
+                         #   >= 32^2 (0.999263 with 1 pass everywhere) against 0.999277 with 3 - like the weight gradient, the
+                         #   gate margin is set by the dY that reaches the layer, not by the operand rounding.  Layers below
+                         #   32^2 (latency-bound, no time to win) keep `passes`
     "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
@@ -208,11 +215,15 @@ _LAYOUT_NORMAL, _LAYOUT_PAIR, _LAYOUT_S2D = 0, 1, 2
 _W_CONV, _W_CONV_PAIR, _W_CONV_S2D, _W_CONVT_PH, _W_CONV_DGRAD, _W_CONV_DGRAD_PAIR = 0, 1, 2, 3, 4, 5
 
 
-_FWD = {"trainable": False}     # set by conv2d / conv_transpose2d / cat_conv2d: is the running layer on the autograd tape?
+_FWD = {"trainable": False, "hw": 0}     # set by conv2d / conv_transpose2d / cat_conv2d: is the running layer on the autograd tape?
 
 
 def _passes(dtype):
     """MMA passes of a forward GEMM (dtype None = the forward operand format) or of a data-gradient GEMM"""
+    if CONFIG["big_hw"] and _FWD["hw"] >= CONFIG["big_hw"]:
+        n = CONFIG["big_fwd_passes"] if dtype is None else CONFIG["big_bwd_passes"]
+        if n:
+            return min(n, CONFIG["passes"])
     if dtype is None and not _FWD["trainable"] and CONFIG["frozen_passes"]:
         return min(CONFIG["frozen_passes"], CONFIG["passes"])       # frozen nets run under no_grad (main_model.py:426)
     if dtype is None and _FWD["trainable"] and CONFIG["fwd_passes"]:
@@ -410,6 +421,7 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
     """stride-1 / stride-2 convolution of `xh` with a Conv2d-layout weight on the tcgen05 path.
     Also serves as the dgrad of ConvTranspose2d (its weight read as a Conv2d weight) and, with
     plan['variant'] == _W_CONV_DGRAD, as the dgrad of a stride-1 Conv2d (flipped / transposed taps)."""
+    _FWD["hw"] = Ho * Wo
     N, H, W, Ci = xh.shape
     R, S = weight.shape[2], weight.shape[3]
     if Co is None:
@@ -419,7 +431,7 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
     a_mode, a_plan = 0, plan
     if plan.get("compact") and Ho * Wo >= 128 and Wo >= 8:
         a_mode, a_plan = 1, dict(layout=_LAYOUT_NORMAL, Cp=8, Ca=8)       # 8-channel operand, same weights / taps
-    ahi, alo, Ha, Wa = _tc_prep(xh, a_plan, pad, pad_mode, dtype=dtype)
+    ahi, alo, Ha, Wa = _tc_prep(xh, a_plan, pad, pad_mode, dtype=dtype, need_lo=_passes(dtype) >= 2)
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     _lib.PROFILE_META = dict(macs=macs if macs is not None else N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
     filled = _tc_gemm(ahi, alo, N, Ha, Wa, a_plan["Ca"], whi, wlo, Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0, Ho, Wo,
@@ -433,9 +445,10 @@ def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stat
     """stride-2 transposed convolution (4 output phases) of `xh` with a ConvTranspose2d-layout weight;
     also the dgrad of a stride-2 Conv2d (whose (Cout, Cin, R, S) weight IS a ConvTranspose2d weight
     from Cout to Cin channels)."""
+    _FWD["hw"] = Ho * Wo
     N, H, W, Ci = xh.shape
     _, Co, R, S = weight.shape
-    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO, dtype=dtype)     # zero halo of 1 around the input
+    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO, dtype=dtype, need_lo=_passes(dtype) >= 2)     # zero halo of 1
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     dr, ds = _int_array([0, 0, 1, 1]), _int_array([0, 1, 0, 1])
     Ht, Wt = (Ho + 1) // 2, (Wo + 1) // 2
@@ -455,10 +468,11 @@ def _tc_dgrad_pair(gP, weight, padq, Hout, Wout, dt):
     GEMM whose rows are PAIRS of horizontally adjacent output pixels: N = 2 * Cin = 64 runs the tensor pipe at full rate
     where N = 32 runs at half, for (S/2 + 1) * 2 / S = 8/7 of the MACs.  The zero-padded dY (N, Ha, Wa, Co) is read
     through the view (N, Ha, Wa/2, 2*Co) - no copy - and the (N, Hout, Wout, Cin) output through (N, Hout, Wout/2, 2*Cin)."""
+    _FWD["hw"] = Hout * Wout
     N, Ho, Wo, Co = gP.shape
     _, Ci, R, S = weight.shape
     a_plan = dict(layout=_LAYOUT_NORMAL, Cp=Co, Ca=Co)
-    ahi, alo, Ha, Wa = _tc_prep(gP, a_plan, padq, PAD_ZERO, dtype=dt)
+    ahi, alo, Ha, Wa = _tc_prep(gP, a_plan, padq, PAD_ZERO, dtype=dt, need_lo=_passes(dt) >= 2)
     Sg = S // 2 + 1
     T = R * Sg
     w_plan = dict(variant=_W_CONV_DGRAD_PAIR, Cp=Co, Ca=2 * Co, T=T)

@@ -282,7 +282,8 @@ def engine(request, ops):
     old = dict(ops.CONFIG)
     # wgrad_passes follows `passes` here: these op-level tolerances are those of the full-precision weight gradient;
     # the default single-pass weight gradient is covered by test_tc_wgrad_large[1-...] and by the step-level gates
-    ops.CONFIG.update(engine=request.param[0], passes=request.param[1], dtype=request.param[2], wgrad_passes=request.param[1])
+    ops.CONFIG.update(engine=request.param[0], passes=request.param[1], dtype=request.param[2], wgrad_passes=request.param[1],
+                      big_hw=0)
     # (engine, passes, forward tolerance, dgrad tolerance: the backward operands are bf16 hi/lo)
     xtol = 1e-5 if request.param[0] == "simt" else {3: 5e-5, 2: 4e-3, 1: 8e-3}[request.param[1]]
     yield (request.param[0], request.param[1], request.param[3], xtol)
@@ -358,7 +359,7 @@ def test_tc_large_tiles_and_split_k(ops):
     """full 16x8 tiles over several images, ragged edges, and the split-K path of the tiny-M layers."""
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
         for (Ci, Co, k, s, p, N, H, W, split) in [(128, 128, 3, 1, 1, 5, 64, 64, 1), (64, 128, 3, 1, 1, 2, 40, 24, 1),
                                                   (512, 512, 4, 2, 1, 3, 8, 8, -1), (512, 512, 4, 2, 1, 12, 4, 4, 8),
                                                   (256, 512, 4, 2, 1, 2, 20, 12, -1)]:
@@ -380,7 +381,7 @@ def test_tc_wgrad_large(ops, wpass, tol):
     (NORMAL / PAIR / S2D conv, S2D transposed conv incl. the 1-channel head)."""
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=wpass)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=wpass, big_hw=0)
         for (kind, Ci, Co, k, s, p, op, N, H, W) in [("conv", 128, 128, 3, 1, 1, 0, 3, 40, 24), ("conv", 32, 128, 7, 1, 3, 0, 2, 36, 20),
                                                      ("conv", 261, 64, 4, 2, 1, 0, 2, 32, 48), ("conv", 64, 128, 3, 2, 1, 0, 2, 24, 24),
                                                      ("conv", 512, 512, 4, 2, 1, 0, 3, 4, 4), ("convT", 1024, 256, 4, 2, 1, 0, 2, 8, 8),
@@ -403,11 +404,34 @@ def test_tc_wgrad_large(ops, wpass, tol):
         ops.CONFIG.update(old)
 
 
+def test_default_dgrad_policy_single_pass_on_big_layers(ops):
+    """ops.CONFIG defaults: data-gradient GEMMs of layers with >= 32^2 output pixels run ONE bf16 pass (8e-3 class),
+    smaller layers keep the three-pass 5e-5 class; forward results are unaffected."""
+    assert ops.CONFIG["big_hw"] == 1024 and ops.CONFIG["big_bwd_passes"] == 1 and ops.CONFIG["big_fwd_passes"] == 0
+    for (kind, Ci, Co, k, s, p, op, H, W, lo, hi) in [("conv", 128, 128, 3, 1, 1, 0, 40, 48, 1e-4, 8e-3), ("conv", 128, 128, 3, 1, 1, 0, 16, 16, 0, 5e-5),
+                                                      ("conv", 32, 128, 7, 1, 3, 0, 64, 64, 1e-4, 8e-3), ("conv", 64, 128, 4, 2, 1, 0, 64, 64, 1e-4, 8e-3),
+                                                      ("convT", 256, 128, 4, 2, 1, 0, 32, 32, 1e-4, 8e-3), ("convT", 128, 64, 3, 2, 1, 1, 8, 8, 0, 5e-5)]:
+        x = torch.randn(2, Ci, H, W, generator=G(180)).requires_grad_(True)
+        if kind == "conv":
+            w = (torch.randn(Co, Ci, k, k, generator=G(181)) * 0.05).requires_grad_(True)
+            ref = F.conv2d(x, w, None, stride=s, padding=p)
+        else:
+            w = (torch.randn(Ci, Co, k, k, generator=G(181)) * 0.05).requires_grad_(True)
+            ref = F.conv_transpose2d(x, w, None, stride=s, padding=p, output_padding=op)
+        go = torch.randn(ref.shape, generator=G(182))
+        (ref * go).sum().backward()
+        xc, wc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True)
+        out = ops.conv2d(xc, wc, None, s, p) if kind == "conv" else ops.conv_transpose2d(xc, wc, None, s, p, op)
+        (out * go.cuda()).sum().backward()
+        e = rel_l2(xc.grad.cpu(), x.grad)
+        assert rel_l2(out.detach().cpu(), ref.detach()) <= 1e-5 and lo <= e <= hi, (kind, Ci, Co, k, H, W, e)
+
+
 def test_cat_conv2d_restricted_dgrad(ops):
     """conv over a lazily concatenated input: forward == conv(cat), gradients only for the parts that need one"""
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
         Cs, H, W = (128, 128, 2, 3), 32, 48
         xs = [torch.randn(2, c, H, W, generator=G(90 + i)) for i, c in enumerate(Cs)]
         xs[1].requires_grad_(True)
@@ -433,7 +457,7 @@ def test_fused_prologue_matches_unfused(ops):
     from dsr_b200 import networks as nw
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
         torch.manual_seed(5)
         mods = [nw.Conv2d(64, 128, 3, stride=2, padding=1), nw.InstanceNorm2d(128), nw.ReLU(True), nw.ReflectionPad2d(1),
                 nw.Conv2d(128, 128, 3, padding=0), nw.InstanceNorm2d(128), nw.ReLU(True),
