@@ -365,10 +365,11 @@ def run_ours(args):
             json.dump(rows, open(args.layer_table, "w"))
         by = {}
         for name, a, b, meta in rec:
-            d = by.setdefault(name, dict(ms=0.0, n=0, macs=0))
+            d = by.setdefault(name, dict(ms=0.0, n=0, macs=0, xmacs=0))
             d["ms"] += a.elapsed_time(b); d["n"] += 1
             if meta:
                 d["macs"] += meta["macs"]
+                d["xmacs"] += meta["macs"] * meta.get("passes", 0)          # MMAs issued: passes differ per launch
         prof = by
     line = None
     if rank == 0:
@@ -381,6 +382,9 @@ def run_ours(args):
         gemm_calls = {k: d for k, d in prof.items() if k in ("dsr_tc_gemm", "dsr_tc_gemm2", "dsr_tc_gemm3", "dsr_tc_wgrad") and d["n"]}
         kernel_of = dict(dsr_tc_gemm="conv_tc_kernel", dsr_tc_gemm2="conv_tc2_kernel", dsr_tc_gemm3="conv_tc3_kernel",
                          dsr_tc_wgrad="wgrad_tc_kernel")
+        # MMAs issued per kernel family: recorded per launch (forward 3 passes, data gradients 1 or 3, weight gradients 1);
+        # launches without a record fall back to the configured pass count
+        xm = lambda k: gemm_calls[k].get("xmacs") or gemm_calls[k]["macs"] * passes_of[k]
         if gemm_calls:
             dom = max(gemm_calls, key=lambda k: gemm_calls[k]["ms"])           # the dominant kernel of the step
             tc = gemm_calls[dom]
@@ -393,16 +397,17 @@ def run_ours(args):
                         traffic=tr["bytes_per_launch"] if tr else None, traffic_source=tr,
                         peak_source=pk_src + " (sustained: timed inside a long step)",
                         launches_per_step=tc["n"], avg_launch_us=1e3 * tc["ms"] / tc["n"], share_of_step=tc["ms"] / total_ms,
-                        mma_passes=passes_of[dom], executed_tflops=achieved * passes_of[dom],
-                        executed_frac=achieved * passes_of[dom] / pk["bf16_tflops_sustained"],
+                        mma_passes=round(xm(dom) / max(tc["macs"], 1), 3), executed_tflops=2.0 * xm(dom) / (tc["ms"] * 1e-3) / 1e12,
+                        executed_frac=2.0 * xm(dom) / (tc["ms"] * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                         all_tcgen05_gemms=dict(share_of_step=fam_ms / total_ms, achieved=2.0 * fam_macs / (fam_ms * 1e-3) / 1e12,
-                                               executed_tflops=2.0 * sum(d["macs"] * passes_of[k] for k, d in gemm_calls.items()) / (fam_ms * 1e-3) / 1e12,
-                                               mma_passes={kernel_of[k]: passes_of[k] for k in gemm_calls},
+                                               executed_tflops=2.0 * sum(xm(k) for k in gemm_calls) / (fam_ms * 1e-3) / 1e12,
+                                               mma_passes={kernel_of[k]: round(xm(k) / max(d["macs"], 1), 3) for k, d in gemm_calls.items()},
                                                ms={kernel_of[k]: round(d["ms"], 3) for k, d in gemm_calls.items()}),
                         note="achieved = algorithmic conv FLOPs of the layers this kernel served / their summed launch time (CUDA "
                              "events on the launching stream around every library call of one eager step enqueued behind a device-side spin, so "
                              "the brackets contain no host gaps); each product is issued as "
-                             "`mma_passes` 16-bit MMAs (hi/lo operand split needed by the parity gates), so the tensor pipe executes "
+                             "`mma_passes` 16-bit MMAs on average (3 for forward GEMMs - the hi/lo operand split the parity gates need - "
+                             "1 for weight gradients and for data gradients of layers >= 32^2), so the tensor pipe executes "
                              "`executed_tflops`; traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the launches "
                              "captured by ncu --set full (profiles/, a previous run of the same command on the same workload)")
         else:

@@ -119,9 +119,123 @@ nearest_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Exact x2 / x0.5 bicubic (the only factors main_sr_model.py uses: :279-293 x2 of the LR feature maps, :361 / :394-398 x0.5).
+// With align_corners=False the source coordinate of output o is o/2 - 1/4 (x2: fractions 3/4, 1/4 alternate) or 2o + 1/2
+// (x0.5: always 1/2), so the 4 tap weights are two fixed vectors and neighbouring outputs share their taps.  The generic
+// kernel above loads 16 taps per output element from L1 (ncu: 15-18 % of the HBM peak, L1-bandwidth bound); these forms
+// run the filter separably with a rolling window of horizontally filtered rows in registers: ~2 loads per output float4 (x2)
+// and exactly the 16 input bytes per output (x0.5).  Same operation order as the generic kernel (horizontal taps
+// ascending, then rows ascending).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_fma(float w, const float4 v, const float4 a) {
+    return make_float4(a.x + w * v.x, a.y + w * v.y, a.z + w * v.z, a.w + w * v.w);
+}
+__device__ __forceinline__ float4 f4_mul(float w, const float4 v) { return make_float4(w * v.x, w * v.y, w * v.z, w * v.w); }
+
+#define UP2_ROWS 8             // input rows per thread (16 output rows)
+// NHWC, C % 4 == 0: thread = (input column k, channel quad); it produces output columns 2k, 2k+1 of 2 * UP2_ROWS output rows
+__global__ void __launch_bounds__(TPB)
+bicubic_up2_kernel(const float4* __restrict__ x, int N, int H, int W, int Cv, float4* __restrict__ y) {
+    const int cols_per_block = TPB / Cv;
+    const int c = threadIdx.x % Cv, k = blockIdx.x * cols_per_block + threadIdx.x / Cv;
+    const int m0 = blockIdx.y * UP2_ROWS, n = blockIdx.z;
+    if (k >= W) return;
+    float wa[4], wb[4];                       // even outputs: taps k-2..k+1, t = 3/4;  odd outputs: taps k-1..k+2, t = 1/4
+    cubic_coeffs(0.75f, wa);
+    cubic_coeffs(0.25f, wb);
+    int xs[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) xs[b] = clampi(k - 2 + b, 0, W - 1);
+    const float4* xn = x + (long)n * H * W * Cv + c;
+    float4* yn = y + (long)n * 4 * H * W * Cv + c;
+    const int Wo = 2 * W;
+    float4 he[5], ho[5];                      // horizontally filtered input rows m-2 .. m+2 (even / odd output column)
+    auto hrow = [&](int r, float4& e, float4& o) {
+        const float4* row = xn + (long)clampi(r, 0, H - 1) * W * Cv;
+        float4 v[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) v[b] = row[(long)xs[b] * Cv];
+        e = f4_mul(wa[0], v[0]); e = f4_fma(wa[1], v[1], e); e = f4_fma(wa[2], v[2], e); e = f4_fma(wa[3], v[3], e);
+        o = f4_mul(wb[0], v[1]); o = f4_fma(wb[1], v[2], o); o = f4_fma(wb[2], v[3], o); o = f4_fma(wb[3], v[4], o);
+    };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) hrow(m0 - 2 + q, he[q], ho[q]);
+#pragma unroll
+    for (int q = 0; q < UP2_ROWS; ++q) {
+        const int m = m0 + q;
+        if (m >= H) break;
+        hrow(m + 2, he[4], ho[4]);
+        // output row 2m: input rows m-2..m+1 (weights wa); output row 2m+1: rows m-1..m+2 (weights wb)
+        float4 a0 = f4_mul(wa[0], he[0]), a1 = f4_mul(wa[0], ho[0]), b0 = f4_mul(wb[0], he[1]), b1 = f4_mul(wb[0], ho[1]);
+#pragma unroll
+        for (int t = 1; t < 4; ++t) {
+            a0 = f4_fma(wa[t], he[t], a0); a1 = f4_fma(wa[t], ho[t], a1);
+            b0 = f4_fma(wb[t], he[t + 1], b0); b1 = f4_fma(wb[t], ho[t + 1], b1);
+        }
+        float4* o0 = yn + ((long)(2 * m) * Wo + 2 * k) * Cv;
+        o0[0] = a0; o0[Cv] = a1;
+        o0[(long)Wo * Cv] = b0; o0[(long)Wo * Cv + Cv] = b1;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { he[t] = he[t + 1]; ho[t] = ho[t + 1]; }
+    }
+}
+
+#define DN2_ROWS 4             // output rows per thread
+// planes (C = 1), W % 4 == 0, 16-byte aligned rows: thread = output columns ox, ox+1 (ox even) of DN2_ROWS output rows
+__global__ void __launch_bounds__(TPB)
+bicubic_down2_kernel(const float* __restrict__ x, int H, int W, float* __restrict__ y) {
+    const int Ho = H / 2, Wo = W / 2;
+    const int lane = threadIdx.x & 31;
+    const int ox = (blockIdx.x * 32 + lane) * 2;
+    const int oy0 = (blockIdx.y * (TPB / 32) + (threadIdx.x >> 5)) * DN2_ROWS;
+    const long pl = blockIdx.z;
+    const float* xp = x + pl * H * W;
+    float* yp = y + pl * Ho * Wo;
+    float w4[4];
+    cubic_coeffs(0.5f, w4);
+    const bool act = ox < Wo;
+    const int xc = act ? 2 * ox : 0;          // input columns 2ox-1 .. 2ox+4 = left, the float4 at 2ox, right
+    float h0[4], h1[4];                       // horizontally filtered input rows (rolling window of 4)
+    auto hrow = [&](int r, float& e, float& o) {
+        const float* row = xp + (long)clampi(r, 0, H - 1) * W;
+        const float4 v = ld4(row + xc);
+        float l = __shfl_up_sync(0xffffffffu, v.w, 1), rr = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (xc == 0) l = v.x; else if (lane == 0) l = __ldg(row + xc - 1);
+        if (xc + 4 >= W) rr = v.w; else if (lane == 31) rr = __ldg(row + xc + 4);
+        e = w4[0] * l; e += w4[1] * v.x; e += w4[2] * v.y; e += w4[3] * v.z;
+        o = w4[0] * v.y; o += w4[1] * v.z; o += w4[2] * v.w; o += w4[3] * rr;
+    };
+    // output row oy reads input rows 2oy-1 .. 2oy+2
+    hrow(2 * oy0 - 1, h0[0], h1[0]);
+    hrow(2 * oy0, h0[1], h1[1]);
+#pragma unroll
+    for (int q = 0; q < DN2_ROWS; ++q) {
+        const int oy = oy0 + q;
+        hrow(2 * oy + 1, h0[2], h1[2]);
+        hrow(2 * oy + 2, h0[3], h1[3]);
+        float a = w4[0] * h0[0], b = w4[0] * h1[0];
+#pragma unroll
+        for (int t = 1; t < 4; ++t) { a += w4[t] * h0[t]; b += w4[t] * h1[t]; }
+        if (act && oy < Ho) *reinterpret_cast<float2*>(yp + (long)oy * Wo + ox) = make_float2(a, b);
+        h0[0] = h0[2]; h0[1] = h0[3]; h1[0] = h1[2]; h1[1] = h1[3];
+    }
+}
+
 extern "C" int dsr_bicubic_fwd(const float* x, int N, int H, int W, int C, int Ho, int Wo, float* y, void* stream) {
     DSR_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "bad arguments");
     const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+    const bool al16 = !((uintptr_t)x & 15) && !((uintptr_t)y & 15);
+    if (Ho == 2 * H && Wo == 2 * W && (C & 3) == 0 && C / 4 <= TPB && TPB % (C / 4) == 0 && al16 && N <= 65535 &&
+        dsr_cdiv(H, UP2_ROWS) <= 65535) {
+        const int Cv = C / 4;
+        bicubic_up2_kernel<<<dim3(dsr_cdiv(W, TPB / Cv), dsr_cdiv(H, UP2_ROWS), N), TPB, 0, ST(stream)>>>((const float4*)x, N, H, W, Cv, (float4*)y);
+        return dsr_check_launch("bicubic_fwd (x2)");
+    }
+    if (C == 1 && H == 2 * Ho && W == 2 * Wo && (W & 3) == 0 && al16 && N <= 65535 && dsr_cdiv(Ho, (TPB / 32) * DN2_ROWS) <= 65535) {
+        bicubic_down2_kernel<<<dim3(dsr_cdiv(Wo, 64), dsr_cdiv(Ho, (TPB / 32) * DN2_ROWS), N), TPB, 0, ST(stream)>>>(x, H, W, y);
+        return dsr_check_launch("bicubic_fwd (x0.5)");
+    }
     if ((C & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)y & 15))
         bicubic_fwd_kernel<4><<<dsr_grid((long)N * Ho * Wo * (C / 4), TPB), TPB, 0, ST(stream)>>>(x, N, H, W, C, Ho, Wo, sh, sw, y);
     else

@@ -728,6 +728,159 @@ smooth_bwd_quad(const float* __restrict__ d, const float* __restrict__ img, int 
     }
 }
 
+// ---- rolling-row forms (16-byte aligned rows): one thread = 4 columns x 4 rows.  Every row of every plane is loaded ONCE per
+// thread as a float4 (5 rows forward, 6 rows backward, all loads of a plane issued back to back), the row below / above is the
+// register copy of the neighbouring row, and the column neighbours j-1 / j+4 come from the adjacent lanes by warp shuffle
+// (a scalar load only at the 64-column tile seam).  The first-generation quad kernels loaded every row two (forward) or
+// three (backward) times plus two scalar edge loads per row and plane, and ran at 31-37 % of the HBM peak, bound by load
+// latency (ncu: long-scoreboard stalls 10 per issue, 36 % occupancy).
+__device__ __forceinline__ float right_of(const float4 v, const float* __restrict__ row, int j, int w, int tx) {
+    float nx = __shfl_down_sync(0xffffffffu, v.x, 1);              // x[j + 4] lives in the next lane's .x
+    if (j + 4 >= w) nx = v.w;                                       // clamped: the difference across the border is 0
+    else if (tx == 15) nx = __ldg(row + j + 4);                     // tile seam
+    return nx;
+}
+__device__ __forceinline__ float left_of(const float4 v, const float* __restrict__ row, int j, int w, int tx) {
+    float px = __shfl_up_sync(0xffffffffu, v.w, 1);                // x[j - 1] lives in the previous lane's .w
+    if (j == 0 || j >= w) px = v.x;
+    else if (tx == 0) px = __ldg(row + j - 1);
+    return px;
+}
+template <int C>
+__global__ void __launch_bounds__(NT, 2)
+smooth_fwd_roll(const float* __restrict__ d, const float* __restrict__ img, int h, int w, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int tx = threadIdx.x & 15;
+    const int j = blockIdx.x * TW + (tx << 2);
+    const int ibase = blockIdx.y * STRIP + (threadIdx.x >> 4) * 4;
+    const int b = blockIdx.z;
+    const long plane = (long)h * w;
+    const int jc = j < w ? j : 0;                                   // lanes right of the image load column 0 and contribute 0
+    float sx[4][4], sy[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sx[k][e] = 0.f; sy[k][e] = 0.f; }
+    long roff[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) roff[k] = (long)min(ibase + k, h - 1) * w;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const float* p = img + ((long)b * C + ch) * plane;
+        float4 r[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] = ld4(p + roff[k] + jc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float nx = right_of(r[k], p + roff[k], j, w, tx);
+            sx[k][0] += fabsf(r[k].x - r[k + 1].x); sx[k][1] += fabsf(r[k].y - r[k + 1].y);
+            sx[k][2] += fabsf(r[k].z - r[k + 1].z); sx[k][3] += fabsf(r[k].w - r[k + 1].w);
+            sy[k][0] += fabsf(r[k].x - r[k].y); sy[k][1] += fabsf(r[k].y - r[k].z);
+            sy[k][2] += fabsf(r[k].z - r[k].w); sy[k][3] += fabsf(r[k].w - nx);
+        }
+    }
+    float fx = 0.f, fy = 0.f;
+    {
+        const float invC = 1.f / (float)C;
+        const float* p = d + b * plane;
+        float4 r[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] = ld4(p + roff[k] + jc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float nx = right_of(r[k], p + roff[k], j, w, tx);
+            if (j < w && ibase + k < h) {
+                const float c[5] = {r[k].x, r[k].y, r[k].z, r[k].w, nx}, l[4] = {r[k + 1].x, r[k + 1].y, r[k + 1].z, r[k + 1].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    fx += fabsf((c[e] - l[e]) * __expf(-sx[k][e] * invC));
+                    fy += fabsf((c[e] - c[e + 1]) * __expf(-sy[k][e] * invC));
+                }
+            }
+        }
+    }
+    const double ax = block_sum<double>((double)fx, red), ay = block_sum<double>((double)fy, red);
+    if (threadIdx.x == 0) { atomicAdd(out, ax); atomicAdd(out + 1, ay); }
+}
+
+template <int C>
+__global__ void __launch_bounds__(NT, 2)
+smooth_bwd_roll(const float* __restrict__ d, const float* __restrict__ img, int h, int w, const float* __restrict__ gscale,
+                float cx, float cy, float* __restrict__ gd, int accumulate) {
+    const int tx = threadIdx.x & 15;
+    const int j = blockIdx.x * TW + (tx << 2);
+    const int ibase = blockIdx.y * STRIP + (threadIdx.x >> 4) * 4;
+    const int b = blockIdx.z;
+    const long plane = (long)h * w;
+    const int jc = j < w ? j : 0;
+    // sv[k][e]: sum_c |I[i-1+k] - I[i+k]| at column j+e (row pairs k = 0..4); sh[k][e]: sum_c |I[.][j+e-1] - I[.][j+e]| of row i+k
+    float sv[5][4], sh[4][5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sv[k][e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 5; ++e) sh[k][e] = 0.f;
+    long roff[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) roff[k] = (long)min(max(ibase - 1 + k, 0), h - 1) * w;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const float* p = img + ((long)b * C + ch) * plane;
+        float4 r[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = ld4(p + roff[k] + jc);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            sv[k][0] += fabsf(r[k].x - r[k + 1].x); sv[k][1] += fabsf(r[k].y - r[k + 1].y);
+            sv[k][2] += fabsf(r[k].z - r[k + 1].z); sv[k][3] += fabsf(r[k].w - r[k + 1].w);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = r[k + 1];
+            const float px = left_of(v, p + roff[k + 1], j, w, tx), nx = right_of(v, p + roff[k + 1], j, w, tx);
+            sh[k][0] += fabsf(px - v.x); sh[k][1] += fabsf(v.x - v.y); sh[k][2] += fabsf(v.y - v.z);
+            sh[k][3] += fabsf(v.z - v.w); sh[k][4] += fabsf(v.w - nx);
+        }
+    }
+    const float g = gscale ? *gscale : 1.f, invC = 1.f / (float)C;
+    const float* p = d + b * plane;
+    float4 r[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = ld4(p + roff[k] + jc);
+    float* orow = gd + b * plane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 v4 = r[k + 1];
+        const float px = left_of(v4, p + roff[k + 1], j, w, tx), nx = right_of(v4, p + roff[k + 1], j, w, tx);
+        if (j >= w || ibase + k >= h) continue;
+        const float c[6] = {px, v4.x, v4.y, v4.z, v4.w, nx};
+        const float u[4] = {r[k].x, r[k].y, r[k].z, r[k].w}, l[4] = {r[k + 2].x, r[k + 2].y, r[k + 2].z, r[k + 2].w};
+        float wh[5], o[4];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) wh[e] = __expf(-sh[k][e] * invC);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v = c[e + 1];
+            const float wl = __expf(-sv[k + 1][e] * invC), wu = __expf(-sv[k][e] * invC);
+            float acc = cx * wl * sgnf((v - l[e]) * wl);
+            acc -= cx * wu * sgnf((u[e] - v) * wu);
+            acc += cy * wh[e + 1] * sgnf((v - c[e + 2]) * wh[e + 1]);
+            acc -= cy * wh[e] * sgnf((c[e] - v) * wh[e]);
+            o[e] = g * acc;
+        }
+        float* op = orow + (long)(ibase + k) * w + j;
+        if (accumulate) {
+            const float4 old = ld4(op);
+            st4(op, make_float4(old.x + o[0], old.y + o[1], old.z + o[2], old.w + o[3]));
+        } else {
+            st4(op, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
@@ -825,12 +978,32 @@ extern "C" int dsr_masked_diff_bwd(const float* a, const float* b, const float* 
 extern "C" int dsr_smooth_level_fwd(const float* d, const float* img, int B, int C, int h, int w, double* out2,
                                     void* stream) {
     DSR_REQUIRE(d && img && out2 && B > 0 && C >= 1 && C <= SM_MAXC && h > 0 && w > 0 && PLANES_OK(B, h, w), "bad arguments (C <= 4)");
-    smooth_fwd_quad<<<dim3((w + TW - 1) / TW, (h + STRIP - 1) / STRIP, B), NT, 0, ST(stream)>>>(d, img, C, h, w, out2);
+    const dim3 grid((w + TW - 1) / TW, (h + STRIP - 1) / STRIP, B);
+    if (!(w & 3) && !((uintptr_t)d & 15) && !((uintptr_t)img & 15)) {
+        switch (C) {
+            case 1: smooth_fwd_roll<1><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, out2); break;
+            case 2: smooth_fwd_roll<2><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, out2); break;
+            case 3: smooth_fwd_roll<3><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, out2); break;
+            default: smooth_fwd_roll<4><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, out2); break;
+        }
+    } else {
+        smooth_fwd_quad<<<grid, NT, 0, ST(stream)>>>(d, img, C, h, w, out2);
+    }
     return dsr_check_launch("smooth_level_fwd");
 }
 extern "C" int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
                                     float cx, float cy, float* gd, int accumulate, void* stream) {
     DSR_REQUIRE(d && img && gd && B > 0 && C >= 1 && C <= SM_MAXC && h > 0 && w > 0 && PLANES_OK(B, h, w), "bad arguments (C <= 4)");
-    smooth_bwd_quad<<<quad_grid(B, h, w), NT, 0, ST(stream)>>>(d, img, C, h, w, gscale, cx, cy, gd, accumulate);
+    if (!(w & 3) && !((uintptr_t)d & 15) && !((uintptr_t)img & 15) && !((uintptr_t)gd & 15)) {
+        const dim3 grid((w + TW - 1) / TW, (h + STRIP - 1) / STRIP, B);
+        switch (C) {
+            case 1: smooth_bwd_roll<1><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, gscale, cx, cy, gd, accumulate); break;
+            case 2: smooth_bwd_roll<2><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, gscale, cx, cy, gd, accumulate); break;
+            case 3: smooth_bwd_roll<3><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, gscale, cx, cy, gd, accumulate); break;
+            default: smooth_bwd_roll<4><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, gscale, cx, cy, gd, accumulate); break;
+        }
+    } else {
+        smooth_bwd_quad<<<quad_grid(B, h, w), NT, 0, ST(stream)>>>(d, img, C, h, w, gscale, cx, cy, gd, accumulate);
+    }
     return dsr_check_launch("smooth_level_bwd");
 }

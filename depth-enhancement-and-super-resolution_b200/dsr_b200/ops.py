@@ -404,6 +404,8 @@ def _tc_gemm(ahi, alo, N, Ha, Wa, Ca, whi, wlo, Co, T, dr, ds, aoh, aow, Ht, Wt,
              dtype, split_k, stats=None, nphase=1, a_mode=0):
     """one GEMM launch on the best kernel for the shape; returns True when `stats` was filled by the epilogue"""
     which = 2 if a_mode else (CONFIG.get("force_kernel") or _tc_kernel_for(N, Ht, Wt, Co, list(ds), nphase))
+    if _lib.PROFILE_META is not None:
+        _lib.PROFILE_META["passes"] = _passes(dtype)            # bench.py: MMAs actually issued per product
     if which == 1:
         _call("dsr_tc_gemm", _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), N, Ha, Wa, Ca,
               _p(whi, torch.bfloat16), _p(wlo, torch.bfloat16), Co, T, dr, ds, aoh, aow, Ht, Wt, _p(bias), _p(y),
@@ -562,7 +564,7 @@ def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, 
     D0, D1, R, S = weight.shape
     dwp = torch.empty((Cm_real, T * Ca), device=M.device, dtype=torch.float32)
     f16 = 3 if dt == "f16" else 0                                        # bit 0: format of M, bit 1: format of A
-    _lib.PROFILE_META = dict(macs=N * Hb * Wb * D0 * D1 * R * S, shape=(N, Hb, Wb, Cm_real, Ca, T, 0))
+    _lib.PROFILE_META = dict(macs=N * Hb * Wb * D0 * D1 * R * S, shape=(N, Hb, Wb, Cm_real, Ca, T, 0), passes=npass)
     _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
           _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
           Hb, Wb, _p(dwp), npass, f16, 1.0, -1)

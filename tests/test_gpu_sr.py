@@ -25,7 +25,9 @@ def test_bicubic_nearest_match_reference_vectors(built_lib):
 
 
 @pytest.mark.parametrize("shape,size", [((2, 128, 20, 28), (40, 56)), ((1, 128, 33, 17), (16, 8)), ((3, 1, 64, 80), (32, 40)),
-                                        ((2, 3, 1, 5), (2, 10)), ((1, 6, 40, 40), (40, 40))])
+                                        ((2, 3, 1, 5), (2, 10)), ((1, 6, 40, 40), (40, 40)),
+                                        ((1, 128, 9, 13), (18, 26)), ((2, 32, 16, 12), (32, 24)), ((2, 4, 3, 300), (6, 600)),
+                                        ((2, 1, 30, 36), (15, 18)), ((1, 2, 70, 264), (35, 132)), ((1, 1, 2, 4), (1, 2))])
 def test_bicubic_layouts_and_adjoint(built_lib, shape, size):
     """channels-last activations (C = 128 feature maps, float4 path), planes, degenerate sizes; backward = exact adjoint"""
     from dsr_b200 import ops
