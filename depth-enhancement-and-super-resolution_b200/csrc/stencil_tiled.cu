@@ -979,6 +979,8 @@ extern "C" int dsr_smooth_level_fwd(const float* d, const float* img, int B, int
                                     void* stream) {
     DSR_REQUIRE(d && img && out2 && B > 0 && C >= 1 && C <= SM_MAXC && h > 0 && w > 0 && PLANES_OK(B, h, w), "bad arguments (C <= 4)");
     const dim3 grid((w + TW - 1) / TW, (h + STRIP - 1) / STRIP, B);
+    if (!((uintptr_t)d & 15) && !((uintptr_t)img & 15) && dsr_smooth_ring_suits(B, C, h, w))
+        return dsr_smooth_level_fwd_ring(d, img, B, C, h, w, out2, stream);          // large plane sets: csrc/stencil_ring.cu
     if (!(w & 3) && !((uintptr_t)d & 15) && !((uintptr_t)img & 15)) {
         switch (C) {
             case 1: smooth_fwd_roll<1><<<grid, NT, 0, ST(stream)>>>(d, img, h, w, out2); break;
@@ -994,6 +996,8 @@ extern "C" int dsr_smooth_level_fwd(const float* d, const float* img, int B, int
 extern "C" int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
                                     float cx, float cy, float* gd, int accumulate, void* stream) {
     DSR_REQUIRE(d && img && gd && B > 0 && C >= 1 && C <= SM_MAXC && h > 0 && w > 0 && PLANES_OK(B, h, w), "bad arguments (C <= 4)");
+    if (!((uintptr_t)d & 15) && !((uintptr_t)img & 15) && !((uintptr_t)gd & 15) && dsr_smooth_ring_suits(B, C, h, w))
+        return dsr_smooth_level_bwd_ring(d, img, B, C, h, w, gscale, cx, cy, gd, accumulate, stream);
     if (!(w & 3) && !((uintptr_t)d & 15) && !((uintptr_t)img & 15) && !((uintptr_t)gd & 15)) {
         const dim3 grid((w + TW - 1) / TW, (h + STRIP - 1) / STRIP, B);
         switch (C) {

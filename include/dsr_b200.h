@@ -77,6 +77,14 @@ int dsr_bilinear_ac_bwd(const float* g, long planes, int H, int W, int nh, int n
 int dsr_smooth_level_fwd(const float* d, const float* img, int B, int C, int h, int w, double* out2, void* stream);
 int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
                          float cx, float cy, float* gd, int accumulate, void* stream);
+/* Row-ring forms of the two calls above for large plane sets (csrc/stencil_ring.cu: image rows streamed through a shared-memory
+ * ring by bulk copies, one producer warp + consumer warps).  dsr_smooth_level_fwd / _bwd dispatch here on their own when
+ * dsr_smooth_ring_suits() says so (>= 2 M pixels, w % 4 == 0, w >= 64, rows fit shared memory); calling them directly on a
+ * shape that does not suit returns DSR_ERR_ARG.  Same results as the register kernels up to fp32 summation order. */
+int dsr_smooth_level_fwd_ring(const float* d, const float* img, int B, int C, int h, int w, double* out2, void* stream);
+int dsr_smooth_level_bwd_ring(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
+                              float cx, float cy, float* gd, int accumulate, void* stream);
+int dsr_smooth_ring_suits(int B, int C, int h, int w);
 /* SSIM, 11x11 Gaussian sigma 1.5, zero padding: *out_sum += sum of the SSIM map; map may be NULL.
  * models/pytorch_ssim/__init__.py:17-37. */
 int dsr_ssim_fwd(const float* a, const float* b, long planes, int H, int W, double* out_sum, float* map,

@@ -605,3 +605,32 @@ def test_rect_holes_ragged_sizes(ops, HW):
     gt, masked, extra = ops.rect_holes(valid.cuda(), d.cuda(), torch.from_numpy(tab).cuda(), torch.from_numpy(cnt).cuda(), 64)
     assert np.array_equal(gt.cpu().numpy(), gt_ref.numpy().astype(np.uint8))
     assert torch.equal(masked.cpu(), masked_ref)
+
+
+@pytest.mark.parametrize("B,C,h,w", [(3, 3, 37, 64), (2, 3, 130, 128), (2, 1, 5, 256), (5, 3, 64, 640), (1, 3, 1, 64), (2, 4, 9, 68),
+                                     (7, 3, 200, 320)])
+def test_smooth_row_ring_matches_register_kernels(ops, B, C, h, w):
+    """csrc/stencil_ring.cu (bulk-copy row ring, the path large plane sets take) against the register kernels that the
+    oracle tests pin: forward sums within fp32 summation-order noise, backward bit-for-bit up to sign-of-zero."""
+    from dsr_b200.ops import _call, _p
+    g = torch.Generator().manual_seed(17)
+    d = (torch.rand(B, 1, h, w, generator=g) * 1.8 - 0.9).cuda()
+    img = (torch.rand(B, C, h, w, generator=g) * 2 - 1).cuda()
+    gs = torch.tensor(0.7, device="cuda")
+    ref_s, ring_s = torch.zeros(2, dtype=torch.float64, device="cuda"), torch.zeros(2, dtype=torch.float64, device="cuda")
+    assert B * h * w < (2 << 20)                  # small enough that the default entry point takes the register kernels
+    _call("dsr_smooth_level_fwd", _p(d), _p(img), B, C, h, w, _p(ref_s, torch.float64))
+    _call("dsr_smooth_level_fwd_ring", _p(d), _p(img), B, C, h, w, _p(ring_s, torch.float64))
+    assert torch.allclose(ref_s, ring_s, rtol=1e-5, atol=1e-6), (ref_s, ring_s)
+    for acc in (0, 1):
+        ref_g, ring_g = torch.full_like(d, 0.25), torch.full_like(d, 0.25)
+        _call("dsr_smooth_level_bwd", _p(d), _p(img), B, C, h, w, _p(gs), 0.3, 0.6, _p(ref_g), acc)
+        _call("dsr_smooth_level_bwd_ring", _p(d), _p(img), B, C, h, w, _p(gs), 0.3, 0.6, _p(ring_g), acc)
+        assert float((ref_g - ring_g).abs().max()) <= 1e-6, acc
+
+
+def test_smooth_row_ring_rejects_unsuitable_shapes(ops):
+    from dsr_b200.ops import _call, _p
+    d, img = torch.zeros(1, 1, 8, 30, device="cuda"), torch.zeros(1, 3, 8, 30, device="cuda")
+    with pytest.raises(RuntimeError):
+        _call("dsr_smooth_level_fwd_ring", _p(d), _p(img), 1, 3, 8, 30, _p(torch.zeros(2, dtype=torch.float64, device="cuda"), torch.float64))
