@@ -1,5 +1,9 @@
 // Row-ring forms of the edge-aware smoothness level (main_model.py:22-73) for large plane sets (full-size frames, big batches).
 //
+// (Measured, r82-r85: the same ring for the total-variation sum - one plane per sample, ~12 instructions of work per pixel -
+// reaches 60 % of the HBM peak against 66 % for its register kernel, so TV stays there; with 640 column quads per group the
+// consumers are bound by their own latency chain: 20 warps 68 %, 10 warps 64 %, 5 warps 49 %.)
+//
 // The register kernels in stencil_tiled.cu are bound by load latency (ncu: long-scoreboard stalls, ~50 % of the HBM peak):
 // a thread can only keep the loads of its own 4 x 4 pixels in flight.  Here the bytes in flight are decoupled from the
 // threads: one producer warp streams whole image rows (all planes of a sample: depth + C image channels) into a ring of
@@ -8,6 +12,7 @@
 // the slots back through `empty` mbarriers.  The image rows are split evenly over one CTA per SM; a CTA reads every row of its
 // share once (+ one or two halo rows per sample it touches) and keeps the pipeline full across samples.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define RING_MAX_WARPS 20
 
@@ -97,8 +102,13 @@ smooth_ring_kernel(const float* __restrict__ d, const float* __restrict__ img, R
             seg.template get<BWD>(g, b, r0, r1, lo, hi, ng);
             for (int k = 0; k < ng; ++k) {
                 const int q = qbase + k, s = q % NGS;
-                mbar_wait(smem_u32(bars + s), (q / NGS) & 1);
-                if (k + 1 < ng) mbar_wait(smem_u32(bars + (q + 1) % NGS), ((q + 1) / NGS) & 1);
+                // one lane per warp polls (640 threads polling one mbarrier word serialise in the shared-memory pipe: measured
+                // ~1.3 us per group whatever its size); __syncwarp hands the observation to the other lanes
+                if (lane == 0) {
+                    if (k == 0) mbar_wait(smem_u32(bars + s), (q / NGS) & 1);        // later groups were waited for as "next"
+                    if (k + 1 < ng) mbar_wait(smem_u32(bars + (q + 1) % NGS), ((q + 1) / NGS) & 1);
+                }
+                __syncwarp();
                 const int ra = lo + k * G;
                 const int ia = max(ra, r0), ib = min(min(ra + G, hi + 1), r1);          // rows of this group that are computed
                 const int nrow_c = ib - ia;
@@ -196,7 +206,7 @@ static int ring_plan(int B, int C, int h, int w, RingGeom* g, int* nthreads, siz
     const size_t rowbytes = (size_t)(C + 1) * w * 4;
     int G = (int)(40960 / rowbytes);
     if (G < 1) return 0;
-    if (G > 4) G = 4;
+    if (G > 16) G = 16;                     // narrow / single-plane rows: more rows per barrier, so the per-group bookkeeping amortises
     if (G > h) G = h;
     const size_t budget = 200 * 1024;
     int NGS = (int)(budget / (G * rowbytes));
@@ -210,12 +220,17 @@ static int ring_plan(int B, int C, int h, int w, RingGeom* g, int* nthreads, siz
         const double eff = (double)items / ((double)rounds * T);
         if (eff > beff + 1e-9 || (eff > beff - 1e-9 && cw > best)) { beff = eff; best = cw; }
     }
+    if (const char* e = getenv("DSR_RING_WARPS")) {           // tuning knob (scripts/bench_stencils.py sweeps it)
+        const int v = atoi(e);
+        if (v >= 1 && v <= RING_MAX_WARPS) best = v;
+    }
     const int sms = dsr_num_sms();
     const long share = ((long)B * h + 4L * G - 1) / (4L * G);            // at least ~4 groups of rows per CTA
     g->B = B; g->h = h; g->w = w; g->G = G; g->NGS = NGS;
     *nthreads = 32 * (best + 1);
     *smem = (size_t)G * NGS * rowbytes + 2 * (size_t)NGS * sizeof(uint64_t);
-    *grid = (int)(share < sms ? share : sms);
+    const long ctas = (long)sms * (*smem <= 100 * 1024 ? 2 : 1);         // small rings: two CTAs per SM
+    *grid = (int)(share < ctas ? share : ctas);
     return 1;
 }
 
@@ -264,3 +279,4 @@ extern "C" int dsr_smooth_ring_suits(int B, int C, int h, int w) {
     RingGeom g; int nt, grid; size_t smem;
     return (long)B * h * w >= (2L << 20) && ring_plan(B, C, h, w, &g, &nt, &smem, &grid);
 }
+

@@ -634,3 +634,4 @@ def test_smooth_row_ring_rejects_unsuitable_shapes(ops):
     d, img = torch.zeros(1, 1, 8, 30, device="cuda"), torch.zeros(1, 3, 8, 30, device="cuda")
     with pytest.raises(RuntimeError):
         _call("dsr_smooth_level_fwd_ring", _p(d), _p(img), 1, 3, 8, 30, _p(torch.zeros(2, dtype=torch.float64, device="cuda"), torch.float64))
+
