@@ -291,200 +291,164 @@ normals_old_bwd_quad(const float* __restrict__ d, const float* __restrict__ g, i
 }
 
 // ------------------------------------------------------------------------------------------
-// camera-space normals (norms.py:75-108): z = (d+1)/2, P = K^-1 [u, v, 1] / ray_z * z, n = normalize(dP/dv x dP/du)
-//
-// The point map P is staged ONCE per pixel in shared memory in fp64 (4 pixels per task from one 16-byte load; the ray
-// division is skipped when the last row of K^-1 is (0, 0, 1) - every pinhole camera - where x / 1.0 == x bit for bit).
-// Positions outside the image hold the border-clamped point, so np.gradient's one-sided differences are plain
-// (P[+1] - P[-1]) * (border ? 1 : 0.5).  The differences and (forward) the cross product stay in fp64 - both cancel -
-// everything after that is fp32.  Shared tile: column c <-> j0 - 4 + c, row r <-> i0 - RH + r.
+// camera-space normals, AFFINE rays (every pin-hole K: last row of K^-1 == (0, 0, 1)): the closed fp32 form of
+// stencil_math.cuh (aff_*) - no fp64 point map, the rx ry Du Dv products of the cross product cancelled analytically.
+// The fp64 tiled kernels this replaces ran at 31 % / 16 % of the HBM peak, bound by ~50 fp64 instructions per pixel (forward)
+// and ~280 instructions per pixel (backward, ncu r36).  A camera with a perspective row in K^-1 (never a pin-hole K) takes
+// the per-pixel fp64 functions of stencil_math.cuh instead - slow, exact, and chosen per plane ON THE DEVICE (the
+// `affine` flag of its camera row), so the choice never depends on host knowledge of K and a captured CUDA graph stays
+// valid whatever K the next batch brings.  (Launching a second, separate kernel for those planes cost ~40-80 us of empty
+// blocks per call at 96 x 512 x 640 - measured r87 - hence one kernel with a block-uniform branch; the register caps keep
+// the occupancy of the fast path and let the rare path spill.)
 // ------------------------------------------------------------------------------------------
-#define PW (TW + 8)
-struct Cam {
-    double k[11];
+struct AffPlane {
+    AffCam c;
+    float rx0, ry0;           // ray of pixel (i, j0q): the quad's pixels are rx0 + e * k0, ry0 + e * k3
     bool affine;
-    __device__ __forceinline__ Cam(const double* __restrict__ cam) {
-#pragma unroll
-        for (int t = 0; t < 11; ++t) k[t] = cam[t];
-        affine = (k[6] == 0.0 && k[7] == 0.0 && k[8] == 1.0);
+    __device__ __forceinline__ AffPlane(const double* __restrict__ cam) {
+        affine = cam_is_affine(cam);
+        c = aff_cam(cam);
     }
-    __device__ __forceinline__ void ray(int i, int j, double& rx, double& ry) const {
-        const double u = k[9] + (double)j, v = k[10] + (double)i;
-        rx = k[0] * u + k[1] * v + k[2];
-        ry = k[3] * u + k[4] * v + k[5];
-        if (!affine) { const double c = k[6] * u + k[7] * v + k[8]; rx = rx / c; ry = ry / c; }
+    __device__ __forceinline__ void at(const double* __restrict__ cam, int i, int j) {
+        // affine rays: c = k6 u + k7 v + k8 == 1, so cam_ray()'s two fp64 divisions (~100 instructions per quad) are skipped
+        const double u = cam[9] + (double)j, v = cam[10] + (double)i;
+        rx0 = (float)(cam[0] * u + cam[1] * v + cam[2]);
+        ry0 = (float)(cam[3] * u + cam[4] * v + cam[5]);
     }
 };
-// raw fp64 differences of the point map for the 4 pixels (i, j .. j+3), from the depths of the quad's row (zc: columns
-// j-1 .. j+4), of the row above (zu) and below (zl), all border-clamped like their coordinates iu / il / jc
-__device__ __forceinline__ void quad_point_diffs(const Cam& cam, int i, int iu, int il, const int jc[6], const float zc[6],
-                                                 const float zu[4], const float zl[4], double du[3][4], double dv[3][4]) {
-    double Pc[3][6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) {
-        double rx, ry;
-        cam.ray(i, jc[e], rx, ry);
-        const double z = ((double)zc[e] + 1.0) / 2.0;
-        Pc[0][e] = rx * z; Pc[1][e] = ry * z; Pc[2][e] = z;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        double rxu, ryu, rxl, ryl;
-        cam.ray(iu, jc[e + 1], rxu, ryu);
-        cam.ray(il, jc[e + 1], rxl, ryl);
-        const double zU = ((double)zu[e] + 1.0) / 2.0, zL = ((double)zl[e] + 1.0) / 2.0;
-        dv[0][e] = rxl * zL - rxu * zU; dv[1][e] = ryl * zL - ryu * zU; dv[2][e] = zL - zU;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) du[k][e] = Pc[k][e + 2] - Pc[k][e];
-    }
+__device__ __noinline__ void normals_generic_fwd_px(const float* __restrict__ p, const double* __restrict__ cam, int H, int W, int i, int j,
+                                                    long plane, float* __restrict__ o) {
+    float n[3];
+    new_normal_fwd(p, cam, H, W, i, j, n);
+    o[(long)i * W + j] = n[0]; o[plane + (long)i * W + j] = n[1]; o[2 * plane + (long)i * W + j] = n[2];
 }
-// forward: no shared memory - the point map of the 14 pixels a quad touches (6 in its row, 4 above, 4 below) is rebuilt in
-// registers from three clamped 16-byte depth loads; the ray is affine in (i, j), so neighbours cost one DFMA each.
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, 4)
 normals_new_fwd_quad(const float* __restrict__ d, const double* __restrict__ cams, int H, int W, float* __restrict__ out) {
     const Quad q(H, W);
+    const double* cam = cams + blockIdx.z * DSR_CAM_DOUBLES;
+    AffPlane a(cam);
     if (!q.ok) return;
     const long plane = (long)H * W;
     const float* p = d + q.pl * plane;
-    const Cam cam(cams + q.pl * DSR_CAM_DOUBLES);
+    if (!a.affine) {                                          // perspective row in K^-1: per-pixel fp64 reference form
+        for (int e = 0; e < 4 && q.j + e < W; ++e) normals_generic_fwd_px(p, cam, H, W, q.i, q.j + e, plane, out + (long)q.pl * 3 * plane);
+        return;
+    }
     const bool vin = vec_ok(d, W), vout = vec_ok(out, W);
-    const int iu = max(q.i - 1, 0), il = min(q.i + 1, H - 1);
-    float zu[4], zl[4], zc[6];
-    load4(p + (long)iu * W, q.j, W, vin, zu);
-    load4(p + (long)il * W, q.j, W, vin, zl);
-    load6(p + (long)q.i * W, q.j, W, vin, zc);
-    // column coordinates clamped like the loads (the !vin path clamps every column; the vec path only the two outer ones)
-    int jc[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) jc[e] = min(max(q.j - 1 + e, 0), W - 1);
-    double du[3][4], dv[3][4];
-    quad_point_diffs(cam, q.i, iu, il, jc, zc, zu, zl, du, dv);
-    const float fh = edge_f(q.i, H);
+    float u[4], l[4], c[6];
+    load4(p + (long)max(q.i - 1, 0) * W, q.j, W, vin, u);
+    load4(p + (long)min(q.i + 1, H - 1) * W, q.j, W, vin, l);
+    load6(p + (long)q.i * W, q.j, W, vin, c);
+    a.at(cam, q.i, q.j);
+    const float mu = q.i > 0 ? 1.f : 0.f, md = q.i < H - 1 ? 1.f : 0.f, fh = edge_f(q.i, H);
     float n0[4], n1[4], n2[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        // m = Pv x Pu with Pu = du * su, Pv = dv * sv: the power-of-two factors commute with every rounding
-        const float sc = fh * edge_f(q.j + e, W);
-        const float m0 = (float)(dv[1][e] * du[2][e] - du[1][e] * dv[2][e]) * sc;
-        const float m1 = (float)(dv[2][e] * du[0][e] - du[2][e] * dv[0][e]) * sc;
-        const float m2 = (float)(dv[0][e] * du[1][e] - du[0][e] * dv[1][e]) * sc;
-        const float r = sqrtf(m0 * m0 + m1 * m1 + m2 * m2);
-        const float k = 1.f / (r > 1e-12f ? r : 1e-12f);
-        n0[e] = m0 * k; n1[e] = m1 * k; n2[e] = m2 * k;
+        const int j = q.j + e;
+        float Du, Su, Dv, Sv, m[3], n[3];
+        aff_terms(c[e], c[e + 2], u[e], l[e], j > 0 ? 1.f : 0.f, j < W - 1 ? 1.f : 0.f, mu, md, Du, Su, Dv, Sv);
+        aff_normal_m(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, Du, Su, Dv, Sv, fh * edge_f(j, W), m);
+        aff_normalize(m, n);
+        n0[e] = n[0]; n1[e] = n[1]; n2[e] = n[2];
     }
     float* o = out + (long)q.pl * 3 * plane;
     store4(o, W, q.i, q.j, n0, vout); store4(o + plane, W, q.i, q.j, n1, vout); store4(o + 2 * plane, W, q.i, q.j, n2, vout);
 }
-// backward: the DEPTH tile (+ 2-pixel halo, fp32) is staged in shared memory; phase 1 = per-pixel adjoints (dL/dPu, dL/dPv)
-// of the tile + 1-pixel halo in fp32 (column quads [j0 - 4, j0 + TW + 4), rows [i0 - 1, i0 + TH]), each task rebuilding
-// the point differences of its quad in fp64 registers; phase 2 = gather through np.gradient's taps and project on the
-// ray of the output pixel: dL/dz = sum c * (dPu . ray) + sum c * (dPv . ray), dL/dd = dL/dz / 2.
+// adjoints (R, L, Dn, Up) of the 4 pixels (i, j .. j+3) -> four shared planes (zeros outside the image)
+__device__ __forceinline__ void aff_adj_quad(const float* __restrict__ p, const float* __restrict__ gp, long plane, AffPlane& a,
+                                             const double* __restrict__ cam, int H, int W, int i, int j, bool vin,
+                                             float* __restrict__ sR, float* __restrict__ sL, float* __restrict__ sD, float* __restrict__ sU) {
+    float R[4] = {0.f, 0.f, 0.f, 0.f}, L[4] = {0.f, 0.f, 0.f, 0.f}, Dn[4] = {0.f, 0.f, 0.f, 0.f}, Up[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i >= 0 && i < H && j < W) {
+        float u[4], l[4], c[6], g0[4], g1[4], g2[4];
+        load4(p + (long)max(i - 1, 0) * W, j, W, vin, u);
+        load4(p + (long)min(i + 1, H - 1) * W, j, W, vin, l);
+        load6(p + (long)i * W, j, W, vin, c);
+        load4(gp + (long)i * W, j, W, vin, g0);
+        load4(gp + plane + (long)i * W, j, W, vin, g1);
+        load4(gp + 2 * plane + (long)i * W, j, W, vin, g2);
+        a.at(cam, i, j);
+        const float mu = i > 0 ? 1.f : 0.f, md = i < H - 1 ? 1.f : 0.f, fh = edge_f(i, H);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (j + e < W)
+                aff_pixel_adj(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, c[e], c[e + 2], u[e], l[e],
+                              j + e > 0 ? 1.f : 0.f, j + e < W - 1 ? 1.f : 0.f, mu, md, fh * edge_f(j + e, W), g0[e], g1[e], g2[e],
+                              R[e], L[e], Dn[e], Up[e]);
+    }
+    *reinterpret_cast<float4*>(sR) = make_float4(R[0], R[1], R[2], R[3]);
+    *reinterpret_cast<float4*>(sL) = make_float4(L[0], L[1], L[2], L[3]);
+    *reinterpret_cast<float4*>(sD) = make_float4(Dn[0], Dn[1], Dn[2], Dn[3]);
+    *reinterpret_cast<float4*>(sU) = make_float4(Up[0], Up[1], Up[2], Up[3]);
+}
+// same tiling as normals_old_bwd_quad: own quad per thread, 64 threads add the halo; shared planes: row r <-> i0 - 1 + r,
+// column c <-> j0 - 4 + c.  gd(i, j) = R(i, j-1) + L(i, j+1) + Dn(i-1, j) + Up(i+1, j) + the pixel's own term where its
+// neighbour was border-clamped onto itself.
+__device__ __noinline__ float normals_generic_bwd_px(const float* __restrict__ p, const float* __restrict__ gp, long plane,
+                                                     const double* __restrict__ cam, int H, int W, int i, int j) {
+    return new_normal_bwd(p, gp, plane, cam, H, W, i, j);
+}
 __global__ void __launch_bounds__(NT, 3)
 normals_new_bwd_quad(const float* __restrict__ d, const float* __restrict__ g, const double* __restrict__ cams, int H, int W,
                      float* __restrict__ gd) {
-    extern __shared__ __align__(16) float sD[];                  // [(TH+4)][PW] depths, then [6][(TH+2)*PW] adjoints
-    constexpr int LN1 = (TH + 2) * PW, QN = PW / 4;
-    float* adj = sD + (TH + 4) * PW;
+    __shared__ __align__(16) float aR[(TH + 2) * AW], aL[(TH + 2) * AW], aD[(TH + 2) * AW], aU[(TH + 2) * AW];
+    const double* cam = cams + blockIdx.z * DSR_CAM_DOUBLES;
+    AffPlane a(cam);
     const int i0 = blockIdx.y * TH, j0 = blockIdx.x * TW;
     const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) << 2;
     const long plane = (long)H * W;
     const float* p = d + blockIdx.z * plane;
-    const Cam cam(cams + blockIdx.z * DSR_CAM_DOUBLES);
-    const bool vin = vec_ok(d, W) && vec_ok(g, W), vout = vec_ok(gd, W);
-    for (int t = threadIdx.x; t < (TH + 4) * QN; t += NT) {      // depths, rows / columns clamped into the image
-        const int r = t / QN, qx = t - r * QN;
-        const int i = min(max(i0 - 2 + r, 0), H - 1), j = j0 - 4 + 4 * qx;
-        float4 v;
-        if (vin && j >= 0 && j + 3 < W) v = ld4(p + (long)i * W + j);
-        else {
-            const float* row = p + (long)i * W;
-            v = make_float4(__ldg(row + min(max(j, 0), W - 1)), __ldg(row + min(max(j + 1, 0), W - 1)),
-                            __ldg(row + min(max(j + 2, 0), W - 1)), __ldg(row + min(max(j + 3, 0), W - 1)));
-        }
-        *reinterpret_cast<float4*>(sD + r * PW + 4 * qx) = v;
-    }
-    __syncthreads();
     const float* gp = g + (long)blockIdx.z * 3 * plane;
-    for (int t = threadIdx.x; t < (TH + 2) * QN; t += NT) {
-        const int r = t / QN, qx = t - r * QN;
-        const int i = i0 - 1 + r, j = j0 - 4 + 4 * qx;
-        float A[6][4];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) A[k][e] = 0.f;
-        if (i >= 0 && i < H && j + 3 >= 0 && j < W) {
-            const float* c = sD + (r + 1) * PW + 4 * qx;            // depth row of pixel row i
-            const float4 c4 = *reinterpret_cast<const float4*>(c), u4 = *reinterpret_cast<const float4*>(c - PW),
-                         l4 = *reinterpret_cast<const float4*>(c + PW);
-            // (the first / last quad of the staged row has no left / right neighbour column; its outer pixel is unused)
-            const float zc[6] = {qx > 0 ? c[-1] : c4.x, c4.x, c4.y, c4.z, c4.w, qx < QN - 1 ? c[4] : c4.w};
-            const float zu[4] = {u4.x, u4.y, u4.z, u4.w}, zl[4] = {l4.x, l4.y, l4.z, l4.w};
-            int jc[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) jc[e] = min(max(j - 1 + e, 0), W - 1);
-            double du[3][4], dv[3][4];
-            quad_point_diffs(cam, i, max(i - 1, 0), min(i + 1, H - 1), jc, zc, zu, zl, du, dv);
-            float g0[4], g1[4], g2[4];
-            if (vin && j >= 0 && j + 3 < W) {
-                load4(gp + (long)i * W, j, W, true, g0); load4(gp + plane + (long)i * W, j, W, true, g1);
-                load4(gp + 2 * plane + (long)i * W, j, W, true, g2);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const long o = (long)i * W + min(max(j + e, 0), W - 1);
-                    g0[e] = __ldg(gp + o); g1[e] = __ldg(gp + plane + o); g2[e] = __ldg(gp + 2 * plane + o);
-                }
-            }
-            const float fh = edge_f(i, H);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (j + e >= 0 && j + e < W) {
-                    const float fw = edge_f(j + e, W);
-                    const float Pu[3] = {(float)du[0][e] * fw, (float)du[1][e] * fw, (float)du[2][e] * fw};
-                    const float Pv[3] = {(float)dv[0][e] * fh, (float)dv[1][e] * fh, (float)dv[2][e] * fh};
-                    float dPu[3], dPv[3];
-                    new_normal_adj_from_grads(Pu, Pv, g0[e], g1[e], g2[e], dPu, dPv);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { A[k][e] = dPu[k]; A[3 + k][e] = dPv[k]; }
-                }
-            }
+    if (!a.affine) {                                          // block-uniform: the whole plane takes the per-pixel fp64 form
+        const int i = i0 + ty;
+        if (i < H)
+            for (int e = 0; e < 4 && j0 + tx + e < W; ++e)
+                gd[blockIdx.z * plane + (long)i * W + j0 + tx + e] = normals_generic_bwd_px(p, gp, plane, cam, H, W, i, j0 + tx + e);
+        return;
+    }
+    const bool vin = vec_ok(d, W) && vec_ok(g, W), vout = vec_ok(gd, W);
+    {
+        const int o = (ty + 1) * AW + 4 + tx;
+        aff_adj_quad(p, gp, plane, a, cam, H, W, i0 + ty, j0 + tx, vin, aR + o, aL + o, aD + o, aU + o);
+    }
+    if (threadIdx.x < 32) {                       // rows i0 - 1 and i0 + TH
+        const int r = (threadIdx.x >> 4) ? TH + 1 : 0, o = r * AW + 4 + tx;
+        aff_adj_quad(p, gp, plane, a, cam, H, W, i0 - 1 + r, j0 + tx, vin, aR + o, aL + o, aD + o, aU + o);
+    } else if (threadIdx.x < 64) {                // columns j0 - 1 (its R is read) and j0 + TW (its L) of the tile's rows
+        const int t = threadIdx.x - 32, r = 1 + (t & 15), c = (t >> 4) ? TW + 4 : 3;
+        const int i = i0 - 1 + r, j = j0 - 4 + c;
+        float R = 0.f, L = 0.f, Dn = 0.f, Up = 0.f;
+        if (i < H && j >= 0 && j < W) {
+            const float* row = p + (long)i * W;
+            const long o = (long)i * W + j;
+            a.at(cam, i, j);
+            aff_pixel_adj(a.c, a.rx0, a.ry0, __ldg(row + max(j - 1, 0)), __ldg(row + min(j + 1, W - 1)),
+                          __ldg(p + (long)max(i - 1, 0) * W + j), __ldg(p + (long)min(i + 1, H - 1) * W + j),
+                          j > 0 ? 1.f : 0.f, j < W - 1 ? 1.f : 0.f, i > 0 ? 1.f : 0.f, i < H - 1 ? 1.f : 0.f,
+                          edge_f(i, H) * edge_f(j, W), __ldg(gp + o), __ldg(gp + plane + o), __ldg(gp + 2 * plane + o), R, L, Dn, Up);
         }
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            *reinterpret_cast<float4*>(adj + k * LN1 + r * PW + 4 * qx) = make_float4(A[k][0], A[k][1], A[k][2], A[k][3]);
+        aR[r * AW + c] = R; aL[r * AW + c] = L;
     }
     __syncthreads();
     const int i = i0 + ty, j = j0 + tx;
     if (i >= H || j >= W) return;
-    float cu, cs, cd;
-    adj_taps(i, H, cu, cs, cd);
-    float S[3][4];
-    const float* base = adj + (ty + 1) * PW + 4 + tx;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float* au = base + k * LN1;                        // dPu_k, this row
-        const float4 c4 = *reinterpret_cast<const float4*>(au);
-        const float w6[6] = {au[-1], c4.x, c4.y, c4.z, c4.w, au[4]};
-        const float* av = base + (3 + k) * LN1;                  // dPv_k, rows above / here / below
-        const float4 vu = *reinterpret_cast<const float4*>(av - PW), vc = *reinterpret_cast<const float4*>(av),
-                     vd = *reinterpret_cast<const float4*>(av + PW);
-        const float U[4] = {vu.x, vu.y, vu.z, vu.w}, C[4] = {vc.x, vc.y, vc.z, vc.w}, D[4] = {vd.x, vd.y, vd.z, vd.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float wl, ws, wr;
-            adj_taps(j + e, W, wl, ws, wr);
-            S[k][e] = wl * w6[e] + ws * w6[e + 1] + wr * w6[e + 2] + cu * U[e] + cs * C[e] + cd * D[e];
-        }
-    }
-    float o[4];
+    const int o = (ty + 1) * AW + 4 + tx;
+    const float4 r4 = *reinterpret_cast<const float4*>(aR + o), l4 = *reinterpret_cast<const float4*>(aL + o),
+                 dn = *reinterpret_cast<const float4*>(aD + o - AW), up = *reinterpret_cast<const float4*>(aU + o + AW);
+    const float Rv[5] = {aR[o - 1], r4.x, r4.y, r4.z, r4.w}, Lv[5] = {l4.x, l4.y, l4.z, l4.w, aL[o + 4]};
+    const float Dv[4] = {dn.x, dn.y, dn.z, dn.w}, Uv[4] = {up.x, up.y, up.z, up.w};
+    float self_d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i == H - 1) { const float4 t = *reinterpret_cast<const float4*>(aD + o); self_d[0] += t.x; self_d[1] += t.y; self_d[2] += t.z; self_d[3] += t.w; }
+    if (i == 0) { const float4 t = *reinterpret_cast<const float4*>(aU + o); self_d[0] += t.x; self_d[1] += t.y; self_d[2] += t.z; self_d[3] += t.w; }
+    float out4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        double rxd, ryd;
-        cam.ray(i, min(j + e, W - 1), rxd, ryd);
-        o[e] = 0.5f * (S[0][e] * (float)rxd + S[1][e] * (float)ryd + S[2][e]);
+        float v = Rv[e] + Lv[e + 1] + Dv[e] + Uv[e] + self_d[e];
+        if (j + e == W - 1) v += Rv[e + 1];
+        if (j + e == 0) v += Lv[e];
+        out4[e] = v;
     }
-    store4(gd + blockIdx.z * plane, W, i, j, o, vout);
+    store4(gd + blockIdx.z * plane, W, i, j, out4, vout);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -924,16 +888,7 @@ extern "C" int dsr_normals_new_fwd(const float* depth, const double* cams, int B
 extern "C" int dsr_normals_new_bwd(const float* depth, const float* gout, const double* cams, int B, int H, int W,
                                    float* gdepth, void* stream) {
     DSR_REQUIRE(depth && gout && cams && gdepth && B > 0 && H >= 2 && W >= 2 && PLANES_OK(B, H, W), "bad arguments");
-    const size_t smem = ((TH + 4) * PW + 6 * (TH + 2) * PW) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(normals_new_bwd_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            dsr_set_error("normals_new_bwd: cannot raise dynamic shared memory to %d", (int)smem);
-            return DSR_ERR_CUDA;
-        }
-        attr = true;
-    }
-    normals_new_bwd_quad<<<quad_grid(B, H, W), NT, smem, ST(stream)>>>(depth, gout, cams, H, W, gdepth);
+    normals_new_bwd_quad<<<quad_grid(B, H, W), NT, 0, ST(stream)>>>(depth, gout, cams, H, W, gdepth);
     return dsr_check_launch("normals_new_bwd");
 }
 

@@ -39,5 +39,30 @@ void host_normals_new_bwd(const float* d, const float* g, const double* cams, in
                 gd[b * plane + (long)i * W + j] =
                     new_normal_bwd(d + b * plane, g + b * 3 * plane, plane, cams + b * DSR_CAM_DOUBLES, H, W, i, j);
 }
+// closed-form fp32 path for affine (pin-hole) cameras; returns 0 when a camera of the batch is not affine
+int host_normals_aff_fwd(const float* d, const double* cams, int B, int H, int W, float* out) {
+    long plane = (long)H * W;
+    for (int b = 0; b < B; ++b) {
+        if (!cam_is_affine(cams + b * DSR_CAM_DOUBLES)) return 0;
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                float n[3];
+                aff_normal_fwd(d + b * plane, cams + b * DSR_CAM_DOUBLES, H, W, i, j, n);
+                for (int c = 0; c < 3; ++c) out[(b * 3 + c) * plane + (long)i * W + j] = n[c];
+            }
+    }
+    return 1;
+}
+int host_normals_aff_bwd(const float* d, const float* g, const double* cams, int B, int H, int W, float* gd) {
+    long plane = (long)H * W;
+    for (int b = 0; b < B; ++b) {
+        if (!cam_is_affine(cams + b * DSR_CAM_DOUBLES)) return 0;
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j)
+                gd[b * plane + (long)i * W + j] =
+                    aff_normal_bwd(d + b * plane, g + b * 3 * plane, plane, cams + b * DSR_CAM_DOUBLES, H, W, i, j);
+    }
+    return 1;
+}
 void host_bilin_ac(int o, int n_out, int n_in, int* i0, int* i1, float* l0, float* l1) { bilin_ac(o, n_out, n_in, *i0, *i1, *l0, *l1); }
 }

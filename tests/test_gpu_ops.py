@@ -118,6 +118,26 @@ def test_normals_new_fwd_bwd_golden(ops):
     assert np.allclose(dc.grad.cpu().numpy(), d2.grad.numpy(), rtol=2e-3, atol=1e-3 * float(d2.grad.abs().median()))
 
 
+def test_normals_new_mixed_cameras(ops):
+    """one pin-hole camera (closed fp32 form, normals_aff_*) and one with a perspective row in K (generic fp64 kernels) in the
+    SAME batch: every plane picks its kernel on the device; both against the fp64 oracle, forward and backward."""
+    from dsr_b200.norms import camera_table
+    H, W = 40, 72
+    K = torch.tensor([[[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]], [[577.87, 0.3, 319.5], [0.1, 570.0, 239.5], [1e-5, 2e-5, 1]],
+                      [[600.0, 0, 320], [0, 600.0, 240], [0, 0, 1]]], dtype=torch.float64)
+    crop = torch.tensor([[10, 10 + H, 20, 20 + W], [0, H, 0, W], [100, 100 + H, 300, 300 + W]])
+    assert float(torch.linalg.inv(K)[1, 2, :2].abs().max()) > 0          # sample 1 really is non-affine
+    d = _smooth_depth(3, H, W, 21).clamp_min(-0.9).requires_grad_(True)
+    go = torch.randn(3, 3, H, W, generator=G(22))
+    ref = ref_ops.surface_normals_new(d, K, crop)
+    (ref * go).sum().backward()
+    dc = d.detach().cuda().requires_grad_(True)
+    out = ops.normals_new(dc, camera_table(K, crop, 0.5, "cuda"))
+    (out * go.cuda()).sum().backward()
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= 2e-6
+    assert np.allclose(dc.grad.cpu().numpy(), d.grad.numpy(), rtol=2e-3, atol=1e-3 * float(d.grad.abs().median()))
+
+
 def test_tv_fwd_bwd(ops):
     x = torch.randn(2, 3, 37, 53, generator=G(8)).requires_grad_(True)
     ref = ref_ops.tv_loss(x)

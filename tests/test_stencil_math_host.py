@@ -67,6 +67,36 @@ def test_new_normals_fwd_bwd(hostlib):
     assert np.allclose(gd, ref, rtol=2e-3, atol=1e-3 * np.median(np.abs(ref)))
 
 
+@pytest.mark.parametrize("kind", ["golden", "smooth", "steep"])
+def test_new_normals_affine_closed_form(hostlib, kind):
+    """fp32 closed form for pin-hole cameras (csrc/stencil_math.cuh aff_*) against the fp64 oracle: forward and backward."""
+    g = load_golden("ops.npz")
+    if kind == "golden":
+        d, K, crop = np.ascontiguousarray(g["d"]), g["K"], g["crop"]
+    else:
+        B, H, W = 2, 37, 52
+        yy, xx = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+        amp = 0.002 if kind == "smooth" else 0.05
+        d = np.stack([np.clip(0.1 * b + amp * (xx * (1 + b) + 0.5 * yy) + 0.05 * np.sin(xx / 5.0 + b) * np.cos(yy / 7.0), -0.95, 0.95)
+                      for b in range(B)])[:, None].astype(np.float32)
+        K = np.repeat(np.array([[[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]]], np.float64), B, 0)
+        crop = np.array([[100, 100 + H, 200, 200 + W], [0, H, 0, W]], np.int64)
+    B, _, H, W = d.shape
+    cams = np.ascontiguousarray(_cams(K, crop))
+    out = np.empty((B, 3, H, W), np.float32)
+    assert hostlib.host_normals_aff_fwd(_ptr(d), _ptr(cams), B, H, W, _ptr(out)) == 1
+    dt = torch.from_numpy(d).requires_grad_(True)
+    ref = ref_ops.surface_normals_new(dt, torch.from_numpy(np.asarray(K)), torch.from_numpy(np.asarray(crop)))
+    assert np.abs(out - ref.detach().numpy()).max() <= 2e-6
+    go = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(4))
+    (ref * go).sum().backward()
+    gd = np.empty_like(d)
+    assert hostlib.host_normals_aff_bwd(_ptr(d), _ptr(go.numpy()), _ptr(cams), B, H, W, _ptr(gd)) == 1
+    refg = dt.grad.numpy()
+    assert np.isfinite(gd).all()
+    assert np.allclose(gd, refg, rtol=2e-3, atol=1e-3 * np.median(np.abs(refg)))
+
+
 def test_bilinear_align_corners_indices(hostlib):
     for n_in, n_out in ((256, 64), (256, 128), (640, 160), (96, 24), (7, 3)):
         x = torch.arange(n_in, dtype=torch.float32)[None, None, None, :]
