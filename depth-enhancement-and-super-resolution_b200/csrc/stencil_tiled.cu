@@ -340,16 +340,28 @@ normals_new_fwd_quad(const float* __restrict__ d, const double* __restrict__ cam
     load4(p + (long)min(q.i + 1, H - 1) * W, q.j, W, vin, l);
     load6(p + (long)q.i * W, q.j, W, vin, c);
     a.at(cam, q.i, q.j);
-    const float mu = q.i > 0 ? 1.f : 0.f, md = q.i < H - 1 ? 1.f : 0.f, fh = edge_f(q.i, H);
     float n0[4], n1[4], n2[4];
+    if (q.i > 0 && q.i < H - 1 && q.j > 0 && q.j + 4 < W) {
+        // quads that touch no image border (all but a frame of tiles): masks and the 1/2 factors are literals
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int j = q.j + e;
-        float Du, Su, Dv, Sv, m[3], n[3];
-        aff_terms(c[e], c[e + 2], u[e], l[e], j > 0 ? 1.f : 0.f, j < W - 1 ? 1.f : 0.f, mu, md, Du, Su, Dv, Sv);
-        aff_normal_m(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, Du, Su, Dv, Sv, fh * edge_f(j, W), m);
-        aff_normalize(m, n);
-        n0[e] = n[0]; n1[e] = n[1]; n2[e] = n[2];
+        for (int e = 0; e < 4; ++e) {
+            float Du, Su, Dv, Sv, m[3], n[3];
+            aff_terms(c[e], c[e + 2], u[e], l[e], 1.f, 1.f, 1.f, 1.f, Du, Su, Dv, Sv);
+            aff_normal_m(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, Du, Su, Dv, Sv, 0.25f, m);
+            aff_normalize(m, n);
+            n0[e] = n[0]; n1[e] = n[1]; n2[e] = n[2];
+        }
+    } else {
+        const float mu = q.i > 0 ? 1.f : 0.f, md = q.i < H - 1 ? 1.f : 0.f, fh = edge_f(q.i, H);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = q.j + e;
+            float Du, Su, Dv, Sv, m[3], n[3];
+            aff_terms(c[e], c[e + 2], u[e], l[e], j > 0 ? 1.f : 0.f, j < W - 1 ? 1.f : 0.f, mu, md, Du, Su, Dv, Sv);
+            aff_normal_m(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, Du, Su, Dv, Sv, fh * edge_f(j, W), m);
+            aff_normalize(m, n);
+            n0[e] = n[0]; n1[e] = n[1]; n2[e] = n[2];
+        }
     }
     float* o = out + (long)q.pl * 3 * plane;
     store4(o, W, q.i, q.j, n0, vout); store4(o + plane, W, q.i, q.j, n1, vout); store4(o + 2 * plane, W, q.i, q.j, n2, vout);
@@ -368,13 +380,20 @@ __device__ __forceinline__ void aff_adj_quad(const float* __restrict__ p, const 
         load4(gp + plane + (long)i * W, j, W, vin, g1);
         load4(gp + 2 * plane + (long)i * W, j, W, vin, g2);
         a.at(cam, i, j);
-        const float mu = i > 0 ? 1.f : 0.f, md = i < H - 1 ? 1.f : 0.f, fh = edge_f(i, H);
+        if (i > 0 && i < H - 1 && j > 0 && j + 4 < W) {          // no image border in reach: literal masks / factors
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (j + e < W)
+            for (int e = 0; e < 4; ++e)
                 aff_pixel_adj(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, c[e], c[e + 2], u[e], l[e],
-                              j + e > 0 ? 1.f : 0.f, j + e < W - 1 ? 1.f : 0.f, mu, md, fh * edge_f(j + e, W), g0[e], g1[e], g2[e],
-                              R[e], L[e], Dn[e], Up[e]);
+                              1.f, 1.f, 1.f, 1.f, 0.25f, g0[e], g1[e], g2[e], R[e], L[e], Dn[e], Up[e]);
+        } else {
+            const float mu = i > 0 ? 1.f : 0.f, md = i < H - 1 ? 1.f : 0.f, fh = edge_f(i, H);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j + e < W)
+                    aff_pixel_adj(a.c, a.rx0 + (float)e * a.c.k0, a.ry0 + (float)e * a.c.k3, c[e], c[e + 2], u[e], l[e],
+                                  j + e > 0 ? 1.f : 0.f, j + e < W - 1 ? 1.f : 0.f, mu, md, fh * edge_f(j + e, W), g0[e], g1[e], g2[e],
+                                  R[e], L[e], Dn[e], Up[e]);
+        }
     }
     *reinterpret_cast<float4*>(sR) = make_float4(R[0], R[1], R[2], R[3]);
     *reinterpret_cast<float4*>(sL) = make_float4(L[0], L[1], L[2], L[3]);
