@@ -427,7 +427,9 @@ def run_ours(args):
         line = dict(metric="RGB-D train pair-samples/sec (main net)", value=world * B * args.steps / (ms * 1e-3),
                     unit="pair-samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype=(f"{args.dtype} x{args.passes} operands (weight gradients: {ops.CONFIG['bwd_dtype']} x{wmult}), f32 accumulate"
+                    dtype=(f"{args.dtype} x{args.passes} operands (weight gradients: {ops.CONFIG['bwd_dtype']} x{wmult}"
+                           + (f"; data gradients of layers >= {ops.CONFIG['big_hw']} px: {ops.CONFIG['bwd_dtype']} x{ops.CONFIG['big_bwd_passes']}"
+                              if ops.CONFIG["big_hw"] and ops.CONFIG["big_bwd_passes"] else "") + "), f32 accumulate"
                            if args.engine == "tc" else "f32"),
                     data="synthetic",
                     config=dict(workload=wl["name"], crop=[H, W], batch_per_gpu=B, parallelism=f"dp{world}", engine=args.engine,
