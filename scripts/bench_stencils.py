@@ -76,7 +76,7 @@ def main():
                                                        -0.97, pu8(gt), p(out1), p(out1b))),
         ("normals_old fwd (4P -> 12P)", 16 * P, lambda: call("dsr_normals_old_fwd", p(d), B, H, W, 100.0, p(out3))),
         ("normals_old bwd (16P -> 4P)", 20 * P, lambda: call("dsr_normals_old_bwd", p(d), p(g3), B, H, W, 100.0, p(out1))),
-        ("normals_new fwd (4P -> 12P, fp64 inside)", 16 * P, lambda: call("dsr_normals_new_fwd", p(d), p64(cams), B, H, W, p(out3))),
+        ("normals_new fwd (4P -> 12P, closed fp32 form)", 16 * P, lambda: call("dsr_normals_new_fwd", p(d), p64(cams), B, H, W, p(out3))),
         ("normals_new bwd (16P -> 4P)", 20 * P, lambda: call("dsr_normals_new_bwd", p(d), p(g3), p64(cams), B, H, W, p(out1))),
         ("tv fwd (12P -> scalar)", 12 * P, lambda: call("dsr_tv_fwd", p(n3), B * 3, H, W, p64(acc))),
         ("tv bwd (12P -> 12P)", 24 * P, lambda: call("dsr_tv_bwd", p(n3), B * 3, H, W, p(one), 1.0, p(out3))),
