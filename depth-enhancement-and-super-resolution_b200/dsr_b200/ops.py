@@ -765,7 +765,7 @@ class _Conv2d(Function):
 
 def _new_stats(N, C, device):
     """per-(n, c) (sum, sum of squares) accumulator the GEMM epilogue adds into (InstanceNorm / GroupNorm statistics)"""
-    st = torch.zeros(N * C * 2, device=device, dtype=torch.float64)
+    st = _zeros_f64(N * C * 2, device)              # the step's pre-zeroed pool: no fill kernel per layer (137 per step before)
     st.filled = False
     return st
 
