@@ -194,6 +194,57 @@ def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=
                 host_cpus=os.cpu_count())
 
 
+def torch_gpu_bar(wl, steps=5, warmup=3, device="cuda:0"):
+    """--torch-gpu-bar (SURVEY.md section 8d "GPU reference bar"): the five nets of the step through torch / cuDNN eager on the
+    SAME GPU - frozen G_A_d, I2D_features, Image2Depth forward, Depth_f and Task forward + backward (oracle/ref_nets.py, the
+    functional restatement of the reference's nn.Modules over reference-layout state_dicts; none of this repo's kernels).
+    No rectangle holes, no loss stack (an L1 on the two predictions stands in), no optimizer: a LOWER bound of the reference's
+    GPU step.  A reported baseline like `cpu_baseline`, not the thing measured or shipped."""
+    import torch
+    from oracle import ref_nets
+    torch.manual_seed(0)
+    host = make_model(wl, [], False, name="cpu")
+    sds = {n: {k: v.detach().float().to(device) for k, v in getattr(host, "net" + n).state_dict().items()} for n in host.model_names}
+    for n in ("Depth_f", "Task"):
+        for v in sds[n].values():
+            v.requires_grad_(True)
+    b = make_batch(wl, 1)
+    si, ri, sd_, rd = (b[k].float().to(device) for k in ("A_i", "B_i", "A_d", "B_d"))
+    out = {}
+    for tag, tf32 in (("fp32", False), ("tf32_conv", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+
+        def step():
+            for n in ("Depth_f", "Task"):
+                for v in sds[n].values():
+                    v.grad = None
+            with torch.no_grad():
+                s2r = ref_nets.translation_generator(sds["G_A_d"], sd_, si)
+                f_s, f_r = ref_nets.resnet_generator(sds["I2D_features"], si), ref_nets.resnet_generator(sds["I2D_features"], ri)
+                dbi_s, dbi_r = ref_nets.unet_generator(sds["Image2Depth"], f_s), ref_nets.unet_generator(sds["Image2Depth"], f_r)
+            in_s, in_r = torch.cat([s2r, dbi_s], 1), torch.cat([rd, dbi_r], 1)
+            fd_s, fd_r = ref_nets.resnet_generator(sds["Depth_f"], in_s), ref_nets.resnet_generator(sds["Depth_f"], in_r)
+            p_s = ref_nets.unet_generator(sds["Task"], torch.cat([f_s, fd_s, in_s, si], 1))
+            p_r = ref_nets.unet_generator(sds["Task"], torch.cat([f_r, fd_r, in_r, ri], 1))
+            ((p_s - sd_).abs().mean() + (p_r - rd).abs().mean()).backward()
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[tag] = dict(ms_per_step=e0.elapsed_time(e1) / steps, pair_samples_per_s=wl["B"] * steps / (e0.elapsed_time(e1) * 1e-3))
+    out["note"] = ("torch %s / cuDNN eager on the same GPU, batch %d at %dx%d: five nets forward, Depth_f + Task backward, L1 stand-in loss; "
+                   "no rectangle holes / loss stack / optimizer (lower bound of the reference's GPU step); fp32 = "
+                   "cudnn.allow_tf32 False, tf32_conv = torch's default" % (torch.__version__, wl["B"], wl["H"], wl["W"]))
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -421,6 +472,12 @@ def run_ours(args):
             r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
             cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
                        sample=f"2 steps of batch {Bc} at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
+        gpu_bar = None
+        if args.torch_gpu_bar and world == 1 and not any(wl.get(k) for k in ("sr", "i2d", "gan", "tr")):
+            try:
+                gpu_bar = torch_gpu_bar(wl, device=f"cuda:{local}")
+            except Exception as e:                      # a baseline that cannot run must not take the measurement down
+                gpu_bar = dict(error=f"{type(e).__name__}: {e}"[:300])
         extras = None
         if args.inference and not any(wl.get(k) for k in ("sr", "i2d", "gan", "tr")) and world == 1:
             extras = inference_ms_per_frame(local)
@@ -441,6 +498,8 @@ def run_ours(args):
                     gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu,
                     step_tflops=flop_step / (ms / args.steps * 1e-3) / 1e12, inference_640x480=extras,
                     kernel_times_ms={k: round(d["ms"], 3) for k, d in top})
+        if gpu_bar is not None:
+            line["torch_eager_gpu"] = gpu_bar
         print(json.dumps(line), flush=True)
     if world > 1:
         # leave without tearing NCCL down: destroying a communicator whose collectives were captured into a live CUDA
@@ -463,6 +522,8 @@ def main():
     ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-bar", action="store_true",
+                    help="also time the five nets through torch / cuDNN eager on the same GPU (SURVEY.md 8d 'GPU reference bar'; off by default)")
     ap.add_argument("--layer-table", default="", help="write every library call of one step (name, ms, shape, GMACs) to this JSON file")
     ap.add_argument("--kernel-table", default="", help="write the in-situ per-kernel device times of 3 steps (torch.profiler / CUPTI, warm caches) to this JSON file")
     ap.add_argument("--inference", type=int, default=1, help="1 = also time the 640x480 inference forward (ms/frame)")
