@@ -7,8 +7,8 @@
 // The register kernels in stencil_tiled.cu are bound by load latency (ncu: long-scoreboard stalls, ~50 % of the HBM peak):
 // a thread can only keep the loads of its own 4 x 4 pixels in flight.  Here the bytes in flight are decoupled from the
 // threads: one producer warp streams whole image rows (all planes of a sample: depth + C image channels) into a ring of
-// shared-memory row slots with 1-D bulk copies (cp.async.bulk, completion counted on mbarriers), 2..4 rows per
-// barrier ("group"), up to ~160 KB in flight per SM; the consumer warps compute from shared memory (16-byte reads) and hand
+// shared-memory row slots with 1-D bulk copies (cp.async.bulk, one copy per plane and "group" of 1..16 consecutive rows -
+// contiguous in every plane - completion counted on the group's mbarrier), up to ~160 KB in flight per SM; the consumer warps compute from shared memory (16-byte reads) and hand
 // the slots back through `empty` mbarriers.  The image rows are split evenly over one CTA per SM; a CTA reads every row of its
 // share once (+ one or two halo rows per sample it touches) and keeps the pipeline full across samples.
 #include "tc_common.cuh"

@@ -53,8 +53,11 @@ int dsr_rect_holes(const float* valid, const float* depth, const int* rects, con
 int dsr_normals_old_fwd(const float* depth, int B, int H, int W, float scale, float* out /*B,3,H,W*/, void* stream);
 int dsr_normals_old_bwd(const float* depth, const float* gout, int B, int H, int W, float scale, float* gdepth,
                         void* stream);
-/* camera-space normals (fp64 inside), fwd / bwd.  models/norms.py:103-108, :75-101, :29-73.
- * cams: double [B][11] = K^-1 row-major (9), w0 + shift, h0 + shift. */
+/* camera-space normals, fwd / bwd.  models/norms.py:103-108, :75-101, :29-73.
+ * cams: double [B][11] = K^-1 row-major (9), w0 + shift, h0 + shift.  A plane whose K^-1 has the last row (0, 0, 1) (every
+ * pin-hole K) runs the closed fp32 form of csrc/stencil_math.cuh (aff_*: the reference's fp64 point map cancelled
+ * analytically, within 2e-6 of it); any other camera runs the reference's fp64 arithmetic per pixel.  Chosen per plane on the
+ * device. */
 int dsr_normals_new_fwd(const float* depth, const double* cams, int B, int H, int W, float* out, void* stream);
 int dsr_normals_new_bwd(const float* depth, const float* gout, const double* cams, int B, int H, int W,
                         float* gdepth, void* stream);

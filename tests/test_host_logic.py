@@ -68,3 +68,34 @@ def test_scheduler_and_optimizer_contract():
     m.update_learning_rate()
     n_train = sum(p.numel() for p in m.netDepth_f.parameters()) + sum(p.numel() for p in m.netTask.parameters())
     assert n_train == 2159616 + 42085761
+
+
+def test_mma_pass_policy_is_pure_host_logic():
+    """ops._passes: forward GEMMs keep the parity mode's three passes; data-gradient GEMMs (a backward operand format is
+    passed) of layers with >= big_hw output pixels run big_bwd_passes; the knobs switch the policy off."""
+    from dsr_b200 import ops
+    old, old_fwd = dict(ops.CONFIG), dict(ops._FWD)
+    try:
+        assert ops.CONFIG["passes"] == 3 and ops.CONFIG["big_hw"] == 1024 and ops.CONFIG["big_bwd_passes"] == 1
+        ops._FWD.update(hw=64 * 64, trainable=True)
+        assert ops._passes(None) == 3 and ops._passes("bf16") == 1
+        ops._FWD.update(hw=16 * 16)
+        assert ops._passes(None) == 3 and ops._passes("bf16") == 3
+        ops.CONFIG.update(big_hw=0)
+        ops._FWD.update(hw=256 * 256)
+        assert ops._passes("bf16") == 3
+        ops.CONFIG.update(big_hw=1024, big_fwd_passes=2, passes=1)
+        assert ops._passes(None) == 1 and ops._passes("bf16") == 1          # never more than the global pass count
+    finally:
+        ops.CONFIG.clear(); ops.CONFIG.update(old)
+        ops._FWD.clear(); ops._FWD.update(old_fwd)
+
+
+def test_ring_planner_is_callable_without_a_gpu(built_lib):
+    """dsr_smooth_ring_suits is host arithmetic: big plane sets suit the row ring, training-crop sizes and ragged widths do not"""
+    from dsr_b200 import _lib
+    lib = _lib.load()
+    assert lib.dsr_smooth_ring_suits(96, 3, 512, 640) == 1
+    assert lib.dsr_smooth_ring_suits(6, 3, 256, 256) == 0           # 393 K pixels: the register kernels
+    assert lib.dsr_smooth_ring_suits(96, 3, 512, 642) == 0          # rows must be 16-byte multiples
+    assert lib.dsr_smooth_ring_suits(64, 3, 1024, 8192) == 0        # one row of all planes must fit a 40 KB group
