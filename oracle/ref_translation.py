@@ -1,7 +1,9 @@
 """Oracle (torch CPU fp32) restatement of the reference's translation block: models/translation_network.py (SurfaceNormals
 :329-360, losses :281-327, GANLoss :139-205) and one ``TranslationModel.optimize_parameters`` call
-(models/translation_model.py:140-291) with the default flags (cycle B, depth + normal discriminators, identity B, depth range
-losses).  TEST INFRASTRUCTURE ONLY.  Pinned against the live reference by tests/golden/translation_step_*.npz."""
+(models/translation_model.py:140-291): the default flags (cycle B, depth + normal discriminators, identity B, depth range
+losses) and, optionally, ``use_cycle_A`` / ``l_mean_A`` / ``l_mean_B`` / ``l_tv_A`` (``inp_B='depth'`` is not restated).
+TEST INFRASTRUCTURE ONLY.  Pinned against the live reference by tests/golden/translation_step_*.npz (default flags) and
+tests/golden/translation_flags_b1_64.npz (the optional terms)."""
 import math
 
 import torch
@@ -35,6 +37,20 @@ def cos_sim_loss(x, y):                 # CosSimLoss (:310-316)
     return torch.mean(1 - F.cosine_similarity(x, y, dim=1))
 
 
+def masked_mean_dif(x, y, mask):        # MaskedMeanDif (:288-293): per-sample masked mean difference, then mean of |.|
+    return torch.mean(torch.abs(((y - x) * mask).sum(dim=(2, 3)) / (mask.sum(dim=(2, 3)) + 1e-6)))
+
+
+def masked_cos_sim_loss(x, y, mask):    # MaskedCosSimLoss (:320-327) - the reference divides by sum(mask) + 1e+6 (sic)
+    loss = 1 - F.cosine_similarity(x, y, dim=1)
+    return (loss.unsqueeze(1) * mask).sum() / (mask.sum() + 1e+6)
+
+
+def tv_norm(x):                         # TV_norm(surf_normal=True) (:302-311): first two components only
+    x = x[:, :2]
+    return ((x[:, :, 1:, :] - x[:, :, :-1, :]).pow(2).sum() + (x[:, :, :, 1:] - x[:, :, :, :-1]).pow(2).sum()) / x.numel()
+
+
 def lsgan(pred, real):                  # GANLoss('lsgan') (:161-205)
     return F.mse_loss(pred, torch.ones_like(pred) if real else torch.zeros_like(pred))
 
@@ -44,10 +60,11 @@ class OracleTranslationStep:
     weight_decay w_decay_G on the generators (translation_model.py:117-118)."""
 
     def __init__(self, sds, lr=2e-4, beta1=0.5, w_decay_G=1e-4, num_iter_gen=3, l_cycle_B=5.0, l_normal=1.0, l_identity=1.0,
-                 l_depth_A=5.0, l_depth_B=5.0):
+                 l_depth_A=5.0, l_depth_B=5.0, use_cycle_A=False, l_cycle_A=10.0, l_mean_A=0.0, l_mean_B=0.0, l_tv_A=0.0):
         self.sd = {k: {n: t.detach().clone().float().requires_grad_(True) for n, t in v.items()} for k, v in sds.items()}
         self.cfg = dict(lr=lr, beta1=beta1, wd=w_decay_G, n_gen=num_iter_gen, l_cycle_B=l_cycle_B, l_normal=l_normal,
-                        l_identity=l_identity, l_depth_A=l_depth_A, l_depth_B=l_depth_B)
+                        l_identity=l_identity, l_depth_A=l_depth_A, l_depth_B=l_depth_B, use_cycle_A=use_cycle_A,
+                        l_cycle_A=l_cycle_A, l_mean_A=l_mean_A, l_mean_B=l_mean_B, l_tv_A=l_tv_A)
         self.adam = {k: {n: (torch.zeros_like(p), torch.zeros_like(p)) for n, p in v.items()} for k, v in self.sd.items()}
         self.steps = {"G": 0, "D": 0}
 
@@ -67,6 +84,9 @@ class OracleTranslationStep:
             src = dict(real_norm_A=A_d, real_norm_B=B_d, fake_norm_A=t["fake_depth_A"], fake_norm_B=t["fake_depth_B"])[k]
             t[k] = fov_normals(src)
         t["hole_mask_B"] = t["fake_depth_A"] <= -0.98
+        if self.cfg["use_cycle_A"]:                                          # (:165-172) A -> B -> A through G_B
+            t["rec_depth_A"] = self._G("G_B", t["fake_depth_B"], A_i)
+            t["rec_norm_A"] = fov_normals(t["rec_depth_A"])
         t["rec_depth_B"] = self._G("G_A", t["fake_depth_A"], B_i)          # (:176-178; the first, detached call is discarded)
         t["rec_norm_B"] = fov_normals(t["rec_depth_B"])
         t["idt_A"] = self._G("G_A", B_d, B_i)                               # (:181-187)
@@ -110,6 +130,19 @@ class OracleTranslationStep:
             rng_A = masked_l1(t["fake_depth_B"], t["A_d"], ~t["hole_mask_A"]) * c["l_depth_A"]
             rng_B = masked_l1(t["fake_depth_A"], t["B_d"], ~t["hole_mask_B"]) * c["l_depth_B"]
             loss_G = (G_A + rng_A) + (G_B + cyc_B + cyc_n_B + idt_B + rng_B)
+            extra = {}
+            if c["use_cycle_A"]:                                             # (:222-225)
+                mA = ~t["hole_mask_A"]
+                extra["cycle_A"] = masked_l1(t["rec_depth_A"], t["A_d"], mA) * c["l_cycle_A"]
+                extra["cycle_n_A"] = masked_cos_sim_loss(t["rec_norm_A"], t["real_norm_A"], mA.repeat(1, 3, 1, 1)) * c["l_normal"] * c["l_cycle_A"]
+            if c["l_mean_A"] > 0:                                            # (:240-245)
+                extra["mean_dif_A"] = masked_mean_dif(t["fake_depth_B"], t["A_d"], ~t["hole_mask_A"]) * c["l_mean_A"]
+            if c["l_mean_B"] > 0:
+                extra["mean_dif_B"] = masked_mean_dif(t["fake_depth_A"], t["B_d"], ~t["hole_mask_B"]) * c["l_mean_B"]
+            if c["l_tv_A"] > 0:                                              # (:247-249)
+                extra["tv_norm_A"] = tv_norm(t["fake_norm_B"]) * c["l_tv_A"]
+            for v in extra.values():
+                loss_G = loss_G + v
             gs = torch.autograd.grad(loss_G, [p for n in ("G_A", "G_B") for p in self.sd[n].values()], allow_unused=True)
             k = 0
             for n in ("G_A", "G_B"):
@@ -117,6 +150,7 @@ class OracleTranslationStep:
                     p.grad = gs[k]; k += 1
             L = dict(G_A=float(G_A), G_B=float(G_B), cycle_B=float(cyc_B), cycle_n_B=float(cyc_n_B), idt_B=float(idt_B),
                      depth_range_A=float(rng_A), depth_range_B=float(rng_B), G=float(loss_G))
+            L.update({k2: float(v) for k2, v in extra.items()})
             if first is None:
                 first = dict(losses=dict(L), tensors={k2: v.detach().clone() for k2, v in t.items()},
                              grads={(n, pn): p.grad.detach().clone() for n in ("G_A", "G_B") for pn, p in self.sd[n].items() if p.grad is not None})

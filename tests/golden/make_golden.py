@@ -287,13 +287,14 @@ def translation_batch(B, H, W, seed=4):
                 B_img=torch.rand(B, 3, H, W, generator=g) * 2 - 1, B_depth=B_d)
 
 
-def golden_translation_step(B=1, H=64, W=64, n_gen=2, tag="translation_step_b1_64"):
-    """One TranslationModel.optimize_parameters (models/translation_model.py:274-291) of the live reference, default loss flags,
-    --num_iter_gen 2, normal init; the loop is unrolled here to record the first generator iteration's gradients."""
+def golden_translation_step(B=1, H=64, W=64, n_gen=2, tag="translation_step_b1_64", extra_flags=(), extra_losses=()):
+    """One TranslationModel.optimize_parameters (models/translation_model.py:274-291) of the live reference, default loss flags
+    (plus `extra_flags`), --num_iter_gen 2, normal init; the loop is unrolled here to record the first generator iteration's
+    gradients."""
     sys.argv = ["main.py", "--gpu_ids", "-1", "--custom_pathes", "--use_scannet", "--lr", "0.0002", "--model", "translation_block",
                 "--batch_size", str(B), "--name", "golden_tr", "--netD", "n_layers", "--crop_size_h", str(H), "--crop_size_w", str(W),
                 "--do_train", "--max_distance", "5100", "--init_type", "normal", "--model_type", "translation",
-                "--num_iter_gen", str(n_gen), "--checkpoints_dir", "/tmp/golden/ckpt"]
+                "--num_iter_gen", str(n_gen), "--checkpoints_dir", "/tmp/golden/ckpt"] + list(extra_flags)
     from options.train_options import TrainOptions
     opt = TrainOptions().parse()
     from models.translation_model import TranslationModel
@@ -316,9 +317,11 @@ def golden_translation_step(B=1, H=64, W=64, n_gen=2, tag="translation_step_b1_6
         if it == 0:
             for k in ("fake_depth_B", "fake_depth_A", "rec_depth_B", "idt_B", "fake_norm_B", "real_norm_A"):
                 out["s0/" + k] = getattr(model, k).detach().numpy()
-            for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+            for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B") + tuple(extra_losses):
                 out["s0/loss/" + k] = np.float64(float(getattr(model, "loss_" + k)))
             out["s0/loss/G"] = np.float64(float(model.loss_G))
+            if "cycle_A" in extra_losses:
+                out["s0/rec_depth_A"] = model.rec_depth_A.detach().numpy()
             gi = 0
             for name in ("G_A", "G_B"):
                 for n, prm in getattr(model, "net" + name).named_parameters():
@@ -339,7 +342,7 @@ def golden_translation_step(B=1, H=64, W=64, n_gen=2, tag="translation_step_b1_6
             out[f"end/g/{name}/{n}"] = np.array([float(gr.norm()), float(gr @ proj_vec(gr.numel(), 5000 + gi))])
             gi += 1
     model.optimizer_D.step()
-    for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+    for k in ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B") + tuple(extra_losses):
         out["end/loss/" + k] = np.float64(float(getattr(model, "loss_" + k)))
     out["end/fake_depth_B"] = model.fake_depth_B.detach().numpy()
     for name in nets:                                   # weights after the step: pins both Adam variants
@@ -412,7 +415,7 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation", "translation_flags"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -430,3 +433,8 @@ if __name__ == "__main__":
         golden_gan_blocks()
     if "translation" in which:
         golden_translation_step()
+    if "translation_flags" in which:
+        # the optional loss terms (translation_model.py:222-249): cycle A (masked L1 + masked cosine), mean differences, TV of normals
+        golden_translation_step(tag="translation_flags_b1_64",
+                                extra_flags=["--use_cycle_A", "--l_mean_A", "0.5", "--l_mean_B", "0.7", "--l_tv_A", "2.0"],
+                                extra_losses=("cycle_A", "cycle_n_A", "mean_dif_A", "mean_dif_B", "tv_norm_A"))

@@ -69,6 +69,38 @@ def test_translation_oracle_matches_reference():
         assert abs(float(v.norm()) - ref_norm) <= 1e-6 * ref_norm and abs(float(v @ proj_vec(v.numel(), 6000)) - ref_proj) <= 1e-4 * ref_norm, n
 
 
+def test_translation_oracle_optional_loss_terms_match_reference():
+    """use_cycle_A + l_mean_A / l_mean_B + l_tv_A (translation_model.py:222-249; MaskedCosSimLoss with its 1e+6 denominator,
+    MaskedMeanDif, TV_norm on the first two normal components): the oracle against one optimize_parameters call of the live
+    reference run with those flags (tests/golden/make_golden.py translation_flags)."""
+    g = load_golden("translation_flags_b1_64.npz")
+    host, sds = _model()
+    for n in NETS:
+        a = float(sum(v.double().abs().sum() for v in sds[n].values()))
+        assert abs(a - float(g["wsum/" + n][0])) <= 1e-9 * a, n
+    orc = ref_translation.OracleTranslationStep(sds, num_iter_gen=2, use_cycle_A=True, l_cycle_A=10.0, l_mean_A=0.5, l_mean_B=0.7,
+                                                l_tv_A=2.0)
+    out = orc.step(translation_batch(1, 64, 64))
+    f = out["first"]
+    assert rel_l2(f["tensors"]["rec_depth_A"], g["s0/rec_depth_A"]) <= 2e-5
+    for k in ("cycle_A", "cycle_n_A", "mean_dif_A", "mean_dif_B", "tv_norm_A", "G", "cycle_B", "depth_range_A"):
+        assert abs(f["losses"][k] - float(g["s0/loss/" + k])) <= 2e-5 * abs(float(g["s0/loss/" + k])), (k, f["losses"][k])
+    gi = 0
+    for name in ("G_A", "G_B"):
+        for n in sds[name]:
+            ref_norm, ref_proj = g[f"s0/g/{name}/{n}"]
+            gr = f["grads"][(name, n)].double().flatten()
+            assert abs(float(gr.norm()) - ref_norm) <= 2e-3 * ref_norm, (name, n)
+            assert abs(float(gr @ proj_vec(gr.numel(), 4000 + gi)) - ref_proj) <= 2e-3 * ref_norm, (name, n)
+            gi += 1
+    for k in DISCS + ["cycle_A", "cycle_n_A", "mean_dif_A", "mean_dif_B", "tv_norm_A"]:
+        assert abs(out["losses"][k] - float(g["end/loss/" + k])) <= 2e-3 * abs(float(g["end/loss/" + k])), k
+    for n in NETS:
+        v = torch.cat([t.detach().double().flatten() for t in orc.sd[n].values()])
+        ref_norm, ref_proj = g["end/w/" + n]
+        assert abs(float(v.norm()) - ref_norm) <= 1e-6 * ref_norm and abs(float(v @ proj_vec(v.numel(), 6000)) - ref_proj) <= 1e-4 * ref_norm, n
+
+
 @pytest.mark.gpu
 def test_fov_normals_and_cos_sim_ops(built_lib):
     from dsr_b200 import ops
