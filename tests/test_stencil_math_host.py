@@ -67,7 +67,7 @@ def test_new_normals_fwd_bwd(hostlib):
     assert np.allclose(gd, ref, rtol=2e-3, atol=1e-3 * np.median(np.abs(ref)))
 
 
-@pytest.mark.parametrize("kind", ["golden", "smooth", "steep"])
+@pytest.mark.parametrize("kind", ["golden", "smooth", "steep", "skewed", "holes", "tiny"])
 def test_new_normals_affine_closed_form(hostlib, kind):
     """fp32 closed form for pin-hole cameras (csrc/stencil_math.cuh aff_*) against the fp64 oracle: forward and backward."""
     g = load_golden("ops.npz")
@@ -81,6 +81,13 @@ def test_new_normals_affine_closed_form(hostlib, kind):
                       for b in range(B)])[:, None].astype(np.float32)
         K = np.repeat(np.array([[[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]]], np.float64), B, 0)
         crop = np.array([[100, 100 + H, 200, 200 + W], [0, H, 0, W]], np.int64)
+        if kind == "skewed":          # both off-diagonal terms of K^-1 non-zero (k1, k3): still affine, every coefficient in play
+            K[:, 0, 1], K[:, 1, 0] = 23.0, -17.0
+        if kind == "holes":           # d = -1 blocks: z = 0, zero-length normals (clamped denominator) and their neighbours
+            d[:, :, 5:12, 7:20] = -1.0
+            d[1, :, :, :3] = -1.0
+        if kind == "tiny":            # every pixel on a border: one-sided differences only
+            d, crop = np.ascontiguousarray(d[:, :, :2, :3]), np.array([[100, 102, 200, 203], [0, 2, 0, 3]], np.int64)
     B, _, H, W = d.shape
     cams = np.ascontiguousarray(_cams(K, crop))
     out = np.empty((B, 3, H, W), np.float32)
