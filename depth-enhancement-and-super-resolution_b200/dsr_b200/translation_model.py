@@ -8,8 +8,8 @@ losses; ``optimize_parameters`` = ``num_iter_gen`` generator iterations with the
 update (:274-291).  Same method surface, ``loss_*`` / visual names and checkpoint names as the reference.
 
 Built for the default flag set (translation_model.py:14-43): ``use_cycle_B``, ``disc_for_depth``, ``disc_for_normals``,
-``l_identity > 0`` with ``no_idt_A``, depth-range losses, ``inp_B='img_depth'``; ``use_cycle_A``, ``l_mean_*``, ``l_tv_A`` and
-``inp_B='depth'`` raise ``NotImplementedError``.  Deliberate difference: the reference runs ``netG_A`` on ``(fake_depth_A,
+``l_identity > 0`` with ``no_idt_A``, depth-range losses, ``inp_B='img_depth'``, optionally ``l_tv_A``; ``use_cycle_A``,
+``l_mean_*`` and ``inp_B='depth'`` raise ``NotImplementedError``.  Deliberate difference: the reference runs ``netG_A`` on ``(fake_depth_A,
 real_img_B)`` twice per forward and throws the first result away (:177-178); here it runs once.
 """
 import torch
@@ -48,7 +48,7 @@ class TranslationModel(GraphStepMixin, BaseModel):
 
     def __init__(self, opt):                                        # translation_model.py:45-127
         BaseModel.__init__(self, opt)
-        if opt.use_cycle_A or opt.l_mean_A > 0 or opt.l_mean_B > 0 or opt.l_tv_A > 0 or opt.inp_B != "img_depth" or \
+        if opt.use_cycle_A or opt.l_mean_A > 0 or opt.l_mean_B > 0 or opt.inp_B != "img_depth" or \
                 not (opt.use_cycle_B and opt.disc_for_depth and opt.disc_for_normals and opt.l_identity > 0 and opt.no_idt_A):
             raise NotImplementedError("dsr_b200.TranslationModel is built for the default loss flags of translation_model.py:14-43 "
                                       "(cycle B, depth + normal discriminators, identity B, depth-range losses, inp_B='img_depth')")
@@ -59,6 +59,8 @@ class TranslationModel(GraphStepMixin, BaseModel):
                 self.loss_names.append("depth_range_A")
             if opt.l_depth_B_begin > 0:
                 self.loss_names.append("depth_range_B")
+            if opt.l_tv_A > 0:
+                self.loss_names.append("tv_norm_A")                  # translation_model.py:67-68
         self.loss_names_test = ["depth_dif_A", "depth_dif_B"]
         self.visual_names = ["real_img_A", "real_depth_A", "real_img_B", "real_depth_B", "fake_depth_B", "fake_depth_A", "name_A",
                              "name_B", "rec_depth_B"]
@@ -184,6 +186,10 @@ class TranslationModel(GraphStepMixin, BaseModel):
         if self.l_depth_B > 0:
             self.loss_depth_range_B = self._masked_l1(self.fake_depth_A, self.real_depth_B, self.valid_B) * self.l_depth_B
             loss_B = loss_B + self.loss_depth_range_B
+        if opt.l_tv_A > 0:                                           # :247-249, TV_norm(surf_normal=True) translation_network.py:302-311:
+            n2 = self.fake_norm_B[:, :2]                             # squared forward differences of the first two components / numel
+            self.loss_tv_norm_A = ops.tv_loss(n2) * (opt.l_tv_A / n2.numel())
+            loss_A = loss_A + self.loss_tv_norm_A
         self.loss_G = loss_A + loss_B
         self.loss_G.backward()
         with torch.no_grad():                                       # :266-270 (metres)

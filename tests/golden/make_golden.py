@@ -415,7 +415,7 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation", "translation_flags"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation", "translation_tv", "translation_flags"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -433,6 +433,9 @@ if __name__ == "__main__":
         golden_gan_blocks()
     if "translation" in which:
         golden_translation_step()
+    if "translation_tv" in which:
+        # the one optional term the CUDA model wires so far (translation_model.py:247-249)
+        golden_translation_step(tag="translation_tv_b1_64", extra_flags=["--l_tv_A", "2.0"], extra_losses=("tv_norm_A",))
     if "translation_flags" in which:
         # the optional loss terms (translation_model.py:222-249): cycle A (masked L1 + masked cosine), mean differences, TV of normals
         golden_translation_step(tag="translation_flags_b1_64",

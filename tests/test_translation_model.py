@@ -23,10 +23,10 @@ def translation_batch(B, H, W, seed=4):          # == tests/golden/make_golden.p
                 B_img=torch.rand(B, 3, H, W, generator=g) * 2 - 1, B_depth=B_d)
 
 
-def _model(gpu_ids=()):
+def _model(gpu_ids=(), **flags):
     from dsr_b200 import options, translation_model
     opt = options.translation_flags(gpu_ids=[], batch_size=1, crop_size_h=64, crop_size_w=64, num_iter_gen=2, name="t",
-                                    checkpoints_dir="/tmp/dsr_ck")
+                                    checkpoints_dir="/tmp/dsr_ck", **flags)
     torch.manual_seed(0)
     host = translation_model.TranslationModel(opt)
     sds = {n: {k: v.detach().clone() for k, v in getattr(host, "net" + n).state_dict().items()} for n in NETS}
@@ -172,3 +172,56 @@ def test_translation_step_matches_reference_golden_and_oracle(built_lib):
         assert abs(float(v.norm()) - ref_norm) <= 1e-5 * ref_norm, n
     losses = model2.get_current_losses()
     assert all(np.isfinite(v) for v in losses.values()) and set(model2.loss_names) == set(losses)
+
+
+def test_translation_oracle_tv_term_matches_reference():
+    g = load_golden("translation_tv_b1_64.npz")
+    host, sds = _model(l_tv_A=2.0)
+    assert "tv_norm_A" in host.loss_names
+    orc = ref_translation.OracleTranslationStep(sds, num_iter_gen=2, l_tv_A=2.0)
+    out = orc.step(translation_batch(1, 64, 64))
+    for k in ("tv_norm_A", "G", "G_A", "cycle_B"):
+        assert abs(out["first"]["losses"][k] - float(g["s0/loss/" + k])) <= 2e-5 * abs(float(g["s0/loss/" + k])), k
+    assert abs(out["losses"]["tv_norm_A"] - float(g["end/loss/tv_norm_A"])) <= 2e-3 * abs(float(g["end/loss/tv_norm_A"]))
+    for n in NETS:
+        v = torch.cat([t.detach().double().flatten() for t in orc.sd[n].values()])
+        ref_norm, ref_proj = g["end/w/" + n]
+        assert abs(float(v.norm()) - ref_norm) <= 1e-6 * ref_norm, n
+
+
+@pytest.mark.gpu
+def test_translation_step_with_tv_norm_term(built_lib):
+    """--l_tv_A 2.0 (translation_model.py:247-249): the CUDA model against the live-reference golden and the oracle - first
+    generator iteration (losses, gradients), then the whole call (end losses, weights after both Adam updates)."""
+    g = load_golden("translation_tv_b1_64.npz")
+    model, sds = _model(gpu_ids=[0], l_tv_A=2.0)
+    batch = translation_batch(1, 64, 64)
+    ref = ref_translation.OracleTranslationStep(sds, num_iter_gen=2, l_tv_A=2.0).step(batch)
+    model.set_input(batch)
+    model.set_requires_grad(model.disc, False)
+    model.forward()
+    model.optimizer_G.zero_grad()
+    model.backward_G()
+    for k in ("tv_norm_A", "G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+        v, want = float(getattr(model, "loss_" + k)), float(g["s0/loss/" + k])
+        assert abs(v - want) <= 1e-3 * abs(want), (k, v, want)
+    assert abs(float(model.loss_G) - float(g["s0/loss/G"])) <= 1e-3 * float(g["s0/loss/G"])
+    fa, fb = [], []
+    for n, prm in model._unwrap(model.netG_A).named_parameters():          # the TV term reaches G_A only
+        gr = ref["first"]["grads"].get(("G_A", n))
+        if gr is None or float(gr.norm()) == 0.0:
+            continue
+        assert cosine(prm.grad.detach().cpu(), gr) >= 0.999, n
+        fa.append(prm.grad.detach().cpu().flatten()); fb.append(gr.flatten())
+    assert cosine(torch.cat(fa), torch.cat(fb)) >= 0.999
+    model.set_requires_grad(model.disc, True)
+    model2, _ = _model(gpu_ids=[0], l_tv_A=2.0)
+    model2.set_input(batch)
+    model2.optimize_parameters(0)
+    v, want = float(model2.loss_tv_norm_A), float(g["end/loss/tv_norm_A"])
+    assert abs(v - want) <= 1e-2 * abs(want)
+    for n in ("G_A", "G_B"):
+        net = model2._unwrap(getattr(model2, "net" + n))
+        w = torch.cat([t.detach().double().flatten().cpu() for t in net.state_dict().values()])
+        assert abs(float(w.norm()) - g["end/w/" + n][0]) <= 1e-5 * g["end/w/" + n][0], n
+    assert set(model2.loss_names) == set(model2.get_current_losses())
