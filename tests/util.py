@@ -82,3 +82,66 @@ def grad_is_informative(net, name):
     arithmetic (the reference produces ~1e-9..1e-4 rounding noise there): only the
     weights and the four biases with no norm behind them carry signal."""
     return name.endswith("weight") or (net, name) in INFORMATIVE_BIASES
+
+
+def _loss_value(model, losses, name):
+    if name == "G":
+        return float(model.loss_G)
+    if name.startswith("mean_of_abs"):
+        return float(getattr(model, "loss_" + name))
+    return losses[name]
+
+
+def compare_step_with_oracle(model, ref, orc, pred_keys=("pred_syn_depth", "pred_real_depth"), tag=""):
+    """The BASELINE.json gates of ONE step of `model` (already run) against the oracle's result `ref` on the same inputs:
+    input-derived masks bit-exact, pred rel-L2 <= 1e-2, every loss term within 1e-3 relative, gradient cosine >= 0.999 per
+    informative tensor and flattened.  Returns the measured margins (worst values) so the caller can log them."""
+    rep = dict(tag=tag)
+
+    def want(k):       # the SR step overwrites some real_* tensors with their LR versions (main_sr_model.py:394-398)
+        v = ref.get("visuals", {}).get(k)
+        return (v if v is not None else ref["tensors"][k]).detach()
+
+    for k in ("syn_mask", "real_mask", "real_hole_mask", "gt_mask_real", "gt_mask_syn"):
+        a = getattr(model, k).detach().cpu().numpy()
+        b = want(k).cpu().numpy()
+        assert a.shape == b.shape and np.array_equal(a.astype(np.int64), b.astype(np.int64)), (tag, k)
+    rep["pred_rel_l2"] = {}
+    for k in ("syn2real_depth", "syn_depth_by_image", "real_depth_by_image") + tuple(pred_keys):
+        r = rel_l2(getattr(model, k).detach().cpu(), want(k))
+        rep["pred_rel_l2"][k] = r
+        assert r <= 1e-2, (tag, k, r)
+    losses = model.get_current_losses()
+    worst_loss = 0.0
+    for k, want in ref["losses"].items():
+        v = _loss_value(model, losses, k)
+        err = abs(v - want) / max(abs(want), 1e-3)
+        worst_loss = max(worst_loss, err)
+        assert err <= 1e-3, (tag, k, v, want)
+    rep["worst_loss_rel"] = worst_loss
+    flat_a, flat_b, worst, worst_name = [], [], 1.0, None
+    for net in ("Depth_f", "Task"):
+        params = dict(model._unwrap(getattr(model, "net" + net)).named_parameters())
+        for n in orc.sd[net]:
+            if not grad_is_informative(net, n):
+                continue
+            mine, gr = params[n].grad.detach().cpu(), ref["grads"][(net, n)]
+            c = cosine(mine, gr)
+            if c < worst:
+                worst, worst_name = c, f"{net}.{n}"
+            flat_a.append(mine.flatten()); flat_b.append(gr.flatten())
+    rep["worst_tensor_cosine"], rep["worst_tensor"] = worst, worst_name
+    rep["flat_cosine"] = cosine(torch.cat(flat_a), torch.cat(flat_b))
+    return rep
+
+
+def log_margins(rep, name="parity_margins.jsonl"):
+    """append the measured gate margins to gpurun_out/ (scratch; merged back from the GPU box) - best effort"""
+    import json
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", name), "a") as f:
+            f.write(json.dumps(rep) + "\n")
+    except OSError:
+        pass
