@@ -117,6 +117,10 @@ class BaseModel(ABC):
             torch.save(sd, save_path)
 
     def load_networks(self, epoch, strict=False):                   # base_model.py:182-237
+        if hasattr(self, "reset_graph"):
+            self.reset_graph()      # a captured graph reads packed copies of the OLD weights through raw pointers: it goes
+        from . import ops
+        ops.WEIGHT_EPOCH += 1
         for name, net in self._nets():
             load_filename = "%s_net_%s.pth" % (epoch, name)
             load_path = os.path.join(self.save_dir, load_filename)
@@ -173,7 +177,9 @@ class GraphStepMixin:
         self._graph, self._gstream, self._eager_steps, self.graph_launches = None, None, 0, 0
 
     def reset_graph(self):
-        self._graph, self._eager_steps = None, 0
+        if getattr(self, "_graph", None) is not None:
+            self._graph.reset()
+        self._graph, self._eager_steps, self._graph_keep = None, 0, None
 
     def _graph_optimize(self):
         from . import _lib, ops
@@ -197,9 +203,11 @@ class GraphStepMixin:
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 l0 = _lib.LAUNCHES
-                with torch.cuda.graph(graph, stream=gs):
-                    self._step_body()
+                with ops.capturing():
+                    with torch.cuda.graph(graph, stream=gs):
+                        self._step_body()
                 self._graph, self.graph_launches = graph, _lib.LAUNCHES - l0
+                self._graph_keep = ops.packed_weight_refs(self)     # the graph reads these buffers through raw pointers
             cur.wait_stream(gs)
         for o in self.optimizers:
             if hasattr(o, "sync_hyper"):

@@ -17,6 +17,7 @@ What changed is how the step runs on the device (all citations into /root/refere
   parallel all-reduce (``parallel.GradBuckets``) works on contiguous slices of it.
 """
 import itertools
+import weakref
 from types import SimpleNamespace
 
 import numpy as np
@@ -99,6 +100,7 @@ class ParamArena:
         self.exp_avg = torch.zeros(off, device=device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(off, device=device, dtype=torch.float32)
         self.index = {}
+        self._registered = []
         for p, o in zip(ordered, self.offsets):
             n = p.numel()
             view = self.flat[o:o + n].view(p.shape)
@@ -108,13 +110,19 @@ class ParamArena:
             p.grad = gview
             self.index[p.data_ptr()] = (o, n)
             ops.DIRECT_GRADS[p.data_ptr()] = gview
+            self._registered.append((p.data_ptr(), gview))
 
     def zero_grad(self):
         self.grad.zero_()
 
     def release(self):
-        for p in self.params:
-            ops.DIRECT_GRADS.pop(p.data_ptr(), None)
+        """unregister the gradient views (called by a finalizer when the owning model is dropped): a dead model's 177 MB
+        gradient arena must not stay alive through ops.DIRECT_GRADS, and a later parameter that lands on an old address must
+        not inherit a stale gradient target"""
+        for ptr, gview in self._registered:
+            if ops.DIRECT_GRADS.get(ptr) is gview:
+                del ops.DIRECT_GRADS[ptr]
+        self._registered = []
 
 
 class ArenaAdam(torch.optim.Optimizer):
@@ -226,6 +234,10 @@ class MainModel(BaseModel):
         self.loss_L1_real = 0
         self.arena = None
         self.grad_sync = None            # set by parallel.GradBuckets for multi-GPU runs
+        self.tv_scale = 1.0              # data parallel: the TV terms are batch SUMS (main_model.py:15-19), every other term a
+                                         # batch mean - a rank weighs its TV terms by the world size so that the rank-averaged
+                                         # gradient equals the gradient of the reference's loss on the concatenated batch
+        self.rect_override = None        # (rects_real, counts_real, rects_syn, counts_syn): explicit tables instead of np.random
         # CUDA-graph replay of the whole training step (static input / rectangle buffers, device-side Adam state)
         self.use_graph = bool(getattr(opt, "cuda_graph", False))
         self.graph_warmup = 2            # eager steps before the capture (fills caches, raises smem limits)
@@ -245,6 +257,7 @@ class MainModel(BaseModel):
 
     def _build_arena(self):
         self.arena = ParamArena([self._unwrap(self.netDepth_f), self._unwrap(self.netTask)], self.device)
+        weakref.finalize(self, ParamArena.release, self.arena)
         self.optimizer_G = ArenaAdam(self.arena, self.opt.lr)
 
     # ------------------------------------------------------------------------------------------
@@ -286,8 +299,11 @@ class MainModel(BaseModel):
     def _stage_rects(self, B, H, W, stage):
         """host RNG in the reference's order - real loop first, then syn (main_model.py:257-298) - into persistent
         pinned tables, then one async H2D copy each"""
-        rr, rc = draw_rects(B, H, W, stage, **self.RECT_REAL)
-        sr, sc = draw_rects(B, H, W, stage, **self.RECT_SYN)
+        if self.rect_override is not None:
+            rr, rc, sr, sc = (np.ascontiguousarray(a, dtype=np.int32) for a in self.rect_override)
+        else:
+            rr, rc = draw_rects(B, H, W, stage, **self.RECT_REAL)
+            sr, sc = draw_rects(B, H, W, stage, **self.RECT_SYN)
         cuda = self.device.type == "cuda"
         if self._rect is None or self._rect["B"] != B:
             mk = lambda shape: torch.zeros(shape, dtype=torch.int32).pin_memory() if cuda else torch.zeros(shape, dtype=torch.int32)
@@ -359,8 +375,9 @@ class MainModel(BaseModel):
         n_syn = ops.normals_old(self.syn_depth, 100.0)
         n_syn_pred = ops.normals_old(ps, 100.0)
         n_real_pred = ops.normals_old(pr, 100.0)
-        self.loss_tv_syn_norm_old = tv_loss(n_syn_pred) * (10 ** -7)
-        self.loss_tv_real_norm_old = tv_loss(n_real_pred) * (10 ** -7)
+        tvw = (10 ** -7) * self.tv_scale
+        self.loss_tv_syn_norm_old = tv_loss(n_syn_pred) * tvw
+        self.loss_tv_real_norm_old = tv_loss(n_real_pred) * tvw
         self.loss_syn_norms_old = ops.masked_l1_l2(n_syn, n_syn_pred, ms)[1]
         a_s = self._a_s                                             # mask_syn_add_holes (:354-357)
         # camera-space normals (:360-372)
@@ -369,8 +386,8 @@ class MainModel(BaseModel):
         self.norm_syn_pred = ops.normals_new(ps, self.cam_A)
         self.norm_real = ops.normals_new(self.real_depth, self.cam_B)
         self.norm_real_pred = ops.normals_new(pr, self.cam_B)
-        self.loss_tv_syn_norm = tv_loss(self.norm_syn_pred) * (10 ** -7)
-        self.loss_tv_real_norm = tv_loss(self.norm_real_pred) * (10 ** -7)
+        self.loss_tv_syn_norm = tv_loss(self.norm_syn_pred) * tvw
+        self.loss_tv_real_norm = tv_loss(self.norm_real_pred) * tvw
         self.loss_syn_norms = ops.masked_l1_l2(self.norm_syn, self.norm_syn_pred, ms)[0]
         self.loss_syn_norms_holes = ops.masked_l1_l2(self.norm_syn, self.norm_syn_pred, ms, a_s)[0]
         # depth terms (:383-390)
@@ -419,7 +436,14 @@ class MainModel(BaseModel):
         self.optimizer_G.step()
 
     def reset_graph(self):
-        self._graph, self._eager_steps = None, 0
+        """drop the captured training / inference graphs (a new batch shape, reloaded weights, orderly shutdown)"""
+        if self._graph is not None:
+            self._graph.reset()
+        self._graph, self._eager_steps, self._graph_keep = None, 0, None
+        st = getattr(self, "_tgraph", None)
+        if st is not None and st.get("graph") is not None:
+            st["graph"].reset()
+        self._tgraph = None
 
     def optimize_parameters(self, iters=0, fr=1):                   # main_model.py:422-429
         """One training step.  With ``use_graph`` the first ``graph_warmup`` calls run eagerly, the next one captures
@@ -454,9 +478,11 @@ class MainModel(BaseModel):
                 graph = torch.cuda.CUDAGraph()
                 from . import _lib
                 l0 = _lib.LAUNCHES
-                with torch.cuda.graph(graph, stream=gs):
-                    self._step_body()
+                with ops.capturing():
+                    with torch.cuda.graph(graph, stream=gs):
+                        self._step_body()
                 self._graph = graph
+                self._graph_keep = ops.packed_weight_refs(self)   # the graph reads these buffers through raw pointers
                 self.graph_launches = _lib.LAUNCHES - l0     # library calls recorded into the graph (= per replay)
             cur.wait_stream(gs)
         B, _, H, W = self.real_depth.shape
@@ -500,14 +526,18 @@ class MainModel(BaseModel):
                 self._rects_staged = True
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=gs):
-                    ops.zero_pool_reset(self.device)     # the accumulators of the pass are re-zeroed by every replay
-                    self.forward("test")
+                with ops.capturing():                    # trainable weights are re-packed INSIDE the graph (every replay sees
+                    with torch.cuda.graph(graph, stream=gs):   # the current weights, whatever training did in between)
+                        ops.zero_pool_reset(self.device)     # the accumulators of the pass are re-zeroed by every replay
+                        self.forward("test")
                 st["graph"] = graph
                 st["outs"] = {k: v for k, v in vars(self).items() if torch.is_tensor(v)}
+                st["keep"] = ops.packed_weight_refs(self)    # frozen nets: the graph reads these packed copies by raw pointer
             cur.wait_stream(gs)
-            return
-        self._stage_rects(B, H, W, "test")
+            # capture records kernels without running them: fall through and replay, so that THIS call's outputs are
+            # computed as well (the rectangle tables of this call are already staged)
+        else:
+            self._stage_rects(B, H, W, "test")
         self._rects_staged = False
         st["graph"].replay()
         for k, v in st["outs"].items():

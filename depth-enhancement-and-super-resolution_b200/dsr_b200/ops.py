@@ -94,6 +94,7 @@ class _ZeroPool:
         if u + n8 > self.CAP:
             return torch.zeros(n, device=device, dtype=torch.float64)
         self.used[key] = u + n8
+        self.high[key] = max(self.high.get(key, 0), u + n8)
         return self.buf[key][u:u + n]
 
     def reset(self, device):
@@ -101,8 +102,11 @@ class _ZeroPool:
         if key not in self.buf:
             self.buf[key] = torch.zeros(self.CAP, device=device, dtype=torch.float64)
             self.used[key] = 0
+            self.high[key] = 0
             return
-        u = self.used[key]
+        # everything the pool has EVER handed out on this device is cleared: a reset captured into a CUDA graph has a fixed
+        # length, and the pass that preceded the capture may have used less of the pool than the captured step does
+        u = self.high.get(key, 0)
         if u:
             self.buf[key][:u].zero_()
         self.used[key] = 0
@@ -231,6 +235,57 @@ def _passes(dtype):
     return CONFIG["passes"]
 
 
+_CAPTURE = {"id": 0, "active": False}
+
+
+class capturing:
+    """``with ops.capturing():`` around a CUDA-graph capture.  Packed 16-bit copies of TRAINABLE weights made before the
+    capture are not trusted inside it: the pack kernels are recorded into the graph, so every replay re-packs from the
+    current fp32 weights (a graph that captured a cache hit would read stale - or freed - buffers after the next
+    optimizer step).  Frozen weights keep their cached copies; the graph owner holds references to them
+    (``packed_weight_refs``) and drops the graph when they are reloaded."""
+
+    def __enter__(self):
+        _CAPTURE["id"] += 1
+        _CAPTURE["active"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _CAPTURE["active"] = False
+        return False
+
+
+def _pack_cache(weight):
+    """-> the per-parameter cache of packed copies, emptied when the parameter changed (in-place update: ``_version``; arena
+    optimizer: WEIGHT_EPOCH; a capture in progress: copies of trainable weights made outside it)"""
+    trainable = weight.data_ptr() in DIRECT_GRADS
+    epoch = WEIGHT_EPOCH if trainable else -1
+    cap = _CAPTURE["id"] if (trainable and _CAPTURE["active"]) else -1
+    stamp = (weight._version, epoch, weight.data_ptr(), cap)
+    cache = getattr(weight, "_dsr_pack", None)
+    if cache is None or cache.get("stamp") != stamp:
+        cache = {"stamp": stamp}
+        try:
+            weight._dsr_pack = cache
+        except AttributeError:
+            pass
+    return cache
+
+
+def packed_weight_refs(model):
+    """strong references to every packed weight copy currently cached on the model's parameters"""
+    keep = []
+    for name in getattr(model, "model_names", []):
+        net = getattr(model, "net" + name, None)
+        if net is None:
+            continue
+        for p in net.parameters():
+            c = getattr(p, "_dsr_pack", None)
+            if c:
+                keep.append([v for k, v in c.items() if k != "stamp"])
+    return keep
+
+
 W_SCALE = 64.0          # power-of-two weight scale of the f16 path: keeps the low half of N(0, 0.02)-sized weights normal
 
 
@@ -276,17 +331,9 @@ def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None):
     """bf16 hi/lo packed copy of a parameter, cached ON the parameter object until it changes
     (in-place updates bump ``_version``; the arena optimizer bumps WEIGHT_EPOCH)."""
     npass = _passes(dtype)
-    epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
-    stamp = (weight._version, epoch, weight.data_ptr())
     f16 = (dtype or CONFIG["dtype"]) == "f16"
     key = (plan["variant"], plan["Ca"], phase, pad, npass >= 3, f16)
-    cache = getattr(weight, "_dsr_pack", None)
-    if cache is None or cache.get("stamp") != stamp:
-        cache = {"stamp": stamp}
-        try:
-            weight._dsr_pack = cache
-        except AttributeError:
-            pass
+    cache = _pack_cache(weight)
     hit = cache.get(key)
     if hit is not None:
         return hit
@@ -339,17 +386,9 @@ def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
     """the four output-phase weight matrices of a stride-2 transposed conv, stacked along rows ([4*Co][T*Ca]) so one GEMM
     launch serves all phases; cached on the parameter like _tc_weights"""
     npass = _passes(dtype)
-    epoch = WEIGHT_EPOCH if weight.data_ptr() in DIRECT_GRADS else -1
-    stamp = (weight._version, epoch, weight.data_ptr())
     f16 = (dtype or CONFIG["dtype"]) == "f16"
     key = ("phases", plan["Ca"], pad, npass >= 3, f16)
-    cache = getattr(weight, "_dsr_pack", None)
-    if cache is None or cache.get("stamp") != stamp:
-        cache = {"stamp": stamp}
-        try:
-            weight._dsr_pack = cache
-        except AttributeError:
-            pass
+    cache = _pack_cache(weight)
     hit = cache.get(key)
     if hit is not None:
         return hit

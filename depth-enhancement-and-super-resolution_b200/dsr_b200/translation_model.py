@@ -100,6 +100,24 @@ class TranslationModel(GraphStepMixin, BaseModel):
         self._in = None
         self.loss_idt_A = 0
         self._graph_init(opt)        # optional CUDA-graph replay of the whole optimize_parameters call (opt.cuda_graph)
+        # the scheduled loss weights (update_loss_weight, :300-305) live in a small device tensor: a captured step multiplies
+        # by the tensor, so a replay sees the current schedule instead of the capture-time floats
+        self._lw_dev = None
+        if self.isTrain and self.gpu_ids:
+            self._lw_dev = torch.zeros(4, device=self.device, dtype=torch.float32)
+            self._lw_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._sync_loss_weights()
+
+    _LW = ("l_depth_A", "l_depth_B", "l_cycle_A", "l_cycle_B")
+
+    def _sync_loss_weights(self):
+        if self._lw_dev is not None:
+            self._lw_host.copy_(torch.tensor([getattr(self, k) for k in self._LW], dtype=torch.float32))
+            self._lw_dev.copy_(self._lw_host, non_blocking=True)
+
+    def _w(self, name):
+        """scheduled loss weight as a multiplier: a device scalar on the GPU path (graph-replay safe), the float otherwise"""
+        return getattr(self, name) if self._lw_dev is None else self._lw_dev[self._LW.index(name)]
 
     def set_input(self, input):                                     # translation_model.py:129-137
         self.name_A, self.name_B = input["A_name"], input["B_name"]
@@ -174,17 +192,17 @@ class TranslationModel(GraphStepMixin, BaseModel):
         self.loss_G_B = 0.5 * self._lsgan(self.netD_B_depth(self.fake_depth_A), 1.0) + \
             0.5 * self._lsgan(self.netD_B_normal(self.fake_norm_A), 1.0)
         loss_A, loss_B = self.loss_G_A, self.loss_G_B
-        self.loss_cycle_B = self._l1(self.rec_depth_B, self.real_depth_B) * self.l_cycle_B
-        self.loss_cycle_n_B = ops.cos_sim_loss(self.rec_norm_B, self.real_norm_B) * opt.l_normal * self.l_cycle_B
+        self.loss_cycle_B = self._l1(self.rec_depth_B, self.real_depth_B) * self._w("l_cycle_B")
+        self.loss_cycle_n_B = ops.cos_sim_loss(self.rec_norm_B, self.real_norm_B) * opt.l_normal * self._w("l_cycle_B")
         loss_B = loss_B + self.loss_cycle_B + self.loss_cycle_n_B
         self.loss_idt_A = 0
         self.loss_idt_B = self._l1(self.idt_B, self.real_depth_A) * opt.l_identity
         loss_B = loss_B + self.loss_idt_B
         if self.l_depth_A > 0:
-            self.loss_depth_range_A = self._masked_l1(self.fake_depth_B, self.real_depth_A, self.valid_A) * self.l_depth_A
+            self.loss_depth_range_A = self._masked_l1(self.fake_depth_B, self.real_depth_A, self.valid_A) * self._w("l_depth_A")
             loss_A = loss_A + self.loss_depth_range_A
         if self.l_depth_B > 0:
-            self.loss_depth_range_B = self._masked_l1(self.fake_depth_A, self.real_depth_B, self.valid_B) * self.l_depth_B
+            self.loss_depth_range_B = self._masked_l1(self.fake_depth_A, self.real_depth_B, self.valid_B) * self._w("l_depth_B")
             loss_B = loss_B + self.loss_depth_range_B
         if opt.l_tv_A > 0:                                           # :247-249, TV_norm(surf_normal=True) translation_network.py:302-311:
             n2 = self.fake_norm_B[:, :2]                             # squared forward differences of the first two components / numel
@@ -240,10 +258,14 @@ class TranslationModel(GraphStepMixin, BaseModel):
 
     def update_loss_weight(self, global_iter):                      # :300-305
         if global_iter > self.opt.l_max_iter:
+            gates = (self.l_depth_A > 0, self.l_depth_B > 0)
             self.l_depth_A -= self.l_depth_A_step
             self.l_depth_B -= self.l_depth_B_step
             self.l_cycle_A += self.l_cycle_A_step
             self.l_cycle_B += self.l_cycle_B_step
+            self._sync_loss_weights()       # the captured step reads the weights from the device
+            if gates != (self.l_depth_A > 0, self.l_depth_B > 0):
+                self.reset_graph()          # a term entered / left the loss: the captured control flow is stale
 
     def calc_test_loss(self):                                       # :307-309
         md = self.opt.max_distance
