@@ -53,6 +53,13 @@ def step_flops(wl):
     return wl["B"] * FLOP_PER_PAIR_256 * px
 
 
+def run_config(wl, n_gpus):
+    """the `config` object of the JSON line - identical for both arms (`--impl ours` / `--impl reference`)"""
+    return dict(workload=wl["name"], crop=[wl["H"], wl["W"]], batch_per_gpu=wl["B"], parallelism=f"dp{n_gpus}",
+                l2_policy="inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                algorithmic_tflop_per_step=step_flops(wl) / 1e12)
+
+
 def make_model(wl, gpu_ids, graph, name="bench"):
     from dsr_b200 import I2D_model, main_model, main_sr_model, options
     if wl.get("tr"):
@@ -78,7 +85,7 @@ def make_model(wl, gpu_ids, graph, name="bench"):
 
 
 def make_batch(wl, seed):
-    from oracle.ref_step import synthetic_batch, synthetic_sr_batch      # synthetic input generator only (shared with the tests)
+    from dsr_b200.synthetic import synthetic_batch, synthetic_sr_batch
     if wl.get("tr"):
         b = synthetic_batch(wl["B"], wl["H"], wl["W"], seed=seed, depth_kind="smooth")
         return dict(A_name=b["A_paths"], B_name=b["B_paths"], A_img=b["A_i"], A_depth=b["A_d"], B_img=b["B_i"], B_depth=b["B_d"])
@@ -152,15 +159,25 @@ def cpu_gan_baseline(sds, batch, steps, warmup):
         ts.append(time.perf_counter() - t0)
     ts = ts[warmup:]
     B = batch["A_d"].shape[0]
-    return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count())
+    return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count(),
+                kind="port", what="oracle/ref_nets.gan_block_step, torch CPU fp32")
 
 
 def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=False, tr=False):
-    """The oracle port of the reference's CPU path (--gpu_ids -1) on this box's host cores."""
+    """The reference's CPU path (--gpu_ids -1) on this box's host cores, all of them: the UNMODIFIED reference staged in
+    oracle/_ref (oracle/build_ref.py; kind "reference") for the main / SR steps when present, the oracle port otherwise."""
+    import contextlib
     import numpy as np
     import torch
-    from oracle import ref_step
+    from oracle import ref_live, ref_step
+    # torch.distributed.run exports OMP_NUM_THREADS=1: give the CPU arm every host core whatever launched us
+    torch.set_num_threads(os.cpu_count() or 1)
     wl = dict(B=B, H=H, W=W, sr=sr, i2d=i2d, gan=gan, tr=tr)
+    if ref_live.available() and not (i2d or gan or tr):
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints its option table and network summary
+            s_per_step, _ = ref_live.time_steps(B, H, W, make_batch(wl, 1), steps, warmup, sr=sr)
+        return dict(s_per_step=s_per_step, value=B / s_per_step, cores=torch.get_num_threads(), host_cpus=os.cpu_count(),
+                    kind="reference", what="unmodified reference (oracle/_ref, models/main%s_model.py) on --gpu_ids -1" % ("_sr" if sr else ""))
     if sds is None:
         torch.manual_seed(0)
         host = make_model(wl, [], False, name="cpu")
@@ -175,7 +192,8 @@ def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=
             orc.step(batch)
             ts.append(time.perf_counter() - t0)
         ts = ts[warmup:]
-        return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count())
+        return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(), host_cpus=os.cpu_count(),
+                    kind="port", what="oracle/ref_translation.py, torch CPU fp32")
     if gan:
         return cpu_gan_baseline(sds, make_batch(wl, 1), steps, warmup)
     if i2d:
@@ -191,7 +209,7 @@ def cpu_baseline(B, H, W, steps=2, warmup=1, sds=None, sr=False, i2d=False, gan=
         ts.append(time.perf_counter() - t0)
     ts = ts[warmup:]
     return dict(s_per_step=sum(ts) / len(ts), value=B * len(ts) / sum(ts), cores=torch.get_num_threads(),
-                host_cpus=os.cpu_count())
+                host_cpus=os.cpu_count(), kind="port", what="oracle/ref_step.py, torch CPU fp32")
 
 
 def torch_gpu_bar(wl, steps=5, warmup=3, device="cuda:0"):
@@ -246,19 +264,20 @@ def torch_gpu_bar(wl, steps=5, warmup=3, device="cuda:0"):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the workload's own batch, all host threads
+    (the unmodified reference from oracle/_ref when staged, else the oracle port)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    Bs = min(wl["B"], 2)                      # bounded sample: B=2 of the workload's crops per step
-    r = cpu_baseline(Bs, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
+    B = wl["B"]
+    r = cpu_baseline(B, wl["H"], wl["W"], steps=args.steps, warmup=args.warmup, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
     line = dict(impl="reference", metric="RGB-D train pair-samples/sec (main net)", value=r["value"], unit="pair-samples/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * r["s_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=wl["name"], crop=[wl["H"], wl["W"]], per_step_batch=Bs),
-                cpu_baseline=dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
-                                  sample=f"{args.steps} steps of batch {Bs} at {wl['H']}x{wl['W']} (oracle/ref_step.py, torch CPU fp32)"),
+                config=run_config(wl, args.gpus),
+                cpu_baseline=dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind=r["kind"],
+                                  sample=f"{args.steps} steps of batch {B} at {wl['H']}x{wl['W']} after {args.warmup} warm-up ({r['what']}, {r['host_cpus']} host CPUs)"),
                 e2e=dict(value=r["value"], unit="pair-samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -323,10 +342,25 @@ def run_ours(args):
     torch.manual_seed(0)
     model = make_model(wl, [local], args.graph)
     model._train()
-    sync = None
+    sync, dp_check = None, None
     if world > 1:
         parallel.broadcast_weights(model)
         sync = parallel.GradBuckets(model)
+        if not any(wl.get(k) for k in ("i2d", "gan", "tr", "sr")):
+            # numerical check of the data-parallel step before anything is timed or captured: rank-averaged gradients of one
+            # sharded step == gradients of ONE process on the concatenated batch (every rank generates every shard)
+            from dsr_b200 import main_model
+            Bc = min(B, 2)
+            cb, cr = [], []
+            for r in range(world):
+                full = make_batch(dict(wl, B=Bc), 101 + r)
+                cb.append(full)
+                rng = np.random.RandomState(500 + r)
+                rr, rc = main_model.draw_rects(Bc, H, W, "train", rng=rng)
+                sr_, sc = main_model.draw_rects(Bc, H, W, "train", rng=rng)
+                cr.append((rr, rc, sr_, sc))
+            dp_check = parallel.dp_self_check(model, sync, cb, cr)
+            dp_check["sample"] = f"one step, {Bc} pairs per rank at {H}x{W}; cos / rel_l2 = worst over ranks"
     # a few distinct host batches in pinned memory (per-rank seeds: each rank draws its own shard)
     host_batches = []
     for i in range(2):
@@ -353,11 +387,19 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        pending = None
         for i in range(steps):
             model.set_input(batches[i % len(batches)])
             model.optimize_parameters(i, 1)
-            if read_loss:
-                float(model.loss_G)                   # D2H read of the step's result
+            if read_loss:                             # D2H read of EVERY step's result: the copy of step i is enqueued behind
+                nxt = model.loss_async("loss_G") if hasattr(model, "loss_async") else (lambda m=model: float(m.loss_G))
+                if pending is not None:               # step i, the host reads it (and checks it) while step i+1 runs
+                    v = pending()
+                    if v != v or v in (float("inf"), float("-inf")):
+                        raise FloatingPointError(f"loss_G is not finite at step {i - 1}")
+                pending = nxt
+        if pending is not None:
+            pending()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -468,10 +510,27 @@ def run_ours(args):
         flop_step = step_flops(wl)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            Bc = min(B, 2)
-            r = cpu_baseline(Bc, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
-            cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind="port",
-                       sample=f"2 steps of batch {Bc} at {H}x{W} after 1 warm-up (oracle/ref_step.py, torch CPU fp32, {r['host_cpus']} host CPUs)")
+            r = cpu_baseline(B, H, W, steps=2, warmup=1, sr=bool(wl.get("sr")), i2d=bool(wl.get("i2d")), gan=bool(wl.get("gan")), tr=bool(wl.get("tr")))
+            cpu = dict(value=r["value"], unit="pair-samples/s", cores=r["cores"], kind=r["kind"],
+                       sample=f"2 steps of batch {B} at {H}x{W} after 1 warm-up ({r['what']}, {r['host_cpus']} host CPUs)")
+        hbm = None
+        if args.stencils and world == 1:
+            from dsr_b200 import stencil_bench
+            tab = stencil_bench.run(batch=96, iters=10, peak=pk["hbm_gbs"], device=local)
+            rows = [r for r in tab["rows"] if not r["kernel"].startswith("ssim")]
+            worst = min(rows, key=lambda r: r["frac"])
+            ssim_row = [r for r in tab["rows"] if r["kernel"].startswith("ssim")]
+            hbm = dict(bound="hbm", peak=pk["hbm_gbs"], unit="GB/s", peak_source=pk_src,
+                       worst=dict(kernel=worst["kernel"], achieved=worst["gbs"], frac=worst["frac"]),
+                       median_frac=sorted(r["frac"] for r in rows)[len(rows) // 2],
+                       at_or_above_70pct=sum(r["frac"] >= 0.70 for r in rows), kernels=len(rows),
+                       table={r["kernel"]: [r["gbs"], r["frac"]] for r in rows},
+                       ssim=(dict(achieved=ssim_row[0]["gbs"], frac_of_hbm=ssim_row[0]["frac"],
+                                  note="fp32-pipe bound (five 11x11 separable Gaussian windows, 127 FMA/pixel): its ceiling is ~35% of the HBM rate")
+                             if ssim_row else None),
+                       shape=tab["shape"], note="achieved = algorithmic bytes (SURVEY.md 8d) / mean launch time, CUDA events on the launching "
+                       "stream, 10 back-to-back launches after 3 warm-ups, in this process; 96 planes of 512x640 (126 MB per fp32 plane set, "
+                       "beyond the L2) - the C3 frame size, batched so that nothing is served from cache")
         gpu_bar = None
         if args.torch_gpu_bar and world == 1 and not any(wl.get(k) for k in ("sr", "i2d", "gan", "tr")):
             try:
@@ -489,26 +548,20 @@ def run_ours(args):
                               if ops.CONFIG["big_hw"] and ops.CONFIG["big_bwd_passes"] else "") + "), f32 accumulate"
                            if args.engine == "tc" else "f32"),
                     data="synthetic",
-                    config=dict(workload=wl["name"], crop=[H, W], batch_per_gpu=B, parallelism=f"dp{world}", engine=args.engine,
-                                cuda_graph=bool(model.use_graph),
-                                l2_policy="inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                                algorithmic_tflop_per_step=flop_step / 1e12),
+                    config=run_config(wl, world), engine=args.engine, cuda_graph=bool(model.use_graph),
                     e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="pair-samples/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu,
+                    gpu_launches=launches, clocks=sampler.summary(), roofline=roof, roofline_hbm=hbm, cpu_baseline=cpu, dp_check=dp_check,
                     step_tflops=flop_step / (ms / args.steps * 1e-3) / 1e12, inference_640x480=extras,
                     kernel_times_ms={k: round(d["ms"], 3) for k, d in top})
         if gpu_bar is not None:
             line["torch_eager_gpu"] = gpu_bar
         print(json.dumps(line), flush=True)
     if world > 1:
-        # leave without tearing NCCL down: destroying a communicator whose collectives were captured into a live CUDA
-        # graph blocked for minutes on the B200 box; a barrier + hard exit is deterministic and torchrun sees exit code 0
+        # orderly exit: the captured graph holds the communicator's collectives, so it is released first, then the device
+        # is drained and the process group destroyed (parallel.shutdown)
         sys.stdout.flush()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        os._exit(0)
+        parallel.shutdown([model])
 
 
 def main():
@@ -527,6 +580,7 @@ def main():
     ap.add_argument("--layer-table", default="", help="write every library call of one step (name, ms, shape, GMACs) to this JSON file")
     ap.add_argument("--kernel-table", default="", help="write the in-situ per-kernel device times of 3 steps (torch.profiler / CUPTI, warm caches) to this JSON file")
     ap.add_argument("--inference", type=int, default=1, help="1 = also time the 640x480 inference forward (ms/frame)")
+    ap.add_argument("--stencils", type=int, default=1, help="1 = also measure the HBM roofline table of the stencil / reduction kernels (roofline_hbm)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the training step as a CUDA graph (default), 0 = eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

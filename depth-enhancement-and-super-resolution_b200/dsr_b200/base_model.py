@@ -104,6 +104,24 @@ class BaseModel(ABC):
                 errors_ret[name] = float(getattr(self, "loss_" + name))
         return errors_ret
 
+    def loss_async(self, name="loss_G"):
+        """Enqueue the device->host copy of a loss scalar into pinned memory and return a zero-argument callable that waits
+        for THAT copy and returns the float: a training loop reads step i's loss while step i+1 is already running instead
+        of draining the device every step (``float(model.loss_G)`` does)."""
+        t = getattr(self, name)
+        if not torch.is_tensor(t) or not t.is_cuda:
+            return lambda: float(t)
+        ring = self.__dict__.setdefault("_loss_ring", dict(turn=0, slots=[(torch.zeros(1).pin_memory(), torch.cuda.Event()) for _ in range(4)]))
+        host, ev = ring["slots"][ring["turn"] % 4]
+        ring["turn"] += 1
+        host.copy_(t.detach().reshape(1), non_blocking=True)
+        ev.record()
+
+        def read():
+            ev.synchronize()
+            return float(host[0])
+        return read
+
     @staticmethod
     def _unwrap(net):
         return net.module if hasattr(net, "module") else net

@@ -210,3 +210,55 @@ def test_checkpoint_roundtrip(model_and_oracle, tmp_path):
     for n, p in model.netTask.named_parameters():
         assert torch.equal(p.detach(), before[n])
     assert model.arena is not None and all(p.data_ptr() in model.arena.index for p in model.arena.params)
+
+
+def test_inference_graph_capture_call_returns_computed_outputs(built_lib):
+    """the call that CAPTURES forward('test') must also run it: its outputs equal the eager pass (they used to be
+    uninitialised graph-pool memory until the next call)"""
+    host = build_host_model(1, 128, 128)
+    m = rehome(host, host.opt, [0])
+    m.eval()
+    batches = [ref_step.synthetic_batch(1, 128, 128, seed=s, depth_kind="noise") for s in (21, 22, 23)]
+    with torch.no_grad():
+        for i in range(3):                              # eager, eager, capture (+ replay)
+            m.set_input(batches[i])
+            m.forward_test_graph()
+        assert m._tgraph["graph"] is not None
+        got = {k: getattr(m, k).detach().clone() for k in ("pred_real_depth", "pred_syn_depth", "syn2real_depth", "depth_masked")}
+        m.set_input(batches[2])
+        m.forward("test")
+        for k, v in got.items():
+            assert rel_l2(v.cpu(), getattr(m, k).detach().cpu()) <= 1e-5, k
+
+
+def test_inference_graph_sees_weights_trained_in_between(built_lib):
+    """training steps between two replays of the inference graph: the trainable nets are re-packed INSIDE the graph, so the
+    replay uses the current weights (not the packed copies cached at capture time, which the optimizer step invalidates
+    and the allocator may hand to somebody else)"""
+    host = build_host_model(1, 128, 128)
+    m = rehome(host, host.opt, [0])
+    b = ref_step.synthetic_batch(1, 128, 128, seed=31, depth_kind="smooth")
+    np.random.seed(3)
+    m.eval()
+    with torch.no_grad():
+        for i in range(4):
+            m.set_input(b)
+            m.forward_test_graph()
+    before = m.pred_real_depth.detach().clone()
+    m._train()
+    m.optimizer_G.param_groups[0]["lr"] = 1e-2          # a visible update
+    for it in range(2):
+        m.set_input(b)
+        m.optimize_parameters(it, 1)
+    junk = [torch.full((1 << 20,), 7.0, device="cuda") for _ in range(64)]      # recycle whatever the allocator freed
+    m.eval()
+    with torch.no_grad():
+        m.set_input(b)
+        m.forward_test_graph()
+        replay = m.pred_real_depth.detach().clone()
+        m.set_input(b)
+        m.forward("test")
+        eager = m.pred_real_depth.detach().clone()
+    del junk
+    assert rel_l2(replay.cpu(), eager.cpu()) <= 1e-5
+    assert rel_l2(before.cpu(), eager.cpu()) >= 1e-3    # the weights did move

@@ -99,3 +99,46 @@ def test_ring_planner_is_callable_without_a_gpu(built_lib):
     assert lib.dsr_smooth_ring_suits(6, 3, 256, 256) == 0           # 393 K pixels: the register kernels
     assert lib.dsr_smooth_ring_suits(96, 3, 512, 642) == 0          # rows must be 16-byte multiples
     assert lib.dsr_smooth_ring_suits(64, 3, 1024, 8192) == 0        # one row of all planes must fit a 40 KB group
+
+
+def test_package_synthetic_batches_equal_the_oracle_generator():
+    """bench.py's product leg draws its inputs from dsr_b200.synthetic (it must not import oracle/): same tensors"""
+    from dsr_b200 import synthetic
+    from oracle import ref_step
+    for kind in ("smooth", "noise"):
+        a, b = synthetic.synthetic_batch(2, 32, 48, seed=4, depth_kind=kind), ref_step.synthetic_batch(2, 32, 48, seed=4, depth_kind=kind)
+        assert a.keys() == b.keys()
+        assert all(torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k] for k in a)
+    a, b = synthetic.synthetic_sr_batch(1, 16, 24, seed=2), ref_step.synthetic_sr_batch(1, 16, 24, seed=2)
+    assert all(torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k] for k in a)
+
+
+def test_bench_product_leg_does_not_import_the_oracle():
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    allowed = {"cpu_baseline", "cpu_gan_baseline", "torch_gpu_bar", "run_reference"}        # the CPU / reference legs
+    for fn in tree.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name not in allowed:
+            for node in ast.walk(fn):
+                if isinstance(node, ast.ImportFrom) and (node.module or "").startswith("oracle"):
+                    raise AssertionError(f"bench.py:{fn.name} imports {node.module}")
+    pkg = os.path.join(root, "depth-enhancement-and-super-resolution_b200", "dsr_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py") and f != "selfcheck.py":
+            assert "oracle" not in open(os.path.join(pkg, f)).read().replace("the oracle", ""), f
+
+
+def test_zero_pool_clears_its_high_water_mark():
+    """a reset captured into a CUDA graph has a fixed length: it must cover everything the pool ever handed out"""
+    from dsr_b200 import ops
+    pool = ops._ZeroPool()
+    dev = torch.device("cpu")
+    pool.reset(dev)
+    a = pool.take(100, dev); a += 1
+    b = pool.take(50, dev); b += 1
+    pool.reset(dev)                  # zeroes [:152]
+    c = pool.take(10, dev); c += 1   # a shorter pass ...
+    pool.reset(dev)                  # ... must still clear the whole region handed out before
+    assert pool.high[("cpu", None)] >= 152
+    assert float(pool.buf[("cpu", None)][:200].abs().sum()) == 0.0

@@ -225,3 +225,37 @@ def test_translation_step_with_tv_norm_term(built_lib):
         w = torch.cat([t.detach().double().flatten().cpu() for t in net.state_dict().values()])
         assert abs(float(w.norm()) - g["end/w/" + n][0]) <= 1e-5 * g["end/w/" + n][0], n
     assert set(model2.loss_names) == set(model2.get_current_losses())
+
+
+@pytest.mark.gpu
+def test_graph_replay_follows_the_loss_weight_schedule(built_lib):
+    """update_loss_weight (translation_model.py:300-305) after the step was captured: the replayed graph multiplies by the
+    device-resident weights, so it tracks the schedule like the eager step does"""
+    import numpy as np
+    import torch
+    from dsr_b200 import ops, options, translation_model
+    from oracle import ref_step
+
+    def make(graph):
+        torch.manual_seed(0)
+        opt = options.translation_flags(gpu_ids=[0], batch_size=1, crop_size_h=64, crop_size_w=64, name="t", checkpoints_dir="/tmp/dsr_ck",
+                                        cuda_graph=graph, l_max_iter=0, l_num_iter=4)
+        return translation_model.TranslationModel(opt)
+
+    b = ref_step.synthetic_batch(1, 64, 64, seed=1, depth_kind="smooth")
+    batch = dict(A_name=b["A_paths"], B_name=b["B_paths"], A_img=b["A_i"], A_depth=b["A_d"], B_img=b["B_i"], B_depth=b["B_d"])
+    out = {}
+    for graph in (True, False):
+        m = make(graph)
+        vals = []
+        for it in range(6):
+            m.set_input(batch)
+            m.optimize_parameters(it, 1)
+            vals.append((float(m.loss_depth_range_A), float(m.loss_cycle_B)) if m.l_depth_A > 0 else (0.0, float(m.loss_cycle_B)))
+            m.update_loss_weight(it + 1)                 # l_max_iter = 0: the weights move after every step
+        out[graph] = (vals, m.l_depth_A, m._graph is not None)
+    (vg, lg, captured), (ve, le, _) = out[True], out[False]
+    assert captured and lg == le
+    assert ve[0][0] > 0 and ve[3][0] < ve[0][0]          # the depth-range weight decays 5 -> 0 over l_num_iter = 4 updates
+    for a, e in zip(vg, ve):
+        assert abs(a[0] - e[0]) <= 5e-2 * max(abs(e[0]), 1e-3) and abs(a[1] - e[1]) <= 5e-2 * max(abs(e[1]), 1e-3), (vg, ve)
