@@ -247,13 +247,14 @@ def test_graph_replay_follows_the_loss_weight_schedule(built_lib):
     out = {}
     for graph in (True, False):
         m = make(graph)
-        vals = []
+        vals, captured_mid = [], False
         for it in range(6):
             m.set_input(batch)
             m.optimize_parameters(it, 1)
+            captured_mid = captured_mid or m._graph is not None     # (the graph is dropped again when a term leaves the loss)
             vals.append((float(m.loss_depth_range_A), float(m.loss_cycle_B)) if m.l_depth_A > 0 else (0.0, float(m.loss_cycle_B)))
             m.update_loss_weight(it + 1)                 # l_max_iter = 0: the weights move after every step
-        out[graph] = (vals, m.l_depth_A, m._graph is not None)
+        out[graph] = (vals, m.l_depth_A, captured_mid)
     (vg, lg, captured), (ve, le, _) = out[True], out[False]
     assert captured and lg == le
     assert ve[0][0] > 0 and ve[3][0] < ve[0][0]          # the depth-range weight decays 5 -> 0 over l_num_iter = 4 updates
