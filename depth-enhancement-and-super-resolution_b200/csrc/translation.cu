@@ -91,8 +91,8 @@ __global__ void fov_normals_bwd_kernel(const float* __restrict__ d, const float*
 }
 
 // cosine similarity along the channel dimension (nn.CosineSimilarity(dim=1), eps 1e-8): x.y / (max(|x|, eps) * max(|y|, eps))
-__global__ void cos_sim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int B, int C, long plane,
-                                   double* __restrict__ out) {
+__global__ void cos_sim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mask,
+                                   int B, int C, long plane, double* __restrict__ out) {
     __shared__ double red[32];
     double acc = 0.0;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)B * plane; idx += (long)gridDim.x * blockDim.x) {
@@ -102,17 +102,19 @@ __global__ void cos_sim_fwd_kernel(const float* __restrict__ x, const float* __r
             const float a = x[(b * C + c) * plane + p], v = y[(b * C + c) * plane + p];
             dot += a * v; nx += a * a; ny += v * v;
         }
-        acc += (double)(1.f - dot / (fmaxf(sqrtf(nx), 1e-8f) * fmaxf(sqrtf(ny), 1e-8f)));
+        const float l = 1.f - dot / (fmaxf(sqrtf(nx), 1e-8f) * fmaxf(sqrtf(ny), 1e-8f));
+        acc += (double)(mask ? l * mask[idx] : l);
     }
     acc = block_sum<double>(acc, red);
     if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 // gx = coef * (*gscale) * d sum(1 - cos) / dx
-__global__ void cos_sim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int B, int C, long plane,
-                                   const float* __restrict__ gscale, float coef, float* __restrict__ gx) {
-    const float gs = coef * (gscale ? *gscale : 1.f);
+__global__ void cos_sim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mask,
+                                   int B, int C, long plane, const float* __restrict__ gscale, float coef, float* __restrict__ gx) {
+    const float gs0 = coef * (gscale ? *gscale : 1.f);
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)B * plane; idx += (long)gridDim.x * blockDim.x) {
         const long b = idx / plane, p = idx - b * plane;
+        const float gs = mask ? gs0 * mask[idx] : gs0;
         float dot = 0.f, nx = 0.f, ny = 0.f;
         for (int c = 0; c < C; ++c) {
             const float a = x[(b * C + c) * plane + p], v = y[(b * C + c) * plane + p];
@@ -141,12 +143,70 @@ extern "C" int dsr_fov_normals_bwd(const float* depth, const float* gout, int B,
 }
 extern "C" int dsr_cos_sim_fwd(const float* x, const float* y, int B, int C, long plane, double* out_sum, void* stream) {
     DSR_REQUIRE(x && y && out_sum && B > 0 && C > 0 && plane > 0, "bad arguments");
-    cos_sim_fwd_kernel<<<dsr_grid((long)B * plane, TT), TT, 0, ST(stream)>>>(x, y, B, C, plane, out_sum);
+    cos_sim_fwd_kernel<<<dsr_grid((long)B * plane, TT), TT, 0, ST(stream)>>>(x, y, nullptr, B, C, plane, out_sum);
     return dsr_check_launch("cos_sim_fwd");
 }
 extern "C" int dsr_cos_sim_bwd(const float* x, const float* y, int B, int C, long plane, const float* gscale, float coef, float* gx,
                                void* stream) {
     DSR_REQUIRE(x && y && gx && B > 0 && C > 0 && plane > 0, "bad arguments");
-    cos_sim_bwd_kernel<<<dsr_grid((long)B * plane, TT), TT, 0, ST(stream)>>>(x, y, B, C, plane, gscale, coef, gx);
+    cos_sim_bwd_kernel<<<dsr_grid((long)B * plane, TT), TT, 0, ST(stream)>>>(x, y, nullptr, B, C, plane, gscale, coef, gx);
     return dsr_check_launch("cos_sim_bwd");
+}
+extern "C" int dsr_cos_sim_masked_fwd(const float* x, const float* y, const float* mask, int B, int C, long plane, double* out_sum,
+                                      void* stream) {
+    DSR_REQUIRE(x && y && mask && out_sum && B > 0 && C > 0 && plane > 0, "bad arguments");
+    cos_sim_fwd_kernel<<<dsr_grid((long)B * plane, TT), TT, 0, ST(stream)>>>(x, y, mask, B, C, plane, out_sum);
+    return dsr_check_launch("cos_sim_masked_fwd");
+}
+extern "C" int dsr_cos_sim_masked_bwd(const float* x, const float* y, const float* mask, int B, int C, long plane, const float* gscale,
+                                      float coef, float* gx, void* stream) {
+    DSR_REQUIRE(x && y && mask && gx && B > 0 && C > 0 && plane > 0, "bad arguments");
+    cos_sim_bwd_kernel<<<dsr_grid((long)B * plane, TT), TT, 0, ST(stream)>>>(x, y, mask, B, C, plane, gscale, coef, gx);
+    return dsr_check_launch("cos_sim_masked_bwd");
+}
+
+// MaskedMeanDif (models/translation_network.py:288-293): sums[b] = (sum (y - x) * mask, sum mask) over sample b's plane
+__global__ void masked_mean_dif_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mask,
+                                           long plane, double* __restrict__ sums) {
+    __shared__ double red[32];
+    const int b = blockIdx.y;
+    double sd = 0.0, sm = 0.0;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += (long)gridDim.x * blockDim.x) {
+        const float m = mask[b * plane + p];
+        sd += (double)((y[b * plane + p] - x[b * plane + p]) * m);
+        sm += (double)m;
+    }
+    sd = block_sum<double>(sd, red);
+    sm = block_sum<double>(sm, red);
+    if (threadIdx.x == 0) { atomicAdd(sums + 2 * b, sd); atomicAdd(sums + 2 * b + 1, sm); }
+}
+// *loss = mean_b |sums[b][0] / (sums[b][1] + 1e-6)|   (one thread)
+__global__ void masked_mean_dif_finish_kernel(const double* __restrict__ sums, int B, float* __restrict__ loss) {
+    double acc = 0.0;
+    for (int b = 0; b < B; ++b) acc += fabs(sums[2 * b] / (sums[2 * b + 1] + 1e-6));
+    *loss = (float)(acc / B);
+}
+// gx = -(*gscale) * sign(mean_b) * mask / (sum mask_b + 1e-6) / B
+__global__ void masked_mean_dif_bwd_kernel(const float* __restrict__ mask, const double* __restrict__ sums, int B, long plane,
+                                           const float* __restrict__ gscale, float* __restrict__ gx) {
+    const int b = blockIdx.y;
+    const double q = sums[2 * b] / (sums[2 * b + 1] + 1e-6);
+    const float c = -(*gscale) * (q > 0.0 ? 1.f : (q < 0.0 ? -1.f : 0.f)) / (float)(sums[2 * b + 1] + 1e-6) / (float)B;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += (long)gridDim.x * blockDim.x)
+        gx[b * plane + p] = c * mask[b * plane + p];
+}
+extern "C" int dsr_masked_mean_dif_fwd(const float* x, const float* y, const float* mask, int B, long plane, double* sums, float* loss,
+                                       void* stream) {
+    DSR_REQUIRE(x && y && mask && sums && loss && B > 0 && plane > 0, "bad arguments");
+    dim3 grid((unsigned)min((plane + TT - 1) / TT, 64L), B);
+    masked_mean_dif_fwd_kernel<<<grid, TT, 0, ST(stream)>>>(x, y, mask, plane, sums);
+    masked_mean_dif_finish_kernel<<<1, 1, 0, ST(stream)>>>(sums, B, loss);
+    return dsr_check_launch("masked_mean_dif_fwd");
+}
+extern "C" int dsr_masked_mean_dif_bwd(const float* mask, const double* sums, int B, long plane, const float* gscale, float* gx,
+                                       void* stream) {
+    DSR_REQUIRE(mask && sums && gscale && gx && B > 0 && plane > 0, "bad arguments");
+    dim3 grid((unsigned)min((plane + TT - 1) / TT, 64L), B);
+    masked_mean_dif_bwd_kernel<<<grid, TT, 0, ST(stream)>>>(mask, sums, B, plane, gscale, gx);
+    return dsr_check_launch("masked_mean_dif_bwd");
 }

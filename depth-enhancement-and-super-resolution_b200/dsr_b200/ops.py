@@ -1517,6 +1517,64 @@ def cos_sim_loss(x, y):
     return _CosSim.apply(x, y)
 
 
+class _CosSimMasked(Function):
+    """sum over pixels of mask * (1 - cos(x, y)) along dim 1 (MaskedCosSimLoss, models/translation_network.py:320-327, without
+    its denominator); gradient to x."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask):
+        xp, yp, mp = planes(x), planes(y.detach()), planes(mask.detach())
+        B, C, H, W = xp.shape
+        acc = _zeros_f64(1, xp.device)
+        _call("dsr_cos_sim_masked_fwd", _p(xp), _p(yp), _p(mp), B, C, H * W, _p(acc, torch.float64))
+        out = torch.empty((), device=xp.device, dtype=torch.float32)
+        _call("dsr_cvt_f64_f32", _p(acc, torch.float64), 1, _p(out), 1, 1.0, 0)
+        ctx.save_for_backward(xp, yp, mp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xp, yp, mp = ctx.saved_tensors
+        B, C, H, W = xp.shape
+        gx = torch.empty_like(xp)
+        _call("dsr_cos_sim_masked_bwd", _p(xp), _p(yp), _p(mp), B, C, H * W, _p(g.contiguous()), 1.0, _p(gx))
+        return gx, None, None
+
+
+def cos_sim_masked_sum(x, y, mask):
+    return _CosSimMasked.apply(x, y, mask)
+
+
+class _MaskedMeanDif(Function):
+    """MaskedMeanDif (models/translation_network.py:288-293): mean over samples of |sum (y - x) mask / (sum mask + 1e-6)|;
+    gradient to x (one channel)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask):
+        xp, yp, mp = planes(x), planes(y.detach()), planes(mask.detach())
+        B, C, H, W = xp.shape
+        if C != 1:
+            raise ValueError("masked_mean_dif: one-channel depth maps only")
+        sums = _zeros_f64(2 * B, xp.device)
+        out = torch.empty((), device=xp.device, dtype=torch.float32)
+        _call("dsr_masked_mean_dif_fwd", _p(xp), _p(yp), _p(mp), B, H * W, _p(sums, torch.float64), _p(out))
+        ctx.save_for_backward(mp, sums)
+        ctx.shape = (B, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mp, sums = ctx.saved_tensors
+        B, H, W = ctx.shape
+        gx = torch.empty_like(mp)
+        _call("dsr_masked_mean_dif_bwd", _p(mp), _p(sums, torch.float64), B, H * W, _p(g.contiguous()), _p(gx))
+        return gx, None, None
+
+
+def masked_mean_dif(x, y, mask):
+    return _MaskedMeanDif.apply(x, y, mask)
+
+
 def ssim(a, b):
     """Mean SSIM (11x11 Gaussian, sigma 1.5).  pytorch_ssim/__init__.py:17-37.  Forward only."""
     a, b = planes(a.detach()), planes(b.detach())

@@ -7,9 +7,10 @@ and field-of-view normals for each domain), LSGAN, cycle B (L1 + cosine similari
 losses; ``optimize_parameters`` = ``num_iter_gen`` generator iterations with the discriminators frozen, then one discriminator
 update (:274-291).  Same method surface, ``loss_*`` / visual names and checkpoint names as the reference.
 
-Built for the default flag set (translation_model.py:14-43): ``use_cycle_B``, ``disc_for_depth``, ``disc_for_normals``,
-``l_identity > 0`` with ``no_idt_A``, depth-range losses, ``inp_B='img_depth'``, optionally ``l_tv_A``; ``use_cycle_A``,
-``l_mean_*`` and ``inp_B='depth'`` raise ``NotImplementedError``.  Deliberate difference: the reference runs ``netG_A`` on ``(fake_depth_A,
+Built around the default flag set (translation_model.py:14-43): ``use_cycle_B``, ``disc_for_depth``, ``disc_for_normals``,
+``l_identity > 0`` with ``no_idt_A`` and the depth-range losses are always on; the optional terms ``use_cycle_A`` (masked L1 +
+masked cosine similarity through G_B, :165-172, :222-225), ``l_mean_A`` / ``l_mean_B`` (:243-247), ``l_tv_A`` (:247-249) and the
+depth-only ``inp_B='depth'`` generator (:146-147) are wired as well.  Deliberate difference: the reference runs ``netG_A`` on ``(fake_depth_A,
 real_img_B)`` twice per forward and throws the first result away (:177-178); here it runs once.
 """
 import torch
@@ -48,13 +49,19 @@ class TranslationModel(GraphStepMixin, BaseModel):
 
     def __init__(self, opt):                                        # translation_model.py:45-127
         BaseModel.__init__(self, opt)
-        if opt.use_cycle_A or opt.l_mean_A > 0 or opt.l_mean_B > 0 or opt.inp_B != "img_depth" or \
+        if opt.inp_B not in ("img_depth", "depth") or \
                 not (opt.use_cycle_B and opt.disc_for_depth and opt.disc_for_normals and opt.l_identity > 0 and opt.no_idt_A):
-            raise NotImplementedError("dsr_b200.TranslationModel is built for the default loss flags of translation_model.py:14-43 "
-                                      "(cycle B, depth + normal discriminators, identity B, depth-range losses, inp_B='img_depth')")
-        if self.isTrain:
-            self.loss_names = ["G_A", "G_B", "depth_dif_A", "depth_dif_B", "cycle_B", "cycle_n_B", "D_A_depth", "D_B_depth",
-                               "D_A_normal", "D_B_normal", "idt_A", "idt_B"]
+            raise NotImplementedError("dsr_b200.TranslationModel: cycle B, the depth + normal discriminators and identity B "
+                                      "(the defaults of translation_model.py:14-43, README.md:51) cannot be switched off")
+        if self.isTrain:                                             # translation_model.py:47-68, same order
+            self.loss_names = ["G_A", "G_B", "depth_dif_A", "depth_dif_B"]
+            if opt.l_mean_A > 0:
+                self.loss_names.append("mean_dif_A")
+            if opt.l_mean_B > 0:
+                self.loss_names.append("mean_dif_B")
+            if opt.use_cycle_A:
+                self.loss_names += ["cycle_A", "cycle_n_A"]
+            self.loss_names += ["cycle_B", "cycle_n_B", "D_A_depth", "D_B_depth", "D_A_normal", "D_B_normal", "idt_A", "idt_B"]
             if opt.l_depth_A_begin > 0:
                 self.loss_names.append("depth_range_A")
             if opt.l_depth_B_begin > 0:
@@ -63,7 +70,7 @@ class TranslationModel(GraphStepMixin, BaseModel):
                 self.loss_names.append("tv_norm_A")                  # translation_model.py:67-68
         self.loss_names_test = ["depth_dif_A", "depth_dif_B"]
         self.visual_names = ["real_img_A", "real_depth_A", "real_img_B", "real_depth_B", "fake_depth_B", "fake_depth_A", "name_A",
-                             "name_B", "rec_depth_B"]
+                             "name_B"] + (["rec_depth_A"] if opt.use_cycle_A else []) + ["rec_depth_B"]
         if self.isTrain:
             self.visual_names += ["idt_A", "idt_B"]
         self.model_names = ["G_A", "G_B"]
@@ -149,18 +156,26 @@ class TranslationModel(GraphStepMixin, BaseModel):
     def forward(self):                                              # translation_model.py:140-187
         self.valid_A = self._valid_mask(self.real_depth_A)          # ~hole_mask_A
         self.fake_depth_B = self.netG_A(self.real_depth_A, self.real_img_A)
-        self.fake_depth_A = self.netG_B(self.real_depth_B, self.real_img_B)
+        self.fake_depth_A = self._G_B(self.real_depth_B, self.real_img_B)
         if self.isTrain:
             self.real_norm_A = ops.fov_normals(self.real_depth_A)
             self.real_norm_B = ops.fov_normals(self.real_depth_B)
             self.fake_norm_A = ops.fov_normals(self.fake_depth_A)
             self.fake_norm_B = ops.fov_normals(self.fake_depth_B)
         self.valid_B = self._valid_mask(self.fake_depth_A)          # ~hole_mask_B (no gradient through the mask)
+        if self.opt.use_cycle_A:                                    # :165-172: A -> B -> A through G_B
+            self.rec_depth_A = self._G_B(self.fake_depth_B, self.real_img_A)
+            if self.isTrain:
+                self.rec_norm_A = ops.fov_normals(self.rec_depth_A)
         self.rec_depth_B = self.netG_A(self.fake_depth_A, self.real_img_B)          # :176-178 (once, see the module docstring)
         if self.isTrain:
             self.rec_norm_B = ops.fov_normals(self.rec_depth_B)
             self.idt_A = self.netG_A(self.real_depth_B, self.real_img_B)            # :181-187
-            self.idt_B = self.netG_B(self.real_depth_A, self.real_img_A)
+            self.idt_B = self._G_B(self.real_depth_A, self.real_img_A)
+
+    def _G_B(self, depth, img):
+        """netG_B is a depth-only generator with --inp_B depth (translation_model.py:146-147, :167-168, :185-186)"""
+        return self.netG_B(depth) if self.opt.inp_B == "depth" else self.netG_B(depth, img)
 
     def _masked_l1(self, x, y, valid):
         """MaskedL1Loss (translation_network.py:281-286): sum(|y - x| * mask) / (sum(mask) + 1e-6); gradient to x."""
@@ -192,12 +207,27 @@ class TranslationModel(GraphStepMixin, BaseModel):
         self.loss_G_B = 0.5 * self._lsgan(self.netD_B_depth(self.fake_depth_A), 1.0) + \
             0.5 * self._lsgan(self.netD_B_normal(self.fake_norm_A), 1.0)
         loss_A, loss_B = self.loss_G_A, self.loss_G_B
+        if opt.use_cycle_A:                                          # :222-225
+            self.loss_cycle_A = self._masked_l1(self.rec_depth_A, self.real_depth_A, self.valid_A) * self._w("l_cycle_A")
+            # MaskedCosSimLoss with the 3-channel mask: 3 * sum(mask * (1 - cos)) / (3 * sum(mask) + 1e+6)  (the 1e+6 is the
+            # reference's, translation_network.py:327)
+            s_mask = ops.masked_sums(self.valid_A, self.valid_A, self.valid_A)[0]
+            scale = (3.0 / (3.0 * s_mask + 1e+6)).to(torch.float32)
+            self.loss_cycle_n_A = ops.cos_sim_masked_sum(self.rec_norm_A, self.real_norm_A, self.valid_A) * scale * \
+                opt.l_normal * self._w("l_cycle_A")
+            loss_A = loss_A + self.loss_cycle_A + self.loss_cycle_n_A
         self.loss_cycle_B = self._l1(self.rec_depth_B, self.real_depth_B) * self._w("l_cycle_B")
         self.loss_cycle_n_B = ops.cos_sim_loss(self.rec_norm_B, self.real_norm_B) * opt.l_normal * self._w("l_cycle_B")
         loss_B = loss_B + self.loss_cycle_B + self.loss_cycle_n_B
         self.loss_idt_A = 0
         self.loss_idt_B = self._l1(self.idt_B, self.real_depth_A) * opt.l_identity
         loss_B = loss_B + self.loss_idt_B
+        if opt.l_mean_A > 0:                                         # :240-245
+            self.loss_mean_dif_A = ops.masked_mean_dif(self.fake_depth_B, self.real_depth_A, self.valid_A) * opt.l_mean_A
+            loss_A = loss_A + self.loss_mean_dif_A
+        if opt.l_mean_B > 0:
+            self.loss_mean_dif_B = ops.masked_mean_dif(self.fake_depth_A, self.real_depth_B, self.valid_B) * opt.l_mean_B
+            loss_B = loss_B + self.loss_mean_dif_B
         if self.l_depth_A > 0:
             self.loss_depth_range_A = self._masked_l1(self.fake_depth_B, self.real_depth_A, self.valid_A) * self._w("l_depth_A")
             loss_A = loss_A + self.loss_depth_range_A

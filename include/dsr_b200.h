@@ -122,6 +122,18 @@ int dsr_fov_normals_bwd(const float* depth, const float* gout, int B, int H, int
 int dsr_cos_sim_fwd(const float* x, const float* y, int B, int C, long plane, double* out_sum, void* stream);
 int dsr_cos_sim_bwd(const float* x, const float* y, int B, int C, long plane, const float* gscale, float coef, float* gx,
                     void* stream);
+/* MaskedCosSimLoss (models/translation_network.py:320-327; call site translation_model.py:225): the same with a per-pixel
+ * weight mask [B][plane]: *out_sum += sum mask * (1 - cos).  (The caller applies the reference's 1 / (sum(mask) + 1e+6).) */
+int dsr_cos_sim_masked_fwd(const float* x, const float* y, const float* mask, int B, int C, long plane, double* out_sum,
+                           void* stream);
+int dsr_cos_sim_masked_bwd(const float* x, const float* y, const float* mask, int B, int C, long plane, const float* gscale,
+                           float coef, float* gx, void* stream);
+/* MaskedMeanDif (models/translation_network.py:288-293; call sites translation_model.py:243-247): sums (zeroed by the caller,
+ * double [B][2]) += per-sample (sum (y - x) * mask, sum mask); *loss = mean_b |sums[b][0] / (sums[b][1] + 1e-6)|;
+ * bwd: gx = d loss / dx * (*gscale). */
+int dsr_masked_mean_dif_fwd(const float* x, const float* y, const float* mask, int B, long plane, double* sums, float* loss,
+                            void* stream);
+int dsr_masked_mean_dif_bwd(const float* mask, const double* sums, int B, long plane, const float* gscale, float* gx, void* stream);
 
 /* ---- network plumbing (NHWC fp32) ------------------------------------------------------------ */
 int dsr_nchw_to_nhwc(const float* x, float* y, int N, int C, long P, void* stream);

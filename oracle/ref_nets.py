@@ -88,9 +88,10 @@ def _rconv(x, w, b, k, stride):
     return F.conv2d(F.pad(x, (p, p, p, p), mode="replicate"), w, b, stride=stride)
 
 
-def translation_generator(sd, depth, img, n_blocks=9, n_down=2):
+def translation_generator(sd, depth, img=None, n_blocks=9, n_down=2):
     """translation_network.Generator('img_depth').forward (models/translation_network.py:641-649):
-    Encoder x2 (:466-483), ResnetBottlenec on cat(depth, img) (:533-575), Decoder (:485-510)."""
+    Encoder x2 (:466-483), ResnetBottlenec on cat(depth, img) (:533-575), Decoder (:485-510).
+    img None = Generator('depth') (:650-653): one 64-channel depth encoder, no image branch."""
 
     def enc(p, x):
         x = F.relu(_gn(_rconv(x, sd[p + "0.weight"], None, 7, 1), sd[p + "1.weight"], sd[p + "1.bias"]))
@@ -101,9 +102,8 @@ def translation_generator(sd, depth, img, n_blocks=9, n_down=2):
             j += 3
         return x
 
-    fi = enc("enc_img.model.", img)
     fd = enc("enc_depth.model.", depth)
-    x = torch.cat((fd, fi), dim=1)                                     # translation_network.py:549
+    x = torch.cat((fd, enc("enc_img.model.", img)), dim=1) if img is not None else fd    # translation_network.py:549
     for i in range(n_blocks):
         p = f"bottlenec.model.{i}.conv_block."
         y = F.relu(_gn(_rconv(x, sd[p + "0.weight"], None, 3, 1), sd[p + "1.weight"], sd[p + "1.bias"]))

@@ -60,15 +60,18 @@ class OracleTranslationStep:
     weight_decay w_decay_G on the generators (translation_model.py:117-118)."""
 
     def __init__(self, sds, lr=2e-4, beta1=0.5, w_decay_G=1e-4, num_iter_gen=3, l_cycle_B=5.0, l_normal=1.0, l_identity=1.0,
-                 l_depth_A=5.0, l_depth_B=5.0, use_cycle_A=False, l_cycle_A=10.0, l_mean_A=0.0, l_mean_B=0.0, l_tv_A=0.0):
+                 l_depth_A=5.0, l_depth_B=5.0, use_cycle_A=False, l_cycle_A=10.0, l_mean_A=0.0, l_mean_B=0.0, l_tv_A=0.0,
+                 inp_B="img_depth"):
         self.sd = {k: {n: t.detach().clone().float().requires_grad_(True) for n, t in v.items()} for k, v in sds.items()}
         self.cfg = dict(lr=lr, beta1=beta1, wd=w_decay_G, n_gen=num_iter_gen, l_cycle_B=l_cycle_B, l_normal=l_normal,
                         l_identity=l_identity, l_depth_A=l_depth_A, l_depth_B=l_depth_B, use_cycle_A=use_cycle_A,
-                        l_cycle_A=l_cycle_A, l_mean_A=l_mean_A, l_mean_B=l_mean_B, l_tv_A=l_tv_A)
+                        l_cycle_A=l_cycle_A, l_mean_A=l_mean_A, l_mean_B=l_mean_B, l_tv_A=l_tv_A, inp_B=inp_B)
         self.adam = {k: {n: (torch.zeros_like(p), torch.zeros_like(p)) for n, p in v.items()} for k, v in self.sd.items()}
         self.steps = {"G": 0, "D": 0}
 
     def _G(self, name, depth, img):
+        if name == "G_B" and self.cfg["inp_B"] == "depth":                  # (:146-147, :167-168, :185-186)
+            img = None
         return ref_nets.translation_generator(self.sd[name], depth, img)
 
     def _D(self, name, x):

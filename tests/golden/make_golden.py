@@ -415,7 +415,8 @@ def golden_ops():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation", "translation_tv", "translation_flags"]
+    which = sys.argv[1:] or ["ops", "step", "resize", "sr", "i2d", "metrics", "gan", "translation", "translation_tv", "translation_flags",
+                             "translation_inpB"]
     sys.argv = sys.argv[:1]
     if "ops" in which:
         golden_ops()
@@ -441,3 +442,7 @@ if __name__ == "__main__":
         golden_translation_step(tag="translation_flags_b1_64",
                                 extra_flags=["--use_cycle_A", "--l_mean_A", "0.5", "--l_mean_B", "0.7", "--l_tv_A", "2.0"],
                                 extra_losses=("cycle_A", "cycle_n_A", "mean_dif_A", "mean_dif_B", "tv_norm_A"))
+    if "translation_inpB" in which:
+        # G_B as a depth-only generator (translation_model.py:146-147, :167-168, :185-186), together with cycle A through it
+        golden_translation_step(tag="translation_inpB_b1_64", extra_flags=["--inp_B", "depth", "--use_cycle_A"],
+                                extra_losses=("cycle_A", "cycle_n_A"))

@@ -260,3 +260,78 @@ def test_graph_replay_follows_the_loss_weight_schedule(built_lib):
     assert ve[0][0] > 0 and ve[3][0] < ve[0][0]          # the depth-range weight decays 5 -> 0 over l_num_iter = 4 updates
     for a, e in zip(vg, ve):
         assert abs(a[0] - e[0]) <= 5e-2 * max(abs(e[0]), 1e-3) and abs(a[1] - e[1]) <= 5e-2 * max(abs(e[1]), 1e-3), (vg, ve)
+
+
+FLAG_SETS = {
+    "flags": (dict(use_cycle_A=True, l_mean_A=0.5, l_mean_B=0.7, l_tv_A=2.0), dict(use_cycle_A=True, l_cycle_A=10.0, l_mean_A=0.5, l_mean_B=0.7, l_tv_A=2.0),
+              "translation_flags_b1_64.npz", ("cycle_A", "cycle_n_A", "mean_dif_A", "mean_dif_B", "tv_norm_A")),
+    "inpB": (dict(use_cycle_A=True, inp_B="depth"), dict(use_cycle_A=True, l_cycle_A=10.0, inp_B="depth"),
+             "translation_inpB_b1_64.npz", ("cycle_A", "cycle_n_A")),
+}
+
+
+def test_translation_oracle_depth_only_G_B_matches_reference():
+    """--inp_B depth --use_cycle_A (translation_model.py:146-147, :167-168, :185-186): the oracle against the live reference"""
+    model_flags, orc_flags, golden, extra = FLAG_SETS["inpB"]
+    g = load_golden(golden)
+    host, sds = _model(**model_flags)
+    assert "enc_img.model.0.weight" not in sds["G_B"] and sds["G_B"]["enc_depth.model.0.weight"].shape[0] == 64
+    for n in NETS:
+        a = float(sum(v.double().abs().sum() for v in sds[n].values()))
+        assert abs(a - float(g["wsum/" + n][0])) <= 1e-9 * a, n
+    orc = ref_translation.OracleTranslationStep(sds, num_iter_gen=2, **orc_flags)
+    out = orc.step(translation_batch(1, 64, 64))
+    f = out["first"]
+    assert rel_l2(f["tensors"]["rec_depth_A"], g["s0/rec_depth_A"]) <= 2e-5
+    for k in extra + ("G", "G_A", "G_B", "cycle_B", "idt_B", "depth_range_B"):
+        assert abs(f["losses"][k] - float(g["s0/loss/" + k])) <= 2e-5 * abs(float(g["s0/loss/" + k])), (k, f["losses"][k])
+    for n in NETS:
+        v = torch.cat([t.detach().double().flatten() for t in orc.sd[n].values()])
+        ref_norm, ref_proj = g["end/w/" + n]
+        assert abs(float(v.norm()) - ref_norm) <= 1e-6 * ref_norm, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["flags", "inpB"])
+def test_translation_step_optional_loss_terms_on_gpu(built_lib, which):
+    """use_cycle_A (MaskedL1 + MaskedCosSim with its 1e+6 denominator), l_mean_A / l_mean_B (MaskedMeanDif), l_tv_A and the
+    depth-only G_B (translation_model.py:146-171, :222-249): the CUDA model against the live-reference golden and the oracle -
+    first generator iteration (losses, gradients), then the whole call (end losses, weights after both Adam updates)."""
+    model_flags, orc_flags, golden, extra = FLAG_SETS[which]
+    g = load_golden(golden)
+    model, sds = _model(gpu_ids=[0], **model_flags)
+    batch = translation_batch(1, 64, 64)
+    ref = ref_translation.OracleTranslationStep(sds, num_iter_gen=2, **orc_flags).step(batch)
+    model.set_input(batch)
+    model.set_requires_grad(model.disc, False)
+    model.forward()
+    model.optimizer_G.zero_grad()
+    model.backward_G()
+    assert rel_l2(model.rec_depth_A.detach().cpu(), g["s0/rec_depth_A"]) <= 1e-2
+    for k in extra + ("G_A", "G_B", "cycle_B", "cycle_n_B", "idt_B", "depth_range_A", "depth_range_B"):
+        v, want = float(getattr(model, "loss_" + k)), float(g["s0/loss/" + k])
+        assert abs(v - want) <= 1e-3 * abs(want), (k, v, want)
+    assert abs(float(model.loss_G) - float(g["s0/loss/G"])) <= 1e-3 * float(g["s0/loss/G"])
+    fa, fb = [], []
+    for name in ("G_A", "G_B"):
+        for n, prm in model._unwrap(getattr(model, "net" + name)).named_parameters():
+            gr = ref["first"]["grads"].get((name, n))
+            if gr is None or float(gr.norm()) == 0.0:
+                continue
+            c = cosine(prm.grad.detach().cpu(), gr)
+            assert c >= 0.999, (name, n, c)
+            fa.append(prm.grad.detach().cpu().flatten()); fb.append(gr.flatten())
+    assert cosine(torch.cat(fa), torch.cat(fb)) >= 0.999
+    model.set_requires_grad(model.disc, True)
+    model2, _ = _model(gpu_ids=[0], **model_flags)
+    model2.set_input(batch)
+    model2.optimize_parameters(0)
+    for k in extra:
+        v, want = float(getattr(model2, "loss_" + k)), float(g["end/loss/" + k])
+        assert abs(v - want) <= 1e-2 * abs(want), (k, v, want)
+    for n in NETS:
+        net = model2._unwrap(getattr(model2, "net" + n))
+        w = torch.cat([t.detach().double().flatten().cpu() for t in net.state_dict().values()])
+        assert abs(float(w.norm()) - g["end/w/" + n][0]) <= 1e-5 * g["end/w/" + n][0], n
+    assert set(model2.loss_names) == set(model2.get_current_losses())
+    assert "rec_depth_A" in model2.get_current_visuals()
