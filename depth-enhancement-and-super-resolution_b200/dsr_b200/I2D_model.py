@@ -70,6 +70,7 @@ class I2DModel(GraphStepMixin, BaseModel):
         src = dict(syn_image=input["A_i" if AtoB else "B_i"], real_image=input["B_i" if AtoB else "A_i"],
                    syn_depth=input["A_d" if AtoB else "B_d"], real_depth=input["B_d" if AtoB else "A_d"])
         self.image_paths = input["A_paths" if AtoB else "B_paths"]
+        self.A_paths, self.B_paths = input.get("A_paths"), input.get("B_paths")
         shapes = {k: tuple(v.shape) for k, v in src.items()}
         if self._in is None or self._in["shapes"] != shapes:
             if getattr(self, "_graph", None) is not None:
@@ -84,7 +85,9 @@ class I2DModel(GraphStepMixin, BaseModel):
             self._in[k].copy_(v, non_blocking=True)
             setattr(self, k, self._in[k])
 
-    def forward(self):                                              # I2D_model.py:163-169
+    def forward(self, stage="train"):                               # I2D_model.py:163-183
+        """``stage``: the reference's ``--save_all`` branch tests an undefined name ``stage`` (I2D_model.py:171 - a NameError as
+        soon as the flag is set); here it is a parameter with the meaning it has in MainModel.forward (main_model.py:321)."""
         B = self.syn_image.shape[0]
         images = torch.cat([self.syn_image, self.real_image], 0)
         with torch.no_grad():                                       # see the module docstring
@@ -92,8 +95,12 @@ class I2DModel(GraphStepMixin, BaseModel):
         self.features_syn, self.features_real = features[:B], features[B:]
         pred = self.netTask(features)
         self.pred_syn_depth, self.pred_real_depth = pred[:B], pred[B:]
-        if getattr(self.opt, "save_all", False):
-            raise NotImplementedError("dsr_b200: PNG export (--save_all) is a 'next' row (SURVEY.md section 8f.4)")
+        if getattr(self.opt, "save_all", False) and stage == "test":               # I2D_model.py:171-182
+            from . import io
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("dsr_b200: --save_all writes files: it cannot run inside a captured CUDA graph")
+            # uint16(clip((pred + 1) / 2, 0, 1) * 5100) of rows [16, H - 16) into f'{save_image_folder}{basename(B_path)}.png'
+            self.saved_files = io.save_predictions(self.pred_real_depth, self.B_paths, self.opt.save_image_folder, 16)
 
     def backward_G(self, back=True):                                # I2D_model.py:212-235
         opt = self.opt

@@ -107,6 +107,16 @@ int dsr_u16_to_depth(const unsigned short* in, long n, int max_mm, float* out, v
 int dsr_u8_to_image(const unsigned char* in, int N, int H, int W, int C, float* out, void* stream);
 int dsr_depth_to_u16(const float* pred, int N, int H, int W, int crop, float scale, unsigned short* out, void* stream);
 
+/* GPU augmentation stage of the dataset (data/my_main_dataset.py:56-90 `trasform`; albumentations 0.4.6 + OpenCV):
+ * dsr_resize_area_int = cv2.resize(INTER_AREA) for integer down-scale factors (A.Resize(interpolation=3), :69);
+ * dsr_augment_gather = A.Rotate(+-30) [cv2.warpAffine INTER_LINEAR / BORDER_REFLECT_101, bit-exact fixed-point coordinates]
+ * -> A.RandomCrop or A.PadIfNeeded(512, 640) [top / left < 0: reflect-101 padding] -> A.HorizontalFlip -> np.clip(-1, 1)
+ * (:71-86) of N samples with C planes each; minv double [N][6] = inverse rotation map, ipar int [N][4] = {rotate?, top, left,
+ * flip} (drawn on the host in the library's `random` call order, like the rectangle tables). */
+int dsr_resize_area_int(const float* src, long planes, int H, int W, int fy, int fx, float* dst, void* stream);
+int dsr_augment_gather(const float* src, int N, int C, int Hs, int Ws, const double* minv, const int* ipar, float* dst, int Hd,
+                       int Wd, void* stream);
+
 /* batch evaluator of new_metrics.py (:115-191): per-image fp64 sums, out double [B][16] =
  * {n, sum|d|, sum d^2} over ~target_hole | the same over ~target_hole & hole | over ~(hole | target_hole) |
  * {3 n, sum |dn|^2} of the first-order normals outside the dilated target holes (kinv: double [B][9] = K^-1, may be NULL) |

@@ -118,3 +118,27 @@ def test_i2d_graph_replay_matches_eager(built_lib):
         out.append((float(model.loss_G), model.pred_real_depth.detach().clone()))
     assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[1][0])
     assert rel_l2(out[0][1].cpu(), out[1][1].cpu()) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_i2d_save_all_writes_pngs(built_lib, tmp_path):
+    """--save_all in the test stage (I2D_model.py:171-182): uint16 PNGs of the real prediction, rows [16, H-16), bit-exact
+    against the numpy restatement of the export"""
+    from dsr_b200 import I2D_model, io, options
+    from oracle import ref_io
+    opt = options.i2d_flags(gpu_ids=[0], batch_size=2, crop_size_h=128, crop_size_w=128, name="t", checkpoints_dir="/tmp/dsr_ck",
+                            save_all=True, save_image_folder=str(tmp_path) + "/")
+    torch.manual_seed(0)
+    model = I2D_model.I2DModel(opt)
+    model.eval()
+    batch = ref_step.synthetic_batch(2, 128, 128, seed=3, depth_kind="smooth")
+    batch["B_paths"] = ["/somewhere/real_0042.png", "x/real_0043.jpg"]
+    with torch.no_grad():
+        model.set_input(batch)
+        model.forward()                      # train stage: nothing is written
+        assert not list(tmp_path.iterdir())
+        model.forward("test")
+    want = ref_io.depth_to_u16(model.pred_real_depth.detach().cpu().numpy(), 16)
+    for i, name in enumerate(("real_0042.png", "real_0043.png")):
+        out = io.read_png_u16(str(tmp_path / name))
+        assert out.shape == (96, 128) and out.dtype == np.uint16 and np.array_equal(out, want[i])
