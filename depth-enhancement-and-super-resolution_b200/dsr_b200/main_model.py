@@ -247,6 +247,7 @@ class MainModel(BaseModel):
         self._in = None                  # persistent device inputs
         self._rect = None                # persistent pinned + device rectangle tables
         self._rects_staged = False
+        self._side = None                # second stream for the independent frozen chain (forward)
         if self.isTrain:
             if self.gpu_ids:
                 self._build_arena()
@@ -352,10 +353,24 @@ class MainModel(BaseModel):
         _, self.syn_mask = ops.hole_valid_masks(self.syn_depth, self.border)
 
         with torch.no_grad():                                       # frozen nets (main_model.py:426)
-            self.syn2real_depth = self.netG_A_d(self.syn_depth, self.syn_image)
+            # G_A_d and the image branch (I2D_features -> Image2Depth) are independent: they run on two streams (an event
+            # fork / join, also inside a captured graph), so the CTAs of one chain fill the partial waves and the small
+            # launches of the other
+            fork = ops.CONFIG["fork_frozen"] and self.device.type == "cuda"
+            if fork:
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                cur = torch.cuda.current_stream()
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self.syn2real_depth = self.netG_A_d(self.syn_depth, self.syn_image)
+            else:
+                self.syn2real_depth = self.netG_A_d(self.syn_depth, self.syn_image)
             images = torch.cat([self.syn_image, self.real_image], 0)
             image_features = self.netI2D_features(images)
             depth_by_image = self.netImage2Depth(image_features)
+            if fork:
+                cur.wait_stream(self._side)
         self.syn_depth_by_image, self.real_depth_by_image = depth_by_image[:B], depth_by_image[B:]
 
         if not self.opt.use_masked:

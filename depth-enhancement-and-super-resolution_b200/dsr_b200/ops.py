@@ -212,6 +212,8 @@ CONFIG = {
                          #   gate margin is set by the dY that reaches the layer, not by the operand rounding.  Layers below
                          #   32^2 (latency-bound, no time to win) keep `passes`
     "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
+    "fork_frozen": True, # MainModel.forward: G_A_d on a second stream beside I2D_features -> Image2Depth
+    "wgrad_kernel": 2,   # 2 = csrc/wgrad_tc2.cu (8 column blocks per CTA, single pass); 1 = first-generation kernel (conv_tc.cu)
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
@@ -604,9 +606,13 @@ def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, 
     dwp = torch.empty((Cm_real, T * Ca), device=M.device, dtype=torch.float32)
     f16 = 3 if dt == "f16" else 0                                        # bit 0: format of M, bit 1: format of A
     _lib.PROFILE_META = dict(macs=N * Hb * Wb * D0 * D1 * R * S, shape=(N, Hb, Wb, Cm_real, Ca, T, 0), passes=npass)
-    _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
-          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
-          Hb, Wb, _p(dwp), npass, f16, 1.0, -1)
+    if CONFIG["wgrad_kernel"] == 2 and npass == 1:
+        _call("dsr_tc_wgrad2", _p(mhi, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad, _p(ahi, torch.bfloat16), Ha, Wa, Ca, T,
+              _int_array(dr), _int_array(ds), 0, 0, Hb, Wb, _p(dwp), f16, 1.0, CONFIG["split_k"])
+    else:
+        _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
+              _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
+              Hb, Wb, _p(dwp), npass, f16, 1.0, -1)
     tgt = DIRECT_GRADS.get(weight.data_ptr())
     if tgt is not None:
         _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(tgt), 1)

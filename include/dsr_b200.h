@@ -287,6 +287,12 @@ int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, int Wm, int 
                  int m_off_w, const void* A_hi, const void* A_lo, int Ha, int Wa, int Ca, int T, const int* tap_dr,
                  const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb, float* dWp, int npass, int f16,
                  float out_scale, int split_k, void* stream);
+/* second-generation schedule of the same weight-gradient GEMM (csrc/wgrad_tc2.cu): eight 64-column blocks (taps / channel
+ * blocks) per CTA in all 512 TMEM columns, N = 256 MMAs, 32-pixel K tiles, vector reductions for split-K; one 16-bit pass
+ * (high planes only - the gate margins do not feel the weight-gradient operand rounding).  Same packed output. */
+int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h, int m_off_w, const void* A_hi,
+                  int Ha, int Wa, int Ca, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb,
+                  float* dWp, int f16, float out_scale, int split_k, void* stream);
 int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
                         float* grad, int accumulate, void* stream);
 

@@ -1,5 +1,6 @@
 """Recipe for ``oracle/_ref/``: the reference's own Python implementation of the path, byte-compiled from the sources
-WHERE THEY LIE under /root/reference into sourceless ``.pyc`` packages (models/, options/, util/, data/).
+WHERE THEY LIE under /root/reference into sourceless byte-code files ``<module>.pyb`` (models/, options/, util/, data/; ``.pyb`` rather than ``.pyc`` because
+repository snapshots commonly drop ``*.pyc``; oracle/ref_live.py installs the importer that reads them).
 
 TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/__init__.py).  Nothing is copied into the repository history:
 ``oracle/_ref/`` is git-ignored build output, exactly like the ``.so`` files - but it is NOT gpurun-ignored, so it travels
@@ -30,7 +31,7 @@ def build_ref(force=False):
                 if not f.endswith(".py"):
                     continue
                 src = os.path.join(dirpath, f)
-                dst = os.path.join(OUT, rel, f + "c")
+                dst = os.path.join(OUT, rel, f + "b")
                 if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
                     continue
                 os.makedirs(os.path.dirname(dst), exist_ok=True)
@@ -48,7 +49,7 @@ def available():
     """True when a staged reference matching this interpreter is present"""
     try:
         return open(os.path.join(OUT, "PYTHON_VERSION")).read().strip() == "%d.%d" % sys.version_info[:2] and \
-            os.path.exists(os.path.join(OUT, "models", "main_model.pyc"))
+            os.path.exists(os.path.join(OUT, "models", "main_model.pyb"))
     except OSError:
         return False
 

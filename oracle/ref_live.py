@@ -20,9 +20,29 @@ def available():
     return build_ref.available()
 
 
+class _RefFinder:
+    """meta-path finder for the byte-compiled reference tree: <pkg>/<module>.pyb, packages as <pkg>/__init__.pyb"""
+
+    @staticmethod
+    def find_spec(fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname.split(".")[0] not in build_ref.PACKAGES:
+            return None
+        base = os.path.join(build_ref.OUT, *fullname.split("."))
+        if os.path.exists(os.path.join(base, "__init__.pyb")):
+            f = os.path.join(base, "__init__.pyb")
+            return importlib.util.spec_from_file_location(fullname, f, loader=importlib.machinery.SourcelessFileLoader(fullname, f),
+                                                          submodule_search_locations=[base])
+        if os.path.exists(base + ".pyb"):
+            return importlib.util.spec_from_file_location(fullname, base + ".pyb",
+                                                          loader=importlib.machinery.SourcelessFileLoader(fullname, base + ".pyb"))
+        return None
+
+
 def _import_reference():
-    if build_ref.OUT not in sys.path:
-        sys.path.insert(0, build_ref.OUT)
+    if not any(f is _RefFinder for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder)
     sys.modules.setdefault("imageio", types.ModuleType("imageio"))      # only used by the --save_all branch (main_model.py:11)
 
 

@@ -655,3 +655,32 @@ def test_smooth_row_ring_rejects_unsuitable_shapes(ops):
     with pytest.raises(RuntimeError):
         _call("dsr_smooth_level_fwd_ring", _p(d), _p(img), 1, 3, 8, 30, _p(torch.zeros(2, dtype=torch.float64, device="cuda"), torch.float64))
 
+
+
+def test_wgrad2_matches_first_generation_kernel(ops):
+    """csrc/wgrad_tc2.cu (8 column blocks per CTA, N = 256 MMAs, 32-pixel K tiles, vector reductions) against the
+    first-generation weight-gradient kernel on the SAME single-pass bf16 operands: identical products, different summation
+    order.  Shapes: every layer class of the step (3x3 / 7x7 pair / first layer with 32 rows / s2d down convs / transposed
+    convs / 2x2 and 4x4 bottleneck levels), ragged edges, short last column-block groups."""
+    old = dict(ops.CONFIG)
+    cases = [("conv", 128, 128, 3, 1, 1, 0, 3, 40, 24), ("conv", 32, 128, 7, 1, 3, 0, 2, 36, 20), ("conv", 2, 32, 7, 1, 3, 0, 2, 32, 48),
+             ("conv", 261, 64, 4, 2, 1, 0, 2, 32, 48), ("conv", 64, 128, 3, 2, 1, 0, 2, 24, 24), ("conv", 512, 512, 4, 2, 1, 0, 3, 4, 4),
+             ("conv", 512, 512, 4, 2, 1, 0, 5, 8, 8), ("convT", 1024, 256, 4, 2, 1, 0, 2, 8, 8), ("convT", 512, 512, 4, 2, 1, 0, 12, 2, 2),
+             ("convT", 128, 64, 3, 2, 1, 1, 2, 20, 12), ("conv", 256, 256, 3, 1, 1, 0, 2, 16, 16)]
+    try:
+        for case in cases:
+            kind, Ci, Co, k, s, p, op, N, H, W = case
+            x = cl(torch.randn(N, Ci, H, W, generator=G(280)))
+            wshape = (Co, Ci, k, k) if kind == "conv" else (Ci, Co, k, k)
+            w0 = torch.randn(wshape, generator=G(281)) * 0.05
+            grads = []
+            for kernel in (1, 2):
+                ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=1, wgrad_kernel=kernel)
+                xc, wc = x.clone().requires_grad_(True), w0.cuda().requires_grad_(True)
+                out = ops.conv2d(xc, wc, None, s, p) if kind == "conv" else ops.conv_transpose2d(xc, wc, None, s, p, op)
+                go = torch.randn(out.shape, generator=G(282)).cuda()
+                (out * go).sum().backward()
+                grads.append(wc.grad.detach().cpu())
+            assert rel_l2(grads[1], grads[0]) <= 2e-6, (case, rel_l2(grads[1], grads[0]))
+    finally:
+        ops.CONFIG.update(old)
