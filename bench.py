@@ -448,10 +448,10 @@ def run_ours(args):
     # ahead of the step lets the host enqueue the whole step first, so the brackets run back to back on the device and
     # measure kernel durations only.
     torch.cuda._sleep(int(0.10 * 1.9e9))
-    fork_was = ops.CONFIG.get("fork_frozen")
-    ops.CONFIG["fork_frozen"] = False         # one stream: a bracket must contain ONE kernel, not two overlapping chains
+    was = {k: ops.CONFIG.get(k) for k in ("fork_frozen", "side_wgrad")}
+    ops.CONFIG.update(fork_frozen=False, side_wgrad=False)    # one stream: a bracket must contain ONE kernel, not overlapping chains
     model._step_body()                        # eager launches, so every library call can be bracketed by events
-    ops.CONFIG["fork_frozen"] = fork_was
+    ops.CONFIG.update(was)
     torch.cuda.synchronize()
     if rank == 0:
         rec, _lib.PROFILE = _lib.PROFILE, None

@@ -120,6 +120,7 @@ class I2DModel(GraphStepMixin, BaseModel):
         self.loss_G = self.loss_G * opt.scale_G
         if back:
             self.loss_G.backward()
+            ops.join_side()
 
     def optimize_parameters(self, iters=0, fr=700):                 # I2D_model.py:237-250
         self._graph_optimize()

@@ -451,6 +451,7 @@ class MainModel(BaseModel):
         self.loss_G = self.loss_G * opt.scale_G                                               # :417
         if back:
             self.loss_G.backward()
+            ops.join_side()          # the weight-gradient stream (ops._on_side) rejoins before anything reads the gradients
 
     # visuals the reference overwrites after the losses (:386, :400) - computed only when read
     @property

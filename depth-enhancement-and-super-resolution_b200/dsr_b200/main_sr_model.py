@@ -161,6 +161,7 @@ class MainSRModel(MainModel):
         self.loss_G = self.loss_G * opt.scale_G                                               # :482
         if back:
             self.loss_G.backward()
+            ops.join_side()
 
     @property
     def mask_real_add_holes(self):                                  # :463

@@ -150,6 +150,71 @@ def _grad_ready(param):
         GRAD_READY(param.data_ptr())
 
 
+# Weight / bias gradients of arena parameters are off the critical path of the backward pass (nothing reads them before the
+# all-reduce / Adam), while the data-gradient chain is a long sequence of dependent launches, many of them far too small to
+# fill 148 SMs.  They therefore run on a SECOND stream: forked behind the operand preparation of dY on the main stream,
+# joined by `join_side()` right after `loss.backward()`.  Tensors allocated on the main stream and read on the side stream
+# are kept alive until the join (`_keep`), so the caching allocator cannot hand their memory to a later main-stream
+# allocation while the side stream still reads it.  Also legal inside a CUDA-graph capture (event fork / join).
+_SIDE = {"stream": {}, "forked": False, "keep": []}
+
+
+def _use_side(*params):
+    """side stream only for gradients accumulated in place in the arena (a gradient RETURNED to autograd must be ready on
+    the main stream)"""
+    return CONFIG["side_wgrad"] and all(p is None or p.data_ptr() in DIRECT_GRADS for p in params)
+
+
+class _on_side:
+    def __init__(self, enabled, device):
+        self.enabled, self.device, self.ctx = enabled, device, None
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        key = self.device.index
+        side = _SIDE["stream"].get(key)
+        if side is None:
+            side = _SIDE["stream"][key] = torch.cuda.Stream(self.device)
+        _SIDE["main"] = torch.cuda.current_stream()
+        side.wait_stream(_SIDE["main"])
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        _SIDE["forked"] = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _keep(*tensors):
+    if _SIDE["forked"]:
+        _SIDE["keep"].extend(t for t in tensors if t is not None)
+
+
+def order_after_gradient_writers():
+    """the current stream waits for every stream that may have written gradients (called before a bucket's all-reduce is
+    enqueued: a bucket can hold gradients written on the main AND on the weight-gradient stream)"""
+    if not _SIDE["forked"]:
+        return
+    cur = torch.cuda.current_stream()
+    for s in list(_SIDE["stream"].values()) + [_SIDE.get("main")]:
+        if s is not None and s != cur:
+            cur.wait_stream(s)
+
+
+def join_side():
+    """main stream waits for the weight-gradient stream (call after loss.backward(), before anything reads the gradients)"""
+    if _SIDE["forked"]:
+        cur = torch.cuda.current_stream()
+        for side in _SIDE["stream"].values():
+            cur.wait_stream(side)
+        _SIDE["forked"] = False
+    _SIDE["keep"] = []
+
+
 def _bias_grad(dy_nhwc, Co, bias, gP=None):
     """bias gradient = per-channel sum of dY: taken for free by the operand prep of dY when there was one (gP.csum),
     by one channel_sums pass otherwise"""
@@ -212,6 +277,7 @@ CONFIG = {
                          #   gate margin is set by the dY that reaches the layer, not by the operand rounding.  Layers below
                          #   32^2 (latency-bound, no time to win) keep `passes`
     "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
+    "side_wgrad": True,  # weight / bias gradients of arena parameters on a second stream beside the data-gradient chain
     "fork_frozen": True, # MainModel.forward: G_A_d on a second stream beside I2D_features -> Image2Depth
     "wgrad_kernel": 2,   # 2 = csrc/wgrad_tc2.cu (8 column blocks per CTA, single pass); 1 = first-generation kernel (conv_tc.cu)
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
@@ -583,6 +649,16 @@ def _tc_convT_dgrad(g, weight, stride, pad, H, W):
     return _tc_conv_fwd(g, weight, None, plan, stride, pad, PAD_ZERO, ACT_NONE, H, W, dtype=CONFIG["bwd_dtype"], Co=Ci)
 
 
+def _tc_wgrad_m_operand(M, Cm_real):
+    """the zero-padded NORMAL 16-bit copy of the weight-gradient GEMM's row operand (made by the data gradient when one ran)"""
+    if not CONFIG["tc_backward"] or CONFIG["engine"] != "tc":
+        return
+    dt, npass = CONFIG["bwd_dtype"], min(CONFIG["wgrad_passes"], CONFIG["passes"])
+    Cm = _rup(Cm_real, 64)
+    if M.any_normal(Cm, dt) is None:
+        M.get(dict(layout=_LAYOUT_NORMAL, Cp=_rup(Cm_real, 8), Ca=Cm), 0, PAD_ZERO, dt, need_lo=npass >= 2)
+
+
 def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, variant):
     """weight gradient GEMM over the base grid (Hb x Wb x N):  rows = channels of M (prepared NORMAL, zero pad),
     columns = arranged channels of A x taps; result unpacked / accumulated into the parameter's gradient."""
@@ -613,6 +689,7 @@ def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, 
         _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
               _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
               Hb, Wb, _p(dwp), npass, f16, 1.0, -1)
+    _keep(mhi, mlo, ahi, alo, M.xh, A.xh)
     tgt = DIRECT_GRADS.get(weight.data_ptr())
     if tgt is not None:
         _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(tgt), 1)
@@ -793,18 +870,24 @@ class _Conv2d(Function):
                     _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
                     gxp = gxh
             gx = nchw(_prologue_bwd(pro, prm, xh, gxp))
-        if ctx.needs_input_grad[1]:
-            xP = ctx.xP or (_Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope))
-            done, gw = _tc_conv_wgrad(xP, gP, weight, stride, pad, pad_mode)
-            if not done:
-                xp, p = _explicit_pad(xh, pad, pad_mode)
-                dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
-                _lib.PROFILE_META = dict(macs=0, shape=("wgrad_simt", N, H, W, Ci, Co, R, stride))
-                _call("dsr_wgrad_simt", _p(xp), _p(g), _p(dwk), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
-                      stride, p)
-                gw = _weight_grad(dwk, weight, 1)
-        if has_bias and ctx.needs_input_grad[2]:
-            gb = _bias_grad(g, Co, ctx.bias_ref, gP)
+        need_w, need_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+        if need_w and gx is None:
+            _tc_wgrad_m_operand(gP, Co)           # no data gradient ran: make the dY operand on the main stream
+        with _on_side((need_w or need_b) and _use_side(weight if need_w else None, ctx.bias_ref if need_b else None), g.device):
+            if need_w:
+                xP = ctx.xP or (_Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope))
+                done, gw = _tc_conv_wgrad(xP, gP, weight, stride, pad, pad_mode)
+                if not done:
+                    xp, p = _explicit_pad(xh, pad, pad_mode)
+                    dwk = torch.empty(R * S * Ci * Co, device=g.device, dtype=torch.float32)
+                    _lib.PROFILE_META = dict(macs=0, shape=("wgrad_simt", N, H, W, Ci, Co, R, stride))
+                    _call("dsr_wgrad_simt", _p(xp), _p(g), _p(dwk), N, xp.shape[1], xp.shape[2], Ci, Ho, Wo, Co, R, S,
+                          stride, p)
+                    gw = _weight_grad(dwk, weight, 1)
+                    _keep(xp, xh)
+            if need_b:
+                gb = _bias_grad(g, Co, ctx.bias_ref, gP)
+            _keep(g, gP.csum, prm)
         return gx, gw, gb, None, None, None, None, None, None
 
 
@@ -901,16 +984,19 @@ class _ConvTranspose2d(Function):
                 _lib.PROFILE_META = dict(macs=0, shape=("conv_simt", N, H, W, Ci, Co, R, stride))
                 _call("dsr_conv_simt", _p(g), _p(wk), None, _p(gxh), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, ACT_NONE)
             gx = nchw(_prologue_bwd(pro, prm, xh, gxh))
-        if ctx.needs_input_grad[1]:
-            xP = ctx.xP or (_Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope))
-            done, gw = _tc_convT_wgrad(xP, gP, weight, stride, pad)
-            if not done:
-                dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
-                _lib.PROFILE_META = dict(macs=0, shape=("wgrad_simt", N, H, W, Ci, Co, R, stride))
-                _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
-                gw = _weight_grad(dwk, weight, 1)
-        if has_bias and ctx.needs_input_grad[2]:
-            gb = _bias_grad(g, Co, ctx.bias_ref, gP)
+        need_w, need_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+        with _on_side((need_w or need_b) and _use_side(weight if need_w else None, ctx.bias_ref if need_b else None), g.device):
+            if need_w:
+                xP = ctx.xP or (_Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope))
+                done, gw = _tc_convT_wgrad(xP, gP, weight, stride, pad)
+                if not done:
+                    dwk = torch.empty(R * S * Co * Ci, device=g.device, dtype=torch.float32)
+                    _lib.PROFILE_META = dict(macs=0, shape=("wgrad_simt", N, H, W, Ci, Co, R, stride))
+                    _call("dsr_wgrad_simt", _p(g), _p(xh), _p(dwk), N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad)
+                    gw = _weight_grad(dwk, weight, 1)
+            if need_b:
+                gb = _bias_grad(g, Co, ctx.bias_ref, gP)
+            _keep(g, gP.csum, prm, xh)
         return gx, gw, gb, None, None, None, None, None, None
 
 
@@ -983,12 +1069,17 @@ class _CatConv2d(Function):
                     _call("dsr_copy_channels", _p(gxr), c1 - c0, offs[i] - c0, _p(gi), Cs[i], 0, Cs[i], N * H * W, 0)
                     gxs[i] = nchw(gi)
         gw = gb = None
-        if ctx.needs_input_grad[0]:
-            done, gw = _tc_conv_wgrad(_Prepared(xh), gP, weight, stride, pad, pad_mode)
-            if not done:
-                raise RuntimeError("internal error: cat_conv2d weight gradient is not covered by the tcgen05 path")
-        if has_bias and ctx.needs_input_grad[1]:
-            gb = _bias_grad(g, Co, ctx.bias_ref, gP)
+        need_w, need_b = ctx.needs_input_grad[0], has_bias and ctx.needs_input_grad[1]
+        if need_w and not idx:
+            _tc_wgrad_m_operand(gP, Co)
+        with _on_side((need_w or need_b) and _use_side(weight if need_w else None, ctx.bias_ref if need_b else None), g.device):
+            if need_w:
+                done, gw = _tc_conv_wgrad(_Prepared(xh), gP, weight, stride, pad, pad_mode)
+                if not done:
+                    raise RuntimeError("internal error: cat_conv2d weight gradient is not covered by the tcgen05 path")
+            if need_b:
+                gb = _bias_grad(g, Co, ctx.bias_ref, gP)
+            _keep(g, gP.csum, xh)
         return (gw, gb, None, None, None, None) + tuple(gxs)
 
 

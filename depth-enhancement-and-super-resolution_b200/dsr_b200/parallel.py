@@ -60,8 +60,9 @@ class GradBuckets:
         self.launched[i] = True
         if self.world == 1:
             return
-        # async_op: the collective is enqueued on the process group's own stream behind an event of the current (compute
-        # or capturing) stream; nothing waits for it until finish()
+        # async_op: the collective is enqueued on the process group's own stream behind an event of the current stream (the
+        # weight-gradient stream of ops._on_side, or the compute stream); nothing waits for it until finish()
+        ops.order_after_gradient_writers()
         self.handles.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _ready(self, ptr):
@@ -81,6 +82,7 @@ class GradBuckets:
 
     def finish(self):
         """Launch whatever is left (parameters that got no gradient this step), join, re-arm."""
+        ops.join_side()
         if not self.overlap_hooks:
             return self.all_at_once()
         for i in range(self.next, len(self.buckets)):

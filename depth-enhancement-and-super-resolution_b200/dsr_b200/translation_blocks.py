@@ -72,12 +72,14 @@ class GanBlockStep(GraphStepMixin, BaseModel):
         self.loss_G_A = 0.5 * self._lsgan(self.netD_A_depth(self.fake_depth_B), 1.0)
         self.loss_G = self.loss_G_A
         self.loss_G.backward()
+        ops.join_side()
         self.optimizer_G.step()
         self.set_requires_grad([self.netD_A_depth], True)
         self.optimizer_D.zero_grad()
         fake = self.fake_depth_B.detach()
         self.loss_D_A_depth = 0.5 * (self._lsgan(self.netD_A_depth(self.real_depth_B), 1.0) + self._lsgan(self.netD_A_depth(fake), 0.0))
         self.loss_D_A_depth.backward()
+        ops.join_side()
         self.optimizer_D.step()
 
     def optimize_parameters(self, iters=0, fr=1):

@@ -190,6 +190,7 @@ class TranslationModel(GraphStepMixin, BaseModel):
     def _d_loss(self, netD, real, fake):                            # backward_D_base :189-194
         loss = 0.5 * (self._lsgan(netD(real.detach()), 1.0) + self._lsgan(netD(fake.detach()), 0.0))
         loss.backward()
+        ops.join_side()
         return loss
 
     def backward_D_A(self):                                         # :196-200
@@ -240,6 +241,7 @@ class TranslationModel(GraphStepMixin, BaseModel):
             loss_A = loss_A + self.loss_tv_norm_A
         self.loss_G = loss_A + loss_B
         self.loss_G.backward()
+        ops.join_side()
         with torch.no_grad():                                       # :266-270 (metres)
             md = opt.max_distance
             self.loss_depth_dif_A = self._masked_l1(data_to_meters(self.fake_depth_B.detach(), md),
