@@ -337,6 +337,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     _lib.load()
     ops.CONFIG.update(engine=args.engine, passes=args.passes, dtype=args.dtype)
+    for kv in filter(None, args.cfg.split(",")):            # ablations: --cfg side_wgrad=0,fork_frozen=0
+        k, v = kv.split("=")
+        ops.CONFIG[k] = type(ops.CONFIG[k])(int(v)) if isinstance(ops.CONFIG[k], (bool, int)) else v
     wl = WORKLOADS[args.workload]
     B, H, W = wl["B"], wl["H"], wl["W"]
     torch.manual_seed(0)
@@ -345,7 +348,7 @@ def run_ours(args):
     sync, dp_check = None, None
     if world > 1:
         parallel.broadcast_weights(model)
-        sync = parallel.GradBuckets(model)
+        sync = parallel.GradBuckets(model, overlap=bool(args.dp_overlap))
         if not any(wl.get(k) for k in ("i2d", "gan", "tr", "sr")):
             # numerical check of the data-parallel step before anything is timed or captured: rank-averaged gradients of one
             # sharded step == gradients of ONE process on the concatenated batch (every rank generates every shard)
@@ -583,6 +586,8 @@ def main():
     ap.add_argument("--layer-table", default="", help="write every library call of one step (name, ms, shape, GMACs) to this JSON file")
     ap.add_argument("--kernel-table", default="", help="write the in-situ per-kernel device times of 3 steps (torch.profiler / CUPTI, warm caches) to this JSON file")
     ap.add_argument("--inference", type=int, default=1, help="1 = also time the 640x480 inference forward (ms/frame)")
+    ap.add_argument("--cfg", default="", help="comma-separated ops.CONFIG overrides (ablations), e.g. side_wgrad=0,fork_frozen=0")
+    ap.add_argument("--dp-overlap", type=int, default=1, help="0 = one in-order all-reduce of the gradient arena instead of overlapped buckets")
     ap.add_argument("--stencils", type=int, default=1, help="1 = also measure the HBM roofline table of the stencil / reduction kernels (roofline_hbm)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay the training step as a CUDA graph (default), 0 = eager launches")
     args = ap.parse_args()

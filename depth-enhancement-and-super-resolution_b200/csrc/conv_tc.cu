@@ -447,16 +447,51 @@ __device__ __forceinline__ void split16x2(float x0, float x1, int f16, unsigned&
 // and the hi/lo split uses the paired conversion instructions.  csum (optional) receives the per-source-channel sum of
 // everything written (the bias gradient when the tensor is dY), accumulated in shared memory per block and flushed with
 // fp64 atomics.
+// torch.cat(dim=1) folded into the preparation: up to 4 NHWC sources side by side along the channel axis (n = 0: `x` alone)
+#define PREP_CAT_MAX_GROUPS 256      // concatenations of up to 2048 channels
+struct PrepCat {
+    const float* p[4];
+    int c[4];            // channels of each source
+    int n;
+};
+__device__ __forceinline__ const float* prep_cat_src(const PrepCat& cat, long pix, int c, int& room) {
+    int off = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < cat.n && c < off + cat.c[k]) { room = off + cat.c[k] - c; return cat.p[k] + pix * cat.c[k] + (c - off); }
+        off += k < cat.n ? cat.c[k] : 0;
+    }
+    room = 0;
+    return nullptr;
+}
+
 __global__ void __launch_bounds__(256)
-tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm,
+tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int W, int C, const float* __restrict__ prm,
                int act, float slope, int pad, int mode, int layout, int Cp,
-               unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, int Ha, int Wa, int Ca,
+               unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, unsigned short* __restrict__ Abf,
+               int Ha, int Wa, int Ca,
                int f16, double* __restrict__ csum, unsigned magic_cg, unsigned magic_cp, unsigned magic_ha) {
     extern __shared__ __align__(16) float prep_sm[];
     const int Cs = (C + 3) & ~3;                  // 16-byte aligned parameter rows
     float* s_prm = prep_sm;
     float* s_sum = prep_sm + (prm ? 3 * Cs : 0);
     const int tid = threadIdx.x;
+    // concatenated sources: per 8-channel group of the concatenation, where it lives (built once per block) - base pointer of
+    // its first channel, the source's pixel pitch, and whether the whole group sits 16-byte aligned inside ONE source
+    __shared__ const float* s_cat_ptr[PREP_CAT_MAX_GROUPS];
+    __shared__ int s_cat_pitch[PREP_CAT_MAX_GROUPS];
+    if (cat.n) {
+        for (int g8 = tid; g8 < (C + 7) / 8; g8 += 256) {
+            int room;
+            const float* q = prep_cat_src(cat, 0, g8 * 8, room);
+            int pitch = 0, off = 0;
+            for (int k = 0; k < cat.n; ++k) { if (g8 * 8 < off + cat.c[k]) { pitch = cat.c[k]; break; } off += cat.c[k]; }
+            const bool whole = room >= 8 && (pitch & 3) == 0 && (((uintptr_t)q) & 15) == 0;
+            s_cat_ptr[g8] = q;
+            s_cat_pitch[g8] = whole ? pitch : -pitch;          // negative: element-wise path
+        }
+        __syncthreads();
+    }
     const int cg = Ca >> 3, items = Wa * cg;
     const int Hq = H + 2 * pad, Wq = W + 2 * pad;
     const bool vec = (C & 3) == 0;
@@ -496,12 +531,26 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
             if (qi < Hq && qj < Wq && c < C) {
                 const int i = prep_pad_src(qi, pad, H, mode), j = prep_pad_src(qj, pad, W, mode);
                 if (i >= 0 && j >= 0) {
-                    const float* src = x + (long)((n * H + i) * W + j) * C + c;
-                    const bool full = vec && c + 8 <= C;
+                    const long pix = (long)((n * H + i) * W + j);
+                    const float* src;
+                    bool full;
+                    if (cat.n == 0) {
+                        src = x + pix * C + c;
+                        full = vec && c + 8 <= C;
+                    } else {
+                        const int pitch = s_cat_pitch[c >> 3];
+                        full = pitch > 0;                                        // the 8 channels sit in ONE source, 16-byte aligned
+                        src = s_cat_ptr[c >> 3] + pix * pitch;
+                        if (!full) {                                             // a group that straddles two sources: element-wise
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (c + e < C) { int r2; const float* q2 = prep_cat_src(cat, pix, c + e, r2); v[e] = *q2; }
+                        }
+                    }
                     if (full) {
                         const float4 a = ld4(src), b4 = ld4(src + 4);
                         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
-                    } else {
+                    } else if (cat.n == 0) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) if (c + e < C) v[e] = src[e];
                     }
@@ -544,6 +593,14 @@ tc_prep_kernel(const float* __restrict__ x, int N, int H, int W, int C, const fl
             const long o = ((long)row * Wa + wa) * Ca + q;
             *reinterpret_cast<uint4*>(Ahi + o) = hi;
             if (Alo) *reinterpret_cast<uint4*>(Alo + o) = lo;
+            if (Abf) {       // the same operand once more as plain bf16: what the weight-gradient GEMM of the backward pass reads
+                uint4 b;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                b.x = *reinterpret_cast<unsigned*>(&t0); b.y = *reinterpret_cast<unsigned*>(&t1);
+                b.z = *reinterpret_cast<unsigned*>(&t2); b.w = *reinterpret_cast<unsigned*>(&t3);
+                *reinterpret_cast<uint4*>(Abf + o) = b;
+            }
         }
     }
     if (csum) {
@@ -678,7 +735,7 @@ static int dispatch_n(int bn, const CUtensorMap& ah, const CUtensorMap& al, cons
 }
 
 extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
-                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
+                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
                            double* csum, void* stream) {
     DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
     DSR_REQUIRE(((Ca & 63) == 0 || (Ca == 8 && layout == DSR_TC_LAYOUT_NORMAL)) && (Cp & 7) == 0 && Cp >= C,
@@ -700,10 +757,52 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
     auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / d + 1); };   // 0: divisor 1
     DSR_REQUIRE((unsigned long long)Wa * (Ca >> 3) * (Ca >> 3) < (1ull << 32) && (unsigned long long)Ca * Cp < (1ull << 32) &&
                     (unsigned long long)rows * Ha < (1ull << 32), "tensor too large for the magic-number index divisions");
-    tc_prep_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
-                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16, csum,
+    PrepCat cat;
+    cat.n = 0;
+    for (int k = 0; k < 4; ++k) { cat.p[k] = nullptr; cat.c[k] = 0; }
+    DSR_REQUIRE(!((uintptr_t)A_bf & 15), "operand buffers must be 16-byte aligned");
+    tc_prep_kernel<<<grid, 256, smem, ST(stream)>>>(x, cat, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
+                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, csum,
                                                     magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha));
     return dsr_check_launch("tc_prep");
+}
+
+// the same preparation over torch.cat((x0, x1, x2, x3), dim=1) without materialising the concatenation
+// (models/main_model.py:305-306: the 261-channel Task input; models/networks.py:629: the U-Net skip connections)
+extern "C" int dsr_tc_prep_cat(const float* x0, int C0, const float* x1, int C1, const float* x2, int C2, const float* x3, int C3,
+                               int N, int H, int W, int pad, int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf,
+                               int Ha, int Wa, int Ca, int f16, void* stream) {
+    PrepCat cat;
+    const float* ps[4] = {x0, x1, x2, x3};
+    const int cs[4] = {C0, C1, C2, C3};
+    cat.n = 0;
+    int C = 0;
+    for (int k = 0; k < 4; ++k) {
+        cat.p[k] = nullptr; cat.c[k] = 0;
+        if (ps[k] && cs[k] > 0) {
+            DSR_REQUIRE(cat.n == k, "sources must be given in order without gaps");
+            cat.p[k] = ps[k]; cat.c[k] = cs[k]; C += cs[k]; cat.n = k + 1;
+        }
+    }
+    DSR_REQUIRE(cat.n >= 1 && A_hi && N > 0 && H > 0 && W > 0, "bad arguments");
+    DSR_REQUIRE(C <= 8 * PREP_CAT_MAX_GROUPS, "too many concatenated channels");
+    DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= the channel total");
+    DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
+    DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_PAIR && Ca % Cp == 0 && Ca >= 2 * Cp) ||
+                    (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
+    DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15), "operand buffers must be 16-byte aligned");
+    DSR_REQUIRE((long)N * (H + 2 * pad) * (W + 2 * pad) < (1L << 31) && C <= 8192, "tensor too large for 32-bit pixel indices");
+    const long rows = (long)N * Ha;
+    const long cap = (long)dsr_num_sms() * 8;
+    const int grid = (int)(rows < cap ? rows : cap);
+    auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / d + 1); };
+    DSR_REQUIRE((unsigned long long)Wa * (Ca >> 3) * (Ca >> 3) < (1ull << 32) && (unsigned long long)Ca * Cp < (1ull << 32) &&
+                    (unsigned long long)rows * Ha < (1ull << 32), "tensor too large for the magic-number index divisions");
+    DSR_REQUIRE(!((uintptr_t)A_bf & 15), "operand buffers must be 16-byte aligned");
+    tc_prep_kernel<<<grid, 256, 0, ST(stream)>>>(x0, cat, N, H, W, C, nullptr, DSR_ACT_NONE, 0.f, pad, pad_mode, layout, Cp,
+                                                 (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, nullptr,
+                                                 magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha));
+    return dsr_check_launch("tc_prep_cat");
 }
 
 extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,

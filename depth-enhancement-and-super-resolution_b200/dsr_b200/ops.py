@@ -277,6 +277,8 @@ CONFIG = {
                          #   gate margin is set by the dY that reaches the layer, not by the operand rounding.  Layers below
                          #   32^2 (latency-bound, no time to win) keep `passes`
     "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
+    "fwd_bf16_copy": True,   # forward operand prep of trainable layers also writes the bf16 copy the weight gradient reads
+    "fused_cat": True,   # Conv2d over a LazyCat: the operand preparation reads the parts (no materialised concatenation)
     "side_wgrad": True,  # weight / bias gradients of arena parameters on a second stream beside the data-gradient chain
     "fork_frozen": True, # MainModel.forward: G_A_d on a second stream beside I2D_features -> Image2Depth
     "wgrad_kernel": 2,   # 2 = csrc/wgrad_tc2.cu (8 column blocks per CTA, single pass); 1 = first-generation kernel (conv_tc.cu)
@@ -428,9 +430,12 @@ class _Prepared:
         self.want_csum, self.csum = want_csum, None           # per-channel sums of xh (bias gradient), taken by the first
                                                               # prep that writes every element exactly once
 
-    def get(self, plan, pad, pad_mode, dtype=None, need_lo=True):
-        """need_lo=False: the caller reads the high plane only (single-pass weight gradient) - skip writing the low one"""
-        key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dtype or CONFIG["dtype"])
+    def get(self, plan, pad, pad_mode, dtype=None, need_lo=True, also_bf16=False):
+        """need_lo=False: the caller reads the high plane only (single-pass weight gradient) - skip writing the low one.
+        also_bf16: the same pass also writes a plain bf16 copy in the same arranged layout (the operand the weight-gradient
+        GEMM of the backward pass needs - both its operands must have ONE 16-bit format), found later under dtype 'bf16'."""
+        dt = dtype or CONFIG["dtype"]
+        key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dt)
         hit = self.made.get(key)
         if hit is not None and need_lo and hit[1] is None and CONFIG["passes"] >= 2:
             hit = None                                    # made without its low plane earlier: make it again in full
@@ -438,9 +443,17 @@ class _Prepared:
             csum = None
             if self.want_csum and self.csum is None and plan["layout"] != _LAYOUT_PAIR and (pad == 0 or pad_mode == PAD_ZERO):
                 csum = self.csum = _zeros_f64(self.shape[3], self.device)
-            hit = self.made[key] = _tc_prep(self.xh, plan, pad, pad_mode, self.prm, self.act, self.slope, dtype=dtype,
-                                            csum=csum, need_lo=need_lo)
+            kbf = key[:5] + ("bf16",)
+            also_bf16 = also_bf16 and dt == "f16" and kbf not in self.made
+            hit = self._make(plan, pad, pad_mode, dtype, csum, need_lo, also_bf16)
+            if also_bf16:
+                self.made[kbf] = (hit[4], None, hit[2], hit[3])
+            hit = self.made[key] = hit[:4]
         return hit
+
+    def _make(self, plan, pad, pad_mode, dtype, csum, need_lo, also_bf16):
+        return _tc_prep(self.xh, plan, pad, pad_mode, self.prm, self.act, self.slope, dtype=dtype, csum=csum, need_lo=need_lo,
+                        also_bf16=also_bf16)
 
     def any_normal(self, Ca, dtype):
         """an already-made NORMAL-layout zero-padded copy -> (ahi, alo, Ha, Wa, pad) or None"""
@@ -448,6 +461,37 @@ class _Prepared:
             if layout == _LAYOUT_NORMAL and ca == Ca and dt == dtype and (mode == PAD_ZERO or pad == 0):
                 return v + (pad,)
         return None
+
+
+class _PreparedCat(_Prepared):
+    """_Prepared over torch.cat(parts, dim=1) of NHWC tensors that is never materialised: the preparation kernel reads the
+    parts side by side (dsr_tc_prep_cat; main_model.py:305-306, networks.py:629)."""
+
+    def __init__(self, parts):
+        if len(parts) > 4:
+            raise ValueError("at most four concatenated sources")
+        N, H, W, _ = parts[0].shape
+        self.parts = list(parts)
+        self.xh, self.made = None, {}
+        self.shape, self.device = (N, H, W, sum(p.shape[3] for p in parts)), parts[0].device
+        self.prm, self.act, self.slope, self.want_csum, self.csum = None, ACT_NONE, 0.0, False, None
+
+    def _make(self, plan, pad, pad_mode, dtype, csum, need_lo, also_bf16):
+        N, H, W, C = self.shape
+        Hq, Wq = H + 2 * pad, W + 2 * pad
+        Ha, Wa = ((Hq + 1) // 2, (Wq + 1) // 2) if plan["layout"] == _LAYOUT_S2D else (Hq, Wq)
+        Ca = plan["Ca"]
+        ahi = torch.empty((N, Ha, Wa, Ca), device=self.device, dtype=torch.bfloat16)
+        alo = torch.empty((N, Ha, Wa, Ca), device=self.device, dtype=torch.bfloat16) if (CONFIG["passes"] >= 2 and need_lo) else None
+        abf = torch.empty((N, Ha, Wa, Ca), device=self.device, dtype=torch.bfloat16) if also_bf16 else None
+        src = []
+        for i in range(4):
+            src += [_p(self.parts[i]), self.parts[i].shape[3]] if i < len(self.parts) else [None, 0]
+        if _lib.PROFILE is not None:
+            _lib.PROFILE_META = dict(macs=0, shape=(N, H, W, C, Ca, plan["layout"], pad, 0, int(alo is not None)))
+        _call("dsr_tc_prep_cat", *src, N, H, W, pad, pad_mode, plan["layout"], plan["Cp"], _p(ahi, torch.bfloat16),
+              _p(alo, torch.bfloat16), _p(abf, torch.bfloat16), Ha, Wa, Ca, int((dtype or CONFIG["dtype"]) == "f16"))
+        return ahi, alo, Ha, Wa, abf
 
 
 def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
@@ -473,10 +517,10 @@ def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
     return whi, wlo
 
 
-def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=None, csum=None, need_lo=True):
-    """fp32 NHWC -> arranged bf16 hi(+lo) operand."""
+def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=None, csum=None, need_lo=True, also_bf16=False):
+    """fp32 NHWC -> arranged bf16 hi(+lo) operand (+ the plain bf16 copy as a fifth element with also_bf16)."""
     if isinstance(xh, _Prepared):
-        return xh.get(plan, pad, pad_mode, dtype, need_lo)
+        return xh.get(plan, pad, pad_mode, dtype, need_lo, also_bf16)
     N, H, W, C = xh.shape
     Hq, Wq = H + 2 * pad, W + 2 * pad
     if plan["layout"] == _LAYOUT_S2D:
@@ -488,10 +532,11 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=N
     alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if (CONFIG["passes"] >= 2 and need_lo) else None
     if _lib.PROFILE is not None:
         _lib.PROFILE_META = dict(macs=0, shape=(N, H, W, C, Ca, plan["layout"], pad, int(prm is not None), int(alo is not None)))
+    abf = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if also_bf16 else None
     _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
-          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, int((dtype or CONFIG["dtype"]) == "f16"),
-          _p(csum, torch.float64))
-    return ahi, alo, Ha, Wa
+          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), _p(abf, torch.bfloat16), Ha, Wa, Ca,
+          int((dtype or CONFIG["dtype"]) == "f16"), _p(csum, torch.float64))
+    return (ahi, alo, Ha, Wa, abf) if also_bf16 else (ahi, alo, Ha, Wa)
 
 
 def _tc_kernel_for(N, Ht, Wt, Co, ds, nphase=1):
@@ -525,8 +570,14 @@ def _tc_gemm(ahi, alo, N, Ha, Wa, Ca, whi, wlo, Co, T, dr, ds, aoh, aow, Ht, Wt,
     return stats is not None
 
 
+def _bwd_copy_wanted(want):
+    """forward operand prep also emits the bf16 copy for the weight-gradient GEMM (single-pass bf16 weight gradients only)"""
+    return bool(want) and CONFIG["reuse_fwd_operand"] and CONFIG["tc_backward"] and CONFIG["dtype"] == "f16" and \
+        CONFIG["bwd_dtype"] == "bf16" and min(CONFIG["wgrad_passes"], CONFIG["passes"]) == 1 and CONFIG["fwd_bf16_copy"]
+
+
 def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo, dtype=None, Co=None, macs=None,
-                 stats=None):
+                 stats=None, bwd_copy=False):
     """stride-1 / stride-2 convolution of `xh` with a Conv2d-layout weight on the tcgen05 path.
     Also serves as the dgrad of ConvTranspose2d (its weight read as a Conv2d weight) and, with
     plan['variant'] == _W_CONV_DGRAD, as the dgrad of a stride-1 Conv2d (flipped / transposed taps)."""
@@ -540,7 +591,8 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
     a_mode, a_plan = 0, plan
     if plan.get("compact") and Ho * Wo >= 128 and Wo >= 8:
         a_mode, a_plan = 1, dict(layout=_LAYOUT_NORMAL, Cp=8, Ca=8)       # 8-channel operand, same weights / taps
-    ahi, alo, Ha, Wa = _tc_prep(xh, a_plan, pad, pad_mode, dtype=dtype, need_lo=_passes(dtype) >= 2)
+    ahi, alo, Ha, Wa = _tc_prep(xh, a_plan, pad, pad_mode, dtype=dtype, need_lo=_passes(dtype) >= 2,
+                                also_bf16=_bwd_copy_wanted(bwd_copy) and a_mode == 0 and isinstance(xh, _Prepared))[:4]
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     _lib.PROFILE_META = dict(macs=macs if macs is not None else N * Ho * Wo * Co * Ci * R * S, shape=(N, H, W, Ci, Co, R, stride))
     filled = _tc_gemm(ahi, alo, N, Ha, Wa, a_plan["Ca"], whi, wlo, Co, plan["T"], _int_array(dr), _int_array(ds), 0, 0, Ho, Wo,
@@ -550,14 +602,15 @@ def _tc_conv_fwd(xh, weight, bias, plan, stride, pad, pad_mode, act_out, Ho, Wo,
     return y
 
 
-def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stats=None):
+def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stats=None, bwd_copy=False):
     """stride-2 transposed convolution (4 output phases) of `xh` with a ConvTranspose2d-layout weight;
     also the dgrad of a stride-2 Conv2d (whose (Cout, Cin, R, S) weight IS a ConvTranspose2d weight
     from Cout to Cin channels)."""
     _FWD["hw"] = Ho * Wo
     N, H, W, Ci = xh.shape
     _, Co, R, S = weight.shape
-    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO, dtype=dtype, need_lo=_passes(dtype) >= 2)     # zero halo of 1
+    ahi, alo, Ha, Wa = _tc_prep(xh, plan, 1, PAD_ZERO, dtype=dtype, need_lo=_passes(dtype) >= 2,     # zero halo of 1
+                                also_bf16=_bwd_copy_wanted(bwd_copy) and isinstance(xh, _Prepared))[:4]
     y = torch.empty((N, Ho, Wo, Co), device=xh.device, dtype=torch.float32)
     dr, ds = _int_array([0, 0, 1, 1]), _int_array([0, 1, 0, 1])
     Ht, Wt = (Ho + 1) // 2, (Wo + 1) // 2
@@ -689,7 +742,7 @@ def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, 
         _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
               _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
               Hb, Wb, _p(dwp), npass, f16, 1.0, -1)
-    _keep(mhi, mlo, ahi, alo, M.xh, A.xh)
+    _keep(mhi, mlo, ahi, alo, M.xh, A.xh, *getattr(M, "parts", ()), *getattr(A, "parts", ()))
     tgt = DIRECT_GRADS.get(weight.data_ptr())
     if tgt is not None:
         _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(tgt), 1)
@@ -807,7 +860,8 @@ class _Conv2d(Function):
                   _p(w if w.is_contiguous() else w.contiguous()), _p(b), R, S, pad, pad_mode, 0, act_out, _p(y))
         elif plan is not None:
             xin = _Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
-            y = _tc_conv_fwd(xin, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, stats=stats)
+            y = _tc_conv_fwd(xin, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, stats=stats,
+                             bwd_copy=ctx.needs_input_grad[1])
             if CONFIG["reuse_fwd_operand"] and ctx.needs_input_grad[1]:
                 ctx.xP = xin
         else:
@@ -948,7 +1002,7 @@ class _ConvTranspose2d(Function):
                   _p(w if w.is_contiguous() else w.contiguous()), _p(b), 4, 4, 1, PAD_ZERO, 1, act_out, _p(y))
         elif plan is not None:
             xin = _Prepared(xh) if pro is None else _Prepared(xh, prm, pro.act, pro.slope)
-            y = _tc_convT_fwd(xin, weight, b, plan, pad, act_out, Ho, Wo, stats=stats)
+            y = _tc_convT_fwd(xin, weight, b, plan, pad, act_out, Ho, Wo, stats=stats, bwd_copy=ctx.needs_input_grad[1])
             if CONFIG["reuse_fwd_operand"] and ctx.needs_input_grad[1]:
                 ctx.xP = xin        # its zero-haloed copy of x is the M operand of the weight-gradient GEMM
         else:
@@ -1020,11 +1074,6 @@ class _CatConv2d(Function):
         N, H, W, _ = hs[0].shape
         Cs = [h.shape[3] for h in hs]
         Ci = sum(Cs)
-        xh = torch.empty((N, H, W, Ci), device=hs[0].device, dtype=torch.float32)
-        off = 0
-        for h, c in zip(hs, Cs):
-            _call("dsr_copy_channels", _p(h), c, 0, _p(xh), Ci, off, c, N * H * W, 0)
-            off += c
         Co, Ci2, R, S = weight.shape
         if Ci2 != Ci:
             raise ValueError(f"conv2d: input has {Ci} channels, weight expects {Ci2}")
@@ -1033,17 +1082,28 @@ class _CatConv2d(Function):
             raise RuntimeError("internal error: cat_conv2d needs the tcgen05 path")
         Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
         b = bias.detach() if bias is not None else None
-        y = _tc_conv_fwd(xh, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo)
-        ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None, Cs)
+        if len(hs) <= 4 and CONFIG["fused_cat"]:
+            xin = _PreparedCat(hs)                      # the concatenation is never written: the operand prep reads the parts
+        else:
+            xh = torch.empty((N, H, W, Ci), device=hs[0].device, dtype=torch.float32)
+            off = 0
+            for h, c in zip(hs, Cs):
+                _call("dsr_copy_channels", _p(h), c, 0, _p(xh), Ci, off, c, N * H * W, 0)
+                off += c
+            xin = _Prepared(xh)
+            hs = [xh]
+        y = _tc_conv_fwd(xin, weight, b, plan, stride, pad, pad_mode, act_out, Ho, Wo, bwd_copy=ctx.needs_input_grad[0])
+        ctx.xP = xin if (CONFIG["reuse_fwd_operand"] and ctx.needs_input_grad[0]) else None
+        ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None, Cs, (N, H, W, Ci))
         ctx.bias_ref = bias
-        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None)
+        ctx.n_src = len(hs)
+        ctx.save_for_backward(weight, y if act_out == ACT_TANH else None, *hs)
         return nchw(y)
 
     @staticmethod
     def backward(ctx, gy):
-        xh, weight, y = ctx.saved_tensors
-        stride, pad, pad_mode, act_out, has_bias, Cs = ctx.cfg
-        N, H, W, Ci = xh.shape
+        weight, y, *hs = ctx.saved_tensors
+        stride, pad, pad_mode, act_out, has_bias, Cs, (N, H, W, Ci) = ctx.cfg
         Co, _, R, S = weight.shape
         g = nhwc(gy)
         if act_out == ACT_TANH:
@@ -1074,12 +1134,13 @@ class _CatConv2d(Function):
             _tc_wgrad_m_operand(gP, Co)
         with _on_side((need_w or need_b) and _use_side(weight if need_w else None, ctx.bias_ref if need_b else None), g.device):
             if need_w:
-                done, gw = _tc_conv_wgrad(_Prepared(xh), gP, weight, stride, pad, pad_mode)
+                xP = ctx.xP or (_PreparedCat(hs) if len(hs) == len(Cs) and len(Cs) > 1 else _Prepared(hs[0]))
+                done, gw = _tc_conv_wgrad(xP, gP, weight, stride, pad, pad_mode)
                 if not done:
                     raise RuntimeError("internal error: cat_conv2d weight gradient is not covered by the tcgen05 path")
             if need_b:
                 gb = _bias_grad(g, Co, ctx.bias_ref, gP)
-            _keep(g, gP.csum, xh)
+            _keep(g, gP.csum, *hs)
         return (gw, gb, None, None, None, None) + tuple(gxs)
 
 

@@ -10,9 +10,9 @@ world size (``model.tv_scale``) before the average.
 
 The arena is laid out in gradient-ready order (``main_model.ParamArena``), so bucket i is complete
 while the backward pass is still producing buckets i+1..; ``GradBuckets`` issues each bucket's
-all-reduce as soon as its last gradient kernel has been enqueued (``ops.GRAD_READY`` hook) with
-``async_op=True``: torch's NCCL process group runs the collective on its own stream behind an event
-of the compute stream, so it overlaps the rest of the backward pass; ``finish()`` joins before Adam.
+all-reduce as soon as its last gradient kernel has been enqueued (``ops.GRAD_READY`` hook) on a
+dedicated communication stream behind an event of the gradient-writing streams, so it overlaps the
+rest of the backward pass; ``finish()`` joins before Adam.
 The same sequence is legal under CUDA-graph capture (an event fork / join inside the captured step),
 so the graph-replayed step - the one bench.py times - overlaps exactly like the eager one.
 """
@@ -41,7 +41,7 @@ class GradBuckets:
         if ptrs:
             self.buckets.append((start, self.arena.total, ptrs))
         self.ptr_to_bucket = {q: i for i, (_, _, ps) in enumerate(self.buckets) for q in ps}
-        self.handles = []
+        self.comm, self.comm_used = None, False
         self._rearm()
         model.grad_sync = self
         model.optimizer_G.grad_scale = 1.0 / self.world      # all-reduce(sum), averaged inside Adam
@@ -60,10 +60,20 @@ class GradBuckets:
         self.launched[i] = True
         if self.world == 1:
             return
-        # async_op: the collective is enqueued on the process group's own stream behind an event of the current stream (the
-        # weight-gradient stream of ops._on_side, or the compute stream); nothing waits for it until finish()
+        view = self.arena.grad[s:e]
+        if not view.is_cuda:                       # gloo / CPU arena (tests): nothing to overlap with
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        # The collective is enqueued on a dedicated communication stream behind everything that has written gradients so
+        # far (the weight-gradient stream of ops._on_side and the compute stream); the compute stream does not wait for it
+        # until finish().  An event fork / join, so the same sequence is legal inside a CUDA-graph capture.
+        if self.comm is None:
+            self.comm = torch.cuda.Stream()
         ops.order_after_gradient_writers()
-        self.handles.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        self.comm_used = True
 
     def _ready(self, ptr):
         i = self.ptr_to_bucket.get(ptr)
@@ -88,9 +98,9 @@ class GradBuckets:
         for i in range(self.next, len(self.buckets)):
             if not self.launched[i]:
                 self._launch(i)
-        for h in self.handles:
-            h.wait()                    # the current stream waits for the collective's stream (an event join under capture)
-        self.handles = []
+        if self.comm_used:
+            torch.cuda.current_stream().wait_stream(self.comm)      # an event join under capture
+            self.comm_used = False
         self._rearm()
 
     def detach(self, model):
@@ -177,12 +187,21 @@ def dp_self_check(model, sync, batches, rects, group=None):
         torch.cuda.synchronize()
         return model.arena.grad.detach().clone() * model.optimizer_G.grad_scale, float(model.loss_G)
 
+    # Everything runs on the stream the training step will later be captured on: the autograd engine remembers the stream each
+    # node (incl. the parameters' gradient accumulators) was first built on and orders later backward passes against it -
+    # a first pass on another stream would plant a dependency on un-captured work into the capture.
+    if getattr(model, "_gstream", None) is None:
+        model._gstream = torch.cuda.Stream()
+    outer = torch.cuda.current_stream()
+    model._gstream.wait_stream(outer)
     try:
-        g_dp, loss_dp = grads(batches[rank], rects[rank])
-        sync.detach(model)
-        import numpy as np
-        full_rect = tuple(np.concatenate([r[i] for r in rects], 0) for i in range(4))
-        g_full, loss_full = grads(_cat_batches(batches), full_rect)
+        with torch.cuda.stream(model._gstream):
+            g_dp, loss_dp = grads(batches[rank], rects[rank])
+            sync.detach(model)
+            import numpy as np
+            full_rect = tuple(np.concatenate([r[i] for r in rects], 0) for i in range(4))
+            g_full, loss_full = grads(_cat_batches(batches), full_rect)
+        outer.wait_stream(model._gstream)
     finally:
         sync.attach(model)
         model.rect_override = None

@@ -241,8 +241,15 @@ int dsr_conv_s2_border_dgrad(const float* g, int N, int Ho, int Wo, int Co, cons
 #define DSR_TC_W_CONV_DGRAD 4
 #define DSR_TC_W_CONV_DGRAD_PAIR 5   /* stride-1 data gradient producing 2 adjacent pixels x Cin outputs per GEMM row (N = 2*Cin) */
 int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
-                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
+                int pad_mode, int layout, int Cp, void* A_hi, void* A_lo,
+                void* A_bf /* optional: the same operand once more as plain bf16 (read by the weight-gradient GEMM later) */,
+                int Ha, int Wa, int Ca, int f16,
                 double* csum /* optional: += per-channel sums of x (bias gradient of a dY), pre-zeroed */, void* stream);
+/* dsr_tc_prep over torch.cat((x0, x1, x2, x3), dim=1) (NULL / 0 = absent) without materialising the concatenation:
+ * models/main_model.py:305-306 (the 261-channel Task input), models/networks.py:629 (U-Net skip connections). */
+int dsr_tc_prep_cat(const float* x0, int C0, const float* x1, int C1, const float* x2, int C2, const float* x3, int C3, int N,
+                    int H, int W, int pad, int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa,
+                    int Ca, int f16, void* stream);
 int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, int variant, int Cp, int phase_a, int phase_b,
                        int pad, int Cout, int T, int Ca, void* W_hi, void* W_lo, int f16, float wscale, void* stream);
 int dsr_tc_gemm(const void* A_hi, const void* A_lo, int N, int Ha, int Wa, int Ca, const void* W_hi, const void* W_lo,
