@@ -465,6 +465,8 @@ class MainModel(BaseModel):
     def _step_body(self):                                           # main_model.py:425-429
         if self.device.type == "cuda":
             ops.zero_pool_reset(self.device)       # one memset for every accumulator of the step
+            if self.arena is not None:
+                ops.prepack(self.arena.params)     # packed copies of the trainable weights: side stream, beside the frozen nets
         self.forward()
         self.set_requires_grad([self.netG_A_d, self.netI2D_features, self.netImage2Depth], False)
         self.optimizer_G.zero_grad()

@@ -212,6 +212,7 @@ def join_side():
         for side in _SIDE["stream"].values():
             cur.wait_stream(side)
         _SIDE["forked"] = False
+        _SIDE["prepack_pending"] = False
     _SIDE["keep"] = []
 
 
@@ -277,6 +278,7 @@ CONFIG = {
                          #   gate margin is set by the dY that reaches the layer, not by the operand rounding.  Layers below
                          #   32^2 (latency-bound, no time to win) keep `passes`
     "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
+    "prepack": True,     # packed 16-bit copies of the trainable weights are re-made on the side stream at the top of the step
     "fwd_bf16_copy": True,   # forward operand prep of trainable layers also writes the bf16 copy the weight gradient reads
     "fused_cat": True,   # Conv2d over a LazyCat: the operand preparation reads the parts (no materialised concatenation)
     "side_wgrad": True,  # weight / bias gradients of arena parameters on a second stream beside the data-gradient chain
@@ -397,16 +399,56 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W, min_ci=16):
     return None
 
 
-def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None):
+def _remember_pack(weight, key, recipe):
+    """the packed copies a parameter needs per step, so that `prepack` can make all of them ahead of time on the side stream"""
+    if weight.data_ptr() in DIRECT_GRADS:
+        try:
+            rec = weight.__dict__.setdefault("_dsr_recipes", {})
+            rec[key] = recipe
+        except AttributeError:
+            pass
+
+
+def prepack(params):
+    """Re-make every packed 16-bit weight copy the previous step used (forward AND data-gradient variants of the trainable
+    nets), on the side stream: the ~60 small gather kernels overlap the frozen networks at the top of the step instead of
+    sitting on the critical path of the trainable forward / backward passes.  The first consumer joins the stream
+    (`_tc_weights` -> `_prepack_join`)."""
+    if not CONFIG["prepack"]:
+        return
+    todo = [(p, r) for p in params for r in getattr(p, "_dsr_recipes", {}).values()]
+    if not todo:
+        return
+    with _on_side(True, todo[0][0].device):
+        for w, (kind, plan, Co, phase, pad, dtype, npass) in todo:
+            if kind == "phases":
+                _tc_weights_phases(w, plan, Co, pad, dtype, npass=npass)
+            else:
+                _tc_weights(w, plan, Co, phase, pad, dtype, npass=npass)
+    _SIDE["prepack_pending"] = True
+
+
+def _prepack_join(weight):
+    if _SIDE.get("prepack_pending") and weight.data_ptr() in DIRECT_GRADS and \
+            torch.cuda.current_stream() == _SIDE.get("main"):
+        _SIDE["prepack_pending"] = False
+        join_side()
+
+
+def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None, npass=None):
     """bf16 hi/lo packed copy of a parameter, cached ON the parameter object until it changes
     (in-place updates bump ``_version``; the arena optimizer bumps WEIGHT_EPOCH)."""
-    npass = _passes(dtype)
+    prepacking = npass is not None
+    if not prepacking:
+        _prepack_join(weight)
+        npass = _passes(dtype)
     f16 = (dtype or CONFIG["dtype"]) == "f16"
     key = (plan["variant"], plan["Ca"], phase, pad, npass >= 3, f16)
     cache = _pack_cache(weight)
     hit = cache.get(key)
     if hit is not None:
         return hit
+    _remember_pack(weight, key, ("conv", dict(plan), Co, phase, pad, dtype, npass))
     D0, D1, R, S = weight.shape
     w = weight.detach()
     w = w if w.is_contiguous() else w.contiguous()
@@ -494,16 +536,19 @@ class _PreparedCat(_Prepared):
         return ahi, alo, Ha, Wa, abf
 
 
-def _tc_weights_phases(weight, plan, Co, pad, dtype=None):
+def _tc_weights_phases(weight, plan, Co, pad, dtype=None, npass=None):
     """the four output-phase weight matrices of a stride-2 transposed conv, stacked along rows ([4*Co][T*Ca]) so one GEMM
     launch serves all phases; cached on the parameter like _tc_weights"""
-    npass = _passes(dtype)
+    if npass is None:
+        _prepack_join(weight)
+        npass = _passes(dtype)
     f16 = (dtype or CONFIG["dtype"]) == "f16"
     key = ("phases", plan["Ca"], pad, npass >= 3, f16)
     cache = _pack_cache(weight)
     hit = cache.get(key)
     if hit is not None:
         return hit
+    _remember_pack(weight, key, ("phases", dict(plan), Co, None, pad, dtype, npass))
     D0, D1, R, S = weight.shape
     w = weight.detach()
     w = w if w.is_contiguous() else w.contiguous()
