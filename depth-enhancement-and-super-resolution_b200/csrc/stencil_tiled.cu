@@ -870,6 +870,18 @@ smooth_bwd_roll(const float* __restrict__ d, const float* __restrict__ img, int 
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
+// warp-strip rolling-row forms (csrc/stencil_roll.cu): 1 = launched, 0 = shape does not suit (ragged rows), take the quads
+int dsr_roll_normals_old_fwd(const float* d, int B, int H, int W, float scale, float* out, void* stream);
+int dsr_roll_normals_old_bwd(const float* d, const float* g, int B, int H, int W, float scale, float* gd, void* stream);
+int dsr_roll_normals_new_fwd(const float* d, const double* cams, int B, int H, int W, float* out, void* stream);
+int dsr_roll_normals_new_bwd(const float* d, const float* g, const double* cams, int B, int H, int W, float* gd, void* stream);
+int dsr_roll_tv_fwd(const float* x, long planes, int H, int W, double* out, void* stream);
+static bool use_roll() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DSR_STENCIL_ROLL"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 #define PLANES_OK(B, H, W) ((long)(B) <= 65535 && (((H) + TH - 1) / TH) <= 65535 && (long)(B) * (((H) + TH - 1) / TH) * (((W) + TW - 1) / TW) < (1L << 31) && (long)(H) * (W) < (1L << 31))
 
 extern "C" int dsr_hole_valid_masks(const float* depth, int B, int H, int W, float border, float* hole,
@@ -892,30 +904,35 @@ extern "C" int dsr_rect_holes(const float* valid, const float* depth, const int*
 
 extern "C" int dsr_normals_old_fwd(const float* depth, int B, int H, int W, float scale, float* out, void* stream) {
     DSR_REQUIRE(depth && out && B > 0 && H >= 2 && W >= 2 && PLANES_OK(B, H, W), "bad arguments");
+    if (use_roll() && dsr_roll_normals_old_fwd(depth, B, H, W, scale, out, stream)) return dsr_check_launch("normals_old_fwd");
     normals_old_fwd_quad<<<quad_grid(B, H, W), NT, 0, ST(stream)>>>(depth, H, W, scale, out);
     return dsr_check_launch("normals_old_fwd");
 }
 extern "C" int dsr_normals_old_bwd(const float* depth, const float* gout, int B, int H, int W, float scale,
                                    float* gdepth, void* stream) {
     DSR_REQUIRE(depth && gout && gdepth && B > 0 && H >= 2 && W >= 2 && PLANES_OK(B, H, W), "bad arguments");
+    if (use_roll() && dsr_roll_normals_old_bwd(depth, gout, B, H, W, scale, gdepth, stream)) return dsr_check_launch("normals_old_bwd");
     normals_old_bwd_quad<<<quad_grid(B, H, W), NT, 0, ST(stream)>>>(depth, gout, H, W, scale, gdepth);
     return dsr_check_launch("normals_old_bwd");
 }
 extern "C" int dsr_normals_new_fwd(const float* depth, const double* cams, int B, int H, int W, float* out,
                                    void* stream) {
     DSR_REQUIRE(depth && cams && out && B > 0 && H >= 2 && W >= 2 && PLANES_OK(B, H, W), "bad arguments");
+    if (use_roll() && dsr_roll_normals_new_fwd(depth, cams, B, H, W, out, stream)) return dsr_check_launch("normals_new_fwd");
     normals_new_fwd_quad<<<quad_grid(B, H, W), NT, 0, ST(stream)>>>(depth, cams, H, W, out);
     return dsr_check_launch("normals_new_fwd");
 }
 extern "C" int dsr_normals_new_bwd(const float* depth, const float* gout, const double* cams, int B, int H, int W,
                                    float* gdepth, void* stream) {
     DSR_REQUIRE(depth && gout && cams && gdepth && B > 0 && H >= 2 && W >= 2 && PLANES_OK(B, H, W), "bad arguments");
+    if (use_roll() && dsr_roll_normals_new_bwd(depth, gout, cams, B, H, W, gdepth, stream)) return dsr_check_launch("normals_new_bwd");
     normals_new_bwd_quad<<<quad_grid(B, H, W), NT, 0, ST(stream)>>>(depth, gout, cams, H, W, gdepth);
     return dsr_check_launch("normals_new_bwd");
 }
 
 extern "C" int dsr_tv_fwd(const float* x, long planes, int H, int W, double* out_sum, void* stream) {
     DSR_REQUIRE(x && out_sum && planes > 0 && H > 0 && W > 0 && PLANES_OK(planes, H, W), "bad arguments");
+    if (use_roll() && dsr_roll_tv_fwd(x, planes, H, W, out_sum, stream)) return dsr_check_launch("tv_fwd");
     tv_fwd_quad<<<dim3((W + TW - 1) / TW, (H + STRIP - 1) / STRIP, (unsigned)planes), NT, 0, ST(stream)>>>(x, H, W, out_sum);
     return dsr_check_launch("tv_fwd");
 }

@@ -7,7 +7,7 @@ time (CUDA events on the launching stream, 3 warm-up + `iters` launches back to 
 import torch
 
 
-def run(batch=96, iters=20, peak=6540.8, device=0, verbose=False):
+def run(batch=96, iters=20, peak=6540.8, device=0, verbose=False, only=None):
     from . import _lib, ops
     from .norms import camera_table
     _lib.load()
@@ -84,6 +84,8 @@ def run(batch=96, iters=20, peak=6540.8, device=0, verbose=False):
     call("dsr_norm_finalize", p64(sums), Bn, C, H * W, 0, None, None, 1e-5, p(prm))
     rows = []
     for name, nbytes, fn in cases:
+        if only and not any(o in name for o in only):
+            continue
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

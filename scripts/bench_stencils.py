@@ -24,13 +24,14 @@ def main():
     ap.add_argument("--batch", type=int, default=96)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="comma-separated substrings of the case names to run")
     args = ap.parse_args()
     from dsr_b200 import stencil_bench
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
-    res = stencil_bench.run(args.batch, args.iters, peak, verbose=True)
+    res = stencil_bench.run(args.batch, args.iters, peak, verbose=True, only=[o for o in args.only.split(',') if o] or None)
     if args.out:
         json.dump(res, open(args.out, "w"), indent=1)
 

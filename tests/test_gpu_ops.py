@@ -138,6 +138,43 @@ def test_normals_new_mixed_cameras(ops):
     assert np.allclose(dc.grad.cpu().numpy(), d.grad.numpy(), rtol=2e-3, atol=1e-3 * float(d.grad.abs().median()))
 
 
+# warp-strip / row-band rolling kernels (csrc/stencil_roll.cu): shapes with several 128-column strips per row, a last strip that
+# is only partly filled, one-strip rows, and chunks of rows that do not divide H - all against the CPU oracle
+ROLL_SHAPES = [(3, 24, 640), (2, 33, 260), (1, 70, 132), (2, 9, 1024), (2, 17, 4), (1, 300, 128)]
+
+
+@pytest.mark.parametrize("BHW", ROLL_SHAPES)
+def test_rolling_normals_and_tv_wide_rows(ops, BHW):
+    from dsr_b200.norms import camera_table
+    B, H, W = BHW
+    d = _smooth_depth(B, max(H, 16), max(W, 16), 31)[:, :, :H, :W].contiguous().clamp_min(-0.9)
+    d = (d + 0.02 * torch.randn(B, 1, H, W, generator=G(32))).requires_grad_(True)
+    go = torch.randn(B, 3, H, W, generator=G(33))
+    K = torch.tensor([[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]], dtype=torch.float64).repeat(B, 1, 1)
+    crop = torch.tensor([[7, 7 + H, 11, 11 + W]] * B)
+    # image-space normals
+    ref = ref_ops.surface_normals_old(d) * 100
+    (ref * go).sum().backward()
+    g_ref, d.grad = d.grad.clone(), None
+    dc = d.detach().cuda().requires_grad_(True)
+    out = ops.normals_old(dc, 100.0)
+    (out * go.cuda()).sum().backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max() <= 1e-4
+    assert rel_l2(dc.grad.cpu(), g_ref) <= 1e-4
+    # camera-space normals
+    ref = ref_ops.surface_normals_new(d, K, crop)
+    (ref * go).sum().backward()
+    g_ref, d.grad = d.grad.clone(), None
+    dc = d.detach().cuda().requires_grad_(True)
+    out = ops.normals_new(dc, camera_table(K, crop, 0.5, "cuda"))
+    (out * go.cuda()).sum().backward()
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= 2e-6
+    assert np.allclose(dc.grad.cpu().numpy(), g_ref.numpy(), rtol=2e-3, atol=1e-3 * float(g_ref.abs().median()))
+    # TV
+    x = torch.randn(B, 3, H, W, generator=G(34))
+    assert abs(float(ops.tv_loss(x.cuda())) - float(ref_ops.tv_loss(x))) <= 1e-5 * float(ref_ops.tv_loss(x))
+
+
 def test_tv_fwd_bwd(ops):
     x = torch.randn(2, 3, 37, 53, generator=G(8)).requires_grad_(True)
     ref = ref_ops.tv_loss(x)
