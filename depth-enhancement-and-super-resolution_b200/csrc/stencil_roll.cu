@@ -11,10 +11,11 @@
 //     of the previous / next iteration; the next iteration's loads are issued before this iteration's math);
 //   * the column neighbours x[j-1] / x[j+4] come from the adjacent lanes by warp shuffle (one scalar load at a strip seam);
 //   * backward: a pixel's adjoint is split into what it adds to its right / left / lower / upper neighbour (R, L, Dn, Up);
-//     R / L travel between lanes by shuffle, Dn / Up between rows in registers - no shared memory, no barrier.  The two
-//     pixels just outside the strip whose R / L the edge lanes need are recomputed by lanes 0 and 31 (1/4 more math on
-//     that warp, no extra lanes);
-//   * the B * H rows are cut into chunks so that all warp tasks fit ONE wave of resident warps (no tail wave).
+//     R / L travel between lanes by shuffle, Dn / Up between rows in registers; the backward kernels run as ROW BANDS (one
+//     CTA = all strips of a band of rows) so that the seam values cross warps through 16 floats of shared memory and one
+//     barrier per row (the first strip version recomputed the seam pixels in lanes 0 / 31: 100 of 660 instructions per row);
+//   * loads travel through per-thread cp.async slots (RowPipe), math runs on packed fp32 pairs (FFMA2 / FMUL2);
+//   * the B * H rows are cut into chunks so that all tasks fit whole waves of resident warps / CTAs (no tail wave).
 #include <stdlib.h>
 #include "common.cuh"
 #include "stencil_math.cuh"
@@ -101,70 +102,7 @@ __device__ __forceinline__ float right_nb(const float4 v, const float* __restric
 }
 __device__ __forceinline__ float edge_half(int i, int n) { return (i == 0 || i == n - 1) ? 1.f : 0.5f; }
 
-// ------------------------------------------------------------------------------------------
-// per-pixel operators.  fwd(e, dl, dr, du, dd, masks, fh, fw) -> n[3];  adj(..., g) -> (R, L, Dn, Up)
-// `e` = column offset of the pixel from the lane's first column (-1 / 4 for the seam pixels)
-// ------------------------------------------------------------------------------------------
-struct OldOp {                                   // image-space normals, norms.py:185-190
-    float scale;
-    __device__ __forceinline__ bool begin(int) { return true; }
-    __device__ __forceinline__ void row_begin(int, int) {}
-    __device__ __forceinline__ void row_next() {}
-    __device__ __forceinline__ void fwd(int, float dl, float dr, float du, float dd, float, float, float, float, float fh, float fw,
-                                        float n[3]) const {
-        const float gh = (dd - du) * fh, gw = (dr - dl) * fw;
-        const float r = sqrtf(gh * gh + gw * gw + 1.f);
-        const float k = scale / (r + 1e-6f);
-        n[0] = -gh * k; n[1] = -gw * k; n[2] = k;
-    }
-    __device__ __forceinline__ void adj(int, float dl, float dr, float du, float dd, float, float, float, float, float fh, float fw,
-                                        float g0, float g1, float g2, float& R, float& L, float& Dn, float& Up) const {
-        const float gh = (dd - du) * fh, gw = (dr - dl) * fw;
-        const float r2 = gh * gh + gw * gw + 1.f;
-        const float ir = rsqrtf(r2), r = r2 * ir;
-        const float iden = __fdividef(1.f, r + 1e-6f);
-        const float dn0 = g0 * scale, dn1 = g1 * scale, dn2 = g2 * scale;
-        const float dot = dn2 - dn0 * gh - dn1 * gw;
-        const float k = dot * ir * iden * iden;
-        const float dgh = -(dn0 * iden + k * gh) * fh, dgw = -(dn1 * iden + k * gw) * fw;
-        Dn = dgh; Up = -dgh; R = dgw; L = -dgw;
-    }
-};
-struct NewOp {                                   // camera-space normals, closed fp32 form (stencil_math.cuh aff_*)
-    const double* cams;
-    const double* cam;
-    AffCam c;
-    float rx0, ry0;
-    double rxd, ryd, k1d, k4d;                   // ray of the lane's first pixel in the current row, advanced in fp64 (exact to
-                                                 // 1e-16: the fp32 copies equal the per-row evaluation up to a rounding tie)
-    __device__ __forceinline__ bool begin(int pl) {
-        cam = cams + (long)pl * DSR_CAM_DOUBLES;
-        c = aff_cam(cam);
-        return cam_is_affine(cam);
-    }
-    __device__ __forceinline__ void row_begin(int i, int j) {
-        const double u = cam[9] + (double)j, v = cam[10] + (double)i;
-        k1d = cam[1]; k4d = cam[4];
-        rxd = cam[0] * u + k1d * v + cam[2];
-        ryd = cam[3] * u + k4d * v + cam[5];
-        rx0 = (float)rxd; ry0 = (float)ryd;
-    }
-    __device__ __forceinline__ void row_next() {
-        rxd += k1d; ryd += k4d;
-        rx0 = (float)rxd; ry0 = (float)ryd;
-    }
-    __device__ __forceinline__ void fwd(int e, float dl, float dr, float du, float dd, float ma, float mb, float mu, float md, float fh,
-                                        float fw, float n[3]) const {
-        float Du, Su, Dv, Sv, m[3];
-        aff_terms(dl, dr, du, dd, ma, mb, mu, md, Du, Su, Dv, Sv);
-        aff_normal_m(c, rx0 + (float)e * c.k0, ry0 + (float)e * c.k3, Du, Su, Dv, Sv, fh * fw, m);
-        aff_normalize(m, n);
-    }
-    __device__ __forceinline__ void adj(int e, float dl, float dr, float du, float dd, float ma, float mb, float mu, float md, float fh,
-                                        float fw, float g0, float g1, float g2, float& R, float& L, float& Dn, float& Up) const {
-        aff_pixel_adj(c, rx0 + (float)e * c.k0, ry0 + (float)e * c.k3, dl, dr, du, dd, ma, mb, mu, md, fh * fw, g0, g1, g2, R, L, Dn, Up);
-    }
-};
+// per-pixel fp64 reference form for cameras with a perspective row in K^-1 (never a pin-hole K): slow, exact, block-uniform
 __device__ __noinline__ void roll_generic_fwd(const float* __restrict__ p, const double* __restrict__ cam, int H, int W, const Task& t,
                                               float* __restrict__ o, long plane) {
     if (!t.act) return;
@@ -193,232 +131,38 @@ __device__ __noinline__ void roll_generic_bwd(const float* __restrict__ p, const
 // ------------------------------------------------------------------------------------------
 template <int NV, int NS, int DEPTH, int NT = RNT>
 struct RowPipe {
-    uint32_t vbase, sbase;
+    uint32_t vbase, sbase, ustride, wstride;                          // byte strides between units / words of one slot
     static constexpr int bytes(int nt = NT) { return DEPTH * (NV * 16 + NS * 4) * nt; }
-    int nt;                                                          // threads per CTA (NT == 0: blockDim.x)
     __device__ __forceinline__ RowPipe() {
         extern __shared__ __align__(16) unsigned char roll_smem[];
         const uint32_t b = (uint32_t)__cvta_generic_to_shared(roll_smem);
-        nt = NT ? NT : (int)blockDim.x;
+        const int nt = NT ? NT : (int)blockDim.x;                     // threads per CTA (NT == 0: blockDim.x)
+        ustride = nt * 16; wstride = nt * 4;
         vbase = b + threadIdx.x * 16;
         sbase = b + DEPTH * NV * 16 * nt + threadIdx.x * 4;
     }
+    __device__ __forceinline__ uint32_t vslot(int slot) const { return vbase + slot * NV * ustride; }
+    __device__ __forceinline__ uint32_t sslot(int slot) const { return sbase + slot * NS * wstride; }
     __device__ __forceinline__ void cp16(int slot, int u, const float* src, bool valid) const {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vbase + (slot * NV + u) * (nt * 16)), "l"(src), "r"(valid ? 16 : 0));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vslot(slot) + u * ustride), "l"(src), "r"(valid ? 16 : 0));
     }
     __device__ __forceinline__ void cp4(int slot, int w, const float* src, bool valid) const {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + (slot * NS + w) * (nt * 4)), "l"(src), "r"(valid ? 4 : 0));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sslot(slot) + w * wstride), "l"(src), "r"(valid ? 4 : 0));
     }
     __device__ __forceinline__ float4 v(int slot, int u) const {
         float4 r;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(vbase + (slot * NV + u) * (nt * 16)));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(vslot(slot) + u * ustride));
         return r;
     }
     __device__ __forceinline__ float s(int slot, int w) const {
         float r;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(sbase + (slot * NS + w) * (nt * 4)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(sslot(slot) + w * wstride));
         return r;
     }
     __device__ __forceinline__ static void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
     __device__ __forceinline__ static void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory"); }
 };
 __device__ __forceinline__ int clampi(int v, int n) { return min(max(v, 0), n - 1); }
-
-// ------------------------------------------------------------------------------------------
-// forward: depth (planes, H, W) -> normals (planes, 3, H, W).  Pipe row k = depth row k + 1 (+ its seam neighbour)
-// ------------------------------------------------------------------------------------------
-#define FWD_DEPTH 6
-template <class OP, bool NEW, int MINB>
-__global__ void __launch_bounds__(RNT, MINB)
-normals_fwd_roll(const float* __restrict__ d, OP op, int H, int W, RollPlan pl, float* __restrict__ out) {
-    Task t;
-    if (!roll_task(pl, H, W, t)) return;
-    const long plane = (long)H * W;
-    const float* p = d + t.pl * plane;
-    float* o = out + (long)t.pl * 3 * plane;
-    if (!op.begin(t.pl)) {
-        if constexpr (NEW) roll_generic_fwd(p, op.cam, H, W, t, o, plane);
-        return;
-    }
-    const RowPipe<1, 1, FWD_DEPTH> pipe;
-    const bool seamL = t.lane == 0 && t.j > 0, seamR = t.lane == 31 && t.j + 4 < W, seam = seamL || seamR;
-    const int jn = seamL ? t.j - 1 : (seamR ? t.j + 4 : 0);          // the seam lane's neighbour column
-    const int jc = t.act ? t.j : 0;
-    auto issue = [&](int k, int slot) {                              // 32-bit offsets inside the plane (H * W < 2^31)
-        if (k < t.i1) {
-            const int od = clampi(k + 1, H) * W;
-            pipe.cp16(slot, 0, p + (od + jc), t.act);
-            if (seam) pipe.cp4(slot, 0, p + (od + jn), true);
-        }
-        pipe.commit();
-    };
-#pragma unroll
-    for (int k = 0; k < FWD_DEPTH; ++k) issue(t.i0 + k, k);
-    float4 dU = ldrow(p, t.i0 - 1, H, W, t), dC = ldrow(p, t.i0, H, W, t);
-    float sC = seam ? __ldg(p + (long)t.i0 * W + jn) : 0.f;
-    const bool colin = t.j > 0 && t.j + 4 < W;
-    op.row_begin(t.i0, t.j);
-    int slot = 0;
-    for (int r = t.i0; r < t.i1; ++r) {
-        pipe.wait();
-        const float4 dD = pipe.v(slot, 0);
-        const float sD = pipe.s(slot, 0);
-        issue(r + FWD_DEPTH, slot);
-        slot = slot + 1 == FWD_DEPTH ? 0 : slot + 1;
-        float xl = __shfl_up_sync(FULL, dC.w, 1), xr = __shfl_down_sync(FULL, dC.x, 1);
-        if (t.lane == 0) xl = seamL ? sC : dC.x;
-        if (t.j + 4 >= W) xr = dC.w; else if (t.lane == 31) xr = sC;
-        const float c[6] = {xl, dC.x, dC.y, dC.z, dC.w, xr};
-        const float u[4] = {dU.x, dU.y, dU.z, dU.w}, l[4] = {dD.x, dD.y, dD.z, dD.w};
-        float n0[4], n1[4], n2[4];
-        if (colin && r > 0 && r < H - 1) {                           // no image border in reach: literal masks / factors
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float n[3];
-                op.fwd(e, c[e], c[e + 2], u[e], l[e], 1.f, 1.f, 1.f, 1.f, 0.5f, 0.5f, n);
-                n0[e] = n[0]; n1[e] = n[1]; n2[e] = n[2];
-            }
-        } else {
-            const float mu = r > 0 ? 1.f : 0.f, md = r < H - 1 ? 1.f : 0.f, fh = edge_half(r, H);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = t.j + e;
-                float n[3];
-                op.fwd(e, c[e], c[e + 2], u[e], l[e], j > 0 ? 1.f : 0.f, j < W - 1 ? 1.f : 0.f, mu, md, fh, edge_half(j, W), n);
-                n0[e] = n[0]; n1[e] = n[1]; n2[e] = n[2];
-            }
-        }
-        if (t.act) {
-            float* q = o + (long)r * W + t.j;
-            st4(q, make_float4(n0[0], n0[1], n0[2], n0[3]));
-            st4(q + plane, make_float4(n1[0], n1[1], n1[2], n1[3]));
-            st4(q + 2 * plane, make_float4(n2[0], n2[1], n2[2], n2[3]));
-        }
-        dU = dC; dC = dD; sC = sD;
-        op.row_next();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// backward: (depth, dL/dn) -> dL/ddepth.  gd(i, j) = R(i, j-1) + L(i, j+1) + Dn(i-1, j) + Up(i+1, j) + the pixel's own term
-// where its neighbour was border-clamped onto itself.  Pipe row k = depth row k + 1 and the three gradient rows k, plus for
-// the seam lanes depth[k+1][js], depth[k+1][jo] (js = the pixel just outside the strip, jo = its outer neighbour) and g[k][js].
-// ------------------------------------------------------------------------------------------
-#define BWD_DEPTH 3
-template <class OP, bool NEW, int MINB>
-__global__ void __launch_bounds__(RNT, MINB)
-normals_bwd_roll(const float* __restrict__ d, const float* __restrict__ g, OP op, int H, int W, RollPlan pl, float* __restrict__ gd) {
-    Task t;
-    if (!roll_task(pl, H, W, t)) return;
-    const long plane = (long)H * W;
-    const float* p = d + t.pl * plane;
-    const float* gp = g + (long)t.pl * 3 * plane;
-    float* o = gd + t.pl * plane;
-    if (!op.begin(t.pl)) {
-        if constexpr (NEW) roll_generic_bwd(p, gp, op.cam, H, W, t, o, plane);
-        return;
-    }
-    const RowPipe<4, 5, BWD_DEPTH> pipe;
-    const bool seamL = t.lane == 0 && t.j > 0, seamR = t.lane == 31 && t.j + 4 < W, seam = seamL || seamR;
-    const int js = seamL ? t.j - 1 : (seamR ? t.j + 4 : 0), es = seamL ? -1 : 4;
-    const int jo = seamL ? max(js - 1, 0) : min(js + 1, W - 1);
-    const int jc = t.act ? t.j : 0;
-    const bool colin = t.j > 0 && t.j + 4 < W;
-    const int r0 = t.i0 - 1;
-    const float* gp1 = gp + plane;
-    const float* gp2 = gp1 + plane;
-    auto issue = [&](int k, int slot) {                              // 32-bit offsets inside the plane (H * W < 2^31)
-        if (k <= t.i1) {
-            const int od = clampi(k + 1, H) * W, og = clampi(k, H) * W;
-            const bool gin = (unsigned)k < (unsigned)H, ga = gin && t.act;
-            pipe.cp16(slot, 0, p + (od + jc), t.act);
-            pipe.cp16(slot, 1, gp + (og + jc), ga);
-            pipe.cp16(slot, 2, gp1 + (og + jc), ga);
-            pipe.cp16(slot, 3, gp2 + (og + jc), ga);
-            if (seam) {
-                pipe.cp4(slot, 0, p + (od + js), true);
-                pipe.cp4(slot, 1, p + (od + jo), true);
-                pipe.cp4(slot, 2, gp + (og + js), gin);
-                pipe.cp4(slot, 3, gp1 + (og + js), gin);
-                pipe.cp4(slot, 4, gp2 + (og + js), gin);
-            }
-        }
-        pipe.commit();
-    };
-#pragma unroll
-    for (int k = 0; k < BWD_DEPTH; ++k) issue(r0 + k, k);
-    float4 dU = ldrow(p, r0 - 1, H, W, t), dC = ldrow(p, r0, H, W, t);
-    float sU = 0.f, sC = 0.f, sO = 0.f;                                // seam column: rows r - 1, r at js; row r at jo
-    if (seam) {
-        sU = __ldg(p + (long)clampi(r0 - 1, H) * W + js);
-        sC = __ldg(p + (long)clampi(r0, H) * W + js);
-        sO = __ldg(p + (long)clampi(r0, H) * W + jo);
-    }
-    float Hp[4] = {0.f, 0.f, 0.f, 0.f}, DnP[4] = {0.f, 0.f, 0.f, 0.f}, DnPP[4] = {0.f, 0.f, 0.f, 0.f};
-    op.row_begin(r0, t.j);
-    int slot = 0;
-    for (int r = r0; r <= t.i1; ++r) {
-        pipe.wait();
-        const float4 dD = pipe.v(slot, 0), G0 = pipe.v(slot, 1), G1 = pipe.v(slot, 2), G2 = pipe.v(slot, 3);
-        const float sD = pipe.s(slot, 0), sOn = pipe.s(slot, 1), sg0 = pipe.s(slot, 2), sg1 = pipe.s(slot, 3), sg2 = pipe.s(slot, 4);
-        issue(r + BWD_DEPTH, slot);
-        slot = slot + 1 == BWD_DEPTH ? 0 : slot + 1;
-        float R[4] = {0.f, 0.f, 0.f, 0.f}, L[4] = {0.f, 0.f, 0.f, 0.f}, Dn[4] = {0.f, 0.f, 0.f, 0.f}, Up[4] = {0.f, 0.f, 0.f, 0.f};
-        float Rs = 0.f, Ls = 0.f;
-        if (r >= 0 && r < H) {                                        // warp-uniform
-            float xl = __shfl_up_sync(FULL, dC.w, 1), xr = __shfl_down_sync(FULL, dC.x, 1);
-            if (t.lane == 0) xl = seamL ? sC : dC.x;
-            if (t.j + 4 >= W) xr = dC.w; else if (t.lane == 31) xr = sC;
-            const float c[6] = {xl, dC.x, dC.y, dC.z, dC.w, xr};
-            const float u[4] = {dU.x, dU.y, dU.z, dU.w}, l[4] = {dD.x, dD.y, dD.z, dD.w};
-            const float g0[4] = {G0.x, G0.y, G0.z, G0.w}, g1[4] = {G1.x, G1.y, G1.z, G1.w}, g2[4] = {G2.x, G2.y, G2.z, G2.w};
-            const float mu = r > 0 ? 1.f : 0.f, md = r < H - 1 ? 1.f : 0.f, fh = edge_half(r, H);
-            if (colin && r > 0 && r < H - 1) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    op.adj(e, c[e], c[e + 2], u[e], l[e], 1.f, 1.f, 1.f, 1.f, 0.5f, 0.5f, g0[e], g1[e], g2[e], R[e], L[e], Dn[e], Up[e]);
-            } else if (t.act) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = t.j + e;
-                    op.adj(e, c[e], c[e + 2], u[e], l[e], j > 0 ? 1.f : 0.f, j < W - 1 ? 1.f : 0.f, mu, md, fh, edge_half(j, W),
-                           g0[e], g1[e], g2[e], R[e], L[e], Dn[e], Up[e]);
-                }
-            }
-            if (seam) {                                               // the pixel just outside the strip (lanes 0 / 31)
-                const float sl = seamL ? sO : dC.w, sr = seamL ? dC.x : sO;
-                float a, b, cc, dd;
-                op.adj(es, sl, sr, sU, sD, js > 0 ? 1.f : 0.f, js < W - 1 ? 1.f : 0.f, mu, md, fh, edge_half(js, W), sg0, sg1, sg2,
-                       a, b, cc, dd);
-                Rs = seamL ? a : 0.f;
-                Ls = seamR ? b : 0.f;
-            }
-        }
-        // horizontal exchange (all lanes): R of the pixel on the left, L of the pixel on the right
-        float Rl = __shfl_up_sync(FULL, R[3], 1), Lr = __shfl_down_sync(FULL, L[0], 1);
-        if (t.lane == 0) Rl = Rs;
-        if (t.lane == 31) Lr = Ls;
-        float Hs[4] = {Rl + L[1], R[0] + L[2], R[1] + L[3], R[2] + Lr};
-        if (t.j == 0) Hs[0] += L[0];
-        if (t.j + 4 == W) Hs[3] += R[3];
-        if (r == 0) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) Hs[e] += Up[e];
-        }
-        if (r == H - 1) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) Hs[e] += Dn[e];
-        }
-        if (r > t.i0 && t.act)                                        // row r - 1 is complete
-            st4(o + (long)(r - 1) * W + t.j,
-                make_float4(Hp[0] + DnPP[0] + Up[0], Hp[1] + DnPP[1] + Up[1], Hp[2] + DnPP[2] + Up[2], Hp[3] + DnPP[3] + Up[3]));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { DnPP[e] = DnP[e]; DnP[e] = Dn[e]; Hp[e] = Hs[e]; }
-        dU = dC; dC = dD; sU = sC; sC = sD; sO = sOn;
-        op.row_next();
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------
 // Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot).  The stencil kernels are bound by
@@ -437,45 +181,55 @@ __device__ __forceinline__ f2 sub(f2 a, f2 b) { return fma(b, bc(-1.f), a); }
 __device__ __forceinline__ f2 inv_len(f2 r2) { return mk(rsqrtf(fmaxf(r2.v.x, 1e-24f)), rsqrtf(fmaxf(r2.v.y, 1e-24f))); }
 __device__ __forceinline__ f2 keep_if_gt(f2 r2, float thr, f2 a) { return mk(r2.v.x > thr ? a.v.x : 0.f, r2.v.y > thr ? a.v.y : 0.f); }
 
-// per-plane / per-row constants of the camera-space adjoint, as broadcast pairs
+// per-plane constants of the camera-space normals, as broadcast pairs
 struct AffPair {
     f2 k0, k4, nk1, nk3, D;
     __device__ __forceinline__ void set(const AffCam& c) { k0 = bc(c.k0); k4 = bc(c.k4); nk1 = bc(-c.k1); nk3 = bc(-c.k3); D = bc(c.D); }
 };
-// Border handling without branches: hma / hmb = 0.5 * (left / right neighbour is a real pixel), hmab = hma + hmb, likewise
-// hmu / hmd / hmud for the rows; sc = product of np.gradient's 1/2 (interior) or 1 (border) factors.
-// m = Pv x Pu of stencil_math.cuh (aff_normal_m) for a pair of pixels
-__device__ __forceinline__ void aff_m_pair(const AffPair& k, f2 nrx, f2 nry, f2 dl, f2 dr, f2 du, f2 dd, f2 hma, f2 hmb, f2 hmab, f2 hmu,
-                                           f2 hmd, f2 hmud, f2 sc, f2& Du, f2& Su, f2& Dv, f2& Sv, f2& m0, f2& m1, f2& m2) {
-    const f2 h = bc(0.5f);
-    Du = mul(h, sub(dr, dl));
-    Su = fma(hmb, dr, fma(hma, dl, hmab));
-    Dv = mul(h, sub(dd, du));
-    Sv = fma(hmd, dd, fma(hmu, du, hmud));
+// The closed form of stencil_math.cuh (aff_terms / aff_normal_m) with its POWER-OF-TWO factors dropped: m is bilinear in
+// (Du, Su, Dv, Sv), each of which carries np.gradient's / the depth map's 1/2, and `sc` (1, 1/2 or 1/4) multiplies all of m,
+// so m here = 4 m_ref / sc EXACTLY (scaling by a power of two), the unit normal is unchanged, and in the adjoint the factors
+// cancel between dn/dm (1 / |m|) and dm/dd.  Only the clamp of norms.py:103 (|m_ref| < 1e-12) sees the scale: its threshold
+// becomes thr = 16e-24 / sc^2 on |m|^2, which reproduces n = m_ref * 1e12 for degenerate pixels.
+// Borders without branches: ma / mb = 1 when the left / right neighbour is a real pixel (0: clamped onto the pixel itself),
+// mab = ma + mb, likewise mu / md / mud for the rows.
+__device__ __forceinline__ void aff_m_pair(const AffPair& k, f2 nrx, f2 nry, f2 dl, f2 dr, f2 du, f2 dd, f2 ma, f2 mb, f2 mab, f2 mu,
+                                           f2 md, f2 mud, f2& Du, f2& Su, f2& Dv, f2& Sv, f2& m0, f2& m1, f2& m2) {
+    Du = sub(dr, dl);
+    Su = fma(mb, dr, fma(ma, dl, mab));
+    Dv = sub(dd, du);
+    Sv = fma(md, dd, fma(mu, du, mud));
     const f2 A = mul(Su, Dv), B = mul(Sv, Du);
-    m0 = mul(sc, fma(k.k4, B, mul(k.nk3, A)));
-    m1 = mul(sc, fma(k.k0, A, mul(k.nk1, B)));
-    m2 = fma(nrx, m0, fma(nry, m1, mul(mul(sc, k.D), mul(Su, Sv))));
+    m0 = fma(k.k4, B, mul(k.nk3, A));
+    m1 = fma(k.k0, A, mul(k.nk1, B));
+    m2 = fma(nrx, m0, fma(nry, m1, mul(k.D, mul(Su, Sv))));
+}
+__device__ __forceinline__ f2 inv_len_thr(f2 r2, f2 thr) { return mk(rsqrtf(fmaxf(r2.v.x, thr.v.x)), rsqrtf(fmaxf(r2.v.y, thr.v.y))); }
+__device__ __forceinline__ void aff_fwd_pair(const AffPair& k, f2 nrx, f2 nry, f2 dl, f2 dr, f2 du, f2 dd, f2 ma, f2 mb, f2 mab, f2 mu,
+                                             f2 md, f2 mud, f2 thr, f2& n0, f2& n1, f2& n2) {
+    f2 Du, Su, Dv, Sv, m0, m1, m2;
+    aff_m_pair(k, nrx, nry, dl, dr, du, dd, ma, mb, mab, mu, md, mud, Du, Su, Dv, Sv, m0, m1, m2);
+    const f2 ir = inv_len_thr(fma(m0, m0, fma(m1, m1, mul(m2, m2))), thr);
+    n0 = mul(m0, ir); n1 = mul(m1, ir); n2 = mul(m2, ir);
 }
 // adjoint of a pair: dL/dn (g) -> what each pixel adds to dL/dd of its right / left / lower / upper neighbour
-__device__ __forceinline__ void aff_adj_pair(const AffPair& k, f2 nrx, f2 nry, f2 dl, f2 dr, f2 du, f2 dd, f2 hma, f2 hmb, f2 hmab, f2 hmu,
-                                             f2 hmd, f2 hmud, f2 sc, f2 g0, f2 g1, f2 g2, f2& R, f2& L, f2& Dn, f2& Up) {
+__device__ __forceinline__ void aff_adj_pair(const AffPair& k, f2 nrx, f2 nry, f2 dl, f2 dr, f2 du, f2 dd, f2 ma, f2 mb, f2 mab, f2 mu,
+                                             f2 md, f2 mud, f2 thr, f2 g0, f2 g1, f2 g2, f2& R, f2& L, f2& Dn, f2& Up) {
     f2 Du, Su, Dv, Sv, m0, m1, m2;
-    aff_m_pair(k, nrx, nry, dl, dr, du, dd, hma, hmb, hmab, hmu, hmd, hmud, sc, Du, Su, Dv, Sv, m0, m1, m2);
+    aff_m_pair(k, nrx, nry, dl, dr, du, dd, ma, mb, mab, mu, md, mud, Du, Su, Dv, Sv, m0, m1, m2);
     const f2 r2 = fma(m0, m0, fma(m1, m1, mul(m2, m2)));
-    const f2 ir = inv_len(r2);
+    const f2 ir = inv_len_thr(r2, thr);
     const f2 n0 = mul(m0, ir), n1 = mul(m1, ir), n2 = mul(m2, ir);
-    const f2 dot = keep_if_gt(r2, 1e-24f, fma(n0, g0, fma(n1, g1, mul(n2, g2))));   // clamped denominator: n = m * 1e12, no projection
-    const f2 ndot = mul(dot, bc(-1.f));
+    const f2 dot = fma(n0, g0, fma(n1, g1, mul(n2, g2)));
+    const f2 ndot = mk(r2.v.x > thr.v.x ? -dot.v.x : 0.f, r2.v.y > thr.v.y ? -dot.v.y : 0.f);   // clamped pixels: no projection
     const f2 dm0 = mul(fma(n0, ndot, g0), ir), dm1 = mul(fma(n1, ndot, g1), ir), dm2 = mul(fma(n2, ndot, g2), ir);
-    const f2 e0 = fma(nrx, dm2, dm0), e1 = fma(nry, dm2, dm1), e2 = mul(mul(sc, k.D), dm2);
-    const f2 p = mul(sc, fma(k.k4, e0, mul(k.nk1, e1))), q = mul(sc, fma(k.k0, e1, mul(k.nk3, e0)));
+    const f2 e0 = fma(nrx, dm2, dm0), e1 = fma(nry, dm2, dm1), e2 = mul(k.D, dm2);
+    const f2 p = fma(k.k4, e0, mul(k.nk1, e1)), q = fma(k.k0, e1, mul(k.nk3, e0));
     const f2 dDu = mul(Sv, p), dSv = fma(Du, p, mul(e2, Su)), dDv = mul(Su, q), dSu = fma(Dv, q, mul(e2, Sv));
-    const f2 hu = mul(bc(0.5f), dDu), hv = mul(bc(0.5f), dDv);
-    R = fma(hmb, dSu, hu);
-    L = sub(mul(hma, dSu), hu);
-    Dn = fma(hmd, dSv, hv);
-    Up = sub(mul(hmu, dSv), hv);
+    R = fma(mb, dSu, dDu);
+    L = sub(mul(ma, dSu), dDu);
+    Dn = fma(md, dSv, dDv);
+    Up = sub(mul(mu, dSv), dDv);
 }
 // image-space normals (norms.py:185-190): gh = (dd - du) fh, gw = (dr - dl) fw with the border factors folded into the pair
 // constants fw2 = 2 * hm-style factors: fwp = fw (0.5 interior / 1 border) per pixel, fh broadcast
@@ -529,6 +283,77 @@ struct NewBand {
 };
 
 // ------------------------------------------------------------------------------------------
+// forward, camera-space normals: depth (planes, H, W) -> normals (planes, 3, H, W).  Warp strips; pipe row k = depth row k + 1
+// (+ the seam lane's neighbour column).  (The image-space forward kernel stays on the register quads of stencil_tiled.cu:
+// 76 % of the HBM peak there, and its IEEE sqrt / division - kept for the 1e-4 gate on values of O(100) - make the strip form
+// no faster: measured r2c 61 %.)
+// ------------------------------------------------------------------------------------------
+#define FWD_DEPTH 6
+template <int MINB>
+__global__ void __launch_bounds__(RNT, MINB)
+normals_new_fwd_roll(const float* __restrict__ d, NewBand op, int H, int W, RollPlan pl, float* __restrict__ out) {
+    Task t;
+    if (!roll_task(pl, H, W, t)) return;
+    const long plane = (long)H * W;
+    const float* p = d + t.pl * plane;
+    float* o = out + (long)t.pl * 3 * plane;
+    if (!op.begin(t.pl)) {
+        roll_generic_fwd(p, op.cam, H, W, t, o, plane);
+        return;
+    }
+    const RowPipe<1, 1, FWD_DEPTH> pipe;
+    const bool seamL = t.lane == 0 && t.j > 0, seamR = t.lane == 31 && t.j + 4 < W, seam = seamL || seamR;
+    const int jn = seamL ? t.j - 1 : (seamR ? t.j + 4 : 0);          // the seam lane's neighbour column
+    const int jc = t.act ? t.j : 0;
+    auto issue = [&](int k, int slot) {                              // 32-bit offsets inside the plane (H * W < 2^31)
+        if (k < t.i1) {
+            const int od = clampi(k + 1, H) * W;
+            pipe.cp16(slot, 0, p + (od + jc), t.act);
+            if (seam) pipe.cp4(slot, 0, p + (od + jn), true);
+        }
+        pipe.commit();
+    };
+#pragma unroll
+    for (int k = 0; k < FWD_DEPTH; ++k) issue(t.i0 + k, k);
+    float4 dU = ldrow(p, t.i0 - 1, H, W, t), dC = ldrow(p, t.i0, H, W, t);
+    float sC = seam ? __ldg(p + (long)t.i0 * W + jn) : 0.f;
+    const bool first = t.j == 0, last = t.j + 4 >= W;                 // (W % 4 == 0)
+    const f2 maA = mk(first ? 0.f : 1.f, 1.f), mbA = bc(1.f), mabA = add(maA, mbA);
+    const f2 maB = bc(1.f), mbB = mk(1.f, last ? 0.f : 1.f), mabB = add(maB, mbB);
+    const f2 ifw2A = mk(first ? 16e-24f : 64e-24f, 64e-24f), ifw2B = mk(64e-24f, last ? 16e-24f : 64e-24f);   // 16e-24 / fw^2
+    op.row_begin(t.i0, t.j);
+    int slot = 0;
+    for (int r = t.i0; r < t.i1; ++r) {
+        pipe.wait();
+        const float4 dD = pipe.v(slot, 0);
+        const float sD = pipe.s(slot, 0);
+        issue(r + FWD_DEPTH, slot);
+        slot = slot + 1 == FWD_DEPTH ? 0 : slot + 1;
+        float xl = __shfl_up_sync(FULL, dC.w, 1), xr = __shfl_down_sync(FULL, dC.x, 1);
+        if (t.lane == 0) xl = seamL ? sC : dC.x;
+        if (last) xr = dC.w; else if (t.lane == 31) xr = sC;
+        const float mu_ = r > 0 ? 1.f : 0.f, md_ = r < H - 1 ? 1.f : 0.f;
+        const f2 mu = bc(mu_), md = bc(md_), mud = bc(mu_ + md_), ifh2 = bc((r == 0 || r == H - 1) ? 1.f : 4.f);   // 1 / fh^2
+        const f2 dlA = mk(xl, dC.x), drA = mk(dC.y, dC.z), dlB = drA, drB = mk(dC.w, xr);
+        const f2 duA = mk(dU.x, dU.y), duB = mk(dU.z, dU.w), ddA = mk(dD.x, dD.y), ddB = mk(dD.z, dD.w);
+        const float rx0 = (float)op.rxd, ry0 = (float)op.ryd;
+        const f2 nrxA = mk(-rx0, -(rx0 + op.k0)), nryA = mk(-ry0, -(ry0 + op.k3));
+        const f2 nrxB = mk(-(rx0 + 2.f * op.k0), -(rx0 + 3.f * op.k0)), nryB = mk(-(ry0 + 2.f * op.k3), -(ry0 + 3.f * op.k3));
+        f2 n0A, n1A, n2A, n0B, n1B, n2B;
+        aff_fwd_pair(op.k, nrxA, nryA, dlA, drA, duA, ddA, maA, mbA, mabA, mu, md, mud, mul(ifh2, ifw2A), n0A, n1A, n2A);
+        aff_fwd_pair(op.k, nrxB, nryB, dlB, drB, duB, ddB, maB, mbB, mabB, mu, md, mud, mul(ifh2, ifw2B), n0B, n1B, n2B);
+        if (t.act) {
+            float* q = o + (r * W + t.j);
+            st4(q, make_float4(n0A.v.x, n0A.v.y, n0B.v.x, n0B.v.y));
+            st4(q + plane, make_float4(n1A.v.x, n1A.v.y, n1B.v.x, n1B.v.y));
+            st4(q + 2 * plane, make_float4(n2A.v.x, n2A.v.y, n2B.v.x, n2B.v.y));
+        }
+        dU = dC; dC = dD; sC = sD;
+        op.row_next();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward, row-band form: one CTA = every column of a band of rows (warp w = columns 128 w ..), so a contiguous piece of
 // each plane streams through one CTA.  Per row: the adjoints' R / L and the next depth row's edge values cross the warp
 // seams through 16 floats of shared memory and ONE barrier; nothing is recomputed and no lane idles.  W <= 1024.
@@ -577,14 +402,16 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
     float4 dU = ldrow(p, r0 - 1, H, W, t), dC = ldrow(p, r0, H, W, t);
     // column-border constants of the lane's two pairs (pixel 0 may be column 0, pixel 3 may be column W - 1)
     const bool first = t.j == 0, last = t.j + 4 >= W;                 // (W % 4 == 0)
-    const f2 hmaA = mk(first ? 0.f : 0.5f, 0.5f), hmbA = bc(0.5f), hmabA = add(hmaA, hmbA);
-    const f2 hmaB = bc(0.5f), hmbB = mk(0.5f, last ? 0.f : 0.5f), hmabB = add(hmaB, hmbB);
+    const f2 maA = mk(first ? 0.f : 1.f, 1.f), mbA = bc(1.f), mabA = add(maA, mbA);
+    const f2 maB = bc(1.f), mbB = mk(1.f, last ? 0.f : 1.f), mabB = add(maB, mbB);
     const f2 fwA = mk(first ? 1.f : 0.5f, 0.5f), fwB = mk(0.5f, last ? 1.f : 0.5f);
+    const f2 ifw2A = mk(first ? 16e-24f : 64e-24f, 64e-24f), ifw2B = mk(64e-24f, last ? 16e-24f : 64e-24f);   // 16e-24 / fw^2
     int buf = 0;
     if (lane == 31) sx[1][warp][2] = dC.w;
     if (lane == 0) sx[1][warp][3] = dC.x;
     __syncthreads();
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, DnP[4] = {0.f, 0.f, 0.f, 0.f};   // acc = Hs(r - 1) + Dn(r - 2)
+    float* orow = o + (t.i0 * W + jc);
     op.row_begin(r0, t.j);
     int slot = 0;
     for (int r = r0; r <= t.i1; ++r) {
@@ -597,7 +424,7 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
         if (lane == 0) xl = warp > 0 ? sx[buf ^ 1][warp - 1][2] : dC.x;
         if (last) xr = dC.w; else if (lane == 31) xr = sx[buf ^ 1][warp + 1][3];
         if (r >= 0 && r < H) {                                        // block-uniform
-            const float hmu_ = r > 0 ? 0.5f : 0.f, hmd_ = r < H - 1 ? 0.5f : 0.f, fh = edge_half(r, H);
+            const float mu_ = r > 0 ? 1.f : 0.f, md_ = r < H - 1 ? 1.f : 0.f, fh = edge_half(r, H);
             const f2 dlA = mk(xl, dC.x), drA = mk(dC.y, dC.z), dlB = drA, drB = mk(dC.w, xr);
             const f2 duA = mk(dU.x, dU.y), duB = mk(dU.z, dU.w), ddA = mk(dD.x, dD.y), ddB = mk(dD.z, dD.w);
             const f2 g0A = mk(G0.x, G0.y), g0B = mk(G0.z, G0.w), g1A = mk(G1.x, G1.y), g1B = mk(G1.z, G1.w), g2A = mk(G2.x, G2.y),
@@ -606,10 +433,10 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
                 const float rx0 = (float)op.rxd, ry0 = (float)op.ryd;
                 const f2 nrxA = mk(-rx0, -(rx0 + op.k0)), nryA = mk(-ry0, -(ry0 + op.k3));
                 const f2 nrxB = mk(-(rx0 + 2.f * op.k0), -(rx0 + 3.f * op.k0)), nryB = mk(-(ry0 + 2.f * op.k3), -(ry0 + 3.f * op.k3));
-                const f2 hmu = bc(hmu_), hmd = bc(hmd_), hmud = bc(hmu_ + hmd_), fhp = bc(fh);
-                aff_adj_pair(op.k, nrxA, nryA, dlA, drA, duA, ddA, hmaA, hmbA, hmabA, hmu, hmd, hmud, mul(fhp, fwA), g0A, g1A, g2A, RA, LA,
+                const f2 mu = bc(mu_), md = bc(md_), mud = bc(mu_ + md_), ifh2 = bc(fh == 1.f ? 1.f : 4.f);       // 1 / fh^2
+                aff_adj_pair(op.k, nrxA, nryA, dlA, drA, duA, ddA, maA, mbA, mabA, mu, md, mud, mul(ifh2, ifw2A), g0A, g1A, g2A, RA, LA,
                              DnA, UpA);
-                aff_adj_pair(op.k, nrxB, nryB, dlB, drB, duB, ddB, hmaB, hmbB, hmabB, hmu, hmd, hmud, mul(fhp, fwB), g0B, g1B, g2B, RB, LB,
+                aff_adj_pair(op.k, nrxB, nryB, dlB, drB, duB, ddB, maB, mbB, mabB, mu, md, mud, mul(ifh2, ifw2B), g0B, g1B, g2B, RB, LB,
                              DnB, UpB);
             } else {
                 old_adj_pair(op.scale, dlA, drA, duA, ddA, bc(fh), fwA, g0A, g1A, g2A, RA, LA, DnA, UpA);
@@ -629,12 +456,133 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
         if (last) Hs[3] += RB.v.y;
         if (r == 0) { Hs[0] += UpA.v.x; Hs[1] += UpA.v.y; Hs[2] += UpB.v.x; Hs[3] += UpB.v.y; }
         if (r == H - 1) { Hs[0] += DnA.v.x; Hs[1] += DnA.v.y; Hs[2] += DnB.v.x; Hs[3] += DnB.v.y; }
-        if (r > t.i0 && t.act)                                        // row r - 1 is complete
-            st4(o + ((r - 1) * W + t.j), make_float4(acc[0] + UpA.v.x, acc[1] + UpA.v.y, acc[2] + UpB.v.x, acc[3] + UpB.v.y));
+        if (r > t.i0) {                                               // row r - 1 is complete
+            if (t.act) st4(orow, make_float4(acc[0] + UpA.v.x, acc[1] + UpA.v.y, acc[2] + UpB.v.x, acc[3] + UpB.v.y));
+            orow += W;
+        }
         acc[0] = Hs[0] + DnP[0]; acc[1] = Hs[1] + DnP[1]; acc[2] = Hs[2] + DnP[2]; acc[3] = Hs[3] + DnP[3];
         DnP[0] = DnA.v.x; DnP[1] = DnA.v.y; DnP[2] = DnB.v.x; DnP[3] = DnB.v.y;
         dU = dC; dC = dD;
         op.row_next();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// edge-aware smoothness, one pyramid level (main_model.py:22-73): d (B, 1, h, w), img (B, C, h, w).  Per EDGE between two
+// pixels: w = exp(-mean_c |I_a - I_b|); forward sum += |(d_a - d_b) w|; backward t = coef * w * sign((d_a - d_b) w),
+// gd_a += t, gd_b -= t.  One thread = 4 columns, rolling down the rows: it owns the 4 vertical edges below and the 4
+// horizontal edges right of its pixels; the edge left of its first pixel comes from the neighbouring lane (shuffle; the seam
+// lane recomputes that one edge from its neighbour column, which travels through the pipe like the rows do).
+// Pipe row k = row k + 1 of the depth plane and of the C image planes (+ the seam lane's neighbour column of each).
+// ------------------------------------------------------------------------------------------
+#define SM_DEPTH 3
+__device__ __forceinline__ float signed_or_zero(float mag, float p) { return p == 0.f ? 0.f : copysignf(mag, p); }
+template <int C, bool BWD>
+__global__ void __launch_bounds__(RNT, 6)
+smooth_roll(const float* __restrict__ d, const float* __restrict__ img, int H, int W, RollPlan pl, const float* __restrict__ gscale,
+            float cx, float cy, float* __restrict__ gd, double* __restrict__ out) {
+    Task t;
+    if (!roll_task(pl, H, W, t)) return;
+    const long plane = (long)H * W;
+    const float* p[C + 1];
+    p[0] = d + t.pl * plane;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p[c + 1] = img + ((long)t.pl * C + c) * plane;
+    const RowPipe<C + 1, C + 1, SM_DEPTH> pipe;
+    const bool seamL = BWD && t.lane == 0 && t.j > 0, seamR = t.lane == 31 && t.j + 4 < W, seam = seamL || seamR;
+    const int jn = seamL ? t.j - 1 : (seamR ? t.j + 4 : 0);
+    const int jc = t.act ? t.j : 0;
+    const bool last = t.j + 4 >= W;
+    const int r0 = BWD ? max(t.i0 - 1, 0) : t.i0;                     // backward: the vertical edges above the chunk's first row
+    auto issue = [&](int k, int slot) {
+        if (k < t.i1) {
+            const int od = clampi(k + 1, H) * W;
+#pragma unroll
+            for (int c = 0; c <= C; ++c) {
+                pipe.cp16(slot, c, p[c] + (od + jc), t.act);
+                if (seam) pipe.cp4(slot, c, p[c] + (od + jn), true);
+            }
+        }
+        pipe.commit();
+    };
+#pragma unroll
+    for (int k = 0; k < SM_DEPTH; ++k) issue(r0 + k, k);
+    float4 cur[C + 1];
+    float sC[C + 1];
+#pragma unroll
+    for (int c = 0; c <= C; ++c) {
+        cur[c] = ldrow(p[c], r0, H, W, t);
+        sC[c] = seam ? __ldg(p[c] + (long)r0 * W + jn) : 0.f;
+    }
+    const float invC = 1.f / (float)C, g = BWD ? (gscale ? *gscale : 1.f) : 0.f, gcx = g * cx, gcy = g * cy;
+    float tvp[4] = {0.f, 0.f, 0.f, 0.f};                              // backward: t of the vertical edges above the current row
+    float fx = 0.f, fy = 0.f;
+    double ax = 0.0, ay = 0.0;
+    float* orow = BWD ? gd + t.pl * plane + (t.i0 * W + jc) : nullptr;
+    int slot = 0;
+    for (int r = r0; r < t.i1; ++r) {
+        pipe.wait();
+        float4 nxt[C + 1];
+        float sD[C + 1];
+#pragma unroll
+        for (int c = 0; c <= C; ++c) { nxt[c] = pipe.v(slot, c); sD[c] = pipe.s(slot, c); }
+        issue(r + SM_DEPTH, slot);
+        slot = slot + 1 == SM_DEPTH ? 0 : slot + 1;
+        float sv[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f}, shl = 0.f, dright, dleft = 0.f;
+#pragma unroll
+        for (int c = 0; c <= C; ++c) {
+            const float4 a = cur[c], b = nxt[c];
+            float xr = __shfl_down_sync(FULL, a.x, 1);
+            if (last) xr = a.w; else if (t.lane == 31) xr = sC[c];          // clamped: the edge across the border is 0
+            if (c == 0) {
+                dright = xr;
+                if (seamL) dleft = sC[0];
+            } else {
+                sv[0] += fabsf(a.x - b.x); sv[1] += fabsf(a.y - b.y); sv[2] += fabsf(a.z - b.z); sv[3] += fabsf(a.w - b.w);
+                sh[0] += fabsf(a.x - a.y); sh[1] += fabsf(a.y - a.z); sh[2] += fabsf(a.z - a.w); sh[3] += fabsf(a.w - xr);
+                if (seamL) shl += fabsf(sC[c] - a.x);
+            }
+        }
+        const float4 dc = cur[0], dn = nxt[0];
+        const float dv[4] = {dc.x - dn.x, dc.y - dn.y, dc.z - dn.z, dc.w - dn.w};
+        const float dh[4] = {dc.x - dc.y, dc.y - dc.z, dc.z - dc.w, dc.w - dright};
+        if (!BWD) {
+            if (t.act) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    fx += fabsf(dv[e] * __expf(-sv[e] * invC));
+                    fy += fabsf(dh[e] * __expf(-sh[e] * invC));
+                }
+            }
+            if (((r - r0) & 15) == 15) { ax += (double)fx; ay += (double)fy; fx = 0.f; fy = 0.f; }
+        } else {
+            float tv[4], th[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float wv = __expf(-sv[e] * invC), wh = __expf(-sh[e] * invC);
+                tv[e] = signed_or_zero(gcx * wv, dv[e] * wv);
+                th[e] = signed_or_zero(gcy * wh, dh[e] * wh);
+            }
+            float tl = __shfl_up_sync(FULL, th[3], 1);                // the edge left of the lane's first pixel
+            if (t.lane == 0) {
+                tl = 0.f;
+                if (seamL) { const float wl = __expf(-shl * invC); tl = signed_or_zero(gcy * wl, (dleft - dc.x) * wl); }
+            }
+            if (r >= t.i0) {
+                if (t.act) st4(orow, make_float4(tv[0] - tvp[0] + th[0] - tl, tv[1] - tvp[1] + th[1] - th[0], tv[2] - tvp[2] + th[2] - th[1],
+                                                 tv[3] - tvp[3] + th[3] - th[2]));
+                orow += W;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tvp[e] = tv[e];
+        }
+#pragma unroll
+        for (int c = 0; c <= C; ++c) { cur[c] = nxt[c]; sC[c] = sD[c]; }
+    }
+    if (!BWD) {
+        ax += (double)fx; ay += (double)fy;
+        ax = warp_sum(ax); ay = warp_sum(ay);
+        if (t.lane == 0) { atomicAdd(out, ax); atomicAdd(out + 1, ay); }
     }
 }
 
@@ -749,14 +697,7 @@ static int band_launch_plan(K kernel, int nt, int smem, long planes, int H, int&
             kern<<<(unsigned)(planes * chunks), nt, smem, ST(stream)>>>(__VA_ARGS__); }             \
     } while (0)
 
-int dsr_roll_normals_old_fwd(const float* d, int B, int H, int W, float scale, float* out, void* stream) {
-    if (!roll_ok(W, d, out, nullptr)) return 0;
-    OldOp op; op.scale = scale;
-#define KT_OF(m) normals_fwd_roll<OldOp, false, m>
-    ROLL_DISPATCH("OLD_FWD", 8, KT_OF, (RowPipe<1, 1, FWD_DEPTH>::bytes()), B, d, op, H, W, pl, out);
-#undef KT_OF
-    return 1;
-}
+int dsr_roll_normals_old_fwd(const float*, int, int, int, float, float*, void*) { return 0; }   // stays on the register quads
 int dsr_roll_normals_old_bwd(const float* d, const float* g, int B, int H, int W, float scale, float* gd, void* stream) {
     if (!roll_ok(W, d, g, gd) || W > RCOLS * BAND_MAXW) return 0;
     OldBand op; op.scale = scale; op.cam = nullptr;
@@ -767,8 +708,8 @@ int dsr_roll_normals_old_bwd(const float* d, const float* g, int B, int H, int W
 }
 int dsr_roll_normals_new_fwd(const float* d, const double* cams, int B, int H, int W, float* out, void* stream) {
     if (!roll_ok(W, d, out, nullptr)) return 0;
-    NewOp op; op.cams = cams;
-#define KT_NF(m) normals_fwd_roll<NewOp, true, m>
+    NewBand op; op.cams = cams; op.cam = nullptr;
+#define KT_NF(m) normals_new_fwd_roll<m>
     ROLL_DISPATCH("NEW_FWD", 6, KT_NF, (RowPipe<1, 1, FWD_DEPTH>::bytes()), B, d, op, H, W, pl, out);
 #undef KT_NF
     return 1;
@@ -780,6 +721,34 @@ int dsr_roll_normals_new_bwd(const float* d, const float* g, const double* cams,
     BAND_DISPATCH("NEW_BWD", 3, KT_NB, (long)B, d, g, op, H, W, rows, chunks, gd);
 #undef KT_NB
     return 1;
+}
+template <int C, bool BWD>
+static int smooth_roll_launch(const float* d, const float* img, int B, int H, int W, const float* gscale, float cx, float cy, float* gd,
+                              double* out, void* stream) {
+    auto kern = smooth_roll<C, BWD>;
+    ROLL_LAUNCH(kern, (RowPipe<C + 1, C + 1, SM_DEPTH>::bytes()), (long)B, d, img, H, W, pl, gscale, cx, cy, gd, out);
+    return 1;
+}
+int dsr_roll_smooth_fwd(const float* d, const float* img, int B, int C, int H, int W, double* out2, void* stream) {
+    if (!roll_ok(W, d, img, nullptr)) return 0;
+    switch (C) {
+        case 1: return smooth_roll_launch<1, false>(d, img, B, H, W, nullptr, 0.f, 0.f, nullptr, out2, stream);
+        case 2: return smooth_roll_launch<2, false>(d, img, B, H, W, nullptr, 0.f, 0.f, nullptr, out2, stream);
+        case 3: return smooth_roll_launch<3, false>(d, img, B, H, W, nullptr, 0.f, 0.f, nullptr, out2, stream);
+        case 4: return smooth_roll_launch<4, false>(d, img, B, H, W, nullptr, 0.f, 0.f, nullptr, out2, stream);
+    }
+    return 0;
+}
+int dsr_roll_smooth_bwd(const float* d, const float* img, int B, int C, int H, int W, const float* gscale, float cx, float cy, float* gd,
+                        void* stream) {
+    if (!roll_ok(W, d, img, gd)) return 0;
+    switch (C) {
+        case 1: return smooth_roll_launch<1, true>(d, img, B, H, W, gscale, cx, cy, gd, nullptr, stream);
+        case 2: return smooth_roll_launch<2, true>(d, img, B, H, W, gscale, cx, cy, gd, nullptr, stream);
+        case 3: return smooth_roll_launch<3, true>(d, img, B, H, W, gscale, cx, cy, gd, nullptr, stream);
+        case 4: return smooth_roll_launch<4, true>(d, img, B, H, W, gscale, cx, cy, gd, nullptr, stream);
+    }
+    return 0;
 }
 int dsr_roll_tv_fwd(const float* x, long planes, int H, int W, double* out, void* stream) {
     if (!roll_ok(W, x, nullptr, nullptr)) return 0;

@@ -876,6 +876,14 @@ int dsr_roll_normals_old_bwd(const float* d, const float* g, int B, int H, int W
 int dsr_roll_normals_new_fwd(const float* d, const double* cams, int B, int H, int W, float* out, void* stream);
 int dsr_roll_normals_new_bwd(const float* d, const float* g, const double* cams, int B, int H, int W, float* gd, void* stream);
 int dsr_roll_tv_fwd(const float* x, long planes, int H, int W, double* out, void* stream);
+int dsr_roll_smooth_fwd(const float* d, const float* img, int B, int C, int H, int W, double* out2, void* stream);
+int dsr_roll_smooth_bwd(const float* d, const float* img, int B, int C, int H, int W, const float* gscale, float cx, float cy, float* gd,
+                        void* stream);
+static int smooth_mode() {             // DSR_SMOOTH_KERNEL: 0 = automatic (strip kernels), 1 = ring / rolling-row kernels of the first two generations
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DSR_SMOOTH_KERNEL"); v = e ? atoi(e) : 0; }
+    return v;
+}
 static bool use_roll() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("DSR_STENCIL_ROLL"); v = e ? atoi(e) : 1; }
@@ -973,6 +981,7 @@ extern "C" int dsr_smooth_level_fwd(const float* d, const float* img, int B, int
                                     void* stream) {
     DSR_REQUIRE(d && img && out2 && B > 0 && C >= 1 && C <= SM_MAXC && h > 0 && w > 0 && PLANES_OK(B, h, w), "bad arguments (C <= 4)");
     const dim3 grid((w + TW - 1) / TW, (h + STRIP - 1) / STRIP, B);
+    if (use_roll() && smooth_mode() == 0 && dsr_roll_smooth_fwd(d, img, B, C, h, w, out2, stream)) return dsr_check_launch("smooth_level_fwd");
     if (!((uintptr_t)d & 15) && !((uintptr_t)img & 15) && dsr_smooth_ring_suits(B, C, h, w))
         return dsr_smooth_level_fwd_ring(d, img, B, C, h, w, out2, stream);          // large plane sets: csrc/stencil_ring.cu
     if (!(w & 3) && !((uintptr_t)d & 15) && !((uintptr_t)img & 15)) {
@@ -990,6 +999,8 @@ extern "C" int dsr_smooth_level_fwd(const float* d, const float* img, int B, int
 extern "C" int dsr_smooth_level_bwd(const float* d, const float* img, int B, int C, int h, int w, const float* gscale,
                                     float cx, float cy, float* gd, int accumulate, void* stream) {
     DSR_REQUIRE(d && img && gd && B > 0 && C >= 1 && C <= SM_MAXC && h > 0 && w > 0 && PLANES_OK(B, h, w), "bad arguments (C <= 4)");
+    if (use_roll() && smooth_mode() == 0 && !accumulate && dsr_roll_smooth_bwd(d, img, B, C, h, w, gscale, cx, cy, gd, stream))
+        return dsr_check_launch("smooth_level_bwd");
     if (!((uintptr_t)d & 15) && !((uintptr_t)img & 15) && !((uintptr_t)gd & 15) && dsr_smooth_ring_suits(B, C, h, w))
         return dsr_smooth_level_bwd_ring(d, img, B, C, h, w, gscale, cx, cy, gd, accumulate, stream);
     if (!(w & 3) && !((uintptr_t)d & 15) && !((uintptr_t)img & 15) && !((uintptr_t)gd & 15)) {
