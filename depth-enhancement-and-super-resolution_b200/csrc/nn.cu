@@ -909,3 +909,51 @@ extern "C" int dsr_adam_step(float* p, const float* g, float* m, float* v, long 
         (float)sqrt(bc2), grad_scale);
     return dsr_check_launch("adam_step");
 }
+
+// ------------------------------------------------------------------------------------------
+// loss assembly: loss_G = scale * sum_k sum_j w[k][j] * term_k[j]   (main_model.py:393-417) - one launch forward, one backward
+// ------------------------------------------------------------------------------------------
+#define LOSS_MAX_TERMS 32
+struct LossTerms {
+    const float* p[LOSS_MAX_TERMS];
+    float w[LOSS_MAX_TERMS][4];
+    int cnt[LOSS_MAX_TERMS];
+    int n;
+};
+__global__ void loss_sum_fwd_kernel(const LossTerms t, float scale, float* __restrict__ out) {
+    float a = 0.f;
+    const int k = threadIdx.x;
+    if (k < t.n)
+        for (int j = 0; j < t.cnt[k]; ++j) a += t.w[k][j] * t.p[k][j];
+    a = warp_sum(a);
+    if (k == 0) *out = a * scale;
+}
+__global__ void loss_sum_bwd_kernel(const float* __restrict__ g, const LossTerms t, float scale, float* __restrict__ grads) {
+    const int i = threadIdx.x, k = i >> 2, j = i & 3;
+    if (k < t.n) grads[i] = *g * scale * t.w[k][j];
+}
+extern "C" int dsr_loss_sum_fwd(const float* const* terms, const int* counts, const float* weights, int n, float scale, float* out,
+                                void* stream) {
+    DSR_REQUIRE(terms && counts && weights && out && n > 0 && n <= LOSS_MAX_TERMS, "1..32 terms");
+    LossTerms t;
+    t.n = n;
+    for (int k = 0; k < LOSS_MAX_TERMS; ++k) {
+        t.p[k] = k < n ? terms[k] : nullptr;
+        t.cnt[k] = k < n ? counts[k] : 0;
+        for (int j = 0; j < 4; ++j) t.w[k][j] = k < n ? weights[4 * k + j] : 0.f;
+        DSR_REQUIRE(k >= n || (t.p[k] && t.cnt[k] >= 1 && t.cnt[k] <= 4), "every term needs a pointer and 1..4 elements");
+    }
+    loss_sum_fwd_kernel<<<1, 32, 0, ST(stream)>>>(t, scale, out);
+    return dsr_check_launch("loss_sum_fwd");
+}
+extern "C" int dsr_loss_sum_bwd(const float* g, const float* weights, int n, float scale, float* grads, void* stream) {
+    DSR_REQUIRE(g && weights && grads && n > 0 && n <= LOSS_MAX_TERMS, "1..32 terms");
+    LossTerms t;
+    t.n = n;
+    for (int k = 0; k < LOSS_MAX_TERMS; ++k) {
+        t.p[k] = nullptr; t.cnt[k] = 0;
+        for (int j = 0; j < 4; ++j) t.w[k][j] = k < n ? weights[4 * k + j] : 0.f;
+    }
+    loss_sum_bwd_kernel<<<1, 4 * LOSS_MAX_TERMS, 0, ST(stream)>>>(g, t, scale, grads);
+    return dsr_check_launch("loss_sum_bwd");
+}

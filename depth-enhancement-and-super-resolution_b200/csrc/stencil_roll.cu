@@ -412,7 +412,17 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
     __syncthreads();
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, DnP[4] = {0.f, 0.f, 0.f, 0.f};   // acc = Hs(r - 1) + Dn(r - 2)
     float* orow = o + (t.i0 * W + jc);
-    op.row_begin(r0, t.j);
+    // negated rays of the lane's two pairs: evaluated in fp64 for the chunk's first row, then advanced by k1 / k4 per row in
+    // fp32 (<= 2^-24 |ray| per step over the <= ~100 rows of a chunk: 1e-6 relative on a GRADIENT whose gate is 1e-3; the
+    // forward kernel, gated at 2e-6 absolute, keeps the fp64 advance)
+    f2 nrxA = bc(0.f), nryA = bc(0.f), nrxB = bc(0.f), nryB = bc(0.f), nk1p = bc(0.f), nk4p = bc(0.f);
+    if constexpr (NEW) {
+        op.row_begin(r0, t.j);
+        const float rx0 = (float)op.rxd, ry0 = (float)op.ryd;
+        nrxA = mk(-rx0, -(rx0 + op.k0)); nryA = mk(-ry0, -(ry0 + op.k3));
+        nrxB = mk(-(rx0 + 2.f * op.k0), -(rx0 + 3.f * op.k0)); nryB = mk(-(ry0 + 2.f * op.k3), -(ry0 + 3.f * op.k3));
+        nk1p = bc(-(float)op.k1d); nk4p = bc(-(float)op.k4d);
+    }
     int slot = 0;
     for (int r = r0; r <= t.i1; ++r) {
         pipe.wait();
@@ -430,9 +440,6 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
             const f2 g0A = mk(G0.x, G0.y), g0B = mk(G0.z, G0.w), g1A = mk(G1.x, G1.y), g1B = mk(G1.z, G1.w), g2A = mk(G2.x, G2.y),
                      g2B = mk(G2.z, G2.w);
             if constexpr (NEW) {
-                const float rx0 = (float)op.rxd, ry0 = (float)op.ryd;
-                const f2 nrxA = mk(-rx0, -(rx0 + op.k0)), nryA = mk(-ry0, -(ry0 + op.k3));
-                const f2 nrxB = mk(-(rx0 + 2.f * op.k0), -(rx0 + 3.f * op.k0)), nryB = mk(-(ry0 + 2.f * op.k3), -(ry0 + 3.f * op.k3));
                 const f2 mu = bc(mu_), md = bc(md_), mud = bc(mu_ + md_), ifh2 = bc(fh == 1.f ? 1.f : 4.f);       // 1 / fh^2
                 aff_adj_pair(op.k, nrxA, nryA, dlA, drA, duA, ddA, maA, mbA, mabA, mu, md, mud, mul(ifh2, ifw2A), g0A, g1A, g2A, RA, LA,
                              DnA, UpA);
@@ -463,7 +470,7 @@ normals_bwd_band(const float* __restrict__ d, const float* __restrict__ g, OP op
         acc[0] = Hs[0] + DnP[0]; acc[1] = Hs[1] + DnP[1]; acc[2] = Hs[2] + DnP[2]; acc[3] = Hs[3] + DnP[3];
         DnP[0] = DnA.v.x; DnP[1] = DnA.v.y; DnP[2] = DnB.v.x; DnP[3] = DnB.v.y;
         dU = dC; dC = dD;
-        op.row_next();
+        if constexpr (NEW) { nrxA = add(nrxA, nk1p); nrxB = add(nrxB, nk1p); nryA = add(nryA, nk4p); nryB = add(nryB, nk4p); }
     }
 }
 

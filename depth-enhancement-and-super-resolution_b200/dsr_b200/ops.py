@@ -1778,6 +1778,48 @@ def masked_mean_dif(x, y, mask):
     return _MaskedMeanDif.apply(x, y, mask)
 
 
+class _LossSum(Function):
+    """scale * sum_k sum_j w[k][j] * term_k[j] over tiny device tensors (1..4 elements each) in one launch; one more launch
+    hands every term its gradient.  main_model.py:393-417."""
+
+    @staticmethod
+    def forward(ctx, scale, weights, *terms):
+        import ctypes
+        n = len(terms)
+        ts = [t.detach().contiguous().view(-1) for t in terms]
+        ptrs = (ctypes.c_void_p * n)(*[_p(t) for t in ts])
+        counts = _int_array([t.numel() for t in ts])
+        flat = []
+        for w, t in zip(weights, ts):
+            w = list(w) if isinstance(w, (tuple, list)) else [w]
+            if len(w) != t.numel() or not 1 <= len(w) <= 4:
+                raise ValueError("loss_sum: one weight per element, 1..4 elements per term")
+            flat += [float(x) for x in w] + [0.0] * (4 - len(w))
+        wts = (ctypes.c_float * len(flat))(*flat)
+        out = torch.empty((), device=ts[0].device, dtype=torch.float32)
+        _call("dsr_loss_sum_fwd", ptrs, counts, wts, n, float(scale), _p(out))
+        ctx.cfg = (float(scale), wts, n, [tuple(t.shape) for t in terms])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        scale, wts, n, shapes = ctx.cfg
+        grads = torch.empty(4 * n, device=g.device, dtype=torch.float32)
+        _call("dsr_loss_sum_bwd", _p(g.contiguous()), wts, n, scale, _p(grads))
+        outs = []
+        for k, shp in enumerate(shapes):
+            m = 1
+            for d in shp:
+                m *= d
+            outs.append(grads[4 * k:4 * k + m].view(shp) if ctx.needs_input_grad[2 + k] else None)
+        return (None, None) + tuple(outs)
+
+
+def loss_sum(terms, scale=1.0):
+    """terms: [(tensor, weight or tuple of per-element weights), ...] -> scale * sum of the weighted elements (0-dim)."""
+    return _LossSum.apply(scale, tuple(w for _, w in terms), *[t for t, _ in terms])
+
+
 def ssim(a, b):
     """Mean SSIM (11x11 Gaussian, sigma 1.5).  pytorch_ssim/__init__.py:17-37.  Forward only."""
     a, b = planes(a.detach()), planes(b.detach())

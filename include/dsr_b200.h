@@ -184,6 +184,13 @@ int dsr_pack_weight(const float* w, int D0, int D1, int R, int S, int kdim, floa
 int dsr_unpack_weight(const float* packed, int D0, int D1, int R, int S, int kdim, float* w, int accumulate,
                       void* stream);
 int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, long n, float scale, int accumulate, void* stream);
+/* Loss assembly (models/main_model.py:393-417: loss_G = sum of ~14 weighted scalar terms, times scale_G) in ONE launch:
+ * out = scale * sum_k sum_j weights[k][j] * terms[k][j] over n <= 32 tiny device tensors of counts[k] <= 4 elements each
+ * (`terms`, `counts`, `weights` are HOST arrays; weights is flat, 4 per term).  The backward form writes
+ * grads[4 k + j] = g * scale * weights[k][j] for every term at once.  Replaces ~40 scalar multiply / add kernels per pass. */
+int dsr_loss_sum_fwd(const float* const* terms, const int* counts, const float* weights, int n, float scale, float* out,
+                     void* stream);
+int dsr_loss_sum_bwd(const float* g, const float* weights, int n, float scale, float* grads, void* stream);
 
 /* ---- convolutions ---------------------------------------------------------------------------- */
 /* generic fp32 implicit GEMM (CUDA cores): out[m][co] = bias[co] + sum_k G(m,k) Wk[k][co].
