@@ -62,6 +62,18 @@ def draw_rects(batch, H, W, stage="train", rng=np.random, p_train=0.90, div=8):
     return rects, counts
 
 
+def _scaled(t, w):
+    """a loss attribute that is `w * t` (read by logging only): the product is formed when somebody asks for the value"""
+    d = t.detach()                 # (a view: no kernel; the closure must not keep the step's autograd graph alive)
+    return LazyScalar(lambda: d * w)
+
+
+def _picked(pair, i, w=1.0):
+    """element i of a (L1, MSE) pair, times w, formed on demand"""
+    d = pair.detach()
+    return LazyScalar(lambda: d[i] * w)
+
+
 class LazyScalar:
     """A device scalar that only synchronises when converted (``float()``): replaces the four
     per-step ``.cpu().detach().numpy()`` reads of main_model.py:311-318."""
@@ -412,10 +424,16 @@ class MainModel(BaseModel):
         n_syn = ops.normals_old(self.syn_depth, 100.0)
         n_syn_pred = ops.normals_old(ps, 100.0)
         n_real_pred = ops.normals_old(pr, 100.0)
+        # The reference multiplies / adds ~40 scalar tensors here (main_model.py:352-417); on the device each of those is a
+        # ~2 us launch on the critical path between the forward and the backward pass.  The raw terms come out of the loss
+        # kernels as tiny device tensors, ONE launch (ops.loss_sum) forms loss_G from them and one more hands every term its
+        # gradient; the scaled per-term attributes (loss_tv_*, loss_holes_*_l2) become lazy products, read only by logging.
         tvw = (10 ** -7) * self.tv_scale
-        self.loss_tv_syn_norm_old = tv_loss(n_syn_pred) * tvw
-        self.loss_tv_real_norm_old = tv_loss(n_real_pred) * tvw
-        self.loss_syn_norms_old = ops.masked_l1_l2(n_syn, n_syn_pred, ms)[1]
+        tv_syn_old, tv_real_old = tv_loss(n_syn_pred), tv_loss(n_real_pred)
+        self.loss_tv_syn_norm_old = _scaled(tv_syn_old, tvw)
+        self.loss_tv_real_norm_old = _scaled(tv_real_old, tvw)
+        norms_old = ops.masked_l1_l2(n_syn, n_syn_pred, ms)
+        self.loss_syn_norms_old = _picked(norms_old, 1)
         a_s = self._a_s                                             # mask_syn_add_holes (:354-357)
         # camera-space normals (:360-372)
         self.norm_syn = ops.normals_new(self.syn_depth, self.cam_A)
@@ -423,32 +441,36 @@ class MainModel(BaseModel):
         self.norm_syn_pred = ops.normals_new(ps, self.cam_A)
         self.norm_real = ops.normals_new(self.real_depth, self.cam_B)
         self.norm_real_pred = ops.normals_new(pr, self.cam_B)
-        self.loss_tv_syn_norm = tv_loss(self.norm_syn_pred) * tvw
-        self.loss_tv_real_norm = tv_loss(self.norm_real_pred) * tvw
-        self.loss_syn_norms = ops.masked_l1_l2(self.norm_syn, self.norm_syn_pred, ms)[0]
-        self.loss_syn_norms_holes = ops.masked_l1_l2(self.norm_syn, self.norm_syn_pred, ms, a_s)[0]
+        tv_syn, tv_real = tv_loss(self.norm_syn_pred), tv_loss(self.norm_real_pred)
+        self.loss_tv_syn_norm = _scaled(tv_syn, tvw)
+        self.loss_tv_real_norm = _scaled(tv_real, tvw)
+        norms = ops.masked_l1_l2(self.norm_syn, self.norm_syn_pred, ms)
+        norms_holes = ops.masked_l1_l2(self.norm_syn, self.norm_syn_pred, ms, a_s)
+        self.loss_syn_norms = _picked(norms, 0)
+        self.loss_syn_norms_holes = _picked(norms_holes, 0)
         # depth terms (:383-390)
         hs = ops.masked_l1_l2(self.syn_depth, ps, ms, a_s)
-        self.loss_holes_syn = hs[0]
-        self.loss_holes_syn_l2 = hs[1] * 5
-        self.loss_task_syn = ops.masked_l1_l2(self.syn_depth, ps, ms)[0]
-        self.loss_task_real_by_depth = ops.masked_l1_l2(self.real_depth, pr, mr)[0]
-        self.loss_task_real_by_image = ops.masked_l1_l2(self.real_depth_by_image, pr, self.real_hole_mask)[0]
-        self.loss_G = (self.loss_task_syn * opt.w_syn_l1 + self.loss_holes_syn * opt.w_syn_holes
-                       + opt.w_syn_holes * self.loss_holes_syn_l2 + self.loss_task_real_by_depth * opt.w_real_l1_d
-                       + self.loss_task_real_by_image * opt.w_real_l1_i + self.loss_tv_syn_norm * 1
-                       + self.loss_syn_norms_holes * opt.w_syn_norm * 5 + self.loss_tv_real_norm * 1
-                       + self.loss_syn_norms_old * opt.w_syn_norm + self.loss_tv_real_norm_old * 1
-                       + self.loss_tv_syn_norm_old * 1)             # :393
+        self.loss_holes_syn = _picked(hs, 0)
+        self.loss_holes_syn_l2 = _picked(hs, 1, 5.0)
+        task_syn = ops.masked_l1_l2(self.syn_depth, ps, ms)
+        task_real_d = ops.masked_l1_l2(self.real_depth, pr, mr)
+        task_real_i = ops.masked_l1_l2(self.real_depth_by_image, pr, self.real_hole_mask)
+        self.loss_task_syn = _picked(task_syn, 0)
+        self.loss_task_real_by_depth = _picked(task_real_d, 0)
+        self.loss_task_real_by_image = _picked(task_real_i, 0)
         hr = ops.masked_l1_l2(self.real_depth, pr, self._a_r)       # mask_real_add_holes (:396-398)
-        self.loss_holes_real = hr[0]
-        self.loss_holes_real_l2 = hr[1] * 5
-        self.loss_G = self.loss_G + self.loss_holes_real * opt.w_real_holes + self.loss_holes_real_l2 * opt.w_real_holes
-        self.loss_G = self.loss_G + self.loss_syn_norms * opt.w_syn_norm                      # :404
+        self.loss_holes_real = _picked(hr, 0)
+        self.loss_holes_real_l2 = _picked(hr, 1, 5.0)
+        terms = [(task_syn, (opt.w_syn_l1, 0.0)), (hs, (opt.w_syn_holes, 5.0 * opt.w_syn_holes)),
+                 (task_real_d, (opt.w_real_l1_d, 0.0)), (task_real_i, (opt.w_real_l1_i, 0.0)), (tv_syn, tvw),
+                 (norms_holes, (opt.w_syn_norm * 5, 0.0)), (tv_real, tvw), (norms_old, (0.0, opt.w_syn_norm)),
+                 (tv_real_old, tvw), (tv_syn_old, tvw),                                        # :393
+                 (hr, (opt.w_real_holes, 5.0 * opt.w_real_holes)),                             # :398-402
+                 (norms, (opt.w_syn_norm, 0.0))]                                               # :404
         if opt.use_smooth_loss:
             self.loss_smooth = get_smooth_weight(pr, self.real_image, 3)                      # :407
-            self.loss_G = self.loss_G + self.loss_smooth * opt.w_smooth
-        self.loss_G = self.loss_G * opt.scale_G                                               # :417
+            terms.append((self.loss_smooth, opt.w_smooth))
+        self.loss_G = ops.loss_sum(terms, opt.scale_G)                                        # :417
         if back:
             self.loss_G.backward()
             ops.join_side()          # the weight-gradient stream (ops._on_side) rejoins before anything reads the gradients
