@@ -20,6 +20,7 @@
 //   warp 1   : TMEM allocator + MMA issuer - tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
 //              smem descriptors K-major SWIZZLE_128B; tcgen05.commit releases the smem stage / signals the epilogue
 //   warps 2-5: epilogue - tcgen05.ld 32x32b.x32 -> +bias -> (tanh) -> fp32 NHWC stores (or red.add for split-K)
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -683,6 +684,94 @@ tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S,
         if (Wlo) *reinterpret_cast<uint4*>(Wlo + o) = *reinterpret_cast<const uint4*>(lo);
     }
 }
+// Tiled form of the same packing for the big layers (R * S <= 16; variants CONV, CONV_S2D, CONV_DGRAD, CONVT_PH).  The gather
+// kernel above reads coalesced but stores 16-byte pieces 2 * Ca bytes apart (a warp's store touches 32 lines), and it was
+// the slowest of the support kernels: 1.4 ms per step for 61 launches over the 44 M trainable parameters (r2a) - ~0.5 TB/s.
+// Here a CTA stages a tile of the parameter in shared memory with contiguous loads - TCO GEMM rows x TC K-channels x all R*S
+// taps: for a Conv2d-style source (K channel = parameter dim 1) TC * R * S floats per row are one contiguous run, for a
+// ConvTranspose-style source (K channel = dim 0) TCO * R * S floats per K channel are - and then writes whole
+// [co][t][c0 .. c0 + TC) runs, 16 bytes per thread with the lanes side by side.  Bit-identical output (tests).
+template <int VARIANT, int RS>
+__global__ void __launch_bounds__(256)
+tc_pack_weight_tiled_kernel(const float* __restrict__ w, int D0, int D1, int Cp, int pa, int pb, int pad, int Cout, int Ca,
+                            unsigned short* __restrict__ Whi, unsigned short* __restrict__ Wlo, int f16, float wscale) {
+    constexpr bool CONVT = VARIANT == DSR_TC_W_CONVT_PH || VARIANT == DSR_TC_W_CONV_DGRAD;
+    constexpr int S = RS == 9 ? 3 : 4, R = S;
+    constexpr int NAB = VARIANT == DSR_TC_W_CONV_S2D ? 4 : 1;
+    constexpr int T = (VARIANT == DSR_TC_W_CONV_S2D || VARIANT == DSR_TC_W_CONVT_PH) ? 4 : RS;
+    constexpr int TCO = CONVT ? 8 : 2, TC = CONVT ? 64 : 128, TCP = TC + 4, C8N = TC / 8;
+    // shared tile [TCO][RS][TC + 4]: K channels fastest, so a thread's 8 output channels are two 16-byte loads and the lanes of
+    // a warp read side by side (conflict-free); every index division below is by a compile-time constant
+    __shared__ __align__(16) float wtile[TCO * RS * TCP];
+    if (pa < 0) {                 // all four output phases of a stride-2 transposed conv in one launch (grid.y = phase)
+        pa = blockIdx.y >> 1; pb = blockIdx.y & 1;
+        Whi += (long)blockIdx.y * Cout * T * Ca;
+        if (Wlo) Wlo += (long)blockIdx.y * Cout * T * Ca;
+    }
+    const int Cin = CONVT ? D0 : D1, Crow = CONVT ? D1 : D0;          // K channels / GEMM rows the parameter really has
+    const int Kc = NAB == 4 ? Cp : Ca;                                // K-channel extent of one (tap, sub-block)
+    const int nc_tiles = (Kc + TC - 1) / TC, nco_tiles = (Cout + TCO - 1) / TCO;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < nc_tiles * nco_tiles; tile += gridDim.x) {
+        const int tco = tile / nc_tiles, co0 = tco * TCO, c0 = (tile - tco * nc_tiles) * TC;
+        const int nc = min(TC, Cin - c0), nrow = min(TCO, Crow - co0);    // (<= 0: the tile lies in the zero padding)
+        __syncthreads();
+        if (nc > 0 && nrow > 0) {
+            if (!CONVT) {
+                for (int co_l = 0; co_l < nrow; ++co_l) {
+                    const float* src = w + ((long)(co0 + co_l) * D1 + c0) * RS;
+                    for (int i = tid; i < nc * RS; i += 256) { const int c_l = i / RS; wtile[(co_l * RS + (i - c_l * RS)) * TCP + c_l] = __ldg(src + i); }
+                }
+            } else {
+                const int run = nrow * RS;                            // contiguous floats per K channel
+                for (int c_l = tid >> 5; c_l < nc; c_l += 8) {        // one warp per K channel
+                    const float* src = w + ((long)(c0 + c_l) * D1 + co0) * RS;
+                    for (int k = tid & 31; k < run; k += 32) { const int co_l = k / RS; wtile[(co_l * RS + (k - co_l * RS)) * TCP + c_l] = __ldg(src + k); }
+                }
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < TCO * T * NAB * C8N; it += 256) {
+            const int c8_l = it % C8N; int u = it / C8N;
+            const int ab = u % NAB; u /= NAB;
+            const int t = u % T, co_l = u / T, co = co0 + co_l;
+            const int cb = c0 + c8_l * 8, q0 = ab * Cp + cb;
+            if (co >= Cout || cb >= Kc) continue;
+            int r, sx, c;
+            tc_map_k(VARIANT, t, q0, R, S, Cp, 1, pa, pb, pad, r, sx, c);
+            const bool tap_ok = r >= 0 && r < R && sx >= 0 && sx < S && co_l < nrow && cb < Cin;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (tap_ok) {
+                const float4* row = reinterpret_cast<const float4*>(wtile + (co_l * RS + r * S + sx) * TCP + c8_l * 8);
+                const float4 a = row[0], b = row[1];
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            }
+            uint4 hi, lo;
+            unsigned h2[4], l2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x0 = cb + 2 * e < Cin ? v[2 * e] * wscale : 0.f, x1 = cb + 2 * e + 1 < Cin ? v[2 * e + 1] * wscale : 0.f;
+                split16x2(x0, x1, f16, h2[e], l2[e]);
+            }
+            hi = make_uint4(h2[0], h2[1], h2[2], h2[3]); lo = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+            const long o = ((long)co * T + t) * Ca + q0;
+            *reinterpret_cast<uint4*>(Whi + o) = hi;
+            if (Wlo) *reinterpret_cast<uint4*>(Wlo + o) = lo;
+        }
+    }
+}
+template <int VARIANT, int RS>
+static void pack_tiled_launch(const float* w, int D0, int D1, int Cp, int pa, int pb, int pad, int Cout, int Ca, void* W_hi, void* W_lo,
+                              int f16, float wscale, cudaStream_t st) {
+    constexpr bool CONVT = VARIANT == DSR_TC_W_CONVT_PH || VARIANT == DSR_TC_W_CONV_DGRAD;
+    constexpr int TCO = CONVT ? 8 : 2, TC = CONVT ? 64 : 128;
+    const int Kc = VARIANT == DSR_TC_W_CONV_S2D ? Cp : Ca;
+    const long tiles = (long)dsr_cdiv(Kc, TC) * dsr_cdiv(Cout, TCO);
+    const long cap = (long)dsr_num_sms() * (pa < 0 ? 2 : 6);
+    const dim3 grid((unsigned)(tiles < cap ? tiles : cap), pa < 0 ? 4 : 1);
+    tc_pack_weight_tiled_kernel<VARIANT, RS><<<grid, 256, 0, st>>>(w, D0, D1, Cp, pa, pb, pad, Cout, Ca, (unsigned short*)W_hi,
+                                                                  (unsigned short*)W_lo, f16, wscale);
+}
 // packed weight gradient [D0][T*Ca] (row = parameter dim 0, K channel = parameter dim 1) -> parameter layout
 __global__ void tc_unpack_wgrad_kernel(const float* __restrict__ dWp, int D0, int D1, int R, int S, int variant, int Cp,
                                        int T, int Ca, float* __restrict__ grad, int accumulate) {
@@ -812,6 +901,24 @@ extern "C" int dsr_tc_pack_weight(const float* w, int D0, int D1, int R, int S, 
     DSR_REQUIRE(!((uintptr_t)W_hi & 15) && !((uintptr_t)W_lo & 15), "packed weight buffers must be 16-byte aligned");
     long total = (long)Cout * T * (Ca / 8);
     DSR_REQUIRE(phase_a >= 0 || variant == DSR_TC_W_CONVT_PH, "phase -1 (all four phases, stacked rows) is for the transposed-conv variant");
+    {
+        // big layers: shared-memory tiled form (DSR_PACK_TILED=0 keeps the gather kernel, for A/B tests)
+        const char* e = getenv("DSR_PACK_TILED");
+        const bool convT = variant == DSR_TC_W_CONVT_PH || variant == DSR_TC_W_CONV_DGRAD;
+        const bool kind_ok = variant == DSR_TC_W_CONV || variant == DSR_TC_W_CONV_S2D || convT;
+        const int RS = R * S;
+        const int Texp = (variant == DSR_TC_W_CONV_S2D || variant == DSR_TC_W_CONVT_PH) ? 4 : RS;
+        if ((!e || atoi(e) != 0) && kind_ok && R == S && (RS == 9 || RS == 16) && T == Texp && (long)D0 * D1 * RS >= (1L << 16) &&
+            (Cp & 7) == 0) {
+#define PACK_TILED(V, K) pack_tiled_launch<V, K>(w, D0, D1, Cp, phase_a, phase_b, pad, Cout, Ca, W_hi, W_lo, f16, wscale, ST(stream))
+            if (variant == DSR_TC_W_CONV) { if (RS == 9) PACK_TILED(DSR_TC_W_CONV, 9); else PACK_TILED(DSR_TC_W_CONV, 16); }
+            else if (variant == DSR_TC_W_CONV_S2D) { if (RS == 9) PACK_TILED(DSR_TC_W_CONV_S2D, 9); else PACK_TILED(DSR_TC_W_CONV_S2D, 16); }
+            else if (variant == DSR_TC_W_CONV_DGRAD) { if (RS == 9) PACK_TILED(DSR_TC_W_CONV_DGRAD, 9); else PACK_TILED(DSR_TC_W_CONV_DGRAD, 16); }
+            else { if (RS == 9) PACK_TILED(DSR_TC_W_CONVT_PH, 9); else PACK_TILED(DSR_TC_W_CONVT_PH, 16); }
+#undef PACK_TILED
+            return dsr_check_launch("tc_pack_weight (tiled)");
+        }
+    }
     tc_pack_weight_kernel<<<dim3(dsr_grid(total, 256, phase_a < 0 ? 2 : 8), phase_a < 0 ? 4 : 1), 256, 0, ST(stream)>>>(w, D0, D1, R, S, variant, Cp, phase_a, phase_b, pad, Cout, T,
                                                                        Ca, (unsigned short*)W_hi, (unsigned short*)W_lo, f16, wscale);
     return dsr_check_launch("tc_pack_weight");

@@ -721,3 +721,37 @@ def test_wgrad2_matches_first_generation_kernel(ops):
             assert rel_l2(grads[1], grads[0]) <= 2e-6, (case, rel_l2(grads[1], grads[0]))
     finally:
         ops.CONFIG.update(old)
+
+
+# weight packing: the shared-memory tiled kernel against the gather kernel, byte for byte (csrc/conv_tc.cu)
+PACK_CASES = [  # variant, (D0, D1, R, S), Cp, T, Ca, Cout, phase
+    (0, (256, 256, 3, 3), 256, 9, 256, 256, (0, 0)),          # CONV 3x3
+    (0, (130, 200, 3, 3), 200, 9, 256, 130, (0, 0)),          # CONV, ragged channels / rows, K padding
+    (2, (512, 256, 4, 4), 256, 4, 1024, 512, (0, 0)),         # CONV_S2D 4x4 stride 2
+    (2, (128, 72, 3, 3), 80, 4, 320, 128, (0, 0)),            # CONV_S2D 3x3 (zero taps), Cp > Cin
+    (4, (256, 128, 3, 3), 256, 9, 256, 128, (0, 0)),          # CONV_DGRAD (K channel = dim 0)
+    (3, (512, 256, 4, 4), 512, 4, 512, 256, (1, 0)),          # CONVT_PH, one phase
+    (3, (300, 100, 4, 4), 304, 4, 320, 100, (-1, -1)),        # CONVT_PH, all four phases stacked, ragged
+    (3, (256, 128, 3, 3), 256, 4, 256, 128, (-1, -1)),        # CONVT_PH 3x3 (output_padding 1 form)
+]
+
+
+@pytest.mark.parametrize("case", PACK_CASES)
+@pytest.mark.parametrize("f16", [1, 0])
+def test_tiled_weight_pack_matches_gather_kernel(ops, case, f16):
+    import os
+    variant, shape, Cp, T, Ca, Cout, (pa, pb) = case
+    D0, D1, R, S = shape
+    w = (torch.randn(shape, generator=G(41)) * 0.02).cuda()
+    rows = Cout * (4 if pa < 0 else 1)
+    outs = []
+    for tiled in ("1", "0"):
+        os.environ["DSR_PACK_TILED"] = tiled
+        hi = torch.full((rows, T * Ca), -1, device="cuda", dtype=torch.int16)
+        lo = torch.full((rows, T * Ca), -1, device="cuda", dtype=torch.int16)
+        ops._call("dsr_tc_pack_weight", ops._p(w), D0, D1, R, S, variant, Cp, pa, pb, 1, Cout, T, Ca, ops._p(hi, torch.int16),
+                  ops._p(lo, torch.int16), f16, 64.0 if f16 else 1.0)
+        outs.append((hi.cpu(), lo.cpu()))
+    os.environ.pop("DSR_PACK_TILED", None)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert int((outs[0][0] != 0).sum()) > 0
