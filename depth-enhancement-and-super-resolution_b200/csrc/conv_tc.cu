@@ -1070,10 +1070,53 @@ extern "C" int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, i
     return dispatch_wg<3>(bn, mmh, mml, mah, mal, p, dWp, grid, ST(stream));
 }
 
+// Tiled inverse of the packing for the big layers (variants CONV and CONV_S2D, 3x3 / 4x4 kernels): a CTA reads the
+// [t][c0 .. c0 + 128) runs of one packed row contiguously, transposes them through shared memory and writes (or accumulates
+// into) the parameter's own contiguous [c][r][s] run.  The gather kernel above reads 4-byte elements Ca floats apart.
+template <int VARIANT, int RS>
+__global__ void __launch_bounds__(256)
+tc_unpack_wgrad_tiled_kernel(const float* __restrict__ dWp, int D0, int D1, int Cp, int Ca, float* __restrict__ grad, int accumulate) {
+    constexpr int S = RS == 9 ? 3 : 4, R = S, TC = 128, RSP = RS + 1;
+    constexpr int NAB = VARIANT == DSR_TC_W_CONV_S2D ? 4 : 1, T = VARIANT == DSR_TC_W_CONV_S2D ? 4 : RS;
+    __shared__ float gt[TC * RSP];
+    const int nc_tiles = (D1 + TC - 1) / TC, tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < D0 * nc_tiles; tile += gridDim.x) {
+        const int d0 = tile / nc_tiles, c0 = (tile - d0 * nc_tiles) * TC, nc = min(TC, D1 - c0);
+        const float* src = dWp + (long)d0 * ((long)T * Ca);
+        __syncthreads();
+        for (int i = tid; i < T * NAB * TC; i += 256) {
+            const int c_l = i % TC, u = i / TC, ab = u % NAB, t = u / NAB;
+            int r, sx;
+            if (NAB == 4) { r = 2 * (t >> 1) + (ab >> 1); sx = 2 * (t & 1) + (ab & 1); } else { r = t / S; sx = t - r * S; }
+            if (c_l < nc && r < R && sx < S) gt[c_l * RSP + r * S + sx] = __ldg(src + (long)t * Ca + ab * Cp + c0 + c_l);
+        }
+        __syncthreads();
+        float* dst = grad + ((long)d0 * D1 + c0) * RS;
+        for (int i = tid; i < nc * RS; i += 256) {
+            const int c_l = i / RS;
+            const float v = gt[c_l * RSP + (i - c_l * RS)];
+            if (accumulate) dst[i] += v; else dst[i] = v;
+        }
+    }
+}
 extern "C" int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
                                    float* grad, int accumulate, void* stream) {
     DSR_REQUIRE(dWp && grad, "null pointer");
     DSR_REQUIRE(variant == DSR_TC_W_CONV || variant == DSR_TC_W_CONV_PAIR || variant == DSR_TC_W_CONV_S2D, "unsupported variant");
+    {
+        const char* e = getenv("DSR_PACK_TILED");
+        const int RS = R * S, Texp = variant == DSR_TC_W_CONV_S2D ? 4 : RS;
+        if ((!e || atoi(e) != 0) && variant != DSR_TC_W_CONV_PAIR && R == S && (RS == 9 || RS == 16) && T == Texp &&
+            (long)D0 * D1 * RS >= (1L << 16)) {
+            const long tiles = (long)D0 * dsr_cdiv(D1, 128), cap = (long)dsr_num_sms() * 8;
+            const int grid = (int)(tiles < cap ? tiles : cap);
+#define UNPACK_TILED(V, K) tc_unpack_wgrad_tiled_kernel<V, K><<<grid, 256, 0, ST(stream)>>>(dWp, D0, D1, Cp, Ca, grad, accumulate)
+            if (variant == DSR_TC_W_CONV) { if (RS == 9) UNPACK_TILED(DSR_TC_W_CONV, 9); else UNPACK_TILED(DSR_TC_W_CONV, 16); }
+            else { if (RS == 9) UNPACK_TILED(DSR_TC_W_CONV_S2D, 9); else UNPACK_TILED(DSR_TC_W_CONV_S2D, 16); }
+#undef UNPACK_TILED
+            return dsr_check_launch("tc_unpack_wgrad (tiled)");
+        }
+    }
     tc_unpack_wgrad_kernel<<<dsr_grid((long)D0 * D1 * R * S, 256), 256, 0, ST(stream)>>>(dWp, D0, D1, R, S, variant, Cp, T, Ca, grad,
                                                                                         accumulate);
     return dsr_check_launch("tc_unpack_wgrad");

@@ -755,3 +755,23 @@ def test_tiled_weight_pack_matches_gather_kernel(ops, case, f16):
     os.environ.pop("DSR_PACK_TILED", None)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert int((outs[0][0] != 0).sum()) > 0
+
+
+@pytest.mark.parametrize("variant,shape,Cp,T,Ca", [(0, (256, 256, 3, 3), 256, 9, 256), (0, (130, 200, 3, 3), 200, 9, 256),
+                                                   (2, (512, 256, 4, 4), 256, 4, 1024), (2, (128, 72, 3, 3), 80, 4, 320),
+                                                   (0, (96, 48, 4, 4), 48, 16, 64)])
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_tiled_wgrad_unpack_matches_gather_kernel(ops, variant, shape, Cp, T, Ca, accumulate):
+    import os
+    D0, D1, R, S = shape
+    dwp = torch.randn((D0, T * Ca), generator=G(43)).cuda()
+    base = torch.randn(shape, generator=G(44)).cuda()
+    outs = []
+    for tiled in ("1", "0"):
+        os.environ["DSR_PACK_TILED"] = tiled
+        g = base.clone()
+        ops._call("dsr_tc_unpack_wgrad", ops._p(dwp), D0, D1, R, S, variant, Cp, T, Ca, ops._p(g), accumulate)
+        outs.append(g.cpu())
+    os.environ.pop("DSR_PACK_TILED", None)
+    assert torch.equal(outs[0], outs[1])
+    assert not torch.equal(outs[0], base.cpu())
