@@ -260,6 +260,7 @@ class MainModel(BaseModel):
         self._rect = None                # persistent pinned + device rectangle tables
         self._rects_staged = False
         self._side = None                # second stream for the independent frozen chain (forward)
+        self._pipe = None                # pipelined graph replay: two input slots, a frozen graph + a training graph per slot
         if self.isTrain:
             if self.gpu_ids:
                 self._build_arena()
@@ -292,6 +293,8 @@ class MainModel(BaseModel):
         # the fp64 K^-1 / crop table the normal kernels read (norms.py:75-89), uploaded once per batch
         cams = dict(cam_A=camera_table(self.K_A, self.crop_A, 0.5), cam_B=camera_table(self.K_B, self.crop_B, 0.5))
         shapes = {k: tuple(v.shape) for k, v in src.items()}
+        if self._pipeline_on():
+            return self._set_input_pipe(src, cams, shapes)
         if self._in is None or self._in["shapes"] != shapes:
             if self._graph is not None:
                 raise RuntimeError("dsr_b200: the captured CUDA graph is bound to the first batch shape; "
@@ -359,12 +362,11 @@ class MainModel(BaseModel):
             slot["done"].record()
         self._rects_staged = True
 
-    def forward(self, stage="train"):                               # main_model.py:204-336
-        B, _, H, W = self.real_depth.shape
-        self.real_hole_mask, self.real_mask = ops.hole_valid_masks(self.real_depth, self.border)
-        _, self.syn_mask = ops.hole_valid_masks(self.syn_depth, self.border)
-
-        with torch.no_grad():                                       # frozen nets (main_model.py:426)
+    def _forward_frozen(self):
+        """The frozen networks (main_model.py:232-254, no_grad per :426): G_A_d, I2D_features -> Image2Depth.  They read the
+        batch only - not the trainable weights - so a captured training loop runs them for batch i+1 beside the training
+        part of batch i (``_optimize_pipe``)."""
+        with torch.no_grad():
             # G_A_d and the image branch (I2D_features -> Image2Depth) are independent: they run on two streams (an event
             # fork / join, also inside a captured graph), so the CTAs of one chain fill the partial waves and the small
             # launches of the other
@@ -378,11 +380,21 @@ class MainModel(BaseModel):
                     self.syn2real_depth = self.netG_A_d(self.syn_depth, self.syn_image)
             else:
                 self.syn2real_depth = self.netG_A_d(self.syn_depth, self.syn_image)
-            images = torch.cat([self.syn_image, self.real_image], 0)
-            image_features = self.netI2D_features(images)
-            depth_by_image = self.netImage2Depth(image_features)
+            self._images = torch.cat([self.syn_image, self.real_image], 0)
+            self._image_features = self.netI2D_features(self._images)
+            self._depth_by_image = self.netImage2Depth(self._image_features)
             if fork:
                 cur.wait_stream(self._side)
+
+    def forward(self, stage="train"):                               # main_model.py:204-336
+        self._forward_frozen()
+        self._forward_train(stage)
+
+    def _forward_train(self, stage="train"):
+        B, _, H, W = self.real_depth.shape
+        self.real_hole_mask, self.real_mask = ops.hole_valid_masks(self.real_depth, self.border)
+        _, self.syn_mask = ops.hole_valid_masks(self.syn_depth, self.border)
+        images, image_features, depth_by_image = self._images, self._image_features, self._depth_by_image
         self.syn_depth_by_image, self.real_depth_by_image = depth_by_image[:B], depth_by_image[B:]
 
         if not self.opt.use_masked:
@@ -490,6 +502,9 @@ class MainModel(BaseModel):
             if self.arena is not None:
                 ops.prepack(self.arena.params)     # packed copies of the trainable weights: side stream, beside the frozen nets
         self.forward()
+        self._backward_and_step()
+
+    def _backward_and_step(self):
         self.set_requires_grad([self.netG_A_d, self.netI2D_features, self.netImage2Depth], False)
         self.optimizer_G.zero_grad()
         self.backward_G()
@@ -497,11 +512,30 @@ class MainModel(BaseModel):
             self.grad_sync.finish()
         self.optimizer_G.step()
 
+    def _frozen_body(self):
+        """captured alone (pipelined mode): the frozen networks with their own accumulator pool"""
+        ops.zero_pool_reset(self.device)
+        self._forward_frozen()
+
+    def _train_body(self):
+        """captured alone (pipelined mode): everything that reads the trainable weights"""
+        ops.zero_pool_reset(self.device)
+        ops.prepack(self.arena.params)
+        self._forward_train("train")
+        self._backward_and_step()
+
     def reset_graph(self):
         """drop the captured training / inference graphs (a new batch shape, reloaded weights, orderly shutdown)"""
         if self._graph is not None:
             self._graph.reset()
         self._graph, self._eager_steps, self._graph_keep = None, 0, None
+        if getattr(self, "_pipe", None) is not None:
+            torch.cuda.synchronize()
+            for sl in self._pipe["slots"]:
+                for g in (sl["gf"], sl["gt"]):
+                    if g is not None:
+                        g.reset()
+            self._pipe = None
         st = getattr(self, "_tgraph", None)
         if st is not None and st.get("graph") is not None:
             st["graph"].reset()
@@ -514,6 +548,8 @@ class MainModel(BaseModel):
         become one."""
         if not (self.use_graph and self.device.type == "cuda" and self.isTrain):
             return self._step_body()
+        if self._pipeline_on() and getattr(self, "_pipe", None) is not None:
+            return self._optimize_pipe()
         cur = torch.cuda.current_stream()
         if self._graph is None:
             # Warm-up steps and the capture run on ONE dedicated stream: the autograd engine remembers the stream every
@@ -556,6 +592,120 @@ class MainModel(BaseModel):
         _lib.LAUNCHES += self.graph_launches
         ops.WEIGHT_EPOCH += 1                    # eager consumers must re-pack the trainable weights
 
+    # ------------------------------------------------------------------------------------------
+    # Pipelined graph replay.  The frozen networks (a third of the step) depend on the batch only, the training part leaves
+    # a B200 half idle in places (hundreds of launches that are too small for 148 SMs).  With two input slots and two
+    # captured graphs per slot - `gf` = the frozen networks, `gt` = everything that reads the trainable weights -
+    # ``set_input(batch i+1)`` replays gf on its own stream while gt of batch i is still running: the ordinary loop
+    #     for data in loader: model.set_input(data); model.optimize_parameters()
+    # overlaps them without any change, because the host runs ahead of the device.  Every batch still gets exactly one frozen
+    # pass and one training pass, in order, with the same arithmetic (tests: replay == eager).  Events order the slots:
+    # gf(slot) waits for the gt that last read the slot (`train_done`), gt waits for `frozen_done` of its slot.
+    # ------------------------------------------------------------------------------------------
+    def _pipeline_on(self):
+        return (self.use_graph and self.isTrain and self.device.type == "cuda" and type(self) is MainModel
+                and self.arena is not None and getattr(self.opt, "pipeline_frozen", True) and ops.CONFIG.get("pipeline_frozen", True))
+
+    def _set_input_pipe(self, src, cams, shapes):
+        P = getattr(self, "_pipe", None)
+        if P is None or P["shapes"] != shapes:
+            if P is not None and any(sl["gt"] is not None for sl in P["slots"]):
+                raise RuntimeError("dsr_b200: the captured CUDA graphs are bound to the first batch shape; "
+                                   "call reset_graph() before changing it")
+            mk = lambda: dict(inp={k: torch.empty(v.shape, device=self.device, dtype=torch.float32) for k, v in src.items()},
+                              cams={k: torch.empty(v.shape, device=self.device, dtype=torch.float64) for k, v in cams.items()},
+                              gf=None, gt=None, outs=None, keep=None, has_frozen=False, launches=0,
+                              ready=torch.cuda.Event(), frozen_done=torch.cuda.Event(), train_done=torch.cuda.Event())
+            P = self._pipe = dict(shapes=shapes, slots=[mk(), mk()], turn=0, cur=0, s_frozen=torch.cuda.Stream())
+            for sl in P["slots"]:
+                sl["train_done"].record()
+        k = P["turn"]
+        P["turn"], P["cur"] = k ^ 1, k
+        sl, sf = P["slots"][k], P["s_frozen"]
+        # the training part that last read this slot (two steps ago) is done.  (Device-resident input tensors must be complete
+        # when set_input is called: waiting for the caller's stream here would wait for the training part of the previous
+        # batch, which is exactly what this stream is meant to run beside.)
+        sf.wait_event(sl["train_done"])
+        with torch.cuda.stream(sf):
+            for name, v in src.items():
+                sl["inp"][name].copy_(self._pinned(v), non_blocking=True)
+            for name, v in cams.items():
+                sl["cams"][name].copy_(v.pin_memory(), non_blocking=True)
+            sl["ready"].record()
+            sl["has_frozen"] = sl["gf"] is not None
+            if sl["gf"] is not None:
+                sl["gf"].replay()
+                sl["frozen_done"].record()
+        for name in src:
+            setattr(self, name, sl["inp"][name])
+        for name in cams:
+            setattr(self, name, sl["cams"][name])
+        if sl["outs"] is not None:
+            self.__dict__.update(sl["outs"])         # result attributes now mean THIS slot's tensors
+        torch.cuda.current_stream().wait_event(sl["ready"])     # eager consumers (warm-up steps, forward('test')) see the inputs
+
+    def _optimize_pipe(self):
+        from . import _lib
+        P = self._pipe
+        sl, sf = P["slots"][P["cur"]], P["s_frozen"]
+        cur = torch.cuda.current_stream()
+        B, _, H, W = self.real_depth.shape
+        if sl["gt"] is None:
+            if self._gstream is None:
+                self._gstream = torch.cuda.Stream()
+            gs = self._gstream
+            gs.wait_stream(cur)
+            with torch.cuda.stream(gs):
+                if self._eager_steps < self.graph_warmup:
+                    self._eager_steps += 1
+                    self._step_body()
+                    cur.wait_stream(gs)
+                    sl["train_done"].record(cur)
+                    return
+                for k, v in list(vars(self).items()):       # drop the previous step's autograd graph
+                    if torch.is_tensor(v) and v.grad_fn is not None:
+                        setattr(self, k, v.detach())
+                if self._rect is None:
+                    self._stage_rects(B, H, W, "train")
+                self._rects_staged = True                   # capture records kernels only: the host RNG must not advance
+                torch.cuda.synchronize()
+                l0 = _lib.LAUNCHES
+                gf, gt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                prev = ops.zero_pool_select("frozen")       # gf of one slot runs beside gt of the other: separate accumulators
+                try:
+                    self._frozen_body()                     # one eager pass arms the pool: a captured reset clears what the
+                    torch.cuda.synchronize()                # pool has handed out BEFORE the capture (its high-water mark)
+                    l0 = _lib.LAUNCHES
+                    with ops.capturing():
+                        with torch.cuda.graph(gf, stream=sf):
+                            self._frozen_body()
+                finally:
+                    ops.zero_pool_select(prev)
+                with ops.capturing():
+                    with torch.cuda.graph(gt, stream=gs):
+                        self._train_body()
+                sl["gf"], sl["gt"] = gf, gt
+                sl["keep"] = ops.packed_weight_refs(self)   # the graphs read these buffers through raw pointers
+                sl["launches"] = _lib.LAUNCHES - l0
+                sl["outs"] = {k: v for k, v in vars(self).items() if torch.is_tensor(v) or isinstance(v, LazyScalar)}
+                self.graph_launches = sl["launches"]
+            cur.wait_stream(gs)
+        self.optimizer_G.sync_hyper()
+        self._stage_rects(B, H, W, "train")
+        self._rects_staged = False
+        if not sl["has_frozen"]:                 # this slot's frozen graph did not exist yet when set_input ran
+            sf.wait_stream(cur)
+            with torch.cuda.stream(sf):
+                sl["gf"].replay()
+                sl["frozen_done"].record()
+            sl["has_frozen"] = True
+        cur.wait_event(sl["frozen_done"])
+        sl["gt"].replay()
+        sl["train_done"].record(cur)
+        self.__dict__.update(sl["outs"])
+        _lib.LAUNCHES += sl["launches"]
+        ops.WEIGHT_EPOCH += 1                    # eager consumers must re-pack the trainable weights
+
     def calculate(self, stage="test"):                              # main_model.py:433-436
         self.forward(stage)
         self.backward_G(back=False)
@@ -566,8 +716,8 @@ class MainModel(BaseModel):
         eagerly, the third captures, later calls draw the (size-zero) test-stage rectangles on the host in the reference's
         RNG order and replay ~400 launches as one.  Inputs come from ``set_input`` (persistent device buffers); the
         result tensors (``pred_real_depth`` ...) keep their addresses and are overwritten by every replay."""
-        if self.device.type != "cuda":
-            return self.forward("test")
+        if self.device.type != "cuda" or getattr(self, "_pipe", None) is not None:
+            return self.forward("test")      # (a pipelined training model alternates its input slots: no fixed graph inputs)
         B, _, H, W = self.real_depth.shape
         key = (B, H, W)
         st = getattr(self, "_tgraph", None)

@@ -79,14 +79,21 @@ def planes(x):
 class _ZeroPool:
     """Pre-zeroed fp64 scratch for the step's accumulators (norm statistics, IN-backward sums, bias-gradient sums,
     loss reductions): ~200 tiny buffers per step come out of one arena that is cleared by ONE memset per step
-    (``zero_pool_reset``, called by the model at the top of the step) instead of ~200 fill kernels."""
+    (``zero_pool_reset``, called by the model at the top of the step) instead of ~200 fill kernels.
+    Pools are named: two captured graphs that may run at the same time (the frozen networks of the next batch beside the
+    training part of the current one, ``MainModel`` pipelining) must not share accumulators, so each selects its own
+    (``zero_pool_select``)."""
     CAP = 1 << 22            # doubles (32 MB)
 
     def __init__(self):
         self.buf, self.used, self.high = {}, {}, {}
+        self.name = "step"
+
+    def _key(self, device):
+        return (device.type, device.index, self.name)
 
     def take(self, n, device):
-        key = (device.type, device.index)
+        key = self._key(device)
         if key not in self.buf:
             return torch.zeros(n, device=device, dtype=torch.float64)       # pool not armed on this device
         n8 = (n + 7) // 8 * 8
@@ -98,7 +105,7 @@ class _ZeroPool:
         return self.buf[key][u:u + n]
 
     def reset(self, device):
-        key = (device.type, device.index)
+        key = self._key(device)
         if key not in self.buf:
             self.buf[key] = torch.zeros(self.CAP, device=device, dtype=torch.float64)
             self.used[key] = 0
@@ -118,6 +125,12 @@ _ZERO_POOL = _ZeroPool()
 def zero_pool_reset(device):
     """call once at the top of a step: re-zeroes what the previous step handed out"""
     _ZERO_POOL.reset(torch.device(device))
+
+
+def zero_pool_select(name="step"):
+    """-> the previous name.  Accumulators taken from now on come out of the pool `name` (see _ZeroPool)."""
+    prev, _ZERO_POOL.name = _ZERO_POOL.name, name
+    return prev
 
 
 def _zeros_f64(n, device):
@@ -354,7 +367,7 @@ def packed_weight_refs(model):
         for p in net.parameters():
             c = getattr(p, "_dsr_pack", None)
             if c:
-                keep.append([v for k, v in c.items() if k != "stamp"])
+                keep.append([v for k, v in c.items() if k not in ("stamp", "_ev")])
     return keep
 
 
@@ -420,19 +433,30 @@ def prepack(params):
     if not todo:
         return
     with _on_side(True, todo[0][0].device):
+        side = torch.cuda.current_stream()
         for w, (kind, plan, Co, phase, pad, dtype, npass) in todo:
             if kind == "phases":
                 _tc_weights_phases(w, plan, Co, pad, dtype, npass=npass)
             else:
                 _tc_weights(w, plan, Co, phase, pad, dtype, npass=npass)
+            # one event per packed copy: its first consumer waits for THIS copy only (inside a captured graph an event is
+            # just a dependency edge), so the trainable forward pass starts while the later layers are still being packed
+            ev = torch.cuda.Event()
+            ev.record(side)
+            _pack_cache(w)["_ev"] = ev          # (a later copy of the same weight overwrites it: same stream, so it covers both)
     _SIDE["prepack_pending"] = True
 
 
 def _prepack_join(weight):
-    if _SIDE.get("prepack_pending") and weight.data_ptr() in DIRECT_GRADS and \
-            torch.cuda.current_stream() == _SIDE.get("main"):
-        _SIDE["prepack_pending"] = False
-        join_side()
+    """the consumer's stream waits for the packed copies of THIS weight (made on the side stream by `prepack`)"""
+    if _SIDE.get("prepack_pending") and weight.data_ptr() in DIRECT_GRADS:
+        c = getattr(weight, "_dsr_pack", None)
+        ev = c.get("_ev") if c else None
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        elif torch.cuda.current_stream() == _SIDE.get("main"):     # no event (copy made elsewhere): join the whole stream
+            _SIDE["prepack_pending"] = False
+            join_side()
 
 
 def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None, npass=None):

@@ -134,7 +134,7 @@ def test_cuda_graph_replay_matches_eager(built_lib):
     for it in range(4):                                 # 2 eager warm-up steps, capture + replay, one more replay
         m.set_input(batches[it % 2])
         m.optimize_parameters(it, 1)
-    assert m._graph is not None and m.optimizer_G.n_steps == 4
+    assert (m._graph is not None or m._pipe is not None) and m.optimizer_G.n_steps == 4
     state = (m.arena.flat, m.arena.exp_avg, m.arena.exp_avg_sq, m.optimizer_G.step_dev)
     snap = [t.clone() for t in state]
     out = []
@@ -155,6 +155,47 @@ def test_cuda_graph_replay_matches_eager(built_lib):
     assert cosine(ga.cpu(), gb.cpu()) >= 0.9999
     assert float((wa - wb).abs().max()) <= 2.1e-4          # at most a sign flip of a noise-level gradient: 2 * lr
     assert m.optimizer_G.n_steps == 5
+
+
+def test_pipelined_replay_matches_single_graph_replay(built_lib):
+    """The pipelined loop (frozen networks of batch i+1 replayed beside the training part of batch i, two input slots) against
+    the single-graph loop on the same sequence of DIFFERENT batches: same losses step by step (first step to fp32 noise, later
+    steps within the growth of that noise through Adam), and the result attributes always belong to the batch just trained."""
+    from dsr_b200 import ops
+    host = build_host_model(2, 128, 128)
+    batches = [ref_step.synthetic_batch(2, 128, 128, seed=s, depth_kind="smooth") for s in (1, 2, 3)]
+    runs = []
+    for pipe in (True, False):
+        ops.CONFIG["pipeline_frozen"] = pipe
+        try:
+            m = rehome(host, host.opt, [0])
+            m.use_graph = True
+            m._train()
+            np.random.seed(7)
+            losses = []
+            for it in range(7):                          # 2 eager steps, 2 capturing steps (one per slot), 3 pure replays
+                m.set_input(batches[it % 3])
+                m.optimize_parameters(it, 1)
+                losses.append(m.loss_G.detach().clone())     # device-side copy, no synchronisation: the host keeps running ahead
+            assert (m._pipe is not None) == pipe
+            # the attributes of the last step belong to the last batch's slot
+            last = (float(m.loss_G), m.pred_real_depth.detach().clone(), m.real_depth.detach().clone())
+            runs.append((last, m.optimizer_G.n_steps, [float(x) for x in losses]))
+            m.reset_graph()
+        finally:
+            ops.CONFIG["pipeline_frozen"] = True
+    (la, pa, da), na, seq_a = runs[0]
+    (lb, pb, db), nb, seq_b = runs[1]
+    assert na == nb == 7
+    assert abs(seq_a[0] - seq_b[0]) <= 1e-5 * abs(seq_b[0])
+    for x, y in zip(seq_a, seq_b):
+        assert abs(x - y) <= 5e-3 * abs(y), (seq_a, seq_b)
+    assert torch.equal(da.cpu(), batches[6 % 3]["B_d"]) and torch.equal(db.cpu(), batches[6 % 3]["B_d"])
+    assert abs(la - lb) <= 5e-3 * abs(lb), (la, lb)              # seven Adam steps of amplified atomics noise
+    # (the prediction itself is not compared after seven steps: at this initialisation it is a noise-level map whose relative
+    # L2 between two EAGER runs is already ~0.1 by then; test_cuda_graph_replay_matches_eager pins one pipelined replay
+    # against one eager step from the same state to 1e-5)
+    assert pa.shape == pb.shape
 
 
 def test_calculate_eval_mode_and_visuals(model_and_oracle):
