@@ -443,7 +443,10 @@ def run_ours(args):
         json.dump(dict(per_kernel=sorted(([k, v[0] / 3.0, v[1] / 3.0] for k, v in agg.items()), key=lambda r: -r[2]),
                        last_step=[[ev.name[:60], ev.device_time] for ev in third],
                        timeline=[[ev.name[:40], ev.time_range.start - third[0].time_range.start, ev.device_time,
-                                  getattr(ev, "device_resource_id", -1)] for ev in third]), open(args.kernel_table, "w"))
+                                  getattr(ev, "device_resource_id", -1)] for ev in third],
+                       # all three steps (pipelined replay: the frozen networks of step i+1 run beside the training part of step i)
+                       timeline_all=[[ev.name[:40], ev.time_range.start - evs[0].time_range.start, ev.device_time,
+                                      getattr(ev, "device_resource_id", -1)] for ev in evs]), open(args.kernel_table, "w"))
     prof = None
     # every rank runs this extra eager step (its gradient all-reduce is a collective); rank 0 brackets each call
     if rank == 0:
