@@ -2,6 +2,7 @@
 // stencils proper live in stencil_tiled.cu.  (HBM-bound; NCHW fp32 planes exactly as the reference holds them.)  Reference call sites: models/main_model.py:208-230 (masks),
 // :257-298 (rectangle holes), :340-417 (loss stack), models/norms.py (normals),
 // models/pytorch_ssim/__init__.py (SSIM).  C-ABI entry points at the bottom (include/dsr_b200.h).
+#include <stdlib.h>
 #include "common.cuh"
 #include "stencil_math.cuh"
 #include "../../include/dsr_b200.h"
@@ -119,6 +120,95 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, 
     if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
+// Rolling form: SSIM is bound by the fp32 pipe, not by HBM (five 11 x 11 separable windows = ~130 FMAs per pixel; at the HBM
+// rate that would be 104 TFMA/s against 37), and the tiled kernel above spends its issue slots on shared-memory loads instead:
+// 22 per pixel in the horizontal pass, 55 in the vertical one, plus 1.7x halo recomputation.  Here one thread owns ONE output
+// column and walks down the rows of a chunk: the horizontal pass reads the current input row from a double-buffered
+// shared-memory row (22 conflict-free loads, one barrier per row, the next row's global loads already in flight), the vertical
+// pass is a SCATTER into 11 x 5 accumulators that live in registers - row r adds g[k] * hz(r) to the 11 output rows it
+// touches, the oldest accumulator is complete and leaves.  The 11 phases of the accumulator ring are unrolled so that every
+// register index is static.
+#define SSIMR_NT 128
+#define SSIMR_W (SSIMR_NT + 2 * SSIM_R)
+__global__ void __launch_bounds__(SSIMR_NT, 4)
+ssim_roll_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows, int chunks,
+                 double* __restrict__ out, float* __restrict__ map) {
+    __shared__ float sa[2][SSIMR_W + 2], sb[2][SSIMR_W + 2];
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    const int pl = blockIdx.z, i0 = blockIdx.y * rows, i1 = min(i0 + rows, H), j0 = blockIdx.x * SSIMR_NT, j = j0 + tid;
+    const float* pa = a + (long)pl * H * W;
+    const float* pb = b + (long)pl * H * W;
+    float g[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) g[k] = c_gauss[k];
+    // columns this thread stages: s = tid (image column j0 - 5 + tid) and, for the first 10 threads, s = 128 + tid
+    const int c1 = j0 - SSIM_R + tid, c2 = c1 + SSIMR_NT;
+    const bool in1 = c1 >= 0 && c1 < W, in2 = tid < 2 * SSIM_R && c2 < W;
+    auto ld = [&](const float* p, int r, int c, bool in) { return (in && r >= 0 && r < H) ? __ldg(p + (long)r * W + c) : 0.f; };
+    const int r0 = i0 - SSIM_R, r1 = i1 + SSIM_R;                 // input rows r0 .. r1 - 1 (zero outside the image)
+    float na1 = ld(pa, r0, c1, in1), nb1 = ld(pb, r0, c1, in1), na2 = ld(pa, r0, c2, in2), nb2 = ld(pb, r0, c2, in2);
+    sa[r0 & 1][tid] = na1; sb[r0 & 1][tid] = nb1;
+    if (tid < 2 * SSIM_R) { sa[r0 & 1][SSIMR_NT + tid] = na2; sb[r0 & 1][SSIMR_NT + tid] = nb2; }
+    na1 = ld(pa, r0 + 1, c1, in1); nb1 = ld(pb, r0 + 1, c1, in1); na2 = ld(pa, r0 + 1, c2, in2); nb2 = ld(pb, r0 + 1, c2, in2);
+    __syncthreads();
+    float acc[11][5];
+#pragma unroll
+    for (int k = 0; k < 11; ++k)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[k][m] = 0.f;
+    double total = 0.0;
+    float part = 0.f;
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    for (int rb = r0; rb < r1; rb += 11) {
+#pragma unroll
+        for (int ph = 0; ph < 11; ++ph) {
+            const int r = rb + ph;
+            if (r < r1) {                                            // block-uniform
+                // stage row r + 1 (loaded during the previous iteration), start the loads of row r + 2
+                if (r + 1 < r1) {
+                    const int nbuf = (r + 1) & 1;
+                    sa[nbuf][tid] = na1; sb[nbuf][tid] = nb1;
+                    if (tid < 2 * SSIM_R) { sa[nbuf][SSIMR_NT + tid] = na2; sb[nbuf][SSIMR_NT + tid] = nb2; }
+                    na1 = ld(pa, r + 2, c1, in1); nb1 = ld(pb, r + 2, c1, in1); na2 = ld(pa, r + 2, c2, in2); nb2 = ld(pb, r + 2, c2, in2);
+                }
+                // horizontal pass of row r at this thread's column
+                const float* ua = sa[r & 1] + tid;
+                const float* ub = sb[r & 1] + tid;
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    const float u = ua[k], v = ub[k], gu = g[k] * u, gv = g[k] * v;
+                    h0 += gu; h1 += gv; h2 += gu * u; h3 += gv * v; h4 += gu * v;
+                }
+                // vertical scatter: input row r is tap k of output row r + 5 - k, which lives in ring slot (ph + 11 - k) % 11
+                // (slot (ph + 1) % 11 = tap 10 = the output row r - 5, complete after this update)
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    const int sl = (ph + 11 - k) % 11;
+                    acc[sl][0] += g[k] * h0; acc[sl][1] += g[k] * h1; acc[sl][2] += g[k] * h2; acc[sl][3] += g[k] * h3; acc[sl][4] += g[k] * h4;
+                }
+                const int done = (ph + 1) % 11, y = r - SSIM_R;
+                if (y >= i0 && y < i1 && j < W) {
+                    const float m1 = acc[done][0], m2 = acc[done][1];
+                    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+                    const float v1 = acc[done][2] - m11, v2 = acc[done][3] - m22, v12 = acc[done][4] - m12;
+                    const float sv = ((2.f * m12 + C1) * (2.f * v12 + C2)) / ((m11 + m22 + C1) * (v1 + v2 + C2));
+                    if (map) map[(long)pl * H * W + (long)y * W + j] = sv;
+                    part += sv;
+                }
+#pragma unroll
+                for (int m = 0; m < 5; ++m) acc[done][m] = 0.f;
+                if (((r - r0) & 31) == 31) { total += (double)part; part = 0.f; }
+                __syncthreads();
+            }
+        }
+    }
+    total += (double)part;
+    total = block_sum<double>(total, red);
+    if (tid == 0) atomicAdd(out, total);
+}
+
 // valid-depth mask of the Image Guidance step (models/I2D_model.py:223,226): out = (d < thr) ? 0 : 1
 __global__ void below_mask_kernel(const float* __restrict__ d, long n, float thr, float* __restrict__ out) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -161,6 +251,23 @@ extern "C" int dsr_ssim_fwd(const float* a, const float* b, long planes, int H, 
         for (int k = 0; k < 11; ++k) g[k] /= s;
         if (cudaMemcpyToSymbol(c_gauss, g, sizeof(g)) != cudaSuccess) { dsr_set_error("ssim: constant upload failed"); return DSR_ERR_CUDA; }
         init = true;
+    }
+    static int mode = -1;                          // DSR_SSIM_KERNEL=0: the first-generation tiled kernel (A/B runs)
+    if (mode < 0) { const char* e = getenv("DSR_SSIM_KERNEL"); mode = e ? atoi(e) : 1; }
+    if (mode != 0 && planes <= 65535) {
+        // chunks of rows: enough CTAs for ~2 waves of 4 CTAs per SM, at least 32 rows each (10 halo rows per chunk)
+        const long strips = (long)dsr_cdiv(W, SSIMR_NT) * planes, want = (long)dsr_num_sms() * 8;
+        long chunks = (want + strips - 1) / strips;
+        if (chunks < 1) chunks = 1;
+        long rows = (H + chunks - 1) / chunks;
+        if (rows < 32) rows = 32;
+        if (rows > H) rows = H;
+        chunks = (H + rows - 1) / rows;
+        if (chunks <= 65535) {
+            dim3 grid(dsr_cdiv(W, SSIMR_NT), (unsigned)chunks, (unsigned)planes);
+            ssim_roll_kernel<<<grid, SSIMR_NT, 0, ST(stream)>>>(a, b, H, W, (int)rows, (int)chunks, out_sum, map);
+            return dsr_check_launch("ssim_fwd");
+        }
     }
     dim3 grid(dsr_cdiv(W, SSIM_T), dsr_cdiv(H, SSIM_T), (unsigned)planes);
     ssim_kernel<<<grid, 256, 0, ST(stream)>>>(a, b, H, W, out_sum, map);
