@@ -129,82 +129,94 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, 
 // touches, the oldest accumulator is complete and leaves.  The 11 phases of the accumulator ring are unrolled so that every
 // register index is static.
 #define SSIMR_NT 128
-#define SSIMR_W (SSIMR_NT + 2 * SSIM_R)
+#define SSIMR_WW (32 + 2 * SSIM_R)                 // one warp's staged row: its 32 columns + the 5-pixel halo on both sides
+__device__ __forceinline__ float2 ssim_f2(float x, float y) { return make_float2(x, y); }
 __global__ void __launch_bounds__(SSIMR_NT, 4)
 ssim_roll_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows, int chunks,
                  double* __restrict__ out, float* __restrict__ map) {
-    __shared__ float sa[2][SSIMR_W + 2], sb[2][SSIMR_W + 2];
+    // every WARP is on its own (32 output columns, its own double-buffered row in shared memory, __syncwarp only): a CTA-wide
+    // row buffer cost one block barrier per row with four warps waiting on each other (measured r2q: 11.5 % of HBM)
+    __shared__ float srow[SSIMR_NT / 32][2][2][SSIMR_WW + 2];
     __shared__ double red[32];
-    const int tid = threadIdx.x;
-    const int pl = blockIdx.z, i0 = blockIdx.y * rows, i1 = min(i0 + rows, H), j0 = blockIdx.x * SSIMR_NT, j = j0 + tid;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pl = blockIdx.z, i0 = blockIdx.y * rows, i1 = min(i0 + rows, H), j0 = blockIdx.x * SSIMR_NT + warp * 32, j = j0 + lane;
     const float* pa = a + (long)pl * H * W;
     const float* pb = b + (long)pl * H * W;
     float g[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) g[k] = c_gauss[k];
-    // columns this thread stages: s = tid (image column j0 - 5 + tid) and, for the first 10 threads, s = 128 + tid
-    const int c1 = j0 - SSIM_R + tid, c2 = c1 + SSIMR_NT;
-    const bool in1 = c1 >= 0 && c1 < W, in2 = tid < 2 * SSIM_R && c2 < W;
+    // columns this lane stages: s = lane (image column j0 - 5 + lane) and, for the first 10 lanes, s = 32 + lane
+    const int c1 = j0 - SSIM_R + lane, c2 = c1 + 32;
+    const bool in1 = c1 >= 0 && c1 < W, in2 = lane < 2 * SSIM_R && c2 < W;
     auto ld = [&](const float* p, int r, int c, bool in) { return (in && r >= 0 && r < H) ? __ldg(p + (long)r * W + c) : 0.f; };
     const int r0 = i0 - SSIM_R, r1 = i1 + SSIM_R;                 // input rows r0 .. r1 - 1 (zero outside the image)
-    float na1 = ld(pa, r0, c1, in1), nb1 = ld(pb, r0, c1, in1), na2 = ld(pa, r0, c2, in2), nb2 = ld(pb, r0, c2, in2);
-    sa[r0 & 1][tid] = na1; sb[r0 & 1][tid] = nb1;
-    if (tid < 2 * SSIM_R) { sa[r0 & 1][SSIMR_NT + tid] = na2; sb[r0 & 1][SSIMR_NT + tid] = nb2; }
-    na1 = ld(pa, r0 + 1, c1, in1); nb1 = ld(pb, r0 + 1, c1, in1); na2 = ld(pa, r0 + 1, c2, in2); nb2 = ld(pb, r0 + 1, c2, in2);
-    __syncthreads();
-    float acc[11][5];
-#pragma unroll
-    for (int k = 0; k < 11; ++k)
-#pragma unroll
-        for (int m = 0; m < 5; ++m) acc[k][m] = 0.f;
+    float (*buf)[2][SSIMR_WW + 2] = srow[warp];
     double total = 0.0;
-    float part = 0.f;
-    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-    for (int rb = r0; rb < r1; rb += 11) {
+    if (j0 < W) {                                                 // (warp-uniform: strips right of the image have nothing to do)
+        float na1 = ld(pa, r0, c1, in1), nb1 = ld(pb, r0, c1, in1), na2 = ld(pa, r0, c2, in2), nb2 = ld(pb, r0, c2, in2);
+        buf[r0 & 1][0][lane] = na1; buf[r0 & 1][1][lane] = nb1;
+        if (lane < 2 * SSIM_R) { buf[r0 & 1][0][32 + lane] = na2; buf[r0 & 1][1][32 + lane] = nb2; }
+        na1 = ld(pa, r0 + 1, c1, in1); nb1 = ld(pb, r0 + 1, c1, in1); na2 = ld(pa, r0 + 1, c2, in2); nb2 = ld(pb, r0 + 1, c2, in2);
+        __syncwarp();
+        // accumulator ring: 11 output rows in flight x (mu_a, mu_b | s_aa, s_bb | s_ab), the pairs as packed fp32 (FFMA2)
+        float2 accm[11], accs[11];
+        float accx[11];
 #pragma unroll
-        for (int ph = 0; ph < 11; ++ph) {
-            const int r = rb + ph;
-            if (r < r1) {                                            // block-uniform
-                // stage row r + 1 (loaded during the previous iteration), start the loads of row r + 2
-                if (r + 1 < r1) {
-                    const int nbuf = (r + 1) & 1;
-                    sa[nbuf][tid] = na1; sb[nbuf][tid] = nb1;
-                    if (tid < 2 * SSIM_R) { sa[nbuf][SSIMR_NT + tid] = na2; sb[nbuf][SSIMR_NT + tid] = nb2; }
-                    na1 = ld(pa, r + 2, c1, in1); nb1 = ld(pb, r + 2, c1, in1); na2 = ld(pa, r + 2, c2, in2); nb2 = ld(pb, r + 2, c2, in2);
-                }
-                // horizontal pass of row r at this thread's column
-                const float* ua = sa[r & 1] + tid;
-                const float* ub = sb[r & 1] + tid;
-                float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
+        for (int k = 0; k < 11; ++k) { accm[k] = ssim_f2(0.f, 0.f); accs[k] = ssim_f2(0.f, 0.f); accx[k] = 0.f; }
+        float part = 0.f;
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        for (int rb = r0; rb < r1; rb += 11) {
 #pragma unroll
-                for (int k = 0; k < 11; ++k) {
-                    const float u = ua[k], v = ub[k], gu = g[k] * u, gv = g[k] * v;
-                    h0 += gu; h1 += gv; h2 += gu * u; h3 += gv * v; h4 += gu * v;
-                }
-                // vertical scatter: input row r is tap k of output row r + 5 - k, which lives in ring slot (ph + 11 - k) % 11
-                // (slot (ph + 1) % 11 = tap 10 = the output row r - 5, complete after this update)
+            for (int ph = 0; ph < 11; ++ph) {
+                const int r = rb + ph;
+                if (r < r1) {                                        // warp-uniform
+                    // stage row r + 1 (loaded during the previous iteration), start the loads of row r + 2
+                    if (r + 1 < r1) {
+                        const int nbuf = (r + 1) & 1;
+                        buf[nbuf][0][lane] = na1; buf[nbuf][1][lane] = nb1;
+                        if (lane < 2 * SSIM_R) { buf[nbuf][0][32 + lane] = na2; buf[nbuf][1][32 + lane] = nb2; }
+                        na1 = ld(pa, r + 2, c1, in1); nb1 = ld(pb, r + 2, c1, in1); na2 = ld(pa, r + 2, c2, in2); nb2 = ld(pb, r + 2, c2, in2);
+                    }
+                    // horizontal pass of row r at this lane's column
+                    const float* ua = buf[r & 1][0] + lane;
+                    const float* ub = buf[r & 1][1] + lane;
+                    float2 hm = ssim_f2(0.f, 0.f), hs = ssim_f2(0.f, 0.f);
+                    float hx = 0.f;
 #pragma unroll
-                for (int k = 0; k < 11; ++k) {
-                    const int sl = (ph + 11 - k) % 11;
-                    acc[sl][0] += g[k] * h0; acc[sl][1] += g[k] * h1; acc[sl][2] += g[k] * h2; acc[sl][3] += g[k] * h3; acc[sl][4] += g[k] * h4;
-                }
-                const int done = (ph + 1) % 11, y = r - SSIM_R;
-                if (y >= i0 && y < i1 && j < W) {
-                    const float m1 = acc[done][0], m2 = acc[done][1];
-                    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
-                    const float v1 = acc[done][2] - m11, v2 = acc[done][3] - m22, v12 = acc[done][4] - m12;
-                    const float sv = ((2.f * m12 + C1) * (2.f * v12 + C2)) / ((m11 + m22 + C1) * (v1 + v2 + C2));
-                    if (map) map[(long)pl * H * W + (long)y * W + j] = sv;
-                    part += sv;
-                }
+                    for (int k = 0; k < 11; ++k) {
+                        const float2 uv = ssim_f2(ua[k], ub[k]);
+                        const float2 guv = __fmul2_rn(ssim_f2(g[k], g[k]), uv);
+                        hm = __fadd2_rn(hm, guv);
+                        hs = __ffma2_rn(guv, uv, hs);
+                        hx = fmaf(guv.x, uv.y, hx);
+                    }
+                    // vertical scatter: input row r is tap k of output row r + 5 - k, which lives in ring slot (ph + 11 - k) % 11
+                    // (slot (ph + 1) % 11 = tap 10 = the output row r - 5, complete after this update)
 #pragma unroll
-                for (int m = 0; m < 5; ++m) acc[done][m] = 0.f;
-                if (((r - r0) & 31) == 31) { total += (double)part; part = 0.f; }
-                __syncthreads();
+                    for (int k = 0; k < 11; ++k) {
+                        const int sl = (ph + 11 - k) % 11;
+                        const float2 gk = ssim_f2(g[k], g[k]);
+                        accm[sl] = __ffma2_rn(gk, hm, accm[sl]);
+                        accs[sl] = __ffma2_rn(gk, hs, accs[sl]);
+                        accx[sl] = fmaf(g[k], hx, accx[sl]);
+                    }
+                    const int done = (ph + 1) % 11, y = r - SSIM_R;
+                    if (y >= i0 && y < i1 && j < W) {
+                        const float m1 = accm[done].x, m2 = accm[done].y;
+                        const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+                        const float v1 = accs[done].x - m11, v2 = accs[done].y - m22, v12 = accx[done] - m12;
+                        const float sv = ((2.f * m12 + C1) * (2.f * v12 + C2)) / ((m11 + m22 + C1) * (v1 + v2 + C2));
+                        if (map) map[(long)pl * H * W + (long)y * W + j] = sv;
+                        part += sv;
+                    }
+                    accm[done] = ssim_f2(0.f, 0.f); accs[done] = ssim_f2(0.f, 0.f); accx[done] = 0.f;
+                    if (((r - r0) & 31) == 31) { total += (double)part; part = 0.f; }
+                    __syncwarp();
+                }
             }
         }
+        total += (double)part;
     }
-    total += (double)part;
     total = block_sum<double>(total, red);
     if (tid == 0) atomicAdd(out, total);
 }
