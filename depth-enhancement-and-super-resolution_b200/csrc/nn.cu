@@ -920,20 +920,23 @@ struct LossTerms {
     int cnt[LOSS_MAX_TERMS];
     int n;
 };
-__global__ void loss_sum_fwd_kernel(const LossTerms t, float scale, float* __restrict__ out) {
+__global__ void loss_sum_fwd_kernel(const LossTerms t, float scale, float* __restrict__ out, int* __restrict__ nonfinite) {
     float a = 0.f;
     const int k = threadIdx.x;
     if (k < t.n)
         for (int j = 0; j < t.cnt[k]; ++j) a += t.w[k][j] * t.p[k][j];
     a = warp_sum(a);
-    if (k == 0) *out = a * scale;
+    if (k == 0) {
+        *out = a * scale;
+        if (nonfinite && !isfinite(a * scale)) atomicAdd(nonfinite, 1);
+    }
 }
 __global__ void loss_sum_bwd_kernel(const float* __restrict__ g, const LossTerms t, float scale, float* __restrict__ grads) {
     const int i = threadIdx.x, k = i >> 2, j = i & 3;
     if (k < t.n) grads[i] = *g * scale * t.w[k][j];
 }
 extern "C" int dsr_loss_sum_fwd(const float* const* terms, const int* counts, const float* weights, int n, float scale, float* out,
-                                void* stream) {
+                                int* nonfinite, void* stream) {
     DSR_REQUIRE(terms && counts && weights && out && n > 0 && n <= LOSS_MAX_TERMS, "1..32 terms");
     LossTerms t;
     t.n = n;
@@ -943,7 +946,7 @@ extern "C" int dsr_loss_sum_fwd(const float* const* terms, const int* counts, co
         for (int j = 0; j < 4; ++j) t.w[k][j] = k < n ? weights[4 * k + j] : 0.f;
         DSR_REQUIRE(k >= n || (t.p[k] && t.cnt[k] >= 1 && t.cnt[k] <= 4), "every term needs a pointer and 1..4 elements");
     }
-    loss_sum_fwd_kernel<<<1, 32, 0, ST(stream)>>>(t, scale, out);
+    loss_sum_fwd_kernel<<<1, 32, 0, ST(stream)>>>(t, scale, out, nonfinite);
     return dsr_check_launch("loss_sum_fwd");
 }
 extern "C" int dsr_loss_sum_bwd(const float* g, const float* weights, int n, float scale, float* grads, void* stream) {

@@ -261,6 +261,7 @@ class MainModel(BaseModel):
         self._rects_staged = False
         self._side = None                # second stream for the independent frozen chain (forward)
         self._pipe = None                # pipelined graph replay: two input slots, a frozen graph + a training graph per slot
+        self._nonfinite = None           # device counter of NaN / Inf values of loss_G (a graph replay cannot raise by itself)
         if self.isTrain:
             if self.gpu_ids:
                 self._build_arena()
@@ -482,7 +483,9 @@ class MainModel(BaseModel):
         if opt.use_smooth_loss:
             self.loss_smooth = get_smooth_weight(pr, self.real_image, 3)                      # :407
             terms.append((self.loss_smooth, opt.w_smooth))
-        self.loss_G = ops.loss_sum(terms, opt.scale_G)                                        # :417
+        if self._nonfinite is None and self.device.type == "cuda":
+            self._nonfinite = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.loss_G = ops.loss_sum(terms, opt.scale_G, self._nonfinite)                       # :417
         if back:
             self.loss_G.backward()
             ops.join_side()          # the weight-gradient stream (ops._on_side) rejoins before anything reads the gradients
@@ -523,6 +526,17 @@ class MainModel(BaseModel):
         ops.prepack(self.arena.params)
         self._forward_train("train")
         self._backward_and_step()
+
+    def nonfinite_steps(self):
+        """How many training steps so far produced a NaN / Inf ``loss_G`` (0 = healthy).  The loss kernel counts on the
+        device - also inside a replayed CUDA graph, where nothing can raise; reading the counter synchronises, so a training
+        loop asks every N steps.  ``check_finite()`` raises instead."""
+        return 0 if self._nonfinite is None else int(self._nonfinite.item())
+
+    def check_finite(self):
+        n = self.nonfinite_steps()
+        if n:
+            raise FloatingPointError(f"dsr_b200: loss_G was NaN / Inf in {n} training step(s)")
 
     def reset_graph(self):
         """drop the captured training / inference graphs (a new batch shape, reloaded weights, orderly shutdown)"""

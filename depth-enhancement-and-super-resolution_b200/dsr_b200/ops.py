@@ -1807,7 +1807,7 @@ class _LossSum(Function):
     hands every term its gradient.  main_model.py:393-417."""
 
     @staticmethod
-    def forward(ctx, scale, weights, *terms):
+    def forward(ctx, scale, weights, flag, *terms):
         import ctypes
         n = len(terms)
         ts = [t.detach().contiguous().view(-1) for t in terms]
@@ -1821,7 +1821,7 @@ class _LossSum(Function):
             flat += [float(x) for x in w] + [0.0] * (4 - len(w))
         wts = (ctypes.c_float * len(flat))(*flat)
         out = torch.empty((), device=ts[0].device, dtype=torch.float32)
-        _call("dsr_loss_sum_fwd", ptrs, counts, wts, n, float(scale), _p(out))
+        _call("dsr_loss_sum_fwd", ptrs, counts, wts, n, float(scale), _p(out), _p(flag, torch.int32))
         ctx.cfg = (float(scale), wts, n, [tuple(t.shape) for t in terms])
         return out
 
@@ -1835,13 +1835,14 @@ class _LossSum(Function):
             m = 1
             for d in shp:
                 m *= d
-            outs.append(grads[4 * k:4 * k + m].view(shp) if ctx.needs_input_grad[2 + k] else None)
-        return (None, None) + tuple(outs)
+            outs.append(grads[4 * k:4 * k + m].view(shp) if ctx.needs_input_grad[3 + k] else None)
+        return (None, None, None) + tuple(outs)
 
 
-def loss_sum(terms, scale=1.0):
-    """terms: [(tensor, weight or tuple of per-element weights), ...] -> scale * sum of the weighted elements (0-dim)."""
-    return _LossSum.apply(scale, tuple(w for _, w in terms), *[t for t, _ in terms])
+def loss_sum(terms, scale=1.0, nonfinite=None):
+    """terms: [(tensor, weight or tuple of per-element weights), ...] -> scale * sum of the weighted elements (0-dim).
+    `nonfinite`: optional int32[1] device counter, incremented whenever the result is NaN / Inf."""
+    return _LossSum.apply(scale, tuple(w for _, w in terms), nonfinite, *[t for t, _ in terms])
 
 
 def ssim(a, b):

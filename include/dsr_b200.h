@@ -189,6 +189,7 @@ int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, long n, float 
  * (`terms`, `counts`, `weights` are HOST arrays; weights is flat, 4 per term).  The backward form writes
  * grads[4 k + j] = g * scale * weights[k][j] for every term at once.  Replaces ~40 scalar multiply / add kernels per pass. */
 int dsr_loss_sum_fwd(const float* const* terms, const int* counts, const float* weights, int n, float scale, float* out,
+                     int* nonfinite /* device, may be NULL: incremented when the sum is NaN / Inf (a guard readable outside a graph) */,
                      void* stream);
 int dsr_loss_sum_bwd(const float* g, const float* weights, int n, float scale, float* grads, void* stream);
 

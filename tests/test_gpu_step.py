@@ -198,6 +198,26 @@ def test_pipelined_replay_matches_single_graph_replay(built_lib):
     assert pa.shape == pb.shape
 
 
+def test_nonfinite_loss_is_counted_on_the_device(built_lib):
+    """a NaN in the batch must not pass silently through a (replayed) step: the loss kernel counts non-finite loss_G values"""
+    host = build_host_model(1, 128, 128)
+    m = rehome(host, host.opt, [0])
+    m._train()
+    good = ref_step.synthetic_batch(1, 128, 128, seed=3, depth_kind="smooth")
+    bad = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in good.items()}
+    bad["B_d"][0, 0, 5, 7] = float("nan")
+    np.random.seed(3)
+    m.set_input(good)
+    m.optimize_parameters(0, 1)
+    assert m.nonfinite_steps() == 0
+    m.check_finite()
+    m.set_input(bad)
+    m.optimize_parameters(1, 1)
+    assert m.nonfinite_steps() == 1
+    with pytest.raises(FloatingPointError):
+        m.check_finite()
+
+
 def test_calculate_eval_mode_and_visuals(model_and_oracle):
     model, _ = model_and_oracle
     batch = ref_step.synthetic_batch(2, 128, 128, seed=2, depth_kind="noise")

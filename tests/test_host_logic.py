@@ -141,5 +141,13 @@ def test_zero_pool_clears_its_high_water_mark():
     pool.reset(dev)                  # zeroes [:152]
     c = pool.take(10, dev); c += 1   # a shorter pass ...
     pool.reset(dev)                  # ... must still clear the whole region handed out before
-    assert pool.high[("cpu", None)] >= 152
-    assert float(pool.buf[("cpu", None)][:200].abs().sum()) == 0.0
+    key = pool._key(dev)
+    assert pool.high[key] >= 152
+    assert float(pool.buf[key][:200].abs().sum()) == 0.0
+    # named pools (two captured graphs that may run at the same time must not share accumulators)
+    pool.name = "frozen"
+    pool.reset(dev)
+    d = pool.take(8, dev); d += 1
+    assert pool._key(dev) != key and float(pool.buf[key][:200].abs().sum()) == 0.0
+    pool.name = "step"
+    assert float(pool.take(8, dev).abs().sum()) == 0.0
