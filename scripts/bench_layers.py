@@ -114,7 +114,7 @@ def run(layer, ops, iters, check=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--halo", default="both", help="kernel generations to run: 0/1 = first, 1 = best available, 'k1,k2,k3' = forced list")
-    ap.add_argument("--baseoff", default="1")
+    ap.add_argument("--baseoff", default="0", help="DSR_TC2_BASEOFF (1 = descriptor base-offset mode: measured WRONG on B200, kept for the record)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--only", default="")
