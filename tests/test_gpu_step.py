@@ -198,6 +198,42 @@ def test_pipelined_replay_matches_single_graph_replay(built_lib):
     assert pa.shape == pb.shape
 
 
+def test_pipelined_replay_survives_irregular_call_patterns(built_lib):
+    """set_input twice before a step (a skipped batch), a step repeated on the same batch, an eager validation pass in the middle
+    of training and a graph reset: the pipelined loop must keep training on the batch of the LAST set_input"""
+    host = build_host_model(1, 128, 128)
+    m = rehome(host, host.opt, [0])
+    m.use_graph = True
+    m._train()
+    b = [ref_step.synthetic_batch(1, 128, 128, seed=s, depth_kind="smooth") for s in (1, 2, 3)]
+    np.random.seed(5)
+    for it in range(5):                                  # warm-up, both slots captured, one pure replay
+        m.set_input(b[it % 3])
+        m.optimize_parameters(it, 1)
+    assert m._pipe is not None and all(sl["gt"] is not None for sl in m._pipe["slots"])
+    m.set_input(b[0])
+    m.set_input(b[1])                                    # b[0] is skipped
+    m.optimize_parameters(5, 1)
+    assert torch.equal(m.real_depth.cpu(), b[1]["B_d"]) and np.isfinite(float(m.loss_G))
+    l1 = float(m.loss_G)
+    m.optimize_parameters(6, 1)                          # the same batch again (weights moved: a different loss)
+    assert torch.equal(m.real_depth.cpu(), b[1]["B_d"]) and np.isfinite(float(m.loss_G)) and float(m.loss_G) != l1
+    with torch.no_grad():                                # validation between two training steps
+        m.set_input(b[2])
+        m.forward("test")
+        pred_eager = m.pred_real_depth.detach().clone()
+        m.forward_test_graph()                           # (falls back to the eager pass on a pipelined model)
+        assert rel_l2(m.pred_real_depth.cpu(), pred_eager.cpu()) <= 1e-5
+    m.set_input(b[0])
+    m.optimize_parameters(7, 1)
+    assert torch.equal(m.real_depth.cpu(), b[0]["B_d"]) and m.optimizer_G.n_steps == 8
+    m.reset_graph()
+    assert m._pipe is None
+    m.set_input(b[1])
+    m.optimize_parameters(8, 1)                          # starts over: eager warm-up steps, new graphs later
+    assert m.optimizer_G.n_steps == 9 and m.nonfinite_steps() == 0
+
+
 def test_nonfinite_loss_is_counted_on_the_device(built_lib):
     """a NaN in the batch must not pass silently through a (replayed) step: the loss kernel counts non-finite loss_G values"""
     host = build_host_model(1, 128, 128)
