@@ -64,6 +64,38 @@ __device__ __forceinline__ T block_sum(T v, T* smem32) {
     if (w == 0) v = warp_sum(v);
     return v;
 }
+// Normalisation statistics -> (mean, scale, shift) of one (n, c): the arithmetic of dsr_norm_finalize, shared with the
+// consumers that fold the finalisation into their own prologue (dsr_tc_prep_fin, dsr_norm_apply_fwd_fin) so that both routes
+// are bit-identical.  groups 0: InstanceNorm2d(affine=False) models/networks.py:30; groups > 0: GroupNorm(groups, C, affine)
+// models/translation_network.py:46.
+struct NormFin {
+    const double* sums;      // [N][C][2] (sum, sum of squares) over P pixels; NULL = no folded finalisation
+    const float* gamma;      // [C] or NULL
+    const float* beta;       // [C] or NULL
+    float* prm_out;          // [3][N][C] written for later readers (backward pass) by one block per sample
+    long P;
+    int groups;
+    float eps;
+};
+__device__ __forceinline__ void norm_fin_one(const double* __restrict__ sums, long P, int groups, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, float eps, int n, int c, int C,
+                                             float& mean_f, float& scale, float& shift) {
+    double s = 0, q = 0, cnt;
+    const long idx = (long)n * C + c;
+    if (groups == 0) { s = sums[idx * 2]; q = sums[idx * 2 + 1]; cnt = (double)P; }
+    else {
+        int cg = C / groups, g0 = (c / cg) * cg;
+        for (int k = 0; k < cg; ++k) { s += sums[((long)n * C + g0 + k) * 2]; q += sums[((long)n * C + g0 + k) * 2 + 1]; }
+        cnt = (double)P * cg;
+    }
+    double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mean_f = (float)mean;
+    scale = groups == 0 ? rstd : rstd * (gamma ? gamma[c] : 1.f);
+    shift = groups == 0 ? 0.f : (beta ? beta[c] : 0.f);
+}
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 #endif

@@ -466,16 +466,17 @@ __device__ __forceinline__ const float* prep_cat_src(const PrepCat& cat, long pi
     return nullptr;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int W, int C, const float* __restrict__ prm,
                int act, float slope, int pad, int mode, int layout, int Cp,
                unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, unsigned short* __restrict__ Abf,
                int Ha, int Wa, int Ca,
-               int f16, double* __restrict__ csum, unsigned magic_cg, unsigned magic_cp, unsigned magic_ha) {
+               int f16, double* __restrict__ csum, int csum_reps, unsigned magic_cg, unsigned magic_cp, unsigned magic_ha, const NormFin fin) {
     extern __shared__ __align__(16) float prep_sm[];
     const int Cs = (C + 3) & ~3;                  // 16-byte aligned parameter rows
+    const bool has_prm = prm != nullptr || fin.sums != nullptr;
     float* s_prm = prep_sm;
-    float* s_sum = prep_sm + (prm ? 3 * Cs : 0);
+    float* s_sum = prep_sm + (has_prm ? 3 * Cs : 0);
     const int tid = threadIdx.x;
     // concatenated sources: per 8-channel group of the concatenation, where it lives (built once per block) - base pointer of
     // its first channel, the source's pixel pitch, and whether the whole group sits 16-byte aligned inside ONE source
@@ -508,10 +509,23 @@ tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int
     int cached_n = -1;
     for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
         const int n = magic_ha ? (int)__umulhi((unsigned)row, magic_ha) : row, ha = row - n * Ha;
-        if (prm && n != cached_n) {
+        if (has_prm && n != cached_n) {
             __syncthreads();
-            for (int i = tid; i < C; i += 256) {
-                s_prm[i] = prm[(long)n * C + i]; s_prm[Cs + i] = prm[NC + (long)n * C + i]; s_prm[2 * Cs + i] = prm[2 * NC + (long)n * C + i];
+            if (fin.sums) {
+                // folded dsr_norm_finalize: every block derives the constants of its sample from the raw sums; the block that
+                // owns the sample's first arranged row also writes them out for the readers of the backward pass
+                for (int i = tid; i < C; i += 256) {
+                    float m, sc, sh;
+                    norm_fin_one(fin.sums, fin.P, fin.groups, fin.gamma, fin.beta, fin.eps, n, i, C, m, sc, sh);
+                    s_prm[i] = m; s_prm[Cs + i] = sc; s_prm[2 * Cs + i] = sh;
+                    if (ha == 0 && fin.prm_out) {
+                        fin.prm_out[(long)n * C + i] = m; fin.prm_out[NC + (long)n * C + i] = sc; fin.prm_out[2 * NC + (long)n * C + i] = sh;
+                    }
+                }
+            } else {
+                for (int i = tid; i < C; i += 256) {
+                    s_prm[i] = prm[(long)n * C + i]; s_prm[Cs + i] = prm[NC + (long)n * C + i]; s_prm[2 * Cs + i] = prm[2 * NC + (long)n * C + i];
+                }
             }
             cached_n = n;
             __syncthreads();
@@ -555,7 +569,7 @@ tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int
 #pragma unroll
                         for (int e = 0; e < 8; ++e) if (c + e < C) v[e] = src[e];
                     }
-                    if (prm) {
+                    if (has_prm) {
                         if (full) {
                             float m[8], sc[8], sh[8];
                             *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(s_prm + c);
@@ -612,7 +626,10 @@ tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int
             for (int e = 0; e < 8; ++e) if (c + e < C) atomicAdd(&s_sum[c + e], racc[e]);
         }
         __syncthreads();
-        for (int i = tid; i < C; i += 256) atomicAdd(&csum[i], (double)s_sum[i]);
+        // csum_reps replicas of the accumulator row: block b adds into replica b % reps, so a launch of G blocks puts G / reps
+        // (not G) serialised fp64 atomics on each address and the grid can stay wide enough to saturate HBM
+        double* dst = csum + (long)(blockIdx.x % csum_reps) * C;
+        for (int i = tid; i < C; i += 256) atomicAdd(&dst[i], (double)s_sum[i]);
     }
 }
 
@@ -823,9 +840,10 @@ static int dispatch_n(int bn, const CUtensorMap& ah, const CUtensorMap& al, cons
     return DSR_ERR_UNSUPPORTED;
 }
 
-extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
-                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
-                           double* csum, void* stream) {
+static int tc_prep_launch(const float* x, int N, int H, int W, int C, const float* prm, const NormFin fin, int act, float slope, int pad,
+                          int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
+                          double* csum, int csum_reps, void* stream) {
+    DSR_REQUIRE(!csum || (csum_reps >= 1 && csum_reps <= 64), "csum_reps: 1..64 replicas of the channel-sum row");
     DSR_REQUIRE(x && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
     DSR_REQUIRE(((Ca & 63) == 0 || (Ca == 8 && layout == DSR_TC_LAYOUT_NORMAL)) && (Cp & 7) == 0 && Cp >= C,
                 "Ca must be a multiple of 64 (or 8 for the compact first-layer operand) and Cp a multiple of 8 >= C");
@@ -838,10 +856,13 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
     DSR_REQUIRE((long)N * (H + 2 * pad) * (W + 2 * pad) < (1L << 31) && C <= 8192, "tensor too large for 32-bit pixel indices");
     const long rows = (long)N * Ha;
     // with bias-gradient sums every block ends with C fp64 atomics on the same C addresses: fewer, longer blocks
-    const long cap = (long)dsr_num_sms() * (csum ? 3 : 8);
-    const int grid = (int)(rows < cap ? rows : cap);
+    const long cap = (long)dsr_num_sms() * ((csum && csum_reps < 4) ? 3 : (csum ? 6 : 8));
+    // balanced: every block gets the same number of rows (a capped grid of 1184 blocks over 1560 rows has a two-row makespan
+    // at three quarters of the blocks' worth of work)
+    const long per = (rows + cap - 1) / cap;
+    const int grid = (int)((rows + per - 1) / per);
     const size_t Cs = ((size_t)C + 3) & ~(size_t)3;
-    const size_t smem = ((prm ? 3 * Cs : 0) + (csum ? (size_t)C : 0)) * sizeof(float);
+    const size_t smem = (((prm || fin.sums) ? 3 * Cs : 0) + (csum ? (size_t)C : 0)) * sizeof(float);
     // floor(n / d) == umulhi(n, 2^32 / d + 1) whenever n * d < 2^32
     auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / d + 1); };   // 0: divisor 1
     DSR_REQUIRE((unsigned long long)Wa * (Ca >> 3) * (Ca >> 3) < (1ull << 32) && (unsigned long long)Ca * Cp < (1ull << 32) &&
@@ -851,9 +872,31 @@ extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const flo
     for (int k = 0; k < 4; ++k) { cat.p[k] = nullptr; cat.c[k] = 0; }
     DSR_REQUIRE(!((uintptr_t)A_bf & 15), "operand buffers must be 16-byte aligned");
     tc_prep_kernel<<<grid, 256, smem, ST(stream)>>>(x, cat, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
-                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, csum,
-                                                    magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha));
+                                                    (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, csum, csum ? csum_reps : 1,
+                                                    magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha), fin);
     return dsr_check_launch("tc_prep");
+}
+
+extern "C" int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, int act, float slope, int pad,
+                           int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
+                           double* csum, int csum_reps, void* stream) {
+    NormFin fin = {};
+    return tc_prep_launch(x, N, H, W, C, prm, fin, act, slope, pad, pad_mode, layout, Cp, A_hi, A_lo, A_bf, Ha, Wa, Ca, f16, csum,
+                          csum_reps, stream);
+}
+
+// dsr_tc_prep with dsr_norm_finalize folded in: the operand preparation derives (mean, scale, shift) from the raw channel
+// sums itself (same arithmetic, bit-identical) and writes prm_out for the readers of the backward pass - one launch less
+// per normalised layer on the critical path of the step
+extern "C" int dsr_tc_prep_fin(const float* x, int N, int H, int W, int C, const double* sums, int groups, const float* gamma,
+                               const float* beta, float eps, float* prm_out, int act, float slope, int pad, int pad_mode,
+                               int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
+                               double* csum, int csum_reps, void* stream) {
+    DSR_REQUIRE(sums && N > 0 && C > 0 && H > 0 && W > 0 && groups >= 0 && (groups == 0 || C % groups == 0), "bad normalisation arguments");
+    NormFin fin;
+    fin.sums = sums; fin.gamma = gamma; fin.beta = beta; fin.prm_out = prm_out; fin.P = (long)H * W; fin.groups = groups; fin.eps = eps;
+    return tc_prep_launch(x, N, H, W, C, nullptr, fin, act, slope, pad, pad_mode, layout, Cp, A_hi, A_lo, A_bf, Ha, Wa, Ca, f16, csum,
+                          csum_reps, stream);
 }
 
 // the same preparation over torch.cat((x0, x1, x2, x3), dim=1) without materialising the concatenation
@@ -889,8 +932,8 @@ extern "C" int dsr_tc_prep_cat(const float* x0, int C0, const float* x1, int C1,
                     (unsigned long long)rows * Ha < (1ull << 32), "tensor too large for the magic-number index divisions");
     DSR_REQUIRE(!((uintptr_t)A_bf & 15), "operand buffers must be 16-byte aligned");
     tc_prep_kernel<<<grid, 256, 0, ST(stream)>>>(x0, cat, N, H, W, C, nullptr, DSR_ACT_NONE, 0.f, pad, pad_mode, layout, Cp,
-                                                 (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, nullptr,
-                                                 magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha));
+                                                 (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, nullptr, 1,
+                                                 magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha), NormFin{});
     return dsr_check_launch("tc_prep_cat");
 }
 

@@ -304,20 +304,11 @@ __global__ void norm_finalize_kernel(const double* __restrict__ sums, int N, int
     long NC = (long)N * C;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < NC; idx += (long)gridDim.x * blockDim.x) {
         int n = (int)(idx / C), c = (int)(idx % C);
-        double s = 0, q = 0, cnt;
-        if (groups == 0) { s = sums[idx * 2]; q = sums[idx * 2 + 1]; cnt = (double)P; }
-        else {
-            int cg = C / groups, g0 = (c / cg) * cg;
-            for (int k = 0; k < cg; ++k) { s += sums[((long)n * C + g0 + k) * 2]; q += sums[((long)n * C + g0 + k) * 2 + 1]; }
-            cnt = (double)P * cg;
-        }
-        double mean = s / cnt;
-        double var = q / cnt - mean * mean;
-        if (var < 0) var = 0;
-        float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        prm[idx] = (float)mean;
-        prm[NC + idx] = groups == 0 ? rstd : rstd * (gamma ? gamma[c] : 1.f);
-        prm[2 * NC + idx] = groups == 0 ? 0.f : (beta ? beta[c] : 0.f);
+        float mean, scale, shift;
+        norm_fin_one(sums, P, groups, gamma, beta, eps, n, c, C, mean, scale, shift);
+        prm[idx] = mean;
+        prm[NC + idx] = scale;
+        prm[2 * NC + idx] = shift;
     }
 }
 
@@ -369,6 +360,36 @@ norm_apply_fwd_vec4_kernel(const float4* __restrict__ x, const float* __restrict
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = (i % C4) * 4;
         const float4 m = ld4(pm + c), sc = ld4(pm + NC + c), sh = ld4(pm + 2 * NC + c);
+        float4 v = x[base + i];
+        v.x = (v.x - m.x) * sc.x + sh.x; v.y = (v.y - m.y) * sc.y + sh.y;
+        v.z = (v.z - m.z) * sc.z + sh.z; v.w = (v.w - m.w) * sc.w + sh.w;
+        if (act == DSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (res) { const float4 r = res[base + i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        y[base + i] = v;
+    }
+}
+// the same pass with dsr_norm_finalize folded in: each block derives its sample's constants from the raw sums into shared
+// memory (norm_fin_one: the finalize kernel's own arithmetic), block x = 0 of every sample writes them out for the backward pass
+__global__ void __launch_bounds__(256, 6)
+norm_apply_fwd_fin_vec4_kernel(const float4* __restrict__ x, const NormFin fin, const float4* __restrict__ res,
+                               float4* __restrict__ y, int N, int P, int C4, int act) {
+    extern __shared__ __align__(16) float s_fin[];          // [3][C]
+    const int n = blockIdx.y, C = C4 * 4;
+    const long NC = (long)N * C;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float m, sc, sh;
+        norm_fin_one(fin.sums, fin.P, fin.groups, fin.gamma, fin.beta, fin.eps, n, c, C, m, sc, sh);
+        s_fin[c] = m; s_fin[C + c] = sc; s_fin[2 * C + c] = sh;
+        if (blockIdx.x == 0 && fin.prm_out) {
+            fin.prm_out[(long)n * C + c] = m; fin.prm_out[NC + (long)n * C + c] = sc; fin.prm_out[2 * NC + (long)n * C + c] = sh;
+        }
+    }
+    __syncthreads();
+    const long base = (long)n * P * C4;
+    const int total = P * C4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = (i % C4) * 4;
+        const float4 m = ld4(s_fin + c), sc = ld4(s_fin + C + c), sh = ld4(s_fin + 2 * C + c);
         float4 v = x[base + i];
         v.x = (v.x - m.x) * sc.x + sh.x; v.y = (v.y - m.y) * sc.y + sh.y;
         v.z = (v.z - m.z) * sc.z + sh.z; v.w = (v.w - m.w) * sc.w + sh.w;
@@ -558,6 +579,15 @@ __global__ void cvt_f64_f32_kernel(const double* __restrict__ in, long stride_in
     }
 }
 
+// out (+)= sum over `reps` replica rows of a double accumulator (the replicated bias-gradient sums of dsr_tc_prep)
+__global__ void sum_reps_f64_f32_kernel(const double* __restrict__ in, int reps, long n, float* __restrict__ out, int accumulate) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double a = 0;
+        for (int r = 0; r < reps; ++r) a += in[(long)r * n + i];
+        if (accumulate) out[i] += (float)a; else out[i] = (float)a;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Adam over one flat fp32 arena (torch.optim.Adam semantics, no weight decay, no amsgrad)
 // ------------------------------------------------------------------------------------------
@@ -688,6 +718,27 @@ extern "C" int dsr_norm_apply_fwd(const float* x, const float* prm, const float*
         norm_apply_fwd_kernel<<<dsr_grid((long)N * P * C, TPB), TPB, 0, ST(stream)>>>(x, prm, res, y, N, P, C, act);
     }
     return dsr_check_launch("norm_apply_fwd");
+}
+// dsr_norm_finalize + dsr_norm_apply_fwd in one launch (prm_out = what dsr_norm_finalize would have written, bit-identical)
+extern "C" int dsr_norm_apply_fwd_fin(const float* x, const double* sums, int groups, const float* gamma, const float* beta,
+                                      float eps, float* prm_out, const float* res, float* y, int N, long P, int C, int act,
+                                      void* stream) {
+    DSR_REQUIRE(x && sums && prm_out && y && N > 0 && C > 0 && P > 0, "null pointer / bad shape");
+    DSR_REQUIRE(groups >= 0 && (groups == 0 || C % groups == 0), "C must be a multiple of groups");
+    const bool vec = !(C & 3) && !((uintptr_t)x & 15) && !((uintptr_t)y & 15) && !((uintptr_t)res & 15) &&
+                     P * (C / 4) < (1L << 31) && C <= 2048;
+    if (!vec) {
+        int rc = dsr_norm_finalize(sums, N, C, P, groups, gamma, beta, eps, prm_out, stream);
+        return rc ? rc : dsr_norm_apply_fwd(x, prm_out, res, y, N, P, C, act, stream);
+    }
+    NormFin fin;
+    fin.sums = sums; fin.gamma = gamma; fin.beta = beta; fin.prm_out = prm_out; fin.P = P; fin.groups = groups; fin.eps = eps;
+    const long items = P * (C / 4);
+    long gx = (items + 255) / 256, cap = (long)dsr_num_sms() * 8 / N + 1;
+    if (gx > cap) gx = cap;
+    norm_apply_fwd_fin_vec4_kernel<<<dim3((unsigned)gx, (unsigned)N), 256, 3 * (size_t)C * sizeof(float), ST(stream)>>>(
+        (const float4*)x, fin, (const float4*)res, (float4*)y, N, (int)P, C / 4, act);
+    return dsr_check_launch("norm_apply_fwd_fin");
 }
 // ------------------------------------------------------------------------------------------
 // GroupNorm(groups, C, affine) [+ReLU] backward (translation_network.py:46; the generators of the translation block).
@@ -846,6 +897,11 @@ extern "C" int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, lon
     DSR_REQUIRE(in && out, "null pointer");
     cvt_f64_f32_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(in, stride_in, out, n, scale, accumulate);
     return dsr_check_launch("cvt_f64_f32");
+}
+extern "C" int dsr_sum_reps_f64_f32(const double* in, int reps, long n, float* out, int accumulate, void* stream) {
+    DSR_REQUIRE(in && out && reps >= 1 && n >= 1, "bad arguments");
+    sum_reps_f64_f32_kernel<<<dsr_grid(n, TPB), TPB, 0, ST(stream)>>>(in, reps, n, out, accumulate);
+    return dsr_check_launch("sum_reps_f64_f32");
 }
 // Adam whose step count and hyper-parameters live on the device, so that the launch parameters never change and the
 // whole training step can be replayed as a CUDA graph: `tick` advances the counter, every block of the update kernel

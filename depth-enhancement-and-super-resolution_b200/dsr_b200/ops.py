@@ -232,18 +232,21 @@ def join_side():
 def _bias_grad(dy_nhwc, Co, bias, gP=None):
     """bias gradient = per-channel sum of dY: taken for free by the operand prep of dY when there was one (gP.csum),
     by one channel_sums pass otherwise"""
+    reps = 0
     if gP is not None and gP.csum is not None:
-        sums, stride = gP.csum, 1
+        sums, stride, reps = gP.csum, 1, gP.csum.numel() // Co        # [reps][Co] replica rows (dsr_tc_prep's csum_reps)
     else:
         sums, stride = _zeros_f64(Co * 2, dy_nhwc.device), 2
         _call("dsr_channel_sums", _p(dy_nhwc), 1, dy_nhwc.numel() // Co, Co, _p(sums, torch.float64))
     tgt = DIRECT_GRADS.get(bias.data_ptr())
+    gb = tgt if tgt is not None else torch.empty(Co, device=dy_nhwc.device, dtype=torch.float32)
+    if reps > 1:
+        _call("dsr_sum_reps_f64_f32", _p(sums, torch.float64), reps, Co, _p(gb), int(tgt is not None))
+    else:
+        _call("dsr_cvt_f64_f32", _p(sums, torch.float64), stride, _p(gb), Co, 1.0, int(tgt is not None))
     if tgt is not None:
-        _call("dsr_cvt_f64_f32", _p(sums, torch.float64), stride, _p(tgt), Co, 1.0, 1)
         _grad_ready(bias)
         return None
-    gb = torch.empty(Co, device=dy_nhwc.device, dtype=torch.float32)
-    _call("dsr_cvt_f64_f32", _p(sums, torch.float64), stride, _p(gb), Co, 1.0, 0)
     return gb
 
 
@@ -297,6 +300,9 @@ CONFIG = {
     "side_wgrad": True,  # weight / bias gradients of arena parameters on a second stream beside the data-gradient chain
     "fork_frozen": True, # MainModel.forward: G_A_d on a second stream beside I2D_features -> Image2Depth
     "wgrad_kernel": 2,   # 2 = csrc/wgrad_tc2.cu (8 column blocks per CTA, single pass); 1 = first-generation kernel (conv_tc.cu)
+    "csum_reps": 8,      # replica rows of the bias-gradient sums dsr_tc_prep takes on the way (fp64 atomics spread over 8 addresses
+                         # per channel, which lets the launch keep the wide grid of the sum-free form); 1 = one row, narrow grid
+    "fold_finalize": True,   # dsr_norm_finalize folded into its first consumer (dsr_tc_prep_fin / dsr_norm_apply_fwd_fin)
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
@@ -508,7 +514,7 @@ class _Prepared:
         if hit is None:
             csum = None
             if self.want_csum and self.csum is None and plan["layout"] != _LAYOUT_PAIR and (pad == 0 or pad_mode == PAD_ZERO):
-                csum = self.csum = _zeros_f64(self.shape[3], self.device)
+                csum = self.csum = _zeros_f64(self.shape[3] * CONFIG["csum_reps"], self.device)
             kbf = key[:5] + ("bf16",)
             also_bf16 = also_bf16 and dt == "f16" and kbf not in self.made
             hit = self._make(plan, pad, pad_mode, dtype, csum, need_lo, also_bf16)
@@ -602,9 +608,17 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=N
     if _lib.PROFILE is not None:
         _lib.PROFILE_META = dict(macs=0, shape=(N, H, W, C, Ca, plan["layout"], pad, int(prm is not None), int(alo is not None)))
     abf = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if also_bf16 else None
-    _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
-          _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), _p(abf, torch.bfloat16), Ha, Wa, Ca,
-          int((dtype or CONFIG["dtype"]) == "f16"), _p(csum, torch.float64))
+    fin = _take_fin(prm)
+    if fin is not None:
+        sums, _, _, P, groups, gamma, beta, eps = fin    # statistics not finalised yet: this launch does it (and writes prm)
+        _call("dsr_tc_prep_fin", _p(xh), N, H, W, C, _p(sums, torch.float64), groups, _p(gamma), _p(beta), eps, _p(prm),
+              act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
+              _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), _p(abf, torch.bfloat16), Ha, Wa, Ca,
+              int((dtype or CONFIG["dtype"]) == "f16"), _p(csum, torch.float64), (csum.numel() // C) if csum is not None else 1)
+    else:
+        _call("dsr_tc_prep", _p(xh), N, H, W, C, _p(prm), act, slope, pad, pad_mode, plan["layout"], plan["Cp"],
+              _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), _p(abf, torch.bfloat16), Ha, Wa, Ca,
+              int((dtype or CONFIG["dtype"]) == "f16"), _p(csum, torch.float64), (csum.numel() // C) if csum is not None else 1)
     return (ahi, alo, Ha, Wa, abf) if also_bf16 else (ahi, alo, Ha, Wa)
 
 
@@ -872,12 +886,13 @@ class Prologue:
         self.stats, self.norm, self.eps, self.groups = stats, norm, eps, groups
         self.gamma, self.beta, self.act, self.slope = gamma, beta, act, slope
 
-    def params(self, xh):
+    def params(self, xh, lazy=False):
+        """lazy: the caller's next launch is an operand preparation that can finalise the statistics itself"""
         if not self.norm:
             return None
         g = self.gamma.detach().contiguous() if self.gamma is not None else None
         b = self.beta.detach().contiguous() if self.beta is not None else None
-        return _norm_params(xh, self.groups, g, b, self.eps, self.stats)
+        return _norm_params(xh, self.groups, g, b, self.eps, self.stats, lazy=lazy)
 
 
 def _prologue_bwd(pro, prm, xh, gz):
@@ -916,12 +931,13 @@ class _Conv2d(Function):
         stats = _new_stats(N, Co, x.device) if want_stats else None
         plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
         prm = None
+        out1 = Co == 1 and stride == 1 and R <= 9 and S <= 9 and CONFIG["out1"] and (pro is None or plan is not None)
         if pro is not None:
             if plan is None:
                 raise RuntimeError("internal error: a fused prologue needs the tcgen05 path (see conv_fusable)")
-            prm = pro.params(xh)
+            prm = pro.params(xh, lazy=not out1)
         ctx.xP = None
-        if Co == 1 and stride == 1 and R <= 9 and S <= 9 and CONFIG["out1"] and (pro is None or plan is not None):
+        if out1:
             # depth head: a bandwidth-bound reduction, on CUDA cores straight from the fp32 activation (csrc/conv_out1.cu)
             y = torch.empty((N, Ho, Wo, 1), device=x.device, dtype=torch.float32)
             w = weight.detach()
@@ -942,7 +958,7 @@ class _Conv2d(Function):
                   stride, p, 0, act_out)
         ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None)
         ctx.bias_ref, ctx.pro = bias, pro
-        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, prm)
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, _prm_ready(prm))
         return _with_stats(ctx, y, stats)
 
     @staticmethod
@@ -1058,13 +1074,14 @@ class _ConvTranspose2d(Function):
         stats = _new_stats(N, Co, x.device) if want_stats else None
         plan = tc_conv_plan("convT", Ci, Co, R, S, stride, pad, opad, H, W)
         prm = None
+        out1 = Co == 1 and R == 4 and S == 4 and stride == 2 and pad == 1 and opad == 0 and CONFIG["out1"] and \
+            (pro is None or plan is not None)
         if pro is not None:
             if plan is None:
                 raise RuntimeError("internal error: a fused prologue needs the tcgen05 path (see conv_fusable)")
-            prm = pro.params(xh)
+            prm = pro.params(xh, lazy=not out1)
         ctx.xP = None
-        if Co == 1 and R == 4 and S == 4 and stride == 2 and pad == 1 and opad == 0 and CONFIG["out1"] and \
-                (pro is None or plan is not None):
+        if out1:
             y = torch.empty((N, Ho, Wo, 1), device=x.device, dtype=torch.float32)
             w = weight.detach()
             _call("dsr_conv_out1", _p(xh), N, H, W, Ci, _p(prm), pro.act if pro else ACT_NONE, pro.slope if pro else 0.0,
@@ -1081,7 +1098,7 @@ class _ConvTranspose2d(Function):
             _call("dsr_conv_simt", _p(xh), _p(wk), _p(b), _p(y), N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, act_out)
         ctx.cfg = (stride, pad, act_out, bias is not None)
         ctx.bias_ref, ctx.pro = bias, pro
-        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, prm)
+        ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, _prm_ready(prm))
         return _with_stats(ctx, y, stats)
 
     @staticmethod
@@ -1271,7 +1288,10 @@ def pad2d(x, pad, mode):
 # ------------------------------------------------------------------------------------------------
 # normalisation / activation / concat
 # ------------------------------------------------------------------------------------------------
-def _norm_params(xh, groups, gamma, beta, eps, sums=None):
+def _norm_params(xh, groups, gamma, beta, eps, sums=None, lazy=False):
+    """(mean, scale, shift) per (n, c) from the channel sums.  lazy (and CONFIG['fold_finalize']): the finalisation is left
+    to the first consumer - dsr_tc_prep_fin / dsr_norm_apply_fwd_fin derive the constants inside their own launch and write
+    `prm` for the backward pass; the pending work rides on the tensor as `prm._fin` until _take_fin / _prm_ready claims it."""
     N, H, W, C = xh.shape
     if sums is None:
         sums = _zeros_f64(N * C * 2, xh.device)
@@ -1279,8 +1299,40 @@ def _norm_params(xh, groups, gamma, beta, eps, sums=None):
     elif sums.numel() != N * C * 2:
         raise ValueError("norm statistics do not match the activation shape")
     prm = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)
+    if lazy and CONFIG["fold_finalize"]:
+        prm._fin = (sums, N, C, H * W, groups, gamma, beta, eps)
+        return prm
     _call("dsr_norm_finalize", _p(sums, torch.float64), N, C, H * W, groups, _p(gamma), _p(beta), eps, _p(prm))
     return prm
+
+
+def _take_fin(prm):
+    """claim the pending finalisation of `prm` (None when there is none): the caller's launch must perform it"""
+    fin = getattr(prm, "_fin", None) if prm is not None else None
+    if fin is not None:
+        prm._fin = None
+    return fin
+
+
+def _prm_ready(prm):
+    """make sure `prm` holds finalised constants (a consumer without the folded route, or nobody claimed the work)"""
+    fin = _take_fin(prm)
+    if fin is not None:
+        sums, N, C, P, groups, gamma, beta, eps = fin
+        _call("dsr_norm_finalize", _p(sums, torch.float64), N, C, P, groups, _p(gamma), _p(beta), eps, _p(prm))
+    return prm
+
+
+def _norm_apply_fwd(xh, prm, rh, y, act):
+    """y = act((x - mean) * scale + shift) (+ residual); finalises the statistics in the same launch when they are pending"""
+    N, H, W, C = xh.shape
+    fin = _take_fin(prm)
+    if fin is not None:
+        sums, _, _, P, groups, gamma, beta, eps = fin
+        _call("dsr_norm_apply_fwd_fin", _p(xh), _p(sums, torch.float64), groups, _p(gamma), _p(beta), eps, _p(prm), _p(rh), _p(y),
+              N, H * W, C, act)
+    else:
+        _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
 
 
 class _InstanceNorm(Function):
@@ -1290,10 +1342,10 @@ class _InstanceNorm(Function):
     def forward(ctx, x, eps, act, residual, stats):
         xh = nhwc(x)
         N, H, W, C = xh.shape
-        prm = _norm_params(xh, 0, None, None, eps, stats)
+        prm = _norm_params(xh, 0, None, None, eps, stats, lazy=True)
         rh = nhwc(residual) if residual is not None else None
         y = torch.empty_like(xh)
-        _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
+        _norm_apply_fwd(xh, prm, rh, y, act)
         ctx.act = act
         ctx.has_res = residual is not None
         ctx.save_for_backward(xh, prm)
@@ -1341,10 +1393,10 @@ class _GroupNorm(Function):
         if stats is None:
             stats = _zeros_f64(N * C * 2, xh.device)
             _call("dsr_channel_sums", _p(xh), N, H * W, C, _p(stats, torch.float64))
-        prm = _norm_params(xh, groups, w, b, eps, stats)
+        prm = _norm_params(xh, groups, w, b, eps, stats, lazy=True)
         rh = nhwc(residual) if residual is not None else None
         y = torch.empty_like(xh)
-        _call("dsr_norm_apply_fwd", _p(xh), _p(prm), _p(rh), _p(y), N, H * W, C, act)
+        _norm_apply_fwd(xh, prm, rh, y, act)
         if any(ctx.needs_input_grad):
             hat = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)         # (mean, rstd, 0): gamma = beta = NULL
             _call("dsr_norm_finalize", _p(stats, torch.float64), N, C, H * W, groups, None, None, eps, _p(hat))

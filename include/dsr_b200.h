@@ -165,6 +165,11 @@ int dsr_norm_finalize(const double* sums, int N, int C, long P, int groups, cons
 /* y = act((x - mean) * scale + shift) (+ res).  act in {NONE, RELU}.  Residual: models/networks.py:480. */
 int dsr_norm_apply_fwd(const float* x, const float* prm, const float* res, float* y, int N, long P, int C, int act,
                        void* stream);
+/* dsr_norm_finalize + dsr_norm_apply_fwd in ONE launch: every block derives its sample's (mean, scale, shift) from the raw
+ * sums (the finalize kernel's own arithmetic: bit-identical) and prm_out receives them for the backward pass.  Same reference
+ * call sites: models/networks.py:30, :380-381, :480 (InstanceNorm2d [+ReLU] [+ residual]), translation_network.py:46. */
+int dsr_norm_apply_fwd_fin(const float* x, const double* sums, int groups, const float* gamma, const float* beta, float eps,
+                           float* prm_out, const float* res, float* y, int N, long P, int C, int act, void* stream);
 int dsr_in_bwd_sums(const float* x, const float* dy, const float* prm, int N, long P, int C, int act, double* sums2,
                     void* stream);
 int dsr_in_bwd_apply(const float* x, const float* dy, const float* prm, const double* sums2, float* dx, int N,
@@ -184,6 +189,10 @@ int dsr_pack_weight(const float* w, int D0, int D1, int R, int S, int kdim, floa
 int dsr_unpack_weight(const float* packed, int D0, int D1, int R, int S, int kdim, float* w, int accumulate,
                       void* stream);
 int dsr_cvt_f64_f32(const double* in, long stride_in, float* out, long n, float scale, int accumulate, void* stream);
+/* out (+)= (float) sum over the `reps` replica rows of a double accumulator [reps][n]: the bias gradient
+ * (sum of dY over batch and pixels; every nn.Conv2d / nn.ConvTranspose2d with bias, networks.py:379-415) from the replicated
+ * channel sums dsr_tc_prep takes on the way. */
+int dsr_sum_reps_f64_f32(const double* in, int reps, long n, float* out, int accumulate, void* stream);
 /* Loss assembly (models/main_model.py:393-417: loss_G = sum of ~14 weighted scalar terms, times scale_G) in ONE launch:
  * out = scale * sum_k sum_j weights[k][j] * terms[k][j] over n <= 32 tiny device tensors of counts[k] <= 4 elements each
  * (`terms`, `counts`, `weights` are HOST arrays; weights is flat, 4 per term).  The backward form writes
@@ -252,7 +261,17 @@ int dsr_tc_prep(const float* x, int N, int H, int W, int C, const float* prm, in
                 int pad_mode, int layout, int Cp, void* A_hi, void* A_lo,
                 void* A_bf /* optional: the same operand once more as plain bf16 (read by the weight-gradient GEMM later) */,
                 int Ha, int Wa, int Ca, int f16,
-                double* csum /* optional: += per-channel sums of x (bias gradient of a dY), pre-zeroed */, void* stream);
+                double* csum /* optional: += per-channel sums of x (bias gradient of a dY), pre-zeroed, double [csum_reps][C] */,
+                int csum_reps /* replica rows of csum (block b adds into row b % csum_reps; >= 4 keeps the wide grid): the
+                                 reader sums them with dsr_sum_reps_f64_f32 */,
+                void* stream);
+/* dsr_tc_prep with dsr_norm_finalize folded in (sums double [N][C][2] of the RAW input, usually taken by the producing GEMM's
+ * epilogue): one launch less per normalised layer on the step's critical path.  prm_out (optional) = float [3][N][C] as
+ * dsr_norm_finalize writes it.  models/networks.py:380-381, :478-480 (conv -> InstanceNorm -> ReLU -> conv chains). */
+int dsr_tc_prep_fin(const float* x, int N, int H, int W, int C, const double* sums, int groups, const float* gamma,
+                    const float* beta, float eps, float* prm_out, int act, float slope, int pad, int pad_mode, int layout,
+                    int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16, double* csum, int csum_reps,
+                    void* stream);
 /* dsr_tc_prep over torch.cat((x0, x1, x2, x3), dim=1) (NULL / 0 = absent) without materialising the concatenation:
  * models/main_model.py:305-306 (the 261-channel Task input), models/networks.py:629 (U-Net skip connections). */
 int dsr_tc_prep_cat(const float* x0, int C0, const float* x1, int C1, const float* x2, int C2, const float* x3, int C3, int N,

@@ -545,6 +545,87 @@ def test_fused_prologue_matches_unfused(ops):
         ops.CONFIG.update(old)
 
 
+@pytest.mark.parametrize("groups,C,HW,layout_pad", [(0, 64, (24, 40), 1), (0, 128, (9, 7), 0), (8, 64, (12, 10), 1), (0, 20, (6, 5), 2)])
+def test_folded_norm_finalize_kernels_bit_identical(ops, groups, C, HW, layout_pad):
+    """dsr_tc_prep_fin / dsr_norm_apply_fwd_fin (statistics finalised inside the consumer's launch) against
+    dsr_norm_finalize + dsr_tc_prep / dsr_norm_apply_fwd on the SAME sums: same arithmetic, so operands, outputs and the
+    constants written for the backward pass must be EQUAL, not close.  InstanceNorm: networks.py:30, :380-381, :478-480;
+    GroupNorm(8, C): translation_network.py:46."""
+    H, W = HW
+    N = 3
+    xh = (torch.randn(N, H, W, C, generator=G(61)) * 2 + 0.7).cuda()
+    gamma = torch.randn(C, generator=G(62)).cuda() if groups else None
+    beta = torch.randn(C, generator=G(63)).cuda() if groups else None
+    plan = dict(layout=0, Cp=(C + 7) // 8 * 8, Ca=(C + 63) // 64 * 64)
+    sums = torch.zeros(N * C * 2, dtype=torch.float64, device="cuda")       # ONE set of statistics for both routes
+    ops._call("dsr_channel_sums", ops._p(xh), N, H * W, C, ops._p(sums, torch.float64))
+    out = []
+    for fold in (True, False):
+        old = dict(ops.CONFIG)
+        try:
+            ops.CONFIG.update(fold_finalize=fold, passes=3, dtype="f16")
+            n0 = _launch_count()
+            prm = ops._norm_params(xh, groups, gamma, beta, 1e-5, sums, lazy=True)
+            assert (getattr(prm, "_fin", None) is not None) == fold
+            ahi, alo, Ha, Wa = ops._tc_prep(xh, plan, layout_pad, ops.PAD_REFLECT, prm, ops.ACT_RELU)[:4]
+            prm2 = ops._norm_params(xh, groups, gamma, beta, 1e-5, sums, lazy=True)
+            y = torch.empty_like(xh)
+            ops._norm_apply_fwd(xh, prm2, xh, y, ops.ACT_RELU)
+            torch.cuda.synchronize()
+            out.append((ahi.view(torch.int16).cpu(), alo.view(torch.int16).cpu(), prm.cpu(), prm2.cpu(), y.cpu(), _launch_count() - n0))
+        finally:
+            ops.CONFIG.update(old)
+    for a, b in zip(out[0][:5], out[1][:5]):
+        assert torch.equal(a, b)
+    assert out[0][5] == out[1][5] - 2                               # two finalize launches fewer
+    ref = F.relu(F.instance_norm(xh.permute(0, 3, 1, 2).cpu(), eps=1e-5) if groups == 0 else
+                 F.group_norm(xh.permute(0, 3, 1, 2).cpu(), groups, gamma.cpu(), beta.cpu(), 1e-5)) + xh.permute(0, 3, 1, 2).cpu()
+    assert torch.allclose(out[0][4].permute(0, 3, 1, 2), ref, atol=5e-5)
+
+
+def test_folded_norm_finalize_through_the_layers(ops):
+    """the same comparison through the layer stack (prologue route and stand-alone InstanceNorm), forward and backward; the
+    statistics come from fp64 atomics in the GEMM epilogues here (run-to-run differences in the last bits, amplified by the
+    single-pass bf16 backward operands), so this is a closeness check - the bitwise one is the kernel-level test above"""
+    from dsr_b200 import networks as nw
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
+        torch.manual_seed(11)
+        mods = [nw.Conv2d(32, 64, 3, stride=2, padding=1), nw.InstanceNorm2d(64), nw.ReLU(True), nw.ReflectionPad2d(1),
+                nw.Conv2d(64, 64, 3, padding=0), nw.InstanceNorm2d(64), nw.ReLU(True),
+                nw.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1), nw.InstanceNorm2d(32), nw.ReLU(True),
+                nw.ReflectionPad2d(3), nw.Conv2d(32, 128, 7, padding=0)]
+        for m in mods:
+            m.cuda()
+        x = torch.randn(3, 32, 24, 40, generator=G(198)) * 2 + 0.3
+        res = []
+        for fold in (True, False):
+            ops.CONFIG.update(fold_finalize=fold)
+            n0 = _launch_count()
+            xc = cl(x).requires_grad_(True)
+            for m in mods:
+                for p_ in m.parameters():
+                    p_.grad = None
+            y = nw.run_fused(mods, xc)                              # prologue route: dsr_tc_prep_fin
+            z = ops.instance_norm(y, 1e-5, 1, None)                 # stand-alone route: dsr_norm_apply_fwd_fin
+            (z * z).sum().backward()
+            res.append((z.detach().cpu(), xc.grad.cpu(), [p_.grad.cpu().clone() for m in mods for p_ in m.parameters()],
+                        _launch_count() - n0))
+        assert rel_l2(res[0][0], res[1][0]) <= 1e-6 and rel_l2(res[0][1], res[1][1]) <= 2e-4
+        for ga, gb in zip(res[0][2], res[1][2]):
+            if gb.dim() == 4:
+                assert rel_l2(ga, gb) <= 2e-4
+        assert res[0][3] == res[1][3] - 4                           # four normalisations, four launches fewer
+    finally:
+        ops.CONFIG.update(old)
+
+
+def _launch_count():
+    from dsr_b200 import _lib
+    return _lib.LAUNCHES
+
+
 def test_adam_matches_oracle(ops):
     n = 1003
     p, g = torch.randn(n, generator=G(50)), torch.randn(n, generator=G(51))
