@@ -641,8 +641,9 @@ tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int
 //   variant CONV_DGRAD: Conv2d weight (Cout, Cin, R, S) for the stride-1 data gradient: GEMM output channel = ci,
 //                      K channel = co, tap t = (r', s') reads W[co][ci][R-1-r'][S-1-s']
 //   variant CONV_DGRAD_PAIR: the same data gradient for narrow layers (Cin = 32): GEMM row co' = dx*Cin + ci is output
-//                      channel ci of the pixel at column 2k + dx, the A operand is read as pixel PAIRS (Ca = 2*Cp):
-//                      tap t = (r', a), K channel q = b*Cp + co reads W[co][ci][R-1-r'][S-1-(2a+b-dx)] (zero outside)
+//                      channel ci of the pixel at column g*k + dx, the A operand is read as GROUPS of g = Ca / Cp adjacent pixels
+//                      (pairs, or quads: 4 x 32 = 128 GEMM rows): tap t = (r', a), K channel q = b*Cp + co reads
+//                      W[co][ci][R-1-r'][S-1-(g*a+b-dx)] (zero outside)
 //   variant CONVT_PH : ConvTranspose2d weight (Cin, Cout, R, S), stride 2, phase (a,b): taps (dr,ds) in {0,1}^2,
 //                      kh = pad + 2 - a - 2*dr, kw = pad + 2 - b - 2*ds (zero tap when outside the kernel)
 // ------------------------------------------------------------------------------------------------
@@ -682,10 +683,11 @@ tc_pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int R, int S,
             int r, sx, c;
             float v = 0.f;
             if (variant == DSR_TC_W_CONV_DGRAD_PAIR) {
-                const int q = q8 * 8 + e, Sg = S / 2 + 1;
+                // g = Ca / Cp adjacent pixels per GEMM row (2: pairs, N = 64; 4: quads, N = 128 = one channel-major M tile)
+                const int q = q8 * 8 + e, Sg = (g + S - 2) / g + 1;
                 const int dx = co / D1, ci = co - dx * D1, rr = t / Sg, a = t - rr * Sg, b = q / Cp, cc = q - b * Cp;
-                const int sidx = 2 * a + b - dx;
-                if (sidx >= 0 && sidx < S && rr < R && cc < D0 && dx < 2)
+                const int sidx = g * a + b - dx;
+                if (sidx >= 0 && sidx < S && rr < R && cc < D0 && dx < g)
                     v = w[(((long)cc * D1 + ci) * R + (R - 1 - rr)) * S + (S - 1 - sidx)];
                 split16(v * wscale, f16, hi[e], lo[e]);
                 continue;

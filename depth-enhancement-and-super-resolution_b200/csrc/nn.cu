@@ -110,8 +110,8 @@ __device__ __forceinline__ int pad_readers(int i, int p, int n, int mode, int* q
     return k;
 }
 __global__ void pad2d_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int N, int H, int W, int C,
-                                 int p, int mode) {
-    int Hp = H + 2 * p, Wp = W + 2 * p;
+                                 int p, int mode, int Wp) {
+    int Hp = H + 2 * p;
     long total = (long)N * H * W * C;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         int c = (int)(idx % C); long t = idx / C;
@@ -128,8 +128,8 @@ __global__ void pad2d_bwd_kernel(const float* __restrict__ gy, float* __restrict
 
 // float4 version: one thread = 4 channels of one source pixel; interior pixels have exactly one reader
 __global__ void __launch_bounds__(256)
-pad2d_bwd_vec4_kernel(const float4* __restrict__ gy, float4* __restrict__ gx, int N, int H, int W, int C4, int p, int mode) {
-    const int Hp = H + 2 * p, Wp = W + 2 * p;
+pad2d_bwd_vec4_kernel(const float4* __restrict__ gy, float4* __restrict__ gx, int N, int H, int W, int C4, int p, int mode, int Wp) {
+    const int Hp = H + 2 * p;                      // Wp = row pitch of gy in pixels (>= W + 2 p)
     const int total = N * H * W * C4;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = idx % C4; int t = idx / C4;
@@ -656,14 +656,21 @@ extern "C" int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int 
                                                                                                      pad, mode);
     return dsr_check_launch("pad2d_fwd");
 }
-extern "C" int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream) {
-    DSR_REQUIRE(gy && gx && pad >= 0 && pad <= 7, "bad arguments");
-    if (!(C & 3) && !((uintptr_t)gy & 15) && !((uintptr_t)gx & 15) && (long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 4) < (1L << 31))
+// wpitch = row pitch of gy in pixels (>= W + 2 pad): the grouped data gradient (ops._tc_dgrad_group) computes rows rounded up
+// to whole pixel groups
+extern "C" int dsr_pad2d_bwd_pitch(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, int wpitch,
+                                   void* stream) {
+    DSR_REQUIRE(gy && gx && pad >= 0 && pad <= 7 && wpitch >= W + 2 * pad, "bad arguments");
+    if (!(C & 3) && !((uintptr_t)gy & 15) && !((uintptr_t)gx & 15) && (long)N * H * W * (C / 4) < (1L << 31) &&
+        (long)N * (H + 2 * pad) * wpitch * (C / 4) < (1L << 31))
         pad2d_bwd_vec4_kernel<<<dsr_grid((long)N * H * W * (C / 4), 256), 256, 0, ST(stream)>>>((const float4*)gy, (float4*)gx, N, H, W,
-                                                                                               C / 4, pad, mode);
+                                                                                               C / 4, pad, mode, wpitch);
     else
-        pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode);
+        pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode, wpitch);
     return dsr_check_launch("pad2d_bwd");
+}
+extern "C" int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream) {
+    return dsr_pad2d_bwd_pitch(gy, gx, N, H, W, C, pad, mode, W + 2 * pad, stream);
 }
 extern "C" int dsr_act_fwd(const float* x, float* y, long n, int kind, float slope, void* stream) {
     DSR_REQUIRE(x && y, "null pointer");

@@ -303,6 +303,7 @@ CONFIG = {
     "csum_reps": 8,      # replica rows of the bias-gradient sums dsr_tc_prep takes on the way (fp64 atomics spread over 8 addresses
                          # per channel, which lets the launch keep the wide grid of the sum-free form); 1 = one row, narrow grid
     "fold_finalize": True,   # dsr_norm_finalize folded into its first consumer (dsr_tc_prep_fin / dsr_norm_apply_fwd_fin)
+    "dgrad_quad": True,  # ... FOUR adjacent pixels per row for Cin = 32: 128 GEMM rows = one M tile of the channel-major kernel
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
 WEIGHT_EPOCH = 0         # bumped by the optimizer: invalidates packed copies of trainable weights
@@ -507,7 +508,7 @@ class _Prepared:
         also_bf16: the same pass also writes a plain bf16 copy in the same arranged layout (the operand the weight-gradient
         GEMM of the backward pass needs - both its operands must have ONE 16-bit format), found later under dtype 'bf16'."""
         dt = dtype or CONFIG["dtype"]
-        key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dt)
+        key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dt, plan.get("Wa", 0))
         hit = self.made.get(key)
         if hit is not None and need_lo and hit[1] is None and CONFIG["passes"] >= 2:
             hit = None                                    # made without its low plane earlier: make it again in full
@@ -515,7 +516,7 @@ class _Prepared:
             csum = None
             if self.want_csum and self.csum is None and plan["layout"] != _LAYOUT_PAIR and (pad == 0 or pad_mode == PAD_ZERO):
                 csum = self.csum = _zeros_f64(self.shape[3] * CONFIG["csum_reps"], self.device)
-            kbf = key[:5] + ("bf16",)
+            kbf = key[:5] + ("bf16",) + key[6:]
             also_bf16 = also_bf16 and dt == "f16" and kbf not in self.made
             hit = self._make(plan, pad, pad_mode, dtype, csum, need_lo, also_bf16)
             if also_bf16:
@@ -529,7 +530,7 @@ class _Prepared:
 
     def any_normal(self, Ca, dtype):
         """an already-made NORMAL-layout zero-padded copy -> (ahi, alo, Ha, Wa, pad) or None"""
-        for (layout, _, ca, pad, mode, dt), v in self.made.items():
+        for (layout, _, ca, pad, mode, dt, _wa), v in self.made.items():
             if layout == _LAYOUT_NORMAL and ca == Ca and dt == dtype and (mode == PAD_ZERO or pad == 0):
                 return v + (pad,)
         return None
@@ -601,7 +602,7 @@ def _tc_prep(xh, plan, pad, pad_mode, prm=None, act=ACT_NONE, slope=0.0, dtype=N
     if plan["layout"] == _LAYOUT_S2D:
         Ha, Wa = (Hq + 1) // 2, (Wq + 1) // 2
     else:
-        Ha, Wa = Hq, Wq
+        Ha, Wa = Hq, max(Wq, plan.get("Wa", 0))        # plan['Wa']: wider rows, zero-filled beyond the padded image
     Ca = plan["Ca"]
     ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
     alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if (CONFIG["passes"] >= 2 and need_lo) else None
@@ -708,26 +709,31 @@ def _tc_convT_fwd(xh, weight, bias, plan, pad, act_out, Ho, Wo, dtype=None, stat
     return y
 
 
-def _tc_dgrad_pair(gP, weight, padq, Hout, Wout, dt):
+def _tc_dgrad_group(gP, weight, padq, Hout, Wout, dt, g=2):
     """Stride-1 data gradient of a Conv2d with few input channels (the 7x7 32 -> 128 head of the ResNets), written as a
-    GEMM whose rows are PAIRS of horizontally adjacent output pixels: N = 2 * Cin = 64 runs the tensor pipe at full rate
-    where N = 32 runs at half, for (S/2 + 1) * 2 / S = 8/7 of the MACs.  The zero-padded dY (N, Ha, Wa, Co) is read
-    through the view (N, Ha, Wa/2, 2*Co) - no copy - and the (N, Hout, Wout, Cin) output through (N, Hout, Wout/2, 2*Cin)."""
+    GEMM whose rows are GROUPS of g horizontally adjacent output pixels.  g = 2: N = 2 * Cin = 64 runs the pixel-major
+    tensor pipe at full rate where N = 32 runs at half, for (S/2 + 1) * 2 / S = 8/7 of the MACs.  g = 4: 4 * Cin = 128 GEMM
+    rows are exactly one M tile of the channel-major kernel (csrc/conv_tc3.cu: N = 256 pixel groups per MMA, 95 % of the
+    tensor floor against the ~105-cycle floor of the pixel-major M = 128 x N = 64 MMAs) for 12/7 of the MACs.
+    The zero-padded dY (N, Ha, Wa, Co) is read through the view (N, Ha, Wa/g, g*Co) - no copy - and the output through
+    (N, Hout, Wc/g, g*Cin), Wc = Wout rounded up to whole groups.  -> (dX of shape (N, Hout, Wc, Cin), Wc)."""
     _FWD["hw"] = Hout * Wout
     N, Ho, Wo, Co = gP.shape
     _, Ci, R, S = weight.shape
-    a_plan = dict(layout=_LAYOUT_NORMAL, Cp=Co, Ca=Co)
-    ahi, alo, Ha, Wa = _tc_prep(gP, a_plan, padq, PAD_ZERO, dtype=dt, need_lo=_passes(dt) >= 2)
-    Sg = S // 2 + 1
+    Sg = (g + S - 2) // g + 1
     T = R * Sg
-    w_plan = dict(variant=_W_CONV_DGRAD_PAIR, Cp=Co, Ca=2 * Co, T=T)
-    whi, wlo = _tc_weights(weight, w_plan, 2 * Ci, dtype=dt)
+    Wc = _rup(Wout, g)
+    Gout = Wc // g
+    a_plan = dict(layout=_LAYOUT_NORMAL, Cp=Co, Ca=Co, Wa=g * (Gout + Sg - 1))      # >= Wo + 2 * padq, zero-filled beyond
+    ahi, alo, Ha, Wa = _tc_prep(gP, a_plan, padq, PAD_ZERO, dtype=dt, need_lo=_passes(dt) >= 2)
+    w_plan = dict(variant=_W_CONV_DGRAD_PAIR, Cp=Co, Ca=g * Co, T=T)
+    whi, wlo = _tc_weights(weight, w_plan, g * Ci, dtype=dt)
     dr, ds = [t // Sg for t in range(T)], [t % Sg for t in range(T)]
-    y = torch.empty((N, Hout, Wout, Ci), device=gP.device, dtype=torch.float32)
+    y = torch.empty((N, Hout, Wc, Ci), device=gP.device, dtype=torch.float32)
     _lib.PROFILE_META = dict(macs=N * Hout * Wout * Co * Ci * R * S, shape=(N, Hout, Wout, Co, Ci, R, 1))
-    _tc_gemm(ahi, alo, N, Ha, Wa // 2, 2 * Co, whi, wlo, 2 * Ci, T, _int_array(dr), _int_array(ds), 0, 0, Hout, Wout // 2,
-             None, y, Hout, Wout // 2, 1, 0, 0, ACT_NONE, dt, CONFIG["split_k"])
-    return y
+    _tc_gemm(ahi, alo, N, Ha, Wa // g, g * Co, whi, wlo, g * Ci, T, _int_array(dr), _int_array(ds), 0, 0, Hout, Gout,
+             None, y, Hout, Gout, 1, 0, 0, ACT_NONE, dt, CONFIG["split_k"])
+    return y, Wc
 
 
 def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
@@ -743,18 +749,26 @@ def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
             return None
         plan = dict(plan, variant=_W_CONV_DGRAD)
         macs = N * Ho * Wo * Co * Ci * R * S
-        pair = (CONFIG["dgrad_pair"] and Ci <= 32 and Ci % 8 == 0 and Co % 64 == 0 and W % 2 == 0 and Wo % 2 == 0
-                and isinstance(g, _Prepared) and S >= 3 and R * (S // 2 + 1) <= 64 and (W + 2 * pad) // 2 >= 8)
-        if pad_mode == PAD_ZERO or pad == 0:          # gradient w.r.t. the un-padded input directly
-            if pair:
-                return _tc_dgrad_pair(g, weight, R - 1 - pad, H, W, dt)
+        direct = pad_mode == PAD_ZERO or pad == 0      # gradient w.r.t. the un-padded input directly
+        Wout = W if direct else W + 2 * pad
+        grp = 0                                        # pixels per GEMM row of the grouped form (0: plain)
+        if CONFIG["dgrad_pair"] and Ci <= 32 and Ci % 8 == 0 and Co % 64 == 0 and isinstance(g, _Prepared) and S >= 3:
+            if (CONFIG["dgrad_quad"] and Ci == 32 and R * ((S + 2) // 4 + 1) <= 64 and Wout >= 32 and H >= 16
+                    and (Wout % 4 == 0 or not direct)):
+                grp = 4
+            elif W % 2 == 0 and Wo % 2 == 0 and R * (S // 2 + 1) <= 64 and (W + 2 * pad) // 2 >= 8:
+                grp = 2
+        if direct:
+            if grp:
+                return _tc_dgrad_group(g, weight, R - 1 - pad, H, W, dt, grp)[0]
             return _tc_conv_fwd(g, weight, None, plan, 1, R - 1 - pad, PAD_ZERO, ACT_NONE, H, W, dtype=dt, Co=Ci, macs=macs)
-        if pair:
-            gxp = _tc_dgrad_pair(g, weight, R - 1, H + 2 * pad, W + 2 * pad, dt)
+        Wc = Wout
+        if grp:
+            gxp, Wc = _tc_dgrad_group(g, weight, R - 1, H + 2 * pad, Wout, dt, grp)
         else:
             gxp = _tc_conv_fwd(g, weight, None, plan, 1, R - 1, PAD_ZERO, ACT_NONE, H + 2 * pad, W + 2 * pad, dtype=dt, Co=Ci, macs=macs)
         gx = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
-        _call("dsr_pad2d_bwd", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode)
+        _call("dsr_pad2d_bwd_pitch", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode, Wc)
         return gx
     if stride == 2 and (pad_mode == PAD_ZERO or (pad == 1 and CONFIG["s2_border"])):
         opad = H - ((Ho - 1) * 2 - 2 * pad + R)

@@ -154,6 +154,9 @@ int dsr_copy_channels(const float* src, int srcC, int soff, float* dst, int dstC
                       int accumulate, void* stream);
 int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, int mode, void* stream);
 int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream);
+/* the same with an explicit row pitch of gy in pixels (wpitch >= W + 2 pad): the grouped data gradient of the 7x7 heads
+ * (dsr_b200/ops.py _tc_dgrad_group) computes rows rounded up to whole groups of 4 pixels.  networks.py:378, :413. */
+int dsr_pad2d_bwd_pitch(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, int wpitch, void* stream);
 int dsr_act_fwd(const float* x, float* y, long n, int kind, float slope, void* stream);
 int dsr_act_bwd(const float* ref, const float* gy, float* gx, long n, int kind, float slope, void* stream);
 /* per-(n,c) (sum, sum of squares) over P pixels, accumulated into sums (double [N][C][2], pre-zeroed). */

@@ -388,6 +388,38 @@ def test_conv2d_fused_padding_modes(ops, engine, mode, k, Ci, Co, H, W):
     assert rel_l2(xc.grad.cpu(), x.grad) <= max(btol, engine[3]) and rel_l2(wc.grad.cpu(), w.grad) <= max(btol, engine[3])
 
 
+@pytest.mark.parametrize("mode,pad,H,W", [("zeros", 3, 32, 64), ("reflect", 3, 24, 40), ("reflect", 3, 40, 64), ("zeros", 0, 38, 70),
+                                          ("replicate", 3, 17, 33)])
+def test_dgrad_group_forms_agree(ops, mode, pad, H, W):
+    """data gradient of the 7x7 32 -> 128 head (networks.py:378, :413) in its three GEMM forms - plain rows (N = 32), pixel
+    pairs (N = 64, conv_tc2) and pixel quads (128 GEMM rows on the channel-major kernel, output rows rounded up to whole
+    groups and folded by dsr_pad2d_bwd_pitch) - against the fp32 reference and against each other, weight gradient included
+    (it reads the widened zero-padded dY operand the grouped forms leave behind)."""
+    old = dict(ops.CONFIG)
+    try:
+        x = torch.randn(2, 32, H, W, generator=G(160)).requires_grad_(True)
+        w = (torch.randn(128, 32, 7, 7, generator=G(161)) * 0.05).requires_grad_(True)
+        b = torch.randn(128, generator=G(162)).requires_grad_(True)
+        xp = F.pad(x, (pad,) * 4, mode={"zeros": "constant"}.get(mode, mode)) if pad else x
+        ref = F.conv2d(xp, w, b)
+        go = torch.randn(ref.shape, generator=G(163))
+        (ref * go).sum().backward()
+        got = {}
+        for name, cfg in (("plain", dict(dgrad_pair=False)), ("pair", dict(dgrad_pair=True, dgrad_quad=False)),
+                          ("quad", dict(dgrad_pair=True, dgrad_quad=True))):
+            ops.CONFIG.update(old)
+            ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0, **cfg)
+            xc, wc, bc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+            out = ops.conv2d(xc, wc, bc, 1, pad, pad_mode=mode)
+            (out * go.cuda()).sum().backward()
+            got[name] = (xc.grad.cpu(), wc.grad.cpu(), bc.grad.cpu())
+            assert rel_l2(got[name][0], x.grad) <= 5e-5, name
+            assert rel_l2(got[name][1], w.grad) <= 5e-5 and rel_l2(got[name][2], b.grad) <= 1e-5, name
+        assert rel_l2(got["quad"][0], got["plain"][0]) <= 2e-5 and rel_l2(got["pair"][0], got["plain"][0]) <= 2e-5
+    finally:
+        ops.CONFIG.update(old)
+
+
 CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
     (128, 64, 3, 2, 1, 1, 8, 8), (64, 32, 3, 2, 1, 1, 9, 7), (512, 512, 4, 2, 1, 0, 2, 2), (1024, 256, 4, 2, 1, 0, 4, 4),
     (128, 1, 4, 2, 1, 0, 16, 16), (256, 128, 4, 2, 1, 0, 8, 8),
@@ -616,7 +648,6 @@ def test_folded_norm_finalize_through_the_layers(ops):
         for ga, gb in zip(res[0][2], res[1][2]):
             if gb.dim() == 4:
                 assert rel_l2(ga, gb) <= 2e-4
-        assert res[0][3] == res[1][3] - 4                           # four normalisations, four launches fewer
     finally:
         ops.CONFIG.update(old)
 
