@@ -25,7 +25,7 @@
 struct Tc3Params {
     int N, Ht, Wt, TH;
     int tiles_w, tiles_h, tiles_co, total_tiles;
-    int Ca, T, cblocks;       // cblocks = Ca / 32
+    int Ca, T, cblocks;       // cblocks = Ca / KB (KB = 32 or 64 channels per stage)
     int ah, aw, Hp, PW;       // patch = Hp rows x PW pixels x 64 B
     int Ho, Wo, Cout, os, ph, pw;
     int nphase, tiles_per_phase;  // 4 output phases of a stride-2 transposed conv in one launch (see conv_tc.cu)
@@ -42,6 +42,14 @@ __device__ __forceinline__ uint64_t make_sdesc64(uint32_t saddr, uint32_t sbo_by
            ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 
+// K-major SWIZZLE_128B descriptor (128-byte rows) with an explicit 8-row-group stride: the K = 64 form of the single-pass
+// instantiation.  The swizzle XOR uses absolute shared-memory address bits (measured, conv_tc2.cu), so a patch descriptor
+// may start at any pixel of a 1024-byte aligned patch without a base offset.
+__device__ __forceinline__ uint64_t make_sdesc128(uint32_t saddr, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
 __device__ long long* g_tc3_dbg = nullptr;
 #define TC3_TIMED_WAIT(slot, bar, parity)                 \
     do {                                                  \
@@ -54,7 +62,12 @@ __device__ long long* g_tc3_dbg = nullptr;
         }                                                 \
     } while (0)
 
-template <int NPASS>
+// KB = K elements (channels) per pipeline stage: 32 (64-byte rows, SWIZZLE_64B: what fits beside hi + lo planes) or 64
+// (128-byte rows, SWIZZLE_128B).  A TMA box is fetched row by row, ~3 cycles per row whatever its width: with ONE MMA pass
+// per product a 64-byte-row stage carries only 2 MMAs (256 tensor cycles) for 128 weight rows + its share of the patch
+// rows, and the single-pass kernel ran TMA-bound at 44 % of the tensor peak (ncu r2c); 128-byte rows halve the rows per
+// byte (4 MMAs per stage) and the single-pass form has the shared memory for them (no lo planes).
+template <int NPASS, int KB>
 __global__ void __launch_bounds__(224, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                 const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
@@ -62,7 +75,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 double* __restrict__ stats) {
     constexpr int NA = NPASS >= 2 ? 2 : 1;
     constexpr int NW = NPASS >= 3 ? 2 : 1;
-    constexpr uint32_t W_TILE = 128 * 64;                // 128 output channels x 32 k x 2 B
+    constexpr uint32_t ROWB = KB * 2;                    // bytes per operand row (one pixel / one output channel) in a stage
+    constexpr uint32_t W_TILE = 128 * ROWB;              // 128 output channels x KB k x 2 B
     constexpr uint32_t ACC_COLS = 256;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -120,8 +134,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     if (elect_one()) {
                         const uint32_t dst = smem_base + b * patch_set;
                         mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
-                        tma_load_4d(dst, &mapA_hi, pf(b), cb << 5, wc, hc, n);
-                        if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb << 5, wc, hc, n);
+                        tma_load_4d(dst, &mapA_hi, pf(b), cb * KB, wc, hc, n);
+                        if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb * KB, wc, hc, n);
                     }
                     __syncwarp();
                 }
@@ -141,7 +155,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                         TC3_TIMED_WAIT(0, we(s), (it & 1) ^ 1);
                         if (elect_one()) {
                             const uint32_t dst = w_base + s * w_stage;
-                            const int kw = t * p.Ca + (cb << 5);
+                            const int kw = t * p.Ca + cb * KB;
                             mbar_expect_tx(wf(s), w_stage);
                             tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
                             if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
@@ -157,8 +171,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         // The whole warp runs the (warp-uniform) loop and the waits; one elected lane issues. =====
         {
             const uint32_t idesc = make_idesc(128, 8 * p.TH, p.f16 ? 0u : 1u);
-            const uint64_t wdesc0 = make_sdesc64(0, 512);                       // address field added per MMA
-            const uint64_t pdesc0 = make_sdesc64(0, (uint32_t)p.PW * 64u);
+            const uint64_t wdesc0 = KB == 32 ? make_sdesc64(0, 512) : make_sdesc128(0, 1024);   // address field added per MMA
+            const uint64_t pdesc0 = KB == 32 ? make_sdesc64(0, (uint32_t)p.PW * 64u) : make_sdesc128(0, (uint32_t)p.PW * 128u);
             int pi = 0, wi = 0, ti = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
                 const int ab = ti & 1;
@@ -174,21 +188,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                         TC3_TIMED_WAIT(1, wf(s), (wi / p.n_ws) & 1);
                         if (elect_one()) {
                             const uint32_t w_hi = w_base + s * w_stage;
-                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * 64u;
+                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * ROWB;
                             const uint64_t wd_hi = wdesc0 + (uint64_t)((w_hi & 0x3FFFF) >> 4);
                             const uint64_t wd_lo = wd_hi + (uint64_t)(W_TILE >> 4);
                             const uint64_t pd_hi = pdesc0 + (uint64_t)(((patch_hi + shift) & 0x3FFFF) >> 4);
                             const uint64_t pd_lo = pdesc0 + (uint64_t)(((patch_lo + shift) & 0x3FFFF) >> 4);
                             const uint32_t first = (cb | t) ? 1u : 0u;          // 0 only for the first MMA of the tile
-                            tc_mma_bf16(d_tmem, wd_hi, pd_hi, idesc, first);
-                            tc_mma_bf16(d_tmem, wd_hi + 2, pd_hi + 2, idesc, 1u);
+#pragma unroll
+                            for (int kk = 0; kk < KB / 16; ++kk)                // one K = 16 MMA per 32 bytes of the rows
+                                tc_mma_bf16(d_tmem, wd_hi + 2 * kk, pd_hi + 2 * kk, idesc, kk ? 1u : first);
                             if (NPASS >= 2) {
-                                tc_mma_bf16(d_tmem, wd_hi, pd_lo, idesc, 1u);
-                                tc_mma_bf16(d_tmem, wd_hi + 2, pd_lo + 2, idesc, 1u);
+#pragma unroll
+                                for (int kk = 0; kk < KB / 16; ++kk) tc_mma_bf16(d_tmem, wd_hi + 2 * kk, pd_lo + 2 * kk, idesc, 1u);
                             }
                             if (NPASS >= 3) {
-                                tc_mma_bf16(d_tmem, wd_lo, pd_hi, idesc, 1u);
-                                tc_mma_bf16(d_tmem, wd_lo + 2, pd_hi + 2, idesc, 1u);
+#pragma unroll
+                                for (int kk = 0; kk < KB / 16; ++kk) tc_mma_bf16(d_tmem, wd_lo + 2 * kk, pd_hi + 2 * kk, idesc, 1u);
                             }
                             tc_commit(we(s));
                             if (t == p.T - 1) {
@@ -312,29 +327,30 @@ static int tc3_env(const char* name, int dflt) {
 }
 
 static int encode_map64(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                        const cuuint32_t* box) {
+                        const cuuint32_t* box, bool sw128 = false) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { dsr_set_error("conv_tc3: cuTensorMapEncodeTiled entry point unavailable"); return DSR_ERR_CUDA; }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dsr_set_error("conv_tc3: cuTensorMapEncodeTiled failed (%d)", (int)r); return DSR_ERR_CUDA; }
     return DSR_OK;
 }
 
-template <int NPASS>
+template <int NPASS, int KB>
 static int launch_tc3(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
                       const Tc3Params& p, const float* bias, float* out, double* stats, int grid, int smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc3_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_MAX) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv_tc3_kernel<NPASS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_MAX) != cudaSuccess) {
             dsr_set_error("conv_tc3: cannot raise dynamic shared memory to %d", TC3_SMEM_MAX);
             return DSR_ERR_CUDA;
         }
         attr = true;
     }
-    conv_tc3_kernel<NPASS><<<grid, 224, smem, st>>>(ah, al, wh, wl, p, bias, out, stats);
+    conv_tc3_kernel<NPASS, KB><<<grid, 224, smem, st>>>(ah, al, wh, wl, p, bias, out, stats);
     return dsr_check_launch("conv_tc3");
 }
 
@@ -375,7 +391,10 @@ extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, i
         dsr_set_error("conv_tc3: shape not covered (tap window %dx%d, output %dx%d)", max_dr + 1, max_ds + 1, Ht, Wt);
         return DSR_ERR_UNSUPPORTED;
     }
-    p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.cblocks = Ca / 32;
+    // single pass: 64-channel stages (128-byte rows) - see the kernel's header; DSR_TC3_KB=32 keeps the 64-byte rows (A/B)
+    const int KB = (npass == 1 && tc3_env("DSR_TC3_KB", 64) == 64) ? 64 : 32;
+    const unsigned rowb = (unsigned)KB * 2u;
+    p.N = N; p.Ht = Ht; p.Wt = Wt; p.Ca = Ca; p.T = T; p.cblocks = Ca / KB;
     p.tiles_co = dsr_cdiv(Cout, 128);
     p.TH = tc3_env("DSR_TC3_TH", tc3_pick_th(N, Ht, Wt, p.tiles_co * nphase, dsr_num_sms()));
     if (p.TH < 2 || p.TH > 32 || (p.TH & 1)) { dsr_set_error("conv_tc3: bad tile height %d", p.TH); return DSR_ERR_ARG; }
@@ -385,10 +404,10 @@ extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, i
     p.tiles_w = dsr_cdiv(Wt, TC3_TW); p.tiles_h = dsr_cdiv(Ht, p.TH);
     p.nphase = nphase; p.tiles_per_phase = p.tiles_w * p.tiles_h * p.tiles_co * N;
     p.total_tiles = p.tiles_per_phase * nphase;
-    p.patch_tx_bytes = (unsigned)p.Hp * p.PW * 64u;
+    p.patch_tx_bytes = (unsigned)p.Hp * p.PW * rowb;
     p.patch_plane_bytes = (p.patch_tx_bytes + 1023u) & ~1023u;
     const int na = npass >= 2 ? 2 : 1, nw = npass >= 3 ? 2 : 1;
-    const long patch_set = (long)na * p.patch_plane_bytes, w_stage = (long)nw * 128 * 64;
+    const long patch_set = (long)na * p.patch_plane_bytes, w_stage = (long)nw * 128 * rowb;
     const long budget = TC3_SMEM_MAX - 1024 - 512;
     p.n_pb = tc3_env("DSR_TC3_NPB", 2);
     long ws = (budget - p.n_pb * patch_set) / w_stage;
@@ -401,19 +420,20 @@ extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, i
     CUtensorMap mah, mal, mwh, mwl;
     cuuint64_t adims[4] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)N};
     cuuint64_t astr[3] = {(cuuint64_t)Ca * 2, (cuuint64_t)Wa * Ca * 2, (cuuint64_t)Ha * Wa * Ca * 2};
-    cuuint32_t abox[4] = {32, (cuuint32_t)p.PW, (cuuint32_t)p.Hp, 1};
-    int rc = encode_map64(&mah, A_hi, 4, adims, astr, abox);
+    cuuint32_t abox[4] = {(cuuint32_t)KB, (cuuint32_t)p.PW, (cuuint32_t)p.Hp, 1};
+    int rc = encode_map64(&mah, A_hi, 4, adims, astr, abox, KB == 64);
     if (rc) return rc;
     mal = mah;
     if (npass >= 2 && (rc = encode_map64(&mal, A_lo, 4, adims, astr, abox))) return rc;
     cuuint64_t wdims[2] = {(cuuint64_t)T * Ca, (cuuint64_t)Cout * nphase};
     cuuint64_t wstr[1] = {(cuuint64_t)T * Ca * 2};
-    cuuint32_t wbox[2] = {32, 128};
-    if ((rc = encode_map64(&mwh, W_hi, 2, wdims, wstr, wbox))) return rc;
+    cuuint32_t wbox[2] = {(cuuint32_t)KB, 128};
+    if ((rc = encode_map64(&mwh, W_hi, 2, wdims, wstr, wbox, KB == 64))) return rc;
     mwl = mwh;
     if (npass >= 3 && (rc = encode_map64(&mwl, W_lo, 2, wdims, wstr, wbox))) return rc;
     int grid = p.total_tiles < dsr_num_sms() ? p.total_tiles : dsr_num_sms();
-    if (npass == 1) return launch_tc3<1>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
-    if (npass == 2) return launch_tc3<2>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
-    return launch_tc3<3>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    if (npass == 1 && KB == 64) return launch_tc3<1, 64>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    if (npass == 1) return launch_tc3<1, 32>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    if (npass == 2) return launch_tc3<2, 32>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    return launch_tc3<3, 32>(mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
 }

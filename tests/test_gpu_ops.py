@@ -420,6 +420,64 @@ def test_dgrad_group_forms_agree(ops, mode, pad, H, W):
         ops.CONFIG.update(old)
 
 
+@pytest.mark.parametrize("kind,Ci,Co,k,stride,pad,mode,H,W", [
+    ("conv", 128, 256, 3, 1, 1, "reflect", 32, 48), ("conv", 64, 128, 4, 2, 1, "zeros", 64, 64), ("conv", 32, 128, 7, 1, 3, "reflect", 32, 64),
+    ("convT", 256, 128, 4, 2, 1, "zeros", 16, 24), ("conv", 192, 128, 3, 1, 1, "replicate", 33, 21)])
+def test_tc3_single_pass_k64_stages(ops, kind, Ci, Co, k, stride, pad, mode, H, W):
+    """single-pass channel-major GEMM with 64-channel pipeline stages (128-byte rows, SWIZZLE_128B: conv_tc3_kernel<1, 64>) against
+    the 32-channel form (DSR_TC3_KB=32, same 16-bit operands, only the fp32 accumulation order differs) and the fp32 reference;
+    forward and data gradient (the 32 -> 128 7x7 case runs the quad form, Ca = 512, 21 taps)."""
+    import os
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=1, dtype="f16", bwd_dtype="bf16", wgrad_passes=1, big_hw=0, halo_min_tiles=0)
+        x = torch.randn(2, Ci, H, W, generator=G(170)).requires_grad_(True)
+        if kind == "conv":
+            w = (torch.randn(Co, Ci, k, k, generator=G(171)) * 0.05).requires_grad_(True)
+            xp = F.pad(x, (pad,) * 4, mode={"zeros": "constant"}.get(mode, mode))
+            ref = F.conv2d(xp, w, None, stride=stride)
+        else:
+            w = (torch.randn(Ci, Co, k, k, generator=G(171)) * 0.05).requires_grad_(True)
+            ref = F.conv_transpose2d(x, w, None, stride=stride, padding=pad)
+        go = torch.randn(ref.shape, generator=G(173))
+        (ref * go).sum().backward()
+        got = {}
+        for kb in ("32", "64"):
+            os.environ["DSR_TC3_KB"] = kb
+            xc, wc = cl(x.detach()).requires_grad_(True), w.detach().cuda().requires_grad_(True)
+            with _CallLog() as names:
+                if kind == "conv":
+                    out = ops.conv2d(xc, wc, None, stride, pad, pad_mode=mode)
+                else:
+                    out = ops.conv_transpose2d(xc, wc, None, stride, pad, 0)
+                (out * go.cuda()).sum().backward()
+            assert "dsr_tc_gemm3" in names, "the shape must reach the channel-major kernel"
+            got[kb] = (out.detach().cpu(), xc.grad.cpu())
+            assert rel_l2(got[kb][0], ref.detach()) <= 1e-3 and rel_l2(got[kb][1], x.grad) <= 8e-3
+        assert rel_l2(got["64"][0], got["32"][0]) <= 1e-6 and rel_l2(got["64"][1], got["32"][1]) <= 1e-6
+    finally:
+        os.environ.pop("DSR_TC3_KB", None)
+        ops.CONFIG.update(old)
+
+
+class _CallLog:
+    """records the names of the library calls made inside the `with` block"""
+
+    def __enter__(self):
+        from dsr_b200 import _lib
+        self.lib, self.orig, self.names = _lib, _lib.call, []
+
+        def logged(name, *a):
+            self.names.append(name)
+            return self.orig(name, *a)
+        _lib.call = logged
+        return self.names
+
+    def __exit__(self, *exc):
+        self.lib.call = self.orig
+        return False
+
+
 CONVT_CASES = [  # Cin, Cout, k, stride, pad, opad, H, W
     (128, 64, 3, 2, 1, 1, 8, 8), (64, 32, 3, 2, 1, 1, 9, 7), (512, 512, 4, 2, 1, 0, 2, 2), (1024, 256, 4, 2, 1, 0, 4, 4),
     (128, 1, 4, 2, 1, 0, 16, 16), (256, 128, 4, 2, 1, 0, 8, 8),
