@@ -793,7 +793,7 @@ static void pack_tiled_launch(const float* w, int D0, int D1, int Cp, int pa, in
 }
 // packed weight gradient [D0][T*Ca] (row = parameter dim 0, K channel = parameter dim 1) -> parameter layout
 __global__ void tc_unpack_wgrad_kernel(const float* __restrict__ dWp, int D0, int D1, int R, int S, int variant, int Cp,
-                                       int T, int Ca, float* __restrict__ grad, int accumulate) {
+                                       int T, int Ca, float* __restrict__ grad, int accumulate, int nsplit, long split_stride) {
     const long total = (long)D0 * D1 * R * S;
     // gather form (one thread per parameter element): invert tc_map_k
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -804,7 +804,9 @@ __global__ void tc_unpack_wgrad_kernel(const float* __restrict__ dWp, int D0, in
         if (variant == DSR_TC_W_CONV) { t = r * S + s; q = c; }
         else if (variant == DSR_TC_W_CONV_PAIR) { const int g = Ca / Cp, Sg = (S + g - 1) / g; t = r * Sg + s / g; q = (s % g) * Cp + c; }
         else { t = (r >> 1) * 2 + (s >> 1); q = ((r & 1) * 2 + (s & 1)) * Cp + c; }          // S2D
-        const float v = dWp[(long)d0 * ((long)T * Ca) + (long)t * Ca + q];
+        const float* src = dWp + (long)d0 * ((long)T * Ca) + (long)t * Ca + q;
+        float v = src[0];
+        for (int z = 1; z < nsplit; ++z) v += src[z * split_stride];      // K-split slabs of dsr_tc_wgrad2p, fixed order
         if (accumulate) grad[idx] += v; else grad[idx] = v;
     }
 }
@@ -1120,7 +1122,8 @@ extern "C" int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, i
 // into) the parameter's own contiguous [c][r][s] run.  The gather kernel above reads 4-byte elements Ca floats apart.
 template <int VARIANT, int RS>
 __global__ void __launch_bounds__(256)
-tc_unpack_wgrad_tiled_kernel(const float* __restrict__ dWp, int D0, int D1, int Cp, int Ca, float* __restrict__ grad, int accumulate) {
+tc_unpack_wgrad_tiled_kernel(const float* __restrict__ dWp, int D0, int D1, int Cp, int Ca, float* __restrict__ grad, int accumulate,
+                             int nsplit, long split_stride) {
     constexpr int S = RS == 9 ? 3 : 4, R = S, TC = 128, RSP = RS + 1;
     constexpr int NAB = VARIANT == DSR_TC_W_CONV_S2D ? 4 : 1, T = VARIANT == DSR_TC_W_CONV_S2D ? 4 : RS;
     __shared__ float gt[TC * RSP];
@@ -1133,7 +1136,12 @@ tc_unpack_wgrad_tiled_kernel(const float* __restrict__ dWp, int D0, int D1, int 
             const int c_l = i % TC, u = i / TC, ab = u % NAB, t = u / NAB;
             int r, sx;
             if (NAB == 4) { r = 2 * (t >> 1) + (ab >> 1); sx = 2 * (t & 1) + (ab & 1); } else { r = t / S; sx = t - r * S; }
-            if (c_l < nc && r < R && sx < S) gt[c_l * RSP + r * S + sx] = __ldg(src + (long)t * Ca + ab * Cp + c0 + c_l);
+            if (c_l < nc && r < R && sx < S) {
+                const float* e = src + (long)t * Ca + ab * Cp + c0 + c_l;
+                float v = __ldg(e);
+                for (int z = 1; z < nsplit; ++z) v += __ldg(e + z * split_stride);     // K-split slabs, fixed order
+                gt[c_l * RSP + r * S + sx] = v;
+            }
         }
         __syncthreads();
         float* dst = grad + ((long)d0 * D1 + c0) * RS;
@@ -1144,9 +1152,11 @@ tc_unpack_wgrad_tiled_kernel(const float* __restrict__ dWp, int D0, int D1, int 
         }
     }
 }
-extern "C" int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
-                                   float* grad, int accumulate, void* stream) {
-    DSR_REQUIRE(dWp && grad, "null pointer");
+// nsplit slabs of [D0][T*Ca] (dsr_tc_wgrad2p with partial = 1) summed in slab order on the way in; nsplit = 1: one matrix
+extern "C" int dsr_tc_unpack_wgrad_splits(const float* dWp, int nsplit, int D0, int D1, int R, int S, int variant, int Cp, int T,
+                                          int Ca, float* grad, int accumulate, void* stream) {
+    DSR_REQUIRE(dWp && grad && nsplit >= 1, "null pointer / bad split count");
+    const long split_stride = (long)D0 * T * Ca;
     DSR_REQUIRE(variant == DSR_TC_W_CONV || variant == DSR_TC_W_CONV_PAIR || variant == DSR_TC_W_CONV_S2D, "unsupported variant");
     {
         const char* e = getenv("DSR_PACK_TILED");
@@ -1155,7 +1165,7 @@ extern "C" int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int 
             (long)D0 * D1 * RS >= (1L << 16)) {
             const long tiles = (long)D0 * dsr_cdiv(D1, 128), cap = (long)dsr_num_sms() * 8;
             const int grid = (int)(tiles < cap ? tiles : cap);
-#define UNPACK_TILED(V, K) tc_unpack_wgrad_tiled_kernel<V, K><<<grid, 256, 0, ST(stream)>>>(dWp, D0, D1, Cp, Ca, grad, accumulate)
+#define UNPACK_TILED(V, K) tc_unpack_wgrad_tiled_kernel<V, K><<<grid, 256, 0, ST(stream)>>>(dWp, D0, D1, Cp, Ca, grad, accumulate, nsplit, split_stride)
             if (variant == DSR_TC_W_CONV) { if (RS == 9) UNPACK_TILED(DSR_TC_W_CONV, 9); else UNPACK_TILED(DSR_TC_W_CONV, 16); }
             else { if (RS == 9) UNPACK_TILED(DSR_TC_W_CONV_S2D, 9); else UNPACK_TILED(DSR_TC_W_CONV_S2D, 16); }
 #undef UNPACK_TILED
@@ -1163,6 +1173,10 @@ extern "C" int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int 
         }
     }
     tc_unpack_wgrad_kernel<<<dsr_grid((long)D0 * D1 * R * S, 256), 256, 0, ST(stream)>>>(dWp, D0, D1, R, S, variant, Cp, T, Ca, grad,
-                                                                                        accumulate);
+                                                                                        accumulate, nsplit, split_stride);
     return dsr_check_launch("tc_unpack_wgrad");
+}
+extern "C" int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
+                                   float* grad, int accumulate, void* stream) {
+    return dsr_tc_unpack_wgrad_splits(dWp, 1, D0, D1, R, S, variant, Cp, T, Ca, grad, accumulate, stream);
 }

@@ -29,6 +29,8 @@ struct Wg2Params {
     int per;                  // column blocks per CTA (<= NB; the groups are balanced: per = ceil(nblocks / groups))
     int f16;
     float out_scale;
+    int partial;              // 1: every K split STORES its own [Cm_real][ld] slab (dWp + z * split_stride), no atomics
+    long split_stride;
     signed char dr[WG2_MAX_TAPS], ds[WG2_MAX_TAPS];
 };
 
@@ -141,8 +143,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap mapM, const __grid_constant
         const int q = warp & 3;
         const int cm = cm0 + q * 32 + lane;
         const bool valid = cm < p.Cm_real && nk > 0;
-        float* orow = dWp + (long)cm * p.ld + (long)gb0 * 64;
-        const bool split = gridDim.z > 1;
+        float* orow = dWp + (p.partial ? (long)blockIdx.z * p.split_stride : 0L) + (long)cm * p.ld + (long)gb0 * 64;
+        const bool split = gridDim.z > 1 && !p.partial;
         if (nk > 0) {
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
@@ -186,19 +188,10 @@ static int launch_wg2(const CUtensorMap& mm, const CUtensorMap& ma, const Wg2Par
     return dsr_check_launch("wgrad_tc2");
 }
 
-// Single-pass (hi planes only) weight gradient; same arguments as dsr_tc_wgrad minus the low planes.
-extern "C" int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h, int m_off_w,
-                             const void* A_hi, int Ha, int Wa, int Ca, int T, const int* tap_dr, const int* tap_ds,
-                             int a_off_h, int a_off_w, int Hb, int Wb, float* dWp, int f16, float out_scale, int split_k,
-                             void* stream) {
-    DSR_REQUIRE(M_hi && A_hi && dWp && tap_dr && tap_ds, "null pointer");
-    DSR_REQUIRE(T >= 1 && T <= WG2_MAX_TAPS && (Ca & 63) == 0 && (Cm & 63) == 0 && Cm_real >= 1 && Cm_real <= Cm, "bad GEMM shape");
-    DSR_REQUIRE(!((uintptr_t)dWp & 15) && (((long)T * Ca) & 3) == 0, "packed gradient rows must be 16-byte aligned");
+// K tiling and split count of a launch (shared by the launch and by dsr_tc_wgrad2_splits)
+static void wg2_plan(int N, int Hb, int Wb, int Cm_real, int Ca, int T, int split_k, Wg2Params& p, int& groups, int& tiles_m, int& splits) {
     constexpr int NB = 8, KT = 32;
-    Wg2Params p;
-    p.N = N; p.Hb = Hb; p.Wb = Wb; p.mh = m_off_h; p.mw = m_off_w; p.ah = a_off_h; p.aw = a_off_w;
-    p.Cm_real = Cm_real; p.ncb = Ca / 64; p.nblocks = T * p.ncb; p.ld = T * Ca; p.f16 = f16; p.out_scale = out_scale;
-    for (int t = 0; t < T; ++t) { p.dr[t] = (signed char)tap_dr[t]; p.ds[t] = (signed char)tap_ds[t]; }
+    p.ncb = Ca / 64; p.nblocks = T * p.ncb; p.ld = T * Ca;
     int TW = Wb >= 16 ? 16 : pow2_ceil(Wb);
     if (TW > KT) TW = KT;
     int TH = KT / TW;
@@ -207,12 +200,12 @@ extern "C" int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, in
     p.TW = TW; p.TH = TH; p.TN = TN;
     p.tiles_w = dsr_cdiv(Wb, TW); p.tiles_h = dsr_cdiv(Hb, TH);
     p.tiles_total = p.tiles_w * p.tiles_h * dsr_cdiv(N, TN);
-    int groups = dsr_cdiv(p.nblocks, NB);
+    groups = dsr_cdiv(p.nblocks, NB);
     p.per = dsr_cdiv(p.nblocks, groups);
     groups = dsr_cdiv(p.nblocks, p.per);
-    const int tiles_m = dsr_cdiv(Cm_real, 128);
+    tiles_m = dsr_cdiv(Cm_real, 128);
     const long ctas = (long)groups * tiles_m;
-    int splits = 1;
+    splits = 1;
     if (split_k < 0) {
         // one wave of CTAs over the SMs (1 CTA / SM: 160 KB of stages, all 512 TMEM columns), at least 8 K tiles per split
         splits = (int)(dsr_num_sms() / ctas);
@@ -221,7 +214,42 @@ extern "C" int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, in
     } else if (split_k > 1) splits = split_k;
     p.tiles_per_split = dsr_cdiv(p.tiles_total, splits);
     splits = dsr_cdiv(p.tiles_total, p.tiles_per_split);
-    if (splits > 1 && cudaMemsetAsync(dWp, 0, (size_t)Cm_real * T * Ca * sizeof(float), ST(stream)) != cudaSuccess) {
+}
+
+// number of K splits dsr_tc_wgrad2 / dsr_tc_wgrad2p will run for this shape (>= 1; < 0 on bad arguments): the caller of the
+// partial-slab form sizes its buffer with it
+extern "C" int dsr_tc_wgrad2_splits(int N, int Hb, int Wb, int Cm_real, int Ca, int T, int split_k) {
+    if (N < 1 || Hb < 1 || Wb < 1 || Cm_real < 1 || T < 1 || T > WG2_MAX_TAPS || (Ca & 63) || Ca < 64) return -1;
+    Wg2Params p;
+    int groups, tiles_m, splits;
+    wg2_plan(N, Hb, Wb, Cm_real, Ca, T, split_k, p, groups, tiles_m, splits);
+    return splits;
+}
+
+// Single-pass (hi planes only) weight gradient; same arguments as dsr_tc_wgrad minus the low planes.
+// partial = 0: dWp is ONE [Cm_real][T*Ca] matrix, K splits add into it with vector reductions (memset first).
+// partial = 1: dWp holds dsr_tc_wgrad2_splits(...) slabs of [Cm_real][T*Ca]; split z stores slab z with plain stores and
+//              dsr_tc_unpack_wgrad_splits sums the slabs in a fixed order on the way into the parameter layout - no memset, no
+//              atomics (a 48-way split of a 3x3 128-channel layer put 28 MB of red.add on a 590 KB matrix), and the weight
+//              gradient becomes bit-reproducible.
+extern "C" int dsr_tc_wgrad2p(const void* M_hi, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h, int m_off_w,
+                              const void* A_hi, int Ha, int Wa, int Ca, int T, const int* tap_dr, const int* tap_ds,
+                              int a_off_h, int a_off_w, int Hb, int Wb, float* dWp, int f16, float out_scale, int split_k,
+                              int partial, void* stream) {
+    DSR_REQUIRE(M_hi && A_hi && dWp && tap_dr && tap_ds, "null pointer");
+    DSR_REQUIRE(T >= 1 && T <= WG2_MAX_TAPS && (Ca & 63) == 0 && (Cm & 63) == 0 && Cm_real >= 1 && Cm_real <= Cm, "bad GEMM shape");
+    DSR_REQUIRE(!((uintptr_t)dWp & 15) && (((long)T * Ca) & 3) == 0, "packed gradient rows must be 16-byte aligned");
+    constexpr int NB = 8, KT = 32;
+    Wg2Params p;
+    p.N = N; p.Hb = Hb; p.Wb = Wb; p.mh = m_off_h; p.mw = m_off_w; p.ah = a_off_h; p.aw = a_off_w;
+    p.Cm_real = Cm_real; p.f16 = f16; p.out_scale = out_scale;
+    for (int t = 0; t < T; ++t) { p.dr[t] = (signed char)tap_dr[t]; p.ds[t] = (signed char)tap_ds[t]; }
+    int groups, tiles_m, splits;
+    wg2_plan(N, Hb, Wb, Cm_real, Ca, T, split_k, p, groups, tiles_m, splits);
+    p.partial = partial ? 1 : 0;
+    p.split_stride = (long)Cm_real * T * Ca;
+    const int TW = p.TW, TH = p.TH, TN = p.TN;
+    if (!partial && splits > 1 && cudaMemsetAsync(dWp, 0, (size_t)Cm_real * T * Ca * sizeof(float), ST(stream)) != cudaSuccess) {
         dsr_set_error("wgrad_tc2: memset failed"); return DSR_ERR_CUDA;
     }
     CUtensorMap mm, ma;
@@ -235,4 +263,12 @@ extern "C" int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, in
     if ((rc = encode_map(&ma, A_hi, 4, adims, astr, box))) return rc;
     dim3 grid((unsigned)groups, (unsigned)tiles_m, (unsigned)splits);
     return launch_wg2<NB, KT>(mm, ma, p, dWp, grid, ST(stream));
+}
+
+extern "C" int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h, int m_off_w,
+                             const void* A_hi, int Ha, int Wa, int Ca, int T, const int* tap_dr, const int* tap_ds,
+                             int a_off_h, int a_off_w, int Hb, int Wb, float* dWp, int f16, float out_scale, int split_k,
+                             void* stream) {
+    return dsr_tc_wgrad2p(M_hi, N, Hm, Wm, Cm, Cm_real, m_off_h, m_off_w, A_hi, Ha, Wa, Ca, T, tap_dr, tap_ds, a_off_h, a_off_w,
+                          Hb, Wb, dWp, f16, out_scale, split_k, 0, stream);
 }

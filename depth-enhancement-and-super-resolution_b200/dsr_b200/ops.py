@@ -303,6 +303,9 @@ CONFIG = {
     "csum_reps": 8,      # replica rows of the bias-gradient sums dsr_tc_prep takes on the way (fp64 atomics spread over 8 addresses
                          # per channel, which lets the launch keep the wide grid of the sum-free form); 1 = one row, narrow grid
     "fold_finalize": True,   # dsr_norm_finalize folded into its first consumer (dsr_tc_prep_fin / dsr_norm_apply_fwd_fin)
+    "wgrad_slabs": False,  # True: weight-gradient K splits store their own slabs (dsr_tc_wgrad2p) and the unpack sums them in a
+                           # fixed order: bit-reproducible weight gradients, no atomics.  Measured on B200 (r2z): +0.35 ms per step
+                           # (the unpack reads up to 48 slabs: 0.50 -> 1.43 ms; the GEMMs themselves gain 3 %), so off by default
     "dgrad_quad": True,  # ... FOUR adjacent pixels per row for Cin = 32: 128 GEMM rows = one M tile of the channel-major kernel
     "dgrad_pair": True,  # stride-1 data gradients with <= 32 output channels: two adjacent pixels per GEMM row (MMA N = 64, not 32)
 }
@@ -829,24 +832,34 @@ def _tc_wgrad(M, Cm_real, A, a_plan, a_pad, a_pad_mode, dr, ds, Hb, Wb, weight, 
     N = M.shape[0]
     T, Ca = a_plan["T"], a_plan["Ca"]
     D0, D1, R, S = weight.shape
-    dwp = torch.empty((Cm_real, T * Ca), device=M.device, dtype=torch.float32)
     f16 = 3 if dt == "f16" else 0                                        # bit 0: format of M, bit 1: format of A
     _lib.PROFILE_META = dict(macs=N * Hb * Wb * D0 * D1 * R * S, shape=(N, Hb, Wb, Cm_real, Ca, T, 0), passes=npass)
+    nsplit = 1
     if CONFIG["wgrad_kernel"] == 2 and npass == 1:
-        _call("dsr_tc_wgrad2", _p(mhi, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad, _p(ahi, torch.bfloat16), Ha, Wa, Ca, T,
-              _int_array(dr), _int_array(ds), 0, 0, Hb, Wb, _p(dwp), f16, 1.0, CONFIG["split_k"])
+        if CONFIG["wgrad_slabs"]:
+            # every K split stores its own slab; the unpack below sums them in a fixed order (no memset, no atomics)
+            nsplit = _lib.load().dsr_tc_wgrad2_splits(N, Hb, Wb, Cm_real, Ca, T, CONFIG["split_k"])
+            if nsplit < 1:
+                raise RuntimeError("dsr_tc_wgrad2_splits: bad weight-gradient shape")
+        dwp = torch.empty((nsplit, Cm_real, T * Ca), device=M.device, dtype=torch.float32)
+        _call("dsr_tc_wgrad2p", _p(mhi, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad, _p(ahi, torch.bfloat16), Ha, Wa, Ca, T,
+              _int_array(dr), _int_array(ds), 0, 0, Hb, Wb, _p(dwp), f16, 1.0, nsplit if CONFIG["wgrad_slabs"] else CONFIG["split_k"],
+              int(CONFIG["wgrad_slabs"]))
     else:
+        dwp = torch.empty((Cm_real, T * Ca), device=M.device, dtype=torch.float32)
         _call("dsr_tc_wgrad", _p(mhi, torch.bfloat16), _p(mlo, torch.bfloat16), N, Hm, Wm, Cm, Cm_real, mpad, mpad,
               _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, T, _int_array(dr), _int_array(ds), 0, 0,
               Hb, Wb, _p(dwp), npass, f16, 1.0, -1)
     _keep(mhi, mlo, ahi, alo, M.xh, A.xh, *getattr(M, "parts", ()), *getattr(A, "parts", ()))
     tgt = DIRECT_GRADS.get(weight.data_ptr())
     if tgt is not None:
-        _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(tgt), 1)
+        _call("dsr_tc_unpack_wgrad_splits", _p(dwp), nsplit, D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(tgt), 1)
+        _keep(dwp)
         _grad_ready(weight)
         return None
     gw = torch.empty(weight.shape, device=M.device, dtype=torch.float32)
-    _call("dsr_tc_unpack_wgrad", _p(dwp), D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(gw), 0)
+    _call("dsr_tc_unpack_wgrad_splits", _p(dwp), nsplit, D0, D1, R, S, variant, a_plan["Cp"], T, Ca, _p(gw), 0)
+    _keep(dwp)
     return gw
 
 

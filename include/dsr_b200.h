@@ -330,8 +330,19 @@ int dsr_tc_wgrad(const void* M_hi, const void* M_lo, int N, int Hm, int Wm, int 
 int dsr_tc_wgrad2(const void* M_hi, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h, int m_off_w, const void* A_hi,
                   int Ha, int Wa, int Ca, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb,
                   float* dWp, int f16, float out_scale, int split_k, void* stream);
+/* the same GEMM with partial = 1: dWp holds dsr_tc_wgrad2_splits(...) slabs of [Cm_real][T*Ca]; K split z STORES slab z (no
+ * memset, no atomics) and dsr_tc_unpack_wgrad_splits sums the slabs in a fixed order on the way into the parameter layout:
+ * the weight gradient of every nn.Conv2d / nn.ConvTranspose2d (networks.py:379-415, :544-616) becomes bit-reproducible and the
+ * 30-50-way red.add fan-in of the short-K layers is gone.  partial = 0 is dsr_tc_wgrad2. */
+int dsr_tc_wgrad2p(const void* M_hi, int N, int Hm, int Wm, int Cm, int Cm_real, int m_off_h, int m_off_w, const void* A_hi,
+                   int Ha, int Wa, int Ca, int T, const int* tap_dr, const int* tap_ds, int a_off_h, int a_off_w, int Hb, int Wb,
+                   float* dWp, int f16, float out_scale, int split_k, int partial, void* stream);
+/* host-only query: the number of K splits (slabs) the launch above will use for this shape; < 0 = bad arguments */
+int dsr_tc_wgrad2_splits(int N, int Hb, int Wb, int Cm_real, int Ca, int T, int split_k);
 int dsr_tc_unpack_wgrad(const float* dWp, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
                         float* grad, int accumulate, void* stream);
+int dsr_tc_unpack_wgrad_splits(const float* dWp, int nsplit, int D0, int D1, int R, int S, int variant, int Cp, int T, int Ca,
+                               float* grad, int accumulate, void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------------- */
 /* torch.optim.Adam (defaults) over one flat arena.  models/main_model.py:176, :429. */

@@ -906,6 +906,32 @@ PACK_CASES = [  # variant, (D0, D1, R, S), Cp, T, Ca, Cout, phase
 ]
 
 
+@pytest.mark.parametrize("kind,Ci,Co,k,stride,pad,H,W", [("conv", 128, 128, 3, 1, 1, 64, 64), ("conv", 64, 128, 4, 2, 1, 64, 48),
+                                                      ("convT", 128, 64, 4, 2, 1, 32, 32), ("conv", 32, 128, 7, 1, 3, 48, 64)])
+def test_wgrad_slabs_match_atomics_and_are_reproducible(ops, kind, Ci, Co, k, stride, pad, H, W):
+    """dsr_tc_wgrad2p with partial = 1 (every K split stores its own slab, dsr_tc_unpack_wgrad_splits sums them in slab order)
+    against the red.add form of the same GEMM: same products, fp32 summation order differs; and two runs of the slab form
+    must be bit-identical (the atomics form is not).  Weight gradients of networks.py:379-415, :544-616."""
+    old = dict(ops.CONFIG)
+    try:
+        x = torch.randn(4, Ci, H, W, generator=G(180))
+        w = (torch.randn(*((Co, Ci, k, k) if kind == "conv" else (Ci, Co, k, k)), generator=G(181)) * 0.05)
+        res = {}
+        for name, slabs in (("atomics", False), ("slabs", True), ("slabs2", True)):
+            ops.CONFIG.update(old)
+            ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=1, wgrad_slabs=slabs)
+            xc, wc = cl(x).requires_grad_(True), w.cuda().requires_grad_(True)
+            with _CallLog() as names:
+                out = ops.conv2d(xc, wc, None, stride, pad) if kind == "conv" else ops.conv_transpose2d(xc, wc, None, stride, pad, 0)
+                (out * out).sum().backward()
+            assert "dsr_tc_wgrad2p" in names
+            res[name] = wc.grad.cpu()
+        assert rel_l2(res["slabs"], res["atomics"]) <= 1e-6
+        assert torch.equal(res["slabs"], res["slabs2"])
+    finally:
+        ops.CONFIG.update(old)
+
+
 @pytest.mark.parametrize("case", PACK_CASES)
 @pytest.mark.parametrize("f16", [1, 0])
 def test_tiled_weight_pack_matches_gather_kernel(ops, case, f16):
