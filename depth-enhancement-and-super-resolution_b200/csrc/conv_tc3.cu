@@ -34,6 +34,7 @@ struct Tc3Params {
     int n_pb, n_ws;
     unsigned patch_plane_bytes, patch_tx_bytes;
     signed char dr[TC3_MAX_TAPS], ds[TC3_MAX_TAPS];
+    unsigned shift16[TC3_MAX_TAPS];   // per tap: (dr * PW + ds) * row bytes >> 4 = what the patch descriptor's address field moves by
 };
 
 // K-major SWIZZLE_64B descriptor (64-byte rows, 8-row groups): layout type 4; LBO unused (1); SBO = group stride
@@ -119,8 +120,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 
     if (warp == 0) {
         // ===== patch producer: one box per (tile, 32-channel block) =====
+        // (ring positions and barrier parities advance incrementally in all three roles: a runtime `i % n` / `i / n` pair is a
+        // ~30-instruction dependent chain through MUFU.RCP, and the MMA issuer's loop was LATENCY-bound at ~860 cycles per
+        // stage - ncu source view r2z - against 512 cycles of tensor work)
         {
-            int pi = 0;
+            int pb = 0;
+            uint32_t pph = 1u;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int phase = tile / p.tiles_per_phase;
                 int r = (tile - phase * p.tiles_per_phase) / p.tiles_co;
@@ -128,16 +133,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 const int th_i = r % p.tiles_h;
                 const int n = r / p.tiles_h;
                 const int hc = th_i * p.TH + p.ah + (phase >> 1), wc = tw_i * TC3_TW + p.aw + (phase & 1);
-                for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
-                    const int b = pi % p.n_pb, it = pi / p.n_pb;
-                    TC3_TIMED_WAIT(0, pe(b), (it & 1) ^ 1);
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    TC3_TIMED_WAIT(0, pe(pb), pph);
                     if (elect_one()) {
-                        const uint32_t dst = smem_base + b * patch_set;
-                        mbar_expect_tx(pf(b), NA * p.patch_tx_bytes);
-                        tma_load_4d(dst, &mapA_hi, pf(b), cb * KB, wc, hc, n);
-                        if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(b), cb * KB, wc, hc, n);
+                        const uint32_t dst = smem_base + pb * patch_set;
+                        mbar_expect_tx(pf(pb), NA * p.patch_tx_bytes);
+                        tma_load_4d(dst, &mapA_hi, pf(pb), cb * KB, wc, hc, n);
+                        if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(pb), cb * KB, wc, hc, n);
                     }
                     __syncwarp();
+                    if (++pb == p.n_pb) { pb = 0; pph ^= 1u; }
                 }
             }
             if (dbg && lane == 0) dbg[blockIdx.x * 16 + 6] = dbg_acc[0];
@@ -145,22 +150,23 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     } else if (warp == 1) {
         // ===== weight producer: one [128 co x 32 k] tile (hi, lo) per (tile, block, tap) =====
         {
-            int wi = 0;
+            int ws = 0;
+            uint32_t wph = 1u, dst = w_base, full = wf(0), empty = we(0);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int phase = tile / p.tiles_per_phase;
                 const int co0 = ((tile - phase * p.tiles_per_phase) % p.tiles_co) * 128 + phase * p.Cout;
                 for (int cb = 0; cb < p.cblocks; ++cb) {
-                    for (int t = 0; t < p.T; ++t, ++wi) {
-                        const int s = wi % p.n_ws, it = wi / p.n_ws;
-                        TC3_TIMED_WAIT(0, we(s), (it & 1) ^ 1);
+                    int kw = cb * KB;
+                    for (int t = 0; t < p.T; ++t, kw += p.Ca) {
+                        TC3_TIMED_WAIT(0, empty, wph);
                         if (elect_one()) {
-                            const uint32_t dst = w_base + s * w_stage;
-                            const int kw = t * p.Ca + cb * KB;
-                            mbar_expect_tx(wf(s), w_stage);
-                            tma_load_2d(dst, &mapW_hi, wf(s), kw, co0);
-                            if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, wf(s), kw, co0);
+                            mbar_expect_tx(full, w_stage);
+                            tma_load_2d(dst, &mapW_hi, full, kw, co0);
+                            if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, full, kw, co0);
                         }
                         __syncwarp();
+                        dst += w_stage; full += 8u; empty += 8u;
+                        if (++ws == p.n_ws) { ws = 0; wph ^= 1u; dst = w_base; full = wf(0); empty = we(0); }
                     }
                 }
             }
@@ -173,26 +179,26 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             const uint32_t idesc = make_idesc(128, 8 * p.TH, p.f16 ? 0u : 1u);
             const uint64_t wdesc0 = KB == 32 ? make_sdesc64(0, 512) : make_sdesc128(0, 1024);   // address field added per MMA
             const uint64_t pdesc0 = KB == 32 ? make_sdesc64(0, (uint32_t)p.PW * 64u) : make_sdesc128(0, (uint32_t)p.PW * 128u);
-            int pi = 0, wi = 0, ti = 0;
+            int pb = 0, ws = 0, ti = 0;
+            uint32_t pph = 0u, wph = 0u, full = wf(0), empty = we(0);
+            const uint64_t wd_first = wdesc0 + (uint64_t)((w_base & 0x3FFFF) >> 4);     // descriptor of weight stage 0
+            uint64_t wd_hi = wd_first;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
                 const int ab = ti & 1;
                 TC3_TIMED_WAIT(2, ae(ab), ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)ab * ACC_COLS;
-                for (int cb = 0; cb < p.cblocks; ++cb, ++pi) {
-                    const int b = pi % p.n_pb;
-                    TC3_TIMED_WAIT(0, pf(b), (pi / p.n_pb) & 1);
-                    const uint32_t patch_hi = smem_base + b * patch_set, patch_lo = patch_hi + p.patch_plane_bytes;
-                    for (int t = 0; t < p.T; ++t, ++wi) {
-                        const int s = wi % p.n_ws;
-                        TC3_TIMED_WAIT(1, wf(s), (wi / p.n_ws) & 1);
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    TC3_TIMED_WAIT(0, pf(pb), pph);
+                    const uint32_t patch_hi = smem_base + pb * patch_set;
+                    const uint64_t pd_base = pdesc0 + (uint64_t)((patch_hi & 0x3FFFF) >> 4);
+                    const uint32_t pe_bar = pe(pb);
+                    for (int t = 0; t < p.T; ++t) {
+                        TC3_TIMED_WAIT(1, full, wph);
                         if (elect_one()) {
-                            const uint32_t w_hi = w_base + s * w_stage;
-                            const uint32_t shift = (uint32_t)(p.dr[t] * p.PW + p.ds[t]) * ROWB;
-                            const uint64_t wd_hi = wdesc0 + (uint64_t)((w_hi & 0x3FFFF) >> 4);
                             const uint64_t wd_lo = wd_hi + (uint64_t)(W_TILE >> 4);
-                            const uint64_t pd_hi = pdesc0 + (uint64_t)(((patch_hi + shift) & 0x3FFFF) >> 4);
-                            const uint64_t pd_lo = pdesc0 + (uint64_t)(((patch_lo + shift) & 0x3FFFF) >> 4);
+                            const uint64_t pd_hi = pd_base + (uint64_t)p.shift16[t];
+                            const uint64_t pd_lo = pd_hi + (uint64_t)(p.patch_plane_bytes >> 4);
                             const uint32_t first = (cb | t) ? 1u : 0u;          // 0 only for the first MMA of the tile
 #pragma unroll
                             for (int kk = 0; kk < KB / 16; ++kk)                // one K = 16 MMA per 32 bytes of the rows
@@ -205,14 +211,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 #pragma unroll
                                 for (int kk = 0; kk < KB / 16; ++kk) tc_mma_bf16(d_tmem, wd_lo + 2 * kk, pd_hi + 2 * kk, idesc, 1u);
                             }
-                            tc_commit(we(s));
+                            tc_commit(empty);
                             if (t == p.T - 1) {
-                                tc_commit(pe(b));
+                                tc_commit(pe_bar);
                                 if (cb == p.cblocks - 1) tc_commit(af(ab));
                             }
                         }
                         __syncwarp();
+                        wd_hi += (uint64_t)(w_stage >> 4); full += 8u; empty += 8u;
+                        if (++ws == p.n_ws) { ws = 0; wph ^= 1u; wd_hi = wd_first; full = wf(0); empty = we(0); }
                     }
+                    if (++pb == p.n_pb) { pb = 0; pph ^= 1u; }
                 }
             }
             if (dbg && lane == 0) {
@@ -404,6 +413,7 @@ extern "C" int dsr_tc_gemm3(const void* A_hi, const void* A_lo, int N, int Ha, i
     p.tiles_w = dsr_cdiv(Wt, TC3_TW); p.tiles_h = dsr_cdiv(Ht, p.TH);
     p.nphase = nphase; p.tiles_per_phase = p.tiles_w * p.tiles_h * p.tiles_co * N;
     p.total_tiles = p.tiles_per_phase * nphase;
+    for (int t = 0; t < T; ++t) p.shift16[t] = ((unsigned)(tap_dr[t] * p.PW + tap_ds[t]) * rowb) >> 4;
     p.patch_tx_bytes = (unsigned)p.Hp * p.PW * rowb;
     p.patch_plane_bytes = (p.patch_tx_bytes + 1023u) & ~1023u;
     const int na = npass >= 2 ? 2 : 1, nw = npass >= 3 ? 2 : 1;

@@ -10,7 +10,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
-LIB_PATH = os.path.join(_HERE, "libdsr_b200.so")
+LIB_PATH = os.environ.get("DSR_B200_LIB") or os.path.join(_HERE, "libdsr_b200.so")     # (override: A/B of two builds on one box)
 HEADER_PATH = os.path.join(_ROOT, "include", "dsr_b200.h")
 
 _lib = None
