@@ -126,6 +126,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         {
             int pb = 0;
             uint32_t pph = 1u;
+            const bool leader = elect_one();           // ONE thread runs the whole role (see the MMA issuer below)
+            if (leader)
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int phase = tile / p.tiles_per_phase;
                 int r = (tile - phase * p.tiles_per_phase) / p.tiles_co;
@@ -135,23 +137,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 const int hc = th_i * p.TH + p.ah + (phase >> 1), wc = tw_i * TC3_TW + p.aw + (phase & 1);
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     TC3_TIMED_WAIT(0, pe(pb), pph);
-                    if (elect_one()) {
+                    {
                         const uint32_t dst = smem_base + pb * patch_set;
                         mbar_expect_tx(pf(pb), NA * p.patch_tx_bytes);
                         tma_load_4d(dst, &mapA_hi, pf(pb), cb * KB, wc, hc, n);
                         if (NPASS >= 2) tma_load_4d(dst + p.patch_plane_bytes, &mapA_lo, pf(pb), cb * KB, wc, hc, n);
                     }
-                    __syncwarp();
                     if (++pb == p.n_pb) { pb = 0; pph ^= 1u; }
                 }
             }
-            if (dbg && lane == 0) dbg[blockIdx.x * 16 + 6] = dbg_acc[0];
+            if (dbg && leader) dbg[blockIdx.x * 16 + 6] = dbg_acc[0];
         }
     } else if (warp == 1) {
         // ===== weight producer: one [128 co x 32 k] tile (hi, lo) per (tile, block, tap) =====
         {
             int ws = 0;
             uint32_t wph = 1u, dst = w_base, full = wf(0), empty = we(0);
+            const bool leader = elect_one();
+            if (leader)
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int phase = tile / p.tiles_per_phase;
                 const int co0 = ((tile - phase * p.tiles_per_phase) % p.tiles_co) * 128 + phase * p.Cout;
@@ -159,18 +162,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     int kw = cb * KB;
                     for (int t = 0; t < p.T; ++t, kw += p.Ca) {
                         TC3_TIMED_WAIT(0, empty, wph);
-                        if (elect_one()) {
+                        {
                             mbar_expect_tx(full, w_stage);
                             tma_load_2d(dst, &mapW_hi, full, kw, co0);
                             if (NPASS >= 3) tma_load_2d(dst + W_TILE, &mapW_lo, full, kw, co0);
                         }
-                        __syncwarp();
                         dst += w_stage; full += 8u; empty += 8u;
                         if (++ws == p.n_ws) { ws = 0; wph ^= 1u; dst = w_base; full = wf(0); empty = we(0); }
                     }
                 }
             }
-            if (dbg && lane == 0) dbg[blockIdx.x * 16 + 7] = dbg_acc[0];
+            if (dbg && leader) dbg[blockIdx.x * 16 + 7] = dbg_acc[0];
         }
     } else if (warp == 2) {
         // ===== MMA issuer: A operand = weights (M = 128 channels), B operand = shifted patch (N = 8*TH pixels).
@@ -183,6 +185,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             uint32_t pph = 0u, wph = 0u, full = wf(0), empty = we(0);
             const uint64_t wd_first = wdesc0 + (uint64_t)((w_base & 0x3FFFF) >> 4);     // descriptor of weight stage 0
             uint64_t wd_hi = wd_first;
+            // ONE elected thread runs the whole loop, waits included: inside a region the compiler knows to be single-threaded
+            // the loop state can live in uniform registers next to the UTCHMMA operands (a per-stage `if (elect_one())` in a
+            // warp-wide loop cost ~12 R2UR moves, an ELECT and a BSSY / BSYNC pair per stage)
+            const bool leader = elect_one();
+            if (leader)
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
                 const int ab = ti & 1;
                 TC3_TIMED_WAIT(2, ae(ab), ((ti >> 1) & 1) ^ 1);
@@ -195,7 +202,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     const uint32_t pe_bar = pe(pb);
                     for (int t = 0; t < p.T; ++t) {
                         TC3_TIMED_WAIT(1, full, wph);
-                        if (elect_one()) {
+                        {
                             const uint64_t wd_lo = wd_hi + (uint64_t)(W_TILE >> 4);
                             const uint64_t pd_hi = pd_base + (uint64_t)p.shift16[t];
                             const uint64_t pd_lo = pd_hi + (uint64_t)(p.patch_plane_bytes >> 4);
@@ -217,14 +224,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                                 if (cb == p.cblocks - 1) tc_commit(af(ab));
                             }
                         }
-                        __syncwarp();
                         wd_hi += (uint64_t)(w_stage >> 4); full += 8u; empty += 8u;
                         if (++ws == p.n_ws) { ws = 0; wph ^= 1u; wd_hi = wd_first; full = wf(0); empty = we(0); }
                     }
                     if (++pb == p.n_pb) { pb = 0; pph ^= 1u; }
                 }
             }
-            if (dbg && lane == 0) {
+            if (dbg && leader) {
                 dbg[blockIdx.x * 16 + 0] = dbg_acc[0]; dbg[blockIdx.x * 16 + 1] = dbg_acc[1];
                 dbg[blockIdx.x * 16 + 2] = dbg_acc[2]; dbg[blockIdx.x * 16 + 3] = clock64() - t_start;
             }
