@@ -92,26 +92,29 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap mapM, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         const uint32_t stage_tx = (uint32_t)(2 + nb) * Cfg::BOX;
+        int s = 0;
+        uint32_t ph = 1u;
+        // K-tile coordinates and the first column block advance incrementally (no per-stage divisions)
+        int tw_i = kb % p.tiles_w, th_i = (kb / p.tiles_w) % p.tiles_h, n_i = kb / (p.tiles_w * p.tiles_h);
+        const int t0 = gb0 / p.ncb, cb0 = gb0 - t0 * p.ncb;
+        if (elect_one())                 // one thread runs the whole role (conv_tc3.cu: no per-stage ELECT / reconvergence)
         for (int i = 0; i < nk; ++i) {
-            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-            mbar_wait(empty_bar(s), (it & 1) ^ 1);
-            if (elect_one()) {
-                int tile = kb + i;
-                const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
-                const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
-                const int n0 = tile * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+            mbar_wait(empty_bar(s), ph);
+            {
+                const int n0 = n_i * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
                 uint32_t dst = smem_base + s * Cfg::STAGE;
                 mbar_expect_tx(full_bar(s), stage_tx);
                 tma_load_4d(dst, &mapM, full_bar(s), cm0, w0 + p.mw, h0 + p.mh, n0);
                 tma_load_4d(dst + Cfg::BOX, &mapM, full_bar(s), cm0 + 64, w0 + p.mw, h0 + p.mh, n0);
                 dst += 2 * Cfg::BOX;
-                int t = gb0 / p.ncb, cb = gb0 - t * p.ncb;
+                int t = t0, cb = cb0;
                 for (int b = 0; b < nb; ++b, dst += Cfg::BOX) {
                     tma_load_4d(dst, &mapA, full_bar(s), cb << 6, w0 + p.aw + p.ds[t], h0 + p.ah + p.dr[t], n0);
                     if (++cb == p.ncb) { cb = 0; ++t; }
                 }
             }
-            __syncwarp();
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++n_i; } }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: both operands MN-major (instruction-descriptor bits 15 / 16); up to two MMAs of N <= 256 per K step
@@ -120,11 +123,13 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap mapM, const __grid_constant
         const uint32_t ibase = (1u << 4) | (fm << 7) | (fa << 10) | ((uint32_t)(128 >> 4) << 24) | (1u << 15) | (1u << 16);
         const uint32_t idesc_lo = ibase | ((uint32_t)(n_lo >> 3) << 17), idesc_hi = ibase | ((uint32_t)(n_hi >> 3) << 17);
         const uint64_t desc0 = wg2_sdesc_mn(Cfg::BOX);
+        int s = 0;
+        uint32_t ph = 0u;
+        if (elect_one())
         for (int i = 0; i < nk; ++i) {
-            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-            mbar_wait(full_bar(s), it & 1);
+            mbar_wait(full_bar(s), ph);
             tc_fence_after();
-            if (elect_one()) {
+            {
                 const uint32_t st = smem_base + s * Cfg::STAGE;
                 const uint64_t md = desc0 + (uint64_t)((st & 0x3FFFF) >> 4);
                 const uint64_t ad = md + (uint64_t)((2 * Cfg::BOX) >> 4);
@@ -136,7 +141,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap mapM, const __grid_constant
                 tc_commit(empty_bar(s));
                 if (i == nk - 1) tc_commit(tmem_full_bar);
             }
-            __syncwarp();
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
     } else {
         // ===== epilogue: TMEM lane = row of dWp, 32 columns per load, 128 contiguous bytes per thread and chunk =====
