@@ -633,6 +633,136 @@ tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int
     }
 }
 
+// The same preparation for the shapes the step is made of (no concatenation, C % 8 == 0, Ca / 8 a power of two <= 256): a
+// thread keeps ONE group of 8 arranged channels for the whole launch, so everything that depends on the channel group -
+// the layout's pixel offset, the source channel, the (mean, scale, shift) constants of the fused norm-apply, the bias-gradient
+// partial sums - lives in registers, the arranged pixel advances by a constant step (no index divisions) and two items are
+// in flight per thread.  Bit-identical to tc_prep_kernel (tests); DSR_PREP_FAST=0 keeps the general kernel for A/B.
+template <bool PRM, bool CSUM>
+__global__ void __launch_bounds__(256, (PRM ? 3 : 4))
+tc_prep_fast_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act, float slope,
+                    int pad, int mode, int layout, int Cp, unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo,
+                    unsigned short* __restrict__ Abf, int Ha, int Wa, int Ca, int f16, double* __restrict__ csum, int csum_reps,
+                    unsigned magic_ha, const NormFin fin) {
+    extern __shared__ __align__(16) float prep_sm[];
+    const int Cs = (C + 3) & ~3;
+    float* s_prm = prep_sm;
+    float* s_sum = prep_sm + (PRM ? 3 * Cs : 0);
+    const int tid = threadIdx.x;
+    const int cg = Ca >> 3, step = 256 / cg;             // 256 % cg == 0 (host)
+    const int q = (tid & (cg - 1)) << 3, wa0 = tid / cg;
+    // layout: arranged pixel (ha, wa), channel group q  ->  padded-space pixel (ha * mh + gh, wa * mw + gw), source channel c
+    int c = q, mh = 1, mw = 1, gh = 0, gw = 0;
+    if (layout != DSR_TC_LAYOUT_NORMAL) {
+        const int g = q / Cp;
+        c = q - g * Cp;
+        if (layout == DSR_TC_LAYOUT_PAIR) gw = g;
+        else { mh = 2; mw = 2; gh = g >> 1; gw = g & 1; }
+    }
+    const bool chan_ok = c < C;                           // (c + 8 <= C then: C % 8 == 0)
+    const int Hq = H + 2 * pad, Wq = W + 2 * pad;
+    const long NC = (long)N * C;
+    if (CSUM) {
+        for (int i = tid; i < C; i += 256) s_sum[i] = 0.f;
+        __syncthreads();
+    }
+    float racc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float4 m0, m1, sc0, sc1, sh0, sh1;
+    m0 = m1 = sc0 = sc1 = sh0 = sh1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cached_n = -1;
+    for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
+        const int n = magic_ha ? (int)__umulhi((unsigned)row, magic_ha) : row, ha = row - n * Ha;
+        if (PRM && n != cached_n) {
+            __syncthreads();
+            if (fin.sums) {
+                for (int i = tid; i < C; i += 256) {
+                    float m, sc, sh;
+                    norm_fin_one(fin.sums, fin.P, fin.groups, fin.gamma, fin.beta, fin.eps, n, i, C, m, sc, sh);
+                    s_prm[i] = m; s_prm[Cs + i] = sc; s_prm[2 * Cs + i] = sh;
+                    if (ha == 0 && fin.prm_out) {
+                        fin.prm_out[(long)n * C + i] = m; fin.prm_out[NC + (long)n * C + i] = sc; fin.prm_out[2 * NC + (long)n * C + i] = sh;
+                    }
+                }
+            } else {
+                for (int i = tid; i < C; i += 256) {
+                    s_prm[i] = prm[(long)n * C + i]; s_prm[Cs + i] = prm[NC + (long)n * C + i]; s_prm[2 * Cs + i] = prm[2 * NC + (long)n * C + i];
+                }
+            }
+            cached_n = n;
+            __syncthreads();
+            if (chan_ok) {
+                m0 = ld4(s_prm + c); m1 = ld4(s_prm + c + 4);
+                sc0 = ld4(s_prm + Cs + c); sc1 = ld4(s_prm + Cs + c + 4);
+                sh0 = ld4(s_prm + 2 * Cs + c); sh1 = ld4(s_prm + 2 * Cs + c + 4);
+            }
+        }
+        const int qi = ha * mh + gh;
+        const int i = (qi < Hq && chan_ok) ? prep_pad_src(qi, pad, H, mode) : -1;
+        const float* xrow = x + ((long)(n * H + (i >= 0 ? i : 0)) * W) * C + c;
+        const long obase = (long)row * Wa * Ca + q;
+        for (int wa = wa0; wa < Wa; wa += 2 * step) {
+            // two items per thread and iteration: both loads are issued before either is consumed
+            const int wb = wa + step;
+            const int qja = wa * mw + gw, qjb = wb * mw + gw;
+            const int ja = (i >= 0 && qja < Wq) ? prep_pad_src(qja, pad, W, mode) : -1;
+            const int jb = (i >= 0 && wb < Wa && qjb < Wq) ? prep_pad_src(qjb, pad, W, mode) : -1;
+            float4 a0, a1, b0, b1;
+            a0 = a1 = b0 = b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ja >= 0) { a0 = ld4(xrow + (long)ja * C); a1 = ld4(xrow + (long)ja * C + 4); }
+            if (jb >= 0) { b0 = ld4(xrow + (long)jb * C); b1 = ld4(xrow + (long)jb * C + 4); }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && wb >= Wa) break;
+                const bool valid = u == 0 ? ja >= 0 : jb >= 0;
+                const float4 p0 = u == 0 ? a0 : b0, p1 = u == 0 ? a1 : b1;
+                float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                if (valid) {
+                    if (PRM) {
+                        v[0] = (v[0] - m0.x) * sc0.x + sh0.x; v[1] = (v[1] - m0.y) * sc0.y + sh0.y;
+                        v[2] = (v[2] - m0.z) * sc0.z + sh0.z; v[3] = (v[3] - m0.w) * sc0.w + sh0.w;
+                        v[4] = (v[4] - m1.x) * sc1.x + sh1.x; v[5] = (v[5] - m1.y) * sc1.y + sh1.y;
+                        v[6] = (v[6] - m1.z) * sc1.z + sh1.z; v[7] = (v[7] - m1.w) * sc1.w + sh1.w;
+                    }
+                    if (act == DSR_ACT_RELU) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                    } else if (act == DSR_ACT_LRELU) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : slope * v[e];
+                    }
+                    if (CSUM) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) racc[e] += v[e];
+                    }
+                }
+                uint4 hi, lo;
+                split16x2(v[0], v[1], f16, hi.x, lo.x); split16x2(v[2], v[3], f16, hi.y, lo.y);
+                split16x2(v[4], v[5], f16, hi.z, lo.z); split16x2(v[6], v[7], f16, hi.w, lo.w);
+                const long o = obase + (long)(u == 0 ? wa : wb) * Ca;
+                *reinterpret_cast<uint4*>(Ahi + o) = hi;
+                if (Alo) *reinterpret_cast<uint4*>(Alo + o) = lo;
+                if (Abf) {
+                    uint4 b;
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                    b.x = *reinterpret_cast<unsigned*>(&t0); b.y = *reinterpret_cast<unsigned*>(&t1);
+                    b.z = *reinterpret_cast<unsigned*>(&t2); b.w = *reinterpret_cast<unsigned*>(&t3);
+                    *reinterpret_cast<uint4*>(Abf + o) = b;
+                }
+            }
+        }
+    }
+    if (CSUM) {
+        if (chan_ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_sum[c + e], racc[e]);
+        }
+        __syncthreads();
+        double* dst = csum + (long)(blockIdx.x % csum_reps) * C;
+        for (int i = tid; i < C; i += 256) atomicAdd(&dst[i], (double)s_sum[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing: 4-D fp32 parameter -> bf16 hi (+lo) [Cout][T*Ca], K-major
 //   variant CONV     : Conv2d weight (Cout, Cin, R, S); tap t = r*S + s, channel c          (stride 1)
@@ -875,6 +1005,20 @@ static int tc_prep_launch(const float* x, int N, int H, int W, int C, const floa
     cat.n = 0;
     for (int k = 0; k < 4; ++k) { cat.p[k] = nullptr; cat.c[k] = 0; }
     DSR_REQUIRE(!((uintptr_t)A_bf & 15), "operand buffers must be 16-byte aligned");
+    {
+        const int cg = Ca >> 3;
+        const char* e = getenv("DSR_PREP_FAST");
+        if ((!e || atoi(e) != 0) && (C & 7) == 0 && cg >= 1 && cg <= 256 && (cg & (cg - 1)) == 0 && !((uintptr_t)x & 15) &&
+            (layout == DSR_TC_LAYOUT_NORMAL || Cp <= Ca)) {
+            const bool has_prm = prm || fin.sums;
+#define PREP_FAST(P, S) tc_prep_fast_kernel<P, S><<<grid, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp, \
+                (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, csum, csum ? csum_reps : 1, magic((unsigned)Ha), fin)
+            if (has_prm) { if (csum) PREP_FAST(true, true); else PREP_FAST(true, false); }
+            else { if (csum) PREP_FAST(false, true); else PREP_FAST(false, false); }
+#undef PREP_FAST
+            return dsr_check_launch("tc_prep (fast)");
+        }
+    }
     tc_prep_kernel<<<grid, 256, smem, ST(stream)>>>(x, cat, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp,
                                                     (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, csum, csum ? csum_reps : 1,
                                                     magic((unsigned)(Ca >> 3)), magic((unsigned)Cp), magic((unsigned)Ha), fin);

@@ -673,6 +673,56 @@ def test_folded_norm_finalize_kernels_bit_identical(ops, groups, C, HW, layout_p
     assert torch.allclose(out[0][4].permute(0, 3, 1, 2), ref, atol=5e-5)
 
 
+@pytest.mark.parametrize("layout,C,Ca,HW,pad,mode", [(0, 128, 128, (20, 33), 1, 1), (0, 32, 64, (17, 40), 3, 1), (0, 64, 64, (9, 7), 2, 0),
+                                                     (2, 64, 256, (24, 18), 1, 0), (2, 32, 128, (13, 11), 1, 2), (1, 32, 64, (12, 30), 3, 1),
+                                                     (0, 256, 256, (6, 5), 0, 0), (0, 512, 512, (4, 4), 1, 2), (0, 16, 64, (8, 300), 1, 0)])
+@pytest.mark.parametrize("variant", ["plain", "prm_relu", "fin_lrelu_bf", "csum_nolo", "bf16"])
+def test_prep_fast_kernel_is_bit_identical(ops, layout, C, Ca, HW, pad, mode, variant):
+    """tc_prep_fast_kernel (one channel group per thread, constants in registers, two items in flight) against the general
+    tc_prep_kernel (DSR_PREP_FAST=0) over the layouts / paddings / fused prologues the step uses: every output plane, the
+    constants written for the backward pass and the bias-gradient sums must be EQUAL.  The operand of every nn.Conv2d /
+    nn.ConvTranspose2d, networks.py:379-415, :544-616."""
+    import os
+    H, W = HW
+    N = 3
+    csum_wanted = variant == "csum_nolo"
+    if csum_wanted and (layout == 1 or (pad and mode != 0)):
+        pytest.skip("bias-gradient sums need every source element written exactly once")
+    xh = (torch.randn(N, H, W, C, generator=G(71)) * 1.7 + 0.2).cuda()
+    plan = dict(layout=layout, Cp=Ca // 4 if layout == 2 else (Ca // 2 if layout == 1 else C), Ca=Ca)
+    sums = torch.zeros(N * C * 2, dtype=torch.float64, device="cuda")
+    ops._call("dsr_channel_sums", ops._p(xh), N, H * W, C, ops._p(sums, torch.float64))
+    out = []
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(passes=3, dtype="f16", fold_finalize=True, csum_reps=1)
+        for fast in ("1", "0"):
+            os.environ["DSR_PREP_FAST"] = fast
+            prm, act, slope, kw = None, ops.ACT_NONE, 0.0, {}
+            if variant == "prm_relu":
+                prm, act = ops._norm_params(xh, 0, None, None, 1e-5, sums, lazy=False), ops.ACT_RELU
+            elif variant == "fin_lrelu_bf":
+                prm, act, slope, kw = ops._norm_params(xh, 0, None, None, 1e-5, sums, lazy=True), ops.ACT_LRELU, 0.2, dict(also_bf16=True)
+            elif variant == "csum_nolo":
+                kw = dict(csum=torch.zeros(C, dtype=torch.float64, device="cuda"), need_lo=False, dtype="bf16")
+            elif variant == "bf16":
+                kw = dict(dtype="bf16")
+            r = ops._tc_prep(xh, plan, pad, mode, prm, act, slope, **kw)
+            torch.cuda.synchronize()
+            planes = [t.view(torch.int16).cpu() for t in r if torch.is_tensor(t)]
+            extra = [prm.cpu()] if prm is not None else []
+            out.append((planes, extra, kw.get("csum")))
+        assert len(out[0][0]) == len(out[1][0]) >= 1
+        for a, b in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
+            assert torch.equal(a, b)
+        if csum_wanted:
+            assert torch.allclose(out[0][2].cpu(), out[1][2].cpu(), rtol=1e-5, atol=1e-4)     # block partials: fp32 shared-memory atomics
+            assert torch.allclose(out[0][2].cpu(), xh.double().sum(dim=(0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
+    finally:
+        os.environ.pop("DSR_PREP_FAST", None)
+        ops.CONFIG.update(old)
+
+
 def test_folded_norm_finalize_through_the_layers(ops):
     """the same comparison through the layer stack (prologue route and stand-alone InstanceNorm), forward and backward; the
     statistics come from fp64 atomics in the GEMM epilogues here (run-to-run differences in the last bits, amplified by the
