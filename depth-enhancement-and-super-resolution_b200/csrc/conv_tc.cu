@@ -106,12 +106,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 
     if (warp == 0) {
         // ===== TMA producer (whole warp loops and waits, one elected lane issues) =====
+        // one elected thread runs the whole role; ring slot / parity / (tap, channel block) advance incrementally (conv_tc3.cu)
+        int s = 0, t = kb / cblocks, cb = kb - t * cblocks;
+        uint32_t ph = 1u;
+        if (elect_one())
         for (int i = 0; i < nk; ++i) {
-            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-            mbar_wait(empty_bar(s), (it & 1) ^ 1);
-            if (elect_one()) {
-                const int k = kb + i;
-                const int t = k / cblocks, cb = k - t * cblocks;
+            mbar_wait(empty_bar(s), ph);
+            {
                 const int ca = cb << 6;
                 const int hc = h0 + p.ah + pa + p.dr[t], wc = w0 + p.aw + pb + p.ds[t];
                 const uint32_t st = smem_base + s * Cfg::STAGE;
@@ -122,16 +123,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 tma_load_2d(st + Cfg::NA * Cfg::A_TILE, &mapW_hi, full_bar(s), kw, wrow);
                 if (NPASS >= 3) tma_load_2d(st + Cfg::NA * Cfg::A_TILE + Cfg::W_TILE, &mapW_lo, full_bar(s), kw, wrow);
             }
-            __syncwarp();
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            if (++cb == cblocks) { cb = 0; ++t; }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (whole warp loops and waits, one elected lane issues: see elect_one) =====
+        // ===== MMA issuer (one elected thread runs the loop) =====
         const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
         const uint64_t desc0 = make_sdesc(0);
+        int s = 0;
+        uint32_t ph = 0u;
+        if (elect_one())
         for (int i = 0; i < nk; ++i) {
-            const int s = i % Cfg::STAGES, it = i / Cfg::STAGES;
-            mbar_wait(full_bar(s), it & 1);
-            if (elect_one()) {
+            mbar_wait(full_bar(s), ph);
+            {
                 const uint32_t st = smem_base + s * Cfg::STAGE;
                 const uint64_t a_hi = desc0 + (uint64_t)((st & 0x3FFFF) >> 4), a_lo = a_hi + (uint64_t)(Cfg::A_TILE >> 4);
                 const uint64_t w_hi = a_hi + (uint64_t)((Cfg::NA * Cfg::A_TILE) >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_TILE >> 4);
@@ -148,7 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 tc_commit(empty_bar(s));            // frees this smem stage when the MMAs above retire
                 if (i == nk - 1) tc_commit(tmem_full_bar);       // accumulator complete -> epilogue
             }
-            __syncwarp();
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
