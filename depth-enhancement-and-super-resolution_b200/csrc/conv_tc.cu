@@ -642,9 +642,13 @@ tc_prep_kernel(const float* __restrict__ x, const PrepCat cat, int N, int H, int
 // the layout's pixel offset, the source channel, the (mean, scale, shift) constants of the fused norm-apply, the bias-gradient
 // partial sums - lives in registers, the arranged pixel advances by a constant step (no index divisions) and two items are
 // in flight per thread.  Bit-identical to tc_prep_kernel (tests); DSR_PREP_FAST=0 keeps the general kernel for A/B.
-template <bool PRM, bool CSUM>
+// YOUT: the pass also IS the normalisation layer of a residual block - y = act(norm(x)) + res leaves as fp32 (written once per
+// source pixel, from its un-padded position) next to the arranged operand of the next convolution, which is made from y
+// (dsr_tc_prep_norm_res: one pass instead of dsr_norm_apply_fwd followed by dsr_tc_prep of its output).
+template <bool PRM, bool CSUM, bool YOUT>
 __global__ void __launch_bounds__(256, (PRM ? 3 : 4))
-tc_prep_fast_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act, float slope,
+tc_prep_fast_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y_out,
+                    int N, int H, int W, int C, const float* __restrict__ prm, int act, float slope,
                     int pad, int mode, int layout, int Cp, unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo,
                     unsigned short* __restrict__ Abf, int Ha, int Wa, int Ca, int f16, double* __restrict__ csum, int csum_reps,
                     unsigned magic_ha, const NormFin fin) {
@@ -710,10 +714,15 @@ tc_prep_fast_kernel(const float* __restrict__ x, int N, int H, int W, int C, con
             const int qja = wa * mw + gw, qjb = wb * mw + gw;
             const int ja = (i >= 0 && qja < Wq) ? prep_pad_src(qja, pad, W, mode) : -1;
             const int jb = (i >= 0 && wb < Wa && qjb < Wq) ? prep_pad_src(qjb, pad, W, mode) : -1;
-            float4 a0, a1, b0, b1;
-            a0 = a1 = b0 = b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a0, a1, b0, b1, ra0, ra1, rb0, rb1;
+            a0 = a1 = b0 = b1 = ra0 = ra1 = rb0 = rb1 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ja >= 0) { a0 = ld4(xrow + (long)ja * C); a1 = ld4(xrow + (long)ja * C + 4); }
             if (jb >= 0) { b0 = ld4(xrow + (long)jb * C); b1 = ld4(xrow + (long)jb * C + 4); }
+            if (YOUT && res) {
+                const float* rrow = res + (xrow - x);
+                if (ja >= 0) { ra0 = ld4(rrow + (long)ja * C); ra1 = ld4(rrow + (long)ja * C + 4); }
+                if (jb >= 0) { rb0 = ld4(rrow + (long)jb * C); rb1 = ld4(rrow + (long)jb * C + 4); }
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (u == 1 && wb >= Wa) break;
@@ -737,6 +746,15 @@ tc_prep_fast_kernel(const float* __restrict__ x, int N, int H, int W, int C, con
                     if (CSUM) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) racc[e] += v[e];
+                    }
+                    if (YOUT) {
+                        const float4 r0 = u == 0 ? ra0 : rb0, r1 = u == 0 ? ra1 : rb1;
+                        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                        const int jj = u == 0 ? ja : jb, qj = u == 0 ? qja : qjb;
+                        if (qi - pad == i && qj - pad == jj) {               // the pixel's own (un-padded) position writes y
+                            float* yp = y_out + (xrow - x) + (long)jj * C;
+                            st4(yp, make_float4(v[0], v[1], v[2], v[3])); st4(yp + 4, make_float4(v[4], v[5], v[6], v[7]));
+                        }
                     }
                 }
                 uint4 hi, lo;
@@ -1015,7 +1033,7 @@ static int tc_prep_launch(const float* x, int N, int H, int W, int C, const floa
         if ((!e || atoi(e) != 0) && (C & 7) == 0 && cg >= 1 && cg <= 256 && (cg & (cg - 1)) == 0 && !((uintptr_t)x & 15) &&
             (layout == DSR_TC_LAYOUT_NORMAL || Cp <= Ca)) {
             const bool has_prm = prm || fin.sums;
-#define PREP_FAST(P, S) tc_prep_fast_kernel<P, S><<<grid, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp, \
+#define PREP_FAST(P, S) tc_prep_fast_kernel<P, S, false><<<grid, 256, smem, ST(stream)>>>(x, nullptr, nullptr, N, H, W, C, prm, act, slope, pad, pad_mode, layout, Cp, \
                 (unsigned short*)A_hi, (unsigned short*)A_lo, (unsigned short*)A_bf, Ha, Wa, Ca, f16, csum, csum ? csum_reps : 1, magic((unsigned)Ha), fin)
             if (has_prm) { if (csum) PREP_FAST(true, true); else PREP_FAST(true, false); }
             else { if (csum) PREP_FAST(false, true); else PREP_FAST(false, false); }
@@ -1049,6 +1067,45 @@ extern "C" int dsr_tc_prep_fin(const float* x, int N, int H, int W, int C, const
     fin.sums = sums; fin.gamma = gamma; fin.beta = beta; fin.prm_out = prm_out; fin.P = (long)H * W; fin.groups = groups; fin.eps = eps;
     return tc_prep_launch(x, N, H, W, C, nullptr, fin, act, slope, pad, pad_mode, layout, Cp, A_hi, A_lo, A_bf, Ha, Wa, Ca, f16, csum,
                           csum_reps, stream);
+}
+
+// Normalisation layer of a residual block + operand of the NEXT convolution in one pass:
+//   y = act(norm(x)) + res  (fp32 NHWC, what dsr_norm_apply_fwd_fin writes; res optional)   and   A = arranged 16-bit planes of y
+// (what dsr_tc_prep makes of y afterwards).  Statistics are finalised in the same launch (prm_out as dsr_norm_finalize).
+// Covers the shapes of the fast kernel only (C % 8 == 0, Ca / 8 a power of two <= 256, NORMAL or S2D layout); anything else
+// returns DSR_ERR_UNSUPPORTED and the caller runs the two passes.  models/networks.py:478-480 (ResnetBlock: out = x + conv_block(x)).
+extern "C" int dsr_tc_prep_norm_res(const float* x, int N, int H, int W, int C, const double* sums, int groups, const float* gamma,
+                                    const float* beta, float eps, float* prm_out, int act, const float* res, float* y_out, int pad,
+                                    int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca,
+                                    int f16, void* stream) {
+    DSR_REQUIRE(x && sums && y_out && A_hi && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
+    DSR_REQUIRE(groups >= 0 && (groups == 0 || C % groups == 0), "C must be a multiple of groups");
+    DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
+    DSR_REQUIRE(pad_mode != DSR_PAD_REFLECT || (pad < H && pad < W), "reflect padding needs pad < size");
+    DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
+    DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15) && !((uintptr_t)A_bf & 15), "operand buffers must be 16-byte aligned");
+    DSR_REQUIRE((long)N * (H + 2 * pad) * (W + 2 * pad) < (1L << 31) && C <= 8192, "tensor too large for 32-bit pixel indices");
+    const int cg = Ca >> 3;
+    if ((C & 7) || cg > 256 || (cg & (cg - 1)) || ((uintptr_t)x & 15) || ((uintptr_t)res & 15) || ((uintptr_t)y_out & 15)) {
+        dsr_set_error("dsr_tc_prep_norm_res: shape not covered by the fused pass");
+        return DSR_ERR_UNSUPPORTED;
+    }
+    // every source pixel must own an arranged position: the arranged grid has to cover the whole padded image
+    DSR_REQUIRE(layout == DSR_TC_LAYOUT_NORMAL ? (Ha >= H + 2 * pad && Wa >= W + 2 * pad) : (2 * Ha >= H + 2 * pad && 2 * Wa >= W + 2 * pad),
+                "arranged grid smaller than the padded image");
+    NormFin fin;
+    fin.sums = sums; fin.gamma = gamma; fin.beta = beta; fin.prm_out = prm_out; fin.P = (long)H * W; fin.groups = groups; fin.eps = eps;
+    const long rows = (long)N * Ha;
+    const long cap = (long)dsr_num_sms() * 8;
+    const long per = (rows + cap - 1) / cap;
+    const int grid = (int)((rows + per - 1) / per);
+    const size_t Cs = ((size_t)C + 3) & ~(size_t)3;
+    DSR_REQUIRE((unsigned long long)rows * Ha < (1ull << 32), "tensor too large for the magic-number index divisions");
+    auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / d + 1); };
+    tc_prep_fast_kernel<true, false, true><<<grid, 256, 3 * Cs * sizeof(float), ST(stream)>>>(
+        x, res, y_out, N, H, W, C, nullptr, act, 0.f, pad, pad_mode, layout, Cp, (unsigned short*)A_hi, (unsigned short*)A_lo,
+        (unsigned short*)A_bf, Ha, Wa, Ca, f16, nullptr, 1, magic((unsigned)Ha), fin);
+    return dsr_check_launch("tc_prep_norm_res");
 }
 
 // the same preparation over torch.cat((x0, x1, x2, x3), dim=1) without materialising the concatenation

@@ -370,7 +370,7 @@ norm_apply_fwd_vec4_kernel(const float4* __restrict__ x, const float* __restrict
 }
 // the same pass with dsr_norm_finalize folded in: each block derives its sample's constants from the raw sums into shared
 // memory (norm_fin_one: the finalize kernel's own arithmetic), block x = 0 of every sample writes them out for the backward pass
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 4)
 norm_apply_fwd_fin_vec4_kernel(const float4* __restrict__ x, const NormFin fin, const float4* __restrict__ res,
                                float4* __restrict__ y, int N, int P, int C4, int act) {
     extern __shared__ __align__(16) float s_fin[];          // [3][C]

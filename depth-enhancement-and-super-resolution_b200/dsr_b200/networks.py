@@ -74,15 +74,15 @@ class ReplicationPad2d(nn.ReplicationPad2d):
 
 
 class InstanceNorm2d(nn.InstanceNorm2d):          # networks.py:30 (affine=False, no running stats)
-    def forward(self, x, act=ops.ACT_NONE, residual=None, stats=None):
+    def forward(self, x, act=ops.ACT_NONE, residual=None, stats=None, hint=None):
         if self.affine or self.track_running_stats:
             raise NotImplementedError("dsr_b200.InstanceNorm2d: only affine=False, track_running_stats=False")
-        return ops.instance_norm(x, self.eps, act, residual, stats)
+        return ops.instance_norm(x, self.eps, act, residual, stats, hint)
 
 
 class GroupNorm(nn.GroupNorm):                    # translation_network.py:46
-    def forward(self, x, act=ops.ACT_NONE, residual=None, stats=None):
-        return ops.group_norm(x, self.num_groups, self.weight, self.bias, self.eps, act, residual, stats)
+    def forward(self, x, act=ops.ACT_NONE, residual=None, stats=None, hint=None):
+        return ops.group_norm(x, self.num_groups, self.weight, self.bias, self.eps, act, residual, stats, hint)
 
 
 class ReLU(nn.ReLU):
@@ -106,6 +106,30 @@ def _conv_like(m):
         return m
     inner = getattr(m, "transposeconv", None)
     return inner if isinstance(inner, ConvTranspose2d) else None
+
+
+def next_operand_hint(mods, i, x):
+    """ops.operand_hint of the convolution that will read the activation `x` when `mods[i:]` run next (a residual block's first
+    conv, or the pad + conv / transposed conv that follows the block stack); None when there is no such plain consumer."""
+    pads = (ReflectionPad2d, ReplicationPad2d)
+    if i >= len(mods):
+        return None
+    m = mods[i]
+    inner = getattr(m, "conv_block", None)
+    if inner is not None:                                  # a residual block: its own first layers
+        return next_operand_hint(list(inner), 0, x)
+    pad_mod = None
+    if isinstance(m, pads) and i + 1 < len(mods) and isinstance(mods[i + 1], Conv2d) and mods[i + 1].padding[0] == 0:
+        pad_mod, m = m, mods[i + 1]
+    conv = _conv_like(m)
+    if conv is None or conv.dilation != (1, 1) or conv.groups != 1:
+        return None
+    if isinstance(conv, Conv2d):
+        p, mode = conv.padding[0], conv.padding_mode
+        if pad_mod is not None:
+            p, mode = pad_mod.padding[0], "reflect" if isinstance(pad_mod, ReflectionPad2d) else "replicate"
+        return ops.operand_hint("conv", x.shape, conv.weight, conv.stride[0], p, mode)
+    return ops.operand_hint("convT", x.shape, conv.weight, conv.stride[0], conv.padding[0], opad=conv.output_padding[0])
 
 
 def run_fused(mods, x, tail_stats=False):
@@ -163,12 +187,16 @@ def run_fused(mods, x, tail_stats=False):
             continue
         m = mods[i]
         if isinstance(m, norms):
+            # (a stand-alone norm in front of a residual block: the same pass also writes the block's first operand)
             if i + 1 < n and isinstance(mods[i + 1], ReLU):
-                x = m(x, act=ops.ACT_RELU, stats=stats)
+                x = m(x, act=ops.ACT_RELU, stats=stats, hint=next_operand_hint(mods, i + 2, x) if stats is not None else None)
                 i += 2
             else:
-                x = m(x, stats=stats)
+                x = m(x, stats=stats, hint=next_operand_hint(mods, i + 1, x) if stats is not None else None)
                 i += 1
+        elif hasattr(m, "conv_block") and hasattr(m, "forward_hinted"):
+            x = m.forward_hinted(x, next_operand_hint(mods, i + 1, x))      # residual block: its closing norm feeds mods[i + 1]
+            i += 1
         else:
             x = m(x)
             i += 1
@@ -346,10 +374,15 @@ class ResnetBlock(nn.Module):                     # networks.py:424-481
         return FusedSequential(*conv_block)
 
     def forward(self, x):
+        return self.forward_hinted(x, None)
+
+    def forward_hinted(self, x, hint):
+        """hint = ops.operand_hint of the layer that reads this block's output: the closing norm + skip add then also writes
+        that layer's arranged operand (one pass instead of two)"""
         mods = list(self.conv_block)
         if isinstance(mods[-1], (InstanceNorm2d, GroupNorm)):      # skip add fused into the norm pass
             y, stats = run_fused(mods[:-1], x, tail_stats=True)
-            return mods[-1](y, residual=x, stats=stats)            # networks.py:480
+            return mods[-1](y, residual=x, stats=stats, hint=hint)  # networks.py:480
         return x + self.conv_block(x)
 
 

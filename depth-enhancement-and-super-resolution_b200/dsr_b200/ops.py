@@ -125,6 +125,7 @@ _ZERO_POOL = _ZeroPool()
 def zero_pool_reset(device):
     """call once at the top of a step: re-zeroes what the previous step handed out"""
     _ZERO_POOL.reset(torch.device(device))
+    _PREMADE.clear()
 
 
 def zero_pool_select(name="step"):
@@ -302,6 +303,7 @@ CONFIG = {
     "wgrad_kernel": 2,   # 2 = csrc/wgrad_tc2.cu (8 column blocks per CTA, single pass); 1 = first-generation kernel (conv_tc.cu)
     "csum_reps": 8,      # replica rows of the bias-gradient sums dsr_tc_prep takes on the way (fp64 atomics spread over 8 addresses
                          # per channel, which lets the launch keep the wide grid of the sum-free form); 1 = one row, narrow grid
+    "fuse_norm_prep": True,  # the closing norm (+ skip add) of a residual block also writes the next conv's operand (dsr_tc_prep_norm_res)
     "fold_finalize": True,   # dsr_norm_finalize folded into its first consumer (dsr_tc_prep_fin / dsr_norm_apply_fwd_fin)
     "wgrad_slabs": False,  # True: weight-gradient K splits store their own slabs (dsr_tc_wgrad2p) and the unpack sums them in a
                            # fixed order: bit-reproducible weight gradients, no atomics.  Measured on B200 (r2z): +0.35 ms per step
@@ -495,6 +497,65 @@ def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None, npass=None):
     return whi, wlo
 
 
+# Operands made by the PRODUCER of an activation (the fused norm + skip-add + preparation pass at the end of a residual
+# block): data_ptr -> (the fp32 tensor itself - held so that its address cannot be handed to another tensor while the entry
+# lives -, cache key, (ahi, alo, Ha, Wa), bf16 plane or None).  Claimed once by the _Prepared of the consumer, dropped at the
+# top of every step.
+_PREMADE = {}
+
+
+def operand_hint(kind, x_shape, weight, stride, pad, pad_mode=PAD_ZERO, opad=0):
+    """What the convolution (kind 'conv' / 'convT') that will read an (N, C, H, W) activation asks of its operand
+    preparation: dict(plan, pad, mode, bf16) - or None when that layer does not take a plain NORMAL / S2D operand."""
+    if not CONFIG["fuse_norm_prep"] or CONFIG["engine"] != "tc":
+        return None
+    N, C, H, W = x_shape
+    pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
+    trains = bool(weight.requires_grad) and torch.is_grad_enabled()
+    if kind == "conv":
+        Co, Ci, R, S = weight.shape
+        if Ci != C or (Co == 1 and stride == 1 and CONFIG["out1"]):
+            return None
+        plan = tc_conv_plan("conv", Ci, Co, R, S, stride, pad, 0, H, W)
+    else:
+        Ci, Co, R, S = weight.shape
+        if Ci != C or (Co == 1 and CONFIG["out1"]):
+            return None
+        plan = tc_conv_plan("convT", Ci, Co, R, S, stride, pad, opad, H, W)
+        pad, pad_mode = 1, PAD_ZERO                       # _tc_convT_fwd: zero halo of 1
+    if plan is None or plan.get("compact") or plan["layout"] not in (_LAYOUT_NORMAL, _LAYOUT_S2D):
+        return None
+    cg = plan["Ca"] // 8
+    if C % 8 or cg > 256 or cg & (cg - 1):
+        return None
+    return dict(plan=plan, pad=pad, mode=pad_mode, bf16=_bwd_copy_wanted(trains))
+
+
+def _norm_res_prep(xh, sums, groups, gamma, beta, eps, act, rh, hint):
+    """one launch: y = act(norm(x)) + res (fp32) AND the arranged operand of the next convolution, registered in _PREMADE.
+    -> (y, prm)"""
+    N, H, W, C = xh.shape
+    plan, pad, mode = hint["plan"], hint["pad"], hint["mode"]
+    Hq, Wq = H + 2 * pad, W + 2 * pad
+    Ha, Wa = ((Hq + 1) // 2, (Wq + 1) // 2) if plan["layout"] == _LAYOUT_S2D else (Hq, Wq)
+    Ca, dt = plan["Ca"], CONFIG["dtype"]
+    prm = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)
+    y = torch.empty_like(xh)
+    ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
+    alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if CONFIG["passes"] >= 2 else None
+    abf = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if (hint["bf16"] and dt == "f16") else None
+    if _lib.PROFILE is not None:
+        _lib.PROFILE_META = dict(macs=0, shape=(N, H, W, C, Ca, plan["layout"], pad, 1, int(alo is not None)))
+    _call("dsr_tc_prep_norm_res", _p(xh), N, H, W, C, _p(sums, torch.float64), groups, _p(gamma), _p(beta), eps, _p(prm), act,
+          _p(rh), _p(y), pad, mode, plan["layout"], plan["Cp"], _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16),
+          _p(abf, torch.bfloat16), Ha, Wa, Ca, int(dt == "f16"))
+    key = (plan["layout"], plan["Cp"], plan["Ca"], pad, mode, dt, plan.get("Wa", 0))
+    if len(_PREMADE) > 64:
+        _PREMADE.clear()
+    _PREMADE[y.data_ptr()] = (y, key, (ahi, alo, Ha, Wa), abf)
+    return y, prm
+
+
 class _Prepared:
     """Arranged 16-bit copies of ONE fp32 NHWC tensor, made at most once per (layout, padding, format):
     the backward pass feeds the same dY (or x) to the data-gradient and the weight-gradient GEMMs."""
@@ -505,6 +566,13 @@ class _Prepared:
         self.prm, self.act, self.slope = prm, act, slope      # fused prologue: norm-apply + activation on the way in
         self.want_csum, self.csum = want_csum, None           # per-channel sums of xh (bias gradient), taken by the first
                                                               # prep that writes every element exactly once
+        if prm is None and act == ACT_NONE and _PREMADE:
+            pre = _PREMADE.pop(xh.data_ptr(), None)           # operand already made by the producer of xh (_norm_res_prep)
+            if pre is not None and pre[0].shape == xh.shape:
+                _, key, hit, abf = pre
+                self.made[key] = hit
+                if abf is not None:
+                    self.made[key[:5] + ("bf16",) + key[6:]] = (abf, None, hit[2], hit[3])
 
     def get(self, plan, pad, pad_mode, dtype=None, need_lo=True, also_bf16=False):
         """need_lo=False: the caller reads the high plane only (single-pass weight gradient) - skip writing the low one.
@@ -1366,13 +1434,16 @@ class _InstanceNorm(Function):
     """InstanceNorm2d(affine=False) [+ ReLU] [+ residual add].  networks.py:30, :380-381, :480."""
 
     @staticmethod
-    def forward(ctx, x, eps, act, residual, stats):
+    def forward(ctx, x, eps, act, residual, stats, hint=None):
         xh = nhwc(x)
         N, H, W, C = xh.shape
-        prm = _norm_params(xh, 0, None, None, eps, stats, lazy=True)
         rh = nhwc(residual) if residual is not None else None
-        y = torch.empty_like(xh)
-        _norm_apply_fwd(xh, prm, rh, y, act)
+        if hint is not None and stats is not None and stats.numel() == N * C * 2 and act in (ACT_NONE, ACT_RELU):
+            y, prm = _norm_res_prep(xh, stats, 0, None, None, eps, act, rh, hint)
+        else:
+            prm = _norm_params(xh, 0, None, None, eps, stats, lazy=True)
+            y = torch.empty_like(xh)
+            _norm_apply_fwd(xh, prm, rh, y, act)
         ctx.act = act
         ctx.has_res = residual is not None
         ctx.save_for_backward(xh, prm)
@@ -1391,11 +1462,12 @@ class _InstanceNorm(Function):
             _call("dsr_in_bwd_apply", _p(xh), _p(g), _p(prm), _p(sums2, torch.float64), _p(gxh), N, H * W, C, ctx.act)
             gx = nchw(gxh)
         gres = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        return gx, None, None, gres, None
+        return gx, None, None, gres, None, None
 
 
-def instance_norm(x, eps=1e-5, act=ACT_NONE, residual=None, stats=None):
-    return _InstanceNorm.apply(x, eps, act, residual, stats)
+def instance_norm(x, eps=1e-5, act=ACT_NONE, residual=None, stats=None, hint=None):
+    """hint (ops.operand_hint of the convolution that reads the result): the same launch also writes that operand"""
+    return _InstanceNorm.apply(x, eps, act, residual, stats, hint)
 
 
 def _param_grad(vals, param):
@@ -1413,17 +1485,20 @@ class _GroupNorm(Function):
     translation block train through it.  translation_network.py:46, :472-483, :563-574."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, groups, eps, act, residual, stats):
+    def forward(ctx, x, weight, bias, groups, eps, act, residual, stats, hint=None):
         xh = nhwc(x)
         N, H, W, C = xh.shape
         w, b = weight.detach().contiguous(), bias.detach().contiguous()
         if stats is None:
             stats = _zeros_f64(N * C * 2, xh.device)
             _call("dsr_channel_sums", _p(xh), N, H * W, C, _p(stats, torch.float64))
-        prm = _norm_params(xh, groups, w, b, eps, stats, lazy=True)
         rh = nhwc(residual) if residual is not None else None
-        y = torch.empty_like(xh)
-        _norm_apply_fwd(xh, prm, rh, y, act)
+        if hint is not None and stats.numel() == N * C * 2 and act in (ACT_NONE, ACT_RELU):
+            y, _ = _norm_res_prep(xh, stats, groups, w, b, eps, act, rh, hint)
+        else:
+            prm = _norm_params(xh, groups, w, b, eps, stats, lazy=True)
+            y = torch.empty_like(xh)
+            _norm_apply_fwd(xh, prm, rh, y, act)
         if any(ctx.needs_input_grad):
             hat = torch.empty(3 * N * C, device=xh.device, dtype=torch.float32)         # (mean, rstd, 0): gamma = beta = NULL
             _call("dsr_norm_finalize", _p(stats, torch.float64), N, C, H * W, groups, None, None, eps, _p(hat))
@@ -1452,12 +1527,12 @@ class _GroupNorm(Function):
         gw = _param_grad(dgamma, weight) if ctx.needs_input_grad[1] else None
         gb = _param_grad(dbeta, bias) if ctx.needs_input_grad[2] else None
         gres = gy if (has_res and ctx.needs_input_grad[6]) else None
-        return gx, gw, gb, None, None, None, gres, None
+        return gx, gw, gb, None, None, None, gres, None, None
 
 
-def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None, stats=None):
+def group_norm(x, groups, weight, bias, eps=1e-5, act=ACT_NONE, residual=None, stats=None, hint=None):
     """GroupNorm(groups, C, affine=True) [+ReLU] [+residual].  translation_network.py:46."""
-    return _GroupNorm.apply(x, weight, bias, groups, eps, act, residual, stats)
+    return _GroupNorm.apply(x, weight, bias, groups, eps, act, residual, stats, hint)
 
 
 class _Act(Function):

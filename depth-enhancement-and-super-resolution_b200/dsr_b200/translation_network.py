@@ -17,7 +17,7 @@ import torch.nn as nn
 from torch.nn import init
 
 from . import ops
-from .networks import (Conv2d, ConvTranspose2d as _ConvT2d, DeviceModule, FusedSequential, GroupNorm, Identity,
+from .networks import (next_operand_hint, Conv2d, ConvTranspose2d as _ConvT2d, DeviceModule, FusedSequential, GroupNorm, Identity,
                        InstanceNorm2d, LeakyReLU, ReLU, Tanh, run_fused)
 
 
@@ -130,9 +130,12 @@ class ResnetBlock(nn.Module):                     # translation_network.py:554-5
             norm_layer(dim))
 
     def forward(self, x):
+        return self.forward_hinted(x, None)
+
+    def forward_hinted(self, x, hint):
         mods = list(self.conv_block)
         y, stats = run_fused(mods[:-1], x, tail_stats=True)
-        return mods[-1](y, residual=x, stats=stats)                # translation_network.py:574
+        return mods[-1](y, residual=x, stats=stats, hint=hint)     # translation_network.py:574
 
 
 class ResnetBottlenec(nn.Module):                 # translation_network.py:533-552
@@ -146,7 +149,10 @@ class ResnetBottlenec(nn.Module):                 # translation_network.py:533-5
 
     def forward(self, depth, img=None):
         x = ops.cat([depth, img]) if img is not None else depth     # translation_network.py:549
-        return self.model(x)
+        blocks = list(self.model)
+        for k, blk in enumerate(blocks):                             # each block's closing norm also prepares the next block's operand
+            x = blk.forward_hinted(x, next_operand_hint(blocks, k + 1, x))
+        return x
 
 
 def define_Gen(opt, input_type, out_type="depth"):                 # translation_network.py:577-585

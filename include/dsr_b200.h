@@ -275,6 +275,15 @@ int dsr_tc_prep_fin(const float* x, int N, int H, int W, int C, const double* su
                     const float* beta, float eps, float* prm_out, int act, float slope, int pad, int pad_mode, int layout,
                     int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16, double* csum, int csum_reps,
                     void* stream);
+/* The normalisation layer that closes a residual block AND the operand of the next convolution in one pass:
+ * y_out = act(norm(x)) + res (fp32 NHWC, res optional; what dsr_norm_apply_fwd_fin writes) and A = the arranged 16-bit planes
+ * of y_out (what dsr_tc_prep makes of it).  NORMAL / S2D layouts, C % 8 == 0, Ca / 8 a power of two <= 256; other shapes
+ * return DSR_ERR_UNSUPPORTED (the caller runs the two passes).  models/networks.py:478-480 (out = x + conv_block(x)),
+ * translation_network.py:46 (GroupNorm variant). */
+int dsr_tc_prep_norm_res(const float* x, int N, int H, int W, int C, const double* sums, int groups, const float* gamma,
+                         const float* beta, float eps, float* prm_out, int act, const float* res, float* y_out, int pad,
+                         int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
+                         void* stream);
 /* dsr_tc_prep over torch.cat((x0, x1, x2, x3), dim=1) (NULL / 0 = absent) without materialising the concatenation:
  * models/main_model.py:305-306 (the 261-channel Task input), models/networks.py:629 (U-Net skip connections). */
 int dsr_tc_prep_cat(const float* x0, int C0, const float* x1, int C1, const float* x2, int C2, const float* x3, int C3, int N,

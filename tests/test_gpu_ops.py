@@ -723,6 +723,51 @@ def test_prep_fast_kernel_is_bit_identical(ops, layout, C, Ca, HW, pad, mode, va
         ops.CONFIG.update(old)
 
 
+@pytest.mark.parametrize("train", [True, False])
+def test_residual_block_tail_fused_with_next_operand(ops, train):
+    """dsr_tc_prep_norm_res: the closing InstanceNorm + skip add of a residual block (networks.py:478-480) and the stand-alone
+    norm + ReLU in front of the block stack also write the NEXT convolution's arranged operand.  Same arithmetic as the two
+    separate passes: outputs and gradients must agree to rounding-order noise, with one launch less per block."""
+    from dsr_b200 import networks as nw
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
+        torch.manual_seed(21)
+        norm = nw.get_norm_layer("instance")
+        mods = [nw.Conv2d(16, 64, 3, stride=2, padding=1), norm(64), nw.ReLU(True)] + \
+               [nw.ResnetBlock(64, "reflect", norm, False, True) for _ in range(3)] + \
+               [nw.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1), norm(32), nw.ReLU(True),
+                nw.ReflectionPad2d(3), nw.Conv2d(32, 8, 7, padding=0)]
+        net = nw.FusedSequential(*mods).cuda()
+        x = torch.randn(2, 16, 48, 40, generator=G(298))
+        res = []
+        for fuse in (True, False):
+            ops.CONFIG.update(fuse_norm_prep=fuse)
+            ops.zero_pool_reset("cuda")
+            for p_ in net.parameters():
+                p_.grad = None
+            xc = cl(x).requires_grad_(train)
+            with _CallLog() as names:
+                if train:
+                    y = net(xc)
+                    (y * y).sum().backward()
+                else:
+                    with torch.no_grad():
+                        y = net(xc)
+            res.append((y.detach().cpu(), xc.grad.cpu() if train else None, [p_.grad.cpu().clone() for p_ in net.parameters()] if train else [],
+                        names.count("dsr_tc_prep_norm_res"), sum(1 for nm in names if "pack" not in nm)))
+        assert res[0][3] == 4 and res[1][3] == 0                    # stand-alone norm + three block tails
+        assert res[0][4] == res[1][4] - 4
+        assert rel_l2(res[0][0], res[1][0]) <= 1e-6
+        if train:
+            assert rel_l2(res[0][1], res[1][1]) <= 2e-4
+            for ga, gb in zip(res[0][2], res[1][2]):
+                if gb.dim() == 4:
+                    assert rel_l2(ga, gb) <= 2e-4
+    finally:
+        ops.CONFIG.update(old)
+
+
 def test_folded_norm_finalize_through_the_layers(ops):
     """the same comparison through the layer stack (prologue route and stand-alone InstanceNorm), forward and backward; the
     statistics come from fp64 atomics in the GEMM epilogues here (run-to-run differences in the last bits, amplified by the
