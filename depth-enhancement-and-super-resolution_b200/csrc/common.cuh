@@ -96,6 +96,14 @@ __device__ __forceinline__ void norm_fin_one(const double* __restrict__ sums, lo
     scale = groups == 0 ? rstd : rstd * (gamma ? gamma[c] : 1.f);
     shift = groups == 0 ? 0.f : (beta ? beta[c] : 0.f);
 }
+// One element of the InstanceNorm2d(affine=False) [+ReLU] backward: dx = rstd * (g' - mean(g') - xhat * mean(g' * xhat)), g' = g
+// gated by xhat > 0 under a fused ReLU.  Shared by dsr_in_bwd_apply (nn.cu) and the fused apply + operand preparation
+// (dsr_tc_prep_in_bwd, conv_tc.cu) so that both routes produce the same bits.
+__device__ __forceinline__ float in_bwd_one(float x, float g, float mean, float rstd, float m1, float m2, bool relu) {
+    const float xh = (x - mean) * rstd;
+    if (relu && !(xh > 0.f)) g = 0.f;
+    return rstd * (g - m1 - xh * m2);
+}
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 #endif

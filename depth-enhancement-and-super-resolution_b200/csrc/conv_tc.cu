@@ -785,6 +785,125 @@ tc_prep_fast_kernel(const float* __restrict__ x, const float* __restrict__ res, 
     }
 }
 
+// InstanceNorm2d(affine=False) [+ReLU] backward AND the operand of the NEXT backward GEMM in one pass: the gradient that
+// leaves a normalisation layer is the dY of the convolution in front of it, whose data- and weight-gradient GEMMs read it as a
+// zero-padded arranged 16-bit tensor.  One thread = one group of 8 arranged channels (the scheme of tc_prep_fast_kernel):
+//   dx = rstd * (g' - mean(g') - xhat * mean(g' * xhat))   (fp32 NHWC, what dsr_in_bwd_apply writes - same arithmetic, same bits)
+//   A  = arranged hi (+lo) planes of dx with a zero frame of `pad` pixels (what dsr_tc_prep makes of dx afterwards)
+//   csum += per-channel sums of dx (the bias gradient of that convolution), replicated rows as in dsr_tc_prep.
+// Zero padding only: every source pixel then owns exactly one arranged position, so dx and the sums are written / counted once.
+template <bool CSUM>
+__global__ void __launch_bounds__(256, 2)
+tc_prep_inbwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int N, int H, int W, int C,
+                     const float* __restrict__ prm, const double* __restrict__ sums2, int act, int pad, int layout, int Cp,
+                     unsigned short* __restrict__ Ahi, unsigned short* __restrict__ Alo, int Ha, int Wa, int Ca, int f16,
+                     double* __restrict__ csum, int csum_reps, unsigned magic_ha) {
+    extern __shared__ __align__(16) float prep_sm[];
+    const int Cs = (C + 3) & ~3;
+    float* s_c = prep_sm;                                 // [4][Cs]: mean, rstd, mean(g'), mean(g' * xhat)
+    float* s_sum = prep_sm + 4 * Cs;
+    const int tid = threadIdx.x;
+    const int cg = Ca >> 3, step = 256 / cg;
+    const int q = (tid & (cg - 1)) << 3, wa0 = tid / cg;
+    int c = q, mh = 1, mw = 1, gh = 0, gw = 0;
+    if (layout != DSR_TC_LAYOUT_NORMAL) {                 // S2D: arranged pixel (ha, wa), group g -> padded pixel (2 ha + g / 2, 2 wa + g % 2)
+        const int g = q / Cp;
+        c = q - g * Cp;
+        mh = 2; mw = 2; gh = g >> 1; gw = g & 1;
+    }
+    const bool chan_ok = c < C;
+    const bool relu = act == DSR_ACT_RELU;
+    const int Hq = H + 2 * pad, Wq = W + 2 * pad;
+    const long NC = (long)N * C;
+    const float invP = 1.f / (float)((long)H * W);
+    if (CSUM) {
+        for (int i = tid; i < C; i += 256) s_sum[i] = 0.f;
+        __syncthreads();
+    }
+    float racc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float4 mu0, mu1, rs0, rs1, a10, a11, a20, a21;
+    mu0 = mu1 = rs0 = rs1 = a10 = a11 = a20 = a21 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cached_n = -1;
+    for (int row = blockIdx.x; row < N * Ha; row += gridDim.x) {
+        const int n = magic_ha ? (int)__umulhi((unsigned)row, magic_ha) : row, ha = row - n * Ha;
+        if (n != cached_n) {
+            __syncthreads();
+            for (int i = tid; i < C; i += 256) {
+                s_c[i] = prm[(long)n * C + i];
+                s_c[Cs + i] = prm[NC + (long)n * C + i];
+                s_c[2 * Cs + i] = (float)sums2[((long)n * C + i) * 2] * invP;
+                s_c[3 * Cs + i] = (float)sums2[((long)n * C + i) * 2 + 1] * invP;
+            }
+            cached_n = n;
+            __syncthreads();
+            if (chan_ok) {
+                mu0 = ld4(s_c + c); mu1 = ld4(s_c + c + 4);
+                rs0 = ld4(s_c + Cs + c); rs1 = ld4(s_c + Cs + c + 4);
+                a10 = ld4(s_c + 2 * Cs + c); a11 = ld4(s_c + 2 * Cs + c + 4);
+                a20 = ld4(s_c + 3 * Cs + c); a21 = ld4(s_c + 3 * Cs + c + 4);
+            }
+        }
+        const int qi = ha * mh + gh;
+        const int i = (qi < Hq && chan_ok) ? prep_pad_src(qi, pad, H, DSR_PAD_ZERO) : -1;
+        const long srow = ((long)(n * H + (i >= 0 ? i : 0)) * W) * C + c;
+        const long obase = (long)row * Wa * Ca + q;
+        for (int wa = wa0; wa < Wa; wa += 2 * step) {
+            const int wb = wa + step;
+            const int qja = wa * mw + gw, qjb = wb * mw + gw;
+            const int ja = (i >= 0 && qja < Wq) ? prep_pad_src(qja, pad, W, DSR_PAD_ZERO) : -1;
+            const int jb = (i >= 0 && wb < Wa && qjb < Wq) ? prep_pad_src(qjb, pad, W, DSR_PAD_ZERO) : -1;
+            float4 ga0, ga1, gb0, gb1, xa0, xa1, xb0, xb1;
+            ga0 = ga1 = gb0 = gb1 = xa0 = xa1 = xb0 = xb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ja >= 0) {
+                const long o = srow + (long)ja * C;
+                ga0 = ld4(dy + o); ga1 = ld4(dy + o + 4); xa0 = ld4(x + o); xa1 = ld4(x + o + 4);
+            }
+            if (jb >= 0) {
+                const long o = srow + (long)jb * C;
+                gb0 = ld4(dy + o); gb1 = ld4(dy + o + 4); xb0 = ld4(x + o); xb1 = ld4(x + o + 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && wb >= Wa) break;
+                const int jj = u == 0 ? ja : jb;
+                const float4 g0 = u == 0 ? ga0 : gb0, g1 = u == 0 ? ga1 : gb1, x0 = u == 0 ? xa0 : xb0, x1 = u == 0 ? xa1 : xb1;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (jj >= 0) {
+                    v[0] = in_bwd_one(x0.x, g0.x, mu0.x, rs0.x, a10.x, a20.x, relu);
+                    v[1] = in_bwd_one(x0.y, g0.y, mu0.y, rs0.y, a10.y, a20.y, relu);
+                    v[2] = in_bwd_one(x0.z, g0.z, mu0.z, rs0.z, a10.z, a20.z, relu);
+                    v[3] = in_bwd_one(x0.w, g0.w, mu0.w, rs0.w, a10.w, a20.w, relu);
+                    v[4] = in_bwd_one(x1.x, g1.x, mu1.x, rs1.x, a11.x, a21.x, relu);
+                    v[5] = in_bwd_one(x1.y, g1.y, mu1.y, rs1.y, a11.y, a21.y, relu);
+                    v[6] = in_bwd_one(x1.z, g1.z, mu1.z, rs1.z, a11.z, a21.z, relu);
+                    v[7] = in_bwd_one(x1.w, g1.w, mu1.w, rs1.w, a11.w, a21.w, relu);
+                    float* dp = dx + srow + (long)jj * C;
+                    st4(dp, make_float4(v[0], v[1], v[2], v[3])); st4(dp + 4, make_float4(v[4], v[5], v[6], v[7]));
+                    if (CSUM) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) racc[e] += v[e];
+                    }
+                }
+                uint4 hi, lo;
+                split16x2(v[0], v[1], f16, hi.x, lo.x); split16x2(v[2], v[3], f16, hi.y, lo.y);
+                split16x2(v[4], v[5], f16, hi.z, lo.z); split16x2(v[6], v[7], f16, hi.w, lo.w);
+                const long o = obase + (long)(u == 0 ? wa : wb) * Ca;
+                *reinterpret_cast<uint4*>(Ahi + o) = hi;
+                if (Alo) *reinterpret_cast<uint4*>(Alo + o) = lo;
+            }
+        }
+    }
+    if (CSUM) {
+        if (chan_ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_sum[c + e], racc[e]);
+        }
+        __syncthreads();
+        double* dst = csum + (long)(blockIdx.x % csum_reps) * C;
+        for (int i = tid; i < C; i += 256) atomicAdd(&dst[i], (double)s_sum[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing: 4-D fp32 parameter -> bf16 hi (+lo) [Cout][T*Ca], K-major
 //   variant CONV     : Conv2d weight (Cout, Cin, R, S); tap t = r*S + s, channel c          (stride 1)
@@ -1106,6 +1225,49 @@ extern "C" int dsr_tc_prep_norm_res(const float* x, int N, int H, int W, int C, 
         x, res, y_out, N, H, W, C, nullptr, act, 0.f, pad, pad_mode, layout, Cp, (unsigned short*)A_hi, (unsigned short*)A_lo,
         (unsigned short*)A_bf, Ha, Wa, Ca, f16, nullptr, 1, magic((unsigned)Ha), fin);
     return dsr_check_launch("tc_prep_norm_res");
+}
+
+// InstanceNorm backward apply + the arranged dY operand of the convolution in front of the norm layer (see tc_prep_inbwd_kernel).
+// x / dy / dx: (N, H, W, C) fp32 NHWC; prm = (mean, rstd, .) per (n, c); sums2 from dsr_in_bwd_sums.  Shapes outside the fast
+// scheme return DSR_ERR_UNSUPPORTED (the caller runs dsr_in_bwd_apply, the consumer its own dsr_tc_prep).
+// models/networks.py:30, :380-381, :480 (the InstanceNorm2d layers), :378-379, :413-414 (the convolutions in front of them).
+extern "C" int dsr_tc_prep_in_bwd(const float* x, const float* dy, const float* prm, const double* sums2, float* dx, int N, int H,
+                                  int W, int C, int act, int pad, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca,
+                                  int f16, double* csum, int csum_reps, void* stream) {
+    DSR_REQUIRE(x && dy && prm && sums2 && dx && A_hi && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0, "bad arguments");
+    DSR_REQUIRE(act == DSR_ACT_NONE || act == DSR_ACT_RELU, "InstanceNorm backward fuses ReLU only");
+    DSR_REQUIRE(!csum || (csum_reps >= 1 && csum_reps <= 64), "csum_reps: 1..64 replicas of the channel-sum row");
+    DSR_REQUIRE((Ca & 63) == 0 && (Cp & 7) == 0 && Cp >= C, "Ca must be a multiple of 64 and Cp a multiple of 8 >= C");
+    DSR_REQUIRE((layout == DSR_TC_LAYOUT_NORMAL && Ca >= Cp) || (layout == DSR_TC_LAYOUT_S2D && Ca == 4 * Cp), "layout / channel mismatch");
+    DSR_REQUIRE(!((uintptr_t)A_hi & 15) && !((uintptr_t)A_lo & 15), "operand buffers must be 16-byte aligned");
+    DSR_REQUIRE((long)N * (H + 2 * pad) * (W + 2 * pad) < (1L << 31) && C <= 8192, "tensor too large for 32-bit pixel indices");
+    const int cg = Ca >> 3;
+    if ((C & 7) || cg > 256 || (cg & (cg - 1)) || ((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)dx & 15)) {
+        dsr_set_error("dsr_tc_prep_in_bwd: shape not covered by the fused pass");
+        return DSR_ERR_UNSUPPORTED;
+    }
+    // every source pixel must own an arranged position: dx is written from there
+    DSR_REQUIRE(layout == DSR_TC_LAYOUT_NORMAL ? (Ha >= H + 2 * pad && Wa >= W + 2 * pad) : (2 * Ha >= H + 2 * pad && 2 * Wa >= W + 2 * pad),
+                "arranged grid smaller than the padded image");
+    const long rows = (long)N * Ha;
+    const long cap = (long)dsr_num_sms() * ((csum && csum_reps < 4) ? 3 : 6);
+    const long per = (rows + cap - 1) / cap;
+    const int grid = (int)((rows + per - 1) / per);
+    const size_t Cs = ((size_t)C + 3) & ~(size_t)3;
+    const size_t smem = (4 * Cs + (csum ? (size_t)C : 0)) * sizeof(float);
+    if (smem > 48 * 1024) {
+        dsr_set_error("dsr_tc_prep_in_bwd: %d channels need more than 48 KB of per-sample constants", C);
+        return DSR_ERR_UNSUPPORTED;
+    }
+    DSR_REQUIRE((unsigned long long)rows * Ha < (1ull << 32), "tensor too large for the magic-number index divisions");
+    auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / d + 1); };
+    if (csum)
+        tc_prep_inbwd_kernel<true><<<grid, 256, smem, ST(stream)>>>(dy, x, dx, N, H, W, C, prm, sums2, act, pad, layout, Cp,
+            (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16, csum, csum_reps, magic((unsigned)Ha));
+    else
+        tc_prep_inbwd_kernel<false><<<grid, 256, smem, ST(stream)>>>(dy, x, dx, N, H, W, C, prm, sums2, act, pad, layout, Cp,
+            (unsigned short*)A_hi, (unsigned short*)A_lo, Ha, Wa, Ca, f16, nullptr, 1, magic((unsigned)Ha));
+    return dsr_check_launch("tc_prep_in_bwd");
 }
 
 // the same preparation over torch.cat((x0, x1, x2, x3), dim=1) without materialising the concatenation

@@ -450,12 +450,7 @@ in_apply_bwd_vec4_kernel(const float4* __restrict__ x, const float4* __restrict_
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float xh = (xs[k] - ms[k]) * rr[k];
-                float g = gs[k];
-                if (act == DSR_ACT_RELU && !(xh > 0.f)) g = 0.f;
-                o[k] = rr[k] * (g - m1[k] - xh * m2[k]);
-            }
+            for (int k = 0; k < 4; ++k) o[k] = in_bwd_one(xs[k], gs[k], ms[k], rr[k], m1[k], m2[k], act == DSR_ACT_RELU);
         }
         dx[base + i] = make_float4(o[0], o[1], o[2], o[3]);
     }

@@ -303,6 +303,9 @@ CONFIG = {
     "wgrad_kernel": 2,   # 2 = csrc/wgrad_tc2.cu (8 column blocks per CTA, single pass); 1 = first-generation kernel (conv_tc.cu)
     "csum_reps": 8,      # replica rows of the bias-gradient sums dsr_tc_prep takes on the way (fp64 atomics spread over 8 addresses
                          # per channel, which lets the launch keep the wide grid of the sum-free form); 1 = one row, narrow grid
+    "fuse_bwd_prep": True,   # InstanceNorm backward also writes the dY operand of the convolution in front of the norm layer
+                             # (dsr_tc_prep_in_bwd: one pass instead of dsr_in_bwd_apply + dsr_tc_prep), from the second step on:
+                             # the operand a convolution's backward asks for is recorded on its weight the first time
     "fuse_norm_prep": True,  # the closing norm (+ skip add) of a residual block also writes the next conv's operand (dsr_tc_prep_norm_res)
     "fold_finalize": True,   # dsr_norm_finalize folded into its first consumer (dsr_tc_prep_fin / dsr_norm_apply_fwd_fin)
     "wgrad_slabs": False,  # True: weight-gradient K splits store their own slabs (dsr_tc_wgrad2p) and the unpack sums them in a
@@ -499,9 +502,15 @@ def _tc_weights(weight, plan, Co, phase=(0, 0), pad=0, dtype=None, npass=None):
 
 # Operands made by the PRODUCER of an activation (the fused norm + skip-add + preparation pass at the end of a residual
 # block): data_ptr -> (the fp32 tensor itself - held so that its address cannot be handed to another tensor while the entry
-# lives -, cache key, (ahi, alo, Ha, Wa), bf16 plane or None).  Claimed once by the _Prepared of the consumer, dropped at the
-# top of every step.
+# lives -, cache key, (ahi, alo, Ha, Wa), bf16 plane or None, bias-gradient sums or None).  Claimed once by the _Prepared of the
+# consumer, dropped at the top of every step.  The backward pass uses the same table for the dY operands the fused
+# InstanceNorm backward makes (_in_bwd).
 _PREMADE = {}
+# What the backward pass of a convolution asks of its dY the first time (weight data_ptr -> dict(key = the _Prepared cache key,
+# need_lo, csum, shape)): recorded by _Prepared.get, read by _in_bwd in the NEXT backward pass (the producer of a dY runs before
+# its consumer, so the request of the previous step is the only one it can know).  A stale or foreign entry costs one unused
+# operand at worst: the consumer looks its operand up by key and makes its own when the key differs.
+_DY_SPEC = {}
 
 
 def operand_hint(kind, x_shape, weight, stride, pad, pad_mode=PAD_ZERO, opad=0):
@@ -552,7 +561,7 @@ def _norm_res_prep(xh, sums, groups, gamma, beta, eps, act, rh, hint):
     key = (plan["layout"], plan["Cp"], plan["Ca"], pad, mode, dt, plan.get("Wa", 0))
     if len(_PREMADE) > 64:
         _PREMADE.clear()
-    _PREMADE[y.data_ptr()] = (y, key, (ahi, alo, Ha, Wa), abf)
+    _PREMADE[y.data_ptr()] = (y, key, (ahi, alo, Ha, Wa), abf, None)
     return y, prm
 
 
@@ -560,8 +569,10 @@ class _Prepared:
     """Arranged 16-bit copies of ONE fp32 NHWC tensor, made at most once per (layout, padding, format):
     the backward pass feeds the same dY (or x) to the data-gradient and the weight-gradient GEMMs."""
 
-    def __init__(self, xh, prm=None, act=ACT_NONE, slope=0.0, want_csum=False):
+    def __init__(self, xh, prm=None, act=ACT_NONE, slope=0.0, want_csum=False, rec=None):
         self.xh, self.made = xh, {}
+        self.rec = rec                                        # the parameter whose backward this dY belongs to: its FIRST operand
+                                                              # request is recorded there for the producer of the next step's dY
         self.shape, self.device = xh.shape, xh.device
         self.prm, self.act, self.slope = prm, act, slope      # fused prologue: norm-apply + activation on the way in
         self.want_csum, self.csum = want_csum, None           # per-channel sums of xh (bias gradient), taken by the first
@@ -569,10 +580,12 @@ class _Prepared:
         if prm is None and act == ACT_NONE and _PREMADE:
             pre = _PREMADE.pop(xh.data_ptr(), None)           # operand already made by the producer of xh (_norm_res_prep)
             if pre is not None and pre[0].shape == xh.shape:
-                _, key, hit, abf = pre
+                _, key, hit, abf, csum = pre
                 self.made[key] = hit
                 if abf is not None:
                     self.made[key[:5] + ("bf16",) + key[6:]] = (abf, None, hit[2], hit[3])
+                if csum is not None and want_csum:
+                    self.csum = csum
 
     def get(self, plan, pad, pad_mode, dtype=None, need_lo=True, also_bf16=False):
         """need_lo=False: the caller reads the high plane only (single-pass weight gradient) - skip writing the low one.
@@ -580,6 +593,11 @@ class _Prepared:
         GEMM of the backward pass needs - both its operands must have ONE 16-bit format), found later under dtype 'bf16'."""
         dt = dtype or CONFIG["dtype"]
         key = (plan["layout"], plan["Cp"], plan["Ca"], pad, pad_mode, dt, plan.get("Wa", 0))
+        if self.rec is not None:
+            rec, self.rec = self.rec, None
+            ok = CONFIG["fuse_bwd_prep"] and self.prm is None and self.act == ACT_NONE and (pad == 0 or pad_mode == PAD_ZERO) \
+                and plan["layout"] in (_LAYOUT_NORMAL, _LAYOUT_S2D)
+            _DY_SPEC[rec.data_ptr()] = dict(key=key, need_lo=bool(need_lo), csum=bool(self.want_csum), shape=tuple(self.shape)) if ok else None
         hit = self.made.get(key)
         if hit is not None and need_lo and hit[1] is None and CONFIG["passes"] >= 2:
             hit = None                                    # made without its low plane earlier: make it again in full
@@ -990,6 +1008,41 @@ class Prologue:
         return _norm_params(xh, self.groups, g, b, self.eps, self.stats, lazy=lazy)
 
 
+def _in_bwd(xh, g, prm, act, src=None):
+    """InstanceNorm2d(affine=False) [+ReLU] backward: gradient w.r.t. the raw input xh given g, both (N, H, W, C).
+    src = the weight of the convolution that produced xh (conv2d / conv_transpose2d leave it on the statistics they hand to
+    the norm layer).  When that convolution's backward has recorded the dY operand it asks for (`_Prepared.rec`), the apply
+    pass writes it as well - dsr_tc_prep_in_bwd - and registers it in _PREMADE for the _Prepared that convolution makes of
+    the returned gradient; otherwise dsr_in_bwd_apply alone."""
+    N, H, W, C = xh.shape
+    sums2 = _zeros_f64(N * C * 2, g.device)
+    _call("dsr_in_bwd_sums", _p(xh), _p(g), _p(prm), N, H * W, C, act, _p(sums2, torch.float64))
+    gx = torch.empty_like(xh)
+    spec = _DY_SPEC.get(src.data_ptr()) if (src is not None and CONFIG["fuse_bwd_prep"] and CONFIG["engine"] == "tc") else None
+    if spec is not None and spec["shape"] == tuple(xh.shape) and g.shape == xh.shape and act in (ACT_NONE, ACT_RELU):
+        layout, Cp, Ca, pad, _mode, dt, wa_min = key = spec["key"]
+        cg = Ca // 8
+        fits = dt == CONFIG["bwd_dtype"] and C % 8 == 0 and Cp >= C and cg <= 256 and cg & (cg - 1) == 0 and \
+            (4 * _rup(C, 4) + C) * 4 <= 48 * 1024 and (Ca >= Cp if layout == _LAYOUT_NORMAL else Ca == 4 * Cp)
+        if fits:
+            Hq, Wq = H + 2 * pad, W + 2 * pad
+            Ha, Wa = ((Hq + 1) // 2, (Wq + 1) // 2) if layout == _LAYOUT_S2D else (Hq, max(Wq, wa_min))
+            ahi = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16)
+            alo = torch.empty((N, Ha, Wa, Ca), device=xh.device, dtype=torch.bfloat16) if (CONFIG["passes"] >= 2 and spec["need_lo"]) else None
+            csum = _zeros_f64(C * CONFIG["csum_reps"], xh.device) if spec["csum"] else None
+            if _lib.PROFILE is not None:
+                _lib.PROFILE_META = dict(macs=0, shape=(N, H, W, C, Ca, layout, pad, 2, int(alo is not None)))
+            _call("dsr_tc_prep_in_bwd", _p(xh), _p(g), _p(prm), _p(sums2, torch.float64), _p(gx), N, H, W, C, act, pad, layout, Cp,
+                  _p(ahi, torch.bfloat16), _p(alo, torch.bfloat16), Ha, Wa, Ca, int(dt == "f16"), _p(csum, torch.float64),
+                  CONFIG["csum_reps"] if csum is not None else 1)
+            if len(_PREMADE) > 64:
+                _PREMADE.clear()
+            _PREMADE[gx.data_ptr()] = (gx, key, (ahi, alo, Ha, Wa), None, csum)
+            return gx
+    _call("dsr_in_bwd_apply", _p(xh), _p(g), _p(prm), _p(sums2, torch.float64), _p(gx), N, H * W, C, act)
+    return gx
+
+
 def _prologue_bwd(pro, prm, xh, gz):
     """gradient w.r.t. the RAW conv input given the gradient w.r.t. the normalised / activated operand"""
     if pro is None:
@@ -998,11 +1051,7 @@ def _prologue_bwd(pro, prm, xh, gz):
     if pro.norm:
         if pro.groups != 0:
             raise NotImplementedError("dsr_b200: GroupNorm backward is not on the main_network_best hot path")
-        sums2 = _zeros_f64(N * C * 2, gz.device)
-        _call("dsr_in_bwd_sums", _p(xh), _p(gz), _p(prm), N, H * W, C, pro.act, _p(sums2, torch.float64))
-        gx = torch.empty_like(xh)
-        _call("dsr_in_bwd_apply", _p(xh), _p(gz), _p(prm), _p(sums2, torch.float64), _p(gx), N, H * W, C, pro.act)
-        return gx
+        return _in_bwd(xh, gz, prm, pro.act, getattr(pro.stats, "src", None))
     if pro.act != ACT_NONE:
         gx = torch.empty_like(xh)
         _call("dsr_act_bwd", _p(xh), _p(gz), _p(gx), gz.numel(), pro.act, pro.slope)
@@ -1069,7 +1118,7 @@ class _Conv2d(Function):
             g2 = torch.empty_like(g)
             _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
             g = g2
-        gP = _Prepared(g, want_csum=has_bias)
+        gP = _Prepared(g, want_csum=has_bias, rec=weight)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gxp = _tc_conv_dgrad(gP, weight, stride, pad, pad_mode, H, W)
@@ -1209,7 +1258,7 @@ class _ConvTranspose2d(Function):
             g2 = torch.empty_like(g)
             _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
             g = g2
-        gP = _Prepared(g, want_csum=has_bias)
+        gP = _Prepared(g, want_csum=has_bias, rec=weight)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gxh = _tc_convT_dgrad(gP, weight, stride, pad, H, W)
@@ -1291,7 +1340,7 @@ class _CatConv2d(Function):
             g2 = torch.empty_like(g)
             _call("dsr_act_bwd", _p(y), _p(g), _p(g2), g.numel(), ACT_TANH, 0.0)
             g = g2
-        gP = _Prepared(g, want_csum=has_bias)
+        gP = _Prepared(g, want_csum=has_bias, rec=weight)
         needs = ctx.needs_input_grad[6:]
         offs = [sum(Cs[:i]) for i in range(len(Cs))]
         gxs = [None] * len(Cs)
@@ -1347,6 +1396,8 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode
     pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
     _FWD["trainable"] = torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad)
     y, st = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats, pro)
+    if st is not None:
+        st.src = weight                                   # the norm layer that takes these statistics: see _in_bwd
     return (y, st) if want_stats else y
 
 
@@ -1354,6 +1405,8 @@ def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0
                      pro=None):
     _FWD["trainable"] = torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad)
     y, st = _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding, act_out, want_stats, pro)
+    if st is not None:
+        st.src = weight
     return (y, st) if want_stats else y
 
 
@@ -1446,21 +1499,17 @@ class _InstanceNorm(Function):
             _norm_apply_fwd(xh, prm, rh, y, act)
         ctx.act = act
         ctx.has_res = residual is not None
+        ctx.src = getattr(stats, "src", None)               # weight of the convolution that produced x (see _in_bwd)
         ctx.save_for_backward(xh, prm)
         return nchw(y)
 
     @staticmethod
     def backward(ctx, gy):
         xh, prm = ctx.saved_tensors
-        N, H, W, C = xh.shape
         g = nhwc(gy)
         gx = None
         if ctx.needs_input_grad[0]:
-            sums2 = _zeros_f64(N * C * 2, g.device)
-            _call("dsr_in_bwd_sums", _p(xh), _p(g), _p(prm), N, H * W, C, ctx.act, _p(sums2, torch.float64))
-            gxh = torch.empty_like(xh)
-            _call("dsr_in_bwd_apply", _p(xh), _p(g), _p(prm), _p(sums2, torch.float64), _p(gxh), N, H * W, C, ctx.act)
-            gx = nchw(gxh)
+            gx = nchw(_in_bwd(xh, g, prm, ctx.act, ctx.src))
         gres = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return gx, None, None, gres, None, None
 

@@ -284,6 +284,15 @@ int dsr_tc_prep_norm_res(const float* x, int N, int H, int W, int C, const doubl
                          const float* beta, float eps, float* prm_out, int act, const float* res, float* y_out, int pad,
                          int pad_mode, int layout, int Cp, void* A_hi, void* A_lo, void* A_bf, int Ha, int Wa, int Ca, int f16,
                          void* stream);
+/* InstanceNorm2d(affine=False) [+ReLU] backward apply AND the arranged dY operand of the convolution in front of the norm layer
+ * in one pass: dx (fp32 NHWC, bit-identical to dsr_in_bwd_apply), A = hi (+lo) planes of dx with a zero frame of `pad` pixels
+ * (what dsr_tc_prep would make of dx: NORMAL / S2D layouts), csum (optional, [csum_reps][C], pre-zeroed) += per-channel sums
+ * of dx = the bias gradient of that convolution.  x, dy, dx: (N, H, W, C); prm from dsr_norm_finalize, sums2 from
+ * dsr_in_bwd_sums.  Shapes outside the fast scheme return DSR_ERR_UNSUPPORTED (the caller runs the two passes).
+ * models/networks.py:30, :380-381, :480 (the InstanceNorm2d layers) with :378-379, :413-414, :553 (the convolutions they follow). */
+int dsr_tc_prep_in_bwd(const float* x, const float* dy, const float* prm, const double* sums2, float* dx, int N, int H, int W,
+                       int C, int act, int pad, int layout, int Cp, void* A_hi, void* A_lo, int Ha, int Wa, int Ca, int f16,
+                       double* csum, int csum_reps, void* stream);
 /* dsr_tc_prep over torch.cat((x0, x1, x2, x3), dim=1) (NULL / 0 = absent) without materialising the concatenation:
  * models/main_model.py:305-306 (the 261-channel Task input), models/networks.py:629 (U-Net skip connections). */
 int dsr_tc_prep_cat(const float* x0, int C0, const float* x1, int C1, const float* x2, int C2, const float* x3, int C3, int N,

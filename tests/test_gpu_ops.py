@@ -768,6 +768,115 @@ def test_residual_block_tail_fused_with_next_operand(ops, train):
         ops.CONFIG.update(old)
 
 
+@pytest.mark.parametrize("layout,C,Cp,Ca,HW,pad,wa_min", [(0, 128, 128, 128, (20, 24), 2, 0), (0, 64, 64, 64, (16, 16), 1, 24),
+                                                          (2, 64, 64, 256, (18, 22), 1, 0), (0, 72, 72, 128, (9, 7), 0, 0),
+                                                          (2, 32, 32, 128, (13, 11), 1, 0), (0, 512, 512, 512, (4, 4), 1, 0)])
+@pytest.mark.parametrize("act,csum_wanted,need_lo", [(0, False, True), (1, True, False), (1, False, True), (0, True, False)])
+def test_in_bwd_apply_fused_with_the_dy_operand_is_bit_identical(ops, layout, C, Cp, Ca, HW, pad, wa_min, act, csum_wanted, need_lo):
+    """dsr_tc_prep_in_bwd: InstanceNorm2d(affine=False) [+ReLU] backward (networks.py:30, :380-381) that also writes the
+    zero-framed 16-bit dY operand of the convolution in front of the norm layer.  Against the two passes it replaces
+    (dsr_in_bwd_apply, then dsr_tc_prep of its output): dx and every operand plane must be EQUAL, the bias-gradient sums equal
+    to summation-order noise."""
+    H, W = HW
+    N = 3
+    ACT = ops.ACT_RELU if act else ops.ACT_NONE
+    xh = (torch.randn(N, H, W, C, generator=G(171)) * 1.3 + 0.4).cuda()
+    g = torch.randn(N, H, W, C, generator=G(172)).cuda()
+    xn = xh.permute(0, 3, 1, 2)
+    mean = xn.mean(dim=(2, 3))
+    rstd = (xn.var(dim=(2, 3), unbiased=False) + 1e-5).rsqrt()
+    prm = torch.stack([mean, rstd, torch.zeros_like(mean)]).contiguous().view(-1)            # [3][N][C]
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(passes=3, csum_reps=4)
+        plan = dict(layout=layout, Cp=Cp, Ca=Ca)
+        if wa_min:
+            plan["Wa"] = wa_min
+        sums2 = torch.zeros(N * C * 2, dtype=torch.float64, device="cuda")
+        ops._call("dsr_in_bwd_sums", ops._p(xh), ops._p(g), ops._p(prm), N, H * W, C, ACT, ops._p(sums2, torch.float64))
+        # the two passes
+        gx_ref = torch.empty_like(xh)
+        ops._call("dsr_in_bwd_apply", ops._p(xh), ops._p(g), ops._p(prm), ops._p(sums2, torch.float64), ops._p(gx_ref), N, H * W, C, ACT)
+        cs_ref = torch.zeros(C * 4, dtype=torch.float64, device="cuda") if csum_wanted else None
+        ahi_r, alo_r, Ha, Wa = ops._tc_prep(gx_ref, plan, pad, ops.PAD_ZERO, dtype="bf16", csum=cs_ref, need_lo=need_lo)
+        # the fused pass
+        gx = torch.full_like(xh, float("nan"))
+        ahi = torch.full((N, Ha, Wa, Ca), -1.0, device="cuda", dtype=torch.bfloat16)
+        alo = torch.full((N, Ha, Wa, Ca), -1.0, device="cuda", dtype=torch.bfloat16) if need_lo else None
+        cs = torch.zeros(C * 4, dtype=torch.float64, device="cuda") if csum_wanted else None
+        ops._call("dsr_tc_prep_in_bwd", ops._p(xh), ops._p(g), ops._p(prm), ops._p(sums2, torch.float64), ops._p(gx), N, H, W, C, ACT,
+                  pad, layout, Cp, ops._p(ahi, torch.bfloat16), ops._p(alo, torch.bfloat16), Ha, Wa, Ca, 0,
+                  ops._p(cs, torch.float64), 4 if csum_wanted else 1)
+        torch.cuda.synchronize()
+        assert torch.equal(gx, gx_ref)
+        assert torch.equal(ahi.view(torch.int16), ahi_r.view(torch.int16))
+        assert (alo_r is None) == (alo is None)
+        if need_lo:
+            assert torch.equal(alo.view(torch.int16), alo_r.view(torch.int16))
+        if csum_wanted:
+            tot, tot_r = cs.view(4, C).sum(0).cpu(), cs_ref.view(4, C).sum(0).cpu()
+            assert torch.allclose(tot, tot_r, rtol=1e-5, atol=1e-4)
+            assert torch.allclose(tot, gx_ref.double().sum(dim=(0, 1, 2)).cpu(), rtol=1e-5, atol=1e-3)
+        # against the closed form (fp64 on the CPU): dx = rstd * (g' - mean(g') - xhat * mean(g' * xhat))
+        xd, gd = xh.double().cpu().permute(0, 3, 1, 2), g.double().cpu().permute(0, 3, 1, 2)
+        xhat = (xd - xd.mean(dim=(2, 3), keepdim=True)) * (xd.var(dim=(2, 3), unbiased=False, keepdim=True) + 1e-5).rsqrt()
+        gp = gd * (xhat > 0) if act else gd
+        ref = (xd.var(dim=(2, 3), unbiased=False, keepdim=True) + 1e-5).rsqrt() * (
+            gp - gp.mean(dim=(2, 3), keepdim=True) - xhat * (gp * xhat).mean(dim=(2, 3), keepdim=True))
+        assert rel_l2(gx.cpu().permute(0, 3, 1, 2).double(), ref) <= 1e-5
+    finally:
+        ops.CONFIG.update(old)
+
+
+def test_norm_backward_writes_the_next_dy_operand_from_the_second_step(ops):
+    """ops._in_bwd: from the second backward pass on (the first one records what each convolution asks of its dY) the
+    InstanceNorm backward in front of a convolution writes that convolution's dY operand itself.  Same arithmetic as the
+    separate passes: gradients agree to summation-order noise, with one launch less per normalised convolution."""
+    from dsr_b200 import networks as nw
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=1, big_hw=0)
+        torch.manual_seed(23)
+        norm = nw.get_norm_layer("instance")
+        mods = [nw.ReflectionPad2d(3), nw.Conv2d(8, 32, 7, padding=0), norm(32), nw.ReLU(True),
+                nw.Conv2d(32, 64, 3, stride=2, padding=1), norm(64), nw.ReLU(True)] + \
+               [nw.ResnetBlock(64, "reflect", norm, False, True) for _ in range(2)] + \
+               [nw.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1), norm(32), nw.ReLU(True),
+                nw.ReflectionPad2d(3), nw.Conv2d(32, 8, 7, padding=0)]
+        net = nw.FusedSequential(*mods).cuda()
+        x = torch.randn(2, 8, 48, 40, generator=G(299))
+        res = []
+        for fuse in (True, False):
+            ops.CONFIG.update(fuse_bwd_prep=fuse)
+            ops._DY_SPEC.clear()
+            per_step = []
+            for step in range(2):
+                ops.zero_pool_reset("cuda")
+                for p_ in net.parameters():
+                    p_.grad = None
+                xc = cl(x).requires_grad_(True)
+                with _CallLog() as names:
+                    y = net(xc)
+                    (y * y).sum().backward()
+                per_step.append((xc.grad.cpu(), [p_.grad.cpu().clone() for p_ in net.parameters()],
+                                 names.count("dsr_tc_prep_in_bwd"), names.count("dsr_in_bwd_apply"),
+                                 sum(1 for nm in names if "pack" not in nm)))
+            res.append(per_step)
+        (f1, f2), (u1, u2) = res
+        assert f1[2] == 0 and u1[2] == 0 and u2[2] == 0            # first step: nothing recorded yet; switch off: never
+        assert f2[2] >= 5 and f2[2] + f2[3] == u2[3]               # fused applies replace plain ones one for one ...
+        assert f2[4] == u2[4] - f2[2]                              # ... and each saves the consumer's dsr_tc_prep launch
+        for a, b in ((f2, u2), (f2, f1)):
+            assert rel_l2(a[0], b[0]) <= 2e-4
+            for ga, gb in zip(a[1], b[1]):
+                if gb.dim() == 4:          # (the bias gradients in front of a norm layer are sums that cancel: pure rounding noise)
+                    assert rel_l2(ga, gb) <= 2e-4
+        assert rel_l2(f2[1][-1], u2[1][-1]) <= 2e-4                # the last bias (no norm behind it) is a real gradient
+    finally:
+        ops.CONFIG.update(old)
+        ops._DY_SPEC.clear()
+
+
 def test_folded_norm_finalize_through_the_layers(ops):
     """the same comparison through the layer stack (prologue route and stand-alone InstanceNorm), forward and backward; the
     statistics come from fp64 atomics in the GEMM epilogues here (run-to-run differences in the last bits, amplified by the
