@@ -637,6 +637,7 @@ class _PreparedCat(_Prepared):
         self.xh, self.made = None, {}
         self.shape, self.device = (N, H, W, sum(p.shape[3] for p in parts)), parts[0].device
         self.prm, self.act, self.slope, self.want_csum, self.csum = None, ACT_NONE, 0.0, False, None
+        self.rec = None
 
     def _make(self, plan, pad, pad_mode, dtype, csum, need_lo, also_bf16):
         N, H, W, C = self.shape

@@ -731,7 +731,7 @@ def test_residual_block_tail_fused_with_next_operand(ops, train):
     from dsr_b200 import networks as nw
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0, fuse_bwd_prep=False)   # (one fusion at a time)
         torch.manual_seed(21)
         norm = nw.get_norm_layer("instance")
         mods = [nw.Conv2d(16, 64, 3, stride=2, padding=1), norm(64), nw.ReLU(True)] + \
@@ -835,7 +835,7 @@ def test_norm_backward_writes_the_next_dy_operand_from_the_second_step(ops):
     from dsr_b200 import networks as nw
     old = dict(ops.CONFIG)
     try:
-        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=1, big_hw=0)
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0)
         torch.manual_seed(23)
         norm = nw.get_norm_layer("instance")
         mods = [nw.ReflectionPad2d(3), nw.Conv2d(8, 32, 7, padding=0), norm(32), nw.ReLU(True),
@@ -867,11 +867,13 @@ def test_norm_backward_writes_the_next_dy_operand_from_the_second_step(ops):
         assert f2[2] >= 5 and f2[2] + f2[3] == u2[3]               # fused applies replace plain ones one for one ...
         assert f2[4] == u2[4] - f2[2]                              # ... and each saves the consumer's dsr_tc_prep launch
         for a, b in ((f2, u2), (f2, f1)):
-            assert rel_l2(a[0], b[0]) <= 2e-4
+            # (closeness, not equality: the norm statistics come from fp64 atomics in the GEMM epilogues, whose run-to-run
+            # differences in the last bits the backward operands amplify - measured 2.0e-4 between two identical runs)
+            assert rel_l2(a[0], b[0]) <= 1e-3
             for ga, gb in zip(a[1], b[1]):
                 if gb.dim() == 4:          # (the bias gradients in front of a norm layer are sums that cancel: pure rounding noise)
-                    assert rel_l2(ga, gb) <= 2e-4
-        assert rel_l2(f2[1][-1], u2[1][-1]) <= 2e-4                # the last bias (no norm behind it) is a real gradient
+                    assert rel_l2(ga, gb) <= 1e-3
+        assert rel_l2(f2[1][-1], u2[1][-1]) <= 1e-3                # the last bias (no norm behind it) is a real gradient
     finally:
         ops.CONFIG.update(old)
         ops._DY_SPEC.clear()
