@@ -5,6 +5,7 @@
 // fp32 NHWC input read once into shared memory (with the fused norm-apply + activation prologue and the padding mode
 // applied on the way in), channel-quad-major tiles so a warp's float4 reads are conflict-free, weights broadcast from
 // shared memory, bias + tanh in the epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/dsr_b200.h"
 
@@ -112,6 +113,90 @@ conv_out1_s1_kernel(const float* __restrict__ x, int N, int H, int W, int C, con
     }
 }
 
+// The same convolution register-blocked for the K x K heads the step runs (K = 7: G_A_d's 64 -> 1 head and the data gradients
+// of the one-channel 7x7 first layers).  conv_out1_s1_kernel issues 8 LDS.128 per 16 FMA instructions (one output pixel per
+// thread: every tap re-reads its activations and its weights) and runs at ~12 % of the fp32 pipe, bound by shared-memory
+// wavefronts.  Here a thread owns O1R_RB = 4 vertically adjacent output pixels: per (channel quad, kernel column s) it loads
+// the RB + K - 1 = 10 activations of its column ONCE into registers and reuses them across the K kernel rows and the RB
+// outputs - 10 conflict-free LDS.128 (a half-warp reads 256 contiguous bytes) + K broadcast weight loads per K * RB * 4 = 112
+// FMAs, i.e. 47 shared-memory wavefronts per 28 FMA issue cycles instead of 32 per 4.  Block = 16 (w) x 64 (h) outputs, 8
+// channels per shared-memory chunk (50 KB: four blocks per SM); lanes stage (pixel, quad) pairs so that a pixel's 32 bytes of
+// a chunk are one sector.
+#define O1R_RB 4
+#define O1R_CQ 2
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_out1_s1_rb_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act_in,
+                       float slope, const float* __restrict__ w /* [C][K][K] */, const float* __restrict__ bias, int pad,
+                       int pad_mode, int act_out, float* __restrict__ out, int Ho, int Wo) {
+    extern __shared__ float4 o1_sm[];
+    constexpr int TH = 16 * O1R_RB, PH = TH + K - 1, PW = O1_TILE + K - 1, PP = PH * PW;
+    const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && (!prm || !((uintptr_t)prm & 15));
+    float4* tile = o1_sm;                                   // [CQ][PH][PW]
+    float4* wsm = o1_sm + O1R_CQ * PP;                      // [K*K][CQ]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tiles_w = (Wo + O1_TILE - 1) / O1_TILE, tiles_h = (Ho + TH - 1) / TH;
+    const long NC = (long)N * C;
+    for (int t = blockIdx.x; t < N * tiles_h * tiles_w; t += gridDim.x) {
+        const int n = t / (tiles_h * tiles_w), r0 = t - n * tiles_h * tiles_w;
+        const int h0 = (r0 / tiles_w) * TH, w0 = (r0 % tiles_w) * O1_TILE;
+        float acc[O1R_RB];
+#pragma unroll
+        for (int i = 0; i < O1R_RB; ++i) acc[i] = 0.f;
+        for (int c0 = 0; c0 < C; c0 += 4 * O1R_CQ) {
+            __syncthreads();
+            for (int i = tid; i < O1R_CQ * PP; i += 256) {
+                const int pq = i / O1R_CQ, cq = i - pq * O1R_CQ;
+                const int py = pq / PW, px = pq - py * PW;
+                const int sy = o1_pad_src(h0 + py - pad, H, pad_mode), sx = o1_pad_src(w0 + px - pad, W, pad_mode);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sy >= 0 && sx >= 0) {
+                    const int c = c0 + cq * 4;
+                    if (c < C) v = o1_load4(x + ((long)(n * H + sy) * W + sx) * C + c, c, C, prm, NC, (long)n * C + c, act_in, slope, vec);
+                }
+                tile[cq * PP + pq] = v;
+            }
+            for (int i = tid; i < K * K * O1R_CQ; i += 256) {
+                const int tap = i / O1R_CQ, cq = i - tap * O1R_CQ, c = c0 + cq * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? w[(long)(c + e) * K * K + tap] : 0.f;
+                wsm[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int cq = 0; cq < O1R_CQ; ++cq) {
+#pragma unroll
+                for (int s = 0; s < K; ++s) {
+                    float4 a[O1R_RB + K - 1];
+#pragma unroll
+                    for (int j = 0; j < O1R_RB + K - 1; ++j) a[j] = tile[cq * PP + (ty * O1R_RB + j) * PW + tx + s];
+#pragma unroll
+                    for (int r = 0; r < K; ++r) {
+                        const float4 b = wsm[(r * K + s) * O1R_CQ + cq];
+#pragma unroll
+                        for (int i = 0; i < O1R_RB; ++i)
+                            acc[i] += a[i + r].x * b.x + a[i + r].y * b.y + a[i + r].z * b.z + a[i + r].w * b.w;
+                    }
+                }
+            }
+        }
+        const int ww = w0 + tx;
+        if (ww < Wo) {
+            const float bv = bias ? bias[0] : 0.f;
+#pragma unroll
+            for (int i = 0; i < O1R_RB; ++i) {
+                const int h = h0 + ty * O1R_RB + i;
+                if (h < Ho) {
+                    float o = acc[i] + bv;
+                    if (act_out == DSR_ACT_TANH) o = tanhf(o);
+                    out[((long)n * Ho + h) * Wo + ww] = o;
+                }
+            }
+        }
+    }
+}
+
 // ConvTranspose2d 4x4 stride 2 pad 1 to one channel: each thread owns one input pixel position (h, w) and produces its four
 // output phases out[2h+a][2w+b] = sum_{dr,ds in {0,1}} sum_c x[h-1+a+dr][w-1+b+ds][c] * W[c][3-a-2dr][3-b-2ds].
 __global__ void __launch_bounds__(256)
@@ -182,6 +267,91 @@ convT4_out1_kernel(const float* __restrict__ x, int N, int H, int W, int C, cons
     }
 }
 
+// The transposed head register-blocked the same way: a thread owns O1R_RB = 4 vertically adjacent input positions (16 outputs),
+// per channel quad it loads its 6 x 3 activations once (18 conflict-free LDS.128) + the 16 taps (broadcast) for 256 FMAs
+// (convT4_out1_kernel: 32 LDS.128 per 64 FMAs).  Block = 128 threads = 16 (w) x 32 (h) input positions, 8 channels per chunk.
+__global__ void __launch_bounds__(128)
+convT4_out1_rb_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ prm, int act_in,
+                      float slope, const float* __restrict__ w /* [C][4][4] */, const float* __restrict__ bias, int act_out,
+                      float* __restrict__ out /* N x 2H x 2W */) {
+    extern __shared__ float4 o1_sm[];
+    constexpr int TH = 8 * O1R_RB, PH = TH + 2, PW = O1_TILE + 2, PP = PH * PW;
+    float4* tile = o1_sm;                                   // [CQ][PH][PW]
+    float4* wsm = o1_sm + O1R_CQ * PP;                      // [16][CQ]
+    const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && (!prm || !((uintptr_t)prm & 15));
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tiles_w = (W + O1_TILE - 1) / O1_TILE, tiles_h = (H + TH - 1) / TH;
+    const long NC = (long)N * C;
+    for (int t = blockIdx.x; t < N * tiles_h * tiles_w; t += gridDim.x) {
+        const int n = t / (tiles_h * tiles_w), r0 = t - n * tiles_h * tiles_w;
+        const int h0 = (r0 / tiles_w) * TH, w0 = (r0 % tiles_w) * O1_TILE;
+        float acc[O1R_RB][4];
+#pragma unroll
+        for (int i = 0; i < O1R_RB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int c0 = 0; c0 < C; c0 += 4 * O1R_CQ) {
+            __syncthreads();
+            for (int i = tid; i < O1R_CQ * PP; i += 128) {
+                const int pq = i / O1R_CQ, cq = i - pq * O1R_CQ;
+                const int py = pq / PW, px = pq - py * PW;
+                const int sy = h0 + py - 1, sx = w0 + px - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+                    const int c = c0 + cq * 4;
+                    if (c < C) v = o1_load4(x + ((long)(n * H + sy) * W + sx) * C + c, c, C, prm, NC, (long)n * C + c, act_in, slope, vec);
+                }
+                tile[cq * PP + pq] = v;
+            }
+            for (int i = tid; i < 16 * O1R_CQ; i += 128) {
+                const int tap = i / O1R_CQ, cq = i - tap * O1R_CQ, c = c0 + cq * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? w[(long)(c + e) * 16 + tap] : 0.f;
+                wsm[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int cq = 0; cq < O1R_CQ; ++cq) {
+                float4 a[O1R_RB + 2][3];
+#pragma unroll
+                for (int j = 0; j < O1R_RB + 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) a[j][k] = tile[cq * PP + (ty * O1R_RB + j) * PW + tx + k];
+#pragma unroll
+                for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+                    for (int pb = 0; pb < 2; ++pb)
+#pragma unroll
+                        for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+                            for (int ds = 0; ds < 2; ++ds) {
+                                const float4 wv = wsm[((3 - pa - 2 * dr) * 4 + (3 - pb - 2 * ds)) * O1R_CQ + cq];
+#pragma unroll
+                                for (int i = 0; i < O1R_RB; ++i) {
+                                    const float4 xv = a[i + pa + dr][pb + ds];
+                                    acc[i][pa * 2 + pb] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+                                }
+                            }
+            }
+        }
+        const int ww = w0 + tx;
+        if (ww < W) {
+            const float bv = bias ? bias[0] : 0.f;
+#pragma unroll
+            for (int i = 0; i < O1R_RB; ++i) {
+                const int h = h0 + ty * O1R_RB + i;
+                if (h < H) {
+#pragma unroll
+                    for (int pa = 0; pa < 2; ++pa) {
+                        float o0 = acc[i][pa * 2] + bv, o1 = acc[i][pa * 2 + 1] + bv;
+                        if (act_out == DSR_ACT_TANH) { o0 = tanhf(o0); o1 = tanhf(o1); }
+                        *reinterpret_cast<float2*>(out + ((long)n * 2 * H + 2 * h + pa) * 2 * W + 2 * ww) = make_float2(o0, o1);
+                    }
+                }
+            }
+        }
+    }
+}
+
 extern "C" int dsr_conv_out1(const float* x, int N, int H, int W, int C, const float* prm, int act_in, float slope,
                              const float* w, const float* bias, int R, int S, int pad, int pad_mode, int transposed,
                              int act_out, float* out, void* stream) {
@@ -189,6 +359,17 @@ extern "C" int dsr_conv_out1(const float* x, int N, int H, int W, int C, const f
     DSR_REQUIRE((long)N * H * W < (1L << 31) / 4, "tensor too large for 32-bit pixel indices");
     if (transposed) {
         DSR_REQUIRE(R == 4 && S == 4 && pad == 1, "transposed variant: 4x4, stride 2, padding 1");
+        {
+            const char* e = getenv("DSR_OUT1_RB");
+            if (H >= 8 * O1R_RB && !((uintptr_t)out & 7) && (!e || atoi(e) != 0)) {
+                const int tiles_rb = N * dsr_cdiv(H, 8 * O1R_RB) * dsr_cdiv(W, O1_TILE);
+                const size_t smem_rb = (size_t)(O1R_CQ * (8 * O1R_RB + 2) * (O1_TILE + 2) + 16 * O1R_CQ) * sizeof(float4);
+                const int cap_rb = dsr_num_sms() * 8;
+                convT4_out1_rb_kernel<<<tiles_rb < cap_rb ? tiles_rb : cap_rb, 128, smem_rb, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w,
+                                                                                                       bias, act_out, out);
+                return dsr_check_launch("conv_out1 (transposed, register-blocked)");
+            }
+        }
         const int tiles = N * dsr_cdiv(H, O1_TILE) * dsr_cdiv(W, O1_TILE);
         const size_t smem = (4 * (O1_TILE + 2) * (O1_TILE + 2) + 64) * sizeof(float4);
         const int cap = dsr_num_sms() * 4;
@@ -201,6 +382,24 @@ extern "C" int dsr_conv_out1(const float* x, int N, int H, int W, int C, const f
     const int tiles = N * dsr_cdiv(Ho, O1_TILE) * dsr_cdiv(Wo, O1_TILE);
     const size_t smem = (4 * (O1_TILE + R - 1) * (O1_TILE + S - 1) + R * S * 4) * sizeof(float4);
     const int cap = dsr_num_sms() * 4;
+    {
+        const char* e = getenv("DSR_OUT1_RB");           // 0: the one-pixel-per-thread kernel (A/B)
+        if (R == 7 && S == 7 && Ho >= 16 * O1R_RB && (!e || atoi(e) != 0)) {
+            constexpr int PHr = 16 * O1R_RB + 6, PWr = O1_TILE + 6;
+            const size_t smem_rb = (size_t)(O1R_CQ * PHr * PWr + 49 * O1R_CQ) * sizeof(float4);
+            static bool attr_set = false;
+            if (!attr_set) {
+                if (cudaFuncSetAttribute(conv_out1_s1_rb_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rb) != cudaSuccess) {
+                    dsr_set_error("conv_out1: cannot raise the shared-memory limit"); return DSR_ERR_CUDA;
+                }
+                attr_set = true;
+            }
+            const int tiles_rb = N * dsr_cdiv(Ho, 16 * O1R_RB) * dsr_cdiv(Wo, O1_TILE);
+            conv_out1_s1_rb_kernel<7><<<tiles_rb < cap ? tiles_rb : cap, 256, smem_rb, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias,
+                                                                                                 pad, pad_mode, act_out, out, Ho, Wo);
+            return dsr_check_launch("conv_out1 (register-blocked)");
+        }
+    }
     if (R == 7 && S == 7)
         conv_out1_s1_kernel<7><<<tiles < cap ? tiles : cap, 256, smem, ST(stream)>>>(x, N, H, W, C, prm, act_in, slope, w, bias, R, S, pad,
                                                                                   pad_mode, act_out, out, Ho, Wo);

@@ -110,7 +110,7 @@ __device__ __forceinline__ int pad_readers(int i, int p, int n, int mode, int* q
     return k;
 }
 __global__ void pad2d_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int N, int H, int W, int C,
-                                 int p, int mode, int Wp) {
+                                 int p, int mode, int Wp, const float* __restrict__ add) {
     int Hp = H + 2 * p;
     long total = (long)N * H * W * C;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -122,13 +122,14 @@ __global__ void pad2d_bwd_kernel(const float* __restrict__ gy, float* __restrict
         float acc = 0.f;
         for (int a = 0; a < nh; ++a)
             for (int b = 0; b < nw; ++b) acc += gy[(((long)n * Hp + qh[a]) * Wp + qw[b]) * C + c];
-        gx[idx] = acc;
+        gx[idx] = add ? acc + add[idx] : acc;
     }
 }
 
 // float4 version: one thread = 4 channels of one source pixel; interior pixels have exactly one reader
 __global__ void __launch_bounds__(256)
-pad2d_bwd_vec4_kernel(const float4* __restrict__ gy, float4* __restrict__ gx, int N, int H, int W, int C4, int p, int mode, int Wp) {
+pad2d_bwd_vec4_kernel(const float4* __restrict__ gy, float4* __restrict__ gx, int N, int H, int W, int C4, int p, int mode, int Wp,
+                      const float4* __restrict__ add) {
     const int Hp = H + 2 * p;                      // Wp = row pitch of gy in pixels (>= W + 2 p)
     const int total = N * H * W * C4;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -147,6 +148,10 @@ pad2d_bwd_vec4_kernel(const float4* __restrict__ gy, float4* __restrict__ gx, in
                     const float4 v = gy[((long)(n * Hp + qh[a]) * Wp + qw[b]) * C4 + c];
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
+        }
+        if (add) {       // a second gradient of the same tensor (the skip connection of a residual block) joins in the same pass
+            const float4 r = add[idx];
+            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
         }
         gx[idx] = acc;
     }
@@ -653,16 +658,20 @@ extern "C" int dsr_pad2d_fwd(const float* x, float* y, int N, int H, int W, int 
 }
 // wpitch = row pitch of gy in pixels (>= W + 2 pad): the grouped data gradient (ops._tc_dgrad_group) computes rows rounded up
 // to whole pixel groups
-extern "C" int dsr_pad2d_bwd_pitch(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, int wpitch,
-                                   void* stream) {
+extern "C" int dsr_pad2d_bwd_pitch_add(const float* gy, const float* add, float* gx, int N, int H, int W, int C, int pad, int mode,
+                                       int wpitch, void* stream) {
     DSR_REQUIRE(gy && gx && pad >= 0 && pad <= 7 && wpitch >= W + 2 * pad, "bad arguments");
-    if (!(C & 3) && !((uintptr_t)gy & 15) && !((uintptr_t)gx & 15) && (long)N * H * W * (C / 4) < (1L << 31) &&
+    if (!(C & 3) && !((uintptr_t)gy & 15) && !((uintptr_t)gx & 15) && !((uintptr_t)add & 15) && (long)N * H * W * (C / 4) < (1L << 31) &&
         (long)N * (H + 2 * pad) * wpitch * (C / 4) < (1L << 31))
         pad2d_bwd_vec4_kernel<<<dsr_grid((long)N * H * W * (C / 4), 256), 256, 0, ST(stream)>>>((const float4*)gy, (float4*)gx, N, H, W,
-                                                                                               C / 4, pad, mode, wpitch);
+                                                                                               C / 4, pad, mode, wpitch, (const float4*)add);
     else
-        pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode, wpitch);
+        pad2d_bwd_kernel<<<dsr_grid((long)N * H * W * C, TPB), TPB, 0, ST(stream)>>>(gy, gx, N, H, W, C, pad, mode, wpitch, add);
     return dsr_check_launch("pad2d_bwd");
+}
+extern "C" int dsr_pad2d_bwd_pitch(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, int wpitch,
+                                   void* stream) {
+    return dsr_pad2d_bwd_pitch_add(gy, nullptr, gx, N, H, W, C, pad, mode, wpitch, stream);
 }
 extern "C" int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, void* stream) {
     return dsr_pad2d_bwd_pitch(gy, gx, N, H, W, C, pad, mode, W + 2 * pad, stream);

@@ -29,10 +29,11 @@ class Identity(nn.Module):                        # networks.py:13-15
 class Conv2d(nn.Conv2d):
     """nn.Conv2d with zeros / reflect / replicate ``padding_mode`` (networks.py:379; translation_network.py:472)."""
 
-    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None, want_stats=False, pro=None):
+    def forward(self, x, act_out=ops.ACT_NONE, pre_pad=None, want_stats=False, pro=None, skip_out=False):
         """pre_pad = (pad, mode) of an nn.ReflectionPad2d / ReplicationPad2d module placed right before
         this conv: it is folded into the conv's operand preparation instead of materialising a padded copy.
-        want_stats: also return the per-(n, c) statistics of the output for the norm layer that follows."""
+        want_stats: also return the per-(n, c) statistics of the output for the norm layer that follows.
+        skip_out: also return an alias of x (last element) for a residual block's skip connection (ops._Conv2d)."""
         if self.dilation != (1, 1) or self.groups != 1:
             raise NotImplementedError("dsr_b200.Conv2d: dilation/groups are not on the hot path")
         p, mode = self.padding[0], self.padding_mode
@@ -41,13 +42,13 @@ class Conv2d(nn.Conv2d):
                 raise NotImplementedError("dsr_b200.Conv2d: explicit pad module followed by a padded conv")
             p, mode = pre_pad
         if isinstance(x, ops.LazyCat):
-            if want_stats or pro is not None:
+            if want_stats or pro is not None or skip_out:
                 raise NotImplementedError("dsr_b200.Conv2d: a LazyCat input takes no fused prologue / statistics")
             if ops.conv_fusable("conv", x, self.weight, self.stride[0], p):
                 return ops.cat_conv2d(x.parts, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode)
             x = ops.cat(x.parts)
         return ops.conv2d(x, self.weight, self.bias, self.stride[0], p, act_out, pad_mode=mode, want_stats=want_stats,
-                          pro=pro)
+                          pro=pro, skip_out=skip_out)
 
     def fusable(self, x, pre_pad=None):
         p = pre_pad[0] if pre_pad is not None else self.padding[0]
@@ -132,16 +133,19 @@ def next_operand_hint(mods, i, x):
     return ops.operand_hint("convT", x.shape, conv.weight, conv.stride[0], conv.padding[0], opad=conv.output_padding[0])
 
 
-def run_fused(mods, x, tail_stats=False):
+def run_fused(mods, x, tail_stats=False, skip_first=False):
     """Run a module list as fused units  [norm] [ReLU | LeakyReLU] [pad module] conv [Tanh]:
       * the norm-apply, the activation and the padding are folded into the conv's operand preparation
         (ops.Prologue) whenever the conv runs on the tcgen05 path - the normalised tensor is never written;
       * Tanh goes into the GEMM epilogue;
       * when a norm layer follows, the GEMM epilogue also takes its statistics and hands them over.
     Anything else runs module by module (norm + ReLU still share one pass).  tail_stats: the list ends with a conv
-    whose norm layer is applied by the caller (residual blocks) -> returns (x, stats)."""
+    whose norm layer is applied by the caller (residual blocks) -> returns (x, stats).  skip_first: when the list opens with a
+    fused [pad] Conv2d, that conv also hands out an alias of the input for the caller's skip connection (ops._Conv2d.forward)
+    -> returns (x, stats, alias or None)."""
     norms, pads = (InstanceNorm2d, GroupNorm), (ReflectionPad2d, ReplicationPad2d)
     n, i, stats = len(mods), 0, None          # stats = statistics of x, meaningful only while mods[i] is a norm layer
+    skip = None
     while i < n:
         j, norm, act, pad = i, None, None, None
         if isinstance(mods[j], norms):
@@ -175,15 +179,23 @@ def run_fused(mods, x, tail_stats=False):
                     kw["pro"] = ops.Prologue(act=a, slope=slope)
             after = mods[j + 1] if j + 1 < n else None
             stats = None
+            want_skip = skip_first and i == 0 and plain and isinstance(conv, Conv2d) and not isinstance(x, ops.LazyCat)
+            if want_skip:
+                kw["skip_out"] = True
             if isinstance(after, Tanh):
-                x = conv(x, act_out=ops.ACT_TANH, **kw)
+                out = conv(x, act_out=ops.ACT_TANH, **kw)
                 i = j + 2
             elif isinstance(after, norms) or (after is None and tail_stats):
-                x, stats = conv(x, want_stats=True, **kw)
+                out = conv(x, want_stats=True, **kw)
+                if want_skip:
+                    out, skip = out[:2], out[2]
+                x, stats = out
                 i = j + 1
+                continue
             else:
-                x = conv(x, **kw)
+                out = conv(x, **kw)
                 i = j + 1
+            x, skip = out if want_skip else (out, skip)
             continue
         m = mods[i]
         if isinstance(m, norms):
@@ -201,6 +213,8 @@ def run_fused(mods, x, tail_stats=False):
             x = m(x)
             i += 1
         stats = None
+    if skip_first:
+        return x, stats, skip
     return (x, stats) if tail_stats else x
 
 
@@ -381,6 +395,10 @@ class ResnetBlock(nn.Module):                     # networks.py:424-481
         that layer's arranged operand (one pass instead of two)"""
         mods = list(self.conv_block)
         if isinstance(mods[-1], (InstanceNorm2d, GroupNorm)):      # skip add fused into the norm pass
+            if ops.CONFIG["fuse_skip_grad"] and torch.is_grad_enabled() and x.requires_grad:
+                # the skip connection leaves through the first conv's node: both gradients of x meet in ITS backward
+                y, stats, skip = run_fused(mods[:-1], x, tail_stats=True, skip_first=True)
+                return mods[-1](y, residual=x if skip is None else skip, stats=stats, hint=hint)
             y, stats = run_fused(mods[:-1], x, tail_stats=True)
             return mods[-1](y, residual=x, stats=stats, hint=hint)  # networks.py:480
         return x + self.conv_block(x)

@@ -306,6 +306,8 @@ CONFIG = {
     "fuse_bwd_prep": True,   # InstanceNorm backward also writes the dY operand of the convolution in front of the norm layer
                              # (dsr_tc_prep_in_bwd: one pass instead of dsr_in_bwd_apply + dsr_tc_prep), from the second step on:
                              # the operand a convolution's backward asks for is recorded on its weight the first time
+    "fuse_skip_grad": True,  # residual blocks: the skip connection's gradient joins the first convolution's padding adjoint
+                             # (dsr_pad2d_bwd_pitch_add) instead of autograd's separate add kernel
     "fuse_norm_prep": True,  # the closing norm (+ skip add) of a residual block also writes the next conv's operand (dsr_tc_prep_norm_res)
     "fold_finalize": True,   # dsr_norm_finalize folded into its first consumer (dsr_tc_prep_fin / dsr_norm_apply_fwd_fin)
     "wgrad_slabs": False,  # True: weight-gradient K splits store their own slabs (dsr_tc_wgrad2p) and the unpack sums them in a
@@ -826,8 +828,10 @@ def _tc_dgrad_group(gP, weight, padq, Hout, Wout, dt, g=2):
     return y, Wc
 
 
-def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
-    """dL/dx of a Conv2d on the tcgen05 path (None when the shape is not covered).  g: (N,Ho,Wo,Co)."""
+def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W, add=None):
+    """dL/dx of a Conv2d on the tcgen05 path (None when the shape is not covered).  g: (N,Ho,Wo,Co).
+    add = [t]: a second gradient of x, (N, H, W, Ci), to be added; the route that can do so in its own last pass does and
+    sets add[0] = None."""
     if not CONFIG["tc_backward"]:
         return None
     N, Ho, Wo, Co = g.shape
@@ -858,7 +862,11 @@ def _tc_conv_dgrad(g, weight, stride, pad, pad_mode, H, W):
         else:
             gxp = _tc_conv_fwd(g, weight, None, plan, 1, R - 1, PAD_ZERO, ACT_NONE, H + 2 * pad, W + 2 * pad, dtype=dt, Co=Ci, macs=macs)
         gx = torch.empty((N, H, W, Ci), device=g.device, dtype=torch.float32)
-        _call("dsr_pad2d_bwd_pitch", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode, Wc)
+        if add is not None and add[0] is not None and add[0].shape == gx.shape:
+            _call("dsr_pad2d_bwd_pitch_add", _p(gxp), _p(add[0]), _p(gx), N, H, W, Ci, pad, pad_mode, Wc)
+            add[0] = None
+        else:
+            _call("dsr_pad2d_bwd_pitch", _p(gxp), _p(gx), N, H, W, Ci, pad, pad_mode, Wc)
         return gx
     if stride == 2 and (pad_mode == PAD_ZERO or (pad == 1 and CONFIG["s2_border"])):
         opad = H - ((Ho - 1) * 2 - 2 * pad + R)
@@ -1065,7 +1073,9 @@ class _Conv2d(Function):
     translation_network.py:472,478,495,563."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out, want_stats, pro):
+    def forward(ctx, x, weight, bias, stride, pad, pad_mode, act_out, want_stats, pro, skip_out=False):
+        """skip_out: x is also returned as a third output (an alias) - a residual block routes its skip connection through
+        it so that BOTH gradients of x arrive in this node's backward and are added inside its last pass."""
         xh = nhwc(x)
         N, H, W, Ci = xh.shape
         Co, Ci2, R, S = weight.shape
@@ -1104,15 +1114,18 @@ class _Conv2d(Function):
         ctx.cfg = (stride, pad, pad_mode, act_out, bias is not None)
         ctx.bias_ref, ctx.pro = bias, pro
         ctx.save_for_backward(xh, weight, y if act_out == ACT_TANH else None, _prm_ready(prm))
-        return _with_stats(ctx, y, stats)
+        return _with_stats(ctx, y, stats) + ((x,) if skip_out else (None,))
 
     @staticmethod
-    def backward(ctx, gy, _gstats=None):
+    def backward(ctx, gy, _gstats=None, gskip=None):
         xh, weight, y, prm = ctx.saved_tensors
         pro = ctx.pro
         stride, pad, pad_mode, act_out, has_bias = ctx.cfg
         N, H, W, Ci = xh.shape
         Co, _, R, S = weight.shape
+        if gy is None:                                          # only the skip alias was used
+            return gskip, None, None, None, None, None, None, None, None, None
+        add = [nhwc(gskip) if (gskip is not None and ctx.needs_input_grad[0]) else None]    # consumed by whoever adds it
         g = nhwc(gy)
         _, Ho, Wo, _ = g.shape
         if act_out == ACT_TANH:
@@ -1122,7 +1135,7 @@ class _Conv2d(Function):
         gP = _Prepared(g, want_csum=has_bias, rec=weight)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gxp = _tc_conv_dgrad(gP, weight, stride, pad, pad_mode, H, W)
+            gxp = _tc_conv_dgrad(gP, weight, stride, pad, pad_mode, H, W, add=add if pro is None else None)
             if gxp is None and stride == 1 and CONFIG["out1"] and R <= 9 and S <= 9 and (
                     (Co == 1 and Ci % 16 == 0 and R * S * Ci * 4 <= 180 * 1024) or Ci == 1):
                 # one-channel layers (csrc/conv_out1.cu): a conv with ONE output channel has an outer-product data gradient;
@@ -1154,6 +1167,8 @@ class _Conv2d(Function):
                     _call("dsr_pad2d_bwd", _p(gxp), _p(gxh), N, H, W, Ci, pad, pad_mode)
                     gxp = gxh
             gx = nchw(_prologue_bwd(pro, prm, xh, gxp))
+            if add[0] is not None:
+                gx = gx + gskip                                 # (a route without the fused add)
         need_w, need_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
         if need_w and gx is None:
             _tc_wgrad_m_operand(gP, Co)           # no data gradient ran: make the dY operand on the main stream
@@ -1172,7 +1187,7 @@ class _Conv2d(Function):
             if need_b:
                 gb = _bias_grad(g, Co, ctx.bias_ref, gP)
             _keep(g, gP.csum, prm)
-        return gx, gw, gb, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
 def _new_stats(N, C, device):
@@ -1391,14 +1406,17 @@ def conv_fusable(kind, x, weight, stride, padding, output_padding=0):
     return tc_conv_plan("convT", Ci, Co, R, S, stride, padding, output_padding, H, W) is not None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO, want_stats=False, pro=None):
+def conv2d(x, weight, bias=None, stride=1, padding=0, act_out=ACT_NONE, pad_mode=PAD_ZERO, want_stats=False, pro=None,
+           skip_out=False):
     """-> y, or (y, stats) with want_stats: stats = float64 [N*Cout*2] per-(n, c) (sum, sum of squares) of y for the
     normalisation layer that follows (instance_norm / group_norm take it through their `stats` argument)."""
     pad_mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else pad_mode
     _FWD["trainable"] = torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad)
-    y, st = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats, pro)
+    y, st, sk = _Conv2d.apply(x, weight, bias, stride, padding, pad_mode, act_out, want_stats, pro, skip_out)
     if st is not None:
         st.src = weight                                   # the norm layer that takes these statistics: see _in_bwd
+    if skip_out:                                          # (..., alias of x: see _Conv2d.forward)
+        return (y, st, sk) if want_stats else (y, sk)
     return (y, st) if want_stats else y
 
 

@@ -157,6 +157,11 @@ int dsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int pa
 /* the same with an explicit row pitch of gy in pixels (wpitch >= W + 2 pad): the grouped data gradient of the 7x7 heads
  * (dsr_b200/ops.py _tc_dgrad_group) computes rows rounded up to whole groups of 4 pixels.  networks.py:378, :413. */
 int dsr_pad2d_bwd_pitch(const float* gy, float* gx, int N, int H, int W, int C, int pad, int mode, int wpitch, void* stream);
+/* ... plus a second gradient of the same (N, H, W, C) tensor added in the same pass (NULL = none): the skip connection of a
+ * residual block hands its gradient to the block's first convolution, whose padding adjoint is the last pass of the block's
+ * backward (out = x + conv_block(x), models/networks.py:478-480; autograd would add the two with a separate kernel). */
+int dsr_pad2d_bwd_pitch_add(const float* gy, const float* add, float* gx, int N, int H, int W, int C, int pad, int mode,
+                            int wpitch, void* stream);
 int dsr_act_fwd(const float* x, float* y, long n, int kind, float slope, void* stream);
 int dsr_act_bwd(const float* ref, const float* gy, float* gx, long n, int kind, float slope, void* stream);
 /* per-(n,c) (sum, sum of squares) over P pixels, accumulated into sums (double [N][C][2], pre-zeroed). */

@@ -879,6 +879,131 @@ def test_norm_backward_writes_the_next_dy_operand_from_the_second_step(ops):
         ops._DY_SPEC.clear()
 
 
+@pytest.mark.parametrize("padding", ["reflect", "zero"])
+def test_residual_skip_gradient_joins_the_first_conv_backward(ops, padding):
+    """out = x + conv_block(x) (networks.py:478-480): with fuse_skip_grad the skip connection leaves through the block's first
+    convolution node, so both gradients of x meet in its backward and are added by its padding adjoint
+    (dsr_pad2d_bwd_pitch_add) - or by one add inside the node where that route does not apply - instead of autograd's own
+    accumulation.  Same sums, same order of the two terms: gradients agree to the noise of the statistics' atomics."""
+    from dsr_b200 import networks as nw
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", passes=3, dtype="f16", wgrad_passes=3, big_hw=0, fuse_bwd_prep=False)
+        torch.manual_seed(29)
+        norm = nw.get_norm_layer("instance")
+        mods = [nw.Conv2d(16, 64, 3, stride=2, padding=1), norm(64), nw.ReLU(True)] + \
+               [nw.ResnetBlock(64, padding, norm, False, True) for _ in range(3)] + [nw.Conv2d(64, 16, 3, padding=1)]
+        net = nw.FusedSequential(*mods).cuda()
+        x = torch.randn(2, 16, 40, 48, generator=G(301))
+        res = []
+        for fuse in (True, False):
+            ops.CONFIG.update(fuse_skip_grad=fuse)
+            ops.zero_pool_reset("cuda")
+            for p_ in net.parameters():
+                p_.grad = None
+            xc = cl(x).requires_grad_(True)
+            with _CallLog() as names:
+                y = net(xc)
+                (y * y).sum().backward()
+            res.append((y.detach().cpu(), xc.grad.cpu(), [p_.grad.cpu().clone() for p_ in net.parameters()],
+                        names.count("dsr_pad2d_bwd_pitch_add")))
+        assert res[0][3] == (3 if padding == "reflect" else 0) and res[1][3] == 0
+        assert rel_l2(res[0][0], res[1][0]) <= 1e-6
+        assert rel_l2(res[0][1], res[1][1]) <= 1e-3
+        for ga, gb in zip(res[0][2], res[1][2]):
+            if gb.dim() == 4:
+                assert rel_l2(ga, gb) <= 1e-3
+        # forward under no_grad takes the plain route (no alias output)
+        with torch.no_grad():
+            assert rel_l2(net(cl(x)).cpu(), res[0][0]) <= 1e-6
+    finally:
+        ops.CONFIG.update(old)
+
+
+@pytest.mark.parametrize("C,H,W,pad,mode,act_in,tanh", [(64, 70, 37, 3, "replicate", 0, True), (64, 128, 128, 3, "reflect", 1, False),
+                                                        (20, 64, 16, 3, "zeros", 0, False), (6, 97, 50, 0, "zeros", 2, True),
+                                                        (32, 256, 40, 3, "zeros", 0, False)])
+def test_conv_out1_register_blocked_kernel(ops, C, H, W, pad, mode, act_in, tanh):
+    """conv_out1_s1_rb_kernel (four output rows per thread, activations of a kernel column held in registers): the 7x7 -> 1
+    channel heads (translation_network.py:495, G_A_d's Conv2d(64, 1, 7) + Tanh behind a replicate pad) at sizes that leave
+    partial tiles in both directions, every padding mode, with the fused norm-apply / activation prologue, against a CPU fp64
+    convolution and against the one-pixel-per-thread kernel (DSR_OUT1_RB=0)."""
+    import os
+    N = 2
+    x = torch.randn(N, C, H, W, generator=G(311)) * 1.5 + 0.2
+    w = torch.randn(1, C, 7, 7, generator=G(312)) * 0.05
+    b = torch.randn(1, generator=G(313))
+    old = dict(ops.CONFIG)
+    try:
+        ops.CONFIG.update(engine="tc", out1=True)
+        xin = x.double()
+        prm, act, slope = None, ops.ACT_NONE, 0.0
+        xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+        if act_in:
+            mean, var = xin.mean(dim=(2, 3), keepdim=True), xin.var(dim=(2, 3), unbiased=False, keepdim=True)
+            rstd = (var + 1e-5).rsqrt()
+            xin = (xin - mean) * rstd
+            xin = F.relu(xin) if act_in == 1 else F.leaky_relu(xin, 0.2)
+            act, slope = (ops.ACT_RELU, 0.0) if act_in == 1 else (ops.ACT_LRELU, 0.2)
+            prm = torch.stack([mean.view(N, C), rstd.view(N, C), torch.zeros(N, C, dtype=torch.float64)]).float().contiguous().view(-1).cuda()
+        pm = {"zeros": "constant"}.get(mode, mode)
+        ref = F.conv2d(F.pad(xin, (pad,) * 4, mode=pm), w.double(), b.double())
+        if tanh:
+            ref = torch.tanh(ref)
+        Ho, Wo = H + 2 * pad - 6, W + 2 * pad - 6
+        outs = []
+        for rb in ("1", "0"):
+            os.environ["DSR_OUT1_RB"] = rb
+            y = torch.full((N, Ho, Wo, 1), float("nan"), device="cuda")
+            ops._call("dsr_conv_out1", ops._p(xh), N, H, W, C, ops._p(prm), act, slope, ops._p(w[0].contiguous().cuda()), ops._p(b.cuda()),
+                      7, 7, pad, ops.PAD_MODES[mode], 0, ops.ACT_TANH if tanh else ops.ACT_NONE, ops._p(y))
+            torch.cuda.synchronize()
+            outs.append(y.cpu().view(N, 1, Ho, Wo))
+        assert rel_l2(outs[0].double(), ref) <= 2e-6
+        assert rel_l2(outs[0], outs[1]) <= 2e-6
+    finally:
+        os.environ.pop("DSR_OUT1_RB", None)
+        ops.CONFIG.update(old)
+
+
+@pytest.mark.parametrize("C,H,W,act_in,tanh", [(128, 40, 23, 1, True), (20, 33, 16, 0, False), (6, 64, 50, 2, True), (128, 128, 128, 1, True)])
+def test_conv_transpose_out1_register_blocked_kernel(ops, C, H, W, act_in, tanh):
+    """convT4_out1_rb_kernel (four input rows = 16 outputs per thread): the U-Net heads ConvTranspose2d(128, 1, 4, 2, 1) + Tanh
+    behind ReLU (networks.py:553-555) at sizes with partial tiles, against a CPU fp64 transposed convolution and against the
+    one-position-per-thread kernel (DSR_OUT1_RB=0)."""
+    import os
+    N = 2
+    x = torch.randn(N, C, H, W, generator=G(321)) * 1.5 + 0.2
+    w = torch.randn(C, 1, 4, 4, generator=G(322)) * 0.05
+    b = torch.randn(1, generator=G(323))
+    xin = x.double()
+    prm, act, slope = None, ops.ACT_NONE, 0.0
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    if act_in:
+        mean, var = xin.mean(dim=(2, 3), keepdim=True), xin.var(dim=(2, 3), unbiased=False, keepdim=True)
+        rstd = (var + 1e-5).rsqrt()
+        xin = (xin - mean) * rstd
+        xin = F.relu(xin) if act_in == 1 else F.leaky_relu(xin, 0.2)
+        act, slope = (ops.ACT_RELU, 0.0) if act_in == 1 else (ops.ACT_LRELU, 0.2)
+        prm = torch.stack([mean.view(N, C), rstd.view(N, C), torch.zeros(N, C, dtype=torch.float64)]).float().contiguous().view(-1).cuda()
+    ref = F.conv_transpose2d(xin, w.double(), b.double(), stride=2, padding=1)
+    if tanh:
+        ref = torch.tanh(ref)
+    outs = []
+    try:
+        for rb in ("1", "0"):
+            os.environ["DSR_OUT1_RB"] = rb
+            y = torch.full((N, 2 * H, 2 * W, 1), float("nan"), device="cuda")
+            ops._call("dsr_conv_out1", ops._p(xh), N, H, W, C, ops._p(prm), act, slope, ops._p(w[:, 0].contiguous().cuda()), ops._p(b.cuda()),
+                      4, 4, 1, ops.PAD_ZERO, 1, ops.ACT_TANH if tanh else ops.ACT_NONE, ops._p(y))
+            torch.cuda.synchronize()
+            outs.append(y.cpu().view(N, 1, 2 * H, 2 * W))
+        assert rel_l2(outs[0].double(), ref) <= 2e-6
+        assert rel_l2(outs[0], outs[1]) <= 2e-6
+    finally:
+        os.environ.pop("DSR_OUT1_RB", None)
+
+
 def test_folded_norm_finalize_through_the_layers(ops):
     """the same comparison through the layer stack (prologue route and stand-alone InstanceNorm), forward and backward; the
     statistics come from fp64 atomics in the GEMM epilogues here (run-to-run differences in the last bits, amplified by the
