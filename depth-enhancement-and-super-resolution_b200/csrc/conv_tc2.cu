@@ -71,7 +71,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     constexpr int NA = NPASS >= 2 ? 2 : 1;
     constexpr int NW = NPASS >= 3 ? 2 : 1;
     constexpr uint32_t W_TILE = BLOCK_N * 128;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    // NPASS == 4 ("wide"): the three products of the parity mode in TWO MMAs per K step.  With the A operand in shared memory
+    // an M = 128 MMA costs ~64 cycles whatever N <= 128 is (4 KB of A rows at 64 B/clk: wait counters r4a - the issuer is busy
+    // 62..69 cycles per MMA at N = 32 and N = 64 alike), so A_hi x [W_hi | W_lo] runs as ONE MMA of N = 2 * BLOCK_N (the W_lo
+    // tile follows the W_hi tile in the stage: one K-major descriptor covers both) into 2 * BLOCK_N accumulator columns, A_lo x
+    // W_hi adds into the first BLOCK_N, and the epilogue adds the two halves: 8 MMAs per stage instead of 12.
+    constexpr bool WIDE = NPASS == 4;
+    constexpr int ACC = WIDE ? 2 * BLOCK_N : BLOCK_N;            // accumulator columns per buffer
+    constexpr uint32_t TMEM_COLS = 2 * ACC < 32 ? 32 : 2 * ACC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t patch_set = NA * p.patch_plane_bytes;
@@ -171,6 +178,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         // ===== MMA issuer: the whole warp runs the (warp-uniform) loop and the waits; one elected lane issues =====
         {
             const uint32_t idesc = make_idesc(128, BLOCK_N < 16 ? 16 : BLOCK_N, p.f16 ? 0u : 1u);
+            const uint32_t idesc_w = make_idesc(128, 2 * BLOCK_N, p.f16 ? 0u : 1u);
             // A descriptor template: SWIZZLE_128B rows of 128 B (stride between the 8-pixel row groups = patch pitch), or
             // for the compact first-layer operand no swizzle, 16-byte rows, LBO = 16 B, SBO = patch pitch
             const uint64_t pdesc0 = p.a_mode
@@ -190,7 +198,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 const int ab = ti & 1;
                 TC2_TIMED_WAIT(2, ae(ab), ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC);
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     TC2_TIMED_WAIT(0, pf(pb), pph);
                     const uint32_t patch_hi = smem_base + pb * patch_set;
@@ -205,16 +213,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                             const uint64_t pd_lo = pd_hi + (uint64_t)(p.patch_plane_bytes >> 4);
                             const uint64_t wd_lo = wd_hi + (uint64_t)(W_TILE >> 4);
                             const uint32_t first = (cb | t) ? 1u : 0u;          // 0 only for the first MMA of the tile
+                            if (WIDE) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_hi + 2 * kk, idesc, kk ? 1u : first);
-                            if (NPASS >= 2) {
+                                for (int kk = 0; kk < 4; ++kk)              // A_hi x [W_hi | W_lo]: columns [0, 2 BLOCK_N)
+                                    tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_hi + 2 * kk, idesc_w, kk ? 1u : first);
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d_tmem, pd_lo + 2 * kk, wd_hi + 2 * kk, idesc, 1u);
-                            }
-                            if (NPASS >= 3) {
+                            } else {
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_lo + 2 * kk, idesc, 1u);
+                                for (int kk = 0; kk < 4; ++kk)
+                                    tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_hi + 2 * kk, idesc, kk ? 1u : first);
+                                if (NPASS >= 2) {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d_tmem, pd_lo + 2 * kk, wd_hi + 2 * kk, idesc, 1u);
+                                }
+                                if (NPASS >= 3) {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d_tmem, pd_hi + 2 * kk, wd_lo + 2 * kk, idesc, 1u);
+                                }
                             }
                             tc_commit(empty);
                             if (t == p.T - 1) {
@@ -275,9 +291,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BLOCK_N + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * ACC + c0);
+                uint32_t v2[WIDE ? 32 : 1];
                 if (CH == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+                if (WIDE) { if (CH == 32) tc_ld32(taddr + BLOCK_N, v2); else tc_ld16(taddr + BLOCK_N, v2); }
                 tc_wait_ld();
+                if (WIDE) {                                 // + the A_hi x W_lo half of the accumulator
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                }
                 float f[32];
                 const int nch = p.Cout - co0 - c0;              // channels of this chunk inside the tensor (may exceed CH)
 #pragma unroll
@@ -379,8 +401,8 @@ static int dispatch_tc2(int bn, const CUtensorMap& ah, const CUtensorMap& al, co
         case 16: return launch_tc2<16, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
         case 32: return launch_tc2<32, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
         case 64: return launch_tc2<64, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
-        case 128: return launch_tc2<128, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
-        case 256: return launch_tc2<256, NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+        case 128: return launch_tc2<128, NPASS == 4 ? 3 : NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
+        case 256: return launch_tc2<256, NPASS == 4 ? 3 : NPASS>(ah, al, wh, wl, p, bias, out, stats, grid, smem, st);
     }
     dsr_set_error("conv_tc2: unsupported BLOCK_N %d", bn);
     return DSR_ERR_UNSUPPORTED;
@@ -471,5 +493,7 @@ extern "C" int dsr_tc_gemm2(const void* A_hi, const void* A_lo, int N, int Ha, i
     int grid = p.total_tiles < dsr_num_sms() ? p.total_tiles : dsr_num_sms();
     if (npass == 1) return dispatch_tc2<1>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
     if (npass == 2) return dispatch_tc2<2>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
+    if (bn <= 64 && tc2_env("DSR_TC2_WIDE", 1))      // three products in two MMAs per K step (see conv_tc2_kernel)
+        return dispatch_tc2<4>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
     return dispatch_tc2<3>(bn, mah, mal, mwh, mwl, p, bias, out, stats, grid, smem, ST(stream));
 }

@@ -952,10 +952,11 @@ def test_conv_out1_register_blocked_kernel(ops, C, H, W, pad, mode, act_in, tanh
             ref = torch.tanh(ref)
         Ho, Wo = H + 2 * pad - 6, W + 2 * pad - 6
         outs = []
+        wd, bd = w[0].contiguous().cuda(), b.cuda()                # (kept alive: _p hands out raw pointers)
         for rb in ("1", "0"):
             os.environ["DSR_OUT1_RB"] = rb
             y = torch.full((N, Ho, Wo, 1), float("nan"), device="cuda")
-            ops._call("dsr_conv_out1", ops._p(xh), N, H, W, C, ops._p(prm), act, slope, ops._p(w[0].contiguous().cuda()), ops._p(b.cuda()),
+            ops._call("dsr_conv_out1", ops._p(xh), N, H, W, C, ops._p(prm), act, slope, ops._p(wd), ops._p(bd),
                       7, 7, pad, ops.PAD_MODES[mode], 0, ops.ACT_TANH if tanh else ops.ACT_NONE, ops._p(y))
             torch.cuda.synchronize()
             outs.append(y.cpu().view(N, 1, Ho, Wo))
@@ -990,11 +991,12 @@ def test_conv_transpose_out1_register_blocked_kernel(ops, C, H, W, act_in, tanh)
     if tanh:
         ref = torch.tanh(ref)
     outs = []
+    wd, bd = w[:, 0].contiguous().cuda(), b.cuda()                 # (kept alive: _p hands out raw pointers)
     try:
         for rb in ("1", "0"):
             os.environ["DSR_OUT1_RB"] = rb
             y = torch.full((N, 2 * H, 2 * W, 1), float("nan"), device="cuda")
-            ops._call("dsr_conv_out1", ops._p(xh), N, H, W, C, ops._p(prm), act, slope, ops._p(w[:, 0].contiguous().cuda()), ops._p(b.cuda()),
+            ops._call("dsr_conv_out1", ops._p(xh), N, H, W, C, ops._p(prm), act, slope, ops._p(wd), ops._p(bd),
                       4, 4, 1, ops.PAD_ZERO, 1, ops.ACT_TANH if tanh else ops.ACT_NONE, ops._p(y))
             torch.cuda.synchronize()
             outs.append(y.cpu().view(N, 1, 2 * H, 2 * W))
