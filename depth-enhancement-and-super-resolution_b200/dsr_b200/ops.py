@@ -295,6 +295,7 @@ CONFIG = {
                          #   gate margin is set by the dY that reaches the layer, not by the operand rounding.  Layers below
                          #   32^2 (latency-bound, no time to win) keep `passes`
     "frozen_passes": 0,  # forward GEMMs of the frozen nets (run under no_grad): 0 = as fwd_passes / passes
+    "prepack_in_use_order": True,   # ... in the order the step first uses them (not in the arena's gradient-ready order)
     "prepack": True,     # packed 16-bit copies of the trainable weights are re-made on the side stream at the top of the step
     "fwd_bf16_copy": True,   # forward operand prep of trainable layers also writes the bf16 copy the weight gradient reads
     "fused_cat": True,   # Conv2d over a LazyCat: the operand preparation reads the parts (no materialised concatenation)
@@ -429,12 +430,19 @@ def tc_conv_plan(kind, Ci, Co, R, S, stride, pad, opad, H, W, min_ci=16):
     return None
 
 
+_PACK_SEQ = [0]
+
+
 def _remember_pack(weight, key, recipe):
     """the packed copies a parameter needs per step, so that `prepack` can make all of them ahead of time on the side stream"""
     if weight.data_ptr() in DIRECT_GRADS:
         try:
             rec = weight.__dict__.setdefault("_dsr_recipes", {})
             rec[key] = recipe
+            seq = weight.__dict__.setdefault("_dsr_recipe_seq", {})
+            if key not in seq:                       # position of the copy's FIRST use in the step (forward layers first, in
+                _PACK_SEQ[0] += 1                    # forward order, then the data-gradient variants in backward order)
+                seq[key] = _PACK_SEQ[0]
         except AttributeError:
             pass
 
@@ -446,9 +454,15 @@ def prepack(params):
     (`_tc_weights` -> `_prepack_join`)."""
     if not CONFIG["prepack"]:
         return
-    todo = [(p, r) for p in params for r in getattr(p, "_dsr_recipes", {}).values()]
+    todo = [(p, r, getattr(p, "_dsr_recipe_seq", {}).get(k, 0)) for p in params for k, r in getattr(p, "_dsr_recipes", {}).items()]
     if not todo:
         return
+    if CONFIG["prepack_in_use_order"]:
+        # the arena lists the parameters in gradient-ready order - the REVERSE of the forward pass: packed in that order, the
+        # copy the first trainable layer waits for was the last of ~60 launches (0.8 ms of serial small kernels at the head of
+        # the training graph, timeline r3e).  In order of first use the forward pass follows right behind the packing chain.
+        todo.sort(key=lambda t: t[2])
+    todo = [(p, r) for p, r, _ in todo]
     with _on_side(True, todo[0][0].device):
         side = torch.cuda.current_stream()
         for w, (kind, plan, Co, phase, pad, dtype, npass) in todo:
