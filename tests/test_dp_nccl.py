@@ -55,7 +55,7 @@ def _worker(rank, world, port, out_dir):
         model.set_input(batches[rank])
         model.optimize_parameters(it, 1)
         losses.append(float(model.loss_G))
-    chk["graph_captured"] = model._graph is not None
+    chk["graph_captured"] = model._graph is not None or getattr(model, "_pipe", None) is not None    # single graph / pipelined slots
     chk["weights_max_diff_after_steps"] = parallel.weights_in_sync(model)
     chk["finite"] = bool(np.all(np.isfinite(losses)))
     torch.save(chk, os.path.join(out_dir, f"r{rank}.pt"))
