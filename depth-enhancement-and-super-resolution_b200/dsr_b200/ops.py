@@ -285,7 +285,9 @@ CONFIG = {
     "out1": True,        # one-output-channel heads on CUDA cores (bandwidth-bound reductions) instead of N = 16 MMAs
     "tc_first_layers": True,
     "tc_compact_first": True,   # ... reading the 8-pixel K blocks from a compact 8-channel operand (no 8x expansion)   # 7x7 first layers (1..8 input channels) on the tensor path (8-pixel K blocks)
-    "halo_min_tiles": 120,
+    "halo_min_tiles": 90,    # fewest output tiles for the persistent halo kernels (below: first generation with split-K).  Was 120;
+                             # measured r4j: the six 96-tile U-Net layers (64 -> 128 at 6 x 64^2, 128 -> 256 at 12 x 32^2, 256 -> 512 at
+                             # 12 x 16^2) run 0.354 -> 0.235 ms on the channel-major kernel although a third of the SMs idle
     "fwd_passes": 0,     # forward GEMMs of the trainable nets: 0 = `passes`, 2 = activations hi+lo x weights hi only
     "big_hw": 1024,      # layers with >= this many output pixels per sample may run fewer MMA passes (0 = off):
     "big_fwd_passes": 0, #   forward GEMMs (0 = no override).  Measured on the golden step (scripts/precision_probe.py, r74):
