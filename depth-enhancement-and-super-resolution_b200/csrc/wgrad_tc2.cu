@@ -16,6 +16,7 @@
 // Both operands are MN-major (the pixel dimension is the MMA K dimension): SWIZZLE_128B boxes of [pixels][64 channels],
 // descriptor SBO = 1024 B (next 8 pixels), LBO = one box (next 64 channels or next column block).
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 #define WG2_MAX_TAPS 64
@@ -214,7 +215,11 @@ static void wg2_plan(int N, int Hb, int Wb, int Cm_real, int Ca, int T, int spli
     if (split_k < 0) {
         // one wave of CTAs over the SMs (1 CTA / SM: 160 KB of stages, all 512 TMEM columns), at least 8 K tiles per split
         splits = (int)(dsr_num_sms() / ctas);
-        if (splits > p.tiles_total / 8) splits = p.tiles_total / 8;
+        // at least 32 K tiles per split (DSR_WG2_MIN_TILES for A/B; was 8): every split ends with 128 x per x 64 fp32 vector
+        // reductions, and a 128-channel 3x3 layer at 12 x 64^2 cut 48 ways put 29 MB of them on a 590 KB matrix.  Measured
+        // (r4o / r4p, same box): step 13.98 ms at 8, 13.92 at 16, 13.88 at 32, 13.8-13.9 at 64, 14.08 at 128.
+        static const int min_tiles = getenv("DSR_WG2_MIN_TILES") ? atoi(getenv("DSR_WG2_MIN_TILES")) : 32;
+        if (splits > p.tiles_total / min_tiles) splits = p.tiles_total / min_tiles;
         if (splits < 1) splits = 1;
     } else if (split_k > 1) splits = split_k;
     p.tiles_per_split = dsr_cdiv(p.tiles_total, splits);
